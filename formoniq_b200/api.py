@@ -1,0 +1,434 @@
+"""Host-side mirror of the reference interfaces for the assembly path, on top
+of the C ABI.  Names, argument meaning and error behaviour follow the
+reference (paths relative to the reference checkout):
+
+  WhitneyPairing / ScalarLumpedMass   formoniq/src/operators.rs:27-40,150-211
+  BilinearForm.assemble               formoniq/src/galerkin.rs:42-58,138-188
+  HodgeBlocks.compute                 formoniq/src/hodge.rs:62-72
+  DeviceVector (InnerProductSpace)    iterative/src/lib.rs:84-141
+  DeviceCsr (LinearOperator)          iterative/src/operator.rs:5-14
+  cg / minres / StopCriterion / Report   iterative/src/krylov.rs:48-211, lib.rs:186-219
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from math import comb
+
+import numpy as np
+
+from . import _lib
+from ._lib import FQ_DIF_BOTH, FQ_DIF_TEST, FQ_DIF_TRIAL, FQ_LUMPED, FQ_MASS, FormoniqError, check
+
+SIZE_MAX = (1 << 64) - 1
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def nlocal(dim: int, grade: int) -> int:
+    return 0 if grade < 0 or grade > dim else comb(dim + 1, grade + 1)
+
+
+class Context:
+    """One CUDA device + stream (fq_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        check(_lib.lib().fq_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, cuda_stream: int):
+        check(_lib.lib().fq_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(_lib.lib().fq_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return _lib.lib().fq_ctx_launch_count(self._h)
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_ctx_destroy(self._h)
+        except Exception:
+            pass
+
+
+class Mesh:
+    """`Complex` + `MeshLengthsSq` as assembly consumes them: per-grade
+    FaceIncidence tables and one signed squared length per edge."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, handle
+        L = _lib.lib()
+        self.dim = L.fq_mesh_dim(handle)
+        self.ncells = L.fq_mesh_ncells(handle)
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, dim: int, nsimplices, cell_faces, edge_lengths_sq) -> "Mesh":
+        """cell_faces: sequence indexed by grade of [ncells, C(dim+1, j+1)] integer arrays (None to skip)."""
+        ns = np.ascontiguousarray(nsimplices, dtype=np.uint64)
+        faces = [None if f is None else np.ascontiguousarray(f, dtype=np.uint64) for f in cell_faces]
+        ptrs = (C.c_void_p * (dim + 1))(*[None if f is None else f.ctypes.data for f in faces])
+        lengths = np.ascontiguousarray(edge_lengths_sq, dtype=np.float64)
+        if lengths.shape[0] != int(ns[1]):
+            raise FormoniqError(-1, "one squared length per edge is required")
+        h = C.c_void_p()
+        check(_lib.lib().fq_mesh_create(ctx._h, dim, int(ns[dim]), _p(ns), C.cast(ptrs, C.c_void_p), _p(lengths), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def kuhn(cls, ctx: Context, dim: int, shape, vmin=None, vmax=None, ambient_diag=None, jitter: float = 0.0,
+             slab=None) -> "Mesh":
+        """CartesianGrid::triangulate + to_edge_lengths_sq generated on the device."""
+        if np.isscalar(shape):
+            shape = [int(shape)] * dim
+        shp = np.ascontiguousarray(shape, dtype=np.uint64)
+        vmin = None if vmin is None else np.ascontiguousarray(vmin, dtype=np.float64)
+        vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
+        diag = None if ambient_diag is None else np.ascontiguousarray(ambient_diag, dtype=np.float64)
+        sb, se = (0, int(shp[dim - 1])) if slab is None else slab
+        h = C.c_void_p()
+        check(_lib.lib().fq_mesh_create_kuhn(ctx._h, dim, _p(shp), _p(vmin), _p(vmax), _p(diag), float(jitter), sb, se,
+                                             C.byref(h)))
+        m = cls(ctx, h)
+        m.shape = [int(s) for s in shp]
+        return m
+
+    def nsimplices(self, grade: int) -> int:
+        return _lib.lib().fq_mesh_nsimplices(self._h, grade)
+
+    def set_lengths(self, edge_lengths_sq):
+        a = np.ascontiguousarray(edge_lengths_sq, dtype=np.float64)
+        if a.shape[0] != self.nsimplices(1):
+            raise FormoniqError(-1, "one squared length per edge is required")
+        check(_lib.lib().fq_mesh_set_lengths(self.ctx._h, self._h, _p(a)))
+
+    def cell_faces(self, grade: int) -> np.ndarray:
+        out = np.zeros((self.ncells, nlocal(self.dim, grade)), dtype=np.uint64)
+        check(_lib.lib().fq_mesh_download_cell_faces(self.ctx._h, self._h, grade, _p(out)))
+        return out
+
+    def lengths(self) -> np.ndarray:
+        out = np.full(self.nsimplices(1), np.nan)
+        check(_lib.lib().fq_mesh_download_lengths(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_mesh_destroy(self._h)
+        except Exception:
+            pass
+
+
+def kuhn_counts(dim: int, shape) -> list[int]:
+    if np.isscalar(shape):
+        shape = [int(shape)] * dim
+    shp = np.ascontiguousarray(shape, dtype=np.uint64)
+    out = np.zeros(dim + 1, dtype=np.uint64)
+    check(_lib.lib().fq_kuhn_counts(dim, _p(shp), _p(out)))
+    return [int(v) for v in out]
+
+
+def kuhn_cell_faces_host(dim: int, shape, grade: int) -> np.ndarray:
+    """Closed-form colex numbering of the Kuhn grid, evaluated on the host."""
+    if np.isscalar(shape):
+        shape = [int(shape)] * dim
+    shp = np.ascontiguousarray(shape, dtype=np.uint64)
+    ncells = kuhn_counts(dim, shape)[dim]
+    out = np.zeros((ncells, nlocal(dim, grade)), dtype=np.uint64)
+    check(_lib.lib().fq_kuhn_cell_faces_host(dim, _p(shp), grade, _p(out)))
+    return out
+
+
+@dataclass
+class StopCriterion:
+    rtol: float
+    max_iters: int = 10_000
+
+
+@dataclass
+class Report:
+    iters: int
+    residual: float
+    converged: bool
+
+
+class DeviceVector:
+    """A vector in HBM implementing iterative::InnerProductSpace."""
+
+    def __init__(self, ctx: Context, n: int):
+        h = C.c_void_p()
+        check(_lib.lib().fq_vec_create(ctx._h, n, C.byref(h)))
+        self.ctx, self._h, self.n = ctx, h, n
+
+    @classmethod
+    def from_numpy(cls, ctx: Context, a) -> "DeviceVector":
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        v = cls(ctx, a.shape[0])
+        check(_lib.lib().fq_vec_upload(ctx._h, v._h, _p(a)))
+        return v
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape[0] != self.n:
+            raise FormoniqError(-1, "vector length mismatch")
+        check(_lib.lib().fq_vec_upload(self.ctx._h, self._h, _p(a)))
+
+    def to_numpy(self) -> np.ndarray:
+        out = np.zeros(self.n)
+        check(_lib.lib().fq_vec_download(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def __len__(self):
+        return self.n
+
+    def zeros_like(self) -> "DeviceVector":
+        return DeviceVector(self.ctx, self.n)
+
+    def clone(self) -> "DeviceVector":
+        v = DeviceVector(self.ctx, self.n)
+        check(_lib.lib().fq_vec_copy(self.ctx._h, v._h, self._h))
+        return v
+
+    def dot(self, other: "DeviceVector") -> float:
+        out = C.c_double()
+        check(_lib.lib().fq_vec_dot(self.ctx._h, self._h, other._h, C.byref(out)))
+        return out.value
+
+    def scale(self, alpha: float):
+        check(_lib.lib().fq_vec_scale(self.ctx._h, self._h, float(alpha)))
+
+    def add_scaled(self, alpha: float, x: "DeviceVector"):
+        check(_lib.lib().fq_vec_axpy(self.ctx._h, self._h, float(alpha), x._h))
+
+    def add(self, x: "DeviceVector"):
+        self.add_scaled(1.0, x)
+
+    def norm(self) -> float:
+        return float(np.sqrt(self.dot(self)))
+
+    @property
+    def device_ptr(self) -> int:
+        return _lib.lib().fq_vec_device_ptr(self._h)
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_vec_destroy(self._h)
+        except Exception:
+            pass
+
+
+class DeviceCsr:
+    """GalerkinMatrix in HBM: nalgebra-sparse CSR contract + LinearOperator::apply."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, handle
+
+    @property
+    def shape(self):
+        nr, nc, nnz = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(_lib.lib().fq_csr_shape(self._h, C.byref(nr), C.byref(nc), C.byref(nnz)))
+        return nr.value, nc.value
+
+    @property
+    def nnz(self) -> int:
+        nnz = C.c_size_t()
+        check(_lib.lib().fq_csr_shape(self._h, None, None, C.byref(nnz)))
+        return nnz.value
+
+    @property
+    def row_range(self):
+        b, e = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().fq_csr_row_range(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def dim(self) -> int:
+        return self.shape[0]
+
+    @classmethod
+    def upload(cls, ctx: Context, nrows, ncols, row_offsets, col_indices, values) -> "DeviceCsr":
+        rp = np.ascontiguousarray(row_offsets, dtype=np.uint64)
+        ci = np.ascontiguousarray(col_indices, dtype=np.uint64)
+        va = np.ascontiguousarray(values, dtype=np.float64)
+        h = C.c_void_p()
+        check(_lib.lib().fq_csr_upload(ctx._h, nrows, ncols, _p(rp), _p(ci), _p(va), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_scipy(cls, ctx: Context, m) -> "DeviceCsr":
+        m = m.tocsr()
+        m.sort_indices()
+        return cls.upload(ctx, m.shape[0], m.shape[1], m.indptr, m.indices, m.data)
+
+    def download(self):
+        """(row_offsets, col_indices, values) as usize/usize/f64 host arrays."""
+        b, e = self.row_range
+        nnz = self.nnz
+        rp = np.zeros(e - b + 1, dtype=np.uint64)
+        ci = np.zeros(nnz, dtype=np.uint64)
+        va = np.zeros(nnz)
+        check(_lib.lib().fq_csr_download(self.ctx._h, self._h, _p(rp), _p(ci), _p(va)))
+        return rp, ci, va
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        rp, ci, va = self.download()
+        b, e = self.row_range
+        return sp.csr_matrix((va, ci.astype(np.int64), rp.astype(np.int64)), shape=(e - b, self.shape[1]))
+
+    def numeric(self, mesh: Mesh, drop_exact_zeros: bool = True):
+        """Re-run the numeric phase (new geometry, same topology)."""
+        check(_lib.lib().fq_assemble_numeric(self.ctx._h, mesh._h, self._h, int(drop_exact_zeros)))
+
+    def apply(self, x: DeviceVector, out: DeviceVector | None = None) -> DeviceVector:
+        b, e = self.row_range
+        y = out if out is not None else DeviceVector(self.ctx, e - b)
+        check(_lib.lib().fq_spmv(self.ctx._h, self._h, x._h, y._h))
+        return y
+
+    @property
+    def assembly_bytes(self) -> int:
+        return _lib.lib().fq_csr_assembly_bytes(self._h)
+
+    @property
+    def spmv_bytes(self) -> int:
+        return _lib.lib().fq_csr_spmv_bytes(self._h)
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_csr_destroy(self._h)
+        except Exception:
+            pass
+
+
+class BilinearForm:
+    """The reference trait: grades, element matrices, assembly."""
+
+    kind: int
+    dim: int
+    grade: int
+
+    def test_grade(self) -> int:
+        return self.grade - (self.kind in (FQ_DIF_TEST, FQ_DIF_BOTH))
+
+    def trial_grade(self) -> int:
+        return self.grade - (self.kind in (FQ_DIF_TRIAL, FQ_DIF_BOTH))
+
+    def element_shape(self):
+        return nlocal(self.dim, self.test_grade()), nlocal(self.dim, self.trial_grade())
+
+    def element_batch(self, mesh: Mesh, cell_begin: int = 0, cell_end: int | None = None, use_generated: bool = True):
+        """BilinearForm::element for cells [cell_begin, cell_end) -> [ncells, rows, cols]."""
+        if mesh.dim != self.dim:
+            raise FormoniqError(-1, "form and mesh dimensions differ")  # assert_eq!(self.dim, metric.dim())
+        cell_end = mesh.ncells if cell_end is None else cell_end
+        r, c = self.element_shape()
+        out = np.zeros((cell_end - cell_begin, r, c))
+        check(_lib.lib().fq_elmat_batch(mesh.ctx._h, mesh._h, self.kind, self.grade, cell_begin, cell_end,
+                                        int(use_generated), _p(out)))
+        return out
+
+    def symbolic(self, mesh: Mesh, row_begin: int = 0, row_end: int = SIZE_MAX) -> DeviceCsr:
+        h = C.c_void_p()
+        check(_lib.lib().fq_assemble_symbolic(mesh.ctx._h, mesh._h, self.kind, self.grade, row_begin, row_end, C.byref(h)))
+        return DeviceCsr(mesh.ctx, h)
+
+    def assemble(self, mesh: Mesh, drop_exact_zeros: bool = True) -> DeviceCsr:
+        """BilinearForm::assemble -> GalerkinMatrix (reference `!= 0.0` filter by default)."""
+        if mesh.dim != self.dim:
+            raise FormoniqError(-1, "form and mesh dimensions differ")
+        h = C.c_void_p()
+        check(_lib.lib().fq_assemble(mesh.ctx._h, mesh._h, self.kind, self.grade, int(drop_exact_zeros), C.byref(h)))
+        return DeviceCsr(mesh.ctx, h)
+
+
+class WhitneyPairing(BilinearForm):
+    def __init__(self, dim: int, grade: int, kind: int):
+        self.dim, self.grade, self.kind = int(dim), int(grade), kind
+
+    @classmethod
+    def mass(cls, dim, grade):
+        return cls(dim, grade, FQ_MASS)
+
+    @classmethod
+    def dif_trial(cls, dim, grade):
+        return cls(dim, grade, FQ_DIF_TRIAL)
+
+    @classmethod
+    def dif_test(cls, dim, grade):
+        return cls(dim, grade, FQ_DIF_TEST)
+
+    @classmethod
+    def dif_both(cls, dim, grade):
+        return cls(dim, grade, FQ_DIF_BOTH)
+
+
+class ScalarLumpedMass(BilinearForm):
+    def __init__(self, dim: int):
+        self.dim, self.grade, self.kind = int(dim), 0, FQ_LUMPED
+
+    def test_grade(self):
+        return 0
+
+    def trial_grade(self):
+        return 0
+
+
+@dataclass
+class HodgeBlocks:
+    """The four matrices of a mixed problem posed at `grade` (hodge.rs:62-72)."""
+
+    n_sigma: int
+    n_u: int
+    mass_sigma: DeviceCsr
+    mass_u: DeviceCsr
+    dif_test: DeviceCsr
+    dif_both: DeviceCsr
+
+    @classmethod
+    def compute(cls, mesh: Mesh, grade: int, drop_exact_zeros: bool = True) -> "HodgeBlocks":
+        if grade > mesh.dim:
+            raise FormoniqError(-1, "grade <= complex.dim() is required")
+        d = mesh.dim
+        return cls(
+            n_sigma=mesh.nsimplices(grade - 1),
+            n_u=mesh.nsimplices(grade),
+            mass_sigma=WhitneyPairing.mass(d, grade - 1).assemble(mesh, drop_exact_zeros),
+            mass_u=WhitneyPairing.mass(d, grade).assemble(mesh, drop_exact_zeros),
+            dif_test=WhitneyPairing.dif_test(d, grade).assemble(mesh, drop_exact_zeros),
+            dif_both=WhitneyPairing.dif_both(d, grade + 1).assemble(mesh, drop_exact_zeros),
+        )
+
+    def mixed_hodge_laplacian(self):
+        """[[M_{k-1}, -dif_test], [dif_test^T, dif_both]] stitched on the host (scipy) and uploaded."""
+        import scipy.sparse as sp
+
+        ms, dt, db = self.mass_sigma.to_scipy(), self.dif_test.to_scipy(), self.dif_both.to_scipy()
+        a = sp.bmat([[ms, -dt], [dt.T, db]], format="csr")
+        return DeviceCsr.from_scipy(self.mass_u.ctx, a)
+
+
+def _krylov(fn, op: DeviceCsr, precond, b: DeviceVector, stop: StopCriterion):
+    pc = {None: 0, "identity": 0, "jacobi": 1}[precond]
+    x = b.zeros_like()
+    it, res, conv = C.c_size_t(), C.c_double(), C.c_int()
+    check(fn(op.ctx._h, op._h, pc, b._h, float(stop.rtol), int(stop.max_iters), x._h, C.byref(it), C.byref(res),
+             C.byref(conv)))
+    return x, Report(it.value, res.value, bool(conv.value))
+
+
+def cg(op: DeviceCsr, precond, b: DeviceVector, stop: StopCriterion):
+    """iterative::krylov::cg on device vectors; precond in {None, "jacobi"}."""
+    return _krylov(_lib.lib().fq_cg, op, precond, b, stop)
+
+
+def minres(op: DeviceCsr, precond, b: DeviceVector, stop: StopCriterion):
+    """iterative::krylov::minres on device vectors; precond in {None, "jacobi"}."""
+    return _krylov(_lib.lib().fq_minres, op, precond, b, stop)

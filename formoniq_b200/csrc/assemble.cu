@@ -1,0 +1,319 @@
+// assemble.cu — K2 (symbolic pattern + cell-slot -> nnz map) and K3 (numeric
+// scatter as a segmented reduction, no atomics).
+//
+// Reference semantics (formoniq/src/galerkin.rs:138-188): triplets are emitted
+// cell by cell (i outer, j inner), entries equal to 0.0 are dropped, and the
+// COO -> CSR conversion sums duplicates.  Here:
+//   symbolic: one key (row, col) per (cell, slot); a stable radix sort groups
+//     the contributions of every structural non-zero in ascending cell order
+//     (so the summation order is deterministic and independent of the
+//     partition); run heads give row_ptr / col_idx and the gather lists.
+//   numeric: the element slab is produced by K1, then one thread per
+//     structural non-zero sums its contributions in order and records whether
+//     any of them was non-zero; with drop_exact_zeros the pattern is
+//     compacted to exactly the reference's value-dependent pattern.
+#include <cub/cub.cuh>
+
+#include "internal.hpp"
+
+namespace fq {
+
+struct IsOwnedKey {
+  __device__ __forceinline__ uint32_t operator()(const uint64_t& k) const { return k != ~0ull ? 1u : 0u; }
+};
+
+static int bits_for(uint64_t n) {  // bits needed to represent values < n
+  int b = 1;
+  while ((1ull << b) < n) ++b;
+  return b;
+}
+
+__global__ void sym_keys_kernel(const uint32_t* __restrict__ faces_t, const uint32_t* __restrict__ faces_r, int nt,
+                                int nr, uint64_t ncontrib, uint32_t row_begin, uint32_t row_end, int col_bits,
+                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  const uint32_t T = uint32_t(nt * nr);
+  for (uint64_t p = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < ncontrib; p += stride) {
+    const uint64_t c = p / T;
+    const uint32_t slot = uint32_t(p % T);
+    const uint32_t i = slot / uint32_t(nr), j = slot % uint32_t(nr);
+    const uint32_t row = faces_t[c * nt + i], col = faces_r[c * nr + j];
+    uint64_t key;
+    if (row < row_begin || row >= row_end)
+      key = ~0ull;  // not owned: sorted to the end and cut off
+    else
+      key = (uint64_t(row - row_begin) << col_bits) | col;
+    keys[p] = key;
+    vals[p] = uint32_t(p);
+  }
+}
+
+__global__ void sym_heads_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ head) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t p = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const uint64_t k = keys[p];
+    head[p] = (k != ~0ull && (p == 0 || keys[p - 1] != k)) ? 1u : 0u;
+  }
+}
+
+// For every run head: record its start (contrib_ptr), its column, and fill
+// row_ptr for the rows that begin at or before it.
+__global__ void sym_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head,
+                                const uint32_t* __restrict__ head_scan, uint64_t n, int col_bits,
+                                uint32_t* __restrict__ contrib_ptr, uint32_t* __restrict__ col_idx,
+                                uint32_t* __restrict__ row_of_nnz) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  const uint64_t col_mask = (1ull << col_bits) - 1;
+  for (uint64_t p = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += stride) {
+    if (!head[p]) continue;
+    const uint32_t q = head_scan[p];
+    const uint64_t k = keys[p];
+    contrib_ptr[q] = uint32_t(p);
+    col_idx[q] = uint32_t(k & col_mask);
+    row_of_nnz[q] = uint32_t(k >> col_bits);
+  }
+}
+
+// row_ptr[r] = first nnz whose row >= r  (rows are sorted)
+__global__ void sym_rowptr_kernel(const uint32_t* __restrict__ row_of_nnz, uint32_t nnz, uint32_t nrows,
+                                  uint32_t* __restrict__ row_ptr) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q <= nnz; q += stride) {
+    const uint32_t r_hi = (q == nnz) ? nrows : row_of_nnz[q];
+    const uint32_t r_lo = (q == 0) ? 0u : row_of_nnz[q - 1] + 1;
+    for (uint32_t r = r_lo; r <= r_hi && r <= nrows; ++r) row_ptr[r] = uint32_t(q);
+  }
+}
+
+void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
+                       fq_csr* out) {
+  const int dim = mesh->dim;
+  int tg, rg;
+  kind_grades(kind, grade, tg, rg);
+  const int nt = nlocal(dim, tg), nr = nlocal(dim, rg);
+  const size_t grows = (tg < 0 || tg > dim) ? 0 : mesh->nsimplices[size_t(tg)];
+  const size_t gcols = (rg < 0 || rg > dim) ? 0 : mesh->nsimplices[size_t(rg)];
+  if (row_end > grows) row_end = grows;
+  if (row_begin > row_end) row_begin = row_end;
+  out->nrows = grows;
+  out->ncols = gcols;
+  out->row_begin = row_begin;
+  out->row_end = row_end;
+  out->kind = kind;
+  out->grade = grade;
+  out->dim = dim;
+  out->el_rows = nt;
+  out->el_cols = nr;
+  out->ncells = mesh->ncells;
+  out->has_plan = true;
+  const size_t nrows_local = row_end - row_begin;
+  const size_t T = size_t(nt) * size_t(nr);
+  const uint64_t ncontrib_all = uint64_t(mesh->ncells) * T;
+  out->s_row_ptr.alloc(nrows_local + 1);
+  if (ncontrib_all == 0 || nrows_local == 0) {
+    // pairing() of an empty space: correctly shaped zero matrix (whitney_complex.rs:113-122)
+    FQ_CUDA(cudaMemsetAsync(out->s_row_ptr.p, 0, (nrows_local + 1) * sizeof(uint32_t), ctx->stream));
+    out->s_nnz = 0;
+    out->ncontrib = 0;
+    out->s_col_idx.alloc(1);
+    out->contrib_ptr.alloc(1);
+    FQ_CUDA(cudaMemsetAsync(out->contrib_ptr.p, 0, sizeof(uint32_t), ctx->stream));
+    out->contrib_src.alloc(1);
+    out->s_values.alloc(1);
+    out->keep.alloc(1);
+    return;
+  }
+  FQ_REQUIRE(mesh->cell_faces[size_t(tg)].p && mesh->cell_faces[size_t(rg)].p,
+             "mesh was created without the face tables of the required grades");
+  FQ_REQUIRE(ncontrib_all < (1ull << 32), "more than 2^32 element entries in one block: not supported");
+  FQ_REQUIRE(gcols < (1ull << 32) && grows < (1ull << 32), "more than 2^32 rows/cols: not supported");
+  const int col_bits = bits_for(gcols);
+  const int row_bits = bits_for(nrows_local + 1);
+  FQ_REQUIRE(col_bits + row_bits <= 63, "key overflow");
+  const int block = 256;
+  DevBuf<uint64_t> keys(ncontrib_all), keys_alt(ncontrib_all);
+  DevBuf<uint32_t> vals(ncontrib_all), vals_alt(ncontrib_all);
+  sym_keys_kernel<<<grid_for(ncontrib_all, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      mesh->cell_faces[size_t(tg)].p, mesh->cell_faces[size_t(rg)].p, nt, nr, ncontrib_all, uint32_t(row_begin),
+      uint32_t(row_end), col_bits, keys.p, vals.p);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  cub::DoubleBuffer<uint64_t> dk(keys.p, keys_alt.p);
+  cub::DoubleBuffer<uint32_t> dv(vals.p, vals_alt.p);
+  size_t tmp_bytes = 0;
+  // non-owned keys are all-ones: sort on 64 bits would be wasteful, so sort on
+  // [0, row_bits+col_bits+1) after remapping ~0 -> the bit just above the range.
+  // Simpler and exact: all-ones keys have every bit set, so sorting on the low
+  // (row_bits + col_bits + 1) bits still places them last.
+  const int end_bit = std::min(64, row_bits + col_bits + 1);
+  FQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, int64_t(ncontrib_all), 0, end_bit, ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes);
+  FQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, int64_t(ncontrib_all), 0, end_bit, ctx->stream));
+  fq_count_launch(ctx, (end_bit + 7) / 8 + 1);
+  const uint64_t* skeys = dk.Current();
+  const uint32_t* svals = dv.Current();
+  // run heads -> nnz ids
+  DevBuf<uint32_t> head(ncontrib_all), head_scan(ncontrib_all + 1);
+  sym_heads_kernel<<<grid_for(ncontrib_all, block, ctx->sm_count), block, 0, ctx->stream>>>(skeys, ncontrib_all, head.p);
+  fq_count_launch(ctx);
+  size_t tmp2 = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, head.p, head_scan.p, int64_t(ncontrib_all), ctx->stream));
+  if (tmp.n < tmp2) tmp.alloc(tmp2);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp2, head.p, head_scan.p, int64_t(ncontrib_all), ctx->stream));
+  fq_count_launch(ctx, 2);
+  uint32_t last_scan = 0, last_head = 0;
+  FQ_CUDA(cudaMemcpyAsync(&last_scan, head_scan.p + (ncontrib_all - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(&last_head, head.p + (ncontrib_all - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  const size_t s_nnz = size_t(last_scan) + last_head;
+  out->s_nnz = s_nnz;
+  out->s_col_idx.alloc(s_nnz ? s_nnz : 1);
+  out->contrib_ptr.alloc(s_nnz + 1);
+  DevBuf<uint32_t> row_of_nnz(s_nnz ? s_nnz : 1);
+  sym_emit_kernel<<<grid_for(ncontrib_all, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      skeys, head.p, head_scan.p, ncontrib_all, col_bits, out->contrib_ptr.p, out->s_col_idx.p, row_of_nnz.p);
+  fq_count_launch(ctx);
+  // number of owned contributions = first position holding an all-ones key
+  // = total - (#non-owned).  Count owned keys with a reduction over a transform.
+  {
+    // owned keys are sorted first; find the boundary by binary search on the host-free path:
+    // count of keys != ~0 via cub::DeviceReduce on a transform iterator.
+    cub::TransformInputIterator<uint32_t, IsOwnedKey, const uint64_t*> it(skeys, IsOwnedKey());
+    DevBuf<uint32_t> d_count(1);
+    size_t tmp3 = 0;
+    FQ_CUDA(cub::DeviceReduce::Sum(nullptr, tmp3, it, d_count.p, int64_t(ncontrib_all), ctx->stream));
+    if (tmp.n < tmp3) tmp.alloc(tmp3);
+    FQ_CUDA(cub::DeviceReduce::Sum(tmp.p, tmp3, it, d_count.p, int64_t(ncontrib_all), ctx->stream));
+    fq_count_launch(ctx);
+    uint32_t owned = 0;
+    FQ_CUDA(cudaMemcpyAsync(&owned, d_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->ncontrib = owned;
+  }
+  const uint32_t ncontrib32 = uint32_t(out->ncontrib);
+  FQ_CUDA(cudaMemcpyAsync(out->contrib_ptr.p + s_nnz, &ncontrib32, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  out->contrib_src.alloc(out->ncontrib ? out->ncontrib : 1);
+  FQ_CUDA(cudaMemcpyAsync(out->contrib_src.p, svals, out->ncontrib * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                          ctx->stream));
+  sym_rowptr_kernel<<<grid_for(s_nnz + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      row_of_nnz.p, uint32_t(s_nnz), uint32_t(nrows_local), out->s_row_ptr.p);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  out->s_values.alloc(s_nnz ? s_nnz : 1);
+  out->keep.alloc(s_nnz ? s_nnz : 1);
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ------------------------------------------------------------------ numeric
+// One thread per structural non-zero: ordered sum of its contributions and the
+// "any contribution != 0.0" flag of galerkin.rs:173.
+__global__ void __launch_bounds__(256) num_gather_kernel(const double* __restrict__ slab,
+                                                          const uint32_t* __restrict__ contrib_ptr,
+                                                          const uint32_t* __restrict__ contrib_src, uint32_t s_nnz,
+                                                          double* __restrict__ values, uint8_t* __restrict__ keep) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < s_nnz; q += stride) {
+    const uint32_t b = contrib_ptr[q], e = contrib_ptr[q + 1];
+    double acc = 0.0;
+    bool any = false;
+    for (uint32_t p = b; p < e; ++p) {
+      const double v = slab[contrib_src[p]];
+      any = any || (v != 0.0);
+      acc = __dadd_rn(acc, v);
+    }
+    values[q] = acc;
+    keep[q] = any ? 1 : 0;
+  }
+}
+
+__global__ void num_keep_to_u32(const uint8_t* __restrict__ keep, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) out[q] = keep[q];
+}
+
+__global__ void num_compact_kernel(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint32_t s_nnz,
+                                   const uint32_t* __restrict__ s_col, const double* __restrict__ s_val,
+                                   uint32_t* __restrict__ col, double* __restrict__ val) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < s_nnz; q += stride)
+    if (keep[q]) {
+      col[pos[q]] = s_col[q];
+      val[pos[q]] = s_val[q];
+    }
+}
+__global__ void num_rowptr_kernel(const uint32_t* __restrict__ s_row_ptr, const uint32_t* __restrict__ pos,
+                                  uint32_t nrows, uint32_t* __restrict__ row_ptr) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nrows; r += stride) row_ptr[r] = pos[s_row_ptr[r]];
+}
+
+void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros) {
+  FQ_REQUIRE(csr->has_plan, "matrix has no assembly plan (uploaded matrices cannot be re-assembled)");
+  FQ_REQUIRE(csr->ncells == mesh->ncells && csr->dim == mesh->dim, "mesh does not match the symbolic phase");
+  const size_t nrows_local = csr->row_end - csr->row_begin;
+  const size_t s_nnz = csr->s_nnz;
+  const int block = 256;
+  const size_t T = size_t(csr->el_rows) * size_t(csr->el_cols);
+  csr->spmv_ready = false;
+  csr->inv_diag.release();
+  if (s_nnz > 0) {
+    // K1: element slab
+    DevBuf<double> slab(mesh->ncells * T);
+    elmat_to_slab(ctx, mesh, {{csr->kind, csr->grade}}, 0, mesh->ncells, true, slab.p, nullptr);
+    // K3: segmented reduction
+    num_gather_kernel<<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
+        slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->s_values.p, csr->keep.p);
+    fq_count_launch(ctx);
+    FQ_CUDA(cudaGetLastError());
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // slab freed below
+  }
+  const int ne = int(binom(mesh->dim + 1, 2));
+  csr->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csr->ncontrib);
+  if (!drop_exact_zeros || s_nnz == 0) {
+    csr->dropped = false;
+    csr->nnz = s_nnz;
+    csr->row_ptr.alloc(nrows_local + 1);
+    csr->col_idx.alloc(s_nnz ? s_nnz : 1);
+    csr->values.alloc(s_nnz ? s_nnz : 1);
+    FQ_CUDA(cudaMemcpyAsync(csr->row_ptr.p, csr->s_row_ptr.p, (nrows_local + 1) * sizeof(uint32_t),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+    if (s_nnz) {
+      FQ_CUDA(cudaMemcpyAsync(csr->col_idx.p, csr->s_col_idx.p, s_nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+      FQ_CUDA(cudaMemcpyAsync(csr->values.p, csr->s_values.p, s_nnz * sizeof(double), cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+    }
+    csr->assembly_bytes += int64_t(8 * s_nnz);
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  // compaction to the reference's value-dependent pattern
+  DevBuf<uint32_t> k32(s_nnz + 1), pos(s_nnz + 1);
+  num_keep_to_u32<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(csr->keep.p, uint32_t(s_nnz), k32.p);
+  FQ_CUDA(cudaMemsetAsync(k32.p + s_nnz, 0, sizeof(uint32_t), ctx->stream));
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, k32.p, pos.p, int64_t(s_nnz + 1), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, k32.p, pos.p, int64_t(s_nnz + 1), ctx->stream));
+  fq_count_launch(ctx, 3);
+  uint32_t nnz = 0;
+  FQ_CUDA(cudaMemcpyAsync(&nnz, pos.p + s_nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  csr->dropped = true;
+  csr->nnz = nnz;
+  csr->row_ptr.alloc(nrows_local + 1);
+  csr->col_idx.alloc(nnz ? nnz : 1);
+  csr->values.alloc(nnz ? nnz : 1);
+  num_compact_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      csr->keep.p, pos.p, uint32_t(s_nnz), csr->s_col_idx.p, csr->s_values.p, csr->col_idx.p, csr->values.p);
+  num_rowptr_kernel<<<grid_for(nrows_local + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      csr->s_row_ptr.p, pos.p, uint32_t(nrows_local), csr->row_ptr.p);
+  fq_count_launch(ctx, 2);
+  FQ_CUDA(cudaGetLastError());
+  csr->assembly_bytes += int64_t(8 * size_t(nnz));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace fq

@@ -1,0 +1,465 @@
+// capi.cu — the extern "C" boundary declared in include/formoniq_b200.h.
+#include <limits>
+
+#include "internal.hpp"
+#include "kuhn.hpp"
+
+namespace fq {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+__global__ void widen_u32_kernel(const uint32_t* __restrict__ in, size_t n, uint64_t* __restrict__ out) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+__global__ void narrow_u64_kernel(const uint64_t* __restrict__ in, size_t n, uint32_t* __restrict__ out,
+                                  int* __restrict__ overflow) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t v = in[i];
+    if (v >> 32) *overflow = 1;
+    out[i] = uint32_t(v);
+  }
+}
+
+// host u64 array -> device u32 array (chunked through a staging buffer)
+static void upload_narrow(fq_ctx* ctx, const uint64_t* host, size_t n, DevBuf<uint32_t>& dst) {
+  dst.alloc(n ? n : 1);
+  if (!n) return;
+  const size_t chunk = size_t(1) << 24;
+  DevBuf<uint64_t> stage(std::min(n, chunk));
+  DevBuf<int> ovf(1);
+  FQ_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), ctx->stream));
+  for (size_t off = 0; off < n; off += chunk) {
+    const size_t m = std::min(chunk, n - off);
+    FQ_CUDA(cudaMemcpyAsync(stage.p, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    narrow_u64_kernel<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(stage.p, m, dst.p + off, ovf.p);
+    fq_count_launch(ctx);
+  }
+  int h = 0;
+  FQ_CUDA(cudaMemcpyAsync(&h, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  FQ_REQUIRE(h == 0, "index does not fit 32 bits");
+}
+// device u32 array -> host u64 array
+static void download_widen(fq_ctx* ctx, const uint32_t* dev, size_t n, uint64_t* host) {
+  if (!n) return;
+  const size_t chunk = size_t(1) << 24;
+  DevBuf<uint64_t> stage(std::min(n, chunk));
+  for (size_t off = 0; off < n; off += chunk) {
+    const size_t m = std::min(chunk, n - off);
+    widen_u32_kernel<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(dev + off, m, stage.p);
+    fq_count_launch(ctx);
+    FQ_CUDA(cudaMemcpyAsync(host + off, stage.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+}
+}  // namespace fq
+
+using namespace fq;
+
+extern "C" {
+
+const char* fq_last_error(void) { return g_last_error.c_str(); }
+
+int fq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fq_ctx_create(int device, fq_ctx** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(out, "null output");
+  int n = 0;
+  FQ_CUDA(cudaGetDeviceCount(&n));
+  if (n <= 0) throw Error(FQ_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+  FQ_REQUIRE(device >= 0 && device < n, "device index out of range");
+  FQ_CUDA(cudaSetDevice(device));
+  fq_ctx* ctx = new fq_ctx;
+  ctx->device = device;
+  FQ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  cudaDeviceProp prop;
+  FQ_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  FQ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->host_scalar), 64));
+  *out = ctx;
+  FQ_API_END
+}
+int fq_ctx_destroy(fq_ctx* ctx) {
+  FQ_API_BEGIN
+  if (ctx) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
+    delete ctx;
+  }
+  FQ_API_END
+}
+int fq_ctx_set_stream(fq_ctx* ctx, void* cuda_stream) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx, "null context");
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  FQ_API_END
+}
+int fq_ctx_synchronize(fq_ctx* ctx) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx, "null context");
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  FQ_API_END
+}
+int64_t fq_ctx_launch_count(const fq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- mesh
+int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices, const uint64_t* const* cell_faces,
+                   const double* edge_lengths_sq, fq_mesh** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && out && nsimplices && cell_faces, "null argument");
+  FQ_REQUIRE(dim >= 1 && dim <= 10, "1 <= dim <= 10");
+  FQ_REQUIRE(nsimplices[dim] == ncells, "nsimplices[dim] must equal ncells");
+  FQ_REQUIRE(cell_faces[1] && edge_lengths_sq, "grade-1 faces and edge lengths are required");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_mesh> m(new fq_mesh);
+  m->dim = dim;
+  m->ncells = ncells;
+  m->nsimplices.assign(nsimplices, nsimplices + dim + 1);
+  m->cell_faces.resize(size_t(dim) + 1);
+  m->id_lo.assign(size_t(dim) + 1, 0);
+  m->id_hi.assign(nsimplices, nsimplices + dim + 1);
+  m->own_lo = m->id_lo;
+  m->own_hi = m->id_hi;
+  for (int j = 0; j <= dim; ++j) {
+    FQ_REQUIRE(nsimplices[j] < (size_t(1) << 32), "more than 2^32 simplices of one grade: not supported");
+    if (cell_faces[j]) upload_narrow(ctx, cell_faces[j], ncells * size_t(nlocal(dim, j)), m->cell_faces[size_t(j)]);
+  }
+  m->lengths.alloc(nsimplices[1] ? nsimplices[1] : 1);
+  m->edge_lo = 0;
+  FQ_CUDA(cudaMemcpyAsync(m->lengths.p, edge_lengths_sq, nsimplices[1] * sizeof(double), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = m.release();
+  FQ_API_END
+}
+
+int fq_mesh_create_kuhn(fq_ctx* ctx, int dim, const size_t* shape, const double* vmin, const double* vmax,
+                        const double* ambient_diag, double jitter, size_t slab_begin, size_t slab_end, fq_mesh** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && out && shape, "null argument");
+  FQ_REQUIRE(dim >= 1 && dim <= 6, "Kuhn generator supports 1 <= dim <= 6");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_mesh> m(new fq_mesh);
+  kuhn_build_mesh(ctx, dim, shape, vmin, vmax, ambient_diag, jitter, slab_begin, slab_end, m.get());
+  *out = m.release();
+  FQ_API_END
+}
+int fq_mesh_destroy(fq_mesh* mesh) {
+  delete mesh;
+  return FQ_OK;
+}
+int fq_mesh_dim(const fq_mesh* mesh) { return mesh ? mesh->dim : -1; }
+size_t fq_mesh_ncells(const fq_mesh* mesh) { return mesh ? mesh->ncells : 0; }
+size_t fq_mesh_nsimplices(const fq_mesh* mesh, int grade) {
+  if (!mesh || grade < 0 || grade > mesh->dim) return 0;
+  return mesh->nsimplices[size_t(grade)];
+}
+int fq_mesh_set_lengths(fq_ctx* ctx, fq_mesh* mesh, const double* edge_lengths_sq) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && edge_lengths_sq, "null argument");
+  // host array covers all edges; the mesh keeps [edge_lo, edge_lo + n)
+  FQ_CUDA(cudaMemcpyAsync(mesh->lengths.p, edge_lengths_sq + mesh->edge_lo,
+                          (mesh->id_hi[1] - mesh->id_lo[1]) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  FQ_API_END
+}
+int fq_mesh_download_cell_faces(fq_ctx* ctx, const fq_mesh* mesh, int grade, uint64_t* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out && grade >= 0 && grade <= mesh->dim, "bad argument");
+  FQ_REQUIRE(mesh->cell_faces[size_t(grade)].p, "grade not present");
+  download_widen(ctx, mesh->cell_faces[size_t(grade)].p, mesh->ncells * size_t(nlocal(mesh->dim, grade)), out);
+  FQ_API_END
+}
+int fq_mesh_download_lengths(fq_ctx* ctx, const fq_mesh* mesh, double* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out, "null argument");
+  // writes the held range at its global position
+  FQ_CUDA(cudaMemcpyAsync(out + mesh->edge_lo, mesh->lengths.p, (mesh->id_hi[1] - mesh->id_lo[1]) * sizeof(double),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  FQ_API_END
+}
+
+int fq_kuhn_counts(int dim, const size_t* shape, size_t* nsimplices) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(shape && nsimplices, "null argument");
+  const KuhnTables kt(dim);
+  const uint32_t full = (1u << dim) - 1;
+  for (int j = 0; j <= dim; ++j) {
+    uint64_t total = 0;
+    for (uint32_t B = 0; B <= full; ++B) {
+      uint64_t nv = 1;
+      for (int a = 0; a < dim; ++a) nv *= (B >> a & 1u) ? shape[a] : 1;
+      total += nv * kt.grades[size_t(j)].cnt[B];
+    }
+    nsimplices[j] = size_t(total);
+  }
+  FQ_API_END
+}
+
+int fq_kuhn_cell_faces_host(int dim, const size_t* shape, int grade, uint64_t* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(shape && out, "null argument");
+  FQ_REQUIRE(grade >= 0 && grade <= dim, "grade out of range");
+  const KuhnTables kt(dim);
+  const KuhnGrid g(dim, shape);
+  const KuhnGrade& kg = kt.grades[size_t(grade)];
+  const std::vector<uint64_t> vbase = kuhn_vbase_host(kt, g, grade);
+  const int nl = nlocal(dim, grade);
+  const uint64_t ncells = g.nboxes * uint64_t(kt.ncelltypes);
+  for (uint64_t c = 0; c < ncells; ++c) {
+    uint64_t box = c / uint64_t(kt.ncelltypes);
+    const int t = int(c % uint64_t(kt.ncelltypes));
+    uint64_t oc[8];
+    for (int a = 0; a < dim; ++a) {
+      oc[a] = box % g.shape[a];
+      box /= g.shape[a];
+    }
+    for (int l = 0; l < nl; ++l) {
+      const uint32_t top = kt.ftop[size_t(grade)][size_t(t) * nl + l];
+      uint64_t w = 0;
+      uint32_t B = 0;
+      for (int a = 0; a < dim; ++a) {
+        const uint64_t ca = oc[a] + ((top >> a) & 1u);
+        w += ca * g.vstride[a];
+        if (ca) B |= 1u << a;
+      }
+      out[c * nl + l] = vbase[size_t(w)] + kg.rank_in[size_t(B) * kg.ntypes + kt.ftype[size_t(grade)][size_t(t) * nl + l]];
+    }
+  }
+  FQ_API_END
+}
+
+// ---------------------------------------------------------------- element matrices
+int fq_elmat_shape(int dim, int kind, int grade, int* rows, int* cols) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(rows && cols, "null argument");
+  int tg, rg;
+  kind_grades(kind, grade, tg, rg);
+  *rows = nlocal(dim, tg);
+  *cols = nlocal(dim, rg);
+  FQ_API_END
+}
+
+int fq_elmat_batch(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t cell_begin, size_t cell_end,
+                   int use_generated, double* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out, "null argument");
+  FQ_REQUIRE(kind >= 0 && kind <= 4, "unknown kind");
+  FQ_REQUIRE(cell_begin <= cell_end && cell_end <= mesh->ncells, "cell range out of bounds");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  const std::vector<BlockSpec> blocks{{kind, grade}};
+  const int nouts = elmat_nouts(mesh->dim, blocks);
+  const size_t nc = cell_end - cell_begin;
+  if (nc == 0 || nouts == 0) return FQ_OK;
+  DevBuf<double> slab(nc * size_t(nouts));
+  DevBuf<int> err(1);
+  FQ_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
+  elmat_to_slab(ctx, mesh, blocks, cell_begin, cell_end, use_generated != 0, slab.p, err.p);
+  int h = 0;
+  FQ_CUDA(cudaMemcpyAsync(&h, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(out, slab.p, slab.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h) throw Error(FQ_ERR_DEGENERATE, "a cell metric is singular");
+  FQ_API_END
+}
+
+// ---------------------------------------------------------------- assembly
+int fq_assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
+                         fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out, "null argument");
+  FQ_REQUIRE(kind >= 0 && kind <= 4, "unknown kind");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_csr> m(new fq_csr);
+  assemble_symbolic(ctx, mesh, kind, grade, row_begin, row_end, m.get());
+  *out = m.release();
+  FQ_API_END
+}
+int fq_assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, int drop_exact_zeros) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && csr, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  assemble_numeric(ctx, mesh, csr, drop_exact_zeros != 0);
+  FQ_API_END
+}
+int fq_assemble(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, int drop_exact_zeros, fq_csr** out) {
+  const int rc = fq_assemble_symbolic(ctx, mesh, kind, grade, 0, std::numeric_limits<size_t>::max(), out);
+  if (rc != FQ_OK) return rc;
+  const int rc2 = fq_assemble_numeric(ctx, mesh, *out, drop_exact_zeros);
+  if (rc2 != FQ_OK) {
+    delete *out;
+    *out = nullptr;
+  }
+  return rc2;
+}
+
+// ---------------------------------------------------------------- CSR
+int fq_csr_shape(const fq_csr* csr, size_t* nrows, size_t* ncols, size_t* nnz) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(csr, "null argument");
+  if (nrows) *nrows = csr->nrows;
+  if (ncols) *ncols = csr->ncols;
+  if (nnz) *nnz = csr->nnz;
+  FQ_API_END
+}
+int fq_csr_row_range(const fq_csr* csr, size_t* row_begin, size_t* row_end) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(csr, "null argument");
+  if (row_begin) *row_begin = csr->row_begin;
+  if (row_end) *row_end = csr->row_end;
+  FQ_API_END
+}
+int fq_csr_download(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t* col_indices, double* values) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && csr, "null argument");
+  static_assert(sizeof(size_t) == sizeof(uint64_t), "usize must be 64-bit");
+  const size_t nrows_local = csr->row_end - csr->row_begin;
+  if (row_offsets) download_widen(ctx, csr->row_ptr.p, nrows_local + 1, reinterpret_cast<uint64_t*>(row_offsets));
+  if (col_indices) download_widen(ctx, csr->col_idx.p, csr->nnz, reinterpret_cast<uint64_t*>(col_indices));
+  if (values && csr->nnz) {
+    FQ_CUDA(cudaMemcpyAsync(values, csr->values.p, csr->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  FQ_API_END
+}
+int fq_csr_upload(fq_ctx* ctx, size_t nrows, size_t ncols, const size_t* row_offsets, const size_t* col_indices,
+                  const double* values, fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && row_offsets && out, "null argument");
+  FQ_REQUIRE(nrows < (size_t(1) << 32) && ncols < (size_t(1) << 32), "more than 2^32 rows/cols: not supported");
+  const size_t nnz = row_offsets[nrows];
+  FQ_REQUIRE(nnz < (size_t(1) << 32), "more than 2^32 non-zeros: not supported");
+  FQ_REQUIRE(nnz == 0 || (col_indices && values), "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_csr> m(new fq_csr);
+  m->nrows = nrows;
+  m->ncols = ncols;
+  m->row_begin = 0;
+  m->row_end = nrows;
+  m->nnz = nnz;
+  upload_narrow(ctx, reinterpret_cast<const uint64_t*>(row_offsets), nrows + 1, m->row_ptr);
+  upload_narrow(ctx, reinterpret_cast<const uint64_t*>(col_indices), nnz, m->col_idx);
+  m->values.alloc(nnz ? nnz : 1);
+  if (nnz) FQ_CUDA(cudaMemcpyAsync(m->values.p, values, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = m.release();
+  FQ_API_END
+}
+int fq_csr_destroy(fq_csr* csr) {
+  delete csr;
+  return FQ_OK;
+}
+int64_t fq_csr_assembly_bytes(const fq_csr* csr) { return csr ? csr->assembly_bytes : 0; }
+int64_t fq_csr_spmv_bytes(const fq_csr* csr) {
+  if (!csr) return 0;
+  const size_t nrows_local = csr->row_end - csr->row_begin;
+  return int64_t(12 * csr->nnz + 4 * (nrows_local + 1) + 8 * nrows_local + 8 * csr->ncols);
+}
+
+// ---------------------------------------------------------------- vectors
+int fq_vec_create(fq_ctx* ctx, size_t n, fq_vec** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_vec> v(new fq_vec);
+  v->d.alloc(n ? n : 1);
+  v->d.n = n;
+  FQ_CUDA(cudaMemsetAsync(v->d.p, 0, (n ? n : 1) * sizeof(double), ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = v.release();
+  FQ_API_END
+}
+int fq_vec_destroy(fq_vec* v) {
+  delete v;
+  return FQ_OK;
+}
+size_t fq_vec_len(const fq_vec* v) { return v ? v->d.n : 0; }
+int fq_vec_upload(fq_ctx* ctx, fq_vec* v, const double* host) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && v && (host || v->d.n == 0), "null argument");
+  if (v->d.n) FQ_CUDA(cudaMemcpyAsync(v->d.p, host, v->d.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  FQ_API_END
+}
+int fq_vec_download(fq_ctx* ctx, const fq_vec* v, double* host) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && v && (host || v->d.n == 0), "null argument");
+  if (v->d.n) FQ_CUDA(cudaMemcpyAsync(host, v->d.p, v->d.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  FQ_API_END
+}
+int fq_vec_copy(fq_ctx* ctx, fq_vec* dst, const fq_vec* src) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && dst && src && dst->d.n == src->d.n, "vector length mismatch");
+  if (src->d.n)
+    FQ_CUDA(cudaMemcpyAsync(dst->d.p, src->d.p, src->d.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  FQ_API_END
+}
+int fq_vec_dot(fq_ctx* ctx, const fq_vec* x, const fq_vec* y, double* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && x && y && out && x->d.n == y->d.n, "vector length mismatch");
+  *out = vec_dot(ctx, x->d.p, y->d.p, x->d.n);
+  FQ_API_END
+}
+int fq_vec_scale(fq_ctx* ctx, fq_vec* x, double alpha) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && x, "null argument");
+  vec_scale(ctx, x->d.p, alpha, x->d.n);
+  FQ_API_END
+}
+int fq_vec_axpy(fq_ctx* ctx, fq_vec* y, double alpha, const fq_vec* x) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && x && y && x->d.n == y->d.n && x != y, "axpy needs two distinct vectors of one length");
+  vec_axpy(ctx, y->d.p, alpha, x->d.p, x->d.n);
+  FQ_API_END
+}
+void* fq_vec_device_ptr(fq_vec* v) { return v ? v->d.p : nullptr; }
+
+// ---------------------------------------------------------------- SpMV / Krylov
+int fq_spmv(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, fq_vec* y) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && x && y, "null argument");
+  FQ_REQUIRE(x->d.n == a->ncols && y->d.n == a->row_end - a->row_begin, "spmv: dimension mismatch");
+  FQ_REQUIRE(x != y, "spmv: x and y must be distinct");
+  spmv_prepare(ctx, const_cast<fq_csr*>(a));
+  spmv_apply(ctx, a, x->d.p, y->d.p);
+  FQ_API_END
+}
+
+static int krylov_common(bool is_cg, fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol,
+                         size_t max_iters, fq_vec* x, size_t* iters, double* residual, int* converged) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && b && x, "null argument");
+  FQ_REQUIRE(precond == 0 || precond == 1, "precond: 0 identity, 1 Jacobi");
+  fq_csr* am = const_cast<fq_csr*>(a);
+  const KrylovReport r = is_cg ? krylov_cg(ctx, am, precond, b, rtol, max_iters, x)
+                               : krylov_minres(ctx, am, precond, b, rtol, max_iters, x);
+  if (iters) *iters = r.iters;
+  if (residual) *residual = r.residual;
+  if (converged) *converged = r.converged ? 1 : 0;
+  FQ_API_END
+}
+int fq_cg(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
+          size_t* iters, double* residual, int* converged) {
+  return krylov_common(true, ctx, a, precond, b, rtol, max_iters, x, iters, residual, converged);
+}
+int fq_minres(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
+              size_t* iters, double* residual, int* converged) {
+  return krylov_common(false, ctx, a, precond, b, rtol, max_iters, x, iters, residual, converged);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// common.cuh — shared plumbing of libformoniq_b200: error handling, context,
+// device buffers, handle structs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/formoniq_b200.h"
+#include "tape.hpp"
+
+namespace fq {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& m);
+
+#define FQ_CUDA(expr)                                                                                       \
+  do {                                                                                                      \
+    cudaError_t err__ = (expr);                                                                             \
+    if (err__ != cudaSuccess)                                                                               \
+      throw ::fq::Error(FQ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__) + " (" + __FILE__ + \
+                                         ":" + std::to_string(__LINE__) + ")");                             \
+  } while (0)
+
+#define FQ_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) throw ::fq::Error(FQ_ERR_INVALID, (msg));     \
+  } while (0)
+
+// Wrap an extern "C" body: exceptions never cross the ABI.
+#define FQ_API_BEGIN try {
+#define FQ_API_END                                  \
+  return FQ_OK;                                     \
+  }                                                 \
+  catch (const ::fq::Error& e) {                    \
+    ::fq::set_last_error(e.what());                 \
+    return e.code;                                  \
+  }                                                 \
+  catch (const std::exception& e) {                 \
+    ::fq::set_last_error(e.what());                 \
+    return FQ_ERR_INVALID;                          \
+  }
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p, n = o.n;
+      o.p = nullptr, o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (n) FQ_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr, n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace fq
+
+struct fq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int64_t launches = 0;
+  fq::DevBuf<double> reduce_scratch;  // two-stage reductions
+  double* host_scalar = nullptr;      // pinned
+};
+
+inline void fq_count_launch(fq_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+struct fq_mesh {
+  int dim = 0;
+  size_t ncells = 0;
+  size_t cell_offset = 0;            // global index of local cell 0 (slab meshes)
+  std::vector<size_t> nsimplices;    // global counts per grade
+  // cell_faces[j]: [ncells][nlocal(dim,j)] global face ids (u32)
+  std::vector<fq::DevBuf<uint32_t>> cell_faces;
+  // signed squared edge lengths for edge ids [edge_lo, edge_lo + lengths.n)
+  fq::DevBuf<double> lengths;
+  size_t edge_lo = 0;
+  // id ranges referenced by the local cells, per grade (global for full meshes)
+  std::vector<size_t> id_lo, id_hi;
+  // rows owned under the owner-computes slab partition (== id range of the
+  // simplices whose top vertex lies in the slab's own vertex layers)
+  std::vector<size_t> own_lo, own_hi;
+};
+
+struct fq_vec {
+  fq::DevBuf<double> d;
+};
+
+// One block's symbolic data: structural pattern + gather lists.
+struct fq_csr {
+  size_t nrows = 0, ncols = 0;     // global shape
+  size_t row_begin = 0, row_end = 0;  // rows held (local row r <-> global row_begin + r)
+  // active pattern (what the consumer sees)
+  size_t nnz = 0;
+  fq::DevBuf<uint32_t> row_ptr;  // [nrows_local+1]
+  fq::DevBuf<uint32_t> col_idx;  // [nnz] global column ids
+  fq::DevBuf<double> values;     // [nnz]
+  // ---- assembly plan (empty for uploaded matrices)
+  bool has_plan = false;
+  int kind = 0, grade = 0, dim = 0;
+  int el_rows = 0, el_cols = 0;
+  size_t ncells = 0;
+  size_t s_nnz = 0;                 // structural nnz
+  fq::DevBuf<uint32_t> s_row_ptr;   // [nrows_local+1]
+  fq::DevBuf<uint32_t> s_col_idx;   // [s_nnz]
+  fq::DevBuf<uint32_t> contrib_ptr; // [s_nnz+1] segments of contrib_src
+  fq::DevBuf<uint32_t> contrib_src; // [ncontrib] cell*T+slot, sorted by (nnz, cell)
+  size_t ncontrib = 0;
+  fq::DevBuf<double> s_values;      // [s_nnz] structural values (scratch when dropping)
+  fq::DevBuf<uint8_t> keep;         // [s_nnz]
+  bool dropped = false;
+  int64_t assembly_bytes = 0;
+  // SpMV row blocks (CSR-stream)
+  fq::DevBuf<uint32_t> rowblocks;
+  size_t nrowblocks = 0;
+  bool spmv_ready = false;
+  // Jacobi (inverse diagonal), built on demand
+  fq::DevBuf<double> inv_diag;
+};

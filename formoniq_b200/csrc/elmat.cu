@@ -1,0 +1,341 @@
+// elmat.cu — K1: batched per-cell element matrices.
+//
+// Two paths share one arithmetic definition (the tape of tape.hpp):
+//   * generated straight-line kernels (elmat_gen.cuh) for dim <= 3, thread per
+//     cell, every intermediate in registers;
+//   * a generic tape interpreter for any runtime (dim, grade): thread per cell,
+//     register file in a coalesced global scratch slab, for dim >= 4 preceded
+//     by a generic geometry stage (closed-form 4x4 inverse, LU beyond).
+// All FP64 arithmetic is explicit round-to-nearest (no FMA contraction), so the
+// zero / non-zero classification of every entry matches the reference's
+// (galerkin.rs:173 makes the CSR pattern depend on it).
+#include <map>
+#include <mutex>
+
+#include "elmat_gen.cuh"
+#include "internal.hpp"
+
+namespace fq {
+
+// ------------------------------------------------------------------ sinks
+struct SlabSink {
+  double* __restrict__ base;  // this cell's block of the slab
+  template <unsigned I>
+  __device__ __forceinline__ void put(double v) const {
+    base[I] = v;
+  }
+};
+
+template <class Fn, int NE>
+__global__ void __launch_bounds__(128) elmat_gen_kernel(Fn fn, const uint32_t* __restrict__ cell_edges,
+                                                         const double* __restrict__ lengths, uint32_t edge_lo,
+                                                         size_t c0, size_t ncells, int nouts,
+                                                         double* __restrict__ out) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < ncells; i += stride) {
+    const uint32_t* ce = cell_edges + (c0 + i) * NE;
+    double s[NE > 0 ? NE : 1];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) s[e] = __ldg(lengths + (ce[e] - edge_lo));
+    SlabSink sink{out + i * size_t(nouts)};
+    fn(s, sink);
+  }
+}
+
+#define FQ_DECLARE_FN(fn, n, fk, kind, grade, nin, nout)                                        \
+  struct Fn_##fn {                                                                              \
+    template <class S>                                                                          \
+    __device__ __forceinline__ void operator()(const double* __restrict__ s, S& sink) const {   \
+      fn(s, sink);                                                                              \
+    }                                                                                           \
+  };
+FQ_GEN_ELMAT_LIST(FQ_DECLARE_FN)
+#undef FQ_DECLARE_FN
+
+struct GenEntry {
+  int n, fused_k, kind, grade, nin, nout;
+  void (*launch)(fq_ctx*, const fq_mesh*, size_t, size_t, double*);
+};
+
+template <class Fn, int NE>
+static void launch_gen(fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int nouts, double* d_out) {
+  const size_t nc = c1 - c0;
+  if (nc == 0) return;
+  const int block = 128;
+  const int grid = grid_for(nc, block, ctx->sm_count, 16);
+  elmat_gen_kernel<Fn, NE><<<grid, block, 0, ctx->stream>>>(Fn{}, mesh->cell_faces[1].p, mesh->lengths.p,
+                                                            uint32_t(mesh->edge_lo), c0, nc, nouts, d_out);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
+
+#define FQ_ENTRY(fn, n, fk, kind, grade, nin, nout)                                              \
+  GenEntry{n, fk, kind, grade, nin, nout,                                                        \
+           [](fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, double* d_out) {           \
+             launch_gen<Fn_##fn, nin>(ctx, mesh, c0, c1, nout, d_out);                           \
+           }},
+static const GenEntry g_entries[] = {FQ_GEN_ELMAT_LIST(FQ_ENTRY)};
+#undef FQ_ENTRY
+
+static const GenEntry* find_generated(int dim, const std::vector<BlockSpec>& blocks) {
+  int fused_k = -2;
+  if (blocks.size() == 4) {
+    const auto hb = hodge_blocks(blocks[1].grade);
+    bool same = true;
+    for (int i = 0; i < 4; ++i) same = same && hb[i].kind == blocks[i].kind && hb[i].grade == blocks[i].grade;
+    if (same) fused_k = blocks[1].grade;
+  }
+  for (const GenEntry& e : g_entries) {
+    if (e.n != dim) continue;
+    if (fused_k >= 0) {
+      if (e.fused_k == fused_k) return &e;
+    } else if (blocks.size() == 1 && e.fused_k < 0 && e.kind == blocks[0].kind &&
+               (e.kind == KIND_LUMPED || e.grade == blocks[0].grade)) {
+      return &e;
+    }
+  }
+  return nullptr;
+}
+
+bool elmat_has_generated(int dim, const std::vector<BlockSpec>& blocks) { return find_generated(dim, blocks) != nullptr; }
+
+int elmat_nouts(int dim, const std::vector<BlockSpec>& blocks) {
+  int total = 0;
+  for (const BlockSpec& b : blocks) {
+    int tg, rg;
+    kind_grades(b.kind, b.grade, tg, rg);
+    if (b.kind == KIND_LUMPED) tg = rg = 0;
+    total += nlocal(dim, tg) * nlocal(dim, rg);
+  }
+  return total;
+}
+
+// ------------------------------------------------------------------ generic geometry (dim >= 4)
+constexpr int kMaxDim = 10;
+
+// Metric by polarisation, inverse and volume for one cell; mirrors the
+// closed-form / LU split of nalgebra (4x4 cofactors, LU with partial pivoting
+// beyond).  Returns false on a singular metric.
+__device__ bool geometry_generic(int n, const double* s, double* ginv /*n*n row-major*/, double* vol) {
+  double g[kMaxDim * kMaxDim];
+  auto eidx = [](int i, int j) { return i + j * (j - 1) / 2; };  // i<j : C(i,1)+C(j,2)
+  for (int i = 0; i < n; ++i) g[i * n + i] = s[eidx(0, i + 1)];
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      const double v = 0.5 * ((s[eidx(0, i + 1)] + s[eidx(0, j + 1)]) - s[eidx(i + 1, j + 1)]);
+      g[i * n + j] = v;
+      g[j * n + i] = v;
+    }
+  // LU (partial pivoting) — determinant always, inverse for n >= 5
+  double lu[kMaxDim * kMaxDim];
+  int piv[kMaxDim];
+  for (int i = 0; i < n * n; ++i) lu[i] = g[i];
+  int nswaps = 0;
+  bool ok = true;
+  for (int i = 0; i < n; ++i) {
+    int p = i;
+    double best = fabs(lu[i * n + i]);
+    for (int r = i + 1; r < n; ++r)
+      if (fabs(lu[r * n + i]) > best) best = fabs(lu[r * n + i]), p = r;
+    piv[i] = p;
+    if (best == 0.0) {
+      ok = false;
+      continue;
+    }
+    if (p != i) {
+      ++nswaps;
+      for (int c = 0; c < n; ++c) {
+        const double t = lu[i * n + c];
+        lu[i * n + c] = lu[p * n + c];
+        lu[p * n + c] = t;
+      }
+    }
+    const double d = lu[i * n + i];
+    for (int r = i + 1; r < n; ++r) lu[r * n + i] = lu[r * n + i] / d;
+    for (int c = i + 1; c < n; ++c) {
+      const double pc = lu[i * n + c];
+      for (int r = i + 1; r < n; ++r) lu[r * n + c] = lu[r * n + c] - lu[r * n + i] * pc;
+    }
+  }
+  if (!ok) return false;
+  double det = 1.0;
+  for (int i = 0; i < n; ++i) det = det * lu[i * n + i];
+  if (nswaps & 1) det = -det;
+  double nf = 1.0;
+  for (int i = 2; i <= n; ++i) nf *= double(i);
+  *vol = (1.0 / nf) * sqrt(fabs(det));
+  if (n == 4) {
+    double m[16], o[16];
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 4; ++i) m[j * 4 + i] = g[i * 4 + j];
+    o[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] +
+           m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    o[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] -
+           m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    o[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] +
+           m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    o[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] -
+           m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    o[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] -
+           m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    o[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] +
+           m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    o[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] -
+           m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    o[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] +
+           m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    o[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] +
+           m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    o[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] -
+           m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    o[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] +
+            m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    o[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] -
+            m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    o[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] -
+            m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    o[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] +
+            m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    o[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] -
+            m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    o[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] +
+            m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double d4 = m[0] * o[0] + m[1] * o[4] + m[2] * o[8] + m[3] * o[12];
+    if (d4 == 0.0) return false;
+    const double inv = 1.0 / d4;
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 4; ++i) ginv[i * 4 + j] = o[j * 4 + i] * inv;
+    return true;
+  }
+  // inverse by LU solves, column by column
+  for (int col = 0; col < n; ++col) {
+    double b[kMaxDim];
+    for (int i = 0; i < n; ++i) b[i] = (i == col) ? 1.0 : 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double t = b[i];
+      b[i] = b[piv[i]];
+      b[piv[i]] = t;
+    }
+    for (int i = 0; i < n; ++i)
+      for (int r = i + 1; r < n; ++r) b[r] = b[r] - lu[r * n + i] * b[i];
+    for (int i = n - 1; i >= 0; --i) {
+      b[i] = b[i] / lu[i * n + i];
+      for (int r = 0; r < i; ++r) b[r] = b[r] - lu[r * n + i] * b[i];
+    }
+    for (int r = 0; r < n; ++r) ginv[r * n + col] = b[r];
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ interpreter
+__global__ void __launch_bounds__(128) elmat_interp_kernel(const uint4* __restrict__ ops, int nops,
+                                                            const double* __restrict__ consts, int ninputs,
+                                                            int inputs_are_lengths, int n, int ne,
+                                                            const uint32_t* __restrict__ cell_edges,
+                                                            const double* __restrict__ lengths, uint32_t edge_lo,
+                                                            size_t c0, size_t ncells, double* __restrict__ scratch,
+                                                            int nouts, double* __restrict__ out, int* __restrict__ err) {
+  const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  double* reg = scratch + tid;  // reg[r * nthreads]
+  for (size_t i = tid; i < ncells; i += nthreads) {
+    const uint32_t* ce = cell_edges + (c0 + i) * size_t(ne);
+    if (inputs_are_lengths) {
+      for (int e = 0; e < ne; ++e) reg[size_t(e) * nthreads] = lengths[ce[e] - edge_lo];
+    } else {
+      double s[kMaxDim * (kMaxDim + 1) / 2];
+      double gi[kMaxDim * kMaxDim];
+      double vol;
+      for (int e = 0; e < ne; ++e) s[e] = lengths[ce[e] - edge_lo];
+      if (!geometry_generic(n, s, gi, &vol)) {
+        if (err) atomicExch(err, 1);
+        vol = 0.0;
+        for (int e = 0; e < n * n; ++e) gi[e] = 0.0;
+      }
+      for (int e = 0; e < n * n; ++e) reg[size_t(e) * nthreads] = gi[e];
+      reg[size_t(n * n) * nthreads] = vol;
+    }
+    double* o = out + i * size_t(nouts);
+    for (int p = 0; p < nops; ++p) {
+      const uint4 op = __ldg(ops + p);
+      switch (op.x) {
+        case OP_ADD: reg[size_t(op.y) * nthreads] = __dadd_rn(reg[size_t(op.z) * nthreads], reg[size_t(op.w) * nthreads]); break;
+        case OP_SUB: reg[size_t(op.y) * nthreads] = __dsub_rn(reg[size_t(op.z) * nthreads], reg[size_t(op.w) * nthreads]); break;
+        case OP_MUL: reg[size_t(op.y) * nthreads] = __dmul_rn(reg[size_t(op.z) * nthreads], reg[size_t(op.w) * nthreads]); break;
+        case OP_MULC: reg[size_t(op.y) * nthreads] = __dmul_rn(reg[size_t(op.z) * nthreads], __ldg(consts + op.w)); break;
+        case OP_DIV: reg[size_t(op.y) * nthreads] = __ddiv_rn(reg[size_t(op.z) * nthreads], reg[size_t(op.w) * nthreads]); break;
+        case OP_SQRTABS: reg[size_t(op.y) * nthreads] = __dsqrt_rn(fabs(reg[size_t(op.z) * nthreads])); break;
+        case OP_LOADC: reg[size_t(op.y) * nthreads] = __ldg(consts + op.w); break;
+        case OP_STORE: o[op.y] = reg[size_t(op.z) * nthreads]; break;
+        case OP_STOREN: o[op.y] = -reg[size_t(op.z) * nthreads]; break;
+        case OP_STOREC: o[op.y] = __ldg(consts + op.w); break;
+      }
+    }
+  }
+}
+
+struct TapeDev {
+  Tape tape;
+  DevBuf<uint4> ops;
+  DevBuf<double> consts;
+};
+static std::mutex g_tape_mu;
+static std::map<std::vector<int>, TapeDev*> g_tapes;
+
+static TapeDev* get_tape(fq_ctx* ctx, int dim, const std::vector<BlockSpec>& blocks) {
+  std::vector<int> key{ctx->device, dim};
+  for (const BlockSpec& b : blocks) key.push_back(b.kind), key.push_back(b.grade);
+  std::lock_guard<std::mutex> lk(g_tape_mu);
+  auto it = g_tapes.find(key);
+  if (it != g_tapes.end()) return it->second;
+  TapeDev* td = new TapeDev;
+  td->tape = build_tape(dim, blocks, nullptr);
+  std::vector<uint4> hops;
+  for (const TapeOp& o : td->tape.ops) hops.push_back(make_uint4(o.op, o.d, o.a, o.b));
+  td->ops.alloc(hops.size() ? hops.size() : 1);
+  td->consts.alloc(td->tape.consts.size() ? td->tape.consts.size() : 1);
+  if (!hops.empty()) FQ_CUDA(cudaMemcpy(td->ops.p, hops.data(), hops.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  if (!td->tape.consts.empty())
+    FQ_CUDA(cudaMemcpy(td->consts.p, td->tape.consts.data(), td->tape.consts.size() * sizeof(double),
+                       cudaMemcpyHostToDevice));
+  g_tapes[key] = td;
+  return td;
+}
+
+int elmat_to_slab(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>& blocks, size_t c0, size_t c1,
+                  bool use_generated, double* d_out, int* d_err) {
+  const int dim = mesh->dim;
+  FQ_REQUIRE(dim >= 1 && dim <= kMaxDim, "element kernels support 1 <= dim <= 10");
+  FQ_REQUIRE(c0 <= c1 && c1 <= mesh->ncells, "cell range out of bounds");
+  const int nouts = elmat_nouts(dim, blocks);
+  if (c1 == c0 || nouts == 0) return nouts;
+  if (use_generated) {
+    if (const GenEntry* e = find_generated(dim, blocks)) {
+      e->launch(ctx, mesh, c0, c1, d_out);
+      return nouts;
+    }
+  }
+  TapeDev* td = get_tape(ctx, dim, blocks);
+  const Tape& t = td->tape;
+  FQ_REQUIRE(t.nouts <= nouts, "tape output count mismatch");
+  const int block = 128;
+  // bound the scratch slab: at most ~256 MB of interpreter registers
+  size_t max_threads = (size_t(256) << 20) / (sizeof(double) * size_t(t.nregs > 0 ? t.nregs : 1));
+  max_threads = max_threads / block * block;
+  if (max_threads < size_t(block)) max_threads = block;
+  size_t want = ((c1 - c0) + block - 1) / block * block;
+  const size_t cap = size_t(ctx->sm_count) * 8 * block;
+  if (want > cap) want = cap;
+  if (want > max_threads) want = max_threads;
+  DevBuf<double> scratch(want * size_t(t.nregs > 0 ? t.nregs : 1));
+  const int ne = int(binom(dim + 1, 2));
+  elmat_interp_kernel<<<int(want / block), block, 0, ctx->stream>>>(
+      td->ops.p, int(t.ops.size()), td->consts.p, t.ninputs, t.inputs_are_lengths ? 1 : 0, dim, ne,
+      mesh->cell_faces[1].p, mesh->lengths.p, uint32_t(mesh->edge_lo), c0, c1 - c0, scratch.p, nouts, d_out, d_err);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch is freed on return
+  return nouts;
+}
+
+}  // namespace fq

@@ -1,0 +1,52 @@
+// internal.hpp — functions shared between the translation units of the library.
+#pragma once
+#include "common.cuh"
+
+namespace fq {
+
+// ---- elmat.cu
+// Element matrices of cells [c0, c1) (local cell indices) of one block or of
+// the fused blocks of hodge_blocks(k) into a device slab, AoS:
+// out[(c - c0) * nouts + e].  Returns nouts.
+int elmat_to_slab(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>& blocks, size_t c0, size_t c1,
+                  bool use_generated, double* d_out, int* d_err);
+int elmat_nouts(int dim, const std::vector<BlockSpec>& blocks);
+bool elmat_has_generated(int dim, const std::vector<BlockSpec>& blocks);
+
+// ---- kuhn.cu
+void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vmin, const double* vmax,
+                     const double* ambient_diag, double jitter, size_t slab_begin, size_t slab_end, fq_mesh* mesh);
+
+// ---- assemble.cu
+void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
+                       fq_csr* out);
+void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros);
+
+// ---- spmv.cu
+void spmv_prepare(fq_ctx* ctx, fq_csr* a);
+void spmv_apply(fq_ctx* ctx, const fq_csr* a, const double* x, double* y);
+void csr_build_inv_diag(fq_ctx* ctx, fq_csr* a);
+
+// ---- blas1.cu
+double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n);
+void vec_scale(fq_ctx* ctx, double* x, double alpha, size_t n);
+void vec_axpy(fq_ctx* ctx, double* y, double alpha, const double* x, size_t n);
+void vec_mul_pointwise(fq_ctx* ctx, double* z, const double* d, const double* r, size_t n);
+
+// ---- krylov.cu
+struct KrylovReport {
+  size_t iters = 0;
+  double residual = 0.0;
+  bool converged = false;
+};
+KrylovReport krylov_cg(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x);
+KrylovReport krylov_minres(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters,
+                           fq_vec* x);
+
+inline int grid_for(size_t n, int block, int sm_count, int ctas_per_sm = 8) {
+  const size_t want = (n + size_t(block) - 1) / size_t(block);
+  const size_t cap = size_t(sm_count) * size_t(ctas_per_sm);
+  return int(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace fq

@@ -1,0 +1,164 @@
+/* formoniq_b200.h — C ABI of the B200-native Galerkin-assembly path.
+ *
+ * This is the drop-in boundary for luiswirth/formoniq's assembly hot path.
+ * The reference has no FFI of its own (pure Rust traits); each entry point
+ * below names the reference interface it replaces (paths relative to the
+ * reference checkout).  A Rust shim binds these with a plain `extern "C"`
+ * block (see INTEGRATION.md and rust/formoniq-b200-sys/).
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; the message is
+ *    available from fq_last_error() (thread-local).  Nothing unwinds across
+ *    the ABI.
+ *  - handles are opaque and owned by the library; host buffers are owned by
+ *    the caller.  Index arrays crossing the ABI are 64-bit (`usize` on the
+ *    reference's targets), values are IEEE-754 binary64.
+ *  - there is NO CPU fallback: every compute entry point needs a CUDA device
+ *    and fails with FQ_ERR_CUDA when none is usable.
+ */
+#ifndef FORMONIQ_B200_H
+#define FORMONIQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQ_OK 0
+#define FQ_ERR_INVALID (-1)  /* bad argument / contract violation (the reference panics) */
+#define FQ_ERR_CUDA (-2)     /* CUDA runtime failure or no device */
+#define FQ_ERR_DEGENERATE (-3) /* a cell metric was singular (Metric::dual's expect) */
+#define FQ_ERR_UNSUPPORTED (-4)
+
+typedef struct fq_ctx fq_ctx;
+typedef struct fq_mesh fq_mesh;
+typedef struct fq_csr fq_csr;
+typedef struct fq_vec fq_vec;
+
+/* formoniq/src/operators.rs:169-191 (the four WhitneyPairing constructors) and
+ * :27-40 (ScalarLumpedMass).  `grade` is always the grade of the inner
+ * product, as in the reference (operators.rs:131-133). */
+enum fq_kind { FQ_MASS = 0, FQ_DIF_TRIAL = 1, FQ_DIF_TEST = 2, FQ_DIF_BOTH = 3, FQ_LUMPED = 4 };
+
+const char* fq_last_error(void);
+/* number of visible CUDA devices (0 when there is none) */
+int fq_device_count(void);
+
+/* ---- context -------------------------------------------------------------
+ * One context per device and host thread.  All work is enqueued on the
+ * context's stream; fq_ctx_set_stream adopts a caller-owned cudaStream_t
+ * (e.g. torch's current stream) so callers can bracket work with their own
+ * events.  rank/nranks describe the owner-computes row partition used by the
+ * multi-GPU entry points (1 process per GPU). */
+int fq_ctx_create(int device, fq_ctx** out);
+int fq_ctx_destroy(fq_ctx* ctx);
+int fq_ctx_set_stream(fq_ctx* ctx, void* cuda_stream);
+int fq_ctx_synchronize(fq_ctx* ctx);
+/* kernels launched by this context so far (for bench.py's gpu_launches) */
+int64_t fq_ctx_launch_count(const fq_ctx* ctx);
+
+/* ---- mesh ----------------------------------------------------------------
+ * What `Complex` + `MeshLengthsSq` expose to assembly:
+ *   cell_faces[j]  = FaceIncidence::faces_flat of grade j, cell-major with
+ *                    stride C(dim+1, j+1)  (simplicial/src/topology/incidence.rs:42-53)
+ *                    entries may be NULL for grades the caller will not use;
+ *                    grade 1 is required (edge lengths are gathered through it)
+ *   edge_lengths_sq = MeshLengthsSq (regge/src/lengths/mesh.rs:34-36), one
+ *                    signed squared length per edge of the 1-skeleton. */
+int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices /*[dim+1]*/,
+                   const uint64_t* const* cell_faces /*[dim+1]*/, const double* edge_lengths_sq, fq_mesh** out);
+/* Kuhn triangulation of a box grid generated on the device with the
+ * reference's colex skeleton numbering (simplicial/src/mesher/grid.rs:77-103,
+ * regge/src/mesher/cartesian.rs:158-169,192-208, regge/src/coord/mesh.rs:208-216).
+ *   shape[a]  cells along axis a;  vmin/vmax the box;  ambient_diag the diagonal
+ *   ambient form (+1 Euclid, -1 for a time axis);  jitter displaces every vertex
+ *   by jitter*h_a*pseudo_random(seed=a, index=v) (formoniq/src/linalg/eigen.rs:259-268).
+ * slab_begin/slab_end restrict the boxes along the LAST axis to
+ * [slab_begin, slab_end) (owner-computes partition); pass 0, shape[dim-1] for
+ * the whole grid.  Simplex ids stay global. */
+int fq_mesh_create_kuhn(fq_ctx* ctx, int dim, const size_t* shape, const double* vmin, const double* vmax,
+                        const double* ambient_diag, double jitter, size_t slab_begin, size_t slab_end,
+                        fq_mesh** out);
+int fq_mesh_destroy(fq_mesh* mesh);
+int fq_mesh_dim(const fq_mesh* mesh);
+size_t fq_mesh_ncells(const fq_mesh* mesh);
+size_t fq_mesh_nsimplices(const fq_mesh* mesh, int grade);
+/* replace the geometry (MeshLengthsSq) of an existing mesh */
+int fq_mesh_set_lengths(fq_ctx* ctx, fq_mesh* mesh, const double* edge_lengths_sq);
+/* copy device-side tables back (parity hooks for the generator) */
+int fq_mesh_download_cell_faces(fq_ctx* ctx, const fq_mesh* mesh, int grade, uint64_t* out);
+int fq_mesh_download_lengths(fq_ctx* ctx, const fq_mesh* mesh, double* out);
+/* Host-only evaluation of the closed-form Kuhn numbering (no device needed):
+ * fills cell_faces of one grade for the whole grid.  Useful to build a
+ * reference-side `Complex` without its hash-based `from_cells`. */
+int fq_kuhn_cell_faces_host(int dim, const size_t* shape, int grade, uint64_t* out);
+int fq_kuhn_counts(int dim, const size_t* shape, size_t* nsimplices /*[dim+1]*/);
+
+/* ---- element matrices ------------------------------------------------------
+ * BilinearForm::element for a batch of cells (formoniq/src/galerkin.rs:50,
+ * operators.rs:84-94,201-211).  out is host memory, row-major
+ * [cell_end-cell_begin][rows][cols].  use_generated=0 forces the generic tape
+ * interpreter (any dim/grade); 1 uses the straight-line kernel when one was
+ * generated for (dim, kind, grade) and the interpreter otherwise. */
+int fq_elmat_shape(int dim, int kind, int grade, int* rows, int* cols);
+int fq_elmat_batch(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t cell_begin, size_t cell_end,
+                   int use_generated, double* out);
+
+/* ---- assembly --------------------------------------------------------------
+ * BilinearForm::assemble / assemble_matrix (formoniq/src/galerkin.rs:52-57,
+ * 138-188) split into a symbolic phase (pattern + cell-slot -> nnz map, once
+ * per mesh and block) and a numeric phase (values; the hot path).
+ * Rows [row_begin,row_end) of the global matrix are assembled (owner-computes;
+ * pass 0, SIZE_MAX for all rows).
+ * drop_exact_zeros=1 reproduces the reference's `val != 0.0` triplet filter
+ * (galerkin.rs:173): an entry exists iff some contribution is non-zero. */
+int fq_assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
+                         fq_csr** out);
+int fq_assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, int drop_exact_zeros);
+/* one-shot convenience: symbolic + numeric */
+int fq_assemble(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, int drop_exact_zeros, fq_csr** out);
+
+/* ---- CSR matrices ----------------------------------------------------------
+ * The data contract of nalgebra_sparse::CsrMatrix<f64> handed to faer by
+ * formoniq/src/linalg/faer.rs:16-24: row_offsets[nrows+1], col_indices strictly
+ * ascending within a row, values. */
+int fq_csr_shape(const fq_csr* csr, size_t* nrows, size_t* ncols, size_t* nnz);
+int fq_csr_row_range(const fq_csr* csr, size_t* row_begin, size_t* row_end);
+int fq_csr_download(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t* col_indices, double* values);
+int fq_csr_upload(fq_ctx* ctx, size_t nrows, size_t ncols, const size_t* row_offsets, const size_t* col_indices,
+                  const double* values, fq_csr** out);
+int fq_csr_destroy(fq_csr* csr);
+/* algorithmic HBM bytes of the last numeric assembly / of one SpMV */
+int64_t fq_csr_assembly_bytes(const fq_csr* csr);
+int64_t fq_csr_spmv_bytes(const fq_csr* csr);
+
+/* ---- vectors: iterative::InnerProductSpace (iterative/src/lib.rs:84-141) ---- */
+int fq_vec_create(fq_ctx* ctx, size_t n, fq_vec** out); /* zeros_like */
+int fq_vec_destroy(fq_vec* v);
+size_t fq_vec_len(const fq_vec* v);
+int fq_vec_upload(fq_ctx* ctx, fq_vec* v, const double* host);
+int fq_vec_download(fq_ctx* ctx, const fq_vec* v, double* host);
+int fq_vec_copy(fq_ctx* ctx, fq_vec* dst, const fq_vec* src);                  /* clone */
+int fq_vec_dot(fq_ctx* ctx, const fq_vec* x, const fq_vec* y, double* out);   /* dot   */
+int fq_vec_scale(fq_ctx* ctx, fq_vec* x, double alpha);                        /* scale */
+int fq_vec_axpy(fq_ctx* ctx, fq_vec* y, double alpha, const fq_vec* x);       /* add_scaled */
+/* raw device pointer (for zero-copy interop with torch / NCCL plumbing) */
+void* fq_vec_device_ptr(fq_vec* v);
+
+/* ---- SpMV: iterative::LinearOperator::apply (iterative/src/operator.rs:5-14) ---- */
+int fq_spmv(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, fq_vec* y);
+
+/* ---- Krylov drivers on device vectors (iterative/src/krylov.rs:48-95, 113-211).
+ * precond: 0 identity (iterative/src/precond.rs:16-41), 1 Jacobi (:113-121).
+ * report: iters, residual, converged (iterative/src/lib.rs:212-219). */
+int fq_cg(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
+          size_t* iters, double* residual, int* converged);
+int fq_minres(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
+              size_t* iters, double* residual, int* converged);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORMONIQ_B200_H */

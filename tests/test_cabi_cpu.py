@@ -1,0 +1,98 @@
+"""CPU-side checks of the product's host logic and C ABI (no GPU compute):
+the shared library loads and exports every symbol include/formoniq_b200.h
+declares, the tape compiler reproduces the oracle bit for bit, the closed-form
+Kuhn numbering equals the reference's sort+dedup numbering, and compute entry
+points fail loudly without a device."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fq():
+    from formoniq_b200 import build
+
+    build.build()
+    import formoniq_b200
+
+    return formoniq_b200
+
+
+def test_library_exports_every_declared_symbol(fq):
+    from formoniq_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "formoniq_b200.h")).read()
+    declared = set(re.findall(r"\b(fq_[a-z0-9_]+)\s*\(", header))
+    declared -= {"fq_ctx", "fq_mesh", "fq_csr", "fq_vec", "fq_kind"}
+    bound = {name for name, _, _ in _lib.SIGNATURES}
+    assert declared == bound, (declared - bound, bound - declared)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_tape_compiler_matches_oracle_bitwise(tmp_path):
+    exe = tmp_path / "tape_host_check"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-ffp-contract=off",
+                           os.path.join(ROOT, "tests", "cpp", "tape_host_check.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.startswith("OK "), out.stdout
+    assert int(out.stdout.split()[1]) > 10000
+
+
+def test_kuhn_closed_form_numbering_matches_reference_construction(fq):
+    from oracle import oracle as O
+
+    for dim, shape in ((1, [3]), (2, [2, 3]), (2, [4, 4]), (3, [2, 3, 2]), (3, [3, 3, 3]), (4, [2, 1, 2, 2]),
+                       (5, [1, 2, 1, 1, 2])):
+        cx = O.Complex.kuhn(dim, shape)
+        assert fq.kuhn_counts(dim, shape) == [cx.nsimplices(j) for j in range(dim + 1)]
+        for j in range(dim + 1):
+            got = fq.kuhn_cell_faces_host(dim, shape, j).astype(np.int64)
+            assert np.array_equal(got, cx.cell_faces(j)), (dim, shape, j)
+
+
+def test_kuhn_counts_polynomials(fq):
+    # V=(N+1)^3, E=7N^3+9N^2+3N, F=12N^3+6N^2, C=6N^3
+    for N in (1, 2, 5, 128):
+        assert fq.kuhn_counts(3, N) == [(N + 1) ** 3, 7 * N ** 3 + 9 * N ** 2 + 3 * N, 12 * N ** 3 + 6 * N ** 2, 6 * N ** 3]
+    for N in (1, 3, 16):
+        assert fq.kuhn_counts(4, N) == [(N + 1) ** 4, 15 * N ** 4 + 28 * N ** 3 + 18 * N ** 2 + 4 * N,
+                                        50 * N ** 4 + 48 * N ** 3 + 12 * N ** 2, 60 * N ** 4 + 24 * N ** 3, 24 * N ** 4]
+
+
+def test_interface_mirrors_reference_grades(fq):
+    # operators.rs:195-200: a differentiated side sits one grade below
+    W = fq.WhitneyPairing
+    assert (W.mass(3, 1).test_grade(), W.mass(3, 1).trial_grade()) == (1, 1)
+    assert (W.dif_trial(3, 1).test_grade(), W.dif_trial(3, 1).trial_grade()) == (1, 0)
+    assert (W.dif_test(3, 1).test_grade(), W.dif_test(3, 1).trial_grade()) == (0, 1)
+    assert (W.dif_both(3, 2).test_grade(), W.dif_both(3, 2).trial_grade()) == (1, 1)
+    assert W.dif_test(3, 1).element_shape() == (4, 6)
+    assert fq.ScalarLumpedMass(3).element_shape() == (4, 4)
+
+
+def test_no_cpu_fallback(fq):
+    from formoniq_b200 import _lib
+
+    if _lib.lib().fq_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(fq.FormoniqError):
+        fq.Context(0)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "formoniq_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                text = open(os.path.join(dp, f), errors="replace").read()
+                assert "fq_oracle" not in text and "liboracle" not in text and "import oracle" not in text and \
+                    "from oracle" not in text, os.path.join(dp, f)

@@ -1,0 +1,338 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+on the same seeded inputs.  Bit-exact for index work (row_ptr / col_idx, mesh
+tables); values within 1e-12 relative (north-star tolerance) — and, for dim <= 3
+where the operation order is pinned, bitwise up to the sign of zero."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import all_blocks, kuhn_problem, mesh_from_oracle, same_bits_mod_zero_sign
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # north_star: values within 1e-12 relative in FP64
+
+
+@pytest.fixture(scope="module")
+def fq():
+    import formoniq_b200
+
+    return formoniq_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(fq):
+    return fq.Context(0)
+
+
+def assert_values_close(got, exp, rtol=RTOL):
+    scale = max(np.abs(exp).max(), 1e-300) if exp.size else 1.0
+    assert np.abs(got - exp).max(initial=0.0) <= rtol * scale
+
+
+# ------------------------------------------------------------------ element matrices
+@pytest.mark.parametrize("dim,shape,variant", [
+    (1, [5], "plain"), (2, [4, 4], "plain"), (2, [5, 3], "jitter"), (2, [4, 4], "minkowski"),
+    (3, [4, 4, 4], "plain"), (3, [3, 3, 3], "plain"), (3, [3, 2, 3], "jitter"), (3, [3, 3, 3], "minkowski"),
+    (4, [2, 2, 2, 2], "plain"), (4, [2, 1, 2, 1], "jitter"), (5, [1, 1, 1, 1, 1], "jitter"),
+])
+def test_elmat_parity(fq, ctx, dim, shape, variant):
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    blocks = all_blocks(dim) + [(O.LUMPED, 0)]
+    if dim >= 5:
+        blocks = [(kind, k) for kind, k in blocks if k <= 2]
+    for kind, k in blocks:
+        form = fq.ScalarLumpedMass(dim) if kind == O.LUMPED else fq.WhitneyPairing(dim, k, kind)
+        exp = cx.elmat_batch(s, kind, k)
+        for use_generated in (True, False):
+            got = form.element_batch(mesh, use_generated=use_generated)
+            assert got.shape == exp.shape
+            assert_values_close(got, exp)
+            # the zero / non-zero classification decides the CSR pattern (galerkin.rs:173)
+            assert np.array_equal(got != 0.0, exp != 0.0), (dim, kind, k, use_generated)
+            if dim <= 3:
+                assert same_bits_mod_zero_sign(got, exp), (dim, kind, k, use_generated)
+
+
+def test_reference_cell_goldens_through_the_gpu(fq, ctx):
+    # unit_elmat.rs:31-90: dif_both(dim,1), mass(dim,0), lumped on the unit simplex, dims 1..10
+    for dim in range(1, 11):
+        ns = [math.comb(dim + 1, j + 1) for j in range(dim + 1)]
+        faces = [np.arange(ns[j], dtype=np.uint64).reshape(1, -1) for j in range(dim + 1)]
+        mesh = fq.Mesh.from_arrays(ctx, dim, ns, faces, O.unit_simplex_lengths_sq(dim))
+        lap = np.zeros((dim + 1, dim + 1))
+        lap[0, 0] = dim
+        for i in range(1, dim + 1):
+            lap[i, 0] = lap[0, i] = -1
+            lap[i, i] = 1
+        vol = 1.0 / math.factorial(dim)
+        got = fq.WhitneyPairing.dif_both(dim, 1).element_batch(mesh)[0]
+        assert np.abs(got - lap * vol).max() <= 4e-16 * dim * vol * dim
+        nv = dim + 1
+        q = (np.ones((nv, nv)) + np.eye(nv)) / (nv * (nv + 1))
+        got = fq.WhitneyPairing.mass(dim, 0).element_batch(mesh)[0]
+        assert np.abs(got - q * vol).max() <= 4e-16 * vol
+        got = fq.ScalarLumpedMass(dim).element_batch(mesh)[0]
+        assert np.abs(got - np.eye(nv) * vol / nv).max() <= 4e-16 * vol
+
+
+def test_hodge_mass_dim2_grade1_golden(fq, ctx):
+    # operators.rs:931-975 on the GPU, exact zeros included
+    faces = [np.arange(3, dtype=np.uint64).reshape(1, -1), np.arange(3, dtype=np.uint64).reshape(1, -1),
+             np.zeros((1, 1), dtype=np.uint64)]
+    mesh = fq.Mesh.from_arrays(ctx, 2, [3, 3, 1], faces, O.unit_simplex_lengths_sq(2))
+    eps = np.finfo(float).eps
+    got = fq.WhitneyPairing.mass(2, 1).element_batch(mesh)[0]
+    exp = np.array([[1 / 3, 1 / 6, 0], [1 / 6, 1 / 3, 0], [0, 0, 1 / 6]])
+    assert np.abs(got - exp).max() <= eps and np.array_equal(got == 0, exp == 0)
+    got = fq.WhitneyPairing.dif_trial(2, 1).element_batch(mesh)[0]
+    assert np.abs(got - np.array([[-1 / 2, 1 / 3, 1 / 6], [-1 / 2, 1 / 6, 1 / 3], [0, -1 / 6, 1 / 6]])).max() <= eps
+    got = fq.WhitneyPairing.dif_test(2, 1).element_batch(mesh)[0]
+    assert np.abs(got - np.array([[-1 / 2, -1 / 2, 0], [1 / 3, 1 / 6, -1 / 6], [1 / 6, 1 / 3, 1 / 6]])).max() <= eps
+
+
+def test_degenerate_and_invalid_inputs(fq, ctx):
+    # contract violations return errors instead of panicking across the ABI
+    cx, s, *_ = kuhn_problem(2, [2, 2])
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    with pytest.raises(fq.FormoniqError):
+        fq.WhitneyPairing.mass(3, 1).assemble(mesh)  # assert_eq!(self.dim, metric.dim())
+    with pytest.raises(fq.FormoniqError):
+        fq.WhitneyPairing.mass(2, 1).element_batch(mesh, 0, cx.ncells + 1)
+    with pytest.raises(fq.FormoniqError):
+        fq.Mesh.from_arrays(ctx, 2, [9, 16, 8], [cx.cell_faces(0), cx.cell_faces(1), cx.cell_faces(2)], s[:-1])
+
+
+# ------------------------------------------------------------------ Kuhn generator
+@pytest.mark.parametrize("dim,shape,variant", [
+    (1, [4], "plain"), (2, [3, 5], "plain"), (2, [4, 4], "minkowski"), (3, [3, 2, 4], "jitter"),
+    (3, [4, 4, 4], "plain"), (3, [3, 3, 3], "minkowski"), (4, [2, 2, 1, 2], "jitter"),
+])
+def test_device_kuhn_generator_matches_reference_numbering(fq, ctx, dim, shape, variant):
+    cx, s, coords, diag, vmax = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = fq.Mesh.kuhn(ctx, dim, shape, vmax=vmax, ambient_diag=diag, jitter=0.2 if variant == "jitter" else 0.0)
+    assert mesh.ncells == cx.ncells
+    for j in range(dim + 1):
+        assert mesh.nsimplices(j) == cx.nsimplices(j)
+        assert np.array_equal(mesh.cell_faces(j).astype(np.int64), cx.cell_faces(j)), j
+    got = mesh.lengths()
+    assert np.array_equal(got, s)  # bit-exact: the pattern depends on these bits
+
+
+def test_device_kuhn_slab_is_a_window_of_the_global_mesh(fq, ctx):
+    shape = [3, 2, 6]
+    cx, s, coords, diag, vmax = kuhn_problem(3, shape, jitter=True)
+    per_layer = 6 * 3 * 2
+    for sb, se in ((0, 2), (2, 5), (5, 6)):
+        mesh = fq.Mesh.kuhn(ctx, 3, shape, jitter=0.2, slab=(sb, se))
+        assert mesh.ncells == per_layer * (se - sb)
+        for j in range(4):
+            assert np.array_equal(mesh.cell_faces(j).astype(np.int64), cx.cell_faces(j)[per_layer * sb:per_layer * se])
+        got = mesh.lengths()
+        used = np.unique(cx.cell_faces(1)[per_layer * sb:per_layer * se])
+        assert np.array_equal(got[used], s[used])
+
+
+# ------------------------------------------------------------------ assembly
+ASSEMBLY_CASES = [
+    # BASELINE configs[0]: 2-D Hodge-Laplace k=1 blocks
+    (2, [8, 8], "plain", 1), (2, [5, 5], "plain", 1), (2, [6, 4], "jitter", 1),
+    # configs[1]: 3-D k=1 mixed (AFW)
+    (3, [4, 4, 4], "plain", 1), (3, [3, 3, 3], "plain", 1), (3, [3, 4, 2], "jitter", 1), (3, [3, 3, 3], "jitter", 2),
+    # configs[2]: 4-D k=2
+    (4, [2, 2, 2, 2], "jitter", 2), (4, [2, 2, 2, 2], "plain", 2),
+    # configs[3]: 2+1 Minkowski (Lorentzian lengths), all masses + k=1 blocks
+    (3, [3, 3, 3], "minkowski", 1), (3, [4, 4, 4], "minkowski", 2),
+]
+
+
+@pytest.mark.parametrize("dim,shape,variant,k", ASSEMBLY_CASES)
+def test_assembly_pattern_bit_exact_and_values(fq, ctx, dim, shape, variant, k):
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    blocks = [(O.MASS, k - 1), (O.MASS, k), (O.DIF_TEST, k), (O.DIF_BOTH, k + 1), (O.DIF_TRIAL, k)]
+    if variant == "minkowski":
+        blocks += [(O.MASS, g) for g in range(dim + 1)]  # dirac.rs:216 assembles M_0..M_n
+    for kind, g in blocks:
+        for drop in (True, False):
+            ref = cx.assemble(s, kind, g, drop_zeros=drop)
+            got = fq.WhitneyPairing(dim, g, kind).assemble(mesh, drop_exact_zeros=drop)
+            assert got.shape == (ref.nrows, ref.ncols)
+            rp, ci, va = got.download()
+            erp, eci, eva = ref.arrays()
+            assert np.array_equal(rp.astype(np.int64), erp), (kind, g, drop)   # bit-exact pattern
+            assert np.array_equal(ci.astype(np.int64), eci), (kind, g, drop)
+            assert_values_close(va, eva)
+            if dim <= 3:
+                assert same_bits_mod_zero_sign(va, eva), (kind, g, drop)
+
+
+def test_assembly_empty_spaces_have_the_right_shape(fq, ctx):
+    # whitney_complex.rs:113-122: grades off [0,n] give correctly shaped empty matrices
+    cx, s, *_ = kuhn_problem(2, [3, 3])
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    m = fq.WhitneyPairing.mass(2, -1).assemble(mesh)
+    assert m.shape == (0, 0) and m.nnz == 0
+    m = fq.WhitneyPairing.dif_test(2, 0).assemble(mesh)
+    assert m.shape == (0, cx.nsimplices(0)) and m.nnz == 0
+    m = fq.WhitneyPairing.dif_both(2, 3).assemble(mesh)
+    assert m.shape == (cx.nsimplices(2), cx.nsimplices(2)) and m.nnz == 0
+    hb = fq.HodgeBlocks.compute(mesh, 0)
+    assert hb.n_sigma == 0 and hb.mass_sigma.shape == (0, 0) and hb.mass_u.shape == (9 + 7, 9 + 7)[:1] * 2
+
+
+def test_row_range_assembly_equals_rows_of_the_global_matrix(fq, ctx):
+    # owner-computes rows: any row block is bit-identical to the same rows of the full matrix
+    cx, s, *_ = kuhn_problem(3, [3, 3, 4], jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    for kind, g in ((O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2)):
+        ref = cx.assemble(s, kind, g).to_scipy()
+        form = fq.WhitneyPairing(3, g, kind)
+        nrows = ref.shape[0]
+        for b, e in ((0, nrows // 3), (nrows // 3, nrows - 5), (nrows - 5, nrows)):
+            part = form.symbolic(mesh, b, e)
+            part.numeric(mesh)
+            got = part.to_scipy()
+            exp = ref[b:e]
+            assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+            assert np.array_equal(got.data, exp.data)
+
+
+def test_numeric_phase_can_be_rerun_with_new_geometry(fq, ctx):
+    cx, s, *_ = kuhn_problem(3, [3, 3, 3])
+    _, s2, *_ = kuhn_problem(3, [3, 3, 3], jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    form = fq.WhitneyPairing.mass(3, 1)
+    a = form.symbolic(mesh)
+    a.numeric(mesh)
+    assert a.nnz == cx.assemble(s, O.MASS, 1).nnz
+    mesh.set_lengths(s2)
+    a.numeric(mesh)
+    ref = cx.assemble(s2, O.MASS, 1)
+    rp, ci, va = a.download()
+    assert a.nnz == ref.nnz and np.array_equal(ci.astype(np.int64), ref.arrays()[1]) and np.array_equal(va, ref.arrays()[2])
+
+
+def test_fem3d_and_fdm_through_the_gpu(fq, ctx):
+    # tests/fem3d.rs:9-16 and tests/fdm.rs:172-185 with the GPU as the assembler
+    from tests.test_oracle_goldens import fem3d_galmat, kron_sum_laplacian
+
+    for N in (1, 2, 3):
+        mesh = fq.Mesh.kuhn(ctx, 3, N)
+        feec = fq.WhitneyPairing.dif_both(3, 1).assemble(mesh).to_scipy().toarray()
+        assert np.abs(feec - fem3d_galmat(N)).max() <= 1e-12
+    for dim in (1, 2, 3, 4):
+        N = 2
+        Nb = N + 2
+        mesh = fq.Mesh.kuhn(ctx, dim, Nb, vmax=[float(Nb)] * dim)
+        A = fq.WhitneyPairing.dif_both(dim, 1).assemble(mesh).to_scipy().toarray()
+        M = fq.WhitneyPairing.mass(dim, 0).assemble(mesh).to_scipy().toarray()
+        A = A / (M @ np.ones(M.shape[0]))[:, None]
+        nvd = Nb + 1
+        idx = np.arange(nvd ** dim)
+        interior = np.ones(nvd ** dim, bool)
+        for a in range(dim):
+            c = (idx // nvd ** a) % nvd
+            interior &= (c != 0) & (c != Nb)
+        A = A[np.ix_(interior, interior)]
+        assert np.array_equal(np.round(A).astype(int), kron_sum_laplacian(dim, N + 1)) and np.abs(A - np.round(A)).max() < 1e-11
+
+
+# ------------------------------------------------------------------ SpMV / BLAS-1 / Krylov
+def probe(n):
+    return np.array([((7 * i) % 13) - 6 for i in range(n)], float)  # matfree.rs:205-207
+
+
+def test_spmv_bitwise_against_serial_reference(fq, ctx):
+    for dim, shape in ((2, [9, 7]), (3, [4, 5, 3])):
+        cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+        mesh = mesh_from_oracle(fq, ctx, cx, s)
+        for kind, g in ((O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2), (O.MASS, 0)):
+            ref = cx.assemble(s, kind, g)
+            a = fq.WhitneyPairing(dim, g, kind).assemble(mesh)
+            x = probe(ref.ncols) * 0.37 + np.cos(np.arange(ref.ncols) ** 2 + 1.0)  # hx.rs:107
+            y = a.apply(fq.DeviceVector.from_numpy(ctx, x)).to_numpy()
+            assert np.array_equal(y, ref.spmv(x))  # same order, no FMA -> same bits
+            assert_values_close(y, ref.to_scipy() @ x)
+
+
+def test_spmv_uploaded_matrix_and_long_rows(fq, ctx):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    m = sp.random(300, 5000, density=0.3, random_state=7, format="csr")  # rows ~1500 nnz and a dense row
+    m = sp.vstack([m, sp.csr_matrix(np.ones((1, 5000)))]).tocsr()
+    a = fq.DeviceCsr.from_scipy(ctx, m)
+    x = rng.normal(size=5000)
+    y = a.apply(fq.DeviceVector.from_numpy(ctx, x)).to_numpy()
+    exp = m @ x
+    assert np.abs(y - exp).max() <= 1e-12 * np.abs(exp).max()
+    rp, ci, va = a.download()
+    assert np.array_equal(rp.astype(np.int64), m.indptr) and np.array_equal(ci.astype(np.int64), m.indices)
+
+
+def test_inner_product_space(fq, ctx):
+    # iterative/src/lib.rs:84-141
+    n = 100003
+    x, y = probe(n) / 7.0, np.cos(np.arange(n) * 0.1)
+    dx, dy = fq.DeviceVector.from_numpy(ctx, x), fq.DeviceVector.from_numpy(ctx, y)
+    assert abs(dx.dot(dy) - x @ y) <= 1e-12 * np.abs(x * y).sum()
+    assert abs(dx.norm() - np.linalg.norm(x)) <= 1e-13 * np.linalg.norm(x)
+    dy.add_scaled(-0.75, dx)
+    assert np.array_equal(dy.to_numpy(), -0.75 * x + y)
+    dy.scale(3.0)
+    assert np.array_equal(dy.to_numpy(), (-0.75 * x + y) * 3.0)
+    z = dx.zeros_like()
+    assert len(z) == n and not z.to_numpy().any()
+    c = dx.clone()
+    c.add(dx)
+    assert np.array_equal(c.to_numpy(), x + x)
+    assert dx.dot(dy) == dx.dot(dy)  # deterministic reduction
+
+
+def test_cg_and_minres_match_the_cpu_solvers(fq, ctx):
+    # krylov.rs:224-320 laws + solved-field parity (north-star 1e-10 relative)
+    cx, s, *_ = kuhn_problem(3, [4, 4, 4], jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    ref = cx.assemble(s, O.MASS, 1)
+    a = fq.WhitneyPairing.mass(3, 1).assemble(mesh)
+    b = np.array([(i % 7) - 3.0 for i in range(ref.nrows)])  # elliptic.rs:270
+    db = fq.DeviceVector.from_numpy(ctx, b)
+    exact = np.linalg.solve(ref.to_scipy().toarray(), b)
+    for solver, osolver in ((fq.cg, ref.cg), (fq.minres, ref.minres)):
+        for pc, opc in ((None, 0), ("jacobi", 1)):
+            x, rep = solver(a, pc, db, fq.StopCriterion(1e-13))
+            ox, orep = osolver(b, rtol=1e-13, precond=opc)
+            assert rep.converged and orep["converged"]
+            assert abs(rep.iters - orep["iters"]) <= 2
+            xs = x.to_numpy()
+            assert np.abs(xs - ox).max() <= 1e-10 * np.abs(ox).max()
+            assert np.abs(xs - exact).max() <= 1e-10 * np.abs(exact).max()
+    x, rep = fq.cg(a, None, db.zeros_like(), fq.StopCriterion(1e-10))
+    assert rep.iters == 0 and rep.converged and not x.to_numpy().any()
+
+
+def test_mixed_hodge_laplace_solve_parity(fq, ctx):
+    # BASELINE configs[0]: 2-D Hodge-Laplace source problem on 1-forms, mixed system
+    # [[M0, -dif_test],[dif_test^T, dif_both]] solved by MINRES on the device vs a host direct solve.
+    import scipy.sparse.linalg as spla
+
+    cx, s, *_ = kuhn_problem(2, [8, 8], jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    hb = fq.HodgeBlocks.compute(mesh, 1)
+    kkt = hb.mixed_hodge_laplacian()
+    n = kkt.shape[0]
+    # the continuous problem pairs the saddle point with a symmetric sign flip; MINRES needs symmetry:
+    ms, dt, db = hb.mass_sigma.to_scipy(), hb.dif_test.to_scipy(), hb.dif_both.to_scipy()
+    import scipy.sparse as sp
+    sym = sp.bmat([[-ms, dt], [dt.T, db]], format="csr")
+    a = fq.DeviceCsr.from_scipy(ctx, sym)
+    rhs = np.concatenate([np.zeros(hb.n_sigma), hb.mass_u.to_scipy() @ np.array([(i % 7) - 3.0 for i in range(hb.n_u)])])
+    x, rep = fq.minres(a, None, fq.DeviceVector.from_numpy(ctx, rhs), fq.StopCriterion(1e-14, 20000))
+    exact = spla.spsolve(sym.tocsc(), rhs)
+    assert rep.converged
+    assert np.abs(x.to_numpy() - exact).max() <= 1e-10 * np.abs(exact).max()
+    assert n == hb.n_sigma + hb.n_u
