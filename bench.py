@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — the north-star benchmark: Galerkin assembly of the four
+Hodge-Laplace blocks (M_{k-1}, M_k, dif_test(k), dif_both(k+1), k = 1) on a
+synthetic 3-D Kuhn mesh of ~10 M tets per GPU, plus the CSR SpMV, reported as
+elements/s, nnz/s and GB/s next to the CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+A "step" is one numeric assembly pass of the four blocks over the rank's
+cells (reference `!= 0.0` pattern semantics) with mesh tables and the
+cell-slot->nnz maps resident in HBM.  Under torchrun every rank owns a slab
+of box layers of a grid that grows with N (weak scaling); there is no
+collective on the assembly path, the SpMV does one halo exchange per apply.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "assembly_elements_per_s"
+UNIT = "elements/s"
+DIM, GRADE = 3, 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hodge_forms(fq):
+    W = fq.WhitneyPairing
+    return [("mass_sigma", W.mass(DIM, GRADE - 1)), ("mass_u", W.mass(DIM, GRADE)), ("dif_test", W.dif_test(DIM, GRADE)),
+            ("dif_both", W.dif_both(DIM, GRADE + 1))]
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_assembly_sample(sample_n: int | None, budget_s: float = 20.0):
+    """The reference's CPU algorithm (oracle port: per-cell element matrices on
+    all host threads, ordered concat, `!= 0.0` filter, serial COO->CSR) on a
+    bounded Kuhn cube; returns elements/s over the four blocks."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    threads = O.max_threads()
+
+    def run(n):
+        cx = O.Complex.kuhn(DIM, n)
+        s = cx.edge_lengths_sq(O.kuhn_vertex_coords(DIM, n))
+        total, nnz = 0.0, 0
+        for kind, k in ((O.MASS, GRADE - 1), (O.MASS, GRADE), (O.DIF_TEST, GRADE), (O.DIF_BOTH, GRADE + 1)):
+            tm = np.zeros(2)
+            a = cx.assemble(s, kind, k, nthreads=threads, times=tm)
+            total += float(tm.sum())
+            nnz += a.nnz
+        return cx.ncells, nnz, total
+
+    if sample_n is None:
+        cells, _, t = run(12)
+        rate = cells / t
+        sample_n = int(max(12, min(64, (budget_s * rate / 6.0) ** (1.0 / 3.0))))
+        sample_n -= sample_n % 4
+    cells, nnz, t = run(sample_n)
+    return {"value": cells / t, "nnz_per_s": nnz / t, "cores": threads, "seconds": t,
+            "sample": f"3-D Kuhn cube N={sample_n} ({cells} tets), four Hodge blocks k=1, {threads} threads + serial COO->CSR"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_assembly_sample(args.sample_n, budget_s=8.0)
+        if i >= args.warmup:
+            vals.append(last)
+        if args.sample_n is None:  # keep the calibrated size for the remaining steps
+            args.sample_n = int(last["sample"].split("N=")[1].split(" ")[0])
+    value = sum(v["value"] for v in vals) / len(vals)
+    ms = 1e3 * sum(v["seconds"] for v in vals) / len(vals)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3-D Hodge-Laplace k=1 mixed (AFW) assembly, Kuhn unit cube, four blocks; CPU sample of the "
+                               f"N={args.n} per-GPU workload", "sample": last["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "nnz_per_s": sum(v["nnz_per_s"] for v in vals) / len(vals),
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import formoniq_b200 as fq
+    from formoniq_b200.dist import SlabPartition, exchange_halo, slab_of
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    ctx = fq.Context(local, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.n
+    shape = [n, n, n * world]  # weak scaling: one n^3 cube of boxes per GPU
+    slab = slab_of(rank, world, shape[2])
+    mesh = fq.Mesh.kuhn(ctx, DIM, shape, slab=slab)
+    forms = hodge_forms(fq)
+    mats = []
+    ctx.set_timing(True)
+    for name, form in forms:
+        lo, hi = mesh.owned_range(form.test_grade())
+        mats.append((name, form, form.symbolic(mesh, lo, hi)))
+    sym_report = ctx.timing_report()
+    owned_cells = mesh.nowned_cells
+
+    def step():
+        for _, _, a in mats:
+            a.numeric(mesh, True)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.timing_report()
+    sampler = ClockSampler(local)
+    launches0 = ctx.launch_count
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    kern = ctx.timing_report()
+    nnz_local = sum(a.nnz for _, _, a in mats)
+    asm_bytes = sum(a.assembly_bytes for _, _, a in mats)
+
+    # ---- SpMV: every block, K applies each (halo exchange included when world > 1)
+    spmv = []
+    for name, form, a in mats:
+        tg = form.trial_grade()
+        part = SlabPartition(DIM, shape, world, tg)
+        r = part.ranges[rank]
+        xw = torch.cos(torch.arange(r.held_lo, r.held_hi, device="cuda", dtype=torch.float64) ** 2 + 1.0)
+        x = fq.DeviceVector.from_torch(ctx, xw)
+        b, e = a.row_range
+        y = fq.DeviceVector(ctx, e - b)
+        for _ in range(max(args.warmup, 1)):
+            exchange_halo(xw, part, rank)
+            a.apply_window(x, r.held_lo, y)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.timing_report()
+        s0.record(stream)
+        for _ in range(args.steps):
+            exchange_halo(xw, part, rank)
+            a.apply_window(x, r.held_lo, y)
+        s1.record(stream)
+        barrier()
+        kr = ctx.timing_report().get("k4_spmv", {"ms": 0.0, "count": 1})
+        spmv.append({"block": name, "ms": s0.elapsed_time(s1) / args.steps, "kernel_ms": kr["ms"] / max(kr["count"], 1),
+                     "bytes": a.spmv_bytes - 8 * a.shape[1] + 8 * (r.held_hi - r.held_lo), "nnz": a.nnz})
+        del x, y, xw
+
+    # ---- reduce over ranks (max time, sum of work)
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_total = allmax(ms_total)
+    cells_all, nnz_all, bytes_all = allsum(owned_cells), allsum(nnz_local), allsum(asm_bytes)
+    spmv_ms = [allmax(s["ms"]) for s in spmv]
+    spmv_bytes = [allsum(s["bytes"]) for s in spmv]
+    secs = ms_total / 1e3
+    value = cells_all * args.steps / secs
+
+    # ---- e2e through the C ABI with host buffers (rank-local; H2D + symbolic + numeric + D2H per step)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum, barrier)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    # dominant block pipeline (K1 element slab + K3 gather + compaction) for the roofline line
+    per_launch = {k: v["ms"] / max(v["count"], 1) for k, v in kern.items()}
+    asm_kernel_ms = sum(v["ms"] for k, v in kern.items() if k.startswith(("k1", "k3"))) / args.steps
+    achieved = (asm_bytes / 1e9) / (asm_kernel_ms / 1e3) if asm_kernel_ms > 0 else 0.0
+    big = max(range(len(spmv)), key=lambda i: spmv[i]["nnz"])
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3-D Hodge-Laplace k=1 mixed (AFW): numeric assembly of M0, M1, dif_test(1), dif_both(2) "
+                               f"on a Kuhn grid {shape[0]}x{shape[1]}x{shape[2]} ({int(cells_all)} tets, {n}^3 boxes per GPU), "
+                               f"reference `!= 0.0` pattern semantics", "cells_per_gpu": owned_cells,
+                   "l2_policy": "inputs_larger_than_l2 (maps + slabs are GBs per step, L2 is 126 MB)",
+                   "parallelism": f"owner-computes z-slabs x{world}, no collective on the assembly path"},
+        "nnz_per_s": nnz_all * args.steps / secs, "nnz": int(nnz_all),
+        "spmv": {"block": spmv[big]["block"], "gbs": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3),
+                 "ms": spmv_ms[big], "frac_of_hbm_peak": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3) / (peak * world),
+                 "all_blocks_gbs": sum(spmv_bytes) / 1e9 / (sum(spmv_ms) / 1e3),
+                 "halo_exchange": "torch.distributed NCCL send/recv with z-neighbours" if world > 1 else "none (1 GPU)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "numeric assembly pipeline K1 elmat -> K3 gather -> compaction (rank 0, all four blocks)",
+                     "algorithmic_bytes_per_step": asm_bytes, "peak_source": peak_src,
+                     "kernel_ms_per_launch": per_launch},
+        "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in kern.items()},
+        "symbolic_ms": {k: v["ms"] for k, v in sym_report.items()},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    try:
+        cb = cpu_assembly_sample(args.sample_n)
+        out["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
+                               "nnz_per_s": cb["nnz_per_s"]}
+    except Exception as exc:  # the oracle is only the checker; never let it break the GPU line
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum, barrier):
+    """Same metric through the reference-facing C ABI with HOST buffers: per
+    step the mesh tables and edge lengths go host->device from pinned memory
+    (fq_mesh_create), the four blocks are assembled from scratch (symbolic +
+    numeric, like BilinearForm::assemble) and the CSR arrays come back to the
+    host as usize/usize/f64 (fq_csr_download)."""
+    import numpy as np
+    import torch
+
+    n_e2e = min(args.e2e_n, args.n)
+    eshape = [n_e2e, n_e2e, n_e2e]
+    # host-side Complex tables by the closed form (untimed setup), lengths from the device generator
+    gen = fq.Mesh.kuhn(ctx, DIM, eshape)
+    lengths = gen.lengths()
+    ns = fq.kuhn_counts(DIM, eshape)
+    del gen
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    faces_t = [pinned(fq.kuhn_cell_faces_host(DIM, eshape, j).view(np.int64)) for j in range(DIM)] + [None]
+    faces = [None if t is None else t.numpy().view(np.uint64) for t in faces_t]
+    len_t = pinned(lengths)
+    h2d = sum(f.nbytes for f in faces if f is not None) + len_t.numpy().nbytes
+    cells = ns[DIM]
+    d2h = 0
+    times = []
+    for it in range(args.e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        m = fq.Mesh.from_arrays(ctx, DIM, ns, faces, len_t.numpy())
+        d2h = 0
+        for _, form in forms:
+            a = form.assemble(m, True)
+            rp, ci, va = a.download()
+            d2h += rp.nbytes + ci.nbytes + va.nbytes
+            del a, rp, ci, va
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        del m
+        if it > 0:  # first pass is the warm-up
+            times.append(dt)
+    t = allmax(sum(times) / len(times))
+    return {"value": allsum(cells) / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": t * 1e3, "workload": f"per rank: fq_mesh_create + 4x fq_assemble + fq_csr_download on a Kuhn cube "
+                                                f"N={n_e2e} ({cells} tets) from pinned host arrays"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="boxes per axis per GPU (128 -> 12.58 M tets)")
+    ap.add_argument("--sample-n", type=int, default=None, help="Kuhn cube size of the CPU sample (default: calibrated)")
+    ap.add_argument("--e2e-n", type=int, default=128)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

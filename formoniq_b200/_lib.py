@@ -32,17 +32,23 @@ SIGNATURES = [
     ("fq_ctx_set_stream", _i, [_vp, _vp]),
     ("fq_ctx_synchronize", _i, [_vp]),
     ("fq_ctx_launch_count", _i64, [_vp]),
+    ("fq_ctx_set_timing", _i, [_vp, _i]),
+    ("fq_ctx_timing_report", _i, [_vp, _vp, _sz]),
     ("fq_mesh_create", _i, [_vp, _i, _sz, _vp, _vp, _vp, _P(_vp)]),
     ("fq_mesh_create_kuhn", _i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _sz, _sz, _P(_vp)]),
     ("fq_mesh_destroy", _i, [_vp]),
     ("fq_mesh_dim", _i, [_vp]),
     ("fq_mesh_ncells", _sz, [_vp]),
     ("fq_mesh_nsimplices", _sz, [_vp, _i]),
+    ("fq_mesh_nowned_cells", _sz, [_vp]),
+    ("fq_mesh_owned_range", _i, [_vp, _i, _P(_sz), _P(_sz)]),
+    ("fq_mesh_held_range", _i, [_vp, _i, _P(_sz), _P(_sz)]),
     ("fq_mesh_set_lengths", _i, [_vp, _vp, _vp]),
     ("fq_mesh_download_cell_faces", _i, [_vp, _vp, _i, _vp]),
     ("fq_mesh_download_lengths", _i, [_vp, _vp, _vp]),
     ("fq_kuhn_cell_faces_host", _i, [_i, _vp, _i, _vp]),
     ("fq_kuhn_counts", _i, [_i, _vp, _vp]),
+    ("fq_kuhn_slab_ranges", _i, [_i, _vp, _sz, _sz, _i, _vp]),
     ("fq_elmat_shape", _i, [_i, _i, _i, _P(_i), _P(_i)]),
     ("fq_elmat_batch", _i, [_vp, _vp, _i, _i, _sz, _sz, _i, _vp]),
     ("fq_assemble_symbolic", _i, [_vp, _vp, _i, _i, _sz, _sz, _P(_vp)]),
@@ -56,6 +62,7 @@ SIGNATURES = [
     ("fq_csr_assembly_bytes", _i64, [_vp]),
     ("fq_csr_spmv_bytes", _i64, [_vp]),
     ("fq_vec_create", _i, [_vp, _sz, _P(_vp)]),
+    ("fq_vec_wrap", _i, [_vp, _vp, _sz, _P(_vp)]),
     ("fq_vec_destroy", _i, [_vp]),
     ("fq_vec_len", _sz, [_vp]),
     ("fq_vec_upload", _i, [_vp, _vp, _vp]),
@@ -66,6 +73,7 @@ SIGNATURES = [
     ("fq_vec_axpy", _i, [_vp, _vp, _d, _vp]),
     ("fq_vec_device_ptr", _vp, [_vp]),
     ("fq_spmv", _i, [_vp, _vp, _vp, _vp]),
+    ("fq_spmv_window", _i, [_vp, _vp, _vp, _sz, _vp]),
     ("fq_cg", _i, [_vp, _vp, _i, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
     ("fq_minres", _i, [_vp, _vp, _i, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
 ]

@@ -52,6 +52,17 @@ class Context:
     def launch_count(self) -> int:
         return _lib.lib().fq_ctx_launch_count(self._h)
 
+    def set_timing(self, on: bool):
+        check(_lib.lib().fq_ctx_set_timing(self._h, int(on)))
+
+    def timing_report(self) -> dict:
+        """Per-kernel device time since the last report: {name: {"ms", "count"}}."""
+        import json
+
+        buf = C.create_string_buffer(8192)
+        check(_lib.lib().fq_ctx_timing_report(self._h, buf, 8192))
+        return json.loads(buf.value.decode())
+
     def __del__(self):
         try:
             _lib.lib().fq_ctx_destroy(self._h)
@@ -103,6 +114,22 @@ class Mesh:
     def nsimplices(self, grade: int) -> int:
         return _lib.lib().fq_mesh_nsimplices(self._h, grade)
 
+    @property
+    def nowned_cells(self) -> int:
+        return _lib.lib().fq_mesh_nowned_cells(self._h)
+
+    def owned_range(self, grade: int):
+        """Rows (simplices of `grade`) this slab owns under owner-computes."""
+        lo, hi = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().fq_mesh_owned_range(self._h, grade, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def held_range(self, grade: int):
+        """Ids of `grade` referenced by the held cells (owned + halos), contiguous."""
+        lo, hi = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().fq_mesh_held_range(self._h, grade, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def set_lengths(self, edge_lengths_sq):
         a = np.ascontiguousarray(edge_lengths_sq, dtype=np.float64)
         if a.shape[0] != self.nsimplices(1):
@@ -133,6 +160,16 @@ def kuhn_counts(dim: int, shape) -> list[int]:
     out = np.zeros(dim + 1, dtype=np.uint64)
     check(_lib.lib().fq_kuhn_counts(dim, _p(shp), _p(out)))
     return [int(v) for v in out]
+
+
+def kuhn_slab_ranges(dim: int, shape, slab, grade: int):
+    """(held_lo, own_lo, own_hi, held_hi) of one grade for a slab, host-only closed form."""
+    if np.isscalar(shape):
+        shape = [int(shape)] * dim
+    shp = np.ascontiguousarray(shape, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    check(_lib.lib().fq_kuhn_slab_ranges(dim, _p(shp), int(slab[0]), int(slab[1]), grade, _p(out)))
+    return tuple(int(v) for v in out)
 
 
 def kuhn_cell_faces_host(dim: int, shape, grade: int) -> np.ndarray:
@@ -173,6 +210,23 @@ class DeviceVector:
         v = cls(ctx, a.shape[0])
         check(_lib.lib().fq_vec_upload(ctx._h, v._h, _p(a)))
         return v
+
+    @classmethod
+    def wrap(cls, ctx: Context, device_ptr: int, n: int, keepalive=None) -> "DeviceVector":
+        """Non-owning view of caller-owned device memory (e.g. a torch CUDA tensor)."""
+        v = cls.__new__(cls)
+        h = C.c_void_p()
+        check(_lib.lib().fq_vec_wrap(ctx._h, C.c_void_p(device_ptr), n, C.byref(h)))
+        v.ctx, v._h, v.n, v._keepalive = ctx, h, n, keepalive
+        return v
+
+    @classmethod
+    def from_torch(cls, ctx: Context, t) -> "DeviceVector":
+        import torch
+
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.dim() == 1):
+            raise FormoniqError(-1, "need a contiguous 1-D float64 CUDA tensor")
+        return cls.wrap(ctx, t.data_ptr(), t.numel(), keepalive=t)
 
     def upload(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
@@ -291,6 +345,13 @@ class DeviceCsr:
         b, e = self.row_range
         y = out if out is not None else DeviceVector(self.ctx, e - b)
         check(_lib.lib().fq_spmv(self.ctx._h, self._h, x._h, y._h))
+        return y
+
+    def apply_window(self, x: DeviceVector, x_lo: int, out: DeviceVector | None = None) -> DeviceVector:
+        """y = A x with x holding the column window [x_lo, x_lo+len(x)) (owned + halo segment)."""
+        b, e = self.row_range
+        y = out if out is not None else DeviceVector(self.ctx, e - b)
+        check(_lib.lib().fq_spmv_window(self.ctx._h, self._h, x._h, x_lo, y._h))
         return y
 
     @property

@@ -131,6 +131,7 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
   const int row_bits = bits_for(nrows_local + 1);
   FQ_REQUIRE(col_bits + row_bits <= 63, "key overflow");
   const int block = 256;
+  ScopedSpan span_sym(ctx, "k2_symbolic");
   DevBuf<uint64_t> keys(ncontrib_all), keys_alt(ncontrib_all);
   DevBuf<uint32_t> vals(ncontrib_all), vals_alt(ncontrib_all);
   sym_keys_kernel<<<grid_for(ncontrib_all, block, ctx->sm_count), block, 0, ctx->stream>>>(
@@ -261,11 +262,17 @@ void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_e
   if (s_nnz > 0) {
     // K1: element slab
     DevBuf<double> slab(mesh->ncells * T);
-    elmat_to_slab(ctx, mesh, {{csr->kind, csr->grade}}, 0, mesh->ncells, true, slab.p, nullptr);
+    {
+      ScopedSpan span(ctx, "k1_elmat");
+      elmat_to_slab(ctx, mesh, {{csr->kind, csr->grade}}, 0, mesh->ncells, true, slab.p, nullptr);
+    }
     // K3: segmented reduction
-    num_gather_kernel<<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
-        slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->s_values.p, csr->keep.p);
-    fq_count_launch(ctx);
+    {
+      ScopedSpan span(ctx, "k3_gather");
+      num_gather_kernel<<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
+          slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->s_values.p, csr->keep.p);
+      fq_count_launch(ctx);
+    }
     FQ_CUDA(cudaGetLastError());
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // slab freed below
   }
@@ -290,6 +297,7 @@ void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_e
     return;
   }
   // compaction to the reference's value-dependent pattern
+  ScopedSpan span_compact(ctx, "k3_compact");
   DevBuf<uint32_t> k32(s_nnz + 1), pos(s_nnz + 1);
   num_keep_to_u32<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(csr->keep.p, uint32_t(s_nnz), k32.p);
   FQ_CUDA(cudaMemsetAsync(k32.p + s_nnz, 0, sizeof(uint32_t), ctx->stream));

@@ -1,4 +1,5 @@
 // capi.cu — the extern "C" boundary declared in include/formoniq_b200.h.
+#include <cstring>
 #include <limits>
 
 #include "internal.hpp"
@@ -114,6 +115,40 @@ int fq_ctx_synchronize(fq_ctx* ctx) {
   FQ_API_END
 }
 int64_t fq_ctx_launch_count(const fq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int fq_ctx_set_timing(fq_ctx* ctx, int on) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx, "null context");
+  ctx->timing = on != 0;
+  FQ_API_END
+}
+int fq_ctx_timing_report(fq_ctx* ctx, char* buf, size_t buflen) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && buf && buflen > 2, "bad argument");
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<double> ms(ctx->span_names.size(), 0.0);
+  std::vector<int64_t> cnt(ctx->span_names.size(), 0);
+  for (fq_span& sp : ctx->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+      ms[size_t(sp.name_id)] += double(t);
+      cnt[size_t(sp.name_id)] += 1;
+    }
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  ctx->spans.clear();
+  std::string out = "{";
+  for (size_t i = 0; i < ms.size(); ++i) {
+    char tmp[256];
+    std::snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"count\": %lld}", i ? ", " : "", ctx->span_names[i].c_str(),
+                  ms[i], static_cast<long long>(cnt[i]));
+    out += tmp;
+  }
+  out += "}";
+  FQ_REQUIRE(out.size() + 1 <= buflen, "timing report buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  FQ_API_END
+}
 
 // ---------------------------------------------------------------- mesh
 int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices, const uint64_t* const* cell_faces,
@@ -127,6 +162,7 @@ int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices
   std::unique_ptr<fq_mesh> m(new fq_mesh);
   m->dim = dim;
   m->ncells = ncells;
+  m->nowned_cells = ncells;
   m->nsimplices.assign(nsimplices, nsimplices + dim + 1);
   m->cell_faces.resize(size_t(dim) + 1);
   m->id_lo.assign(size_t(dim) + 1, 0);
@@ -166,6 +202,21 @@ size_t fq_mesh_ncells(const fq_mesh* mesh) { return mesh ? mesh->ncells : 0; }
 size_t fq_mesh_nsimplices(const fq_mesh* mesh, int grade) {
   if (!mesh || grade < 0 || grade > mesh->dim) return 0;
   return mesh->nsimplices[size_t(grade)];
+}
+size_t fq_mesh_nowned_cells(const fq_mesh* mesh) { return mesh ? mesh->nowned_cells : 0; }
+int fq_mesh_owned_range(const fq_mesh* mesh, int grade, size_t* lo, size_t* hi) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(mesh && grade >= 0 && grade <= mesh->dim, "bad argument");
+  if (lo) *lo = mesh->own_lo[size_t(grade)];
+  if (hi) *hi = mesh->own_hi[size_t(grade)];
+  FQ_API_END
+}
+int fq_mesh_held_range(const fq_mesh* mesh, int grade, size_t* lo, size_t* hi) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(mesh && grade >= 0 && grade <= mesh->dim, "bad argument");
+  if (lo) *lo = mesh->id_lo[size_t(grade)];
+  if (hi) *hi = mesh->id_hi[size_t(grade)];
+  FQ_API_END
 }
 int fq_mesh_set_lengths(fq_ctx* ctx, fq_mesh* mesh, const double* edge_lengths_sq) {
   FQ_API_BEGIN
@@ -207,6 +258,33 @@ int fq_kuhn_counts(int dim, const size_t* shape, size_t* nsimplices) {
     }
     nsimplices[j] = size_t(total);
   }
+  FQ_API_END
+}
+
+int fq_kuhn_slab_ranges(int dim, const size_t* shape, size_t slab_begin, size_t slab_end, int grade, size_t* out4) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(shape && out4 && grade >= 0 && grade <= dim, "bad argument");
+  FQ_REQUIRE(slab_begin < slab_end && slab_end <= shape[dim - 1], "invalid slab range");
+  const KuhnTables kt(dim);
+  const KuhnGrid g(dim, shape);
+  // number of simplices of `grade` whose top vertex lies in vertex layers [0, z)
+  auto below = [&](uint64_t z) {
+    const uint32_t full = (1u << dim) - 1;
+    uint64_t total = 0;
+    for (uint32_t B = 0; B <= full; ++B) {
+      uint64_t nv = 1;
+      for (int a = 0; a + 1 < dim; ++a) nv *= (B >> a & 1u) ? shape[a] : 1;
+      // last axis: layers [0, z) contain 1 layer with coordinate 0 (if z > 0) and z-1 with coordinate >= 1
+      const uint64_t last = (B >> (dim - 1) & 1u) ? (z > 0 ? z - 1 : 0) : (z > 0 ? 1 : 0);
+      total += nv * last * kt.grades[size_t(grade)].cnt[B];
+    }
+    return total;
+  };
+  const size_t halo_end = slab_end < shape[dim - 1] ? slab_end + 1 : slab_end;
+  out4[0] = size_t(below(slab_begin));                                  // held_lo
+  out4[1] = size_t(slab_begin == 0 ? 0 : below(slab_begin + 1));        // own_lo
+  out4[2] = size_t(below(slab_end + 1));                                // own_hi
+  out4[3] = size_t(below(halo_end + 1));                                // held_hi
   FQ_API_END
 }
 
@@ -383,6 +461,16 @@ int fq_vec_create(fq_ctx* ctx, size_t n, fq_vec** out) {
   *out = v.release();
   FQ_API_END
 }
+int fq_vec_wrap(fq_ctx* ctx, void* device_ptr, size_t n, fq_vec** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && out && (device_ptr || n == 0), "null argument");
+  std::unique_ptr<fq_vec> v(new fq_vec);
+  v->d.p = static_cast<double*>(device_ptr);
+  v->d.n = n;
+  v->d.owned = false;
+  *out = v.release();
+  FQ_API_END
+}
 int fq_vec_destroy(fq_vec* v) {
   delete v;
   return FQ_OK;
@@ -437,6 +525,16 @@ int fq_spmv(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, fq_vec* y) {
   FQ_REQUIRE(x != y, "spmv: x and y must be distinct");
   spmv_prepare(ctx, const_cast<fq_csr*>(a));
   spmv_apply(ctx, a, x->d.p, y->d.p);
+  FQ_API_END
+}
+int fq_spmv_window(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, size_t x_lo, fq_vec* y) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && x && y, "null argument");
+  FQ_REQUIRE(x_lo + x->d.n <= a->ncols && y->d.n == a->row_end - a->row_begin, "spmv_window: dimension mismatch");
+  FQ_REQUIRE(x != y, "spmv: x and y must be distinct");
+  spmv_prepare(ctx, const_cast<fq_csr*>(a));
+  // column ids are global: shift the base so that x[col] addresses the window
+  spmv_apply(ctx, a, x->d.p - x_lo, y->d.p);
   FQ_API_END
 }
 

@@ -53,15 +53,16 @@ template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;  // false: wraps caller-owned device memory
   DevBuf() = default;
   explicit DevBuf(size_t n_) { alloc(n_); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr, o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
     if (this != &o) {
       release();
-      p = o.p, n = o.n;
+      p = o.p, n = o.n, owned = o.owned;
       o.p = nullptr, o.n = 0;
     }
     return *this;
@@ -69,11 +70,12 @@ struct DevBuf {
   ~DevBuf() { release(); }
   void alloc(size_t n_) {
     release();
+    owned = true;
     n = n_;
     if (n) FQ_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr, n = 0;
   }
   size_t bytes() const { return n * sizeof(T); }
@@ -81,6 +83,10 @@ struct DevBuf {
 
 }  // namespace fq
 
+struct fq_span {
+  int name_id;
+  cudaEvent_t a, b;
+};
 struct fq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -89,13 +95,46 @@ struct fq_ctx {
   int64_t launches = 0;
   fq::DevBuf<double> reduce_scratch;  // two-stage reductions
   double* host_scalar = nullptr;      // pinned
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool timing = false;
+  std::vector<std::string> span_names;
+  std::vector<fq_span> spans;
 };
 
 inline void fq_count_launch(fq_ctx* ctx, int n = 1) { ctx->launches += n; }
 
+namespace fq {
+// Brackets the kernels launched in its scope with two events when timing is on.
+struct ScopedSpan {
+  fq_ctx* ctx;
+  fq_span sp{};
+  bool on;
+  ScopedSpan(fq_ctx* c, const char* name) : ctx(c), on(c->timing) {
+    if (!on) return;
+    int id = -1;
+    for (size_t i = 0; i < c->span_names.size(); ++i)
+      if (c->span_names[i] == name) id = int(i);
+    if (id < 0) {
+      c->span_names.push_back(name);
+      id = int(c->span_names.size()) - 1;
+    }
+    sp.name_id = id;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, c->stream);
+  }
+  ~ScopedSpan() {
+    if (!on) return;
+    cudaEventRecord(sp.b, ctx->stream);
+    ctx->spans.push_back(sp);
+  }
+};
+}  // namespace fq
+
 struct fq_mesh {
   int dim = 0;
-  size_t ncells = 0;
+  size_t ncells = 0;                 // cells held (owned + halo layer)
+  size_t nowned_cells = 0;           // cells of the owned box layers (== ncells for full meshes)
   size_t cell_offset = 0;            // global index of local cell 0 (slab meshes)
   std::vector<size_t> nsimplices;    // global counts per grade
   // cell_faces[j]: [ncells][nlocal(dim,j)] global face ids (u32)

@@ -138,8 +138,15 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
   const uint64_t boxes_per_layer = grid.nboxes / shape[dim - 1];
   const uint64_t cells_per_layer = boxes_per_layer * uint64_t(kt.ncelltypes);
   mesh->dim = dim;
+  // owner-computes: the slab owns box layers [slab_begin, slab_end) and the
+  // simplices whose top vertex lies in vertex layers (slab_begin, slab_end]
+  // (plus layer 0 for the first slab).  The cells incident to those simplices
+  // also include the box layer slab_end (its bottom faces), held as a halo.
+  const size_t own_end = slab_end;
+  if (slab_end < shape[dim - 1]) slab_end += 1;
   mesh->cell_offset = size_t(cells_per_layer * slab_begin);
   mesh->ncells = size_t(cells_per_layer * (slab_end - slab_begin));
+  mesh->nowned_cells = size_t(cells_per_layer * (own_end - slab_begin));
   mesh->nsimplices.assign(size_t(dim) + 1, 0);
   mesh->cell_faces.clear();
   mesh->cell_faces.resize(size_t(dim) + 1);
@@ -153,6 +160,7 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
   const uint64_t layer = grid.vstride[dim - 1];
   const uint64_t v_lo = layer * slab_begin, v_hi = layer * (slab_end + 1);
   const uint64_t own_v_lo = slab_begin == 0 ? 0 : layer * (slab_begin + 1);
+  const uint64_t own_v_hi = layer * (own_end + 1);
   const int block = 256;
   DevBuf<uint32_t> cnt(size_t(grid.nverts) + 1);
   std::vector<DevBuf<uint32_t>> vbase(size_t(dim) + 1);
@@ -187,14 +195,15 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
     fq_count_launch(ctx, 2);
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
     // id ranges: vbase at the slab's vertex bounds
-    uint32_t h[3];
+    uint32_t h[4];
     FQ_CUDA(cudaMemcpy(&h[0], vbase[size_t(j)].p + v_lo, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     FQ_CUDA(cudaMemcpy(&h[1], vbase[size_t(j)].p + v_hi, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     FQ_CUDA(cudaMemcpy(&h[2], vbase[size_t(j)].p + own_v_lo, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    FQ_CUDA(cudaMemcpy(&h[3], vbase[size_t(j)].p + own_v_hi, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     mesh->id_lo[size_t(j)] = h[0];
     mesh->id_hi[size_t(j)] = h[1];
     mesh->own_lo[size_t(j)] = h[2];
-    mesh->own_hi[size_t(j)] = h[1];
+    mesh->own_hi[size_t(j)] = h[3];
   }
   // cells are themselves the grade-dim simplices: owned = all local cells
   for (int j = 0; j <= dim; ++j) {

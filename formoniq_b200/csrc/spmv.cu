@@ -80,6 +80,7 @@ void spmv_apply(fq_ctx* ctx, const fq_csr* a, const double* x, double* y) {
   FQ_REQUIRE(a->spmv_ready, "spmv_prepare was not called");
   if (a->nrowblocks == 0) return;
   const int grid = int(std::min<size_t>(a->nrowblocks, size_t(ctx->sm_count) * 8));
+  ScopedSpan span(ctx, "k4_spmv");
   spmv_stream_kernel<<<grid, kSpmvThreads, 0, ctx->stream>>>(a->rowblocks.p, a->row_ptr.p, a->col_idx.p, a->values.p, x,
                                                               y, uint32_t(a->nrowblocks));
   fq_count_launch(ctx);

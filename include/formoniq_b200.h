@@ -58,6 +58,11 @@ int fq_ctx_set_stream(fq_ctx* ctx, void* cuda_stream);
 int fq_ctx_synchronize(fq_ctx* ctx);
 /* kernels launched by this context so far (for bench.py's gpu_launches) */
 int64_t fq_ctx_launch_count(const fq_ctx* ctx);
+/* per-kernel device timing: when on, the hot kernels are bracketed with CUDA
+ * events on the context's stream; the report is a JSON object
+ * {"kernel": {"ms": total, "count": launches}, ...} and resets the spans. */
+int fq_ctx_set_timing(fq_ctx* ctx, int on);
+int fq_ctx_timing_report(fq_ctx* ctx, char* buf, size_t buflen);
 
 /* ---- mesh ----------------------------------------------------------------
  * What `Complex` + `MeshLengthsSq` expose to assembly:
@@ -75,9 +80,12 @@ int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices
  *   shape[a]  cells along axis a;  vmin/vmax the box;  ambient_diag the diagonal
  *   ambient form (+1 Euclid, -1 for a time axis);  jitter displaces every vertex
  *   by jitter*h_a*pseudo_random(seed=a, index=v) (formoniq/src/linalg/eigen.rs:259-268).
- * slab_begin/slab_end restrict the boxes along the LAST axis to
- * [slab_begin, slab_end) (owner-computes partition); pass 0, shape[dim-1] for
- * the whole grid.  Simplex ids stay global. */
+ * slab_begin/slab_end select the box layers [slab_begin, slab_end) along the
+ * LAST axis that this context owns (owner-computes partition); pass
+ * 0, shape[dim-1] for the whole grid.  Simplex ids stay global.  The mesh also
+ * holds the halo layer slab_end (when it exists): its cells touch owned rows.
+ * fq_mesh_owned_range gives the rows (simplices of a grade) this slab owns,
+ * fq_mesh_held_range the ids its cells reference (owned + halos, contiguous). */
 int fq_mesh_create_kuhn(fq_ctx* ctx, int dim, const size_t* shape, const double* vmin, const double* vmax,
                         const double* ambient_diag, double jitter, size_t slab_begin, size_t slab_end,
                         fq_mesh** out);
@@ -85,6 +93,9 @@ int fq_mesh_destroy(fq_mesh* mesh);
 int fq_mesh_dim(const fq_mesh* mesh);
 size_t fq_mesh_ncells(const fq_mesh* mesh);
 size_t fq_mesh_nsimplices(const fq_mesh* mesh, int grade);
+size_t fq_mesh_nowned_cells(const fq_mesh* mesh);
+int fq_mesh_owned_range(const fq_mesh* mesh, int grade, size_t* lo, size_t* hi);
+int fq_mesh_held_range(const fq_mesh* mesh, int grade, size_t* lo, size_t* hi);
 /* replace the geometry (MeshLengthsSq) of an existing mesh */
 int fq_mesh_set_lengths(fq_ctx* ctx, fq_mesh* mesh, const double* edge_lengths_sq);
 /* copy device-side tables back (parity hooks for the generator) */
@@ -95,6 +106,10 @@ int fq_mesh_download_lengths(fq_ctx* ctx, const fq_mesh* mesh, double* out);
  * reference-side `Complex` without its hash-based `from_cells`. */
 int fq_kuhn_cell_faces_host(int dim, const size_t* shape, int grade, uint64_t* out);
 int fq_kuhn_counts(int dim, const size_t* shape, size_t* nsimplices /*[dim+1]*/);
+/* Host-only: id ranges of one grade for the slab [slab_begin, slab_end):
+ * out4 = {held_lo, own_lo, own_hi, held_hi} (what fq_mesh_held_range /
+ * fq_mesh_owned_range report for the device mesh). */
+int fq_kuhn_slab_ranges(int dim, const size_t* shape, size_t slab_begin, size_t slab_end, int grade, size_t* out4);
 
 /* ---- element matrices ------------------------------------------------------
  * BilinearForm::element for a batch of cells (formoniq/src/galerkin.rs:50,
@@ -136,6 +151,8 @@ int64_t fq_csr_spmv_bytes(const fq_csr* csr);
 
 /* ---- vectors: iterative::InnerProductSpace (iterative/src/lib.rs:84-141) ---- */
 int fq_vec_create(fq_ctx* ctx, size_t n, fq_vec** out); /* zeros_like */
+/* non-owning view of caller-owned device memory (e.g. a torch tensor) */
+int fq_vec_wrap(fq_ctx* ctx, void* device_ptr, size_t n, fq_vec** out);
 int fq_vec_destroy(fq_vec* v);
 size_t fq_vec_len(const fq_vec* v);
 int fq_vec_upload(fq_ctx* ctx, fq_vec* v, const double* host);
@@ -149,6 +166,9 @@ void* fq_vec_device_ptr(fq_vec* v);
 
 /* ---- SpMV: iterative::LinearOperator::apply (iterative/src/operator.rs:5-14) ---- */
 int fq_spmv(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, fq_vec* y);
+/* y = A x where x holds only the window [x_lo, x_lo + len(x)) of the global
+ * column space (owned segment + halos of a row-partitioned operator). */
+int fq_spmv_window(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, size_t x_lo, fq_vec* y);
 
 /* ---- Krylov drivers on device vectors (iterative/src/krylov.rs:48-95, 113-211).
  * precond: 0 identity (iterative/src/precond.rs:16-41), 1 Jacobi (:113-121).

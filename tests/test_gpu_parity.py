@@ -126,14 +126,48 @@ def test_device_kuhn_slab_is_a_window_of_the_global_mesh(fq, ctx):
     shape = [3, 2, 6]
     cx, s, coords, diag, vmax = kuhn_problem(3, shape, jitter=True)
     per_layer = 6 * 3 * 2
+    owned_rows = {j: [] for j in range(4)}
     for sb, se in ((0, 2), (2, 5), (5, 6)):
         mesh = fq.Mesh.kuhn(ctx, 3, shape, jitter=0.2, slab=(sb, se))
-        assert mesh.ncells == per_layer * (se - sb)
+        he = min(se + 1, shape[2])  # one halo layer of boxes above the owned ones
+        assert mesh.nowned_cells == per_layer * (se - sb) and mesh.ncells == per_layer * (he - sb)
         for j in range(4):
-            assert np.array_equal(mesh.cell_faces(j).astype(np.int64), cx.cell_faces(j)[per_layer * sb:per_layer * se])
+            assert np.array_equal(mesh.cell_faces(j).astype(np.int64), cx.cell_faces(j)[per_layer * sb:per_layer * he])
+            owned_rows[j].append(mesh.owned_range(j))
+            lo, hi = mesh.held_range(j)
+            ids = cx.cell_faces(j)[per_layer * sb:per_layer * he]
+            assert lo <= ids.min() and ids.max() < hi
         got = mesh.lengths()
-        used = np.unique(cx.cell_faces(1)[per_layer * sb:per_layer * se])
+        used = np.unique(cx.cell_faces(1)[per_layer * sb:per_layer * he])
         assert np.array_equal(got[used], s[used])
+    for j in range(4):  # the owned row ranges tile [0, nsimplices) without gaps
+        r = owned_rows[j]
+        assert r[0][0] == 0 and r[-1][1] == cx.nsimplices(j) and all(r[i][1] == r[i + 1][0] for i in range(2))
+
+
+def test_slab_assembly_tiles_the_global_matrix(fq, ctx):
+    # owner-computes rows with a halo layer: the rank-local row blocks, stacked, are the 1-GPU matrix bit for bit
+    shape = [3, 3, 6]
+    cx, s, *_ = kuhn_problem(3, shape, jitter=True)
+    for kind, g in ((O.MASS, 0), (O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2)):
+        ref = cx.assemble(s, kind, g).to_scipy()
+        form = fq.WhitneyPairing(3, g, kind)
+        x = np.cos(np.arange(ref.shape[1]) ** 2 + 1.0)
+        yref = ref @ x
+        for sb, se in ((0, 2), (2, 4), (4, 6)):
+            mesh = fq.Mesh.kuhn(ctx, 3, shape, jitter=0.2, slab=(sb, se))
+            b, e = mesh.owned_range(form.test_grade())
+            part = form.symbolic(mesh, b, e)
+            part.numeric(mesh)
+            got, exp = part.to_scipy(), ref[b:e]
+            assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+            assert np.array_equal(got.data, exp.data)
+            # windowed SpMV: x restricted to the held column range (owned + halos)
+            lo, hi = mesh.held_range(form.trial_grade())
+            assert exp.indices.min() >= lo and exp.indices.max() < hi
+            y = part.apply_window(fq.DeviceVector.from_numpy(ctx, x[lo:hi]), lo).to_numpy()
+            assert np.array_equal(y, cx.assemble(s, kind, g).spmv(x)[b:e])
+            assert np.abs(y - yref[b:e]).max() <= 1e-12 * np.abs(yref).max()
 
 
 # ------------------------------------------------------------------ assembly
