@@ -182,17 +182,15 @@ def run_b200(args):
     slab = slab_of(rank, world, shape[2])
     mesh = fq.Mesh.kuhn(ctx, DIM, shape, slab=slab)
     forms = hodge_forms(fq)
-    mats = []
     ctx.set_timing(True)
-    for name, form in forms:
-        lo, hi = mesh.owned_range(form.test_grade())
-        mats.append((name, form, form.symbolic(mesh, lo, hi)))
+    # HodgeBlocks plan: symbolic once (pattern + cell-slot -> nnz maps), rows owned by this rank
+    hb = fq.HodgeBlocks.symbolic(mesh, GRADE, sigma_rows=mesh.owned_range(GRADE - 1), u_rows=mesh.owned_range(GRADE))
+    mats = [(name, form, a) for (name, form), a in zip(forms, hb.blocks)]
     sym_report = ctx.timing_report()
     owned_cells = mesh.nowned_cells
 
     def step():
-        for _, _, a in mats:
-            a.numeric(mesh, True)
+        hb.numeric(mesh, True)  # one fused element kernel + one segmented reduction per block
 
     for _ in range(args.warmup):
         step()

@@ -54,6 +54,10 @@ SIGNATURES = [
     ("fq_assemble_symbolic", _i, [_vp, _vp, _i, _i, _sz, _sz, _P(_vp)]),
     ("fq_assemble_numeric", _i, [_vp, _vp, _vp, _i]),
     ("fq_assemble", _i, [_vp, _vp, _i, _i, _i, _P(_vp)]),
+    ("fq_hodge_symbolic", _i, [_vp, _vp, _i, _sz, _sz, _sz, _sz, _P(_vp)]),
+    ("fq_hodge_numeric", _i, [_vp, _vp, _vp, _i]),
+    ("fq_hodge_block", _vp, [_vp, _i]),
+    ("fq_hodge_destroy", _i, [_vp]),
     ("fq_csr_shape", _i, [_vp, _P(_sz), _P(_sz), _P(_sz)]),
     ("fq_csr_row_range", _i, [_vp, _P(_sz), _P(_sz)]),
     ("fq_csr_download", _i, [_vp, _vp, _vp, _vp, _vp]),

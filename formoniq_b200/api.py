@@ -281,8 +281,8 @@ class DeviceVector:
 class DeviceCsr:
     """GalerkinMatrix in HBM: nalgebra-sparse CSR contract + LinearOperator::apply."""
 
-    def __init__(self, ctx: Context, handle):
-        self.ctx, self._h = ctx, handle
+    def __init__(self, ctx: Context, handle, owner=None):
+        self.ctx, self._h, self._owner = ctx, handle, owner  # owner: a HodgeBlocks plan that owns the handle
 
     @property
     def shape(self):
@@ -364,7 +364,8 @@ class DeviceCsr:
 
     def __del__(self):
         try:
-            _lib.lib().fq_csr_destroy(self._h)
+            if self._owner is None:
+                _lib.lib().fq_csr_destroy(self._h)
         except Exception:
             pass
 
@@ -442,9 +443,21 @@ class ScalarLumpedMass(BilinearForm):
         return 0
 
 
+class _HodgePlan:
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_hodge_destroy(self._h)
+        except Exception:
+            pass
+
+
 @dataclass
 class HodgeBlocks:
-    """The four matrices of a mixed problem posed at `grade` (hodge.rs:62-72)."""
+    """The four matrices of a mixed problem posed at `grade` (hodge.rs:62-72),
+    assembled with one fused element kernel per numeric pass."""
 
     n_sigma: int
     n_u: int
@@ -452,20 +465,31 @@ class HodgeBlocks:
     mass_u: DeviceCsr
     dif_test: DeviceCsr
     dif_both: DeviceCsr
+    _plan: _HodgePlan = None
+
+    @classmethod
+    def symbolic(cls, mesh: Mesh, grade: int, sigma_rows=(0, SIZE_MAX), u_rows=(0, SIZE_MAX)) -> "HodgeBlocks":
+        h = C.c_void_p()
+        check(_lib.lib().fq_hodge_symbolic(mesh.ctx._h, mesh._h, grade, sigma_rows[0], sigma_rows[1], u_rows[0], u_rows[1],
+                                           C.byref(h)))
+        plan = _HodgePlan(h)
+        blk = [DeviceCsr(mesh.ctx, C.c_void_p(_lib.lib().fq_hodge_block(h, i)), owner=plan) for i in range(4)]
+        return cls(mesh.nsimplices(grade - 1), mesh.nsimplices(grade), blk[0], blk[1], blk[2], blk[3], plan)
+
+    def numeric(self, mesh: Mesh, drop_exact_zeros: bool = True):
+        check(_lib.lib().fq_hodge_numeric(mesh.ctx._h, mesh._h, self._plan._h, int(drop_exact_zeros)))
+
+    @property
+    def blocks(self):
+        return [self.mass_sigma, self.mass_u, self.dif_test, self.dif_both]
 
     @classmethod
     def compute(cls, mesh: Mesh, grade: int, drop_exact_zeros: bool = True) -> "HodgeBlocks":
-        if grade > mesh.dim:
+        if grade > mesh.dim or grade < 0:
             raise FormoniqError(-1, "grade <= complex.dim() is required")
-        d = mesh.dim
-        return cls(
-            n_sigma=mesh.nsimplices(grade - 1),
-            n_u=mesh.nsimplices(grade),
-            mass_sigma=WhitneyPairing.mass(d, grade - 1).assemble(mesh, drop_exact_zeros),
-            mass_u=WhitneyPairing.mass(d, grade).assemble(mesh, drop_exact_zeros),
-            dif_test=WhitneyPairing.dif_test(d, grade).assemble(mesh, drop_exact_zeros),
-            dif_both=WhitneyPairing.dif_both(d, grade + 1).assemble(mesh, drop_exact_zeros),
-        )
+        hb = cls.symbolic(mesh, grade)
+        hb.numeric(mesh, drop_exact_zeros)
+        return hb
 
     def mixed_hodge_laplacian(self):
         """[[M_{k-1}, -dif_test], [dif_test^T, dif_both]] stitched on the host (scipy) and uploaded."""

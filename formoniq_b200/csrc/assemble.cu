@@ -106,6 +106,8 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
   out->el_cols = nr;
   out->ncells = mesh->ncells;
   out->has_plan = true;
+  out->compact_valid = false;
+  out->pattern_valid = false;
   const size_t nrows_local = row_end - row_begin;
   const size_t T = size_t(nt) * size_t(nr);
   const uint64_t ncontrib_all = uint64_t(mesh->ncells) * T;
@@ -210,10 +212,17 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
 // ------------------------------------------------------------------ numeric
 // One thread per structural non-zero: ordered sum of its contributions and the
 // "any contribution != 0.0" flag of galerkin.rs:173.
+//
+// MODE 0: structural output  values[q] = sum, keep[q] = any   (first pass / no dropping)
+// MODE 1: cached compaction  values[pos[q]] = sum for kept entries; if the
+//         zero/non-zero classification differs from the cached one (the geometry
+//         changed), raise *changed so the host redoes the compaction.
+template <int MODE>
 __global__ void __launch_bounds__(256) num_gather_kernel(const double* __restrict__ slab,
                                                           const uint32_t* __restrict__ contrib_ptr,
                                                           const uint32_t* __restrict__ contrib_src, uint32_t s_nnz,
-                                                          double* __restrict__ values, uint8_t* __restrict__ keep) {
+                                                          double* __restrict__ values, uint8_t* __restrict__ keep,
+                                                          const uint32_t* __restrict__ pos, int* __restrict__ changed) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < s_nnz; q += stride) {
     const uint32_t b = contrib_ptr[q], e = contrib_ptr[q + 1];
@@ -224,8 +233,14 @@ __global__ void __launch_bounds__(256) num_gather_kernel(const double* __restric
       any = any || (v != 0.0);
       acc = __dadd_rn(acc, v);
     }
-    values[q] = acc;
-    keep[q] = any ? 1 : 0;
+    if (MODE == 0) {
+      values[q] = acc;
+      keep[q] = any ? 1 : 0;
+    } else {
+      const bool kept = keep[q] != 0;
+      if (kept != any) *changed = 1;
+      if (kept) values[pos[q]] = acc;
+    }
   }
 }
 
@@ -250,64 +265,82 @@ __global__ void num_rowptr_kernel(const uint32_t* __restrict__ s_row_ptr, const 
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nrows; r += stride) row_ptr[r] = pos[s_row_ptr[r]];
 }
 
-void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros) {
-  FQ_REQUIRE(csr->has_plan, "matrix has no assembly plan (uploaded matrices cannot be re-assembled)");
-  FQ_REQUIRE(csr->ncells == mesh->ncells && csr->dim == mesh->dim, "mesh does not match the symbolic phase");
+static void gather_structural(fq_ctx* ctx, fq_csr* csr) {
+  ScopedSpan span(ctx, "k3_gather");
+  num_gather_kernel<0><<<grid_for(csr->s_nnz, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(
+      csr->slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(csr->s_nnz), csr->s_values.p, csr->keep.p, nullptr,
+      nullptr);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
+
+// After K1 filled csr->slab: reduce into the CSR values under the requested pattern semantics.
+static void numeric_reduce(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros) {
   const size_t nrows_local = csr->row_end - csr->row_begin;
   const size_t s_nnz = csr->s_nnz;
   const int block = 256;
-  const size_t T = size_t(csr->el_rows) * size_t(csr->el_cols);
-  csr->spmv_ready = false;
-  csr->inv_diag.release();
-  if (s_nnz > 0) {
-    // K1: element slab
-    DevBuf<double> slab(mesh->ncells * T);
-    {
-      ScopedSpan span(ctx, "k1_elmat");
-      elmat_to_slab(ctx, mesh, {{csr->kind, csr->grade}}, 0, mesh->ncells, true, slab.p, nullptr);
-    }
-    // K3: segmented reduction
-    {
-      ScopedSpan span(ctx, "k3_gather");
-      num_gather_kernel<<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
-          slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->s_values.p, csr->keep.p);
-      fq_count_launch(ctx);
-    }
-    FQ_CUDA(cudaGetLastError());
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // slab freed below
-  }
   const int ne = int(binom(mesh->dim + 1, 2));
   csr->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csr->ncontrib);
   if (!drop_exact_zeros || s_nnz == 0) {
+    // the structural pattern is the result; its index arrays are shared once
+    if (csr->dropped || csr->row_ptr.n != nrows_local + 1 || csr->nnz != s_nnz || !csr->pattern_valid) {
+      csr->row_ptr.alloc(nrows_local + 1);
+      csr->col_idx.alloc(s_nnz ? s_nnz : 1);
+      csr->values.alloc(s_nnz ? s_nnz : 1);
+      FQ_CUDA(cudaMemcpyAsync(csr->row_ptr.p, csr->s_row_ptr.p, (nrows_local + 1) * sizeof(uint32_t),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+      if (s_nnz)
+        FQ_CUDA(cudaMemcpyAsync(csr->col_idx.p, csr->s_col_idx.p, s_nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+      csr->spmv_ready = false;
+    }
     csr->dropped = false;
+    csr->pattern_valid = true;
+    csr->compact_valid = false;
     csr->nnz = s_nnz;
-    csr->row_ptr.alloc(nrows_local + 1);
-    csr->col_idx.alloc(s_nnz ? s_nnz : 1);
-    csr->values.alloc(s_nnz ? s_nnz : 1);
-    FQ_CUDA(cudaMemcpyAsync(csr->row_ptr.p, csr->s_row_ptr.p, (nrows_local + 1) * sizeof(uint32_t),
-                            cudaMemcpyDeviceToDevice, ctx->stream));
     if (s_nnz) {
-      FQ_CUDA(cudaMemcpyAsync(csr->col_idx.p, csr->s_col_idx.p, s_nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
-                              ctx->stream));
-      FQ_CUDA(cudaMemcpyAsync(csr->values.p, csr->s_values.p, s_nnz * sizeof(double), cudaMemcpyDeviceToDevice,
-                              ctx->stream));
+      ScopedSpan span(ctx, "k3_gather");
+      num_gather_kernel<0><<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
+          csr->slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->values.p, csr->keep.p, nullptr,
+          nullptr);
+      fq_count_launch(ctx);
+      FQ_CUDA(cudaGetLastError());
     }
     csr->assembly_bytes += int64_t(8 * s_nnz);
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
     return;
   }
-  // compaction to the reference's value-dependent pattern
+  if (csr->compact_valid && csr->dropped) {
+    // fast path: the cached value-dependent pattern is reused and verified
+    {
+      ScopedSpan span(ctx, "k3_gather");
+      FQ_CUDA(cudaMemsetAsync(csr->d_changed.p, 0, sizeof(int), ctx->stream));
+      num_gather_kernel<1><<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
+          csr->slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->values.p, csr->keep.p, csr->pos.p,
+          csr->d_changed.p);
+      fq_count_launch(ctx);
+      FQ_CUDA(cudaGetLastError());
+    }
+    int changed = 0;
+    FQ_CUDA(cudaMemcpyAsync(&changed, csr->d_changed.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    csr->assembly_bytes += int64_t(8 * csr->nnz);
+    if (!changed) return;
+  }
+  // slow path: structural gather, then compaction to the reference's value-dependent pattern
+  gather_structural(ctx, csr);
   ScopedSpan span_compact(ctx, "k3_compact");
-  DevBuf<uint32_t> k32(s_nnz + 1), pos(s_nnz + 1);
+  DevBuf<uint32_t> k32(s_nnz + 1);
+  if (csr->pos.n != s_nnz + 1) csr->pos.alloc(s_nnz + 1);
+  if (csr->d_changed.n != 1) csr->d_changed.alloc(1);
   num_keep_to_u32<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(csr->keep.p, uint32_t(s_nnz), k32.p);
   FQ_CUDA(cudaMemsetAsync(k32.p + s_nnz, 0, sizeof(uint32_t), ctx->stream));
   size_t tmp_bytes = 0;
-  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, k32.p, pos.p, int64_t(s_nnz + 1), ctx->stream));
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, k32.p, csr->pos.p, int64_t(s_nnz + 1), ctx->stream));
   DevBuf<uint8_t> tmp(tmp_bytes);
-  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, k32.p, pos.p, int64_t(s_nnz + 1), ctx->stream));
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, k32.p, csr->pos.p, int64_t(s_nnz + 1), ctx->stream));
   fq_count_launch(ctx, 3);
   uint32_t nnz = 0;
-  FQ_CUDA(cudaMemcpyAsync(&nnz, pos.p + s_nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(&nnz, csr->pos.p + s_nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   csr->dropped = true;
   csr->nnz = nnz;
@@ -315,13 +348,51 @@ void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_e
   csr->col_idx.alloc(nnz ? nnz : 1);
   csr->values.alloc(nnz ? nnz : 1);
   num_compact_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      csr->keep.p, pos.p, uint32_t(s_nnz), csr->s_col_idx.p, csr->s_values.p, csr->col_idx.p, csr->values.p);
+      csr->keep.p, csr->pos.p, uint32_t(s_nnz), csr->s_col_idx.p, csr->s_values.p, csr->col_idx.p, csr->values.p);
   num_rowptr_kernel<<<grid_for(nrows_local + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      csr->s_row_ptr.p, pos.p, uint32_t(nrows_local), csr->row_ptr.p);
+      csr->s_row_ptr.p, csr->pos.p, uint32_t(nrows_local), csr->row_ptr.p);
   fq_count_launch(ctx, 2);
   FQ_CUDA(cudaGetLastError());
   csr->assembly_bytes += int64_t(8 * size_t(nnz));
+  csr->compact_valid = true;
+  csr->pattern_valid = true;
+  csr->spmv_ready = false;
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros) {
+  std::vector<BlockSpec> blocks;
+  std::vector<double*> outs;
+  bool any_work = false;
+  for (int b = 0; b < nblocks; ++b) {
+    fq_csr* csr = csrs[b];
+    FQ_REQUIRE(csr->has_plan, "matrix has no assembly plan (uploaded matrices cannot be re-assembled)");
+    FQ_REQUIRE(csr->ncells == mesh->ncells && csr->dim == mesh->dim, "mesh does not match the symbolic phase");
+    csr->inv_diag.release();
+    const size_t T = size_t(csr->el_rows) * size_t(csr->el_cols);
+    const size_t want = mesh->ncells * T;
+    if (csr->slab.n != (want ? want : 1)) csr->slab.alloc(want ? want : 1);  // persistent across numeric calls
+    blocks.push_back(BlockSpec{csr->kind, csr->grade});
+    outs.push_back(csr->slab.p);
+    any_work = any_work || (csr->s_nnz > 0);
+  }
+  if (any_work) {
+    ScopedSpan span(ctx, "k1_elmat");
+    if (nblocks == 1 || elmat_has_generated(mesh->dim, blocks)) {
+      elmat_to_slabs(ctx, mesh, blocks, 0, mesh->ncells, true, outs.data(), nullptr);
+    } else {
+      for (int b = 0; b < nblocks; ++b) {
+        double* one[1] = {outs[size_t(b)]};
+        if (csrs[b]->s_nnz > 0) elmat_to_slabs(ctx, mesh, {blocks[size_t(b)]}, 0, mesh->ncells, true, one, nullptr);
+      }
+    }
+  }
+  for (int b = 0; b < nblocks; ++b) numeric_reduce(ctx, mesh, csrs[b], drop_exact_zeros);
+}
+
+void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros) {
+  fq_csr* one[1] = {csr};
+  assemble_numeric_multi(ctx, mesh, one, 1, drop_exact_zeros);
 }
 
 }  // namespace fq

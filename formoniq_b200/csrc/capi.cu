@@ -346,7 +346,8 @@ int fq_elmat_batch(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t
   DevBuf<double> slab(nc * size_t(nouts));
   DevBuf<int> err(1);
   FQ_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
-  elmat_to_slab(ctx, mesh, blocks, cell_begin, cell_end, use_generated != 0, slab.p, err.p);
+  double* outs[1] = {slab.p};
+  elmat_to_slabs(ctx, mesh, blocks, cell_begin, cell_end, use_generated != 0, outs, err.p);
   int h = 0;
   FQ_CUDA(cudaMemcpyAsync(&h, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FQ_CUDA(cudaMemcpyAsync(out, slab.p, slab.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -383,6 +384,45 @@ int fq_assemble(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, int drop_
     *out = nullptr;
   }
   return rc2;
+}
+
+struct fq_hodge {
+  int grade = 0;
+  std::unique_ptr<fq_csr> blocks[4];
+};
+
+int fq_hodge_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int grade, size_t sigma_row_begin, size_t sigma_row_end,
+                      size_t u_row_begin, size_t u_row_end, fq_hodge** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out, "null argument");
+  FQ_REQUIRE(grade >= 0 && grade <= mesh->dim, "grade <= complex.dim() is required");  // hodge.rs:63
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_hodge> h(new fq_hodge);
+  h->grade = grade;
+  const auto specs = hodge_blocks(grade);
+  for (int b = 0; b < 4; ++b) {
+    h->blocks[b].reset(new fq_csr);
+    const bool sigma_rows = (b == 0 || b == 2);
+    assemble_symbolic(ctx, mesh, specs[size_t(b)].kind, specs[size_t(b)].grade, sigma_rows ? sigma_row_begin : u_row_begin,
+                      sigma_rows ? sigma_row_end : u_row_end, h->blocks[b].get());
+  }
+  *out = h.release();
+  FQ_API_END
+}
+int fq_hodge_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_hodge* blocks, int drop_exact_zeros) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && blocks, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  fq_csr* ptrs[4] = {blocks->blocks[0].get(), blocks->blocks[1].get(), blocks->blocks[2].get(), blocks->blocks[3].get()};
+  assemble_numeric_multi(ctx, mesh, ptrs, 4, drop_exact_zeros != 0);
+  FQ_API_END
+}
+fq_csr* fq_hodge_block(fq_hodge* blocks, int which) {
+  return (blocks && which >= 0 && which < 4) ? blocks->blocks[which].get() : nullptr;
+}
+int fq_hodge_destroy(fq_hodge* blocks) {
+  delete blocks;
+  return FQ_OK;
 }
 
 // ---------------------------------------------------------------- CSR

@@ -174,8 +174,13 @@ struct fq_csr {
   fq::DevBuf<uint32_t> contrib_src; // [ncontrib] cell*T+slot, sorted by (nnz, cell)
   size_t ncontrib = 0;
   fq::DevBuf<double> s_values;      // [s_nnz] structural values (scratch when dropping)
-  fq::DevBuf<uint8_t> keep;         // [s_nnz]
+  fq::DevBuf<uint8_t> keep;         // [s_nnz] "some contribution != 0.0" (galerkin.rs:173)
+  fq::DevBuf<double> slab;          // [ncells][el_rows*el_cols] element slab, persistent
+  fq::DevBuf<uint32_t> pos;         // [s_nnz+1] structural -> compacted index (exclusive scan of keep)
+  fq::DevBuf<int> d_changed;        // device flag: classification differs from the cached pattern
   bool dropped = false;
+  bool compact_valid = false;       // pos / keep / compacted pattern describe the last geometry
+  bool pattern_valid = false;
   int64_t assembly_bytes = 0;
   // SpMV row blocks (CSR-stream)
   fq::DevBuf<uint32_t> rowblocks;

@@ -18,26 +18,58 @@
 namespace fq {
 
 // ------------------------------------------------------------------ sinks
-struct SlabSink {
-  double* __restrict__ base;  // this cell's block of the slab
-  template <unsigned I>
+// A warp evaluates 32 consecutive cells, one per lane.  Each block's entries
+// are staged in shared memory ([entry][lane], padded to 33 so both the
+// lane-major writes and the cell-major reads are bank-conflict free) and then
+// flushed as one contiguous, fully coalesced run of 32*T doubles of that
+// block's cell-major slab  slab_b[(cell) * T_b + entry].
+constexpr int kStagePad = 33;
+constexpr int kMaxBlocks = 4;
+struct SlabPtrs {
+  double* p[kMaxBlocks];
+};
+struct WarpStageSink {
+  double* __restrict__ stage;  // this warp's staging area [maxT][33]
+  SlabPtrs slabs;              // per block: slab base + first_cell_of_this_warp * T_b is added in flush
+  size_t cell0;                // first cell (slab-relative) of this warp's group
+  int lane, nvalid;
+  template <int B, int E>
   __device__ __forceinline__ void put(double v) const {
-    base[I] = v;
+    stage[E * kStagePad + lane] = v;
+  }
+  template <int B, int TB>
+  __device__ __forceinline__ void flush() const {
+    __syncwarp();
+    double* __restrict__ g = slabs.p[B] + cell0 * size_t(TB);
+    const int total = nvalid * TB;
+#pragma unroll 4
+    for (int k = lane; k < total; k += 32) {
+      const int c = k / TB, e = k - c * TB;
+      g[k] = stage[e * kStagePad + c];
+    }
+    __syncwarp();
   }
 };
 
 template <class Fn, int NE>
 __global__ void __launch_bounds__(128) elmat_gen_kernel(Fn fn, const uint32_t* __restrict__ cell_edges,
                                                          const double* __restrict__ lengths, uint32_t edge_lo,
-                                                         size_t c0, size_t ncells, int nouts,
-                                                         double* __restrict__ out) {
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < ncells; i += stride) {
+                                                         size_t c0, size_t ncells, int max_t, SlabPtrs slabs) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* stage = stage_all + size_t(warp) * size_t(max_t) * kStagePad;
+  const size_t ngroups = (ncells + 31) / 32;
+  const size_t wstride = size_t(gridDim.x) * (blockDim.x >> 5);
+  for (size_t grp = size_t(blockIdx.x) * (blockDim.x >> 5) + warp; grp < ngroups; grp += wstride) {
+    const size_t first = grp * 32;
+    const int nvalid = int(ncells - first < 32 ? ncells - first : 32);
+    // lanes past the end recompute the last valid cell; their results are never flushed
+    const size_t i = first + size_t(lane < nvalid ? lane : nvalid - 1);
     const uint32_t* ce = cell_edges + (c0 + i) * NE;
     double s[NE > 0 ? NE : 1];
 #pragma unroll
     for (int e = 0; e < NE; ++e) s[e] = __ldg(lengths + (ce[e] - edge_lo));
-    SlabSink sink{out + i * size_t(nouts)};
+    WarpStageSink sink{stage, slabs, first, lane, nvalid};
     fn(s, sink);
   }
 }
@@ -54,25 +86,31 @@ FQ_GEN_ELMAT_LIST(FQ_DECLARE_FN)
 
 struct GenEntry {
   int n, fused_k, kind, grade, nin, nout;
-  void (*launch)(fq_ctx*, const fq_mesh*, size_t, size_t, double*);
+  void (*launch)(fq_ctx*, const fq_mesh*, size_t, size_t, int, const SlabPtrs&);
 };
 
 template <class Fn, int NE>
-static void launch_gen(fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int nouts, double* d_out) {
+static void launch_gen(fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int max_t, const SlabPtrs& slabs) {
   const size_t nc = c1 - c0;
   if (nc == 0) return;
   const int block = 128;
-  const int grid = grid_for(nc, block, ctx->sm_count, 16);
-  elmat_gen_kernel<Fn, NE><<<grid, block, 0, ctx->stream>>>(Fn{}, mesh->cell_faces[1].p, mesh->lengths.p,
-                                                            uint32_t(mesh->edge_lo), c0, nc, nouts, d_out);
+  const size_t smem = size_t(block / 32) * size_t(max_t) * kStagePad * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQ_CUDA(cudaFuncSetAttribute(elmat_gen_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const int grid = grid_for((nc + 31) / 32 * 32, block, ctx->sm_count, 4);
+  elmat_gen_kernel<Fn, NE><<<grid, block, smem, ctx->stream>>>(Fn{}, mesh->cell_faces[1].p, mesh->lengths.p,
+                                                               uint32_t(mesh->edge_lo), c0, nc, max_t, slabs);
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
 }
 
-#define FQ_ENTRY(fn, n, fk, kind, grade, nin, nout)                                              \
-  GenEntry{n, fk, kind, grade, nin, nout,                                                        \
-           [](fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, double* d_out) {           \
-             launch_gen<Fn_##fn, nin>(ctx, mesh, c0, c1, nout, d_out);                           \
+#define FQ_ENTRY(fn, n, fk, kind, grade, nin, nout)                                                        \
+  GenEntry{n, fk, kind, grade, nin, nout,                                                                  \
+           [](fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int max_t, const SlabPtrs& slabs) {  \
+             launch_gen<Fn_##fn, nin>(ctx, mesh, c0, c1, max_t, slabs);                                    \
            }},
 static const GenEntry g_entries[] = {FQ_GEN_ELMAT_LIST(FQ_ENTRY)};
 #undef FQ_ENTRY
@@ -97,16 +135,17 @@ static const GenEntry* find_generated(int dim, const std::vector<BlockSpec>& blo
   return nullptr;
 }
 
+static int block_nouts(int dim, const BlockSpec& b) {
+  int tg, rg;
+  kind_grades(b.kind, b.grade, tg, rg);
+  return nlocal(dim, tg) * nlocal(dim, rg);
+}
+
 bool elmat_has_generated(int dim, const std::vector<BlockSpec>& blocks) { return find_generated(dim, blocks) != nullptr; }
 
 int elmat_nouts(int dim, const std::vector<BlockSpec>& blocks) {
   int total = 0;
-  for (const BlockSpec& b : blocks) {
-    int tg, rg;
-    kind_grades(b.kind, b.grade, tg, rg);
-    if (b.kind == KIND_LUMPED) tg = rg = 0;
-    total += nlocal(dim, tg) * nlocal(dim, rg);
-  }
+  for (const BlockSpec& b : blocks) total += block_nouts(dim, b);
   return total;
 }
 
@@ -302,20 +341,13 @@ static TapeDev* get_tape(fq_ctx* ctx, int dim, const std::vector<BlockSpec>& blo
   return td;
 }
 
-int elmat_to_slab(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>& blocks, size_t c0, size_t c1,
-                  bool use_generated, double* d_out, int* d_err) {
+// Runs the interpreter for ONE block into its cell-major slab.
+static void interp_block(fq_ctx* ctx, const fq_mesh* mesh, const BlockSpec& blk, size_t c0, size_t c1, double* d_out,
+                         int* d_err) {
   const int dim = mesh->dim;
-  FQ_REQUIRE(dim >= 1 && dim <= kMaxDim, "element kernels support 1 <= dim <= 10");
-  FQ_REQUIRE(c0 <= c1 && c1 <= mesh->ncells, "cell range out of bounds");
-  const int nouts = elmat_nouts(dim, blocks);
-  if (c1 == c0 || nouts == 0) return nouts;
-  if (use_generated) {
-    if (const GenEntry* e = find_generated(dim, blocks)) {
-      e->launch(ctx, mesh, c0, c1, d_out);
-      return nouts;
-    }
-  }
-  TapeDev* td = get_tape(ctx, dim, blocks);
+  const int nouts = block_nouts(dim, blk);
+  if (nouts == 0) return;
+  TapeDev* td = get_tape(ctx, dim, {blk});
   const Tape& t = td->tape;
   FQ_REQUIRE(t.nouts <= nouts, "tape output count mismatch");
   const int block = 128;
@@ -335,7 +367,28 @@ int elmat_to_slab(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch is freed on return
-  return nouts;
+}
+
+void elmat_to_slabs(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>& blocks, size_t c0, size_t c1,
+                    bool use_generated, double* const* d_outs, int* d_err) {
+  const int dim = mesh->dim;
+  FQ_REQUIRE(dim >= 1 && dim <= kMaxDim, "element kernels support 1 <= dim <= 10");
+  FQ_REQUIRE(c0 <= c1 && c1 <= mesh->ncells, "cell range out of bounds");
+  FQ_REQUIRE(int(blocks.size()) <= kMaxBlocks, "too many fused blocks");
+  if (c1 == c0 || elmat_nouts(dim, blocks) == 0) return;
+  if (use_generated) {
+    if (const GenEntry* e = find_generated(dim, blocks)) {
+      SlabPtrs sp{};
+      int max_t = 1;
+      for (size_t b = 0; b < blocks.size(); ++b) {
+        sp.p[b] = d_outs[b];
+        max_t = std::max(max_t, block_nouts(dim, blocks[b]));
+      }
+      e->launch(ctx, mesh, c0, c1, max_t, sp);
+      return;
+    }
+  }
+  for (size_t b = 0; b < blocks.size(); ++b) interp_block(ctx, mesh, blocks[b], c0, c1, d_outs[b], d_err);
 }
 
 }  // namespace fq

@@ -5,11 +5,11 @@
 namespace fq {
 
 // ---- elmat.cu
-// Element matrices of cells [c0, c1) (local cell indices) of one block or of
-// the fused blocks of hodge_blocks(k) into a device slab, AoS:
-// out[(c - c0) * nouts + e].  Returns nouts.
-int elmat_to_slab(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>& blocks, size_t c0, size_t c1,
-                  bool use_generated, double* d_out, int* d_err);
+// Element matrices of cells [c0, c1) (local cell indices) of one block, or of
+// the fused blocks of hodge_blocks(k), into per-block cell-major device slabs:
+// d_outs[b][(c - c0) * T_b + e].
+void elmat_to_slabs(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpec>& blocks, size_t c0, size_t c1,
+                    bool use_generated, double* const* d_outs, int* d_err);
 int elmat_nouts(int dim, const std::vector<BlockSpec>& blocks);
 bool elmat_has_generated(int dim, const std::vector<BlockSpec>& blocks);
 
@@ -21,6 +21,8 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
 void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
                        fq_csr* out);
 void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros);
+// fused numeric phase of several blocks sharing one element kernel launch (HodgeBlocks)
+void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros);
 
 // ---- spmv.cu
 void spmv_prepare(fq_ctx* ctx, fq_csr* a);

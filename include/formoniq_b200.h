@@ -36,6 +36,7 @@ typedef struct fq_ctx fq_ctx;
 typedef struct fq_mesh fq_mesh;
 typedef struct fq_csr fq_csr;
 typedef struct fq_vec fq_vec;
+typedef struct fq_hodge fq_hodge;
 
 /* formoniq/src/operators.rs:169-191 (the four WhitneyPairing constructors) and
  * :27-40 (ScalarLumpedMass).  `grade` is always the grade of the inner
@@ -134,6 +135,19 @@ int fq_assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, 
 int fq_assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, int drop_exact_zeros);
 /* one-shot convenience: symbolic + numeric */
 int fq_assemble(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, int drop_exact_zeros, fq_csr** out);
+
+/* HodgeBlocks::compute (formoniq/src/hodge.rs:62-72): the four blocks of a mixed
+ * problem posed at `grade` — mass(grade-1), mass(grade), dif_test(grade),
+ * dif_both(grade+1) — with ONE fused element kernel per numeric pass (the cell
+ * metric, its inverse and the shared masses are evaluated once per cell instead
+ * of once per block).  sigma rows = simplices of grade-1, u rows = grade.
+ * fq_hodge_block borrows block `which` (0 mass_sigma, 1 mass_u, 2 dif_test,
+ * 3 dif_both); it stays owned by the fq_hodge. */
+int fq_hodge_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int grade, size_t sigma_row_begin, size_t sigma_row_end,
+                      size_t u_row_begin, size_t u_row_end, fq_hodge** out);
+int fq_hodge_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_hodge* blocks, int drop_exact_zeros);
+fq_csr* fq_hodge_block(fq_hodge* blocks, int which);
+int fq_hodge_destroy(fq_hodge* blocks);
 
 /* ---- CSR matrices ----------------------------------------------------------
  * The data contract of nalgebra_sparse::CsrMatrix<f64> handed to faer by

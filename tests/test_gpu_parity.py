@@ -204,6 +204,44 @@ def test_assembly_pattern_bit_exact_and_values(fq, ctx, dim, shape, variant, k):
                 assert same_bits_mod_zero_sign(va, eva), (kind, g, drop)
 
 
+@pytest.mark.parametrize("dim,shape,variant,k", [(2, [6, 5], "plain", 1), (2, [4, 4], "jitter", 2), (3, [4, 4, 4], "plain", 1),
+                                                  (3, [3, 2, 3], "jitter", 1), (3, [3, 3, 3], "minkowski", 2),
+                                                  (3, [2, 2, 2], "plain", 0), (3, [2, 2, 2], "jitter", 3),
+                                                  (4, [2, 2, 1, 2], "jitter", 2), (1, [7], "plain", 1)])
+def test_fused_hodge_blocks_match_the_oracle(fq, ctx, dim, shape, variant, k):
+    # hodge.rs:62-72 with one fused element kernel; re-running the numeric phase hits the cached-pattern fast path
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    hb = fq.HodgeBlocks.compute(mesh, k)
+    specs = [(O.MASS, k - 1), (O.MASS, k), (O.DIF_TEST, k), (O.DIF_BOTH, k + 1)]
+    for rerun in range(2):
+        for blk, (kind, g) in zip(hb.blocks, specs):
+            tg, rg = O.kind_grades(kind, g)
+            if tg < 0 or rg < 0:
+                assert blk.nnz == 0
+                continue
+            ref = cx.assemble(s, kind, g)
+            rp, ci, va = blk.download()
+            erp, eci, eva = ref.arrays()
+            assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci), (kind, g, rerun)
+            assert_values_close(va, eva)
+            if dim <= 3:
+                assert same_bits_mod_zero_sign(va, eva)
+        hb.numeric(mesh)
+    # new geometry through the cached pattern: the classification change must be detected
+    _, s2, *_ = kuhn_problem(dim, shape, jitter=variant != "jitter", minkowski=False)
+    mesh.set_lengths(s2)
+    hb.numeric(mesh)
+    for blk, (kind, g) in zip(hb.blocks, specs):
+        tg, rg = O.kind_grades(kind, g)
+        if tg < 0 or rg < 0:
+            continue
+        ref = cx.assemble(s2, kind, g)
+        rp, ci, va = blk.download()
+        assert np.array_equal(rp.astype(np.int64), ref.arrays()[0]) and np.array_equal(ci.astype(np.int64), ref.arrays()[1])
+        assert_values_close(va, ref.arrays()[2])
+
+
 def test_assembly_empty_spaces_have_the_right_shape(fq, ctx):
     # whitney_complex.rs:113-122: grades off [0,n] give correctly shaped empty matrices
     cx, s, *_ = kuhn_problem(2, [3, 3])
