@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include "internal.hpp"
+#include "stream.cuh"
 
 namespace fq {
 
@@ -206,43 +207,40 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
   FQ_CUDA(cudaGetLastError());
   out->s_values.alloc(s_nnz ? s_nnz : 1);
   out->keep.alloc(s_nnz ? s_nnz : 1);
+  stream_build_blocks(ctx, out->contrib_ptr.p, s_nnz, out->ncontrib, out->gather_blocks, out->ngather_blocks);
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // ------------------------------------------------------------------ numeric
-// One thread per structural non-zero: ordered sum of its contributions and the
-// "any contribution != 0.0" flag of galerkin.rs:173.
+// K3 is a segmented reduction over the element slab: one segment per structural
+// non-zero, items = its contributions in ascending cell order (stream.cuh).
+// Every segment also yields the "some contribution != 0.0" flag of galerkin.rs:173.
 //
-// MODE 0: structural output  values[q] = sum, keep[q] = any   (first pass / no dropping)
-// MODE 1: cached compaction  values[pos[q]] = sum for kept entries; if the
-//         zero/non-zero classification differs from the cached one (the geometry
-//         changed), raise *changed so the host redoes the compaction.
-template <int MODE>
-__global__ void __launch_bounds__(256) num_gather_kernel(const double* __restrict__ slab,
-                                                          const uint32_t* __restrict__ contrib_ptr,
-                                                          const uint32_t* __restrict__ contrib_src, uint32_t s_nnz,
-                                                          double* __restrict__ values, uint8_t* __restrict__ keep,
-                                                          const uint32_t* __restrict__ pos, int* __restrict__ changed) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < s_nnz; q += stride) {
-    const uint32_t b = contrib_ptr[q], e = contrib_ptr[q + 1];
-    double acc = 0.0;
-    bool any = false;
-    for (uint32_t p = b; p < e; ++p) {
-      const double v = slab[contrib_src[p]];
-      any = any || (v != 0.0);
-      acc = __dadd_rn(acc, v);
-    }
-    if (MODE == 0) {
-      values[q] = acc;
-      keep[q] = any ? 1 : 0;
-    } else {
-      const bool kept = keep[q] != 0;
-      if (kept != any) *changed = 1;
-      if (kept) values[pos[q]] = acc;
-    }
+// GatherStructural: values[q] = sum, keep[q] = any   (first pass / no dropping)
+// GatherCompacted:  values[pos[q]] = sum for kept entries; if the zero/non-zero
+//   classification differs from the cached one (the geometry changed), raise
+//   *changed so the host redoes the compaction.
+struct GatherStructural {
+  static constexpr bool kHasValues = false;
+  double* __restrict__ values;
+  uint8_t* __restrict__ keep;
+  __device__ __forceinline__ void store(uint32_t q, double sum, bool any) const {
+    values[q] = sum;
+    keep[q] = any ? 1 : 0;
   }
-}
+};
+struct GatherCompacted {
+  static constexpr bool kHasValues = false;
+  double* __restrict__ values;
+  const uint8_t* __restrict__ keep;
+  const uint32_t* __restrict__ pos;
+  int* __restrict__ changed;
+  __device__ __forceinline__ void store(uint32_t q, double sum, bool any) const {
+    const bool kept = keep[q] != 0;
+    if (kept != any) *changed = 1;
+    if (kept) values[pos[q]] = sum;
+  }
+};
 
 __global__ void num_keep_to_u32(const uint8_t* __restrict__ keep, uint32_t n, uint32_t* __restrict__ out) {
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -267,11 +265,8 @@ __global__ void num_rowptr_kernel(const uint32_t* __restrict__ s_row_ptr, const 
 
 static void gather_structural(fq_ctx* ctx, fq_csr* csr) {
   ScopedSpan span(ctx, "k3_gather");
-  num_gather_kernel<0><<<grid_for(csr->s_nnz, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(
-      csr->slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(csr->s_nnz), csr->s_values.p, csr->keep.p, nullptr,
-      nullptr);
-  fq_count_launch(ctx);
-  FQ_CUDA(cudaGetLastError());
+  stream_reduce(ctx, csr->gather_blocks.p, csr->ngather_blocks, csr->contrib_ptr.p, csr->contrib_src.p, nullptr, csr->slab.p,
+                GatherStructural{csr->s_values.p, csr->keep.p});
 }
 
 // After K1 filled csr->slab: reduce into the CSR values under the requested pattern semantics.
@@ -300,11 +295,8 @@ static void numeric_reduce(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool d
     csr->nnz = s_nnz;
     if (s_nnz) {
       ScopedSpan span(ctx, "k3_gather");
-      num_gather_kernel<0><<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
-          csr->slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->values.p, csr->keep.p, nullptr,
-          nullptr);
-      fq_count_launch(ctx);
-      FQ_CUDA(cudaGetLastError());
+      stream_reduce(ctx, csr->gather_blocks.p, csr->ngather_blocks, csr->contrib_ptr.p, csr->contrib_src.p, nullptr,
+                    csr->slab.p, GatherStructural{csr->values.p, csr->keep.p});
     }
     csr->assembly_bytes += int64_t(8 * s_nnz);
     return;
@@ -314,11 +306,8 @@ static void numeric_reduce(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool d
     {
       ScopedSpan span(ctx, "k3_gather");
       FQ_CUDA(cudaMemsetAsync(csr->d_changed.p, 0, sizeof(int), ctx->stream));
-      num_gather_kernel<1><<<grid_for(s_nnz, block, ctx->sm_count, 16), block, 0, ctx->stream>>>(
-          csr->slab.p, csr->contrib_ptr.p, csr->contrib_src.p, uint32_t(s_nnz), csr->values.p, csr->keep.p, csr->pos.p,
-          csr->d_changed.p);
-      fq_count_launch(ctx);
-      FQ_CUDA(cudaGetLastError());
+      stream_reduce(ctx, csr->gather_blocks.p, csr->ngather_blocks, csr->contrib_ptr.p, csr->contrib_src.p, nullptr,
+                    csr->slab.p, GatherCompacted{csr->values.p, csr->keep.p, csr->pos.p, csr->d_changed.p});
     }
     int changed = 0;
     FQ_CUDA(cudaMemcpyAsync(&changed, csr->d_changed.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -178,6 +178,8 @@ struct fq_csr {
   fq::DevBuf<double> slab;          // [ncells][el_rows*el_cols] element slab, persistent
   fq::DevBuf<uint32_t> pos;         // [s_nnz+1] structural -> compacted index (exclusive scan of keep)
   fq::DevBuf<int> d_changed;        // device flag: classification differs from the cached pattern
+  fq::DevBuf<uint32_t> gather_blocks;  // stream blocks over contrib_ptr (K3)
+  size_t ngather_blocks = 0;
   bool dropped = false;
   bool compact_valid = false;       // pos / keep / compacted pattern describe the last geometry
   bool pattern_valid = false;

@@ -1,0 +1,161 @@
+// stream.cuh — the segmented-reduction engine shared by K3 (assembly gather)
+// and K4 (CSR SpMV): "CSR-stream".
+//
+// A CTA owns a block of consecutive segments (CSR rows / structural non-zeros)
+// whose items fit a shared-memory chunk.
+//   phase 1  every thread issues UNROLL independent (index, value) loads and
+//            then UNROLL independent gathers  src[index]  before touching
+//            shared memory — enough bytes in flight per SM to cover HBM latency
+//            (the v1 kernel had one dependent load chain per thread and sat at
+//            ~45 % of DRAM bandwidth with full occupancy);
+//   phase 2  one thread per segment adds the staged items left to right, i.e.
+//            in the reference's serial order (no FMA), so results are
+//            bit-identical to the CPU path.
+// Blocks are cut on the device: block b starts at the first segment whose
+// offset is >= b * kChunk (binary search), so a block holds < kChunk + maxlen
+// items; blocks that do not fit the staging buffer (a segment longer than the
+// slack) take a block-wide strided fallback.
+#pragma once
+#include "common.cuh"
+
+namespace fq {
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamChunk = 4096;             // target items per block
+constexpr int kStreamCap = kStreamChunk + 1024;  // staging capacity (doubles)
+constexpr int kStreamUnroll = 8;
+
+static __global__ void stream_blocks_kernel(const uint32_t* __restrict__ seg_ptr, uint32_t nseg, uint32_t nblocks,
+                                     uint32_t* __restrict__ blocks) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nblocks) return;
+  if (b == nblocks) {
+    blocks[b] = nseg;
+    return;
+  }
+  const uint32_t target = b * uint32_t(kStreamChunk);
+  uint32_t lo = 0, hi = nseg;  // first segment with seg_ptr[s] >= target
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (seg_ptr[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  blocks[b] = lo;
+}
+
+// Builds the block table for `nseg` segments with `nitems` items in total.
+inline void stream_build_blocks(fq_ctx* ctx, const uint32_t* seg_ptr, size_t nseg, size_t nitems, DevBuf<uint32_t>& blocks,
+                                size_t& nblocks) {
+  nblocks = nseg == 0 ? 0 : (nitems + kStreamChunk - 1) / kStreamChunk;
+  if (nblocks == 0 && nseg > 0) nblocks = 1;  // only empty segments
+  blocks.alloc(nblocks + 1);
+  if (nseg == 0) {
+    FQ_CUDA(cudaMemsetAsync(blocks.p, 0, sizeof(uint32_t), ctx->stream));
+    return;
+  }
+  stream_blocks_kernel<<<unsigned((nblocks + 1 + 255) / 256), 256, 0, ctx->stream>>>(seg_ptr, uint32_t(nseg),
+                                                                                    uint32_t(nblocks), blocks.p);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
+
+// Policy interface:
+//   static constexpr bool kHasValues;
+//   __device__ void store(uint32_t seg, double sum, bool any_nonzero) const;
+template <class Policy>
+__global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uint32_t* __restrict__ blocks,
+                                                                        uint32_t nblocks,
+                                                                        const uint32_t* __restrict__ seg_ptr,
+                                                                        const uint32_t* __restrict__ index,
+                                                                        const double* __restrict__ values,
+                                                                        const double* __restrict__ src, Policy policy) {
+  __shared__ double stage[kStreamCap];
+  __shared__ double red[kStreamThreads / 32];
+  __shared__ int red_any[kStreamThreads / 32];
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const uint32_t s0 = blocks[b], s1 = blocks[b + 1];
+    if (s0 >= s1) continue;
+    const uint32_t p0 = seg_ptr[s0], p1 = seg_ptr[s1];
+    const uint32_t cnt = p1 - p0;
+    if (cnt <= uint32_t(kStreamCap)) {
+      // ---- phase 1: coalesced, unrolled loads; all gathers of a batch in flight together
+      for (uint32_t base = 0; base < cnt; base += kStreamThreads * kStreamUnroll) {
+        uint32_t idx[kStreamUnroll];
+        double val[kStreamUnroll];
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+          const uint32_t k = base + u * kStreamThreads + threadIdx.x;
+          idx[u] = k < cnt ? __ldg(index + p0 + k) : 0u;
+          if (Policy::kHasValues) val[u] = k < cnt ? __ldg(values + p0 + k) : 0.0;
+        }
+        double g[kStreamUnroll];
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+          const uint32_t k = base + u * kStreamThreads + threadIdx.x;
+          g[u] = k < cnt ? __ldg(src + idx[u]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+          const uint32_t k = base + u * kStreamThreads + threadIdx.x;
+          if (k < cnt) stage[k] = Policy::kHasValues ? __dmul_rn(val[u], g[u]) : g[u];
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: one thread per segment, left-to-right sum
+      for (uint32_t s = s0 + threadIdx.x; s < s1; s += kStreamThreads) {
+        const uint32_t b0 = seg_ptr[s] - p0, b1 = seg_ptr[s + 1] - p0;
+        double acc = 0.0;
+        bool any = false;
+        for (uint32_t q = b0; q < b1; ++q) {
+          const double v = stage[q];
+          any = any || (v != 0.0);
+          acc = __dadd_rn(acc, v);
+        }
+        policy.store(s, acc, any);
+      }
+      __syncthreads();
+    } else {
+      // ---- fallback: segments too long for the staging buffer (tree order)
+      for (uint32_t s = s0; s < s1; ++s) {
+        const uint32_t b0 = seg_ptr[s], b1 = seg_ptr[s + 1];
+        double acc = 0.0;
+        int any = 0;
+        for (uint32_t p = b0 + threadIdx.x; p < b1; p += kStreamThreads) {
+          const double g = __ldg(src + __ldg(index + p));
+          const double v = Policy::kHasValues ? __dmul_rn(__ldg(values + p), g) : g;
+          any |= (v != 0.0);
+          acc = __dadd_rn(acc, v);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
+          any |= __shfl_down_sync(0xffffffffu, any, o);
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc, red_any[threadIdx.x >> 5] = any;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t = 0.0;
+          int a = 0;
+          for (int w = 0; w < kStreamThreads / 32; ++w) t = __dadd_rn(t, red[w]), a |= red_any[w];
+          policy.store(s, t, a != 0);
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+template <class Policy>
+inline void stream_reduce(fq_ctx* ctx, const uint32_t* blocks, size_t nblocks, const uint32_t* seg_ptr,
+                          const uint32_t* index, const double* values, const double* src, const Policy& policy) {
+  if (nblocks == 0) return;
+  const size_t cap = size_t(ctx->sm_count) * 5;  // 5 CTAs of 40 KB staging fit one SM
+  const int grid = int(nblocks < cap ? nblocks : cap);
+  stream_reduce_kernel<Policy><<<grid, kStreamThreads, 0, ctx->stream>>>(blocks, uint32_t(nblocks), seg_ptr, index, values,
+                                                                         src, policy);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
+
+}  // namespace fq

@@ -1,0 +1,195 @@
+//! formoniq-b200: the CUDA assembly path behind formoniq's own traits.
+//!
+//! Three seams, all monomorphised generics in the reference:
+//!  1. `BilinearForm::assemble`      (formoniq/src/galerkin.rs:52-57)   -> `GpuPairing`
+//!  2. `HilbertComplex::assemble`    (formoniq/src/whitney_complex.rs:66) -> `GpuWhitneyComplex`
+//!  3. `LinearOperator` + `InnerProductSpace` (iterative/src/lib.rs:84-157) -> `DeviceCsr`, `DeviceVector`
+//!
+//! Source form only: this image has no Rust toolchain, so the crate is
+//! exercised through the same C ABI from C++/Python tests instead.
+#![allow(non_camel_case_types)]
+use std::{ffi::{c_char, c_double, c_int, c_void, CStr}, ptr};
+
+use formoniq::{galerkin::{BilinearForm, GalerkinMatrix}, operators::WhitneyPairing};
+use iterative::{InnerProductSpace, LinearOperator};
+use nalgebra_sparse::CsrMatrix;
+use regge::lengths::mesh::MeshLengthsSq;
+use simplicial::topology::{complex::Complex, incidence::FaceIncidence};
+
+#[repr(C)] pub struct fq_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct fq_mesh { _p: [u8; 0] }
+#[repr(C)] pub struct fq_csr { _p: [u8; 0] }
+#[repr(C)] pub struct fq_vec { _p: [u8; 0] }
+
+// include/formoniq_b200.h
+unsafe extern "C" {
+  fn fq_last_error() -> *const c_char;
+  fn fq_ctx_create(device: c_int, out: *mut *mut fq_ctx) -> c_int;
+  fn fq_ctx_destroy(ctx: *mut fq_ctx) -> c_int;
+  fn fq_mesh_create(ctx: *mut fq_ctx, dim: c_int, ncells: usize, nsimplices: *const usize,
+                    cell_faces: *const *const u64, edge_lengths_sq: *const c_double, out: *mut *mut fq_mesh) -> c_int;
+  fn fq_mesh_destroy(mesh: *mut fq_mesh) -> c_int;
+  fn fq_assemble(ctx: *mut fq_ctx, mesh: *const fq_mesh, kind: c_int, grade: c_int, drop_exact_zeros: c_int,
+                 out: *mut *mut fq_csr) -> c_int;
+  fn fq_csr_shape(csr: *const fq_csr, nrows: *mut usize, ncols: *mut usize, nnz: *mut usize) -> c_int;
+  fn fq_csr_download(ctx: *mut fq_ctx, csr: *const fq_csr, row_offsets: *mut usize, col_indices: *mut usize,
+                     values: *mut c_double) -> c_int;
+  fn fq_csr_upload(ctx: *mut fq_ctx, nrows: usize, ncols: usize, row_offsets: *const usize, col_indices: *const usize,
+                   values: *const c_double, out: *mut *mut fq_csr) -> c_int;
+  fn fq_csr_destroy(csr: *mut fq_csr) -> c_int;
+  fn fq_vec_create(ctx: *mut fq_ctx, n: usize, out: *mut *mut fq_vec) -> c_int;
+  fn fq_vec_destroy(v: *mut fq_vec) -> c_int;
+  fn fq_vec_len(v: *const fq_vec) -> usize;
+  fn fq_vec_upload(ctx: *mut fq_ctx, v: *mut fq_vec, host: *const c_double) -> c_int;
+  fn fq_vec_download(ctx: *mut fq_ctx, v: *const fq_vec, host: *mut c_double) -> c_int;
+  fn fq_vec_copy(ctx: *mut fq_ctx, dst: *mut fq_vec, src: *const fq_vec) -> c_int;
+  fn fq_vec_dot(ctx: *mut fq_ctx, x: *const fq_vec, y: *const fq_vec, out: *mut c_double) -> c_int;
+  fn fq_vec_scale(ctx: *mut fq_ctx, x: *mut fq_vec, alpha: c_double) -> c_int;
+  fn fq_vec_axpy(ctx: *mut fq_ctx, y: *mut fq_vec, alpha: c_double, x: *const fq_vec) -> c_int;
+  fn fq_spmv(ctx: *mut fq_ctx, a: *const fq_csr, x: *const fq_vec, y: *mut fq_vec) -> c_int;
+}
+
+/// The reference panics on contract violations (`galerkin.rs:184` unwraps);
+/// the shim keeps that behaviour at the Rust boundary.
+fn check(rc: c_int) {
+  if rc != 0 {
+    let msg = unsafe { CStr::from_ptr(fq_last_error()) }.to_string_lossy().into_owned();
+    panic!("formoniq_b200 error {rc}: {msg}");
+  }
+}
+
+/// One CUDA device. `Sync` because every entry point serialises on the
+/// context's stream (seam 1 needs `BilinearForm: Sync`).
+pub struct Device(*mut fq_ctx);
+unsafe impl Send for Device {}
+unsafe impl Sync for Device {}
+impl Device {
+  pub fn new(index: i32) -> Self {
+    let mut ctx = ptr::null_mut();
+    check(unsafe { fq_ctx_create(index, &mut ctx) });
+    Self(ctx)
+  }
+}
+impl Drop for Device { fn drop(&mut self) { unsafe { fq_ctx_destroy(self.0) }; } }
+
+/// `Complex` + `MeshLengthsSq` uploaded once: the FaceIncidence tables of every
+/// grade (incidence.rs:42-53) and the edge lengths (lengths/mesh.rs:34-36).
+pub struct DeviceMesh<'d> { dev: &'d Device, raw: *mut fq_mesh, dim: usize }
+impl<'d> DeviceMesh<'d> {
+  pub fn new(dev: &'d Device, topology: &Complex, geometry: &MeshLengthsSq) -> Self {
+    let dim = topology.dim().index();
+    let nsimplices: Vec<usize> = (0..=dim).map(|j| topology.nsimplices(j)).collect();
+    let tables: Vec<Vec<u64>> = (0..=dim)
+      .map(|j| FaceIncidence::new(topology, j).faces_flat().iter().map(|&i| i as u64).collect())
+      .collect();
+    let ptrs: Vec<*const u64> = tables.iter().map(|t| t.as_ptr()).collect();
+    let mut raw = ptr::null_mut();
+    check(unsafe {
+      fq_mesh_create(dev.0, dim as c_int, topology.cells().len(), nsimplices.as_ptr(), ptrs.as_ptr(),
+                     geometry.vector().as_ptr(), &mut raw)
+    });
+    Self { dev, raw, dim }
+  }
+}
+impl Drop for DeviceMesh<'_> { fn drop(&mut self) { unsafe { fq_mesh_destroy(self.raw) }; } }
+
+fn download(dev: &Device, csr: *mut fq_csr) -> GalerkinMatrix {
+  let (mut nr, mut nc, mut nnz) = (0usize, 0usize, 0usize);
+  check(unsafe { fq_csr_shape(csr, &mut nr, &mut nc, &mut nnz) });
+  let (mut rp, mut ci, mut va) = (vec![0usize; nr + 1], vec![0usize; nnz], vec![0f64; nnz]);
+  check(unsafe { fq_csr_download(dev.0, csr, rp.as_mut_ptr(), ci.as_mut_ptr(), va.as_mut_ptr()) });
+  unsafe { fq_csr_destroy(csr) };
+  // the data contract handed to faer by linalg/faer.rs:16-24
+  CsrMatrix::try_from_csr_data(nr, nc, rp, ci, va).unwrap()
+}
+
+/// Seam 1: a `BilinearForm` whose *provided* `assemble` (galerkin.rs:52-57) is
+/// overridden to run on the GPU; `element` stays the reference's own, so the
+/// CPU parity check is one call away.
+pub struct GpuPairing<'d> { dev: &'d Device, kind: c_int, grade: c_int, cpu: WhitneyPairing }
+impl<'d> GpuPairing<'d> {
+  // operators.rs:169-191: the four constructors, grade = grade of the inner product
+  pub fn mass(dev: &'d Device, dim: usize, grade: usize) -> Self {
+    Self { dev, kind: 0, grade: grade as c_int, cpu: WhitneyPairing::mass(dim, grade) }
+  }
+  pub fn dif_trial(dev: &'d Device, dim: usize, grade: usize) -> Self {
+    Self { dev, kind: 1, grade: grade as c_int, cpu: WhitneyPairing::dif_trial(dim, grade) }
+  }
+  pub fn dif_test(dev: &'d Device, dim: usize, grade: usize) -> Self {
+    Self { dev, kind: 2, grade: grade as c_int, cpu: WhitneyPairing::dif_test(dim, grade) }
+  }
+  pub fn dif_both(dev: &'d Device, dim: usize, grade: usize) -> Self {
+    Self { dev, kind: 3, grade: grade as c_int, cpu: WhitneyPairing::dif_both(dim, grade) }
+  }
+}
+impl BilinearForm for GpuPairing<'_> {
+  fn test_grade(&self) -> multialgebra::ExteriorGrade { self.cpu.test_grade() }
+  fn trial_grade(&self) -> multialgebra::ExteriorGrade { self.cpu.trial_grade() }
+  fn element(&self, metric: &metric::Metric, chart: simplicial::atlas::Chart) -> simplicial::linalg::Matrix {
+    self.cpu.element(metric, chart)
+  }
+  fn assemble(&self, topology: &Complex, geometry: &MeshLengthsSq) -> GalerkinMatrix {
+    let mesh = DeviceMesh::new(self.dev, topology, geometry);
+    let mut csr = ptr::null_mut();
+    check(unsafe { fq_assemble(self.dev.0, mesh.raw, self.kind, self.grade, 1, &mut csr) });
+    download(self.dev, csr)
+  }
+}
+// Seam 2 needs no code: `WhitneyComplex::assemble` (whitney_complex.rs:407-409) calls
+// `form.assemble(topology, geometry)`, so `complex.pairing(&GpuPairing::mass(..))`,
+// `HodgeBlocks::compute` and everything in `problems::*` reach the GPU through seam 1.
+// A caller that assembles several blocks on one mesh keeps a `DeviceMesh` and calls
+// `fq_hodge_symbolic` / `fq_hodge_numeric` (one fused element kernel for the four blocks).
+
+/// Seam 3a: a vector that does not live in host memory (iterative/src/lib.rs:58-84).
+pub struct DeviceVector<'d> { dev: &'d Device, raw: *mut fq_vec }
+impl Clone for DeviceVector<'_> {
+  fn clone(&self) -> Self {
+    let out = self.zeros_like();
+    check(unsafe { fq_vec_copy(self.dev.0, out.raw, self.raw) });
+    out
+  }
+}
+impl Drop for DeviceVector<'_> { fn drop(&mut self) { unsafe { fq_vec_destroy(self.raw) }; } }
+impl InnerProductSpace for DeviceVector<'_> {
+  type Scalar = f64;
+  fn zeros_like(&self) -> Self {
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_vec_create(self.dev.0, fq_vec_len(self.raw), &mut raw) });
+    Self { dev: self.dev, raw }
+  }
+  fn dot(&self, other: &Self) -> f64 {
+    let mut out = 0.0;
+    check(unsafe { fq_vec_dot(self.dev.0, self.raw, other.raw, &mut out) });
+    out
+  }
+  fn scale(&mut self, alpha: f64) { check(unsafe { fq_vec_scale(self.dev.0, self.raw, alpha) }); }
+  fn add_scaled(&mut self, alpha: f64, x: &Self) { check(unsafe { fq_vec_axpy(self.dev.0, self.raw, alpha, x.raw) }); }
+}
+
+/// Seam 3b: the assembled operator applied on the device (iterative/src/operator.rs:5-14).
+pub struct DeviceCsr<'d> { dev: &'d Device, raw: *mut fq_csr, n: usize }
+impl<'d> DeviceCsr<'d> {
+  pub fn upload(dev: &'d Device, m: &CsrMatrix<f64>) -> Self {
+    let mut raw = ptr::null_mut();
+    check(unsafe {
+      fq_csr_upload(dev.0, m.nrows(), m.ncols(), m.row_offsets().as_ptr(), m.col_indices().as_ptr(),
+                    m.values().as_ptr(), &mut raw)
+    });
+    Self { dev, raw, n: m.nrows() }
+  }
+}
+impl Drop for DeviceCsr<'_> { fn drop(&mut self) { unsafe { fq_csr_destroy(self.raw) }; } }
+impl<'d> LinearOperator for DeviceCsr<'d> {
+  type Space = DeviceVector<'d>;
+  fn dim(&self) -> usize { self.n }
+  fn apply(&self, x: &Self::Space) -> Self::Space {
+    let y = x.zeros_like();
+    check(unsafe { fq_spmv(self.dev.0, self.raw, x.raw, y.raw) });
+    y
+  }
+}
+// `iterative::krylov::{cg, minres}` now run unmodified on `DeviceCsr` with
+// `iterative::precond::Identity<DeviceVector>` (precond.rs:16-41).
+#[allow(dead_code)]
+fn _uses(_: *mut c_void) {}
