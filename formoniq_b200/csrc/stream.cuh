@@ -21,9 +21,10 @@
 namespace fq {
 
 constexpr int kStreamThreads = 256;
-constexpr int kStreamChunk = 4096;             // target items per block
-constexpr int kStreamCap = kStreamChunk + 1024;  // staging capacity (doubles)
-constexpr int kStreamUnroll = 8;
+constexpr int kStreamChunk = 2048;              // target items per block
+constexpr int kStreamCap = kStreamChunk + 512;  // staging capacity (doubles, 20 KB -> 8+ CTAs/SM)
+constexpr int kStreamUnroll = 8;                // gathers in flight per thread
+constexpr int kStreamSegRegs = 4;               // segment bounds preloaded per thread
 
 static __global__ void stream_blocks_kernel(const uint32_t* __restrict__ seg_ptr, uint32_t nseg, uint32_t nblocks,
                                      uint32_t* __restrict__ blocks) {
@@ -80,6 +81,14 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
     const uint32_t p0 = seg_ptr[s0], p1 = seg_ptr[s1];
     const uint32_t cnt = p1 - p0;
     if (cnt <= uint32_t(kStreamCap)) {
+      // segment bounds for phase 2, requested now so that their latency overlaps phase 1
+      uint32_t sb[kStreamSegRegs], se[kStreamSegRegs];
+#pragma unroll
+      for (int j = 0; j < kStreamSegRegs; ++j) {
+        const uint32_t s = s0 + j * kStreamThreads + threadIdx.x;
+        sb[j] = s < s1 ? __ldg(seg_ptr + s) : 0u;
+        se[j] = s < s1 ? __ldg(seg_ptr + s + 1) : 0u;
+      }
       // ---- phase 1: coalesced, unrolled loads; all gathers of a batch in flight together
       for (uint32_t base = 0; base < cnt; base += kStreamThreads * kStreamUnroll) {
         uint32_t idx[kStreamUnroll];
@@ -104,7 +113,21 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
       }
       __syncthreads();
       // ---- phase 2: one thread per segment, left-to-right sum
-      for (uint32_t s = s0 + threadIdx.x; s < s1; s += kStreamThreads) {
+#pragma unroll
+      for (int j = 0; j < kStreamSegRegs; ++j) {
+        const uint32_t s = s0 + j * kStreamThreads + threadIdx.x;
+        if (s < s1) {
+          double acc = 0.0;
+          bool any = false;
+          for (uint32_t q = sb[j] - p0; q < se[j] - p0; ++q) {
+            const double v = stage[q];
+            any = any || (v != 0.0);
+            acc = __dadd_rn(acc, v);
+          }
+          policy.store(s, acc, any);
+        }
+      }
+      for (uint32_t s = s0 + kStreamSegRegs * kStreamThreads + threadIdx.x; s < s1; s += kStreamThreads) {
         const uint32_t b0 = seg_ptr[s] - p0, b1 = seg_ptr[s + 1] - p0;
         double acc = 0.0;
         bool any = false;
@@ -150,7 +173,7 @@ template <class Policy>
 inline void stream_reduce(fq_ctx* ctx, const uint32_t* blocks, size_t nblocks, const uint32_t* seg_ptr,
                           const uint32_t* index, const double* values, const double* src, const Policy& policy) {
   if (nblocks == 0) return;
-  const size_t cap = size_t(ctx->sm_count) * 5;  // 5 CTAs of 40 KB staging fit one SM
+  const size_t cap = size_t(ctx->sm_count) * 8;  // 8 CTAs of 20 KB staging per SM
   const int grid = int(nblocks < cap ? nblocks : cap);
   stream_reduce_kernel<Policy><<<grid, kStreamThreads, 0, ctx->stream>>>(blocks, uint32_t(nblocks), seg_ptr, index, values,
                                                                          src, policy);
