@@ -166,6 +166,11 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints (e.g. NCCL's
+    # version banner) goes to stderr until the result is ready.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -308,7 +313,9 @@ def run_b200(args):
                                "nnz_per_s": cb["nnz_per_s"]}
     except Exception as exc:  # the oracle is only the checker; never let it break the GPU line
         out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
