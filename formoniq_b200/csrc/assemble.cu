@@ -349,7 +349,43 @@ static void numeric_reduce(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool d
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// The pattern the tile plan would be built from is the one the last slab pass left.
+static bool pattern_ready(const fq_csr* csr, bool drop) {
+  if (!csr->has_plan || csr->slab_passes < 1) return false;
+  if (csr->s_nnz == 0) return true;
+  return drop ? (csr->dropped && csr->compact_valid) : (!csr->dropped && csr->pattern_valid);
+}
+
 void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros) {
+  // ---- fast path: tile-fused K1+K3 (tile.cu), from the second numeric pass on
+  {
+    bool ready = nblocks >= 1 && mesh->vertex_tile.p != nullptr;
+    for (int b = 0; ready && b < nblocks; ++b)
+      ready = csrs[b]->ncells == mesh->ncells && csrs[b]->dim == mesh->dim && pattern_ready(csrs[b], drop_exact_zeros);
+    if (ready) {
+      std::shared_ptr<TilePlan> plan = csrs[0]->tile_plan;
+      if (plan && !tile_plan_matches(*plan, mesh, csrs, nblocks, drop_exact_zeros)) plan.reset();
+      if (!plan && csrs[0]->tile_refused == 0) {
+        plan = tile_plan_build(ctx, mesh, csrs, nblocks, drop_exact_zeros);
+        if (!plan) csrs[0]->tile_refused = 1;  // does not apply to this block set / mesh: stay on the slab path
+        if (plan)
+          for (int b = 0; b < nblocks; ++b) csrs[b]->slab.release();  // the slab is only needed by the slab path
+      }
+      for (int b = 0; b < nblocks; ++b) csrs[b]->tile_plan = plan;
+      if (plan) {
+        for (int b = 0; b < nblocks; ++b) csrs[b]->inv_diag.release();
+        if (tile_assemble(ctx, mesh, *plan)) {
+          const int ne = int(binom(mesh->dim + 1, 2));
+          for (int b = 0; b < nblocks; ++b)
+            csrs[b]->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csrs[b]->ncontrib +
+                                              8 * csrs[b]->nnz);
+          return;
+        }
+        // the zero / non-zero classification changed with the geometry: redo the slab pass
+        for (int b = 0; b < nblocks; ++b) csrs[b]->tile_plan.reset();
+      }
+    }
+  }
   std::vector<BlockSpec> blocks;
   std::vector<double*> outs;
   bool any_work = false;
@@ -376,7 +412,10 @@ void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csr
       }
     }
   }
-  for (int b = 0; b < nblocks; ++b) numeric_reduce(ctx, mesh, csrs[b], drop_exact_zeros);
+  for (int b = 0; b < nblocks; ++b) {
+    numeric_reduce(ctx, mesh, csrs[b], drop_exact_zeros);
+    csrs[b]->slab_passes += 1;
+  }
 }
 
 void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros) {

@@ -178,6 +178,7 @@ int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices
   FQ_CUDA(cudaMemcpyAsync(m->lengths.p, edge_lengths_sq, nsimplices[1] * sizeof(double), cudaMemcpyHostToDevice,
                           ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cell_faces[0]) tile_cluster_generic(ctx, m.get(), cell_faces[0]);
   *out = m.release();
   FQ_API_END
 }

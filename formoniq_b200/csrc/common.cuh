@@ -104,6 +104,7 @@ struct fq_ctx {
 inline void fq_count_launch(fq_ctx* ctx, int n = 1) { ctx->launches += n; }
 
 namespace fq {
+struct TilePlan;  // tile.cu: plan of the tile-fused numeric assembly
 // Brackets the kernels launched in its scope with two events when timing is on.
 struct ScopedSpan {
   fq_ctx* ctx;
@@ -147,6 +148,11 @@ struct fq_mesh {
   // rows owned under the owner-computes slab partition (== id range of the
   // simplices whose top vertex lies in the slab's own vertex layers)
   std::vector<size_t> own_lo, own_hi;
+  // vertex clustering for the tile-fused assembly (tile.cu): tile id of the held
+  // vertices [vtile_lo, vtile_lo + vertex_tile.n); empty when not clustered
+  fq::DevBuf<uint32_t> vertex_tile;
+  size_t vtile_lo = 0;
+  size_t ntiles = 0;
 };
 
 struct fq_vec {
@@ -190,4 +196,8 @@ struct fq_csr {
   bool spmv_ready = false;
   // Jacobi (inverse diagonal), built on demand
   fq::DevBuf<double> inv_diag;
+  // tile-fused numeric path (shared by the blocks assembled together)
+  std::shared_ptr<fq::TilePlan> tile_plan;
+  int tile_refused = 0;
+  int slab_passes = 0;  // numeric passes done through the slab path since the symbolic phase
 };

@@ -98,6 +98,85 @@ static void emit_function(const std::string& name, int n, const std::vector<Bloc
   std::printf("}\n\n");
 }
 
+
+// "Core" functions for the tile-fused assembly kernel (tile.cu): the masses of
+// grades k-1, k, k+1 of an n-cell, emitting every DISTINCT stored value once
+// (entries that hash-cons to one register share a slot).  The sandwiches
+// d*M*D are evaluated by the gather phase from these values.  map[] gives for
+// every mass entry (three row-major matrices concatenated) the distinct slot
+// | 0x100 when negated, or -1 for an exact zero.
+struct CoreEntry {
+  std::string name;
+  int n, k, ninputs, ndistinct, nouts;
+};
+static void emit_core(const std::string& name, int n, int k, CoreEntry& e) {
+  TapeBuilder tb;
+  std::vector<BlockLayout> layout;
+  const std::vector<BlockSpec> blocks{{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_MASS, k + 1}};
+  const Tape t = build_tape(n, blocks, &layout, &tb);
+  int nouts = 0;
+  for (const BlockLayout& l : layout) nouts += l.rows * l.cols;
+  std::vector<int> map(size_t(nouts), -1);
+  std::map<uint32_t, int> slot_of;
+  std::printf("// core n=%d k=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, t.ninputs, nouts,
+              t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
+  std::printf("template <class Sink>\n__device__ __forceinline__ void %s(const double* __restrict__ s, Sink& sink) {\n",
+              name.c_str());
+  for (int i = 0; i < t.ninputs; ++i) std::printf("  const double r%d = s[%d];\n", i, i);
+  for (const TapeOp& o : tb.ssa_ops()) {
+    switch (o.op) {
+      case OP_ADD:
+        std::printf("  const double %s = __dadd_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
+        break;
+      case OP_SUB:
+        std::printf("  const double %s = __dsub_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
+        break;
+      case OP_MUL:
+        std::printf("  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
+        break;
+      case OP_MULC:
+        std::printf("  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(),
+                    cst(tb.consts[o.b]).c_str());
+        break;
+      case OP_DIV:
+        std::printf("  const double %s = __ddiv_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
+        break;
+      case OP_SQRTABS:
+        std::printf("  const double %s = __dsqrt_rn(fabs(%s));\n", reg(o.d).c_str(), reg(o.a).c_str());
+        break;
+      case OP_LOADC:
+        std::printf("  const double %s = %s;\n", reg(o.d).c_str(), cst(tb.consts[o.b]).c_str());
+        break;
+      case OP_STORE:
+      case OP_STOREN: {
+        auto it = slot_of.find(o.a);
+        if (it == slot_of.end()) {
+          const int slot = int(slot_of.size());
+          it = slot_of.emplace(o.a, slot).first;
+          std::printf("  sink.template put<0, %d>(%s);\n", slot, reg(o.a).c_str());
+        }
+        map[o.d] = it->second | (o.op == OP_STOREN ? 0x100 : 0);
+        break;
+      }
+      case OP_STOREC:
+        if (tb.consts[o.b] != 0.0) throw std::runtime_error("core: non-zero constant mass entry");
+        map[o.d] = -1;
+        break;
+    }
+  }
+  std::printf("}\n");
+  std::printf("static const short %s_map[%d] = {", name.c_str(), nouts > 0 ? nouts : 1);
+  for (int i = 0; i < nouts; ++i) std::printf("%s%d", i ? ", " : "", map[size_t(i)]);
+  if (nouts == 0) std::printf("0");
+  std::printf("};\n\n");
+  e.name = name;
+  e.n = n;
+  e.k = k;
+  e.ninputs = t.ninputs;
+  e.ndistinct = int(slot_of.size());
+  e.nouts = nouts;
+}
+
 int main() {
   std::printf("// GENERATED by gen_elmat.cpp from tape.hpp — do not edit.\n#pragma once\n\n");
   std::vector<Entry> entries;
@@ -141,6 +220,19 @@ int main() {
   for (const Entry& e : entries)
     std::printf("  X(%s, %d, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.fused_k, e.kind, e.grade, e.ninputs,
                 e.nouts);
+  std::printf("\n");
+  // cores: n <= 3, every grade
+  std::vector<CoreEntry> cores;
+  for (int n = 1; n <= 3; ++n)
+    for (int k = 0; k <= n; ++k) {
+      CoreEntry e{};
+      emit_core("fq_core_n" + std::to_string(n) + "_k" + std::to_string(k), n, k, e);
+      cores.push_back(e);
+    }
+  // X-macro list: (function, n, k, ninputs, ndistinct, nouts)
+  std::printf("#define FQ_GEN_CORE_LIST(X) \\\n");
+  for (const CoreEntry& e : cores)
+    std::printf("  X(%s, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.k, e.ninputs, e.ndistinct, e.nouts);
   std::printf("\n");
   return 0;
 }

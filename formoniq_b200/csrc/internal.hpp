@@ -24,6 +24,14 @@ void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_e
 // fused numeric phase of several blocks sharing one element kernel launch (HodgeBlocks)
 void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros);
 
+// ---- tile.cu (tile-fused numeric assembly)
+void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held);
+void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh, const uint64_t* cell_verts);
+std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop);
+bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop);
+bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan);
+int64_t tile_plan_bytes(const TilePlan& plan);
+
 // ---- spmv.cu
 void spmv_prepare(fq_ctx* ctx, fq_csr* a);
 void spmv_apply(fq_ctx* ctx, const fq_csr* a, const double* x, double* y);

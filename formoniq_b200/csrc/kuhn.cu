@@ -251,6 +251,8 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
     FQ_CUDA(cudaGetLastError());
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  // vertex bricks for the tile-fused numeric assembly (tile.cu)
+  tile_cluster_kuhn(ctx, mesh, dim, shape, slab_begin, slab_end);
 }
 
 }  // namespace fq

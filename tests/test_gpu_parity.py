@@ -408,3 +408,112 @@ def test_mixed_hodge_laplace_solve_parity(fq, ctx):
     assert rep.converged
     assert np.abs(x.to_numpy() - exact).max() <= 1e-10 * np.abs(exact).max()
     assert n == hb.n_sigma + hb.n_u
+
+
+# ------------------------------------------------------------------ tile-fused numeric assembly (tile.cu)
+def _tile_fused_ran(ctx):
+    return ctx.timing_report().get("k13_tile_fused", {}).get("count", 0) > 0
+
+
+TILE_CASES = [
+    (3, [6, 5, 7], "plain", 1, "kuhn"), (3, [5, 6, 4], "jitter", 1, "kuhn"), (3, [4, 4, 4], "minkowski", 1, "kuhn"),
+    (3, [5, 4, 6], "jitter", 2, "kuhn"), (3, [4, 5, 3], "plain", 0, "kuhn"), (3, [3, 4, 5], "jitter", 3, "kuhn"),
+    (2, [9, 7], "plain", 1, "kuhn"), (2, [6, 8], "jitter", 2, "kuhn"), (2, [5, 5], "jitter", 0, "kuhn"),
+    (1, [9], "plain", 1, "kuhn"),
+    (3, [4, 5, 4], "jitter", 1, "arrays"), (3, [4, 4, 4], "plain", 1, "arrays"), (2, [7, 6], "plain", 1, "arrays"),
+]
+
+
+@pytest.mark.parametrize("dim,shape,variant,k,source", TILE_CASES)
+@pytest.mark.parametrize("drop", [True, False])
+def test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, variant, k, source, drop):
+    # second numeric pass = the tile-fused kernel (K1+K3 in shared memory); it must reproduce the oracle's
+    # pattern bit for bit and the values bitwise (same operation order, same cell-ascending summation)
+    cx, s, coords, diag, vmax = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    if source == "kuhn":
+        mesh = fq.Mesh.kuhn(ctx, dim, shape, vmax=vmax, ambient_diag=diag, jitter=0.2 if variant == "jitter" else 0.0)
+        assert np.array_equal(mesh.lengths(), s)
+    else:
+        mesh = mesh_from_oracle(fq, ctx, cx, s)
+    hb = fq.HodgeBlocks.symbolic(mesh, k)
+    hb.numeric(mesh, drop)          # slab pass: classification + pattern
+    first = [blk.download() for blk in hb.blocks]
+    ctx.set_timing(True)
+    ctx.timing_report()
+    hb.numeric(mesh, drop)          # tile-fused pass
+    assert _tile_fused_ran(ctx)
+    ctx.set_timing(False)
+    specs = [(O.MASS, k - 1), (O.MASS, k), (O.DIF_TEST, k), (O.DIF_BOTH, k + 1)]
+    for blk, (kind, g), (rp0, ci0, va0) in zip(hb.blocks, specs, first):
+        tg, rg = O.kind_grades(kind, g)
+        if tg < 0 or rg < 0:
+            assert blk.nnz == 0
+            continue
+        ref = cx.assemble(s, kind, g, drop_zeros=drop)
+        rp, ci, va = blk.download()
+        erp, eci, eva = ref.arrays()
+        assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci), (kind, g)
+        assert same_bits_mod_zero_sign(va, eva), (kind, g)
+        assert same_bits_mod_zero_sign(va, va0), (kind, g)
+
+
+def test_tile_fused_detects_a_classification_change(fq, ctx):
+    # dyadic geometry (many exact zeros) -> jittered geometry (none): the cached pattern is stale and must be rebuilt
+    dim, shape = 3, [4, 4, 4]
+    cx, s, *_ = kuhn_problem(dim, shape)
+    _, s2, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    hb = fq.HodgeBlocks.symbolic(mesh, 1)
+    hb.numeric(mesh)
+    hb.numeric(mesh)
+    for geometry in (s2, s, s2):
+        mesh.set_lengths(geometry)
+        for _ in range(3):  # fallback pass, plan rebuild, steady state
+            hb.numeric(mesh)
+            for blk, (kind, g) in zip(hb.blocks, [(O.MASS, 0), (O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2)]):
+                ref = cx.assemble(geometry, kind, g)
+                rp, ci, va = blk.download()
+                erp, eci, eva = ref.arrays()
+                assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci)
+                assert same_bits_mod_zero_sign(va, eva)
+
+
+@pytest.mark.parametrize("kind,g", [(0, 1), (1, 1), (2, 1), (3, 2), (0, 2), (3, 1), (1, 2), (2, 3), (0, 3), (3, 4)])
+def test_tile_fused_single_blocks(fq, ctx, kind, g):
+    dim, shape = 3, [5, 4, 6]
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = fq.Mesh.kuhn(ctx, dim, shape, jitter=0.2)
+    a = fq.WhitneyPairing(dim, g, kind).symbolic(mesh)
+    a.numeric(mesh)
+    ctx.set_timing(True)
+    ctx.timing_report()
+    a.numeric(mesh)
+    assert _tile_fused_ran(ctx)
+    ctx.set_timing(False)
+    ref = cx.assemble(s, kind, g)
+    rp, ci, va = a.download()
+    erp, eci, eva = ref.arrays()
+    assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci)
+    assert same_bits_mod_zero_sign(va, eva)
+
+
+def test_tile_fused_on_slabs_tiles_the_global_matrix(fq, ctx):
+    # owner-computes slabs + tile-fused numeric pass: stacked row blocks == the 1-GPU matrix, bit for bit
+    shape = [5, 4, 9]
+    cx, s, *_ = kuhn_problem(3, shape, jitter=True)
+    specs = [(O.MASS, 0), (O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2)]
+    refs = [cx.assemble(s, kind, g).to_scipy() for kind, g in specs]
+    for sb, se in ((0, 3), (3, 6), (6, 9)):
+        mesh = fq.Mesh.kuhn(ctx, 3, shape, jitter=0.2, slab=(sb, se))
+        hb = fq.HodgeBlocks.symbolic(mesh, 1, mesh.owned_range(0), mesh.owned_range(1))
+        hb.numeric(mesh)
+        ctx.set_timing(True)
+        ctx.timing_report()
+        hb.numeric(mesh)
+        assert _tile_fused_ran(ctx)
+        ctx.set_timing(False)
+        for blk, ref in zip(hb.blocks, refs):
+            b, e = blk.row_range
+            got, exp = blk.to_scipy(), ref[b:e]
+            assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+            assert np.array_equal(got.data, exp.data)
