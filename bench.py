@@ -308,6 +308,8 @@ def run_b200(args):
     if e2e is not None:
         out["e2e"] = e2e
     try:
+        if args.no_cpu:
+            raise RuntimeError("skipped (--no-cpu)")
         cb = cpu_assembly_sample(args.sample_n)
         out["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
                                "nnz_per_s": cb["nnz_per_s"]}
@@ -381,6 +383,7 @@ def main():
     ap.add_argument("--e2e-n", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

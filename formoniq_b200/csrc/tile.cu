@@ -4,7 +4,8 @@
 // (8*T bytes per cell written and read back through HBM) disappears.
 //
 // Decomposition = the multi-GPU one, repeated at CTA level: *owner computes*.
-//   * vertices are clustered into tiles (closed-form bricks on Kuhn grids);
+//   * vertices are clustered into tiles (closed-form bricks on Kuhn grids,
+//     breadth-first clusters on generic meshes);
 //   * a tile owns the rows (simplices) whose top vertex it contains, hence
 //     whole CSR rows, hence every structural non-zero of those rows;
 //   * it evaluates the element masses of ALL cells touching its vertices
@@ -20,11 +21,20 @@
 // reference's k-ascending gemm order, exact because the incidence entries are
 // 0/+-1 (tape.hpp evaluates the same products symbolically).
 //
+// The cell-slot -> nnz map is laid out per tile as ONE contiguous byte stream
+// of warp-sized records {dest[32]; entry[L][32]} (non-zeros grouped by their
+// number of contributions L, so a warp runs L uniform iterations, lanes read
+// consecutive 2-byte entries, no per-nnz offsets are stored).  The stream is
+// pulled into a shared-memory ring by TMA bulk copies (cp.async.bulk +
+// mbarrier) a few chunks ahead of the consumers, so HBM sees long sequential
+// reads and no thread ever waits on a dependent global load.
+//
 // Reference path replaced: formoniq/src/galerkin.rs:138-188 (assemble_matrix)
 // + hodge.rs:62-72 (the four HodgeBlocks), numeric phase.
 #include <cub/cub.cuh>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "elmat_gen.cuh"
 #include "internal.hpp"
@@ -32,36 +42,40 @@
 
 namespace fq {
 
-constexpr int kTileThreads = 512;
 constexpr int kTileMaxBlocks = 4;
-constexpr uint32_t kNoDest = 0xFFFFFFFFu;
+constexpr uint32_t kPadDest = 0xFFFFFFFFu;  // padding lane of a record
+constexpr uint32_t kNoDest = 0xFFFFFFFEu;   // dropped non-zero: must stay all-zero (galerkin.rs:173)
+constexpr int kChunkBytes = 8192;           // TMA chunk of the tile stream; records never straddle a chunk
+constexpr int kMaxRecPerTile = 1024;        // directory capacity in shared memory
+constexpr int kMaxChunksPerTile = 96;
+constexpr int kMaxLen = 255;                // contributions per non-zero (8 bits in the directory)
 
 struct TileBlockDev {
-  const uint32_t* tile_nnz_ptr;  // [ntiles+1] into the tile-ordered nnz arrays
-  const uint32_t* tile_con_ptr;  // [ntiles+1] into con_src
-  const uint32_t* nnz_dest;      // [s_nnz] position in csr->values, kNoDest = dropped (must stay all-zero)
-  const uint16_t* nnz_end;       // [s_nnz] end of the nnz's contributions, relative to tile_con_ptr[tile]
-  const uint16_t* con_src;       // [ncontrib] (local cell << slot_bits) | slot
   double* values;
-  int no, ni;                    // recipe shape: outer x inner signed terms per slot
-  int recipe_off;                // byte offset of this block's recipes (nslots * no * ni codes)
+  int no, ni;      // recipe shape: outer x inner signed terms per slot
+  int recipe_off;  // byte offset of this block's recipes (nslots * no * ni codes)
   int slot_bits;
 };
 
 struct TileParams {
-  const uint32_t* tile_cell_ptr;  // [ntiles+1]
-  const uint32_t* tile_cells;     // local cell ids, ascending within a tile
-  const uint32_t* cell_edges;
+  const uint32_t* tile_cell_ptr;    // [ntiles+1]
+  const uint32_t* tile_cell_edges;  // [tile cell slots][NE] edge ids, pre-gathered
   const double* lengths;
   uint32_t edge_lo;
   uint32_t ntiles;
-  int cstride;                    // cells capacity of the shared slab
+  const uint32_t* tile_dir_ptr;     // [ntiles+1] into rec_dir
+  const uint32_t* rec_dir;          // per record: block<<30 | L<<22 | offset/64 within the tile stream
+  const uint32_t* tile_stream_ptr;  // [ntiles+1] in 64-byte units
+  const unsigned char* stream;
+  int cstride;                      // cells capacity of the shared slab
   int nblocks;
-  const uint8_t* recipes;         // code = distinct slot | 0x80 negated; 0xFF = no term
+  int nstages;                      // ring slots
+  uint32_t ring_off, dir_off, chunk_off, rec_off, mbar_off;  // byte offsets in dynamic shared memory
+  const uint8_t* recipes;           // code = distinct slot | 0x80 negated; 0xFF = no term
   int recipe_bytes;
-  int check_classification;       // 1 when the plan carries the reference's value-dependent pattern
-  int* changed;                   // raised when the zero/non-zero classification differs from the plan's
-  unsigned int* ticket;           // dynamic tile scheduler
+  int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
+  int* changed;                     // raised when the zero/non-zero classification differs from the plan's
+  unsigned int* ticket;             // dynamic tile scheduler
   TileBlockDev blk[kTileMaxBlocks];
 };
 
@@ -74,90 +88,216 @@ struct TileSink {
   }
 };
 
-template <class Fn, int NE>
-__global__ void __launch_bounds__(kTileThreads, 1) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
-  extern __shared__ double smem[];
-  double* slab = smem;
-  uint8_t* rec = reinterpret_cast<uint8_t*>(smem + size_t(P.cstride) * Fn::kDistinct);
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_hdr[2 + 3 * kTileMaxBlocks];
-  for (int i = threadIdx.x; i < P.recipe_bytes; i += kTileThreads) rec[i] = P.recipes[i];
-  for (;;) {
-    __syncthreads();  // previous tile fully consumed (and recipes visible)
-    if (threadIdx.x == 0) s_tile = atomicAdd(P.ticket, 1u);
-    __syncthreads();
-    const uint32_t t = s_tile;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (bytes % 16 == 0, 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// x with the sign bit flipped when bit 15 of `code` is set (exact negation)
+__device__ __forceinline__ double signed_load(const double* __restrict__ p, uint32_t code) {
+  const double x = p[code & 0x7FFFu];
+  return __hiloint2double(__double2hiint(x) ^ int((code & 0x8000u) << 16), __double2loint(x));
+}
+
+// One lane's non-zero of a record: sum over its L contributions, each a recipe of
+// NO x NI signed mass entries:  v = (((x00 + x01) + ..) + ((x10 + x11) + ..)) + ..
+// (the k-ascending gemm order of operators.rs:201-211 with the +-1 incidence entries folded in).
+template <int NO, int NI>
+__device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent, uint32_t L, const double* __restrict__ slab,
+                                              const uint16_t* __restrict__ brec, uint32_t sb, uint32_t slot_mask, double& acc,
+                                              bool& any) {
+  constexpr int NT4 = (NO * NI + 3) / 4 * 4;  // codes per slot, padded to 8-byte groups
+#pragma unroll 2
+  for (uint32_t j = 0; j < L; ++j) {
+    const uint32_t e = ent[j * 32];
+    const double* __restrict__ sc = slab + (e >> sb);
+    const uint2* __restrict__ rr = reinterpret_cast<const uint2*>(brec + (e & slot_mask) * NT4);
+    uint32_t code[NT4];
+#pragma unroll
+    for (int w = 0; w < NT4 / 4; ++w) {
+      const uint2 c = rr[w];
+      code[4 * w + 0] = c.x & 0xFFFFu;
+      code[4 * w + 1] = c.x >> 16;
+      code[4 * w + 2] = c.y & 0xFFFFu;
+      code[4 * w + 3] = c.y >> 16;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      double inner = signed_load(sc, code[o * NI]);
+#pragma unroll
+      for (int q = 1; q < NI; ++q) inner = __dadd_rn(inner, signed_load(sc, code[o * NI + q]));
+      v = (o == 0) ? inner : __dadd_rn(v, inner);
+    }
+    any = any || (v != 0.0);
+    acc = __dadd_rn(acc, v);
+  }
+}
+// mass blocks: the stream entries are pre-translated to sign | slab offset
+__device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict__ ent, uint32_t L,
+                                                     const double* __restrict__ slab, double& acc, bool& any) {
+#pragma unroll 4
+  for (uint32_t j = 0; j < L; ++j) {
+    const double x = signed_load(slab, ent[j * 32]);
+    any = any || (x != 0.0);
+    acc = __dadd_rn(acc, x);
+  }
+}
+
+template <class Fn, int NE, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* slab = reinterpret_cast<double*>(smem_raw);
+  unsigned char* ring = smem_raw + P.ring_off;
+  uint32_t* dir = reinterpret_cast<uint32_t*>(smem_raw + P.dir_off);
+  uint32_t* chunk_first = reinterpret_cast<uint32_t*>(smem_raw + P.chunk_off);
+  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
+  __shared__ uint32_t s_hdr[2][8];
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = P.nstages;
+  uint64_t* empty = full + S;
+  auto fetch_header = [&](uint32_t* h) {  // thread 0: next tile from the dynamic scheduler
+    const uint32_t t = atomicAdd(P.ticket, 1u);
+    h[0] = t;
+    if (t < P.ntiles) {
+      h[1] = __ldg(P.tile_cell_ptr + t);
+      h[2] = __ldg(P.tile_cell_ptr + t + 1);
+      h[3] = __ldg(P.tile_dir_ptr + t);
+      h[4] = __ldg(P.tile_dir_ptr + t + 1);
+      h[5] = __ldg(P.tile_stream_ptr + t);
+      h[6] = __ldg(P.tile_stream_ptr + t + 1);
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fetch_header(s_hdr[0]);
+  }
+  for (int i = tid; i < P.recipe_bytes / 2; i += NT) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
+  uint32_t g = 0;  // chunks this CTA has pushed through the ring so far (slot = g % S, parity = (g / S) & 1)
+  for (uint32_t it = 0;; ++it) {
+    __syncthreads();  // previous tile fully consumed, this tile's header visible
+    const uint32_t* hdr = s_hdr[it & 1];
+    const uint32_t t = hdr[0];
     if (t >= P.ntiles) break;
-    if (threadIdx.x < 2) s_hdr[threadIdx.x] = P.tile_cell_ptr[t + threadIdx.x];
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + 3 * P.nblocks) {
-      const int j = threadIdx.x - 32, b = j / 3, w = j - 3 * b;
-      s_hdr[2 + j] = w == 0 ? P.blk[b].tile_nnz_ptr[t] : (w == 1 ? P.blk[b].tile_nnz_ptr[t + 1] : P.blk[b].tile_con_ptr[t]);
+    const uint32_t cbase = hdr[1], nc = hdr[2] - hdr[1];
+    const uint32_t d0 = hdr[3], nrec = hdr[4] - hdr[3];
+    const uint32_t sbytes = (hdr[6] - hdr[5]) * 64u;
+    const unsigned char* sbase = P.stream + size_t(hdr[5]) * 64u;
+    const uint32_t nchunks = (sbytes + kChunkBytes - 1) / kChunkBytes;
+    // ---- the first ring slots start filling now and land while K1 runs
+    if (tid == 0) {
+      for (uint32_t k = 0; k < nchunks && k < uint32_t(S); ++k) {
+        const uint32_t bytes = min(uint32_t(kChunkBytes), sbytes - k * kChunkBytes);
+        uint64_t* bar = &full[(g + k) % S];
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(ring + ((g + k) % S) * kChunkBytes, sbase + size_t(k) * kChunkBytes, bytes, bar);
+      }
     }
-    __syncthreads();
-    const uint32_t cbase = s_hdr[0], nc = s_hdr[1] - s_hdr[0];
-    uint32_t work = 0;
-    for (int b = 0; b < P.nblocks; ++b) work += s_hdr[2 + 3 * b + 1] - s_hdr[2 + 3 * b];
-    if (work == 0) continue;
+    for (uint32_t i = tid; i < nrec; i += NT) dir[i] = __ldg(P.rec_dir + d0 + i);
     // ---- K1: element masses of the tile's cells -> shared slab [distinct][cell]
-    for (uint32_t c = threadIdx.x; c < nc; c += kTileThreads) {
-      const uint32_t cell = __ldg(P.tile_cells + cbase + c);
-      const uint32_t* ce = P.cell_edges + size_t(cell) * NE;
-      uint32_t eid[NE > 0 ? NE : 1];
+    if (nrec != 0) {
+      for (uint32_t c = tid; c < nc; c += NT) {
+        const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
+        uint32_t eid[NE > 0 ? NE : 1];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
-      double s[NE > 0 ? NE : 1];
+        for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
+        double s[NE > 0 ? NE : 1];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
-      TileSink sink{slab + c, P.cstride};
-      fn(s, sink);
+        for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
+        TileSink sink{slab + c, P.cstride};
+        fn(s, sink);
+      }
     }
     __syncthreads();
-    // ---- K3: one thread per owned structural non-zero, contributions in ascending cell order
-    for (int b = 0; b < P.nblocks; ++b) {
-      const TileBlockDev& B = P.blk[b];
-      const uint32_t n0 = s_hdr[2 + 3 * b], n1 = s_hdr[2 + 3 * b + 1], c0 = s_hdr[2 + 3 * b + 2];
-      const int no = B.no, ni = B.ni, nterms = no * ni;
-      const uint8_t* brec = rec + B.recipe_off;
-      const uint32_t slot_mask = (1u << B.slot_bits) - 1u;
-      for (uint32_t i = n0 + threadIdx.x; i < n1; i += kTileThreads) {
-        const uint32_t e0 = (i == n0) ? 0u : uint32_t(__ldg(B.nnz_end + i - 1));
-        const uint32_t e1 = __ldg(B.nnz_end + i);
-        const uint32_t dest = __ldg(B.nnz_dest + i);
+    // the next tile's header is fetched while this one is gathered
+    if (tid == 0) fetch_header(s_hdr[(it + 1) & 1]);
+    // first record of every chunk (records are laid out in order and never straddle a chunk)
+    for (uint32_t i = tid; i < nrec; i += NT) {
+      const uint32_t ck = ((dir[i] & 0x3FFFFFu) * 64u) / kChunkBytes;
+      if (i == 0 || ck != ((dir[i - 1] & 0x3FFFFFu) * 64u) / kChunkBytes) chunk_first[ck] = i;
+    }
+    if (tid == 0) chunk_first[nchunks] = nrec;
+    __syncthreads();
+    // ---- K3: one warp per record, one lane per owned structural non-zero
+    for (uint32_t k = 0; k < nchunks; ++k) {
+      const uint32_t slot = (g + k) % S, parity = ((g + k) / S) & 1u;
+      mbar_wait(&full[slot], parity);
+      const unsigned char* chunk = ring + slot * kChunkBytes;
+      const uint32_t r1 = chunk_first[k + 1];
+      for (uint32_t r = chunk_first[k] + warp; r < r1; r += NW) {
+        const uint32_t d = dir[r];
+        const uint32_t b = d >> 30, L = (d >> 22) & 0xFFu;
+        const unsigned char* rp = chunk + ((d & 0x3FFFFFu) * 64u - k * kChunkBytes);
+        const uint32_t dest = reinterpret_cast<const uint32_t*>(rp)[lane];
+        if (dest == kPadDest) continue;
+        const uint16_t* __restrict__ ent = reinterpret_cast<const uint16_t*>(rp + 128) + lane;
+        const TileBlockDev& B = P.blk[b];
+        const uint16_t* __restrict__ brec = rec + B.recipe_off;
+        const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
         double acc = 0.0;
         bool any = false;
-        for (uint32_t p = e0; p < e1; ++p) {
-          const uint32_t src = __ldg(B.con_src + c0 + p);
-          const double* __restrict__ sc = slab + (src >> B.slot_bits);
-          const uint8_t* __restrict__ r = brec + (src & slot_mask) * nterms;
-          double v = 0.0;
-          for (int o = 0; o < no; ++o) {
-            double inner = 0.0;
-            bool first = true;
-            for (int q = 0; q < ni; ++q) {
-              const uint32_t code = r[o * ni + q];
-              if (code == 0xFFu) continue;
-              double x = sc[(code & 0x7Fu) * P.cstride];
-              if (code & 0x80u) x = -x;
-              inner = first ? x : __dadd_rn(inner, x);
-              first = false;
-            }
-            v = (o == 0) ? inner : __dadd_rn(v, inner);
-          }
-          any = any || (v != 0.0);
-          acc = __dadd_rn(acc, v);
+        switch (B.no * 8 + B.ni) {
+          case 0: break;  // zero space: every contribution is an exact zero
+          case 1 * 8 + 1: gather_record_direct(ent, L, slab, acc, any); break;
+          case 1 * 8 + 2: gather_record<1, 2>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
+          case 1 * 8 + 3: gather_record<1, 3>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
+          case 1 * 8 + 4: gather_record<1, 4>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
+          case 2 * 8 + 2: gather_record<2, 2>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
+          case 3 * 8 + 3: gather_record<3, 3>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
+          default: gather_record<4, 4>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
         }
         const bool kept = dest != kNoDest;
         if (P.check_classification && kept != any) *P.changed = 1;
         if (kept) B.values[dest] = acc;
       }
+      // this warp is done with the slot; the chunk's refill is issued by one rotating warp
+      // once every warp has left it (no CTA-wide barrier on the stream)
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[slot])) : "memory");
+      if (k + S < nchunks && warp == int(k % NW)) {
+        mbar_wait(&empty[slot], parity);
+        if (lane == 0) {
+          const uint32_t kk = k + S;
+          const uint32_t bytes = min(uint32_t(kChunkBytes), sbytes - kk * kChunkBytes);
+          mbar_expect_tx(&full[slot], bytes);
+          tma_load_1d(ring + slot * kChunkBytes, sbase + size_t(kk) * kChunkBytes, bytes, &full[slot]);
+        }
+      }
     }
+    g += nchunks;
   }
 }
 
 // ------------------------------------------------------------------ plan
 struct TileBlockPlan {
-  DevBuf<uint32_t> tile_nnz_ptr, tile_con_ptr, nnz_dest;
-  DevBuf<uint16_t> nnz_end, con_src;
   int no = 1, ni = 1, recipe_off = 0, slot_bits = 7;
   fq_csr* csr = nullptr;
   size_t nnz_at_build = 0;
@@ -169,8 +309,11 @@ struct TilePlan {
   int dim = 0, core_k = 0, ndistinct = 0;
   uint32_t ntiles = 0;
   int cstride = 0;
+  int nthreads = 512, nstages = 3;
   size_t smem_bytes = 0;
-  DevBuf<uint32_t> tile_cell_ptr, tile_cells;
+  uint32_t ring_off = 0, dir_off = 0, chunk_off = 0, rec_off = 0, mbar_off = 0;
+  DevBuf<uint32_t> tile_cell_ptr, tile_cell_edges, tile_dir_ptr, rec_dir, tile_stream_ptr;
+  DevBuf<unsigned char> stream;
   DevBuf<uint8_t> recipes;
   DevBuf<int> changed;
   DevBuf<unsigned int> ticket;
@@ -195,10 +338,16 @@ template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static bool attr_set = false;
   if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024 - 256));
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 113 * 1024 - 256));
     attr_set = true;
   }
-  tile_assemble_kernel<Fn, NE><<<plan.grid, kTileThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  if (plan.nthreads == 512)
+    tile_assemble_kernel<Fn, NE, 512, 1><<<plan.grid, 512, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  else
+    tile_assemble_kernel<Fn, NE, 256, 2><<<plan.grid, 256, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
 }
@@ -216,6 +365,28 @@ static const CoreEntryRt* find_core(int n, int k) {
   for (const CoreEntryRt& e : g_cores)
     if (e.n == n && e.k == k) return &e;
   return nullptr;
+}
+
+// ---- launch configuration (tunable through the environment for sweeps) -------
+struct TileConfig {
+  int nthreads, ctas_per_sm, nstages;
+  size_t smem_cta;  // dynamic shared memory budget of one CTA
+};
+static TileConfig tile_config() {
+  TileConfig c{512, 1, 3, size_t(227) * 1024 - 256};
+  if (const char* e = std::getenv("FQ_TILE_THREADS"))
+    if (std::atoi(e) == 256) c = TileConfig{256, 2, 2, size_t(113) * 1024 - 256};
+  if (const char* e = std::getenv("FQ_TILE_STAGES")) c.nstages = std::max(1, std::min(8, std::atoi(e)));
+  return c;
+}
+static size_t tile_fixed_smem(const TileConfig& c) {
+  return size_t(c.nstages) * kChunkBytes + size_t(kMaxRecPerTile) * 4 + size_t(kMaxChunksPerTile + 1) * 4 + 2048 /*recipes*/ +
+         128 /*mbarriers*/ + 512 /*alignment slack*/;
+}
+int tile_cells_capacity(int ndistinct) {
+  const TileConfig c = tile_config();
+  int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double)));
+  return std::min(cap, 1023);
 }
 
 // Recipes of one block over the distinct values of core(n, kc).
@@ -294,6 +465,7 @@ static bool build_recipes(int n, int kc, const CoreEntryRt& core, int kind, int 
   return true;
 }
 
+
 // ---- vertex clustering -------------------------------------------------------
 __global__ void vtile_kuhn_kernel(int n, const uint32_t* __restrict__ nv /*[n] vertices per axis*/,
                                   const uint32_t* __restrict__ brick, const uint32_t* __restrict__ nb, uint64_t v_lo,
@@ -339,7 +511,7 @@ __global__ void split_keys_kernel(const uint64_t* __restrict__ keys, size_t n, u
     cell[i] = uint32_t(keys[i]);
   }
 }
-// ptr[t] = first i with key[i] >= t, for sorted keys; ptr[nkeys_range] = n
+// ptr[t] = first i with key[i] >= t, for sorted keys; ptr[nseg] = n
 __global__ void seg_ptr_kernel(const uint32_t* __restrict__ key, size_t n, uint32_t nseg, uint32_t* __restrict__ ptr) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i <= n; i += stride) {
@@ -347,6 +519,13 @@ __global__ void seg_ptr_kernel(const uint32_t* __restrict__ key, size_t n, uint3
     const uint32_t lo = (i == 0) ? 0u : key[i - 1] + 1;
     for (uint32_t t = lo; t <= hi && t <= nseg; ++t) ptr[t] = uint32_t(i);
   }
+}
+__global__ void tile_cell_edges_kernel(const uint32_t* __restrict__ tile_cells, size_t n, const uint32_t* __restrict__ cell_edges,
+                                       int ne, uint32_t* __restrict__ out) {
+  const size_t total = n * size_t(ne);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x; p < total; p += stride)
+    out[p] = cell_edges[size_t(tile_cells[p / size_t(ne)]) * ne + p % size_t(ne)];
 }
 
 // row -> tile of its top vertex
@@ -363,47 +542,123 @@ __global__ void row_tile_kernel(const uint32_t* __restrict__ faces, int nl, cons
     row_tile[row - row_begin] = vtile[cell_verts[c * nv + top_pos[i]] - v_lo];
   }
 }
-__global__ void nnz_tile_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nrows, const uint32_t* __restrict__ row_tile,
-                                uint32_t* __restrict__ nnz_tile, uint32_t* __restrict__ nnz_id) {
+// sort key of every structural non-zero: tile | L | signature of its slot sequence
+__global__ void nnz_key_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nrows, const uint32_t* __restrict__ row_tile,
+                               const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
+                               int use_sig, uint64_t* __restrict__ key, uint32_t* __restrict__ nnz_id, int* __restrict__ err) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
-    const uint32_t t = row_tile[r];
-    for (uint32_t q = row_ptr[r]; q < row_ptr[r + 1]; ++q) nnz_tile[q] = t, nnz_id[q] = q;
+    const uint64_t t = row_tile[r];
+    for (uint32_t q = row_ptr[r]; q < row_ptr[r + 1]; ++q) {
+      const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
+      uint32_t L = p1 - p0;
+      if (L > uint32_t(kMaxLen)) {
+        atomicExch(err, 4);
+        L = kMaxLen;
+      }
+      uint32_t sig = 0;
+      if (use_sig)
+        for (uint32_t p = p0; p < p1; ++p) sig = sig * 131u + (contrib_src[p] % T) + 1u;
+      sig = (sig ^ (sig >> 16)) & 0xFFFFu;
+      key[q] = (t << 24) | (uint64_t(L) << 16) | sig;
+      nnz_id[q] = q;
+    }
   }
 }
-__global__ void nnz_len_kernel(const uint32_t* __restrict__ perm, uint32_t n, const uint32_t* __restrict__ contrib_ptr,
-                               uint32_t* __restrict__ len) {
+__global__ void run_heads_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ head) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    head[i] = (i == 0 || (key[i] >> 16) != (key[i - 1] >> 16)) ? 1u : 0u;
+}
+// run r: start, tile, L
+__global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ head,
+                                const uint32_t* __restrict__ run_scan /*inclusive*/, uint32_t n, uint32_t* __restrict__ run_start,
+                                uint32_t* __restrict__ run_tile, uint32_t* __restrict__ run_len_code) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (head[i]) {
+      const uint32_t r = run_scan[i] - 1;
+      run_start[r] = i;
+      run_tile[r] = uint32_t(key[i] >> 24);
+      run_len_code[r] = uint32_t(key[i] >> 16) & 0xFFu;
+    }
+}
+__global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, uint32_t nruns, uint32_t* __restrict__ nrec) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nruns; r += stride)
+    nrec[r] = r < nruns ? (run_start[r + 1] - run_start[r] + 31u) / 32u : 0u;
+}
+__global__ void rec_len_kernel(const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
+                               uint8_t* __restrict__ rec_len) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride)
+    for (uint32_t k = rec_base[r]; k < rec_base[r + 1]; ++k) rec_len[k] = uint8_t(run_len_code[r]);
+}
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ idx, uint32_t n, const uint32_t* __restrict__ src,
+                                  uint32_t* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = src[idx[i]];
+}
+
+struct TileLayoutBlock {
+  const uint32_t* rec_tile_ptr;  // [ntiles+1] first record of every tile
+  const uint8_t* rec_len;        // [nrec]
+  uint32_t* rec_rel;             // [nrec] out: offset within the tile stream, 64-byte units
+};
+struct TileLayoutArgs {
+  TileLayoutBlock blk[kTileMaxBlocks];
+  int nblocks;
+};
+// One thread per tile lays its records out (records never straddle a chunk).
+// pass 0: sizes (tile_units, tile_nrec);  pass 1: directory entries.
+__global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, uint32_t* __restrict__ tile_units,
+                                   uint32_t* __restrict__ tile_nrec, const uint32_t* __restrict__ tile_dir_ptr,
+                                   uint32_t* __restrict__ rec_dir) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
+    uint32_t off = 0, nrec = 0;
+    const uint32_t dbase = pass ? tile_dir_ptr[t] : 0u;
+    for (int b = 0; b < A.nblocks; ++b) {
+      const TileLayoutBlock& B = A.blk[b];
+      for (uint32_t k = B.rec_tile_ptr[t]; k < B.rec_tile_ptr[t + 1]; ++k) {
+        const uint32_t L = B.rec_len[k];
+        const uint32_t size = 128u + 64u * L;
+        if (off / kChunkBytes != (off + size - 1) / kChunkBytes) off = (off / kChunkBytes + 1) * kChunkBytes;
+        if (pass) {
+          B.rec_rel[k] = off / 64u;
+          rec_dir[dbase + nrec] = (uint32_t(b) << 30) | (L << 22) | (off / 64u);
+        }
+        off += size;
+        ++nrec;
+      }
+    }
+    if (!pass) {
+      tile_units[t] = off / 64u;
+      tile_nrec[t] = nrec;
+    }
+  }
+}
+// One thread per (sorted) non-zero: its lane of its record.
+__global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n, const uint32_t* __restrict__ run_scan,
+                                   const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_tile,
+                                   const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ rec_rel,
+                                   const uint32_t* __restrict__ tile_stream_ptr, const uint32_t* __restrict__ contrib_ptr,
+                                   const uint32_t* __restrict__ contrib_src, uint32_t T, int slot_bits,
+                                   const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
+                                   const uint8_t* __restrict__ keep, const uint32_t* __restrict__ pos, int drop,
+                                   const uint16_t* __restrict__ direct_map /*mass blocks: slot -> sign | slab offset*/,
+                                   unsigned char* __restrict__ stream, int* __restrict__ err) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t q = perm[i];
-    len[i] = contrib_ptr[q + 1] - contrib_ptr[q];
-  }
-}
-__global__ void tile_con_ptr_kernel(const uint32_t* __restrict__ tile_nnz_ptr, uint32_t ntiles, const uint32_t* __restrict__ G,
-                                    uint32_t nnz, uint32_t ncontrib, uint32_t* __restrict__ tile_con_ptr) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += stride) {
-    const uint32_t i = tile_nnz_ptr[t];
-    tile_con_ptr[t] = i < nnz ? G[i] : ncontrib;
-  }
-}
-// per tile-ordered nnz: destination, end offset and the remapped contributions
-__global__ void nnz_fill_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ sorted_tile, uint32_t n,
-                                const uint32_t* __restrict__ G, const uint32_t* __restrict__ tile_con_ptr,
-                                const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src,
-                                uint32_t T, int slot_bits, const uint32_t* __restrict__ tile_cell_ptr,
-                                const uint32_t* __restrict__ tile_cells, const uint8_t* __restrict__ keep,
-                                const uint32_t* __restrict__ pos, int drop, uint32_t* __restrict__ nnz_dest,
-                                uint16_t* __restrict__ nnz_end, uint16_t* __restrict__ con_src, int* __restrict__ err) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t q = perm[i], t = sorted_tile[i];
+    const uint32_t r = run_scan[i] - 1;
+    const uint32_t idx = i - run_start[r];
+    const uint32_t k = rec_base[r] + idx / 32u, lane = idx % 32u;
+    const uint32_t t = run_tile[r];
+    unsigned char* rp = stream + (size_t(tile_stream_ptr[t]) + rec_rel[k]) * 64u;
+    reinterpret_cast<uint32_t*>(rp)[lane] = drop ? (keep[q] ? pos[q] : kNoDest) : q;
+    uint16_t* ent = reinterpret_cast<uint16_t*>(rp + 128) + lane;
     const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
-    const uint32_t g0 = G[i];
-    const uint32_t end = g0 + (p1 - p0) - tile_con_ptr[t];
-    if (end > 0xFFFFu) atomicExch(err, 1);
-    nnz_end[i] = uint16_t(end);
-    nnz_dest[i] = drop ? (keep[q] ? pos[q] : kNoDest) : q;
     const uint32_t cb = tile_cell_ptr[t], ce = tile_cell_ptr[t + 1];
     for (uint32_t p = p0; p < p1; ++p) {
       const uint32_t src = contrib_src[p];
@@ -421,8 +676,14 @@ __global__ void nnz_fill_kernel(const uint32_t* __restrict__ perm, const uint32_
         continue;
       }
       const uint32_t local = lo - cb;
-      if ((local << slot_bits) > 0xFFFFu) atomicExch(err, 3);
-      con_src[g0 + (p - p0)] = uint16_t((local << slot_bits) | slot);
+      if (direct_map) {
+        const uint32_t code = direct_map[slot];
+        if ((code & 0x7FFFu) + local > 0x7FFFu) atomicExch(err, 3);
+        ent[(p - p0) * 32u] = uint16_t((code & 0x8000u) | ((code & 0x7FFFu) + local));
+      } else {
+        if ((local << slot_bits) > 0xFFFFu) atomicExch(err, 3);
+        ent[(p - p0) * 32u] = uint16_t((local << slot_bits) | slot);
+      }
     }
   }
 }
@@ -437,6 +698,28 @@ template <class T>
 static void upload_vec(DevBuf<T>& d, const std::vector<T>& h) {
   d.alloc(h.size() ? h.size() : 1);
   if (!h.empty()) FQ_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+static uint32_t read_u32(fq_ctx* ctx, const uint32_t* p) {
+  uint32_t v = 0;
+  FQ_CUDA(cudaMemcpyAsync(&v, p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return v;
+}
+static void exclusive_scan_u32(fq_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n) {
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, int64_t(n), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, int64_t(n), ctx->stream));
+  fq_count_launch(ctx, 2);
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+static void inclusive_scan_u32(fq_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n) {
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, int64_t(n), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, in, out, int64_t(n), ctx->stream));
+  fq_count_launch(ctx, 2);
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // Closed-form vertex bricks on a Kuhn grid.
@@ -564,17 +847,12 @@ void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh, const uint64_t* cell_verts
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-int tile_cells_capacity(int ndistinct) {
-  // shared slab: ndistinct doubles per cell, leave room for recipes and headers
-  const size_t budget = 227 * 1024 - 256 - 4096;
-  int cap = int(budget / (size_t(ndistinct) * sizeof(double)));
-  if (cap > 511) cap = 511;
-  return cap;
-}
 
-static void radix_sort_pairs_u32(fq_ctx* ctx, DevBuf<uint32_t>& keys, DevBuf<uint32_t>& vals, size_t n, int end_bit) {
-  DevBuf<uint32_t> keys_alt(n ? n : 1), vals_alt(n ? n : 1);
-  cub::DoubleBuffer<uint32_t> dk(keys.p, keys_alt.p), dv(vals.p, vals_alt.p);
+static void radix_sort_pairs_u64(fq_ctx* ctx, DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, size_t n, int end_bit) {
+  DevBuf<uint64_t> keys_alt(n ? n : 1);
+  DevBuf<uint32_t> vals_alt(n ? n : 1);
+  cub::DoubleBuffer<uint64_t> dk(keys.p, keys_alt.p);
+  cub::DoubleBuffer<uint32_t> dv(vals.p, vals_alt.p);
   size_t tmp_bytes = 0;
   FQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, int64_t(n), 0, end_bit, ctx->stream));
   DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
@@ -584,6 +862,13 @@ static void radix_sort_pairs_u32(fq_ctx* ctx, DevBuf<uint32_t>& keys, DevBuf<uin
   if (dk.Current() != keys.p) std::swap(keys, keys_alt);
   if (dv.Current() != vals.p) std::swap(vals, vals_alt);
 }
+
+// Per-block intermediate data of the plan build (kept until the stream is filled).
+struct BlockBuild {
+  DevBuf<uint32_t> perm, run_scan, run_start, run_tile, run_len, rec_base, rec_tile_ptr, rec_rel;
+  DevBuf<uint8_t> rec_len;
+  uint32_t nruns = 0, nrec = 0;
+};
 
 // Builds the tile plan for the fused blocks `csrs` (their structural phase and,
 // when dropping, their cached classification keep/pos must be valid).
@@ -607,6 +892,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   if (gmin < kc - 1 || gmax > kc + 1) return nullptr;
   const CoreEntryRt* core = find_core(dim, kc);
   if (!core) return nullptr;
+  const TileConfig cfg = tile_config();
   auto plan = std::make_shared<TilePlan>();
   plan->mesh = mesh;
   plan->dim = dim;
@@ -615,25 +901,37 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   plan->nblocks = nblocks;
   plan->launch = core->launch;
   plan->ntiles = uint32_t(mesh->ntiles);
-  // recipes
-  std::vector<uint8_t> all_codes;
+  plan->nthreads = cfg.nthreads;
+  plan->nstages = cfg.nstages;
+  if (plan->ntiles >= (1u << 30)) return nullptr;
+  // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)
+  std::vector<std::vector<uint8_t>> codes8(static_cast<size_t>(nblocks));
+  size_t recipe_u16 = 0;
   for (int b = 0; b < nblocks; ++b) {
-    std::vector<uint8_t> codes;
     TileBlockPlan& bp = plan->blk[b];
+    std::vector<uint8_t>& codes = codes8[size_t(b)];
     if (!build_recipes(dim, kc, *core, csrs[b]->kind, csrs[b]->grade, bp.no, bp.ni, codes)) return nullptr;
-    bp.recipe_off = int(all_codes.size());
-    all_codes.insert(all_codes.end(), codes.begin(), codes.end());
+    for (uint8_t c : codes)
+      if (c == 0xFF) return nullptr;  // a constant-zero mass entry inside a non-zero block: not generated for n <= 3
+    const bool shape_ok = (bp.no == 0 && bp.ni == 0) || (bp.no == 1 && bp.ni >= 1 && bp.ni <= 4) ||
+                          (bp.no == bp.ni && bp.no >= 2 && bp.no <= 4);
+    if (!shape_ok) return nullptr;
+    if (bp.no * bp.ni > 1) recipe_u16 += size_t(csrs[b]->el_rows * csrs[b]->el_cols) * size_t((bp.no * bp.ni + 3) / 4 * 4);
     bp.csr = csrs[b];
+    bp.nnz_at_build = csrs[b]->nnz;
+    bp.dropped_at_build = drop;
     const uint32_t T = uint32_t(csrs[b]->el_rows * csrs[b]->el_cols);
     bp.slot_bits = bits_for32(T ? T : 1);
   }
-  while (all_codes.size() % 8) all_codes.push_back(0xFF);
-  upload_vec(plan->recipes, all_codes);
+  const size_t recipe_bytes = (recipe_u16 * 2 + 15) / 16 * 16;
+  if (recipe_bytes > 2048) return nullptr;
   const int block = 256;
   const int nv = dim + 1;
+  const int ne = int(binom(dim + 1, 2));
   const size_t ncells = mesh->ncells;
   const uint32_t v_lo = uint32_t(mesh->vtile_lo);
   // ---- tile cell lists
+  DevBuf<uint32_t> tile_cells;
   {
     const size_t nkeys = ncells * size_t(nv);
     DevBuf<uint64_t> keys(nkeys), keys_alt(nkeys);
@@ -654,17 +952,18 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     if (tmp.n < tmp3) tmp.alloc(tmp3);
     FQ_CUDA(cub::DeviceReduce::Sum(tmp.p, tmp3, it, d_count.p, int64_t(nkeys), ctx->stream));
     fq_count_launch(ctx);
-    uint32_t nvalid = 0;
-    FQ_CUDA(cudaMemcpyAsync(&nvalid, d_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t nvalid = read_u32(ctx, d_count.p);
     DevBuf<uint32_t> tile_of(nvalid ? nvalid : 1);
-    plan->tile_cells.alloc(nvalid ? nvalid : 1);
+    tile_cells.alloc(nvalid ? nvalid : 1);
     split_keys_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(dk.Current(), nvalid, tile_of.p,
-                                                                                       plan->tile_cells.p);
+                                                                                       tile_cells.p);
     plan->tile_cell_ptr.alloc(size_t(plan->ntiles) + 1);
     seg_ptr_kernel<<<grid_for(size_t(nvalid) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
         tile_of.p, nvalid, plan->ntiles, plan->tile_cell_ptr.p);
-    fq_count_launch(ctx, 2);
+    plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne));
+    tile_cell_edges_kernel<<<grid_for(size_t(nvalid) * ne, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        tile_cells.p, nvalid, mesh->cell_faces[1].p, ne, plan->tile_cell_edges.p);
+    fq_count_launch(ctx, 3);
     FQ_CUDA(cudaGetLastError());
     std::vector<uint32_t> h_ptr(size_t(plan->ntiles) + 1);
     FQ_CUDA(cudaMemcpyAsync(h_ptr.data(), plan->tile_cell_ptr.p, h_ptr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -674,34 +973,74 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     for (uint32_t t = 0; t < plan->ntiles; ++t) max_cells = std::max(max_cells, h_ptr[t + 1] - h_ptr[t]);
     if (int(max_cells) > tile_cells_capacity(plan->ndistinct)) return nullptr;
     plan->cstride = int(max_cells) | 1;  // odd stride: distinct rows start on different banks
-    plan->smem_bytes = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double) + all_codes.size();
-    if (plan->smem_bytes > 227 * 1024 - 256) return nullptr;
+    // dynamic shared memory layout
+    size_t off = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double);
+    off = (off + 127) / 128 * 128;
+    plan->ring_off = uint32_t(off);
+    off += size_t(plan->nstages) * kChunkBytes;
+    plan->dir_off = uint32_t(off);
+    off += size_t(kMaxRecPerTile) * 4;
+    plan->chunk_off = uint32_t(off);
+    off += size_t(kMaxChunksPerTile + 1) * 4;
+    off = (off + 15) / 16 * 16;
+    plan->rec_off = uint32_t(off);
+    off += recipe_bytes;
+    off = (off + 7) / 8 * 8;
+    plan->mbar_off = uint32_t(off);
+    off += size_t(plan->nstages) * 16;  // full + empty barriers
+    plan->smem_bytes = off;
+    if (plan->smem_bytes > cfg.smem_cta) return nullptr;
   }
-  // ---- per block: tile-ordered nnz lists and remapped contributions
+  // ---- recipes as slab offsets: code16 = sign << 15 | distinct * cstride
+  if (size_t(plan->ndistinct) * size_t(plan->cstride) > 0x8000u) return nullptr;
+  std::vector<DevBuf<uint16_t>> direct_map(static_cast<size_t>(nblocks));  // (1,1) blocks: slot -> code16, used by the stream fill
+  {
+    std::vector<uint16_t> table(recipe_bytes / 2, 0);
+    size_t off16 = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      TileBlockPlan& bp = plan->blk[b];
+      const std::vector<uint8_t>& codes = codes8[size_t(b)];
+      const int nterms = bp.no * bp.ni;
+      const size_t nslots = size_t(csrs[b]->el_rows * csrs[b]->el_cols);
+      auto widen = [&](uint8_t c) { return uint16_t(((c & 0x80u) << 8) | uint32_t((c & 0x7Fu) * plan->cstride)); };
+      bp.recipe_off = int(off16);
+      if (nterms == 1) {
+        std::vector<uint16_t> dm(nslots);
+        for (size_t sl = 0; sl < nslots; ++sl) dm[sl] = widen(codes[sl]);
+        upload_vec(direct_map[size_t(b)], dm);
+      } else if (nterms > 1) {
+        const int nt4 = (nterms + 3) / 4 * 4;
+        for (size_t sl = 0; sl < nslots; ++sl)
+          for (int q = 0; q < nterms; ++q) table[off16 + sl * nt4 + q] = widen(codes[sl * nterms + q]);
+        off16 += nslots * size_t(nt4);
+      }
+    }
+    std::vector<uint8_t> bytes(recipe_bytes ? recipe_bytes : 16, 0);
+    if (recipe_bytes) std::memcpy(bytes.data(), table.data(), recipe_bytes);
+    upload_vec(plan->recipes, bytes);
+  }
+  // ---- per block: non-zeros sorted by (tile, L, signature), cut into warp records
+  const int use_sig = std::getenv("FQ_TILE_SIG") ? std::atoi(std::getenv("FQ_TILE_SIG")) : 0;
   DevBuf<int> d_err(1);
   FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+  std::vector<BlockBuild> bb(static_cast<size_t>(nblocks));
   for (int b = 0; b < nblocks; ++b) {
     fq_csr* csr = csrs[b];
-    TileBlockPlan& bp = plan->blk[b];
+    BlockBuild& B = bb[size_t(b)];
     const size_t s_nnz = csr->s_nnz;
     const size_t nrows_local = csr->row_end - csr->row_begin;
-    bp.tile_nnz_ptr.alloc(size_t(plan->ntiles) + 1);
-    bp.tile_con_ptr.alloc(size_t(plan->ntiles) + 1);
-    bp.nnz_at_build = csr->nnz;
-    bp.dropped_at_build = drop;
+    B.rec_tile_ptr.alloc(size_t(plan->ntiles) + 1);
     if (s_nnz == 0) {
-      FQ_CUDA(cudaMemsetAsync(bp.tile_nnz_ptr.p, 0, bp.tile_nnz_ptr.bytes(), ctx->stream));
-      FQ_CUDA(cudaMemsetAsync(bp.tile_con_ptr.p, 0, bp.tile_con_ptr.bytes(), ctx->stream));
-      bp.nnz_dest.alloc(1);
-      bp.nnz_end.alloc(1);
-      bp.con_src.alloc(1);
+      FQ_CUDA(cudaMemsetAsync(B.rec_tile_ptr.p, 0, B.rec_tile_ptr.bytes(), ctx->stream));
+      B.rec_len.alloc(1);
+      B.rec_rel.alloc(1);
       continue;
     }
     int tg, rg;
     kind_grades(csr->kind, csr->grade, tg, rg);
     const int nt = nlocal(dim, tg);
-    // top position of every local face of the test grade
-    std::vector<uint8_t> top_pos;
+    const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
+    std::vector<uint8_t> top_pos;  // top position of every local face of the test grade
     for (uint32_t m : colex_subsets(dim + 1, tg + 1)) top_pos.push_back(uint8_t(mask_elems(m).back()));
     DevBuf<uint8_t> d_top;
     upload_vec(d_top, top_pos);
@@ -710,41 +1049,103 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     row_tile_kernel<<<grid_for(ncells * size_t(nt), block, ctx->sm_count), block, 0, ctx->stream>>>(
         mesh->cell_faces[size_t(tg)].p, nt, mesh->cell_faces[0].p, nv, d_top.p, ncells, mesh->vertex_tile.p, v_lo,
         uint32_t(csr->row_begin), uint32_t(csr->row_end), row_tile.p);
-    DevBuf<uint32_t> nnz_tile(s_nnz), perm(s_nnz);
-    nnz_tile_kernel<<<grid_for(nrows_local, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        csr->s_row_ptr.p, uint32_t(nrows_local), row_tile.p, nnz_tile.p, perm.p);
+    DevBuf<uint64_t> key(s_nnz);
+    B.perm.alloc(s_nnz);
+    nnz_key_kernel<<<grid_for(nrows_local, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        csr->s_row_ptr.p, uint32_t(nrows_local), row_tile.p, csr->contrib_ptr.p, csr->contrib_src.p, T, use_sig, key.p,
+        B.perm.p, d_err.p);
     fq_count_launch(ctx, 2);
     FQ_CUDA(cudaGetLastError());
-    radix_sort_pairs_u32(ctx, nnz_tile, perm, s_nnz, bits_for32(plan->ntiles));
-    seg_ptr_kernel<<<grid_for(s_nnz + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(nnz_tile.p, s_nnz, plan->ntiles,
-                                                                                        bp.tile_nnz_ptr.p);
-    DevBuf<uint32_t> len(s_nnz), G(s_nnz);
-    nnz_len_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(perm.p, uint32_t(s_nnz),
-                                                                                    csr->contrib_ptr.p, len.p);
-    size_t tmp_bytes = 0;
-    FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len.p, G.p, int64_t(s_nnz), ctx->stream));
-    DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
-    FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, len.p, G.p, int64_t(s_nnz), ctx->stream));
-    tile_con_ptr_kernel<<<grid_for(size_t(plan->ntiles) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        bp.tile_nnz_ptr.p, plan->ntiles, G.p, uint32_t(s_nnz), uint32_t(csr->ncontrib), bp.tile_con_ptr.p);
-    bp.nnz_dest.alloc(s_nnz);
-    bp.nnz_end.alloc(s_nnz);
-    bp.con_src.alloc(csr->ncontrib ? csr->ncontrib : 1);
-    const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
-    nnz_fill_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        perm.p, nnz_tile.p, uint32_t(s_nnz), G.p, bp.tile_con_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, bp.slot_bits,
-        plan->tile_cell_ptr.p, plan->tile_cells.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0, bp.nnz_dest.p,
-        bp.nnz_end.p, bp.con_src.p, d_err.p);
+    radix_sort_pairs_u64(ctx, key, B.perm, s_nnz, 24 + bits_for32(plan->ntiles));
+    DevBuf<uint32_t> head(s_nnz);
+    B.run_scan.alloc(s_nnz);
+    run_heads_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), head.p);
+    inclusive_scan_u32(ctx, head.p, B.run_scan.p, s_nnz);
+    B.nruns = read_u32(ctx, B.run_scan.p + (s_nnz - 1));
+    B.run_start.alloc(size_t(B.nruns) + 1);
+    B.run_tile.alloc(B.nruns);
+    B.run_len.alloc(B.nruns);
+    run_info_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        key.p, head.p, B.run_scan.p, uint32_t(s_nnz), B.run_start.p, B.run_tile.p, B.run_len.p);
+    const uint32_t n32 = uint32_t(s_nnz);
+    FQ_CUDA(cudaMemcpyAsync(B.run_start.p + B.nruns, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<uint32_t> nrec_run(size_t(B.nruns) + 1);
+    B.rec_base.alloc(size_t(B.nruns) + 1);
+    run_nrec_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(B.run_start.p, B.nruns,
+                                                                                                 nrec_run.p);
+    exclusive_scan_u32(ctx, nrec_run.p, B.rec_base.p, size_t(B.nruns) + 1);
+    B.nrec = read_u32(ctx, B.rec_base.p + B.nruns);
+    B.rec_len.alloc(B.nrec ? B.nrec : 1);
+    B.rec_rel.alloc(B.nrec ? B.nrec : 1);
+    rec_len_kernel<<<grid_for(B.nruns, block, ctx->sm_count), block, 0, ctx->stream>>>(B.rec_base.p, B.run_len.p, B.nruns,
+                                                                                      B.rec_len.p);
+    // first record of every tile: first run of the tile -> its record base
+    DevBuf<uint32_t> first_run(size_t(plan->ntiles) + 1);
+    seg_ptr_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(B.run_tile.p, B.nruns,
+                                                                                                 plan->ntiles, first_run.p);
+    gather_u32_kernel<<<grid_for(size_t(plan->ntiles) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        first_run.p, plan->ntiles + 1, B.rec_base.p, B.rec_tile_ptr.p);
     fq_count_launch(ctx, 6);
     FQ_CUDA(cudaGetLastError());
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  // ---- layout of the per-tile streams
+  TileLayoutArgs la{};
+  la.nblocks = nblocks;
+  for (int b = 0; b < nblocks; ++b)
+    la.blk[b] = TileLayoutBlock{bb[size_t(b)].rec_tile_ptr.p, bb[size_t(b)].rec_len.p, bb[size_t(b)].rec_rel.p};
+  DevBuf<uint32_t> tile_units(size_t(plan->ntiles) + 1), tile_nrec(size_t(plan->ntiles) + 1);
+  FQ_CUDA(cudaMemsetAsync(tile_units.p, 0, tile_units.bytes(), ctx->stream));
+  FQ_CUDA(cudaMemsetAsync(tile_nrec.p, 0, tile_nrec.bytes(), ctx->stream));
+  tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      la, plan->ntiles, 0, tile_units.p, tile_nrec.p, nullptr, nullptr);
+  fq_count_launch(ctx);
+  {
+    // capacity checks on the host (ntiles is small)
+    std::vector<uint32_t> h_units(size_t(plan->ntiles) + 1), h_nrec(size_t(plan->ntiles) + 1);
+    FQ_CUDA(cudaMemcpyAsync(h_units.data(), tile_units.p, h_units.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaMemcpyAsync(h_nrec.data(), tile_nrec.p, h_nrec.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t total_units = 0;
+    for (uint32_t t = 0; t < plan->ntiles; ++t) {
+      if (h_nrec[t] > uint32_t(kMaxRecPerTile)) return nullptr;
+      if (uint64_t(h_units[t]) * 64 > uint64_t(kMaxChunksPerTile) * kChunkBytes) return nullptr;
+      total_units += h_units[t];
+    }
+    if (total_units >= (1ull << 32)) return nullptr;
+  }
+  plan->tile_stream_ptr.alloc(size_t(plan->ntiles) + 1);
+  plan->tile_dir_ptr.alloc(size_t(plan->ntiles) + 1);
+  exclusive_scan_u32(ctx, tile_units.p, plan->tile_stream_ptr.p, size_t(plan->ntiles) + 1);
+  exclusive_scan_u32(ctx, tile_nrec.p, plan->tile_dir_ptr.p, size_t(plan->ntiles) + 1);
+  const uint32_t total_units = read_u32(ctx, plan->tile_stream_ptr.p + plan->ntiles);
+  const uint32_t total_rec = read_u32(ctx, plan->tile_dir_ptr.p + plan->ntiles);
+  plan->stream.alloc(size_t(total_units ? total_units : 1) * 64);
+  plan->rec_dir.alloc(total_rec ? total_rec : 1);
+  FQ_CUDA(cudaMemsetAsync(plan->stream.p, 0xFF, plan->stream.bytes(), ctx->stream));
+  tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      la, plan->ntiles, 1, nullptr, nullptr, plan->tile_dir_ptr.p, plan->rec_dir.p);
+  fq_count_launch(ctx);
+  for (int b = 0; b < nblocks; ++b) {
+    fq_csr* csr = csrs[b];
+    BlockBuild& B = bb[size_t(b)];
+    if (csr->s_nnz == 0) continue;
+    const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
+    stream_fill_kernel<<<grid_for(csr->s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        B.perm.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.rec_base.p, B.rec_rel.p,
+        plan->tile_stream_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, plan->blk[b].slot_bits, plan->tile_cell_ptr.p,
+        tile_cells.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0,
+        plan->blk[b].no * plan->blk[b].ni == 1 ? direct_map[size_t(b)].p : nullptr, plan->stream.p, d_err.p);
+    fq_count_launch(ctx);
+  }
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   int h_err = 0;
   FQ_CUDA(cudaMemcpy(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-  if (h_err) return nullptr;  // a tile exceeds the 16-bit local index space: keep the slab path
+  if (h_err) return nullptr;  // a tile exceeds the 16-bit local index space / 255 contributions: keep the slab path
   plan->changed.alloc(1);
   plan->ticket.alloc(1);
-  plan->grid = ctx->sm_count;
+  plan->grid = ctx->sm_count * cfg.ctas_per_sm;
   return plan;
 }
 
@@ -753,13 +1154,22 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
 bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   TileParams P{};
   P.tile_cell_ptr = plan.tile_cell_ptr.p;
-  P.tile_cells = plan.tile_cells.p;
-  P.cell_edges = mesh->cell_faces[1].p;
+  P.tile_cell_edges = plan.tile_cell_edges.p;
   P.lengths = mesh->lengths.p;
   P.edge_lo = uint32_t(mesh->edge_lo);
   P.ntiles = plan.ntiles;
+  P.tile_dir_ptr = plan.tile_dir_ptr.p;
+  P.rec_dir = plan.rec_dir.p;
+  P.tile_stream_ptr = plan.tile_stream_ptr.p;
+  P.stream = plan.stream.p;
   P.cstride = plan.cstride;
   P.nblocks = plan.nblocks;
+  P.nstages = plan.nstages;
+  P.ring_off = plan.ring_off;
+  P.dir_off = plan.dir_off;
+  P.chunk_off = plan.chunk_off;
+  P.rec_off = plan.rec_off;
+  P.mbar_off = plan.mbar_off;
   P.recipes = plan.recipes.p;
   P.recipe_bytes = int(plan.recipes.n);
   P.check_classification = plan.blk[0].dropped_at_build ? 1 : 0;
@@ -768,11 +1178,6 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   for (int b = 0; b < plan.nblocks; ++b) {
     const TileBlockPlan& bp = plan.blk[b];
     TileBlockDev& d = P.blk[b];
-    d.tile_nnz_ptr = bp.tile_nnz_ptr.p;
-    d.tile_con_ptr = bp.tile_con_ptr.p;
-    d.nnz_dest = bp.nnz_dest.p;
-    d.nnz_end = bp.nnz_end.p;
-    d.con_src = bp.con_src.p;
     d.values = bp.csr->values.p;
     d.no = bp.no;
     d.ni = bp.ni;
@@ -801,13 +1206,8 @@ bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const*
 }
 
 int64_t tile_plan_bytes(const TilePlan& plan) {
-  int64_t total = int64_t(plan.tile_cell_ptr.bytes() + plan.tile_cells.bytes());
-  for (int b = 0; b < plan.nblocks; ++b) {
-    const TileBlockPlan& bp = plan.blk[b];
-    total += int64_t(bp.tile_nnz_ptr.bytes() + bp.tile_con_ptr.bytes() + bp.nnz_dest.bytes() + bp.nnz_end.bytes() +
-                     bp.con_src.bytes());
-  }
-  return total;
+  return int64_t(plan.tile_cell_ptr.bytes() + plan.tile_cell_edges.bytes() + plan.tile_dir_ptr.bytes() + plan.rec_dir.bytes() +
+                 plan.tile_stream_ptr.bytes() + plan.stream.bytes());
 }
 
 }  // namespace fq
