@@ -43,10 +43,13 @@
 namespace fq {
 
 constexpr int kTileMaxBlocks = 4;
-constexpr uint32_t kPadDest = 0xFFFFFFFFu;  // padding lane of a record
-constexpr uint32_t kNoDest = 0xFFFFFFFEu;   // dropped non-zero: must stay all-zero (galerkin.rs:173)
+// dest codes of the stream: 0 = padding lane, 1 = dropped non-zero (must stay all-zero, galerkin.rs:173),
+// d >= 2 = position d - 2 of csr->values
+constexpr uint32_t kPadDest = 0u;
+constexpr uint32_t kNoDest = 1u;
+constexpr int kRecLanes = 64;               // non-zeros per record: two per lane (two independent chains)
 constexpr int kChunkBytes = 8192;           // TMA chunk of the tile stream; records never straddle a chunk
-constexpr int kMaxRecPerTile = 1024;        // directory capacity in shared memory
+constexpr int kMaxRecPerTile = 512;         // directory capacity in shared memory
 constexpr int kMaxChunksPerTile = 96;
 constexpr int kMaxLen = 255;                // contributions per non-zero (8 bits in the directory)
 
@@ -70,9 +73,10 @@ struct TileParams {
   int cstride;                      // cells capacity of the shared slab
   int nblocks;
   int nstages;                      // ring slots
-  uint32_t ring_off, dir_off, chunk_off, rec_off, mbar_off;  // byte offsets in dynamic shared memory
+  uint32_t ring_off, dir_off, chunk_off, rec_off, eid_off, mbar_off;  // byte offsets in dynamic shared memory
   const uint8_t* recipes;           // code = distinct slot | 0x80 negated; 0xFF = no term
   int recipe_bytes;
+  int debug;                        // development knobs (FQ_TILE_DEBUG): 1 skip K1, 2 skip records, 4 skip stores
   int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
   int* changed;                     // raised when the zero/non-zero classification differs from the plan's
   unsigned int* ticket;             // dynamic tile scheduler
@@ -121,48 +125,62 @@ __device__ __forceinline__ double signed_load(const double* __restrict__ p, uint
   return __hiloint2double(__double2hiint(x) ^ int((code & 0x8000u) << 16), __double2loint(x));
 }
 
-// One lane's non-zero of a record: sum over its L contributions, each a recipe of
-// NO x NI signed mass entries:  v = (((x00 + x01) + ..) + ((x10 + x11) + ..)) + ..
+// Value of one contribution: a recipe of NO x NI signed mass entries
+//   v = (((x00 + x01) + ..) + ((x10 + x11) + ..)) + ..
 // (the k-ascending gemm order of operators.rs:201-211 with the +-1 incidence entries folded in).
 template <int NO, int NI>
-__device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent, uint32_t L, const double* __restrict__ slab,
-                                              const uint16_t* __restrict__ brec, uint32_t sb, uint32_t slot_mask, double& acc,
-                                              bool& any) {
+__device__ __forceinline__ double recipe_value(uint32_t e, const double* __restrict__ slab, const uint16_t* __restrict__ brec,
+                                               uint32_t sb, uint32_t slot_mask) {
   constexpr int NT4 = (NO * NI + 3) / 4 * 4;  // codes per slot, padded to 8-byte groups
-#pragma unroll 2
+  const double* __restrict__ sc = slab + (e >> sb);
+  const uint2* __restrict__ rr = reinterpret_cast<const uint2*>(brec + (e & slot_mask) * NT4);
+  uint32_t code[NT4];
+#pragma unroll
+  for (int w = 0; w < NT4 / 4; ++w) {
+    const uint2 c = rr[w];
+    code[4 * w + 0] = c.x & 0xFFFFu;
+    code[4 * w + 1] = c.x >> 16;
+    code[4 * w + 2] = c.y & 0xFFFFu;
+    code[4 * w + 3] = c.y >> 16;
+  }
+  double v = 0.0;
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    double inner = signed_load(sc, code[o * NI]);
+#pragma unroll
+    for (int q = 1; q < NI; ++q) inner = __dadd_rn(inner, signed_load(sc, code[o * NI + q]));
+    v = (o == 0) ? inner : __dadd_rn(v, inner);
+  }
+  return v;
+}
+// The two non-zeros of a lane (columns lane and lane + 32 of the record): left-to-right sums over L contributions.
+template <int NO, int NI>
+__device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent, uint32_t L, const double* __restrict__ slab,
+                                              const uint16_t* __restrict__ brec, uint32_t sb, uint32_t slot_mask, double& acc0,
+                                              double& acc1, bool& any0, bool& any1) {
+#pragma unroll 1
   for (uint32_t j = 0; j < L; ++j) {
-    const uint32_t e = ent[j * 32];
-    const double* __restrict__ sc = slab + (e >> sb);
-    const uint2* __restrict__ rr = reinterpret_cast<const uint2*>(brec + (e & slot_mask) * NT4);
-    uint32_t code[NT4];
-#pragma unroll
-    for (int w = 0; w < NT4 / 4; ++w) {
-      const uint2 c = rr[w];
-      code[4 * w + 0] = c.x & 0xFFFFu;
-      code[4 * w + 1] = c.x >> 16;
-      code[4 * w + 2] = c.y & 0xFFFFu;
-      code[4 * w + 3] = c.y >> 16;
-    }
-    double v = 0.0;
-#pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      double inner = signed_load(sc, code[o * NI]);
-#pragma unroll
-      for (int q = 1; q < NI; ++q) inner = __dadd_rn(inner, signed_load(sc, code[o * NI + q]));
-      v = (o == 0) ? inner : __dadd_rn(v, inner);
-    }
-    any = any || (v != 0.0);
-    acc = __dadd_rn(acc, v);
+    const uint32_t e0 = ent[j * kRecLanes], e1 = ent[j * kRecLanes + 32];
+    const double v0 = recipe_value<NO, NI>(e0, slab, brec, sb, slot_mask);
+    const double v1 = recipe_value<NO, NI>(e1, slab, brec, sb, slot_mask);
+    any0 = any0 || (v0 != 0.0);
+    any1 = any1 || (v1 != 0.0);
+    acc0 = __dadd_rn(acc0, v0);
+    acc1 = __dadd_rn(acc1, v1);
   }
 }
 // mass blocks: the stream entries are pre-translated to sign | slab offset
 __device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict__ ent, uint32_t L,
-                                                     const double* __restrict__ slab, double& acc, bool& any) {
-#pragma unroll 4
+                                                     const double* __restrict__ slab, double& acc0, double& acc1, bool& any0,
+                                                     bool& any1) {
+#pragma unroll 1
   for (uint32_t j = 0; j < L; ++j) {
-    const double x = signed_load(slab, ent[j * 32]);
-    any = any || (x != 0.0);
-    acc = __dadd_rn(acc, x);
+    const double x0 = signed_load(slab, ent[j * kRecLanes]);
+    const double x1 = signed_load(slab, ent[j * kRecLanes + 32]);
+    any0 = any0 || (x0 != 0.0);
+    any1 = any1 || (x1 != 0.0);
+    acc0 = __dadd_rn(acc0, x0);
+    acc1 = __dadd_rn(acc1, x1);
   }
 }
 
@@ -174,12 +192,17 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
   uint32_t* dir = reinterpret_cast<uint32_t*>(smem_raw + P.dir_off);
   uint32_t* chunk_first = reinterpret_cast<uint32_t*>(smem_raw + P.chunk_off);
   uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
+  unsigned char* eid_stage = smem_raw + P.eid_off;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
-  __shared__ uint32_t s_hdr[2][8];
+  __shared__ uint32_t s_hdr[3][8];
+  __shared__ uint32_t s_nrec;
   constexpr int NW = NT / 32;
+  constexpr int NEE = NE > 0 ? NE : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = P.nstages;
   uint64_t* empty = full + S;
+  uint64_t* dirbar = empty + S;
+  uint64_t* eidbar = dirbar + 1;
   auto fetch_header = [&](uint32_t* h) {  // thread 0: next tile from the dynamic scheduler
     const uint32_t t = atomicAdd(P.ticket, 1u);
     h[0] = t;
@@ -192,91 +215,139 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
       h[6] = __ldg(P.tile_stream_ptr + t + 1);
     }
   };
+  // thread 0: TMA of a tile's pre-gathered edge ids into the staging buffer (16-byte aligned window)
+  auto issue_eids = [&](const uint32_t* h) {
+    if (h[0] >= P.ntiles) return;
+    const size_t b0 = size_t(h[1]) * NE * 4, b1 = size_t(h[2]) * NE * 4;
+    const size_t a0 = b0 & ~size_t(15);
+    const uint32_t bytes = uint32_t(((b1 - a0) + 15) & ~size_t(15));
+    mbar_expect_tx(eidbar, bytes);
+    tma_load_1d(eid_stage, reinterpret_cast<const unsigned char*>(P.tile_cell_edges) + a0, bytes, eidbar);
+  };
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NW);
     }
+    mbar_init(dirbar, 1);
+    mbar_init(eidbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fetch_header(s_hdr[0]);
+    fetch_header(s_hdr[1]);
+    issue_eids(s_hdr[0]);
   }
   for (int i = tid; i < P.recipe_bytes / 2; i += NT) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
-  uint32_t g = 0;  // chunks this CTA has pushed through the ring so far (slot = g % S, parity = (g / S) & 1)
+  uint32_t g = 0;          // chunks this CTA has pushed through the ring so far (slot = g % S, parity = (g / S) & 1)
+  double s_next[NEE];      // this thread's cell of the NEXT tile: edge lengths, loaded while the current tile is gathered
+  bool have_next = false;
+  uint32_t dir_uses = 0;   // completed phases of dirbar (tiles with a non-empty directory)
   for (uint32_t it = 0;; ++it) {
     __syncthreads();  // previous tile fully consumed, this tile's header visible
-    const uint32_t* hdr = s_hdr[it & 1];
+    const uint32_t* hdr = s_hdr[it % 3];
     const uint32_t t = hdr[0];
     if (t >= P.ntiles) break;
-    const uint32_t cbase = hdr[1], nc = hdr[2] - hdr[1];
-    const uint32_t d0 = hdr[3], nrec = hdr[4] - hdr[3];
+    const uint32_t nc = hdr[2] - hdr[1];
+    const uint32_t d0 = hdr[3], ndir = hdr[4] - hdr[3];
     const uint32_t sbytes = (hdr[6] - hdr[5]) * 64u;
     const unsigned char* sbase = P.stream + size_t(hdr[5]) * 64u;
     const uint32_t nchunks = (sbytes + kChunkBytes - 1) / kChunkBytes;
-    // ---- the first ring slots start filling now and land while K1 runs
+    // ---- the first ring slots and the directory start filling now and land while K1 runs
     if (tid == 0) {
+      uint32_t sl = g % S;
       for (uint32_t k = 0; k < nchunks && k < uint32_t(S); ++k) {
         const uint32_t bytes = min(uint32_t(kChunkBytes), sbytes - k * kChunkBytes);
-        uint64_t* bar = &full[(g + k) % S];
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(ring + ((g + k) % S) * kChunkBytes, sbase + size_t(k) * kChunkBytes, bytes, bar);
+        mbar_expect_tx(&full[sl], bytes);
+        tma_load_1d(ring + sl * kChunkBytes, sbase + size_t(k) * kChunkBytes, bytes, &full[sl]);
+        if (++sl == uint32_t(S)) sl = 0;
+      }
+      if (ndir) {
+        mbar_expect_tx(dirbar, ndir * 4u);
+        tma_load_1d(dir, P.rec_dir + d0, ndir * 4u, dirbar);
       }
     }
-    for (uint32_t i = tid; i < nrec; i += NT) dir[i] = __ldg(P.rec_dir + d0 + i);
     // ---- K1: element masses of the tile's cells -> shared slab [distinct][cell]
-    if (nrec != 0) {
-      for (uint32_t c = tid; c < nc; c += NT) {
-        const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
-        uint32_t eid[NE > 0 ? NE : 1];
+    if (!have_next) {  // first tile of this CTA: no prefetched lengths yet
+      mbar_wait(eidbar, it & 1u);
+      if (uint32_t(tid) < nc) {
+        const uint32_t* ce = reinterpret_cast<const uint32_t*>(eid_stage + ((size_t(hdr[1]) * NE * 4) & 15)) + size_t(tid) * NE;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
-        double s[NE > 0 ? NE : 1];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
-        TileSink sink{slab + c, P.cstride};
-        fn(s, sink);
+        for (int e = 0; e < NE; ++e) s_next[e] = __ldg(P.lengths + (ce[e] - P.edge_lo));
       }
     }
-    __syncthreads();
-    // the next tile's header is fetched while this one is gathered
-    if (tid == 0) fetch_header(s_hdr[(it + 1) & 1]);
-    // first record of every chunk (records are laid out in order and never straddle a chunk)
-    for (uint32_t i = tid; i < nrec; i += NT) {
-      const uint32_t ck = ((dir[i] & 0x3FFFFFu) * 64u) / kChunkBytes;
-      if (i == 0 || ck != ((dir[i - 1] & 0x3FFFFFu) * 64u) / kChunkBytes) chunk_first[ck] = i;
+    if (uint32_t(tid) < nc && ndir != 0 && !(P.debug & 1)) {
+      TileSink sink{slab + tid, P.cstride};
+      fn(s_next, sink);
     }
-    if (tid == 0) chunk_first[nchunks] = nrec;
+    have_next = false;
     __syncthreads();
-    // ---- K3: one warp per record, one lane per owned structural non-zero
+    // the header after next is fetched, and the next tile's edge ids are staged, while this tile is gathered
+    if (tid == 0) {
+      issue_eids(s_hdr[(it + 1) % 3]);
+      fetch_header(s_hdr[(it + 2) % 3]);
+    }
+    // first record of every chunk (records are laid out in order and never straddle a chunk);
+    // the directory is padded with 0xFFFFFFFF to a multiple of four entries
+    if (ndir) mbar_wait(dirbar, dir_uses++ & 1u);
+    for (uint32_t i = tid; i < ndir; i += NT) {
+      const uint32_t di = dir[i];
+      if (di == 0xFFFFFFFFu) continue;
+      const uint32_t ck = ((di & 0x3FFFFFu) * 64u) / kChunkBytes;
+      if (i == 0 || ck != ((dir[i - 1] & 0x3FFFFFu) * 64u) / kChunkBytes) chunk_first[ck] = i;
+      if (i + 1 == ndir || dir[i + 1] == 0xFFFFFFFFu) s_nrec = i + 1;
+    }
+    __syncthreads();
+    if (tid == 0) chunk_first[nchunks] = s_nrec;
+    const uint32_t* hnext = s_hdr[(it + 1) % 3];
+    // lengths of this thread's cell of the next tile (their latency is covered by the gather below)
+    auto prefetch_next = [&]() {
+      if (hnext[0] < P.ntiles) {
+        mbar_wait(eidbar, (it + 1) & 1u);
+        if (uint32_t(tid) < hnext[2] - hnext[1]) {
+          const uint32_t* ce =
+              reinterpret_cast<const uint32_t*>(eid_stage + ((size_t(hnext[1]) * NE * 4) & 15)) + size_t(tid) * NE;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) s_next[e] = __ldg(P.lengths + (ce[e] - P.edge_lo));
+        }
+        have_next = true;
+      }
+    };
+    if (nchunks < 2) prefetch_next();
+    __syncthreads();
+    // ---- K3: one warp per record, two owned structural non-zeros per lane
+    uint32_t slot = g % S, parity = (g / S) & 1u;
     for (uint32_t k = 0; k < nchunks; ++k) {
-      const uint32_t slot = (g + k) % S, parity = ((g + k) / S) & 1u;
       mbar_wait(&full[slot], parity);
-      const unsigned char* chunk = ring + slot * kChunkBytes;
+      const unsigned char* chunk = ring + slot * kChunkBytes - k * kChunkBytes;
       const uint32_t r1 = chunk_first[k + 1];
-      for (uint32_t r = chunk_first[k] + warp; r < r1; r += NW) {
+      for (uint32_t r = chunk_first[k] + warp; r < r1 && !(P.debug & 2); r += NW) {
         const uint32_t d = dir[r];
         const uint32_t b = d >> 30, L = (d >> 22) & 0xFFu;
-        const unsigned char* rp = chunk + ((d & 0x3FFFFFu) * 64u - k * kChunkBytes);
-        const uint32_t dest = reinterpret_cast<const uint32_t*>(rp)[lane];
-        if (dest == kPadDest) continue;
-        const uint16_t* __restrict__ ent = reinterpret_cast<const uint16_t*>(rp + 128) + lane;
+        const unsigned char* rp = chunk + (d & 0x3FFFFFu) * 64u;
+        const uint32_t dest0 = reinterpret_cast<const uint32_t*>(rp)[lane];
+        const uint32_t dest1 = reinterpret_cast<const uint32_t*>(rp)[lane + 32];
+        const uint16_t* __restrict__ ent = reinterpret_cast<const uint16_t*>(rp + 4 * kRecLanes) + lane;
         const TileBlockDev& B = P.blk[b];
         const uint16_t* __restrict__ brec = rec + B.recipe_off;
         const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
-        double acc = 0.0;
-        bool any = false;
+        double acc0 = 0.0, acc1 = 0.0;
+        bool any0 = false, any1 = false;
         switch (B.no * 8 + B.ni) {
           case 0: break;  // zero space: every contribution is an exact zero
-          case 1 * 8 + 1: gather_record_direct(ent, L, slab, acc, any); break;
-          case 1 * 8 + 2: gather_record<1, 2>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
-          case 1 * 8 + 3: gather_record<1, 3>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
-          case 1 * 8 + 4: gather_record<1, 4>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
-          case 2 * 8 + 2: gather_record<2, 2>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
-          case 3 * 8 + 3: gather_record<3, 3>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
-          default: gather_record<4, 4>(ent, L, slab, brec, sb, slot_mask, acc, any); break;
+          case 1 * 8 + 1: gather_record_direct(ent, L, slab, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 2: gather_record<1, 2>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 3: gather_record<1, 3>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 4: gather_record<1, 4>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 2 * 8 + 2: gather_record<2, 2>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 3 * 8 + 3: gather_record<3, 3>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          default: gather_record<4, 4>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
         }
-        const bool kept = dest != kNoDest;
-        if (P.check_classification && kept != any) *P.changed = 1;
-        if (kept) B.values[dest] = acc;
+        // padding lanes carry zero entries (they read slab[0]) and never store
+        if (P.check_classification && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) ||
+                                       (dest1 != kPadDest && (dest1 != kNoDest) != any1)))
+          *P.changed = 1;
+        if (P.debug & 4) continue;
+        if (dest0 > kNoDest) B.values[dest0 - 2u] = acc0;
+        if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
       }
       // this warp is done with the slot; the chunk's refill is issued by one rotating warp
       // once every warp has left it (no CTA-wide barrier on the stream)
@@ -291,6 +362,8 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
           tma_load_1d(ring + slot * kChunkBytes, sbase + size_t(kk) * kChunkBytes, bytes, &full[slot]);
         }
       }
+      if (++slot == uint32_t(S)) slot = 0, parity ^= 1u;
+      if (k == 0 && nchunks >= 2) prefetch_next();
     }
     g += nchunks;
   }
@@ -311,7 +384,7 @@ struct TilePlan {
   int cstride = 0;
   int nthreads = 512, nstages = 3;
   size_t smem_bytes = 0;
-  uint32_t ring_off = 0, dir_off = 0, chunk_off = 0, rec_off = 0, mbar_off = 0;
+  uint32_t ring_off = 0, dir_off = 0, chunk_off = 0, rec_off = 0, eid_off = 0, mbar_off = 0;
   DevBuf<uint32_t> tile_cell_ptr, tile_cell_edges, tile_dir_ptr, rec_dir, tile_stream_ptr;
   DevBuf<unsigned char> stream;
   DevBuf<uint8_t> recipes;
@@ -334,20 +407,23 @@ struct TilePlan {
 FQ_GEN_CORE_LIST(FQ_DECLARE_CORE)
 #undef FQ_DECLARE_CORE
 
-template <class Fn, int NE>
-static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+template <class Fn, int NE, int NT>
+static void launch_tile_nt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static bool attr_set = false;
   if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024 - 256));
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 113 * 1024 - 256));
     attr_set = true;
   }
-  if (plan.nthreads == 512)
-    tile_assemble_kernel<Fn, NE, 512, 1><<<plan.grid, 512, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
-  else
-    tile_assemble_kernel<Fn, NE, 256, 2><<<plan.grid, 256, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  tile_assemble_kernel<Fn, NE, NT, 1><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+}
+template <class Fn, int NE>
+static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+  switch (plan.nthreads) {
+    case 1024: launch_tile_nt<Fn, NE, 1024>(ctx, plan, params); break;
+    case 768: launch_tile_nt<Fn, NE, 768>(ctx, plan, params); break;
+    default: launch_tile_nt<Fn, NE, 512>(ctx, plan, params); break;
+  }
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
 }
@@ -374,19 +450,22 @@ struct TileConfig {
 };
 static TileConfig tile_config() {
   TileConfig c{512, 1, 3, size_t(227) * 1024 - 256};
-  if (const char* e = std::getenv("FQ_TILE_THREADS"))
-    if (std::atoi(e) == 256) c = TileConfig{256, 2, 2, size_t(113) * 1024 - 256};
-  if (const char* e = std::getenv("FQ_TILE_STAGES")) c.nstages = std::max(1, std::min(8, std::atoi(e)));
+  if (const char* e = std::getenv("FQ_TILE_THREADS")) {
+    const int nt = std::atoi(e);
+    if (nt == 512 || nt == 768 || nt == 1024) c.nthreads = nt;
+  }
+  if (const char* e = std::getenv("FQ_TILE_STAGES")) c.nstages = std::max(1, std::min(16, std::atoi(e)));
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
   return size_t(c.nstages) * kChunkBytes + size_t(kMaxRecPerTile) * 4 + size_t(kMaxChunksPerTile + 1) * 4 + 2048 /*recipes*/ +
-         128 /*mbarriers*/ + 512 /*alignment slack*/;
+         256 /*mbarriers*/ + 512 /*alignment slack*/;
 }
 int tile_cells_capacity(int ndistinct) {
   const TileConfig c = tile_config();
-  int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double)));
-  return std::min(cap, 1023);
+  // per cell: its distinct mass values + 6 staged edge ids (dim <= 3)
+  int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double) + 24));
+  return std::min(cap, c.nthreads);  // K1 is one cell per thread
 }
 
 // Recipes of one block over the distinct values of core(n, kc).
@@ -586,7 +665,7 @@ __global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t
 __global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, uint32_t nruns, uint32_t* __restrict__ nrec) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nruns; r += stride)
-    nrec[r] = r < nruns ? (run_start[r + 1] - run_start[r] + 31u) / 32u : 0u;
+    nrec[r] = r < nruns ? (run_start[r + 1] - run_start[r] + uint32_t(kRecLanes) - 1u) / uint32_t(kRecLanes) : 0u;
 }
 __global__ void rec_len_kernel(const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
                                uint8_t* __restrict__ rec_len) {
@@ -622,7 +701,7 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
       const TileLayoutBlock& B = A.blk[b];
       for (uint32_t k = B.rec_tile_ptr[t]; k < B.rec_tile_ptr[t + 1]; ++k) {
         const uint32_t L = B.rec_len[k];
-        const uint32_t size = 128u + 64u * L;
+        const uint32_t size = uint32_t(kRecLanes) * (4u + 2u * L);
         if (off / kChunkBytes != (off + size - 1) / kChunkBytes) off = (off / kChunkBytes + 1) * kChunkBytes;
         if (pass) {
           B.rec_rel[k] = off / 64u;
@@ -634,7 +713,7 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
     }
     if (!pass) {
       tile_units[t] = off / 64u;
-      tile_nrec[t] = nrec;
+      tile_nrec[t] = (nrec + 3u) & ~3u;  // the directory of a tile is TMA-copied: 16-byte granules
     }
   }
 }
@@ -653,11 +732,11 @@ __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n
     const uint32_t q = perm[i];
     const uint32_t r = run_scan[i] - 1;
     const uint32_t idx = i - run_start[r];
-    const uint32_t k = rec_base[r] + idx / 32u, lane = idx % 32u;
+    const uint32_t k = rec_base[r] + idx / uint32_t(kRecLanes), lane = idx % uint32_t(kRecLanes);
     const uint32_t t = run_tile[r];
     unsigned char* rp = stream + (size_t(tile_stream_ptr[t]) + rec_rel[k]) * 64u;
-    reinterpret_cast<uint32_t*>(rp)[lane] = drop ? (keep[q] ? pos[q] : kNoDest) : q;
-    uint16_t* ent = reinterpret_cast<uint16_t*>(rp + 128) + lane;
+    reinterpret_cast<uint32_t*>(rp)[lane] = drop ? (keep[q] ? pos[q] + 2u : kNoDest) : q + 2u;
+    uint16_t* ent = reinterpret_cast<uint16_t*>(rp + 4 * kRecLanes) + lane;
     const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
     const uint32_t cb = tile_cell_ptr[t], ce = tile_cell_ptr[t + 1];
     for (uint32_t p = p0; p < p1; ++p) {
@@ -679,10 +758,10 @@ __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n
       if (direct_map) {
         const uint32_t code = direct_map[slot];
         if ((code & 0x7FFFu) + local > 0x7FFFu) atomicExch(err, 3);
-        ent[(p - p0) * 32u] = uint16_t((code & 0x8000u) | ((code & 0x7FFFu) + local));
+        ent[(p - p0) * uint32_t(kRecLanes)] = uint16_t((code & 0x8000u) | ((code & 0x7FFFu) + local));
       } else {
         if ((local << slot_bits) > 0xFFFFu) atomicExch(err, 3);
-        ent[(p - p0) * 32u] = uint16_t((local << slot_bits) | slot);
+        ent[(p - p0) * uint32_t(kRecLanes)] = uint16_t((local << slot_bits) | slot);
       }
     }
   }
@@ -960,7 +1039,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     plan->tile_cell_ptr.alloc(size_t(plan->ntiles) + 1);
     seg_ptr_kernel<<<grid_for(size_t(nvalid) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
         tile_of.p, nvalid, plan->ntiles, plan->tile_cell_ptr.p);
-    plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne));
+    plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne) + 8);  // + slack: TMA copies 16-byte granules
     tile_cell_edges_kernel<<<grid_for(size_t(nvalid) * ne, block, ctx->sm_count), block, 0, ctx->stream>>>(
         tile_cells.p, nvalid, mesh->cell_faces[1].p, ne, plan->tile_cell_edges.p);
     fq_count_launch(ctx, 3);
@@ -985,9 +1064,12 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     off = (off + 15) / 16 * 16;
     plan->rec_off = uint32_t(off);
     off += recipe_bytes;
+    off = (off + 15) / 16 * 16;
+    plan->eid_off = uint32_t(off);
+    off += size_t(plan->cstride) * size_t(ne) * 4 + 32;  // staged edge ids of the next tile
     off = (off + 7) / 8 * 8;
     plan->mbar_off = uint32_t(off);
-    off += size_t(plan->nstages) * 16;  // full + empty barriers
+    off += size_t(plan->nstages) * 16 + 16;  // full + empty ring barriers, directory, edge ids
     plan->smem_bytes = off;
     if (plan->smem_bytes > cfg.smem_cta) return nullptr;
   }
@@ -1121,8 +1203,9 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   const uint32_t total_units = read_u32(ctx, plan->tile_stream_ptr.p + plan->ntiles);
   const uint32_t total_rec = read_u32(ctx, plan->tile_dir_ptr.p + plan->ntiles);
   plan->stream.alloc(size_t(total_units ? total_units : 1) * 64);
-  plan->rec_dir.alloc(total_rec ? total_rec : 1);
-  FQ_CUDA(cudaMemsetAsync(plan->stream.p, 0xFF, plan->stream.bytes(), ctx->stream));
+  plan->rec_dir.alloc(total_rec ? total_rec : 4);
+  FQ_CUDA(cudaMemsetAsync(plan->rec_dir.p, 0xFF, plan->rec_dir.bytes(), ctx->stream));  // padding entries
+  FQ_CUDA(cudaMemsetAsync(plan->stream.p, 0, plan->stream.bytes(), ctx->stream));  // padding lanes: dest 0, entries 0
   tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(
       la, plan->ntiles, 1, nullptr, nullptr, plan->tile_dir_ptr.p, plan->rec_dir.p);
   fq_count_launch(ctx);
@@ -1169,10 +1252,12 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   P.dir_off = plan.dir_off;
   P.chunk_off = plan.chunk_off;
   P.rec_off = plan.rec_off;
+  P.eid_off = plan.eid_off;
   P.mbar_off = plan.mbar_off;
   P.recipes = plan.recipes.p;
   P.recipe_bytes = int(plan.recipes.n);
-  P.check_classification = plan.blk[0].dropped_at_build ? 1 : 0;
+  P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
+  P.check_classification = (plan.blk[0].dropped_at_build && !P.debug) ? 1 : 0;
   P.changed = plan.changed.p;
   P.ticket = plan.ticket.p;
   for (int b = 0; b < plan.nblocks; ++b) {
