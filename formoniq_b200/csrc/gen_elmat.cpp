@@ -107,18 +107,24 @@ static void emit_function(const std::string& name, int n, const std::vector<Bloc
 // | 0x100 when negated, or -1 for an exact zero.
 struct CoreEntry {
   std::string name;
-  int n, k, ninputs, ndistinct, nouts;
+  int n, k, variant, ninputs, ndistinct, nouts;
 };
-static void emit_core(const std::string& name, int n, int k, CoreEntry& e) {
+// variant 0: the three masses M_{k-1}, M_k, M_{k+1} (every sandwich is a recipe);
+// variant 1: M_{k-1}, M_k and the sandwich dif_both(k+1) stored directly (HodgeBlocks: fewer gather terms)
+static std::vector<BlockSpec> core_blocks(int k, int variant) {
+  if (variant == 1) return {{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_DIF_BOTH, k + 1}};
+  return {{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_MASS, k + 1}};
+}
+static void emit_core(const std::string& name, int n, int k, int variant, CoreEntry& e) {
   TapeBuilder tb;
   std::vector<BlockLayout> layout;
-  const std::vector<BlockSpec> blocks{{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_MASS, k + 1}};
+  const std::vector<BlockSpec> blocks = core_blocks(k, variant);
   const Tape t = build_tape(n, blocks, &layout, &tb);
   int nouts = 0;
   for (const BlockLayout& l : layout) nouts += l.rows * l.cols;
   std::vector<int> map(size_t(nouts), -1);
   std::map<uint32_t, int> slot_of;
-  std::printf("// core n=%d k=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, t.ninputs, nouts,
+  std::printf("// core n=%d k=%d variant=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, variant, t.ninputs, nouts,
               t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
   std::printf("template <class Sink>\n__device__ __forceinline__ void %s(const double* __restrict__ s, Sink& sink) {\n",
               name.c_str());
@@ -172,6 +178,7 @@ static void emit_core(const std::string& name, int n, int k, CoreEntry& e) {
   e.name = name;
   e.n = n;
   e.k = k;
+  e.variant = variant;
   e.ninputs = t.ninputs;
   e.ndistinct = int(slot_of.size());
   e.nouts = nouts;
@@ -224,15 +231,17 @@ int main() {
   // cores: n <= 3, every grade
   std::vector<CoreEntry> cores;
   for (int n = 1; n <= 3; ++n)
-    for (int k = 0; k <= n; ++k) {
-      CoreEntry e{};
-      emit_core("fq_core_n" + std::to_string(n) + "_k" + std::to_string(k), n, k, e);
-      cores.push_back(e);
-    }
-  // X-macro list: (function, n, k, ninputs, ndistinct, nouts)
+    for (int k = 0; k <= n; ++k)
+      for (int variant = 0; variant < 2; ++variant) {
+        CoreEntry e{};
+        emit_core(std::string(variant ? "fq_hcore_n" : "fq_core_n") + std::to_string(n) + "_k" + std::to_string(k), n, k,
+                  variant, e);
+        cores.push_back(e);
+      }
+  // X-macro list: (function, n, k, variant, ninputs, ndistinct, nouts)
   std::printf("#define FQ_GEN_CORE_LIST(X) \\\n");
   for (const CoreEntry& e : cores)
-    std::printf("  X(%s, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.k, e.ninputs, e.ndistinct, e.nouts);
+    std::printf("  X(%s, %d, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.k, e.variant, e.ninputs, e.ndistinct, e.nouts);
   std::printf("\n");
   return 0;
 }

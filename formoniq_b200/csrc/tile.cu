@@ -14,20 +14,24 @@
 //     its non-zeros over the contributing (cell, slot) pairs in ascending cell
 //     order — the same order as the slab path, so values are bit-identical.
 //
-// Shared memory holds only the DISTINCT values of the masses M_{k-1}, M_k,
-// M_{k+1} of a cell (54 doubles for the 3-D k = 1 Hodge blocks instead of 112
-// element entries); the sandwiches d*M*D (operators.rs:201-211) are evaluated by
-// the gather through per-slot "recipes" — signed sums of mass entries in the
-// reference's k-ascending gemm order, exact because the incidence entries are
-// 0/+-1 (tape.hpp evaluates the same products symbolically).
+// Shared memory holds only the DISTINCT values a cell contributes: for
+// HodgeBlocks the masses M_{k-1}, M_k and the sandwich dif_both(k+1) (74 doubles
+// for 3-D k = 1 instead of 112 element entries).  dif_test = d*M_k
+// (operators.rs:201-211) is evaluated by the gather through per-slot "recipes" —
+// signed sums of mass entries in the reference's k-ascending gemm order, exact
+// because the incidence entries are 0/+-1 (tape.hpp evaluates the same products
+// symbolically).
 //
 // The cell-slot -> nnz map is laid out per tile as ONE contiguous byte stream
-// of warp-sized records {dest[32]; entry[L][32]} (non-zeros grouped by their
-// number of contributions L, so a warp runs L uniform iterations, lanes read
-// consecutive 2-byte entries, no per-nnz offsets are stored).  The stream is
-// pulled into a shared-memory ring by TMA bulk copies (cp.async.bulk +
-// mbarrier) a few chunks ahead of the consumers, so HBM sees long sequential
-// reads and no thread ever waits on a dependent global load.
+// of 2 KB chunks holding warp-sized records {header; dest[64]; entry[L][64]}
+// (non-zeros grouped by their number of contributions L, so a warp runs L
+// uniform iterations on two independent chains per lane, lanes read
+// consecutive 2-byte entries, no per-nnz offsets are stored).  Chunk c of a
+// tile belongs to warp c mod NW: every warp streams its own chunks through a
+// private double buffer filled by TMA bulk copies (cp.async.bulk + mbarrier),
+// prefetching across tile boundaries — no warp ever waits on another warp or
+// on a dependent global load during the gather, and HBM sees long sequential
+// reads.
 //
 // Reference path replaced: formoniq/src/galerkin.rs:138-188 (assemble_matrix)
 // + hodge.rs:62-72 (the four HodgeBlocks), numeric phase.
@@ -47,16 +51,20 @@ constexpr int kTileMaxBlocks = 4;
 // d >= 2 = position d - 2 of csr->values
 constexpr uint32_t kPadDest = 0u;
 constexpr uint32_t kNoDest = 1u;
-constexpr int kRecLanes = 64;               // non-zeros per record: two per lane (two independent chains)
-constexpr int kChunkBytes = 8192;           // TMA chunk of the tile stream; records never straddle a chunk
-constexpr int kMaxRecPerTile = 512;         // directory capacity in shared memory
-constexpr int kMaxChunksPerTile = 96;
-constexpr int kMaxLen = 255;                // contributions per non-zero (8 bits in the directory)
+constexpr int kChunkBytes = 2048;   // TMA granule of the tile stream; records never straddle a chunk
+constexpr int kChunkHdr = 16;       // u32 nrec + padding
+constexpr int kRecHdr = 16;         // u32 (L | block << 8 | wide << 16) + padding
+constexpr int kWideMaxLen = 13;     // 64-lane records: 16 + 64 * (4 + 2 L) <= 2032
+constexpr int kMaxLen = 29;         // 32-lane records: 16 + 32 * (4 + 2 L) <= 2032
+constexpr int kSlotsPerWarp = 2;    // private double buffer of every warp
+
+__host__ __device__ inline uint32_t rec_lanes(uint32_t L) { return L <= uint32_t(kWideMaxLen) ? 64u : 32u; }
+__host__ __device__ inline uint32_t rec_bytes(uint32_t L) { return uint32_t(kRecHdr) + rec_lanes(L) * (4u + 2u * L); }
 
 struct TileBlockDev {
   double* values;
-  int no, ni;      // recipe shape: outer x inner signed terms per slot
-  int recipe_off;  // byte offset of this block's recipes (nslots * no * ni codes)
+  int no, ni;      // recipe shape: outer x inner signed terms per slot (1 x 1: entries are pre-translated)
+  int recipe_off;  // offset (u16 units) of this block's recipes
   int slot_bits;
 };
 
@@ -66,15 +74,12 @@ struct TileParams {
   const double* lengths;
   uint32_t edge_lo;
   uint32_t ntiles;
-  const uint32_t* tile_dir_ptr;     // [ntiles+1] into rec_dir
-  const uint32_t* rec_dir;          // per record: block<<30 | L<<22 | offset/64 within the tile stream
-  const uint32_t* tile_stream_ptr;  // [ntiles+1] in 64-byte units
-  const unsigned char* stream;
+  const uint32_t* tile_chunk_ptr;   // [ntiles+1] chunk index of the tile's stream
+  const unsigned char* stream;      // chunks of kChunkBytes
   int cstride;                      // cells capacity of the shared slab
   int nblocks;
-  int nstages;                      // ring slots
-  uint32_t ring_off, dir_off, chunk_off, rec_off, eid_off, mbar_off;  // byte offsets in dynamic shared memory
-  const uint8_t* recipes;           // code = distinct slot | 0x80 negated; 0xFF = no term
+  uint32_t ring_off, rec_off, mbar_off;  // byte offsets in dynamic shared memory
+  const uint8_t* recipes;           // u16 codes: sign << 15 | distinct * cstride
   int recipe_bytes;
   int debug;                        // development knobs (FQ_TILE_DEBUG): 1 skip K1, 2 skip records, 4 skip stores
   int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
@@ -125,7 +130,7 @@ __device__ __forceinline__ double signed_load(const double* __restrict__ p, uint
   return __hiloint2double(__double2hiint(x) ^ int((code & 0x8000u) << 16), __double2loint(x));
 }
 
-// Value of one contribution: a recipe of NO x NI signed mass entries
+// Value of one contribution: a recipe of NO x NI signed stored entries
 //   v = (((x00 + x01) + ..) + ((x10 + x11) + ..)) + ..
 // (the k-ascending gemm order of operators.rs:201-211 with the +-1 incidence entries folded in).
 template <int NO, int NI>
@@ -153,14 +158,16 @@ __device__ __forceinline__ double recipe_value(uint32_t e, const double* __restr
   }
   return v;
 }
-// The two non-zeros of a lane (columns lane and lane + 32 of the record): left-to-right sums over L contributions.
+// The two non-zeros of a lane (columns lane and lane + 32 of a wide record; a narrow record runs the
+// second chain on the first column and discards it): left-to-right sums over L contributions.
 template <int NO, int NI>
-__device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent, uint32_t L, const double* __restrict__ slab,
+__device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent0, const uint16_t* __restrict__ ent1,
+                                              uint32_t stride, uint32_t L, const double* __restrict__ slab,
                                               const uint16_t* __restrict__ brec, uint32_t sb, uint32_t slot_mask, double& acc0,
                                               double& acc1, bool& any0, bool& any1) {
 #pragma unroll 1
   for (uint32_t j = 0; j < L; ++j) {
-    const uint32_t e0 = ent[j * kRecLanes], e1 = ent[j * kRecLanes + 32];
+    const uint32_t e0 = ent0[j * stride], e1 = ent1[j * stride];
     const double v0 = recipe_value<NO, NI>(e0, slab, brec, sb, slot_mask);
     const double v1 = recipe_value<NO, NI>(e1, slab, brec, sb, slot_mask);
     any0 = any0 || (v0 != 0.0);
@@ -169,14 +176,14 @@ __device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent, 
     acc1 = __dadd_rn(acc1, v1);
   }
 }
-// mass blocks: the stream entries are pre-translated to sign | slab offset
-__device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict__ ent, uint32_t L,
-                                                     const double* __restrict__ slab, double& acc0, double& acc1, bool& any0,
-                                                     bool& any1) {
+// blocks stored directly: the stream entries are pre-translated to sign | slab offset
+__device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict__ ent0, const uint16_t* __restrict__ ent1,
+                                                     uint32_t stride, uint32_t L, const double* __restrict__ slab,
+                                                     double& acc0, double& acc1, bool& any0, bool& any1) {
 #pragma unroll 1
   for (uint32_t j = 0; j < L; ++j) {
-    const double x0 = signed_load(slab, ent[j * kRecLanes]);
-    const double x1 = signed_load(slab, ent[j * kRecLanes + 32]);
+    const double x0 = signed_load(slab, ent0[j * stride]);
+    const double x1 = signed_load(slab, ent1[j * stride]);
     any0 = any0 || (x0 != 0.0);
     any1 = any1 || (x1 != 0.0);
     acc0 = __dadd_rn(acc0, x0);
@@ -184,148 +191,107 @@ __device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict_
   }
 }
 
-template <class Fn, int NE, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
+template <class Fn, int NE, int NT>
+__global__ void __launch_bounds__(NT, 1) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* slab = reinterpret_cast<double*>(smem_raw);
-  unsigned char* ring = smem_raw + P.ring_off;
-  uint32_t* dir = reinterpret_cast<uint32_t*>(smem_raw + P.dir_off);
-  uint32_t* chunk_first = reinterpret_cast<uint32_t*>(smem_raw + P.chunk_off);
-  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
-  unsigned char* eid_stage = smem_raw + P.eid_off;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
-  __shared__ uint32_t s_hdr[3][8];
-  __shared__ uint32_t s_nrec;
   constexpr int NW = NT / 32;
   constexpr int NEE = NE > 0 ? NE : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int S = P.nstages;
-  uint64_t* empty = full + S;
-  uint64_t* dirbar = empty + S;
-  uint64_t* eidbar = dirbar + 1;
+  unsigned char* myring = smem_raw + P.ring_off + size_t(warp) * kSlotsPerWarp * kChunkBytes;  // this warp's double buffer
+  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
+  uint64_t* mybar = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off) + warp * kSlotsPerWarp;
+  __shared__ uint32_t s_hdr[3][8];
   auto fetch_header = [&](uint32_t* h) {  // thread 0: next tile from the dynamic scheduler
     const uint32_t t = atomicAdd(P.ticket, 1u);
     h[0] = t;
     if (t < P.ntiles) {
       h[1] = __ldg(P.tile_cell_ptr + t);
       h[2] = __ldg(P.tile_cell_ptr + t + 1);
-      h[3] = __ldg(P.tile_dir_ptr + t);
-      h[4] = __ldg(P.tile_dir_ptr + t + 1);
-      h[5] = __ldg(P.tile_stream_ptr + t);
-      h[6] = __ldg(P.tile_stream_ptr + t + 1);
+      h[3] = __ldg(P.tile_chunk_ptr + t);
+      h[4] = __ldg(P.tile_chunk_ptr + t + 1);
     }
   };
-  // thread 0: TMA of a tile's pre-gathered edge ids into the staging buffer (16-byte aligned window)
-  auto issue_eids = [&](const uint32_t* h) {
-    if (h[0] >= P.ntiles) return;
-    const size_t b0 = size_t(h[1]) * NE * 4, b1 = size_t(h[2]) * NE * 4;
-    const size_t a0 = b0 & ~size_t(15);
-    const uint32_t bytes = uint32_t(((b1 - a0) + 15) & ~size_t(15));
-    mbar_expect_tx(eidbar, bytes);
-    tma_load_1d(eid_stage, reinterpret_cast<const unsigned char*>(P.tile_cell_edges) + a0, bytes, eidbar);
-  };
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NW);
-    }
-    mbar_init(dirbar, 1);
-    mbar_init(eidbar, 1);
+  if (lane == 0) {
+    for (int s = 0; s < kSlotsPerWarp; ++s) mbar_init(&mybar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == 0) {
     fetch_header(s_hdr[0]);
     fetch_header(s_hdr[1]);
-    issue_eids(s_hdr[0]);
   }
   for (int i = tid; i < P.recipe_bytes / 2; i += NT) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
-  uint32_t g = 0;          // chunks this CTA has pushed through the ring so far (slot = g % S, parity = (g / S) & 1)
-  double s_next[NEE];      // this thread's cell of the NEXT tile: edge lengths, loaded while the current tile is gathered
-  bool have_next = false;
-  uint32_t dir_uses = 0;   // completed phases of dirbar (tiles with a non-empty directory)
+  // this warp's chunk stream: chunks issued / consumed so far (slot = n & 1, parity = (n >> 1) & 1) and the
+  // issue cursor (tile iteration it is on, next chunk, end of that tile's chunks); runs ahead across tiles
+  uint32_t n_issued = 0, n_consumed = 0;
+  uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
   for (uint32_t it = 0;; ++it) {
     __syncthreads();  // previous tile fully consumed, this tile's header visible
     const uint32_t* hdr = s_hdr[it % 3];
     const uint32_t t = hdr[0];
     if (t >= P.ntiles) break;
-    const uint32_t nc = hdr[2] - hdr[1];
-    const uint32_t d0 = hdr[3], ndir = hdr[4] - hdr[3];
-    const uint32_t sbytes = (hdr[6] - hdr[5]) * 64u;
-    const unsigned char* sbase = P.stream + size_t(hdr[5]) * 64u;
-    const uint32_t nchunks = (sbytes + kChunkBytes - 1) / kChunkBytes;
-    // ---- the first ring slots and the directory start filling now and land while K1 runs
-    if (tid == 0) {
-      uint32_t sl = g % S;
-      for (uint32_t k = 0; k < nchunks && k < uint32_t(S); ++k) {
-        const uint32_t bytes = min(uint32_t(kChunkBytes), sbytes - k * kChunkBytes);
-        mbar_expect_tx(&full[sl], bytes);
-        tma_load_1d(ring + sl * kChunkBytes, sbase + size_t(k) * kChunkBytes, bytes, &full[sl]);
-        if (++sl == uint32_t(S)) sl = 0;
-      }
-      if (ndir) {
-        mbar_expect_tx(dirbar, ndir * 4u);
-        tma_load_1d(dir, P.rec_dir + d0, ndir * 4u, dirbar);
-      }
-    }
-    // ---- K1: element masses of the tile's cells -> shared slab [distinct][cell]
-    if (!have_next) {  // first tile of this CTA: no prefetched lengths yet
-      mbar_wait(eidbar, it & 1u);
-      if (uint32_t(tid) < nc) {
-        const uint32_t* ce = reinterpret_cast<const uint32_t*>(eid_stage + ((size_t(hdr[1]) * NE * 4) & 15)) + size_t(tid) * NE;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) s_next[e] = __ldg(P.lengths + (ce[e] - P.edge_lo));
-      }
-    }
-    if (uint32_t(tid) < nc && ndir != 0 && !(P.debug & 1)) {
-      TileSink sink{slab + tid, P.cstride};
-      fn(s_next, sink);
-    }
-    have_next = false;
-    __syncthreads();
-    // the header after next is fetched, and the next tile's edge ids are staged, while this tile is gathered
-    if (tid == 0) {
-      issue_eids(s_hdr[(it + 1) % 3]);
-      fetch_header(s_hdr[(it + 2) % 3]);
-    }
-    // first record of every chunk (records are laid out in order and never straddle a chunk);
-    // the directory is padded with 0xFFFFFFFF to a multiple of four entries
-    if (ndir) mbar_wait(dirbar, dir_uses++ & 1u);
-    for (uint32_t i = tid; i < ndir; i += NT) {
-      const uint32_t di = dir[i];
-      if (di == 0xFFFFFFFFu) continue;
-      const uint32_t ck = ((di & 0x3FFFFFu) * 64u) / kChunkBytes;
-      if (i == 0 || ck != ((dir[i - 1] & 0x3FFFFFu) * 64u) / kChunkBytes) chunk_first[ck] = i;
-      if (i + 1 == ndir || dir[i + 1] == 0xFFFFFFFFu) s_nrec = i + 1;
-    }
-    __syncthreads();
-    if (tid == 0) chunk_first[nchunks] = s_nrec;
+    const uint32_t cbase = hdr[1], nc = hdr[2] - hdr[1];
+    const uint32_t c0 = hdr[3], c1 = hdr[4];
     const uint32_t* hnext = s_hdr[(it + 1) % 3];
-    // lengths of this thread's cell of the next tile (their latency is covered by the gather below)
-    auto prefetch_next = [&]() {
-      if (hnext[0] < P.ntiles) {
-        mbar_wait(eidbar, (it + 1) & 1u);
-        if (uint32_t(tid) < hnext[2] - hnext[1]) {
-          const uint32_t* ce =
-              reinterpret_cast<const uint32_t*>(eid_stage + ((size_t(hnext[1]) * NE * 4) & 15)) + size_t(tid) * NE;
-#pragma unroll
-          for (int e = 0; e < NE; ++e) s_next[e] = __ldg(P.lengths + (ce[e] - P.edge_lo));
+    auto issue_more = [&]() {  // keep this warp's double buffer full, crossing into the next tile when this one is done
+      while (n_issued - n_consumed < uint32_t(kSlotsPerWarp)) {
+        if (cur_chunk >= cur_end) {
+          if (cur_it == it && hnext[0] < P.ntiles) {
+            cur_it = it + 1;
+            cur_chunk = hnext[3] + warp;
+            cur_end = hnext[4];
+            if (cur_chunk >= cur_end) break;
+          } else {
+            break;
+          }
         }
-        have_next = true;
+        if (lane == 0) {
+          uint64_t* bar = &mybar[n_issued & 1u];
+          mbar_expect_tx(bar, kChunkBytes);
+          tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
+        }
+        cur_chunk += NW;
+        ++n_issued;
       }
     };
-    if (nchunks < 2) prefetch_next();
+    if (cur_it != it) {  // the cursor did not run ahead into this tile: start here
+      cur_it = it;
+      cur_chunk = c0 + warp;
+      cur_end = c1;
+    }
+    issue_more();  // lands while K1 runs
+    // ---- K1: element values of the tile's cells -> shared slab [distinct][cell]
+    if (c1 > c0 && !(P.debug & 1)) {
+      for (uint32_t c = tid; c < nc; c += NT) {
+        const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
+        uint32_t eid[NEE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
+        double s[NEE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
+        TileSink sink{slab + c, P.cstride};
+        fn(s, sink);
+      }
+    }
     __syncthreads();
-    // ---- K3: one warp per record, two owned structural non-zeros per lane
-    uint32_t slot = g % S, parity = (g / S) & 1u;
-    for (uint32_t k = 0; k < nchunks; ++k) {
-      mbar_wait(&full[slot], parity);
-      const unsigned char* chunk = ring + slot * kChunkBytes - k * kChunkBytes;
-      const uint32_t r1 = chunk_first[k + 1];
-      for (uint32_t r = chunk_first[k] + warp; r < r1 && !(P.debug & 2); r += NW) {
-        const uint32_t d = dir[r];
-        const uint32_t b = d >> 30, L = (d >> 22) & 0xFFu;
-        const unsigned char* rp = chunk + (d & 0x3FFFFFu) * 64u;
-        const uint32_t dest0 = reinterpret_cast<const uint32_t*>(rp)[lane];
-        const uint32_t dest1 = reinterpret_cast<const uint32_t*>(rp)[lane + 32];
-        const uint16_t* __restrict__ ent = reinterpret_cast<const uint16_t*>(rp + 4 * kRecLanes) + lane;
+    if (tid == 0) fetch_header(s_hdr[(it + 2) % 3]);  // two tiles ahead: its latency hides behind this gather
+    // ---- K3: this warp's chunks; one record at a time, two owned structural non-zeros per lane
+    for (uint32_t c = c0 + warp; c < c1; c += NW) {
+      mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
+      const unsigned char* chunk = myring + (n_consumed & 1u) * kChunkBytes;
+      const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
+      const unsigned char* rp = chunk + kChunkHdr;
+      for (uint32_t r = 0; r < nrec; ++r) {
+        const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
+        const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, wide = (h >> 16) & 1u;
+        const uint32_t stride = wide ? 64u : 32u;
+        const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
+        const uint32_t dest0 = destp[lane];
+        const uint32_t dest1 = wide ? destp[lane + 32] : kPadDest;
+        const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + lane;
+        const uint16_t* __restrict__ ent1 = ent0 + (wide ? 32 : 0);
+        rp += kRecHdr + stride * (4u + 2u * L);
         const TileBlockDev& B = P.blk[b];
         const uint16_t* __restrict__ brec = rec + B.recipe_off;
         const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
@@ -333,13 +299,13 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
         bool any0 = false, any1 = false;
         switch (B.no * 8 + B.ni) {
           case 0: break;  // zero space: every contribution is an exact zero
-          case 1 * 8 + 1: gather_record_direct(ent, L, slab, acc0, acc1, any0, any1); break;
-          case 1 * 8 + 2: gather_record<1, 2>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 1 * 8 + 3: gather_record<1, 3>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 1 * 8 + 4: gather_record<1, 4>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 2 * 8 + 2: gather_record<2, 2>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 3 * 8 + 3: gather_record<3, 3>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          default: gather_record<4, 4>(ent, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 1: gather_record_direct(ent0, ent1, stride, L, slab, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 2: gather_record<1, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 3: gather_record<1, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 1 * 8 + 4: gather_record<1, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 2 * 8 + 2: gather_record<2, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          case 3 * 8 + 3: gather_record<3, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+          default: gather_record<4, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
         }
         // padding lanes carry zero entries (they read slab[0]) and never store
         if (P.check_classification && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) ||
@@ -349,23 +315,10 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
         if (dest0 > kNoDest) B.values[dest0 - 2u] = acc0;
         if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
       }
-      // this warp is done with the slot; the chunk's refill is issued by one rotating warp
-      // once every warp has left it (no CTA-wide barrier on the stream)
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[slot])) : "memory");
-      if (k + S < nchunks && warp == int(k % NW)) {
-        mbar_wait(&empty[slot], parity);
-        if (lane == 0) {
-          const uint32_t kk = k + S;
-          const uint32_t bytes = min(uint32_t(kChunkBytes), sbytes - kk * kChunkBytes);
-          mbar_expect_tx(&full[slot], bytes);
-          tma_load_1d(ring + slot * kChunkBytes, sbase + size_t(kk) * kChunkBytes, bytes, &full[slot]);
-        }
-      }
-      if (++slot == uint32_t(S)) slot = 0, parity ^= 1u;
-      if (k == 0 && nchunks >= 2) prefetch_next();
+      __syncwarp();  // every lane is done reading the slot before it is refilled
+      ++n_consumed;
+      issue_more();
     }
-    g += nchunks;
   }
 }
 
@@ -382,10 +335,11 @@ struct TilePlan {
   int dim = 0, core_k = 0, ndistinct = 0;
   uint32_t ntiles = 0;
   int cstride = 0;
-  int nthreads = 512, nstages = 3;
+  int nthreads = 512;
   size_t smem_bytes = 0;
-  uint32_t ring_off = 0, dir_off = 0, chunk_off = 0, rec_off = 0, eid_off = 0, mbar_off = 0;
-  DevBuf<uint32_t> tile_cell_ptr, tile_cell_edges, tile_dir_ptr, rec_dir, tile_stream_ptr;
+  uint32_t ring_off = 0, rec_off = 0, mbar_off = 0;
+  int recipe_bytes = 0;
+  DevBuf<uint32_t> tile_cell_ptr, tile_cell_edges, tile_chunk_ptr;
   DevBuf<unsigned char> stream;
   DevBuf<uint8_t> recipes;
   DevBuf<int> changed;
@@ -396,7 +350,7 @@ struct TilePlan {
   void (*launch)(fq_ctx*, const TilePlan&, const TileParams&) = nullptr;
 };
 
-#define FQ_DECLARE_CORE(fn, n, k, nin, nd, nout)                                               \
+#define FQ_DECLARE_CORE(fn, n, k, variant, nin, nd, nout)                                      \
   struct Core_##fn {                                                                           \
     static constexpr int kDistinct = nd;                                                       \
     template <class S>                                                                         \
@@ -411,61 +365,79 @@ template <class Fn, int NE, int NT>
 static void launch_tile_nt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static bool attr_set = false;
   if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024 - 256));
     attr_set = true;
   }
-  tile_assemble_kernel<Fn, NE, NT, 1><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  tile_assemble_kernel<Fn, NE, NT><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  switch (plan.nthreads) {
-    case 1024: launch_tile_nt<Fn, NE, 1024>(ctx, plan, params); break;
-    case 768: launch_tile_nt<Fn, NE, 768>(ctx, plan, params); break;
-    default: launch_tile_nt<Fn, NE, 512>(ctx, plan, params); break;
-  }
+  if (plan.nthreads == 768)
+    launch_tile_nt<Fn, NE, 768>(ctx, plan, params);
+  else
+    launch_tile_nt<Fn, NE, 512>(ctx, plan, params);
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
 }
 
+// variant 0: stores M_{k-1}, M_k, M_{k+1};  variant 1: stores M_{k-1}, M_k, dif_both(k+1)
 struct CoreEntryRt {
-  int n, k, nin, ndistinct, nouts;
+  int n, k, variant, nin, ndistinct, nouts;
   const short* map;
   void (*launch)(fq_ctx*, const TilePlan&, const TileParams&);
 };
-#define FQ_CORE_ENTRY(fn, n, k, nin, nd, nout) CoreEntryRt{n, k, nin, nd, nout, fn##_map, &launch_tile<Core_##fn, nin>},
+#define FQ_CORE_ENTRY(fn, n, k, variant, nin, nd, nout) \
+  CoreEntryRt{n, k, variant, nin, nd, nout, fn##_map, &launch_tile<Core_##fn, nin>},
 static const CoreEntryRt g_cores[] = {FQ_GEN_CORE_LIST(FQ_CORE_ENTRY)};
 #undef FQ_CORE_ENTRY
 
-static const CoreEntryRt* find_core(int n, int k) {
+static const CoreEntryRt* find_core(int n, int k, int variant) {
   for (const CoreEntryRt& e : g_cores)
-    if (e.n == n && e.k == k) return &e;
+    if (e.n == n && e.k == k && e.variant == variant) return &e;
   return nullptr;
+}
+// offset of the stored block (kind, g) inside the core's map, or -1 when the core does not store it
+static int stored_offset(const CoreEntryRt& core, int kind, int g) {
+  const BlockSpec stored[3] = {{KIND_MASS, core.k - 1},
+                               {KIND_MASS, core.k},
+                               {core.variant == 1 ? int(KIND_DIF_BOTH) : int(KIND_MASS), core.k + 1}};
+  int off = 0;
+  for (const BlockSpec& b : stored) {
+    int tg, rg;
+    kind_grades(b.kind, b.grade, tg, rg);
+    if (b.kind == kind && b.grade == g) return off;
+    off += nlocal(core.n, tg) * nlocal(core.n, rg);
+  }
+  return -1;
 }
 
 // ---- launch configuration (tunable through the environment for sweeps) -------
 struct TileConfig {
-  int nthreads, ctas_per_sm, nstages;
-  size_t smem_cta;  // dynamic shared memory budget of one CTA
+  int nthreads;
+  size_t smem_cta;  // dynamic shared memory budget of the CTA (one CTA per SM)
 };
 static TileConfig tile_config() {
-  TileConfig c{512, 1, 3, size_t(227) * 1024 - 256};
+  TileConfig c{512, size_t(227) * 1024 - 256};
   if (const char* e = std::getenv("FQ_TILE_THREADS")) {
     const int nt = std::atoi(e);
-    if (nt == 512 || nt == 768 || nt == 1024) c.nthreads = nt;
+    if (nt == 512 || nt == 768) c.nthreads = nt;
   }
-  if (const char* e = std::getenv("FQ_TILE_STAGES")) c.nstages = std::max(1, std::min(16, std::atoi(e)));
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
-  return size_t(c.nstages) * kChunkBytes + size_t(kMaxRecPerTile) * 4 + size_t(kMaxChunksPerTile + 1) * 4 + 2048 /*recipes*/ +
-         256 /*mbarriers*/ + 512 /*alignment slack*/;
+  const size_t nwarps = size_t(c.nthreads) / 32;
+  return nwarps * kSlotsPerWarp * kChunkBytes /*ring*/ + 2048 /*recipes*/ + nwarps * kSlotsPerWarp * 8 /*mbarriers*/ +
+         512 /*alignment slack*/;
 }
 int tile_cells_capacity(int ndistinct) {
   const TileConfig c = tile_config();
-  // per cell: its distinct mass values + 6 staged edge ids (dim <= 3)
-  int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double) + 24));
-  return std::min(cap, c.nthreads);  // K1 is one cell per thread
+  const int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double)));
+  return std::min(cap, 1023);
+}
+static int tile_core_variant() {
+  const char* e = std::getenv("FQ_TILE_CORE");
+  return (e && e[0] == 's') ? 0 : 1;
 }
 
 // Recipes of one block over the distinct values of core(n, kc).
@@ -477,10 +449,25 @@ static bool build_recipes(int n, int kc, const CoreEntryRt& core, int kind, int 
   kind_grades(kind, g, tg, rg);
   const int rows = nlocal(n, tg), cols = nlocal(n, rg);
   const int nslots = rows * cols;
-  if (g < kc - 1 || g > kc + 1) return false;
-  // offset of mass g inside the core map
-  int off = 0;
-  for (int gg = kc - 1; gg < g; ++gg) off += nlocal(n, gg) * nlocal(n, gg);
+  (void)kc;
+  if (g < 0 || g > n || nslots == 0) {  // zero space: every entry is an exact zero
+    no = 0;
+    ni = 0;
+    codes.clear();
+    return true;
+  }
+  if (core.ndistinct > 127) return false;
+  auto direct_code = [&](int m) -> int { return m < 0 ? 0xFF : ((m & 0xFF) | ((m & 0x100) ? 0x80 : 0)); };
+  const int doff = stored_offset(core, kind, g);
+  if (doff >= 0) {  // the block itself is stored: every slot is one signed stored value
+    no = 1, ni = 1;
+    codes.resize(size_t(nslots));
+    for (int sl = 0; sl < nslots; ++sl) codes[size_t(sl)] = uint8_t(direct_code(core.map[doff + sl]));
+    return true;
+  }
+  // otherwise a sandwich of the stored mass of grade g
+  const int off = stored_offset(core, KIND_MASS, g);
+  if (off < 0 || kind == KIND_MASS) return false;
   const int nd = nlocal(n, g);
   auto mcode = [&](int i, int j, int sign) -> int {  // signed mass entry -> code or -1 (zero)
     const int m = core.map[off + i * nd + j];
@@ -489,13 +476,6 @@ static bool build_recipes(int n, int kc, const CoreEntryRt& core, int kind, int 
     const bool neg = ((m & 0x100) != 0) != (sign < 0);
     return slot | (neg ? 0x80 : 0);
   };
-  if (g < 0 || g > n || nslots == 0) {  // zero space: every entry is an exact zero
-    no = 0;
-    ni = 0;
-    codes.clear();
-    return true;
-  }
-  if (core.ndistinct > 127) return false;
   // boundary operator rows -> list of (coface index, sign), ascending
   struct Inc {
     int idx, sign;
@@ -631,7 +611,7 @@ __global__ void nnz_key_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nr
     for (uint32_t q = row_ptr[r]; q < row_ptr[r + 1]; ++q) {
       const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
       uint32_t L = p1 - p0;
-      if (L > uint32_t(kMaxLen)) {
+      if (L > uint32_t(kMaxLen)) {  // does not fit a 32-lane record of one chunk: the slab path handles this mesh
         atomicExch(err, 4);
         L = kMaxLen;
       }
@@ -662,10 +642,17 @@ __global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t
       run_len_code[r] = uint32_t(key[i] >> 16) & 0xFFu;
     }
 }
-__global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, uint32_t nruns, uint32_t* __restrict__ nrec) {
+__global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
+                                uint32_t* __restrict__ nrec) {
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nruns; r += stride)
-    nrec[r] = r < nruns ? (run_start[r + 1] - run_start[r] + uint32_t(kRecLanes) - 1u) / uint32_t(kRecLanes) : 0u;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nruns; r += stride) {
+    if (r == nruns) {
+      nrec[r] = 0u;
+      continue;
+    }
+    const uint32_t lanes = rec_lanes(run_len_code[r]);
+    nrec[r] = (run_start[r + 1] - run_start[r] + lanes - 1u) / lanes;
+  }
 }
 __global__ void rec_len_kernel(const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
                                uint8_t* __restrict__ rec_len) {
@@ -682,64 +669,75 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ idx, uint32_t n, 
 struct TileLayoutBlock {
   const uint32_t* rec_tile_ptr;  // [ntiles+1] first record of every tile
   const uint8_t* rec_len;        // [nrec]
-  uint32_t* rec_rel;             // [nrec] out: offset within the tile stream, 64-byte units
+  uint32_t* rec_rel;             // [nrec] out: byte offset / 16 of the record within the tile's stream
 };
 struct TileLayoutArgs {
   TileLayoutBlock blk[kTileMaxBlocks];
   int nblocks;
 };
-// One thread per tile lays its records out (records never straddle a chunk).
-// pass 0: sizes (tile_units, tile_nrec);  pass 1: directory entries.
-__global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, uint32_t* __restrict__ tile_units,
-                                   uint32_t* __restrict__ tile_nrec, const uint32_t* __restrict__ tile_dir_ptr,
-                                   uint32_t* __restrict__ rec_dir) {
+// One thread per tile packs its records into chunks (a record never straddles a chunk).
+// pass 0: chunk count of the tile;  pass 1: record offsets, record and chunk headers written into the stream.
+__global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, uint32_t* __restrict__ tile_nchunks,
+                                   const uint32_t* __restrict__ tile_chunk_ptr, unsigned char* __restrict__ stream) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
-    uint32_t off = 0, nrec = 0;
-    const uint32_t dbase = pass ? tile_dir_ptr[t] : 0u;
+    uint32_t off = 0;          // byte offset within the tile's stream; 0 = no chunk opened yet
+    uint32_t in_chunk = 0;     // records in the open chunk
+    unsigned char* base = pass ? stream + size_t(tile_chunk_ptr[t]) * kChunkBytes : nullptr;
     for (int b = 0; b < A.nblocks; ++b) {
       const TileLayoutBlock& B = A.blk[b];
       for (uint32_t k = B.rec_tile_ptr[t]; k < B.rec_tile_ptr[t + 1]; ++k) {
         const uint32_t L = B.rec_len[k];
-        const uint32_t size = uint32_t(kRecLanes) * (4u + 2u * L);
-        if (off / kChunkBytes != (off + size - 1) / kChunkBytes) off = (off / kChunkBytes + 1) * kChunkBytes;
+        const uint32_t size = rec_bytes(L);
+        const uint32_t chunk = off / kChunkBytes;
+        if (off % kChunkBytes == 0 || off + size > (chunk + 1) * kChunkBytes) {  // open a new chunk
+          if (off % kChunkBytes != 0) {
+            if (pass) *reinterpret_cast<uint32_t*>(base + size_t(chunk) * kChunkBytes) = in_chunk;
+            off = (chunk + 1) * kChunkBytes;
+          }
+          off += kChunkHdr;
+          in_chunk = 0;
+        }
         if (pass) {
-          B.rec_rel[k] = off / 64u;
-          rec_dir[dbase + nrec] = (uint32_t(b) << 30) | (L << 22) | (off / 64u);
+          B.rec_rel[k] = off / 16u;
+          *reinterpret_cast<uint32_t*>(base + off) = L | (uint32_t(b) << 8) | ((rec_lanes(L) == 64u ? 1u : 0u) << 16);
         }
         off += size;
-        ++nrec;
+        ++in_chunk;
       }
     }
-    if (!pass) {
-      tile_units[t] = off / 64u;
-      tile_nrec[t] = (nrec + 3u) & ~3u;  // the directory of a tile is TMA-copied: 16-byte granules
+    if (off % kChunkBytes != 0) {
+      if (pass) *reinterpret_cast<uint32_t*>(base + size_t(off / kChunkBytes) * kChunkBytes) = in_chunk;
+      off = (off / kChunkBytes + 1) * kChunkBytes;
     }
+    if (!pass) tile_nchunks[t] = off / kChunkBytes;
   }
 }
 // One thread per (sorted) non-zero: its lane of its record.
 __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n, const uint32_t* __restrict__ run_scan,
                                    const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_tile,
-                                   const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ rec_rel,
-                                   const uint32_t* __restrict__ tile_stream_ptr, const uint32_t* __restrict__ contrib_ptr,
-                                   const uint32_t* __restrict__ contrib_src, uint32_t T, int slot_bits,
-                                   const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
-                                   const uint8_t* __restrict__ keep, const uint32_t* __restrict__ pos, int drop,
-                                   const uint16_t* __restrict__ direct_map /*mass blocks: slot -> sign | slab offset*/,
+                                   const uint32_t* __restrict__ run_len_code, const uint32_t* __restrict__ rec_base,
+                                   const uint32_t* __restrict__ rec_rel, const uint32_t* __restrict__ tile_chunk_ptr,
+                                   const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
+                                   int slot_bits, const uint32_t* __restrict__ tile_cell_ptr,
+                                   const uint32_t* __restrict__ tile_cells, const uint8_t* __restrict__ keep,
+                                   const uint32_t* __restrict__ pos, int drop,
+                                   const uint16_t* __restrict__ direct_map /*stored blocks: slot -> sign | slab offset*/,
                                    unsigned char* __restrict__ stream, int* __restrict__ err) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t q = perm[i];
     const uint32_t r = run_scan[i] - 1;
     const uint32_t idx = i - run_start[r];
-    const uint32_t k = rec_base[r] + idx / uint32_t(kRecLanes), lane = idx % uint32_t(kRecLanes);
+    const uint32_t lanes = rec_lanes(run_len_code[r]);
+    const uint32_t k = rec_base[r] + idx / lanes, lane = idx % lanes;
     const uint32_t t = run_tile[r];
-    unsigned char* rp = stream + (size_t(tile_stream_ptr[t]) + rec_rel[k]) * 64u;
+    unsigned char* rp = stream + size_t(tile_chunk_ptr[t]) * kChunkBytes + size_t(rec_rel[k]) * 16u + kRecHdr;
     reinterpret_cast<uint32_t*>(rp)[lane] = drop ? (keep[q] ? pos[q] + 2u : kNoDest) : q + 2u;
-    uint16_t* ent = reinterpret_cast<uint16_t*>(rp + 4 * kRecLanes) + lane;
+    uint16_t* ent = reinterpret_cast<uint16_t*>(rp + 4u * lanes) + lane;
     const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
     const uint32_t cb = tile_cell_ptr[t], ce = tile_cell_ptr[t + 1];
-    for (uint32_t p = p0; p < p1; ++p) {
+    for (uint32_t p = p0; p < p1 && p - p0 < uint32_t(kMaxLen); ++p) {
       const uint32_t src = contrib_src[p];
       const uint32_t cell = src / T, slot = src - cell * T;
       uint32_t lo = cb, hi = ce;  // first index with tile_cells[idx] >= cell
@@ -758,10 +756,10 @@ __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n
       if (direct_map) {
         const uint32_t code = direct_map[slot];
         if ((code & 0x7FFFu) + local > 0x7FFFu) atomicExch(err, 3);
-        ent[(p - p0) * uint32_t(kRecLanes)] = uint16_t((code & 0x8000u) | ((code & 0x7FFFu) + local));
+        ent[(p - p0) * lanes] = uint16_t((code & 0x8000u) | ((code & 0x7FFFu) + local));
       } else {
         if ((local << slot_bits) > 0xFFFFu) atomicExch(err, 3);
-        ent[(p - p0) * uint32_t(kRecLanes)] = uint16_t((local << slot_bits) | slot);
+        ent[(p - p0) * lanes] = uint16_t((local << slot_bits) | slot);
       }
     }
   }
@@ -802,13 +800,12 @@ static void inclusive_scan_u32(fq_ctx* ctx, const uint32_t* in, uint32_t* out, s
 }
 
 // Closed-form vertex bricks on a Kuhn grid.
-int tile_cells_capacity(int ndistinct);
-
+// Closed-form vertex bricks on a Kuhn grid.
 void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held) {
   if (dim > 3 || std::getenv("FQ_NO_TILE")) return;
   int max_distinct = 1;
   for (const CoreEntryRt& e : g_cores)
-    if (e.n == dim) max_distinct = std::max(max_distinct, e.ndistinct);
+    if (e.n == dim && (tile_core_variant() == 1 || e.variant == 0)) max_distinct = std::max(max_distinct, e.ndistinct);
   const int cells_capacity = tile_cells_capacity(max_distinct);
   // brick[a] owned vertices per axis; a tile needs the cells of prod(brick[a]+1) boxes
   const int ncelltypes = int(fact(dim));
@@ -876,7 +873,7 @@ void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh, const uint64_t* cell_verts
   if (dim > 3 || std::getenv("FQ_NO_TILE") || !cell_verts) return;
   int max_distinct = 1;
   for (const CoreEntryRt& e : g_cores)
-    if (e.n == dim) max_distinct = std::max(max_distinct, e.ndistinct);
+    if (e.n == dim && (tile_core_variant() == 1 || e.variant == 0)) max_distinct = std::max(max_distinct, e.ndistinct);
   const uint32_t capacity = uint32_t(tile_cells_capacity(max_distinct));
   const size_t nv = size_t(dim) + 1, ncells = mesh->ncells, V = mesh->nsimplices[0];
   if (V == 0 || ncells == 0 || V >= (size_t(1) << 32)) return;
@@ -949,6 +946,30 @@ struct BlockBuild {
   uint32_t nruns = 0, nrec = 0;
 };
 
+// Picks the core (grade, variant) that can serve every block with the fewest gather terms.
+static const CoreEntryRt* choose_core(int dim, fq_csr* const* csrs, int nblocks) {
+  const int pref = tile_core_variant();
+  const CoreEntryRt* best = nullptr;
+  long best_score = 0;
+  for (const CoreEntryRt& core : g_cores) {
+    if (core.n != dim) continue;
+    if (pref == 0 && core.variant != 0) continue;
+    long score = 0;
+    bool ok = true;
+    for (int b = 0; ok && b < nblocks; ++b) {
+      int no, ni;
+      std::vector<uint8_t> codes;
+      ok = build_recipes(dim, core.k, core, csrs[b]->kind, csrs[b]->grade, no, ni, codes);
+      for (uint8_t c : codes) ok = ok && c != 0xFF;
+      score += long(no) * ni * 1000;
+    }
+    if (!ok) continue;
+    score += core.ndistinct;
+    if (!best || score < best_score) best = &core, best_score = score;
+  }
+  return best;
+}
+
 // Builds the tile plan for the fused blocks `csrs` (their structural phase and,
 // when dropping, their cached classification keep/pos must be valid).
 // Returns nullptr when the tile path does not apply (falls back to the slab path).
@@ -958,19 +979,11 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   if (!mesh->vertex_tile.p || mesh->ntiles == 0 || !mesh->cell_faces[0].p) return nullptr;
   const int dim = mesh->dim;
   if (dim > 3) return nullptr;
-  // core grade: the middle grade of the block set (hodge_blocks(k) -> k)
-  int gmin = 1 << 30, gmax = -(1 << 30);
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = 0; b < nblocks; ++b)
     if (csrs[b]->kind == KIND_LUMPED) return nullptr;
-    gmin = std::min(gmin, csrs[b]->grade);
-    gmax = std::max(gmax, csrs[b]->grade);
-  }
-  if (gmax - gmin > 2) return nullptr;
-  int kc = (gmax - gmin == 2) ? gmin + 1 : (gmax - gmin == 1 ? gmax : gmin);
-  kc = std::max(0, std::min(dim, kc));
-  if (gmin < kc - 1 || gmax > kc + 1) return nullptr;
-  const CoreEntryRt* core = find_core(dim, kc);
+  const CoreEntryRt* core = choose_core(dim, csrs, nblocks);
   if (!core) return nullptr;
+  const int kc = core->k;
   const TileConfig cfg = tile_config();
   auto plan = std::make_shared<TilePlan>();
   plan->mesh = mesh;
@@ -981,7 +994,6 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   plan->launch = core->launch;
   plan->ntiles = uint32_t(mesh->ntiles);
   plan->nthreads = cfg.nthreads;
-  plan->nstages = cfg.nstages;
   if (plan->ntiles >= (1u << 30)) return nullptr;
   // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)
   std::vector<std::vector<uint8_t>> codes8(static_cast<size_t>(nblocks));
@@ -990,8 +1002,6 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     TileBlockPlan& bp = plan->blk[b];
     std::vector<uint8_t>& codes = codes8[size_t(b)];
     if (!build_recipes(dim, kc, *core, csrs[b]->kind, csrs[b]->grade, bp.no, bp.ni, codes)) return nullptr;
-    for (uint8_t c : codes)
-      if (c == 0xFF) return nullptr;  // a constant-zero mass entry inside a non-zero block: not generated for n <= 3
     const bool shape_ok = (bp.no == 0 && bp.ni == 0) || (bp.no == 1 && bp.ni >= 1 && bp.ni <= 4) ||
                           (bp.no == bp.ni && bp.no >= 2 && bp.no <= 4);
     if (!shape_ok) return nullptr;
@@ -1039,7 +1049,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     plan->tile_cell_ptr.alloc(size_t(plan->ntiles) + 1);
     seg_ptr_kernel<<<grid_for(size_t(nvalid) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
         tile_of.p, nvalid, plan->ntiles, plan->tile_cell_ptr.p);
-    plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne) + 8);  // + slack: TMA copies 16-byte granules
+    plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne));
     tile_cell_edges_kernel<<<grid_for(size_t(nvalid) * ne, block, ctx->sm_count), block, 0, ctx->stream>>>(
         tile_cells.p, nvalid, mesh->cell_faces[1].p, ne, plan->tile_cell_edges.p);
     fq_count_launch(ctx, 3);
@@ -1053,29 +1063,22 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     if (int(max_cells) > tile_cells_capacity(plan->ndistinct)) return nullptr;
     plan->cstride = int(max_cells) | 1;  // odd stride: distinct rows start on different banks
     // dynamic shared memory layout
+    const size_t nwarps = size_t(plan->nthreads) / 32;
     size_t off = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double);
     off = (off + 127) / 128 * 128;
     plan->ring_off = uint32_t(off);
-    off += size_t(plan->nstages) * kChunkBytes;
-    plan->dir_off = uint32_t(off);
-    off += size_t(kMaxRecPerTile) * 4;
-    plan->chunk_off = uint32_t(off);
-    off += size_t(kMaxChunksPerTile + 1) * 4;
-    off = (off + 15) / 16 * 16;
+    off += nwarps * kSlotsPerWarp * kChunkBytes;
     plan->rec_off = uint32_t(off);
     off += recipe_bytes;
-    off = (off + 15) / 16 * 16;
-    plan->eid_off = uint32_t(off);
-    off += size_t(plan->cstride) * size_t(ne) * 4 + 32;  // staged edge ids of the next tile
     off = (off + 7) / 8 * 8;
     plan->mbar_off = uint32_t(off);
-    off += size_t(plan->nstages) * 16 + 16;  // full + empty ring barriers, directory, edge ids
+    off += nwarps * kSlotsPerWarp * 8;
     plan->smem_bytes = off;
     if (plan->smem_bytes > cfg.smem_cta) return nullptr;
   }
   // ---- recipes as slab offsets: code16 = sign << 15 | distinct * cstride
   if (size_t(plan->ndistinct) * size_t(plan->cstride) > 0x8000u) return nullptr;
-  std::vector<DevBuf<uint16_t>> direct_map(static_cast<size_t>(nblocks));  // (1,1) blocks: slot -> code16, used by the stream fill
+  std::vector<DevBuf<uint16_t>> direct_map(static_cast<size_t>(nblocks));  // stored blocks: slot -> code16, used by the stream fill
   {
     std::vector<uint16_t> table(recipe_bytes / 2, 0);
     size_t off16 = 0;
@@ -1100,9 +1103,10 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     std::vector<uint8_t> bytes(recipe_bytes ? recipe_bytes : 16, 0);
     if (recipe_bytes) std::memcpy(bytes.data(), table.data(), recipe_bytes);
     upload_vec(plan->recipes, bytes);
+    plan->recipe_bytes = int(recipe_bytes);
   }
   // ---- per block: non-zeros sorted by (tile, L, signature), cut into warp records
-  const int use_sig = std::getenv("FQ_TILE_SIG") ? std::atoi(std::getenv("FQ_TILE_SIG")) : 0;
+  const int use_sig = std::getenv("FQ_TILE_SIG") ? std::atoi(std::getenv("FQ_TILE_SIG")) : 1;
   DevBuf<int> d_err(1);
   FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
   std::vector<BlockBuild> bb(static_cast<size_t>(nblocks));
@@ -1153,8 +1157,8 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     FQ_CUDA(cudaMemcpyAsync(B.run_start.p + B.nruns, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     DevBuf<uint32_t> nrec_run(size_t(B.nruns) + 1);
     B.rec_base.alloc(size_t(B.nruns) + 1);
-    run_nrec_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(B.run_start.p, B.nruns,
-                                                                                                 nrec_run.p);
+    run_nrec_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        B.run_start.p, B.run_len.p, B.nruns, nrec_run.p);
     exclusive_scan_u32(ctx, nrec_run.p, B.rec_base.p, size_t(B.nruns) + 1);
     B.nrec = read_u32(ctx, B.rec_base.p + B.nruns);
     B.rec_len.alloc(B.nrec ? B.nrec : 1);
@@ -1171,43 +1175,36 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     FQ_CUDA(cudaGetLastError());
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  {
+    int h_err = 0;
+    FQ_CUDA(cudaMemcpy(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_err) return nullptr;  // a non-zero with more contributions than a record holds: keep the slab path
+  }
   // ---- layout of the per-tile streams
   TileLayoutArgs la{};
   la.nblocks = nblocks;
   for (int b = 0; b < nblocks; ++b)
     la.blk[b] = TileLayoutBlock{bb[size_t(b)].rec_tile_ptr.p, bb[size_t(b)].rec_len.p, bb[size_t(b)].rec_rel.p};
-  DevBuf<uint32_t> tile_units(size_t(plan->ntiles) + 1), tile_nrec(size_t(plan->ntiles) + 1);
-  FQ_CUDA(cudaMemsetAsync(tile_units.p, 0, tile_units.bytes(), ctx->stream));
-  FQ_CUDA(cudaMemsetAsync(tile_nrec.p, 0, tile_nrec.bytes(), ctx->stream));
-  tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      la, plan->ntiles, 0, tile_units.p, tile_nrec.p, nullptr, nullptr);
+  DevBuf<uint32_t> tile_nchunks(size_t(plan->ntiles) + 1);
+  FQ_CUDA(cudaMemsetAsync(tile_nchunks.p, 0, tile_nchunks.bytes(), ctx->stream));
+  tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(la, plan->ntiles, 0,
+                                                                                             tile_nchunks.p, nullptr, nullptr);
   fq_count_launch(ctx);
+  plan->tile_chunk_ptr.alloc(size_t(plan->ntiles) + 1);
   {
-    // capacity checks on the host (ntiles is small)
-    std::vector<uint32_t> h_units(size_t(plan->ntiles) + 1), h_nrec(size_t(plan->ntiles) + 1);
-    FQ_CUDA(cudaMemcpyAsync(h_units.data(), tile_units.p, h_units.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FQ_CUDA(cudaMemcpyAsync(h_nrec.data(), tile_nrec.p, h_nrec.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> h_n(size_t(plan->ntiles) + 1);
+    FQ_CUDA(cudaMemcpyAsync(h_n.data(), tile_nchunks.p, h_n.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint64_t total_units = 0;
-    for (uint32_t t = 0; t < plan->ntiles; ++t) {
-      if (h_nrec[t] > uint32_t(kMaxRecPerTile)) return nullptr;
-      if (uint64_t(h_units[t]) * 64 > uint64_t(kMaxChunksPerTile) * kChunkBytes) return nullptr;
-      total_units += h_units[t];
-    }
-    if (total_units >= (1ull << 32)) return nullptr;
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < plan->ntiles; ++t) total += h_n[t];
+    if (total >= (1ull << 31)) return nullptr;
   }
-  plan->tile_stream_ptr.alloc(size_t(plan->ntiles) + 1);
-  plan->tile_dir_ptr.alloc(size_t(plan->ntiles) + 1);
-  exclusive_scan_u32(ctx, tile_units.p, plan->tile_stream_ptr.p, size_t(plan->ntiles) + 1);
-  exclusive_scan_u32(ctx, tile_nrec.p, plan->tile_dir_ptr.p, size_t(plan->ntiles) + 1);
-  const uint32_t total_units = read_u32(ctx, plan->tile_stream_ptr.p + plan->ntiles);
-  const uint32_t total_rec = read_u32(ctx, plan->tile_dir_ptr.p + plan->ntiles);
-  plan->stream.alloc(size_t(total_units ? total_units : 1) * 64);
-  plan->rec_dir.alloc(total_rec ? total_rec : 4);
-  FQ_CUDA(cudaMemsetAsync(plan->rec_dir.p, 0xFF, plan->rec_dir.bytes(), ctx->stream));  // padding entries
+  exclusive_scan_u32(ctx, tile_nchunks.p, plan->tile_chunk_ptr.p, size_t(plan->ntiles) + 1);
+  const uint32_t total_chunks = read_u32(ctx, plan->tile_chunk_ptr.p + plan->ntiles);
+  plan->stream.alloc(size_t(total_chunks ? total_chunks : 1) * kChunkBytes);
   FQ_CUDA(cudaMemsetAsync(plan->stream.p, 0, plan->stream.bytes(), ctx->stream));  // padding lanes: dest 0, entries 0
   tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      la, plan->ntiles, 1, nullptr, nullptr, plan->tile_dir_ptr.p, plan->rec_dir.p);
+      la, plan->ntiles, 1, nullptr, plan->tile_chunk_ptr.p, plan->stream.p);
   fq_count_launch(ctx);
   for (int b = 0; b < nblocks; ++b) {
     fq_csr* csr = csrs[b];
@@ -1215,8 +1212,8 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     if (csr->s_nnz == 0) continue;
     const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
     stream_fill_kernel<<<grid_for(csr->s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        B.perm.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.rec_base.p, B.rec_rel.p,
-        plan->tile_stream_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, plan->blk[b].slot_bits, plan->tile_cell_ptr.p,
+        B.perm.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.rec_base.p, B.rec_rel.p,
+        plan->tile_chunk_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, plan->blk[b].slot_bits, plan->tile_cell_ptr.p,
         tile_cells.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0,
         plan->blk[b].no * plan->blk[b].ni == 1 ? direct_map[size_t(b)].p : nullptr, plan->stream.p, d_err.p);
     fq_count_launch(ctx);
@@ -1225,10 +1222,10 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   int h_err = 0;
   FQ_CUDA(cudaMemcpy(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-  if (h_err) return nullptr;  // a tile exceeds the 16-bit local index space / 255 contributions: keep the slab path
+  if (h_err) return nullptr;  // a tile exceeds the 15/16-bit local index space: keep the slab path
   plan->changed.alloc(1);
   plan->ticket.alloc(1);
-  plan->grid = ctx->sm_count * cfg.ctas_per_sm;
+  plan->grid = ctx->sm_count;
   return plan;
 }
 
@@ -1241,21 +1238,15 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   P.lengths = mesh->lengths.p;
   P.edge_lo = uint32_t(mesh->edge_lo);
   P.ntiles = plan.ntiles;
-  P.tile_dir_ptr = plan.tile_dir_ptr.p;
-  P.rec_dir = plan.rec_dir.p;
-  P.tile_stream_ptr = plan.tile_stream_ptr.p;
+  P.tile_chunk_ptr = plan.tile_chunk_ptr.p;
   P.stream = plan.stream.p;
   P.cstride = plan.cstride;
   P.nblocks = plan.nblocks;
-  P.nstages = plan.nstages;
   P.ring_off = plan.ring_off;
-  P.dir_off = plan.dir_off;
-  P.chunk_off = plan.chunk_off;
   P.rec_off = plan.rec_off;
-  P.eid_off = plan.eid_off;
   P.mbar_off = plan.mbar_off;
   P.recipes = plan.recipes.p;
-  P.recipe_bytes = int(plan.recipes.n);
+  P.recipe_bytes = plan.recipe_bytes;
   P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
   P.check_classification = (plan.blk[0].dropped_at_build && !P.debug) ? 1 : 0;
   P.changed = plan.changed.p;
@@ -1291,8 +1282,7 @@ bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const*
 }
 
 int64_t tile_plan_bytes(const TilePlan& plan) {
-  return int64_t(plan.tile_cell_ptr.bytes() + plan.tile_cell_edges.bytes() + plan.tile_dir_ptr.bytes() + plan.rec_dir.bytes() +
-                 plan.tile_stream_ptr.bytes() + plan.stream.bytes());
+  return int64_t(plan.tile_cell_ptr.bytes() + plan.tile_cell_edges.bytes() + plan.tile_chunk_ptr.bytes() + plan.stream.bytes());
 }
 
 }  // namespace fq
