@@ -153,6 +153,9 @@ struct fq_mesh {
   fq::DevBuf<uint32_t> vertex_tile;
   size_t vtile_lo = 0;
   size_t ntiles = 0;
+  // cells are numbered (box, type) with `cell_type_period` types per box (Kuhn grids: dim!); 0 = unknown.
+  // The tile kernel numbers a tile's cells type-major so that same-type gathers hit distinct banks.
+  int cell_type_period = 0;
 };
 
 struct fq_vec {

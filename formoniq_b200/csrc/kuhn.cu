@@ -252,6 +252,7 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   // vertex bricks for the tile-fused numeric assembly (tile.cu)
+  mesh->cell_type_period = kt.ncelltypes;
   tile_cluster_kuhn(ctx, mesh, dim, shape, slab_begin, slab_end);
 }
 

@@ -53,12 +53,11 @@ constexpr uint32_t kPadDest = 0u;
 constexpr uint32_t kNoDest = 1u;
 constexpr int kChunkBytes = 2048;   // TMA granule of the tile stream; records never straddle a chunk
 constexpr int kChunkHdr = 16;       // u32 nrec + padding
-constexpr int kRecHdr = 16;         // u32 (L | block << 8 | wide << 16) + padding
-constexpr int kWideMaxLen = 13;     // 64-lane records: 16 + 64 * (4 + 2 L) <= 2032
-constexpr int kMaxLen = 29;         // 32-lane records: 16 + 32 * (4 + 2 L) <= 2032
+constexpr int kRecHdr = 16;         // u32 (L | block << 8 | lanes << 16) + padding
+constexpr int kMaxLen = 61;         // record of 16 + lanes * (4 + 2 L) <= 2032 bytes: 64 lanes up to L = 13, 32 up to 29, 16 up to 61
 constexpr int kSlotsPerWarp = 2;    // private double buffer of every warp
 
-__host__ __device__ inline uint32_t rec_lanes(uint32_t L) { return L <= uint32_t(kWideMaxLen) ? 64u : 32u; }
+__host__ __device__ inline uint32_t rec_lanes(uint32_t L) { return L <= 13u ? 64u : (L <= 29u ? 32u : 16u); }
 __host__ __device__ inline uint32_t rec_bytes(uint32_t L) { return uint32_t(kRecHdr) + rec_lanes(L) * (4u + 2u * L); }
 
 struct TileBlockDev {
@@ -85,6 +84,7 @@ struct TileParams {
   int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
   int* changed;                     // raised when the zero/non-zero classification differs from the plan's
   unsigned int* ticket;             // dynamic tile scheduler
+  unsigned long long* stats;        // debug & 8: per-phase warp cycles [k1, bar_k1, chunk_wait, records, bar_top, other]
   TileBlockDev blk[kTileMaxBlocks];
 };
 
@@ -191,8 +191,8 @@ __device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict_
   }
 }
 
-template <class Fn, int NE, int NT>
-__global__ void __launch_bounds__(NT, 1) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
+template <class Fn, int NE, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* slab = reinterpret_cast<double*>(smem_raw);
   constexpr int NW = NT / 32;
@@ -225,8 +225,20 @@ __global__ void __launch_bounds__(NT, 1) tile_assemble_kernel(Fn fn, const __gri
   // issue cursor (tile iteration it is on, next chunk, end of that tile's chunks); runs ahead across tiles
   uint32_t n_issued = 0, n_consumed = 0;
   uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
+  const bool prof = (P.debug & 8) && lane == 0;
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  long long t_last = clock64();
+  auto lap = [&](int which) {
+    if (prof) {
+      const long long now = clock64();
+      tk[which] += now - t_last;
+      t_last = now;
+    }
+  };
   for (uint32_t it = 0;; ++it) {
+    lap(5);
     __syncthreads();  // previous tile fully consumed, this tile's header visible
+    lap(4);
     const uint32_t* hdr = s_hdr[it % 3];
     const uint32_t t = hdr[0];
     if (t >= P.ntiles) break;
@@ -274,23 +286,27 @@ __global__ void __launch_bounds__(NT, 1) tile_assemble_kernel(Fn fn, const __gri
         fn(s, sink);
       }
     }
+    lap(0);
     __syncthreads();
+    lap(1);
     if (tid == 0) fetch_header(s_hdr[(it + 2) % 3]);  // two tiles ahead: its latency hides behind this gather
     // ---- K3: this warp's chunks; one record at a time, two owned structural non-zeros per lane
     for (uint32_t c = c0 + warp; c < c1; c += NW) {
+      lap(5);
       mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
+      lap(2);
       const unsigned char* chunk = myring + (n_consumed & 1u) * kChunkBytes;
       const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
       const unsigned char* rp = chunk + kChunkHdr;
       for (uint32_t r = 0; r < nrec; ++r) {
         const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
-        const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, wide = (h >> 16) & 1u;
-        const uint32_t stride = wide ? 64u : 32u;
+        const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
         const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
-        const uint32_t dest0 = destp[lane];
-        const uint32_t dest1 = wide ? destp[lane + 32] : kPadDest;
-        const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + lane;
-        const uint16_t* __restrict__ ent1 = ent0 + (wide ? 32 : 0);
+        const uint32_t l0 = lane & (stride - 1u);  // lanes beyond a 16-wide record shadow the first ones and never store
+        const uint32_t dest0 = lane < stride ? destp[l0] : kPadDest;
+        const uint32_t dest1 = stride == 64u ? destp[lane + 32] : kPadDest;
+        const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
+        const uint16_t* __restrict__ ent1 = ent0 + (stride == 64u ? 32 : 0);
         rp += kRecHdr + stride * (4u + 2u * L);
         const TileBlockDev& B = P.blk[b];
         const uint16_t* __restrict__ brec = rec + B.recipe_off;
@@ -316,10 +332,13 @@ __global__ void __launch_bounds__(NT, 1) tile_assemble_kernel(Fn fn, const __gri
         if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
       }
       __syncwarp();  // every lane is done reading the slot before it is refilled
+      lap(3);
       ++n_consumed;
       issue_more();
     }
   }
+  if (prof)
+    for (int i = 0; i < 6; ++i) atomicAdd(P.stats + i, (unsigned long long)tk[i]);
 }
 
 // ------------------------------------------------------------------ plan
@@ -344,6 +363,7 @@ struct TilePlan {
   DevBuf<uint8_t> recipes;
   DevBuf<int> changed;
   DevBuf<unsigned int> ticket;
+  DevBuf<unsigned long long> stats;
   int nblocks = 0;
   TileBlockPlan blk[kTileMaxBlocks];
   int grid = 0;
@@ -361,22 +381,22 @@ struct TilePlan {
 FQ_GEN_CORE_LIST(FQ_DECLARE_CORE)
 #undef FQ_DECLARE_CORE
 
-template <class Fn, int NE, int NT>
+template <class Fn, int NE, int NT, int MINB>
 static void launch_tile_nt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static bool attr_set = false;
   if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024 - 256));
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (MINB == 1 ? 227 : 113) * 1024 - 256));
     attr_set = true;
   }
-  tile_assemble_kernel<Fn, NE, NT><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  tile_assemble_kernel<Fn, NE, NT, MINB><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  if (plan.nthreads == 768)
-    launch_tile_nt<Fn, NE, 768>(ctx, plan, params);
+  if (plan.nthreads == 256)
+    launch_tile_nt<Fn, NE, 256, 2>(ctx, plan, params);  // two CTAs per SM: one tile's K1 overlaps the other's gather
   else
-    launch_tile_nt<Fn, NE, 512>(ctx, plan, params);
+    launch_tile_nt<Fn, NE, 512, 1>(ctx, plan, params);
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
 }
@@ -419,10 +439,8 @@ struct TileConfig {
 };
 static TileConfig tile_config() {
   TileConfig c{512, size_t(227) * 1024 - 256};
-  if (const char* e = std::getenv("FQ_TILE_THREADS")) {
-    const int nt = std::atoi(e);
-    if (nt == 512 || nt == 768) c.nthreads = nt;
-  }
+  if (const char* e = std::getenv("FQ_TILE_THREADS"))
+    if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256};
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
@@ -433,11 +451,12 @@ static size_t tile_fixed_smem(const TileConfig& c) {
 int tile_cells_capacity(int ndistinct) {
   const TileConfig c = tile_config();
   const int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double)));
-  return std::min(cap, 1023);
+  return std::min(cap, c.nthreads);  // K1 evaluates one cell per thread in one pass
 }
 static int tile_core_variant() {
+  // default: masses only (54 doubles per 3-D cell -> larger tiles); FQ_TILE_CORE=h also stores dif_both(k+1)
   const char* e = std::getenv("FQ_TILE_CORE");
-  return (e && e[0] == 's') ? 0 : 1;
+  return (e && e[0] == 'h') ? 1 : 0;
 }
 
 // Recipes of one block over the distinct values of core(n, kc).
@@ -579,6 +598,28 @@ __global__ void seg_ptr_kernel(const uint32_t* __restrict__ key, size_t n, uint3
     for (uint32_t t = lo; t <= hi && t <= nseg; ++t) ptr[t] = uint32_t(i);
   }
 }
+// type-major slot order inside every tile: key = tile | cell type | cell
+__global__ void tile_slot_keys_kernel(const uint32_t* __restrict__ tile_of, const uint32_t* __restrict__ tile_cells, size_t n,
+                                      uint32_t period, uint64_t cell_offset, uint64_t* __restrict__ keys,
+                                      uint32_t* __restrict__ pos) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t type = period ? (cell_offset + tile_cells[i]) % period : 0;
+    keys[i] = (uint64_t(tile_of[i]) << 35) | (type << 32) | uint64_t(tile_cells[i]);
+    pos[i] = uint32_t(i);
+  }
+}
+// after the sort: slot i holds the cell at (tile, cell)-sorted position pos[i]
+__global__ void tile_slots_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, size_t n,
+                                  const uint32_t* __restrict__ tile_cell_ptr, uint32_t* __restrict__ cells_by_slot,
+                                  uint32_t* __restrict__ local_of_pos) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t t = uint32_t(keys[i] >> 35);
+    cells_by_slot[i] = uint32_t(keys[i]);
+    local_of_pos[pos[i]] = uint32_t(i) - tile_cell_ptr[t];
+  }
+}
 __global__ void tile_cell_edges_kernel(const uint32_t* __restrict__ tile_cells, size_t n, const uint32_t* __restrict__ cell_edges,
                                        int ne, uint32_t* __restrict__ out) {
   const size_t total = n * size_t(ne);
@@ -616,8 +657,13 @@ __global__ void nnz_key_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nr
         L = kMaxLen;
       }
       uint32_t sig = 0;
-      if (use_sig)
-        for (uint32_t p = p0; p < p1; ++p) sig = sig * 131u + (contrib_src[p] % T) + 1u;
+      if (use_sig) {  // "type" of the non-zero: its slot sequence and the relative cell offsets of its contributions
+        const uint32_t cell0 = contrib_src[p0] / T;
+        for (uint32_t p = p0; p < p1; ++p) {
+          const uint32_t cell = contrib_src[p] / T;
+          sig = (sig * 131u + (contrib_src[p] - cell * T) + 1u) * 31u + (cell - cell0);
+        }
+      }
       sig = (sig ^ (sig >> 16)) & 0xFFFFu;
       key[q] = (t << 24) | (uint64_t(L) << 16) | sig;
       nnz_id[q] = q;
@@ -700,7 +746,7 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
         }
         if (pass) {
           B.rec_rel[k] = off / 16u;
-          *reinterpret_cast<uint32_t*>(base + off) = L | (uint32_t(b) << 8) | ((rec_lanes(L) == 64u ? 1u : 0u) << 16);
+          *reinterpret_cast<uint32_t*>(base + off) = L | (uint32_t(b) << 8) | (rec_lanes(L) << 16);
         }
         off += size;
         ++in_chunk;
@@ -720,7 +766,8 @@ __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n
                                    const uint32_t* __restrict__ rec_rel, const uint32_t* __restrict__ tile_chunk_ptr,
                                    const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
                                    int slot_bits, const uint32_t* __restrict__ tile_cell_ptr,
-                                   const uint32_t* __restrict__ tile_cells, const uint8_t* __restrict__ keep,
+                                   const uint32_t* __restrict__ tile_cells, const uint32_t* __restrict__ tile_local,
+                                   const uint8_t* __restrict__ keep,
                                    const uint32_t* __restrict__ pos, int drop,
                                    const uint16_t* __restrict__ direct_map /*stored blocks: slot -> sign | slab offset*/,
                                    unsigned char* __restrict__ stream, int* __restrict__ err) {
@@ -752,7 +799,7 @@ __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n
         atomicExch(err, 2);
         continue;
       }
-      const uint32_t local = lo - cb;
+      const uint32_t local = tile_local[lo];
       if (direct_map) {
         const uint32_t code = direct_map[slot];
         if ((code & 0x7FFFu) + local > 0x7FFFu) atomicExch(err, 3);
@@ -807,9 +854,33 @@ void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape,
   for (const CoreEntryRt& e : g_cores)
     if (e.n == dim && (tile_core_variant() == 1 || e.variant == 0)) max_distinct = std::max(max_distinct, e.ndistinct);
   const int cells_capacity = tile_cells_capacity(max_distinct);
-  // brick[a] owned vertices per axis; a tile needs the cells of prod(brick[a]+1) boxes
-  const int ncelltypes = int(fact(dim));
+  // brick[a] owned vertices per axis; a tile needs every cell with a vertex in the brick
   std::vector<uint32_t> brick(size_t(dim), 1);
+  // exact count for a brick in the interior of the grid: boxes with origin in prod [-1, b_a - 1], dim! chains each
+  auto cells_touching = [&](const std::vector<uint32_t>& b) {
+    std::vector<int> perm(size_t(dim), 0);
+    uint64_t count = 0;
+    std::vector<int> o(size_t(dim), -1);
+    for (;;) {
+      for (int a = 0; a < dim; ++a) perm[size_t(a)] = a;
+      do {
+        std::vector<int> v = o;
+        bool hit = true;
+        for (int a = 0; a < dim; ++a) hit = hit && v[size_t(a)] >= 0 && v[size_t(a)] < int(b[size_t(a)]);
+        for (int step = 0; step < dim && !hit; ++step) {
+          v[size_t(perm[size_t(step)])] += 1;
+          bool in = true;
+          for (int a = 0; a < dim; ++a) in = in && v[size_t(a)] >= 0 && v[size_t(a)] < int(b[size_t(a)]);
+          hit = in;
+        }
+        if (hit) ++count;
+      } while (std::next_permutation(perm.begin(), perm.end()));
+      int a = 0;
+      while (a < dim && ++o[size_t(a)] >= int(b[size_t(a)])) o[size_t(a++)] = -1;
+      if (a == dim) break;
+    }
+    return count;
+  };
   if (const char* env = std::getenv("FQ_TILE_BRICK")) {
     int a = 0;
     const char* p = env;
@@ -824,14 +895,13 @@ void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape,
       double best_ratio = 1e300;
       for (int a = 0; a < dim; ++a) {
         if (brick[size_t(a)] >= shape[a] + 1) continue;
-        uint64_t boxes = 1, owned = 1;
-        for (int b = 0; b < dim; ++b) {
-          const uint64_t bb = brick[size_t(b)] + (b == a ? 1 : 0);
-          boxes *= bb + 1;
-          owned *= bb;
-        }
-        if (boxes * uint64_t(ncelltypes) > uint64_t(cells_capacity)) continue;
-        const double ratio = double(boxes) / double(owned);
+        uint64_t owned = 1;
+        std::vector<uint32_t> cand = brick;
+        cand[size_t(a)] += 1;
+        for (int b = 0; b < dim; ++b) owned *= cand[size_t(b)];
+        const uint64_t ncell = cells_touching(cand);
+        if (ncell > uint64_t(cells_capacity)) continue;
+        const double ratio = double(ncell) / double(owned);
         // prefer the lower axis on ties (longer contiguous CSR runs)
         if (ratio < best_ratio - 1e-12) best_ratio = ratio, best = a;
       }
@@ -1020,7 +1090,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   const size_t ncells = mesh->ncells;
   const uint32_t v_lo = uint32_t(mesh->vtile_lo);
   // ---- tile cell lists
-  DevBuf<uint32_t> tile_cells;
+  DevBuf<uint32_t> tile_cells, tile_local;  // cells of every tile sorted by id, and their slab slot
   {
     const size_t nkeys = ncells * size_t(nv);
     DevBuf<uint64_t> keys(nkeys), keys_alt(nkeys);
@@ -1049,10 +1119,23 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     plan->tile_cell_ptr.alloc(size_t(plan->ntiles) + 1);
     seg_ptr_kernel<<<grid_for(size_t(nvalid) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
         tile_of.p, nvalid, plan->ntiles, plan->tile_cell_ptr.p);
+    // slab slots: type-major inside a tile when the cell numbering is (box, type), else ascending cell id
+    DevBuf<uint32_t> cells_by_slot(nvalid ? nvalid : 1);
+    tile_local.alloc(nvalid ? nvalid : 1);
+    {
+      DevBuf<uint64_t> skeys(nvalid ? nvalid : 1);
+      DevBuf<uint32_t> spos(nvalid ? nvalid : 1);
+      const uint32_t period = std::getenv("FQ_TILE_NO_TYPE_MAJOR") ? 0u : uint32_t(mesh->cell_type_period);
+      tile_slot_keys_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(
+          tile_of.p, tile_cells.p, nvalid, period, uint64_t(mesh->cell_offset), skeys.p, spos.p);
+      radix_sort_pairs_u64(ctx, skeys, spos, nvalid, 64);
+      tile_slots_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(
+          skeys.p, spos.p, nvalid, plan->tile_cell_ptr.p, cells_by_slot.p, tile_local.p);
+    }
     plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne));
     tile_cell_edges_kernel<<<grid_for(size_t(nvalid) * ne, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        tile_cells.p, nvalid, mesh->cell_faces[1].p, ne, plan->tile_cell_edges.p);
-    fq_count_launch(ctx, 3);
+        cells_by_slot.p, nvalid, mesh->cell_faces[1].p, ne, plan->tile_cell_edges.p);
+    fq_count_launch(ctx, 5);
     FQ_CUDA(cudaGetLastError());
     std::vector<uint32_t> h_ptr(size_t(plan->ntiles) + 1);
     FQ_CUDA(cudaMemcpyAsync(h_ptr.data(), plan->tile_cell_ptr.p, h_ptr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -1214,7 +1297,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     stream_fill_kernel<<<grid_for(csr->s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
         B.perm.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.rec_base.p, B.rec_rel.p,
         plan->tile_chunk_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, plan->blk[b].slot_bits, plan->tile_cell_ptr.p,
-        tile_cells.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0,
+        tile_cells.p, tile_local.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0,
         plan->blk[b].no * plan->blk[b].ni == 1 ? direct_map[size_t(b)].p : nullptr, plan->stream.p, d_err.p);
     fq_count_launch(ctx);
   }
@@ -1225,7 +1308,8 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   if (h_err) return nullptr;  // a tile exceeds the 15/16-bit local index space: keep the slab path
   plan->changed.alloc(1);
   plan->ticket.alloc(1);
-  plan->grid = ctx->sm_count;
+  plan->stats.alloc(8);
+  plan->grid = ctx->sm_count * (cfg.nthreads == 256 ? 2 : 1);
   return plan;
 }
 
@@ -1248,9 +1332,10 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   P.recipes = plan.recipes.p;
   P.recipe_bytes = plan.recipe_bytes;
   P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
-  P.check_classification = (plan.blk[0].dropped_at_build && !P.debug) ? 1 : 0;
+  P.check_classification = (plan.blk[0].dropped_at_build && !(P.debug & 7)) ? 1 : 0;
   P.changed = plan.changed.p;
   P.ticket = plan.ticket.p;
+  P.stats = plan.stats.p;
   for (int b = 0; b < plan.nblocks; ++b) {
     const TileBlockPlan& bp = plan.blk[b];
     TileBlockDev& d = P.blk[b];
@@ -1264,11 +1349,19 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
     ScopedSpan span(ctx, "k13_tile_fused");
     FQ_CUDA(cudaMemsetAsync(plan.changed.p, 0, sizeof(int), ctx->stream));
     FQ_CUDA(cudaMemsetAsync(plan.ticket.p, 0, sizeof(unsigned int), ctx->stream));
+    if (P.debug & 8) FQ_CUDA(cudaMemsetAsync(plan.stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     plan.launch(ctx, plan, P);
   }
   int changed = 0;
   FQ_CUDA(cudaMemcpyAsync(&changed, plan.changed.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (P.debug & 8) {  // development aid: where the warps spend their cycles
+    unsigned long long h[6];
+    FQ_CUDA(cudaMemcpy(h, plan.stats.p, sizeof h, cudaMemcpyDeviceToHost));
+    const double tot = double(h[0] + h[1] + h[2] + h[3] + h[4] + h[5]);
+    std::fprintf(stderr, "[tile stats] k1 %.1f%%  bar_k1 %.1f%%  chunk_wait %.1f%%  records %.1f%%  bar_top %.1f%%  other %.1f%%  (warp-cycles %.3g)\n",
+                 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot);
+  }
   return changed == 0;
 }
 
