@@ -279,7 +279,14 @@ def run_b200(args):
     peak, peak_src = peaks()
     # dominant block pipeline (K1 element slab + K3 gather + compaction) for the roofline line
     per_launch = {k: v["ms"] / max(v["count"], 1) for k, v in kern.items()}
-    asm_kernel_ms = sum(v["ms"] for k, v in kern.items() if k.startswith(("k1", "k3"))) / args.steps
+    asm_kernel_ms = sum(v["ms"] for k, v in kern.items() if k.startswith(("k1", "k3"))) / args.steps  # k13_tile_fused included
+    fused = kern.get("k13_tile_fused", {}).get("count", 0) > 0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_tile_traffic.json")
+    if fused and os.path.exists(tp):  # dram__bytes_read+write per launch of the same workload, from the committed ncu capture
+        tj = json.load(open(tp))
+        if tj.get("n") == n and tj.get("cells") == owned_cells:
+            traffic = tj.get("dram_bytes_per_launch")
     achieved = (asm_bytes / 1e9) / (asm_kernel_ms / 1e3) if asm_kernel_ms > 0 else 0.0
     big = max(range(len(spmv)), key=lambda i: spmv[i]["nnz"])
     out = {
@@ -289,7 +296,7 @@ def run_b200(args):
         "config": {"workload": f"3-D Hodge-Laplace k=1 mixed (AFW): numeric assembly of M0, M1, dif_test(1), dif_both(2) "
                                f"on a Kuhn grid {shape[0]}x{shape[1]}x{shape[2]} ({int(cells_all)} tets, {n}^3 boxes per GPU), "
                                f"reference `!= 0.0` pattern semantics", "cells_per_gpu": owned_cells,
-                   "l2_policy": "inputs_larger_than_l2 (maps + slabs are GBs per step, L2 is 126 MB)",
+                   "l2_policy": "inputs_larger_than_l2 (the per-tile map stream and the CSR values are GBs per step, L2 is 126 MB)",
                    "parallelism": f"owner-computes z-slabs x{world}, no collective on the assembly path"},
         "nnz_per_s": nnz_all * args.steps / secs, "nnz": int(nnz_all),
         "spmv": {"block": spmv[big]["block"], "gbs": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3),
@@ -297,7 +304,10 @@ def run_b200(args):
                  "all_blocks_gbs": sum(spmv_bytes) / 1e9 / (sum(spmv_ms) / 1e3),
                  "halo_exchange": "torch.distributed NCCL send/recv with z-neighbours" if world > 1 else "none (1 GPU)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "numeric assembly pipeline K1 elmat -> K3 gather -> compaction (rank 0, all four blocks)",
+                     "traffic": traffic,
+                     "kernel": ("tile_assemble_kernel: K1 element masses + K3 segmented reduction fused in shared memory, "
+                                "all four blocks in one persistent launch (rank 0)") if fused else
+                               "numeric assembly pipeline K1 elmat -> K3 gather -> compaction (rank 0, all four blocks)",
                      "algorithmic_bytes_per_step": asm_bytes, "peak_source": peak_src,
                      "kernel_ms_per_launch": per_launch},
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in kern.items()},
@@ -351,6 +361,9 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
     cells = ns[DIM]
     d2h = 0
     times = []
+    # the caller's result buffers (the Vec<usize>/Vec<f64> of the CsrMatrix): pinned, sized by the warm-up pass, reused
+    out = None
+    max_nnz = 0
     for it in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
@@ -358,7 +371,8 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
         d2h = 0
         for _, form in forms:
             a = form.assemble(m, True)
-            rp, ci, va = a.download()
+            max_nnz = max(max_nnz, a.nnz)
+            rp, ci, va = a.download(out=out)
             d2h += rp.nbytes + ci.nbytes + va.nbytes
             del a, rp, ci, va
         torch.cuda.synchronize()
@@ -366,10 +380,14 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
         del m
         if it > 0:  # first pass is the warm-up
             times.append(dt)
+        elif out is None:
+            out = (torch.empty(max(ns) + 1, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64),
+                   torch.empty(max(max_nnz, 1), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64),
+                   torch.empty(max(max_nnz, 1), dtype=torch.float64, pin_memory=True).numpy())
     t = allmax(sum(times) / len(times))
     return {"value": allsum(cells) / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": t * 1e3, "workload": f"per rank: fq_mesh_create + 4x fq_assemble + fq_csr_download on a Kuhn cube "
-                                                f"N={n_e2e} ({cells} tets) from pinned host arrays"}
+                                                f"N={n_e2e} ({cells} tets), pinned host arrays in and out"}
 
 
 def main():

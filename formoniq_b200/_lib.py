@@ -32,6 +32,7 @@ SIGNATURES = [
     ("fq_ctx_set_stream", _i, [_vp, _vp]),
     ("fq_ctx_synchronize", _i, [_vp]),
     ("fq_ctx_launch_count", _i64, [_vp]),
+    ("fq_device_cache_trim", _i, []),
     ("fq_ctx_set_timing", _i, [_vp, _i]),
     ("fq_ctx_timing_report", _i, [_vp, _vp, _sz]),
     ("fq_mesh_create", _i, [_vp, _i, _sz, _vp, _vp, _vp, _P(_vp)]),

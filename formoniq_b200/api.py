@@ -320,13 +320,23 @@ class DeviceCsr:
         m.sort_indices()
         return cls.upload(ctx, m.shape[0], m.shape[1], m.indptr, m.indices, m.data)
 
-    def download(self):
-        """(row_offsets, col_indices, values) as usize/usize/f64 host arrays."""
+    def download(self, out=None):
+        """(row_offsets, col_indices, values) as usize/usize/f64 host arrays.
+
+        `out` = (row_offsets, col_indices, values) buffers to fill (uint64, uint64, float64, at least as long as
+        needed); pass views of pinned memory to get PCIe-rate copies.  Returns views of the filled parts."""
         b, e = self.row_range
         nnz = self.nnz
-        rp = np.zeros(e - b + 1, dtype=np.uint64)
-        ci = np.zeros(nnz, dtype=np.uint64)
-        va = np.zeros(nnz)
+        if out is None:
+            rp = np.empty(e - b + 1, dtype=np.uint64)
+            ci = np.empty(nnz, dtype=np.uint64)
+            va = np.empty(nnz)
+        else:
+            rp, ci, va = out[0][:e - b + 1], out[1][:nnz], out[2][:nnz]
+            if rp.dtype != np.uint64 or ci.dtype != np.uint64 or va.dtype != np.float64:
+                raise FormoniqError(-1, "download buffers must be uint64 / uint64 / float64")
+            if rp.shape[0] != e - b + 1 or ci.shape[0] != nnz or va.shape[0] != nnz:
+                raise FormoniqError(-1, "download buffers are too small")
         check(_lib.lib().fq_csr_download(self.ctx._h, self._h, _p(rp), _p(ci), _p(va)))
         return rp, ci, va
 

@@ -359,9 +359,12 @@ static bool pattern_ready(const fq_csr* csr, bool drop) {
 void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros) {
   // ---- fast path: tile-fused K1+K3 (tile.cu), from the second numeric pass on
   {
-    bool ready = nblocks >= 1 && mesh->vertex_tile.p != nullptr;
+    bool ready = nblocks >= 1;
     for (int b = 0; ready && b < nblocks; ++b)
       ready = csrs[b]->ncells == mesh->ncells && csrs[b]->dim == mesh->dim && pattern_ready(csrs[b], drop_exact_zeros);
+    if (ready && !mesh->vertex_tile.p && !mesh->cluster_tried && csrs[0]->tile_refused == 0)
+      tile_cluster_generic(ctx, const_cast<fq_mesh*>(mesh));  // uploaded meshes: clustered on first reuse, never in one-shot assembly
+    ready = ready && mesh->vertex_tile.p != nullptr;
     if (ready) {
       std::shared_ptr<TilePlan> plan = csrs[0]->tile_plan;
       if (plan && !tile_plan_matches(*plan, mesh, csrs, nblocks, drop_exact_zeros)) plan.reset();

@@ -1,6 +1,8 @@
 // capi.cu — the extern "C" boundary declared in include/formoniq_b200.h.
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 
 #include "internal.hpp"
 #include "kuhn.hpp"
@@ -8,6 +10,85 @@
 namespace fq {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
+
+// ---- caching device allocator ------------------------------------------------
+// Blocks are rounded up (512 B below 1 MB, 2 MB above) and kept per (device, size) when released; reuse is
+// stream-ordered because every context enqueues its work on one stream and the API calls that release large
+// temporaries synchronise first.  cudaMalloc failures trim the cache and retry once.
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::map<std::pair<int, size_t>, std::vector<void*>> free_blocks;
+  std::map<void*, std::pair<int, size_t>> live;
+  size_t cached_bytes = 0;
+};
+DevCache& dev_cache() {
+  static DevCache* c = new DevCache;  // leaked on purpose: outlives every static destructor that may release buffers
+  return *c;
+}
+size_t round_size(size_t b) {
+  const size_t g = b < (size_t(1) << 20) ? 512 : (size_t(2) << 20);
+  return (b + g - 1) / g * g;
+}
+}  // namespace
+void dev_cache_trim() {
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  for (auto& kv : c.free_blocks)
+    for (void* p : kv.second) cudaFree(p);
+  c.free_blocks.clear();
+  c.cached_bytes = 0;
+}
+void* dev_alloc(size_t bytes) {
+  DevCache& c = dev_cache();
+  int dev = 0;
+  FQ_CUDA(cudaGetDevice(&dev));
+  const size_t sz = round_size(bytes);
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    // best fit: the smallest cached block that is large enough and wastes at most a quarter
+    for (auto it = c.free_blocks.lower_bound({dev, sz}); it != c.free_blocks.end() && it->first.first == dev; ++it) {
+      if (it->first.second > sz + sz / 4 + (size_t(2) << 20)) break;
+      if (it->second.empty()) continue;
+      void* p = it->second.back();
+      it->second.pop_back();
+      c.cached_bytes -= it->first.second;
+      c.live[p] = it->first;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, sz);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    dev_cache_trim();
+    err = cudaMalloc(&p, sz);
+  }
+  if (err != cudaSuccess)
+    throw Error(FQ_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(sz) + " bytes: " + cudaGetErrorString(err));
+  std::lock_guard<std::mutex> lk(c.mu);
+  c.live[p] = {dev, sz};
+  return p;
+}
+void dev_free(void* p) {
+  if (!p) return;
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto it = c.live.find(p);
+  if (it == c.live.end()) {
+    cudaFree(p);
+    return;
+  }
+  const auto key = it->second;
+  c.live.erase(it);
+  // keep at most 96 GB cached per process; beyond that hand the block back to the driver
+  if (c.cached_bytes + key.second > (size_t(96) << 30)) {
+    cudaFree(p);
+    return;
+  }
+  c.free_blocks[key].push_back(p);
+  c.cached_bytes += key.second;
+}
 
 __global__ void widen_u32_kernel(const uint32_t* __restrict__ in, size_t n, uint64_t* __restrict__ out) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
@@ -42,18 +123,29 @@ static void upload_narrow(fq_ctx* ctx, const uint64_t* host, size_t n, DevBuf<ui
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   FQ_REQUIRE(h == 0, "index does not fit 32 bits");
 }
-// device u32 array -> host u64 array
+// device u32 array -> host u64 array: widened on the device in pieces of up to 2 GB, each copied back with one
+// cudaMemcpyAsync (PCIe-bound when the destination is pinned or registered host memory)
 static void download_widen(fq_ctx* ctx, const uint32_t* dev, size_t n, uint64_t* host) {
   if (!n) return;
-  const size_t chunk = size_t(1) << 24;
-  DevBuf<uint64_t> stage(std::min(n, chunk));
-  for (size_t off = 0; off < n; off += chunk) {
+  const size_t chunk = size_t(1) << 28;
+  DevBuf<uint64_t> stage[2];
+  stage[0].alloc(std::min(n, chunk));
+  if (n > chunk) stage[1].alloc(std::min(n - chunk, chunk));
+  cudaEvent_t done[2];
+  FQ_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+  FQ_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+  int k = 0;
+  for (size_t off = 0; off < n; off += chunk, k ^= 1) {
     const size_t m = std::min(chunk, n - off);
-    widen_u32_kernel<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(dev + off, m, stage.p);
+    if (off >= 2 * chunk) FQ_CUDA(cudaEventSynchronize(done[k]));  // the staging piece is free again
+    widen_u32_kernel<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(dev + off, m, stage[k].p);
     fq_count_launch(ctx);
-    FQ_CUDA(cudaMemcpyAsync(host + off, stage.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    FQ_CUDA(cudaMemcpyAsync(host + off, stage[k].p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaEventRecord(done[k], ctx->stream));
   }
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEventDestroy(done[0]);
+  cudaEventDestroy(done[1]);
 }
 }  // namespace fq
 
@@ -115,6 +207,12 @@ int fq_ctx_synchronize(fq_ctx* ctx) {
   FQ_API_END
 }
 int64_t fq_ctx_launch_count(const fq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int fq_device_cache_trim(void) {
+  FQ_API_BEGIN
+  cudaDeviceSynchronize();
+  dev_cache_trim();
+  FQ_API_END
+}
 int fq_ctx_set_timing(fq_ctx* ctx, int on) {
   FQ_API_BEGIN
   FQ_REQUIRE(ctx, "null context");
@@ -178,7 +276,6 @@ int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices
   FQ_CUDA(cudaMemcpyAsync(m->lengths.p, edge_lengths_sq, nsimplices[1] * sizeof(double), cudaMemcpyHostToDevice,
                           ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (cell_faces[0]) tile_cluster_generic(ctx, m.get(), cell_faces[0]);
   *out = m.release();
   FQ_API_END
 }

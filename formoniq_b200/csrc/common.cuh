@@ -49,6 +49,12 @@ void set_last_error(const std::string& m);
     return FQ_ERR_INVALID;                          \
   }
 
+// Device memory comes from a process-wide caching allocator (capi.cu): multi-GB cudaMalloc/cudaFree calls cost tens of
+// milliseconds each and synchronise the device, which dominated the symbolic phase and the one-shot assembly.
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+void dev_cache_trim();
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -72,10 +78,10 @@ struct DevBuf {
     release();
     owned = true;
     n = n_;
-    if (n) FQ_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+    if (n) p = static_cast<T*>(dev_alloc(n * sizeof(T)));
   }
   void release() {
-    if (p && owned) cudaFree(p);
+    if (p && owned) dev_free(p);
     p = nullptr, n = 0;
   }
   size_t bytes() const { return n * sizeof(T); }
@@ -156,6 +162,7 @@ struct fq_mesh {
   // cells are numbered (box, type) with `cell_type_period` types per box (Kuhn grids: dim!); 0 = unknown.
   // The tile kernel numbers a tile's cells type-major so that same-type gathers hit distinct banks.
   int cell_type_period = 0;
+  bool cluster_tried = false;  // generic meshes are clustered lazily, when a tile plan is first built
 };
 
 struct fq_vec {

@@ -333,6 +333,7 @@ static TapeDev* get_tape(fq_ctx* ctx, int dim, const std::vector<BlockSpec>& blo
   for (const TapeOp& o : td->tape.ops) hops.push_back(make_uint4(o.op, o.d, o.a, o.b));
   td->ops.alloc(hops.size() ? hops.size() : 1);
   td->consts.alloc(td->tape.consts.size() ? td->tape.consts.size() : 1);
+  FQ_CUDA(cudaDeviceSynchronize());  // recycled blocks: order the blocking copies after everything in flight
   if (!hops.empty()) FQ_CUDA(cudaMemcpy(td->ops.p, hops.data(), hops.size() * sizeof(uint4), cudaMemcpyHostToDevice));
   if (!td->tape.consts.empty())
     FQ_CUDA(cudaMemcpy(td->consts.p, td->tape.consts.data(), td->tape.consts.size() * sizeof(double),

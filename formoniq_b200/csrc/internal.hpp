@@ -26,7 +26,7 @@ void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csr
 
 // ---- tile.cu (tile-fused numeric assembly)
 void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held);
-void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh, const uint64_t* cell_verts);
+void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh);  // lazy: run when a tile plan is first built
 std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop);
 bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop);
 bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan);

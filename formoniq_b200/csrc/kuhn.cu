@@ -118,6 +118,8 @@ __global__ void kuhn_lengths_kernel(GridDev g, CoordDev cd, int ntypes, const ui
 template <class T>
 static void upload(DevBuf<T>& d, const std::vector<T>& h) {
   d.alloc(h.size() ? h.size() : 1);
+  // blocks may be recycled by the caching allocator: order this blocking copy after everything in flight
+  FQ_CUDA(cudaDeviceSynchronize());
   if (!h.empty()) FQ_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
 }
 

@@ -821,6 +821,8 @@ static int bits_for32(uint64_t n) {
 template <class T>
 static void upload_vec(DevBuf<T>& d, const std::vector<T>& h) {
   d.alloc(h.size() ? h.size() : 1);
+  // blocks may be recycled by the caching allocator: order this blocking copy after everything in flight
+  FQ_CUDA(cudaDeviceSynchronize());
   if (!h.empty()) FQ_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
 }
 static uint32_t read_u32(fq_ctx* ctx, const uint32_t* p) {
@@ -938,9 +940,14 @@ void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape,
 // Generic meshes: greedy breadth-first growth of vertex clusters on the host (once
 // per mesh), each limited to `capacity` incident cells.  cell_verts is the
 // grade-0 FaceIncidence table ([ncells][dim+1], global vertex ids).
-void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh, const uint64_t* cell_verts) {
+void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh) {
   const int dim = mesh->dim;
-  if (dim > 3 || std::getenv("FQ_NO_TILE") || !cell_verts) return;
+  mesh->cluster_tried = true;
+  if (dim > 3 || std::getenv("FQ_NO_TILE") || !mesh->cell_faces[0].p || mesh->edge_lo != 0 || mesh->cell_offset != 0) return;
+  std::vector<uint32_t> cell_verts(mesh->cell_faces[0].n);
+  FQ_CUDA(cudaMemcpyAsync(cell_verts.data(), mesh->cell_faces[0].p, cell_verts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   int max_distinct = 1;
   for (const CoreEntryRt& e : g_cores)
     if (e.n == dim && (tile_core_variant() == 1 || e.variant == 0)) max_distinct = std::max(max_distinct, e.ndistinct);

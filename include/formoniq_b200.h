@@ -62,6 +62,9 @@ int64_t fq_ctx_launch_count(const fq_ctx* ctx);
 /* per-kernel device timing: when on, the hot kernels are bracketed with CUDA
  * events on the context's stream; the report is a JSON object
  * {"kernel": {"ms": total, "count": launches}, ...} and resets the spans. */
+/* Device memory released by the library is kept in a process-wide cache for reuse (multi-GB cudaMalloc/cudaFree
+ * calls synchronise the device and cost tens of milliseconds); this hands the cached blocks back to the driver. */
+int fq_device_cache_trim(void);
 int fq_ctx_set_timing(fq_ctx* ctx, int on);
 int fq_ctx_timing_report(fq_ctx* ctx, char* buf, size_t buflen);
 
