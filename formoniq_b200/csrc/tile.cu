@@ -645,7 +645,9 @@ __global__ void row_tile_kernel(const uint32_t* __restrict__ faces, int nl, cons
 // sort key of every structural non-zero: tile | L | signature of its slot sequence
 __global__ void nnz_key_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nrows, const uint32_t* __restrict__ row_tile,
                                const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
-                               int use_sig, uint64_t* __restrict__ key, uint32_t* __restrict__ nnz_id, int* __restrict__ err) {
+                               int use_sig, const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
+                               const uint32_t* __restrict__ tile_local, uint64_t* __restrict__ key,
+                               uint32_t* __restrict__ nnz_id, int* __restrict__ err) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
     const uint64_t t = row_tile[r];
@@ -665,15 +667,44 @@ __global__ void nnz_key_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nr
         }
       }
       sig = (sig ^ (sig >> 16)) & 0xFFFFu;
-      key[q] = (t << 24) | (uint64_t(L) << 16) | sig;
+      // shared-memory bank (8-byte units, 16 per wavefront) of the slab slot of the first contributing cell
+      uint32_t bank = 0;
+      if (tile_local) {
+        const uint32_t cell = contrib_src[p0] / T;
+        uint32_t lo = tile_cell_ptr[t], hi = tile_cell_ptr[t + 1];
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (tile_cells[mid] < cell)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        bank = tile_local[lo] & 15u;
+      }
+      // tile | L | signature | occurrence (filled in later) | bank
+      key[q] = (t << 36) | (uint64_t(L) << 28) | (uint64_t(sig) << 12) | bank;
       nnz_id[q] = q;
     }
+  }
+}
+// Bank interleaving: within a group of equal (tile, L, signature, bank) the k-th member gets occurrence k; sorting by
+// (.., occurrence, bank) then makes consecutive lanes of a record hit different banks of the slab.
+__global__ void group_start_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ start) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    start[i] = (i == 0 || key[i] != key[i - 1]) ? i : 0u;
+}
+__global__ void occurrence_kernel(uint64_t* __restrict__ key, uint32_t n, const uint32_t* __restrict__ start_scan) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t occ = min(i - start_scan[i], 255u);
+    key[i] |= uint64_t(occ) << 4;
   }
 }
 __global__ void run_heads_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ head) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    head[i] = (i == 0 || (key[i] >> 16) != (key[i - 1] >> 16)) ? 1u : 0u;
+    head[i] = (i == 0 || (key[i] >> 28) != (key[i - 1] >> 28)) ? 1u : 0u;
 }
 // run r: start, tile, L
 __global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ head,
@@ -684,8 +715,8 @@ __global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t
     if (head[i]) {
       const uint32_t r = run_scan[i] - 1;
       run_start[r] = i;
-      run_tile[r] = uint32_t(key[i] >> 24);
-      run_len_code[r] = uint32_t(key[i] >> 16) & 0xFFu;
+      run_tile[r] = uint32_t(key[i] >> 36);
+      run_len_code[r] = uint32_t(key[i] >> 28) & 0xFFu;
     }
 }
 __global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
@@ -1071,7 +1102,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   plan->launch = core->launch;
   plan->ntiles = uint32_t(mesh->ntiles);
   plan->nthreads = cfg.nthreads;
-  if (plan->ntiles >= (1u << 30)) return nullptr;
+  if (plan->ntiles >= (1u << 27)) return nullptr;
   // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)
   std::vector<std::vector<uint8_t>> codes8(static_cast<size_t>(nblocks));
   size_t recipe_u16 = 0;
@@ -1196,7 +1227,9 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     plan->recipe_bytes = int(recipe_bytes);
   }
   // ---- per block: non-zeros sorted by (tile, L, signature), cut into warp records
-  const int use_sig = std::getenv("FQ_TILE_SIG") ? std::atoi(std::getenv("FQ_TILE_SIG")) : 1;
+  // orderings inside a (tile, L) run — measured neutral on B200 (the gathers stay scattered), off by default
+  const int use_sig = std::getenv("FQ_TILE_SIG") ? std::atoi(std::getenv("FQ_TILE_SIG")) : 0;
+  const bool use_bank = std::getenv("FQ_TILE_BANK") ? std::atoi(std::getenv("FQ_TILE_BANK")) != 0 : false;
   DevBuf<int> d_err(1);
   FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
   std::vector<BlockBuild> bb(static_cast<size_t>(nblocks));
@@ -1228,11 +1261,23 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     DevBuf<uint64_t> key(s_nnz);
     B.perm.alloc(s_nnz);
     nnz_key_kernel<<<grid_for(nrows_local, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        csr->s_row_ptr.p, uint32_t(nrows_local), row_tile.p, csr->contrib_ptr.p, csr->contrib_src.p, T, use_sig, key.p,
-        B.perm.p, d_err.p);
+        csr->s_row_ptr.p, uint32_t(nrows_local), row_tile.p, csr->contrib_ptr.p, csr->contrib_src.p, T, use_sig,
+        use_bank ? plan->tile_cell_ptr.p : nullptr, tile_cells.p, use_bank ? tile_local.p : nullptr, key.p, B.perm.p, d_err.p);
     fq_count_launch(ctx, 2);
     FQ_CUDA(cudaGetLastError());
-    radix_sort_pairs_u64(ctx, key, B.perm, s_nnz, 24 + bits_for32(plan->ntiles));
+    radix_sort_pairs_u64(ctx, key, B.perm, s_nnz, 36 + bits_for32(plan->ntiles));
+    if (use_bank) {
+      DevBuf<uint32_t> gstart(s_nnz), gscan(s_nnz);
+      group_start_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), gstart.p);
+      size_t tmp_bytes = 0;
+      FQ_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, gstart.p, gscan.p, cub::Max(), int64_t(s_nnz), ctx->stream));
+      DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+      FQ_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, gstart.p, gscan.p, cub::Max(), int64_t(s_nnz), ctx->stream));
+      occurrence_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), gscan.p);
+      fq_count_launch(ctx, 4);
+      FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      radix_sort_pairs_u64(ctx, key, B.perm, s_nnz, 36 + bits_for32(plan->ntiles));
+    }
     DevBuf<uint32_t> head(s_nnz);
     B.run_scan.alloc(s_nnz);
     run_heads_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), head.p);
