@@ -241,8 +241,29 @@ def run_b200(args):
         s1.record(stream)
         barrier()
         kr = ctx.timing_report().get("k4_spmv", {"ms": 0.0, "count": 1})
-        spmv.append({"block": name, "ms": s0.elapsed_time(s1) / args.steps, "kernel_ms": kr["ms"] / max(kr["count"], 1),
-                     "bytes": a.spmv_bytes - 8 * a.shape[1] + 8 * (r.held_hi - r.held_lo), "nnz": a.nnz})
+        entry = {"block": name, "ms": s0.elapsed_time(s1) / args.steps, "kernel_ms": kr["ms"] / max(kr["count"], 1),
+                 "bytes": a.spmv_bytes - 8 * a.shape[1] + 8 * (r.held_hi - r.held_lo), "nnz": a.nnz, "peer_ms": None}
+        if world > 1 and not args.no_peer:
+            # the same product with the exchange fused into the SpMV: neighbours' columns are loaded over NVLink
+            # (CUDA IPC peer memory) by the gather itself; epoch flags order it against the producers of x
+            from formoniq_b200.dist import PeerHalo
+
+            xv = fq.DeviceVector(ctx, r.held_hi - r.held_lo)
+            fq._lib.check(fq._lib.lib().fq_vec_copy(ctx._h, xv._h, x._h))
+            ph = PeerHalo(ctx, part, rank, xv)
+            for _ in range(max(args.warmup, 1)):
+                ph.publish(); ph.apply(a, y); ph.release()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(args.steps):
+                ph.publish(); ph.apply(a, y); ph.release()
+            p1.record(stream)
+            barrier()
+            ph.check()
+            entry["peer_ms"] = p0.elapsed_time(p1) / args.steps
+            del ph, xv
+        spmv.append(entry)
         del x, y, xw
 
     # ---- reduce over ranks (max time, sum of work)
@@ -263,6 +284,7 @@ def run_b200(args):
     ms_total = allmax(ms_total)
     cells_all, nnz_all, bytes_all = allsum(owned_cells), allsum(nnz_local), allsum(asm_bytes)
     spmv_ms = [allmax(s["ms"]) for s in spmv]
+    peer_ms = [allmax(s["peer_ms"]) if s["peer_ms"] is not None else None for s in spmv]
     spmv_bytes = [allsum(s["bytes"]) for s in spmv]
     secs = ms_total / 1e3
     value = cells_all * args.steps / secs
@@ -302,7 +324,11 @@ def run_b200(args):
         "spmv": {"block": spmv[big]["block"], "gbs": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3),
                  "ms": spmv_ms[big], "frac_of_hbm_peak": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3) / (peak * world),
                  "all_blocks_gbs": sum(spmv_bytes) / 1e9 / (sum(spmv_ms) / 1e3),
-                 "halo_exchange": "torch.distributed NCCL send/recv with z-neighbours" if world > 1 else "none (1 GPU)"},
+                 "halo_exchange": "torch.distributed NCCL send/recv with z-neighbours" if world > 1 else "none (1 GPU)",
+                 "fused_peer_ms": peer_ms[big],
+                 "fused_peer_gbs": (spmv_bytes[big] / 1e9 / (peer_ms[big] / 1e3)) if peer_ms[big] else None,
+                 "fused_peer": "one kernel: halo columns loaded from the neighbours' HBM over NVLink (CUDA IPC) inside the "
+                               "SpMV gather, epoch flags instead of a collective" if world > 1 else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "kernel": ("tile_assemble_kernel: K1 element masses + K3 segmented reduction fused in shared memory, "
@@ -402,6 +428,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning runs only)")
+    ap.add_argument("--no-peer", action="store_true", help="skip the fused peer-memory SpMV measurement (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

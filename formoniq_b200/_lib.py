@@ -79,6 +79,12 @@ SIGNATURES = [
     ("fq_vec_device_ptr", _vp, [_vp]),
     ("fq_spmv", _i, [_vp, _vp, _vp, _vp]),
     ("fq_spmv_window", _i, [_vp, _vp, _vp, _sz, _vp]),
+    ("fq_vec_ipc_export", _i, [_vp, _vp, _vp]),
+    ("fq_vec_ipc_import", _i, [_vp, _vp, _sz, _P(_vp)]),
+    ("fq_spmv_peer", _i, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _sz, _vp]),
+    ("fq_flag_signal", _i, [_vp, _vp, _d]),
+    ("fq_flag_wait", _i, [_vp, _vp, _d]),
+    ("fq_flag_check", _i, [_vp]),
     ("fq_cg", _i, [_vp, _vp, _i, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
     ("fq_minres", _i, [_vp, _vp, _i, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
 ]

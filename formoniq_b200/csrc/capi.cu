@@ -610,8 +610,61 @@ int fq_vec_wrap(fq_ctx* ctx, void* device_ptr, size_t n, fq_vec** out) {
   FQ_API_END
 }
 int fq_vec_destroy(fq_vec* v) {
+  if (v && v->ipc_base) cudaIpcCloseMemHandle(v->ipc_base);
   delete v;
   return FQ_OK;
+}
+int fq_vec_ipc_export(fq_ctx* ctx, const fq_vec* v, unsigned char* handle64) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && v && handle64 && v->d.p, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  FQ_CUDA(cudaIpcGetMemHandle(&h, v->d.p));
+  std::memcpy(handle64, &h, 64);
+  FQ_API_END
+}
+int fq_vec_ipc_import(fq_ctx* ctx, const unsigned char* handle64, size_t n, fq_vec** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && handle64 && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  FQ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  std::unique_ptr<fq_vec> v(new fq_vec);
+  v->d.p = static_cast<double*>(p);
+  v->d.n = n;
+  v->d.owned = false;
+  v->ipc_base = p;
+  *out = v.release();
+  FQ_API_END
+}
+int fq_flag_signal(fq_ctx* ctx, fq_vec* flag, double value) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && flag && flag->d.n >= 1, "null argument");
+  flag_signal(ctx, flag->d.p, value);
+  FQ_API_END
+}
+int fq_flag_wait(fq_ctx* ctx, const fq_vec* flag, double value) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && flag && flag->d.n >= 1, "null argument");
+  if (ctx->d_flag_timeout.n != 1) {
+    ctx->d_flag_timeout.alloc(1);
+    FQ_CUDA(cudaMemsetAsync(ctx->d_flag_timeout.p, 0, sizeof(int), ctx->stream));
+  }
+  flag_wait(ctx, flag->d.p, value, ctx->d_flag_timeout.p);
+  FQ_API_END
+}
+int fq_flag_check(fq_ctx* ctx) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx, "null argument");
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_flag_timeout.n == 1) {
+    int h = 0;
+    FQ_CUDA(cudaMemcpy(&h, ctx->d_flag_timeout.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) throw Error(FQ_ERR_CUDA, "a peer flag wait timed out");
+  }
+  FQ_API_END
 }
 size_t fq_vec_len(const fq_vec* v) { return v ? v->d.n : 0; }
 int fq_vec_upload(fq_ctx* ctx, fq_vec* v, const double* host) {
@@ -673,6 +726,22 @@ int fq_spmv_window(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, size_t x_lo, f
   spmv_prepare(ctx, const_cast<fq_csr*>(a));
   // column ids are global: shift the base so that x[col] addresses the window
   spmv_apply(ctx, a, x->d.p - x_lo, y->d.p);
+  FQ_API_END
+}
+
+int fq_spmv_peer(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t held_lo, size_t own_lo, size_t own_hi,
+                 const fq_vec* x_lower, size_t lower_held_lo, const fq_vec* x_upper, size_t upper_held_lo, fq_vec* y) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && x_window && y, "null argument");
+  FQ_REQUIRE(held_lo <= own_lo && own_lo <= own_hi && own_hi <= a->ncols, "spmv_peer: bad ranges");
+  FQ_REQUIRE(y->d.n == a->row_end - a->row_begin, "spmv_peer: dimension mismatch");
+  FQ_REQUIRE(x_window != y, "spmv: x and y must be distinct");
+  spmv_prepare(ctx, const_cast<fq_csr*>(a));
+  // pointers pre-offset so that ptr[global column] addresses the right window
+  const double* own = x_window->d.p - held_lo;
+  const double* lower = x_lower ? x_lower->d.p - lower_held_lo : own;
+  const double* upper = x_upper ? x_upper->d.p - upper_held_lo : own;
+  spmv_apply_peer(ctx, a, own, lower, upper, x_lower ? own_lo : 0, x_upper ? own_hi : a->ncols, y->d.p);
   FQ_API_END
 }
 

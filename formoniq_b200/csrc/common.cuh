@@ -101,6 +101,7 @@ struct fq_ctx {
   int64_t launches = 0;
   fq::DevBuf<double> reduce_scratch;  // two-stage reductions
   double* host_scalar = nullptr;      // pinned
+  fq::DevBuf<int> d_flag_timeout;     // raised by a peer-flag wait that gave up
   // optional per-kernel timing (CUDA events on the launching stream)
   bool timing = false;
   std::vector<std::string> span_names;
@@ -167,6 +168,7 @@ struct fq_mesh {
 
 struct fq_vec {
   fq::DevBuf<double> d;
+  void* ipc_base = nullptr;  // non-null: d.p is a CUDA IPC mapping of a peer's vector (closed on destroy)
 };
 
 // One block's symbolic data: structural pattern + gather lists.

@@ -15,9 +15,68 @@ namespace fq {
 
 struct SpmvPolicy {
   static constexpr bool kHasValues = true;
+  static constexpr bool kCustomSrc = false;
   double* __restrict__ y;
+  __device__ __forceinline__ double load(uint32_t) const { return 0.0; }
   __device__ __forceinline__ void store(uint32_t row, double sum, bool) const { y[row] = sum; }
 };
+
+// SpMV fused with the halo exchange: x lives distributed over the ranks' windows; columns below / above this rank's
+// owned range are loaded straight from the neighbouring GPU's memory (CUDA IPC mapping, NVLink 5 / NVSwitch P2P
+// loads issued by the gather itself), so the transfer overlaps the row blocks that do not need it — there is no
+// separate exchange step and no staging copy.  Pointers are pre-offset so that ptr[global column] is valid.
+struct SpmvPeerPolicy {
+  static constexpr bool kHasValues = true;
+  static constexpr bool kCustomSrc = true;
+  double* __restrict__ y;
+  const double* own;    // this rank's window
+  const double* lower;  // rank - 1's window (columns < own_lo)
+  const double* upper;  // rank + 1's window (columns >= own_hi)
+  uint32_t own_lo, own_hi;
+  __device__ __forceinline__ double load(uint32_t col) const {
+    const double* p = col < own_lo ? lower : (col >= own_hi ? upper : own);
+    return p[col];  // plain ld.global: peer memory is not read through the non-coherent path
+  }
+  __device__ __forceinline__ void store(uint32_t row, double sum, bool) const { y[row] = sum; }
+};
+
+void spmv_apply_peer(fq_ctx* ctx, const fq_csr* a, const double* own, const double* lower, const double* upper, size_t own_lo,
+                     size_t own_hi, double* y) {
+  FQ_REQUIRE(a->spmv_ready, "spmv_prepare was not called");
+  if (a->nrowblocks == 0) return;
+  ScopedSpan span(ctx, "k4_spmv_peer");
+  stream_reduce(ctx, a->rowblocks.p, a->nrowblocks, a->row_ptr.p, a->col_idx.p, a->values.p, nullptr,
+                SpmvPeerPolicy{y, own, lower, upper, uint32_t(own_lo), uint32_t(own_hi)});
+}
+
+// Stream-ordered flags in (peer-mapped) device memory: the producer of x publishes an epoch after its last write,
+// the consumers wait for it before the fused SpMV reads x over NVLink.
+__global__ void flag_signal_kernel(volatile double* flag, double value) {
+  __threadfence_system();
+  *flag = value;
+  __threadfence_system();
+}
+__global__ void flag_wait_kernel(const volatile double* flag, double value, int* timeout) {
+  long long spins = 0;
+  while (*flag < value) {
+    __nanosleep(200);
+    if (++spins > (1ll << 24)) {  // ~3 s: never hang the device on a lost peer
+      *timeout = 1;
+      return;
+    }
+  }
+  __threadfence_system();
+}
+void flag_signal(fq_ctx* ctx, double* flag, double value) {
+  flag_signal_kernel<<<1, 1, 0, ctx->stream>>>(flag, value);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
+void flag_wait(fq_ctx* ctx, const double* flag, double value, int* d_timeout) {
+  flag_wait_kernel<<<1, 1, 0, ctx->stream>>>(flag, value, d_timeout);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
 
 void spmv_prepare(fq_ctx* ctx, fq_csr* a) {
   if (a->spmv_ready) return;

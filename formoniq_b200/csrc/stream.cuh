@@ -64,6 +64,8 @@ inline void stream_build_blocks(fq_ctx* ctx, const uint32_t* seg_ptr, size_t nse
 
 // Policy interface:
 //   static constexpr bool kHasValues;
+//   static constexpr bool kCustomSrc;   // true: the gathered operand comes from policy.load(index) instead of src[index]
+//   __device__ double load(uint32_t index) const;
 //   __device__ void store(uint32_t seg, double sum, bool any_nonzero) const;
 template <class Policy>
 __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uint32_t* __restrict__ blocks,
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
           const uint32_t k = base + u * kStreamThreads + threadIdx.x;
-          g[u] = k < cnt ? __ldg(src + idx[u]) : 0.0;
+          g[u] = k < cnt ? (Policy::kCustomSrc ? policy.load(idx[u]) : __ldg(src + idx[u])) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
@@ -146,7 +148,8 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
         double acc = 0.0;
         int any = 0;
         for (uint32_t p = b0 + threadIdx.x; p < b1; p += kStreamThreads) {
-          const double g = __ldg(src + __ldg(index + p));
+          const uint32_t ip = __ldg(index + p);
+          const double g = Policy::kCustomSrc ? policy.load(ip) : __ldg(src + ip);
           const double v = Policy::kHasValues ? __dmul_rn(__ldg(values + p), g) : g;
           any |= (v != 0.0);
           acc = __dadd_rn(acc, v);

@@ -84,3 +84,95 @@ def exchange_halo(window, part: SlabPartition, rank: int, group=None):
         ops.append(dist.P2POp(dist.irecv, window[lo - base:hi - base], peer, group=group))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+class PeerHalo:
+    """SpMV fused with the halo exchange over peer memory (NVLink 5 / NVSwitch).
+
+    Every rank keeps x as a window vector [held_lo, held_hi) allocated by the library; the windows and two
+    epoch flags per rank are mapped into the neighbouring processes with CUDA IPC.  `apply` runs ONE kernel
+    whose gather loads the columns owned by rank-1 / rank+1 straight from their windows (P2P loads), so no halo
+    is ever copied and the NVLink traffic overlaps the row blocks that do not need it.
+
+        ph = PeerHalo(ctx, part, rank, x_window)        # collective: exchanges the IPC handles
+        ph.publish()                                     # after this rank finished writing its owned x
+        y = ph.apply(a, y)                               # waits for the neighbours' epoch, then the fused SpMV
+        ph.release()                                     # before x is overwritten again: neighbours are done reading
+    """
+
+    def __init__(self, ctx, part: SlabPartition, rank: int, x_window, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _lib
+        from .api import DeviceVector
+
+        self.ctx, self.part, self.rank, self.x, self.group = ctx, part, rank, x_window, group
+        self.epoch = 0
+        self.ready = DeviceVector(ctx, 1)     # epoch of the last published x
+        self.consumed = DeviceVector(ctx, 1)  # epoch this rank has finished reading from its neighbours
+        L = _lib.lib()
+
+        def export(v):
+            buf = (C.c_ubyte * 64)()
+            _lib.check(L.fq_vec_ipc_export(ctx._h, v._h, C.cast(buf, C.c_void_p)))
+            return bytes(buf)
+
+        mine = {"x": export(x_window), "ready": export(self.ready), "consumed": export(self.consumed), "n": len(x_window)}
+        world = part.world
+        table = [None] * world
+        if world > 1:
+            dist.all_gather_object(table, mine, group=group)
+        else:
+            table[0] = mine
+
+        def imp(handle, n):
+            h = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+            _lib.check(L.fq_vec_ipc_import(ctx._h, C.cast(buf, C.c_void_p), n, C.byref(h)))
+            v = DeviceVector.__new__(DeviceVector)
+            v.ctx, v._h, v.n = ctx, h, n
+            return v
+
+        self.peers = {}
+        for peer in (rank - 1, rank + 1):
+            if 0 <= peer < world:
+                t = table[peer]
+                self.peers[peer] = {"x": imp(t["x"], t["n"]), "ready": imp(t["ready"], 1), "consumed": imp(t["consumed"], 1)}
+        if world > 1:
+            dist.barrier(group=group)
+
+    def publish(self):
+        """This rank's owned x entries are final for the next epoch (stream-ordered)."""
+        from . import _lib
+
+        self.epoch += 1
+        _lib.check(_lib.lib().fq_flag_signal(self.ctx._h, self.ready._h, float(self.epoch)))
+
+    def apply(self, a, y):
+        """y = A x with the neighbours' columns read over NVLink inside the SpMV kernel."""
+        from . import _lib
+
+        L = _lib.lib()
+        r = self.part.ranges[self.rank]
+        for p in self.peers.values():
+            _lib.check(L.fq_flag_wait(self.ctx._h, p["ready"]._h, float(self.epoch)))
+        lo, hi = self.peers.get(self.rank - 1), self.peers.get(self.rank + 1)
+        _lib.check(L.fq_spmv_peer(self.ctx._h, a._h, self.x._h, r.held_lo, r.own_lo, r.own_hi,
+                                  lo["x"]._h if lo else None, self.part.ranges[self.rank - 1].held_lo if lo else 0,
+                                  hi["x"]._h if hi else None, self.part.ranges[self.rank + 1].held_lo if hi else 0, y._h))
+        _lib.check(L.fq_flag_signal(self.ctx._h, self.consumed._h, float(self.epoch)))
+        return y
+
+    def release(self):
+        """Wait until the neighbours have finished reading this rank's x of the current epoch."""
+        from . import _lib
+
+        for p in self.peers.values():
+            _lib.check(_lib.lib().fq_flag_wait(self.ctx._h, p["consumed"]._h, float(self.epoch)))
+
+    def check(self):
+        from . import _lib
+
+        _lib.check(_lib.lib().fq_flag_check(self.ctx._h))

@@ -187,6 +187,25 @@ int fq_spmv(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, fq_vec* y);
  * column space (owned segment + halos of a row-partitioned operator). */
 int fq_spmv_window(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, size_t x_lo, fq_vec* y);
 
+/* ---- SpMV fused with the halo exchange (one process per GPU, NVLink 5 / NVSwitch peer memory) -----------------
+ * The reference is single-process; under the owner-computes row partition the only exchange step of the path is
+ * the x halo of `LinearOperator::apply`.  Instead of exchanging halos and then multiplying, the gather of the SpMV
+ * loads the columns owned by the neighbouring ranks directly from their windows over NVLink:
+ *   fq_vec_ipc_export / fq_vec_ipc_import  map a peer rank's vector (64-byte CUDA IPC handle, shipped by the caller,
+ *                                          e.g. with torch.distributed.all_gather_object)
+ *   fq_spmv_peer   y = A x; x_window covers [held_lo, ..) of this rank, columns < own_lo come from x_lower (the
+ *                  window of rank-1, starting at lower_held_lo), columns >= own_hi from x_upper; NULL = no neighbour
+ *   fq_flag_signal / fq_flag_wait  stream-ordered epoch flags in peer-mapped memory: a rank signals after its last
+ *                  write of x and waits for its neighbours' epochs before the fused SpMV reads them (and the
+ *                  reverse before x is overwritten); fq_flag_check reports a wait that timed out (~3 s). */
+int fq_vec_ipc_export(fq_ctx* ctx, const fq_vec* v, unsigned char* handle64);
+int fq_vec_ipc_import(fq_ctx* ctx, const unsigned char* handle64, size_t n, fq_vec** out);
+int fq_spmv_peer(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t held_lo, size_t own_lo, size_t own_hi,
+                 const fq_vec* x_lower, size_t lower_held_lo, const fq_vec* x_upper, size_t upper_held_lo, fq_vec* y);
+int fq_flag_signal(fq_ctx* ctx, fq_vec* flag, double value);
+int fq_flag_wait(fq_ctx* ctx, const fq_vec* flag, double value);
+int fq_flag_check(fq_ctx* ctx);
+
 /* ---- Krylov drivers on device vectors (iterative/src/krylov.rs:48-95, 113-211).
  * precond: 0 identity (iterative/src/precond.rs:16-41), 1 Jacobi (:113-121).
  * report: iters, residual, converged (iterative/src/lib.rs:212-219). */

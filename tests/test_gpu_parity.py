@@ -517,3 +517,19 @@ def test_tile_fused_on_slabs_tiles_the_global_matrix(fq, ctx):
             got, exp = blk.to_scipy(), ref[b:e]
             assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
             assert np.array_equal(got.data, exp.data)
+
+
+def test_spmv_fused_with_the_halo_exchange_over_peer_memory(fq):
+    # needs two GPUs on the box (skipped on the 1-GPU round-end run): one process per GPU under torchrun; the fused
+    # kernel loads the neighbours' columns over NVLink and must equal NCCL exchange + windowed SpMV bit for bit
+    import os
+    import subprocess
+    import sys
+
+    if fq._lib.lib().fq_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "scripts", "peer_spmv_check.py"), "--size", "12", "--reps", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert "PEER_SPMV_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
