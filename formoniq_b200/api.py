@@ -340,6 +340,11 @@ class DeviceCsr:
         check(_lib.lib().fq_csr_download(self.ctx._h, self._h, _p(rp), _p(ci), _p(va)))
         return rp, ci, va
 
+    def transpose(self) -> "DeviceCsr":
+        h = C.c_void_p()
+        check(_lib.lib().fq_csr_transpose(self.ctx._h, self._h, C.byref(h)))
+        return DeviceCsr(self.ctx, h)
+
     def to_scipy(self):
         import scipy.sparse as sp
 
@@ -501,8 +506,13 @@ class HodgeBlocks:
         hb.numeric(mesh, drop_exact_zeros)
         return hb
 
-    def mixed_hodge_laplacian(self):
-        """[[M_{k-1}, -dif_test], [dif_test^T, dif_both]] stitched on the host (scipy) and uploaded."""
+    def mixed_hodge_laplacian(self, on_device: bool = True):
+        """[[M_{k-1}, -dif_test], [dif_test^T, dif_both]] (hodge.rs:93-99), stitched on the device
+        (on_device=False: on the host with scipy, then uploaded — the cross-check of the tests)."""
+        if on_device:
+            h = C.c_void_p()
+            check(_lib.lib().fq_hodge_mixed_laplacian(self.mass_u.ctx._h, self._plan._h, C.byref(h)))
+            return DeviceCsr(self.mass_u.ctx, h)
         import scipy.sparse as sp
 
         ms, dt, db = self.mass_sigma.to_scipy(), self.dif_test.to_scipy(), self.dif_both.to_scipy()

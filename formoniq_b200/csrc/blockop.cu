@@ -1,0 +1,130 @@
+// blockop.cu — block operators built on the device from assembled blocks.
+//
+// HodgeBlocks::mixed_hodge_laplacian (formoniq/src/hodge.rs:93-99) stitches
+//     [[ M_{k-1},  -dif_test   ],
+//      [ dif_test^T,  dif_both ]]
+// through CooMatrixExt::block (simplicial/src/linalg.rs:110-167) and one more serial
+// COO -> CSR conversion.  Here the transpose is a stable radix sort by column and the
+// stitching is a row-wise concatenation, both on the device; entries are copied (or
+// negated) exactly, so the result is bit-identical to the reference's stitched matrix.
+#include <cub/cub.cuh>
+
+#include "internal.hpp"
+
+namespace fq {
+
+__global__ void expand_rows_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nrows, uint32_t* __restrict__ row_of,
+                                   uint32_t* __restrict__ id) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride)
+    for (uint32_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p) row_of[p] = r, id[p] = p;
+}
+__global__ void transpose_fill_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ row_of,
+                                      const double* __restrict__ val, uint32_t nnz, uint32_t* __restrict__ col_t,
+                                      double* __restrict__ val_t) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    const uint32_t p = perm[i];
+    col_t[i] = row_of[p];
+    val_t[i] = val[p];
+  }
+}
+// row_ptr[r] = first i with key[i] >= r  (keys sorted)
+__global__ void lower_bound_ptr_kernel(const uint32_t* __restrict__ key, uint32_t n, uint32_t nrows, uint32_t* __restrict__ ptr) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i <= n; i += stride) {
+    const uint32_t hi = (i == n) ? nrows : key[i];
+    const uint32_t lo = (i == 0) ? 0u : key[i - 1] + 1;
+    for (uint32_t r = lo; r <= hi && r <= nrows; ++r) ptr[r] = uint32_t(i);
+  }
+}
+
+void csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr* out) {
+  FQ_REQUIRE(a->row_begin == 0 && a->row_end == a->nrows, "transpose needs a fully held matrix");
+  const uint32_t nnz = uint32_t(a->nnz), nrows = uint32_t(a->nrows), ncols = uint32_t(a->ncols);
+  out->nrows = ncols;
+  out->ncols = nrows;
+  out->row_begin = 0;
+  out->row_end = ncols;
+  out->nnz = nnz;
+  out->row_ptr.alloc(size_t(ncols) + 1);
+  out->col_idx.alloc(nnz ? nnz : 1);
+  out->values.alloc(nnz ? nnz : 1);
+  if (nnz == 0) {
+    FQ_CUDA(cudaMemsetAsync(out->row_ptr.p, 0, out->row_ptr.bytes(), ctx->stream));
+    return;
+  }
+  const int block = 256;
+  DevBuf<uint32_t> row_of(nnz), id(nnz), keys(nnz), keys_alt(nnz), id_alt(nnz);
+  expand_rows_kernel<<<grid_for(nrows, block, ctx->sm_count), block, 0, ctx->stream>>>(a->row_ptr.p, nrows, row_of.p, id.p);
+  FQ_CUDA(cudaMemcpyAsync(keys.p, a->col_idx.p, size_t(nnz) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  cub::DoubleBuffer<uint32_t> dk(keys.p, keys_alt.p), dv(id.p, id_alt.p);
+  int end_bit = 1;
+  while ((1ull << end_bit) < ncols) ++end_bit;
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, int64_t(nnz), 0, end_bit, ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, int64_t(nnz), 0, end_bit, ctx->stream));  // stable
+  transpose_fill_kernel<<<grid_for(nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(dv.Current(), row_of.p, a->values.p, nnz,
+                                                                                      out->col_idx.p, out->values.p);
+  lower_bound_ptr_kernel<<<grid_for(size_t(nnz) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(dk.Current(), nnz, ncols,
+                                                                                                   out->row_ptr.p);
+  fq_count_launch(ctx, 8);
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// out = [[a00, s01 * a01], [a10, a11]] with a01: n0 x n1, a10: n1 x n0
+__global__ void block2x2_ptr_kernel(const uint32_t* __restrict__ p00, const uint32_t* __restrict__ p01,
+                                    const uint32_t* __restrict__ p10, const uint32_t* __restrict__ p11, uint32_t n0, uint32_t n1,
+                                    uint32_t* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t top = p00[n0] + p01[n0];
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= n0 + n1; r += stride)
+    out[r] = r <= n0 ? p00[r] + p01[r] : top + p10[r - n0] + p11[r - n0];
+}
+__global__ void block2x2_fill_kernel(const uint32_t* __restrict__ pa, const uint32_t* __restrict__ ca, const double* __restrict__ va,
+                                     double sa, uint32_t shift_a, const uint32_t* __restrict__ pb,
+                                     const uint32_t* __restrict__ cb, const double* __restrict__ vb, double sb, uint32_t shift_b,
+                                     uint32_t nrows, uint32_t row_shift, const uint32_t* __restrict__ out_ptr,
+                                     uint32_t* __restrict__ out_col, double* __restrict__ out_val) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    uint32_t o = out_ptr[r + row_shift];
+    for (uint32_t p = pa[r]; p < pa[r + 1]; ++p, ++o) out_col[o] = ca[p] + shift_a, out_val[o] = sa < 0 ? -va[p] : va[p];
+    for (uint32_t p = pb[r]; p < pb[r + 1]; ++p, ++o) out_col[o] = cb[p] + shift_b, out_val[o] = sb < 0 ? -vb[p] : vb[p];
+  }
+}
+
+void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01, const fq_csr* a10, const fq_csr* a11,
+                  fq_csr* out) {
+  const size_t n0 = a00->nrows, n1 = a11->nrows;
+  FQ_REQUIRE(a00->ncols == n0 && a11->ncols == n1 && a01->nrows == n0 && a01->ncols == n1 && a10->nrows == n1 && a10->ncols == n0,
+             "block shapes do not fit");
+  for (const fq_csr* b : {a00, a01, a10, a11}) FQ_REQUIRE(b->row_begin == 0 && b->row_end == b->nrows, "blocks must be fully held");
+  const size_t nnz = a00->nnz + a01->nnz + a10->nnz + a11->nnz;
+  FQ_REQUIRE(nnz < (size_t(1) << 32) && n0 + n1 < (size_t(1) << 32), "block matrix too large for 32-bit indices");
+  out->nrows = out->ncols = n0 + n1;
+  out->row_begin = 0;
+  out->row_end = n0 + n1;
+  out->nnz = nnz;
+  out->row_ptr.alloc(n0 + n1 + 1);
+  out->col_idx.alloc(nnz ? nnz : 1);
+  out->values.alloc(nnz ? nnz : 1);
+  const int block = 256;
+  block2x2_ptr_kernel<<<grid_for(n0 + n1 + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      a00->row_ptr.p, a01->row_ptr.p, a10->row_ptr.p, a11->row_ptr.p, uint32_t(n0), uint32_t(n1), out->row_ptr.p);
+  if (n0)
+    block2x2_fill_kernel<<<grid_for(n0, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        a00->row_ptr.p, a00->col_idx.p, a00->values.p, 1.0, 0u, a01->row_ptr.p, a01->col_idx.p, a01->values.p, s01, uint32_t(n0),
+        uint32_t(n0), 0u, out->row_ptr.p, out->col_idx.p, out->values.p);
+  if (n1)
+    block2x2_fill_kernel<<<grid_for(n1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        a10->row_ptr.p, a10->col_idx.p, a10->values.p, 1.0, 0u, a11->row_ptr.p, a11->col_idx.p, a11->values.p, 1.0, uint32_t(n0),
+        uint32_t(n1), uint32_t(n0), out->row_ptr.p, out->col_idx.p, out->values.p);
+  fq_count_launch(ctx, 3);
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace fq

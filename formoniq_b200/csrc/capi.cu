@@ -515,6 +515,29 @@ int fq_hodge_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_hodge* blocks, int dro
   assemble_numeric_multi(ctx, mesh, ptrs, 4, drop_exact_zeros != 0);
   FQ_API_END
 }
+int fq_csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_csr> t(new fq_csr);
+  csr_transpose(ctx, a, t.get());
+  *out = t.release();
+  FQ_API_END
+}
+int fq_hodge_mixed_laplacian(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && blocks && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  const fq_csr* m_sigma = blocks->blocks[0].get();
+  const fq_csr* dif_test = blocks->blocks[2].get();
+  const fq_csr* dif_both = blocks->blocks[3].get();
+  fq_csr dt_t;
+  csr_transpose(ctx, dif_test, &dt_t);
+  std::unique_ptr<fq_csr> a(new fq_csr);
+  csr_block2x2(ctx, m_sigma, dif_test, -1.0, &dt_t, dif_both, a.get());
+  *out = a.release();
+  FQ_API_END
+}
 fq_csr* fq_hodge_block(fq_hodge* blocks, int which) {
   return (blocks && which >= 0 && which < 4) ? blocks->blocks[which].get() : nullptr;
 }

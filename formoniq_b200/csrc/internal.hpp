@@ -41,6 +41,11 @@ void flag_signal(fq_ctx* ctx, double* flag, double value);
 void flag_wait(fq_ctx* ctx, const double* flag, double value, int* d_timeout);
 void csr_build_inv_diag(fq_ctx* ctx, fq_csr* a);
 
+// ---- blockop.cu
+void csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr* out);
+void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01, const fq_csr* a10, const fq_csr* a11,
+                  fq_csr* out);
+
 // ---- blas1.cu
 double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n);
 void vec_scale(fq_ctx* ctx, double* x, double alpha, size_t n);

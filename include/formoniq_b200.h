@@ -150,6 +150,12 @@ int fq_hodge_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int grade, size_t sigma_
                       size_t u_row_begin, size_t u_row_end, fq_hodge** out);
 int fq_hodge_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_hodge* blocks, int drop_exact_zeros);
 fq_csr* fq_hodge_block(fq_hodge* blocks, int which);
+/* HodgeBlocks::mixed_hodge_laplacian (formoniq/src/hodge.rs:93-99): [[M_{k-1}, -dif_test], [dif_test^T, dif_both]]
+ * stitched on the device (stable transpose + row-wise concatenation instead of CooMatrixExt::block,
+ * simplicial/src/linalg.rs:110-167, and a second COO->CSR); bit-identical entries.  The blocks must be fully held
+ * (single-GPU row range).  fq_csr_transpose is the transpose used for the lower-left block. */
+int fq_hodge_mixed_laplacian(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out);
+int fq_csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr** out);
 int fq_hodge_destroy(fq_hodge* blocks);
 
 /* ---- CSR matrices ----------------------------------------------------------

@@ -533,3 +533,29 @@ def test_spmv_fused_with_the_halo_exchange_over_peer_memory(fq):
            "--master-port", "29533", os.path.join(root, "scripts", "peer_spmv_check.py"), "--size", "12", "--reps", "2"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert "PEER_SPMV_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dim,shape,k", [(2, [7, 6], 1), (3, [4, 3, 5], 1), (3, [3, 3, 3], 2), (2, [5, 5], 2)])
+def test_mixed_hodge_laplacian_stitched_on_the_device(fq, ctx, dim, shape, k):
+    # hodge.rs:93-99: [[M_{k-1}, -dif_test], [dif_test^T, dif_both]]; the device stitching (stable transpose +
+    # row concatenation) must equal the host stitching of the same blocks entry for entry, and its SpMV the host's
+    import scipy.sparse as sp
+
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    hb = fq.HodgeBlocks.compute(mesh, k)
+    ms, dt, db = hb.mass_sigma.to_scipy(), hb.dif_test.to_scipy(), hb.dif_both.to_scipy()
+    exp = sp.bmat([[ms, -dt], [dt.T, db]], format="csr")
+    exp.sort_indices()
+    got = hb.mixed_hodge_laplacian().to_scipy()
+    assert got.shape == exp.shape
+    assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+    assert np.array_equal(got.data, exp.data)
+    # transpose alone, on a rectangular block
+    t = hb.dif_test.transpose().to_scipy()
+    e = dt.T.tocsr()
+    e.sort_indices()
+    assert np.array_equal(t.indptr, e.indptr) and np.array_equal(t.indices, e.indices) and np.array_equal(t.data, e.data)
+    x = np.cos(np.arange(exp.shape[1]) ** 2 + 1.0)
+    y = hb.mixed_hodge_laplacian().apply(fq.DeviceVector.from_numpy(ctx, x)).to_numpy()
+    assert np.abs(y - exp @ x).max() <= 1e-12 * np.abs(exp @ x).max()
