@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libformoniq_b200.so")
+LIB_PATH = os.environ.get("FQ_LIB_PATH") or os.path.join(HERE, "lib", "libformoniq_b200.so")  # FQ_LIB_PATH: tuning builds
 
 FQ_MASS, FQ_DIF_TRIAL, FQ_DIF_TEST, FQ_DIF_BOTH, FQ_LUMPED = 0, 1, 2, 3, 4
 

@@ -51,13 +51,19 @@ constexpr int kTileMaxBlocks = 4;
 // d >= 2 = position d - 2 of csr->values
 constexpr uint32_t kPadDest = 0u;
 constexpr uint32_t kNoDest = 1u;
-constexpr int kChunkBytes = 2048;   // TMA granule of the tile stream; records never straddle a chunk
+#ifndef FQ_TILE_CHUNK_BYTES
+#define FQ_TILE_CHUNK_BYTES 1536
+#endif
+constexpr int kChunkBytes = FQ_TILE_CHUNK_BYTES;  // TMA granule of the tile stream; records never straddle a chunk
 constexpr int kChunkHdr = 16;       // u32 nrec + padding
 constexpr int kRecHdr = 16;         // u32 (L | block << 8 | lanes << 16) + padding
-constexpr int kMaxLen = 61;         // record of 16 + lanes * (4 + 2 L) <= 2032 bytes: 64 lanes up to L = 13, 32 up to 29, 16 up to 61
+// a record is 16 + lanes * (4 + 2 L) bytes and must fit a chunk after its 16-byte header
+constexpr int kMaxLen64 = ((kChunkBytes - 32) / 64 - 4) / 2;   // 2 KB chunks: 64 lanes up to L = 13
+constexpr int kMaxLen32 = ((kChunkBytes - 32) / 32 - 4) / 2;   //              32 lanes up to L = 29
+constexpr int kMaxLen = ((kChunkBytes - 32) / 16 - 4) / 2;     //              16 lanes up to L = 61
 constexpr int kSlotsPerWarp = 2;    // private double buffer of every warp
 
-__host__ __device__ inline uint32_t rec_lanes(uint32_t L) { return L <= 13u ? 64u : (L <= 29u ? 32u : 16u); }
+__host__ __device__ inline uint32_t rec_lanes(uint32_t L) { return L <= uint32_t(kMaxLen64) ? 64u : (L <= uint32_t(kMaxLen32) ? 32u : 16u); }
 __host__ __device__ inline uint32_t rec_bytes(uint32_t L) { return uint32_t(kRecHdr) + rec_lanes(L) * (4u + 2u * L); }
 
 struct TileBlockDev {
@@ -78,6 +84,7 @@ struct TileParams {
   int cstride;                      // cells capacity of the shared slab
   int nblocks;
   uint32_t ring_off, rec_off, mbar_off;  // byte offsets in dynamic shared memory
+  uint32_t slab_bytes;                   // warp-specialised kernel: size of one of its two slabs
   const uint8_t* recipes;           // u16 codes: sign << 15 | distinct * cstride
   int recipe_bytes;
   int debug;                        // development knobs (FQ_TILE_DEBUG): 1 skip K1, 2 skip records, 4 skip stores
@@ -191,6 +198,46 @@ __device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict_
   }
 }
 
+// All records of one chunk of the tile stream, processed by one warp.
+__device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ chunk, const TileParams& P,
+                                             const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane) {
+  const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
+  const unsigned char* rp = chunk + kChunkHdr;
+  for (uint32_t r = 0; r < nrec; ++r) {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
+    const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
+    const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
+    const uint32_t l0 = lane & (stride - 1u);  // lanes beyond a 16-wide record shadow the first ones and never store
+    const uint32_t dest0 = uint32_t(lane) < stride ? destp[l0] : kPadDest;
+    const uint32_t dest1 = stride == 64u ? destp[lane + 32] : kPadDest;
+    const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
+    const uint16_t* __restrict__ ent1 = ent0 + (stride == 64u ? 32 : 0);
+    rp += kRecHdr + stride * (4u + 2u * L);
+    const TileBlockDev& B = P.blk[b];
+    const uint16_t* __restrict__ brec = rec + B.recipe_off;
+    const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
+    double acc0 = 0.0, acc1 = 0.0;
+    bool any0 = false, any1 = false;
+    switch (B.no * 8 + B.ni) {
+      case 0: break;  // zero space: every contribution is an exact zero
+      case 1 * 8 + 1: gather_record_direct(ent0, ent1, stride, L, slab, acc0, acc1, any0, any1); break;
+      case 1 * 8 + 2: gather_record<1, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 1 * 8 + 3: gather_record<1, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 1 * 8 + 4: gather_record<1, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 2 * 8 + 2: gather_record<2, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 3 * 8 + 3: gather_record<3, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      default: gather_record<4, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+    }
+    // padding lanes carry zero entries (they read slab[0]) and never store
+    if (P.check_classification && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) ||
+                                   (dest1 != kPadDest && (dest1 != kNoDest) != any1)))
+      *P.changed = 1;
+    if (P.debug & 4) continue;
+    if (dest0 > kNoDest) B.values[dest0 - 2u] = acc0;
+    if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
+  }
+}
+
 template <class Fn, int NE, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -296,41 +343,7 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
       mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
       lap(2);
       const unsigned char* chunk = myring + (n_consumed & 1u) * kChunkBytes;
-      const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
-      const unsigned char* rp = chunk + kChunkHdr;
-      for (uint32_t r = 0; r < nrec; ++r) {
-        const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
-        const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
-        const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
-        const uint32_t l0 = lane & (stride - 1u);  // lanes beyond a 16-wide record shadow the first ones and never store
-        const uint32_t dest0 = lane < stride ? destp[l0] : kPadDest;
-        const uint32_t dest1 = stride == 64u ? destp[lane + 32] : kPadDest;
-        const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
-        const uint16_t* __restrict__ ent1 = ent0 + (stride == 64u ? 32 : 0);
-        rp += kRecHdr + stride * (4u + 2u * L);
-        const TileBlockDev& B = P.blk[b];
-        const uint16_t* __restrict__ brec = rec + B.recipe_off;
-        const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
-        double acc0 = 0.0, acc1 = 0.0;
-        bool any0 = false, any1 = false;
-        switch (B.no * 8 + B.ni) {
-          case 0: break;  // zero space: every contribution is an exact zero
-          case 1 * 8 + 1: gather_record_direct(ent0, ent1, stride, L, slab, acc0, acc1, any0, any1); break;
-          case 1 * 8 + 2: gather_record<1, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 1 * 8 + 3: gather_record<1, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 1 * 8 + 4: gather_record<1, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 2 * 8 + 2: gather_record<2, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          case 3 * 8 + 3: gather_record<3, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-          default: gather_record<4, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-        }
-        // padding lanes carry zero entries (they read slab[0]) and never store
-        if (P.check_classification && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) ||
-                                       (dest1 != kPadDest && (dest1 != kNoDest) != any1)))
-          *P.changed = 1;
-        if (P.debug & 4) continue;
-        if (dest0 > kNoDest) B.values[dest0 - 2u] = acc0;
-        if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
-      }
+      gather_chunk(chunk, P, slab, rec, lane);
       __syncwarp();  // every lane is done reading the slot before it is refilled
       lap(3);
       ++n_consumed;
@@ -339,6 +352,162 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
   }
   if (prof)
     for (int i = 0; i < 6; ++i) atomicAdd(P.stats + i, (unsigned long long)tk[i]);
+}
+
+
+// ---- warp-specialised variant --------------------------------------------------------------------------------
+// 8 producer warps evaluate the element values of tile i+1 into one of two shared slabs while 16 consumer warps
+// reduce tile i out of the other: the FP64 pipe (K1) and the shared-memory crossbar (gather) work concurrently and
+// no warp idles at a CTA barrier.  setmaxnreg gives the producers the 128 registers the straight-line tape needs
+// and leaves 56 to each consumer (launch: 768 x 80; the consumers release 16*32*24 = the 8*32*48 the producers acquire).  Hand-offs are mbarriers:
+// Measured on B200: 6.7 ms vs 5.8 ms for the phase-serialised kernel (the two slabs halve the tile, K1 of a small tile
+// is latency-bound at ~3 us) - kept behind FQ_TILE_KERNEL=w.
+//   hdr_ready[b]  (1 arrival)   the tile of buffer b is known (consumers start prefetching its stream)
+//   slab_full[b]  (8 arrivals)  every producer warp has stored its cells
+//   slab_empty[b] (16 arrivals) every consumer warp is done with the tile
+constexpr int kWsProducerWarps = 8, kWsConsumerWarps = 16;
+constexpr int kWsThreads = 32 * (kWsProducerWarps + kWsConsumerWarps);
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+template <class Fn, int NE>
+__global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws_kernel(Fn fn, const __grid_constant__ TileParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NEE = NE > 0 ? NE : 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* slabs[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + P.slab_bytes)};
+  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
+  uint64_t* hdr_ready = bars;         // [2]
+  uint64_t* slab_full = bars + 2;     // [2]
+  uint64_t* slab_empty = bars + 4;    // [2]
+  uint64_t* tma_bar = bars + 6;       // [consumer warp][2]
+  __shared__ uint32_t s_hdr[2][8];
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hdr_ready[b], 1);
+      mbar_init(&slab_full[b], kWsProducerWarps);
+      mbar_init(&slab_empty[b], kWsConsumerWarps);
+    }
+    for (int i = 0; i < 2 * kWsConsumerWarps; ++i) mbar_init(&tma_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < P.recipe_bytes / 2; i += kWsThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
+  __syncthreads();
+  if (warp < kWsProducerWarps) {
+    // ------------------------------------------------------------------ producers: K1
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    uint32_t h[5] = {0xFFFFFFFFu, 0, 0, 0, 0};
+    auto fetch = [&]() {  // thread 0: next tile from the dynamic scheduler (latency hidden behind the current K1)
+      h[0] = atomicAdd(P.ticket, 1u);
+      if (h[0] < P.ntiles) {
+        h[1] = __ldg(P.tile_cell_ptr + h[0]);
+        h[2] = __ldg(P.tile_cell_ptr + h[0] + 1);
+        h[3] = __ldg(P.tile_chunk_ptr + h[0]);
+        h[4] = __ldg(P.tile_chunk_ptr + h[0] + 1);
+      }
+    };
+    if (tid == 0) fetch();
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t b = it & 1u, u = it >> 1;
+      if (it >= 2) mbar_wait(&slab_empty[b], (u - 1u) & 1u);  // the consumers left the tile that used this buffer
+      if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s_hdr[b][i] = h[i];
+        mbar_arrive(&hdr_ready[b]);
+      }
+      mbar_wait(&hdr_ready[b], u & 1u);
+      const uint32_t t = s_hdr[b][0];
+      if (t >= P.ntiles) break;
+      const uint32_t cbase = s_hdr[b][1], nc = s_hdr[b][2] - s_hdr[b][1];
+      const bool work = s_hdr[b][4] > s_hdr[b][3];
+      if (tid == 0) fetch();
+      if (work && !(P.debug & 1)) {
+        double* slab = slabs[b];
+        for (uint32_t c = tid; c < nc; c += 32 * kWsProducerWarps) {
+          const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
+          uint32_t eid[NEE];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
+          double s[NEE];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
+          TileSink sink{slab + c, P.cstride};
+          fn(s, sink);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slab_full[b]);
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers: K3
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 16 warps x 24 released = the 12288 registers the producers acquire
+    const int cw = warp - kWsProducerWarps;
+    unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
+    uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
+    uint32_t n_issued = 0, n_consumed = 0;
+    uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t b = it & 1u, u = it >> 1;
+      mbar_wait(&hdr_ready[b], u & 1u);
+      const uint32_t t = s_hdr[b][0];
+      if (t >= P.ntiles) break;
+      const uint32_t c0 = s_hdr[b][3], c1 = s_hdr[b][4];
+      auto issue_more = [&]() {  // keep this warp's double buffer full, crossing into the next tile once it is known
+        while (n_issued - n_consumed < uint32_t(kSlotsPerWarp)) {
+          if (cur_chunk >= cur_end) {
+            if (cur_it == it && mbar_test(&hdr_ready[b ^ 1u], ((it + 1u) >> 1) & 1u) && s_hdr[b ^ 1u][0] < P.ntiles) {
+              cur_it = it + 1;
+              cur_chunk = s_hdr[b ^ 1u][3] + cw;
+              cur_end = s_hdr[b ^ 1u][4];
+              if (cur_chunk >= cur_end) break;
+            } else {
+              break;
+            }
+          }
+          if (lane == 0) {
+            uint64_t* bar = &mybar[n_issued & 1u];
+            mbar_expect_tx(bar, kChunkBytes);
+            tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
+          }
+          cur_chunk += kWsConsumerWarps;
+          ++n_issued;
+        }
+      };
+      if (cur_it != it) {
+        cur_it = it;
+        cur_chunk = c0 + cw;
+        cur_end = c1;
+      }
+      issue_more();
+      mbar_wait(&slab_full[b], u & 1u);
+      const double* slab = slabs[b];
+      for (uint32_t c = c0 + cw; c < c1; c += kWsConsumerWarps) {
+        mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
+        gather_chunk(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane);
+        __syncwarp();
+        ++n_consumed;
+        issue_more();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slab_empty[b]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ plan
@@ -355,6 +524,8 @@ struct TilePlan {
   uint32_t ntiles = 0;
   int cstride = 0;
   int nthreads = 512;
+  bool ws = false;
+  uint32_t slab_bytes = 0;
   size_t smem_bytes = 0;
   uint32_t ring_off = 0, rec_off = 0, mbar_off = 0;
   int recipe_bytes = 0;
@@ -392,8 +563,19 @@ static void launch_tile_nt(fq_ctx* ctx, const TilePlan& plan, const TileParams& 
   tile_assemble_kernel<Fn, NE, NT, MINB><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE>
+static void launch_tile_ws(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_ws_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    attr_set = true;
+  }
+  tile_assemble_ws_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+}
+template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  if (plan.nthreads == 256)
+  if (plan.ws)
+    launch_tile_ws<Fn, NE>(ctx, plan, params);
+  else if (plan.nthreads == 256)
     launch_tile_nt<Fn, NE, 256, 2>(ctx, plan, params);  // two CTAs per SM: one tile's K1 overlaps the other's gather
   else
     launch_tile_nt<Fn, NE, 512, 1>(ctx, plan, params);
@@ -435,23 +617,27 @@ static int stored_offset(const CoreEntryRt& core, int kind, int g) {
 // ---- launch configuration (tunable through the environment for sweeps) -------
 struct TileConfig {
   int nthreads;
-  size_t smem_cta;  // dynamic shared memory budget of the CTA (one CTA per SM)
+  size_t smem_cta;  // dynamic shared memory budget of the CTA
+  bool ws;          // warp-specialised kernel: two slabs, 8 producer + 16 consumer warps
 };
 static TileConfig tile_config() {
-  TileConfig c{512, size_t(227) * 1024 - 256};
+  TileConfig c{512, size_t(227) * 1024 - 256, false};
   if (const char* e = std::getenv("FQ_TILE_THREADS"))
-    if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256};
+    if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256, false};
+  if (const char* e = std::getenv("FQ_TILE_KERNEL"))
+    if (e[0] == 'w') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true};
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
-  const size_t nwarps = size_t(c.nthreads) / 32;
-  return nwarps * kSlotsPerWarp * kChunkBytes /*ring*/ + 2048 /*recipes*/ + nwarps * kSlotsPerWarp * 8 /*mbarriers*/ +
+  const size_t nwarps = c.ws ? size_t(kWsConsumerWarps) : size_t(c.nthreads) / 32;  // warps that stream chunks
+  return nwarps * kSlotsPerWarp * kChunkBytes /*ring*/ + 2048 /*recipes*/ + (nwarps * kSlotsPerWarp + 8) * 8 /*mbarriers*/ +
          512 /*alignment slack*/;
 }
 int tile_cells_capacity(int ndistinct) {
   const TileConfig c = tile_config();
-  const int cap = int((c.smem_cta - tile_fixed_smem(c)) / (size_t(ndistinct) * sizeof(double)));
-  return std::min(cap, c.nthreads);  // K1 evaluates one cell per thread in one pass
+  const size_t slabs = c.ws ? 2 : 1;
+  const int cap = int((c.smem_cta - tile_fixed_smem(c)) / slabs / (size_t(ndistinct) * sizeof(double)));
+  return std::min(cap, c.ws ? 32 * kWsProducerWarps : c.nthreads);  // K1 evaluates one cell per thread in one pass
 }
 static int tile_core_variant() {
   // default: masses only (54 doubles per 3-D cell -> larger tiles); FQ_TILE_CORE=h also stores dif_both(k+1)
@@ -1102,6 +1288,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   plan->launch = core->launch;
   plan->ntiles = uint32_t(mesh->ntiles);
   plan->nthreads = cfg.nthreads;
+  plan->ws = cfg.ws;
   if (plan->ntiles >= (1u << 27)) return nullptr;
   // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)
   std::vector<std::vector<uint8_t>> codes8(static_cast<size_t>(nblocks));
@@ -1184,16 +1371,18 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     if (int(max_cells) > tile_cells_capacity(plan->ndistinct)) return nullptr;
     plan->cstride = int(max_cells) | 1;  // odd stride: distinct rows start on different banks
     // dynamic shared memory layout
-    const size_t nwarps = size_t(plan->nthreads) / 32;
+    const size_t nwarps = plan->ws ? size_t(kWsConsumerWarps) : size_t(plan->nthreads) / 32;
     size_t off = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double);
     off = (off + 127) / 128 * 128;
+    plan->slab_bytes = uint32_t(off);
+    if (plan->ws) off *= 2;
     plan->ring_off = uint32_t(off);
     off += nwarps * kSlotsPerWarp * kChunkBytes;
     plan->rec_off = uint32_t(off);
     off += recipe_bytes;
     off = (off + 7) / 8 * 8;
     plan->mbar_off = uint32_t(off);
-    off += nwarps * kSlotsPerWarp * 8;
+    off += (nwarps * kSlotsPerWarp + 8) * 8;
     plan->smem_bytes = off;
     if (plan->smem_bytes > cfg.smem_cta) return nullptr;
   }
@@ -1381,6 +1570,7 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   P.ring_off = plan.ring_off;
   P.rec_off = plan.rec_off;
   P.mbar_off = plan.mbar_off;
+  P.slab_bytes = plan.slab_bytes;
   P.recipes = plan.recipes.p;
   P.recipe_bytes = plan.recipe_bytes;
   P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
