@@ -25,6 +25,10 @@ constexpr int kStreamChunk = 2048;              // target items per block
 constexpr int kStreamCap = kStreamChunk + 512;  // staging capacity (doubles, 20 KB -> 8+ CTAs/SM)
 constexpr int kStreamUnroll = 8;                // gathers in flight per thread
 constexpr int kStreamSegRegs = 4;               // segment bounds preloaded per thread
+// Staged items are padded by one slot every 16: in phase 2 consecutive threads walk consecutive segments (~16 items
+// each for the FEM blocks), which without padding start in the same shared-memory bank.
+__device__ __forceinline__ uint32_t stream_slot(uint32_t k) { return k + (k >> 4); }
+constexpr int kStreamStage = kStreamCap + kStreamCap / 16 + 1;
 
 static __global__ void stream_blocks_kernel(const uint32_t* __restrict__ seg_ptr, uint32_t nseg, uint32_t nblocks,
                                      uint32_t* __restrict__ blocks) {
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
                                                                         const uint32_t* __restrict__ index,
                                                                         const double* __restrict__ values,
                                                                         const double* __restrict__ src, Policy policy) {
-  __shared__ double stage[kStreamCap];
+  __shared__ double stage[kStreamStage];
   __shared__ double red[kStreamThreads / 32];
   __shared__ int red_any[kStreamThreads / 32];
   for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
           const uint32_t k = base + u * kStreamThreads + threadIdx.x;
-          if (k < cnt) stage[k] = Policy::kHasValues ? __dmul_rn(val[u], g[u]) : g[u];
+          if (k < cnt) stage[stream_slot(k)] = Policy::kHasValues ? __dmul_rn(val[u], g[u]) : g[u];
         }
       }
       __syncthreads();
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
           double acc = 0.0;
           bool any = false;
           for (uint32_t q = sb[j] - p0; q < se[j] - p0; ++q) {
-            const double v = stage[q];
+            const double v = stage[stream_slot(q)];
             any = any || (v != 0.0);
             acc = __dadd_rn(acc, v);
           }
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
         double acc = 0.0;
         bool any = false;
         for (uint32_t q = b0; q < b1; ++q) {
-          const double v = stage[q];
+          const double v = stage[stream_slot(q)];
           any = any || (v != 0.0);
           acc = __dadd_rn(acc, v);
         }
