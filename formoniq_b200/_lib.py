@@ -61,6 +61,7 @@ SIGNATURES = [
     ("fq_hodge_destroy", _i, [_vp]),
     ("fq_hodge_mixed_laplacian", _i, [_vp, _vp, _P(_vp)]),
     ("fq_csr_transpose", _i, [_vp, _vp, _P(_vp)]),
+    ("fq_csr_restrict", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _P(_vp)]),
     ("fq_csr_shape", _i, [_vp, _P(_sz), _P(_sz), _P(_sz)]),
     ("fq_csr_row_range", _i, [_vp, _P(_sz), _P(_sz)]),
     ("fq_csr_download", _i, [_vp, _vp, _vp, _vp, _vp]),

@@ -345,6 +345,14 @@ class DeviceCsr:
         check(_lib.lib().fq_csr_transpose(self.ctx._h, self._h, C.byref(h)))
         return DeviceCsr(self.ctx, h)
 
+    def restrict(self, rows_keep, cols_keep) -> "DeviceCsr":
+        """E_test^T A E_trial of RelativeWhitneyComplex::assemble: the sub-matrix on ascending index lists."""
+        r = np.ascontiguousarray(rows_keep, dtype=np.uint64)
+        c = np.ascontiguousarray(cols_keep, dtype=np.uint64)
+        h = C.c_void_p()
+        check(_lib.lib().fq_csr_restrict(self.ctx._h, self._h, _p(r), r.shape[0], _p(c), c.shape[0], C.byref(h)))
+        return DeviceCsr(self.ctx, h)
+
     def to_scipy(self):
         import scipy.sparse as sp
 

@@ -127,4 +127,73 @@ void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01,
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// ---- restriction to a subset of rows / columns -----------------------------------------------------------------
+// RelativeWhitneyComplex::assemble (formoniq/src/whitney_complex.rs:620-624) forms E_test^T A E_trial with the 0/1
+// inclusion matrices of the interior DOFs through two sparse products; since every product has a single term
+// A_ij * 1 * 1 the result is the sub-matrix A[interior rows, interior cols] — here an index compaction.
+__global__ void restrict_colmap_kernel(const uint32_t* __restrict__ keep, uint32_t n, uint32_t* __restrict__ col_map) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) col_map[keep[i]] = i;
+}
+__global__ void restrict_count_kernel(const uint32_t* __restrict__ rows_keep, uint32_t nr, const uint32_t* __restrict__ row_ptr,
+                                      const uint32_t* __restrict__ col_idx, const uint32_t* __restrict__ col_map,
+                                      uint32_t* __restrict__ count) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= nr; i += stride) {
+    uint32_t c = 0;
+    if (i < nr) {
+      const uint32_t r = rows_keep[i];
+      for (uint32_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p) c += col_map[col_idx[p]] != 0xFFFFFFFFu;
+    }
+    count[i] = c;
+  }
+}
+__global__ void restrict_fill_kernel(const uint32_t* __restrict__ rows_keep, uint32_t nr, const uint32_t* __restrict__ row_ptr,
+                                     const uint32_t* __restrict__ col_idx, const double* __restrict__ val,
+                                     const uint32_t* __restrict__ col_map, const uint32_t* __restrict__ out_ptr,
+                                     uint32_t* __restrict__ out_col, double* __restrict__ out_val) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += stride) {
+    const uint32_t r = rows_keep[i];
+    uint32_t o = out_ptr[i];
+    for (uint32_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+      const uint32_t c = col_map[col_idx[p]];
+      if (c != 0xFFFFFFFFu) out_col[o] = c, out_val[o] = val[p], ++o;
+    }
+  }
+}
+
+// rows_keep / cols_keep: ascending device index lists
+void csr_restrict(fq_ctx* ctx, const fq_csr* a, const uint32_t* rows_keep, size_t nr, const uint32_t* cols_keep, size_t nc,
+                  fq_csr* out) {
+  FQ_REQUIRE(a->row_begin == 0 && a->row_end == a->nrows, "restriction needs a fully held matrix");
+  const int block = 256;
+  DevBuf<uint32_t> col_map(a->ncols ? a->ncols : 1), count(nr + 1);
+  FQ_CUDA(cudaMemsetAsync(col_map.p, 0xFF, col_map.bytes(), ctx->stream));
+  if (nc) restrict_colmap_kernel<<<grid_for(nc, block, ctx->sm_count), block, 0, ctx->stream>>>(cols_keep, uint32_t(nc), col_map.p);
+  restrict_count_kernel<<<grid_for(nr + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(rows_keep, uint32_t(nr), a->row_ptr.p,
+                                                                                          a->col_idx.p, col_map.p, count.p);
+  out->nrows = nr;
+  out->ncols = nc;
+  out->row_begin = 0;
+  out->row_end = nr;
+  out->row_ptr.alloc(nr + 1);
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count.p, out->row_ptr.p, int64_t(nr + 1), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, count.p, out->row_ptr.p, int64_t(nr + 1), ctx->stream));
+  uint32_t nnz = 0;
+  FQ_CUDA(cudaMemcpyAsync(&nnz, out->row_ptr.p + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->nnz = nnz;
+  out->col_idx.alloc(nnz ? nnz : 1);
+  out->values.alloc(nnz ? nnz : 1);
+  if (nr)
+    restrict_fill_kernel<<<grid_for(nr, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        rows_keep, uint32_t(nr), a->row_ptr.p, a->col_idx.p, a->values.p, col_map.p, out->row_ptr.p, out->col_idx.p, out->values.p);
+  fq_count_launch(ctx, 5);
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 }  // namespace fq

@@ -524,6 +524,23 @@ int fq_csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr** out) {
   *out = t.release();
   FQ_API_END
 }
+int fq_csr_restrict(fq_ctx* ctx, const fq_csr* a, const size_t* rows_keep, size_t nrows_keep, const size_t* cols_keep,
+                    size_t ncols_keep, fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && out && (rows_keep || nrows_keep == 0) && (cols_keep || ncols_keep == 0), "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < nrows_keep; ++i)
+    FQ_REQUIRE(rows_keep[i] < a->nrows && (i == 0 || rows_keep[i] > rows_keep[i - 1]), "rows_keep must be ascending and in range");
+  for (size_t i = 0; i < ncols_keep; ++i)
+    FQ_REQUIRE(cols_keep[i] < a->ncols && (i == 0 || cols_keep[i] > cols_keep[i - 1]), "cols_keep must be ascending and in range");
+  DevBuf<uint32_t> dr, dc;
+  upload_narrow(ctx, reinterpret_cast<const uint64_t*>(rows_keep), nrows_keep, dr);
+  upload_narrow(ctx, reinterpret_cast<const uint64_t*>(cols_keep), ncols_keep, dc);
+  std::unique_ptr<fq_csr> r(new fq_csr);
+  csr_restrict(ctx, a, dr.p, nrows_keep, dc.p, ncols_keep, r.get());
+  *out = r.release();
+  FQ_API_END
+}
 int fq_hodge_mixed_laplacian(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out) {
   FQ_API_BEGIN
   FQ_REQUIRE(ctx && blocks && out, "null argument");

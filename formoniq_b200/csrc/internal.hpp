@@ -46,6 +46,9 @@ void csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr* out);
 void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01, const fq_csr* a10, const fq_csr* a11,
                   fq_csr* out);
 
+void csr_restrict(fq_ctx* ctx, const fq_csr* a, const uint32_t* rows_keep, size_t nr, const uint32_t* cols_keep, size_t nc,
+                  fq_csr* out);
+
 // ---- blas1.cu
 double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n);
 void vec_scale(fq_ctx* ctx, double* x, double alpha, size_t n);

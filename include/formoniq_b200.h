@@ -156,6 +156,11 @@ fq_csr* fq_hodge_block(fq_hodge* blocks, int which);
  * (single-GPU row range).  fq_csr_transpose is the transpose used for the lower-left block. */
 int fq_hodge_mixed_laplacian(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out);
 int fq_csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr** out);
+/* RelativeWhitneyComplex::assemble (formoniq/src/whitney_complex.rs:620-624): E_test^T A E_trial for the 0/1 inclusions of
+ * the interior DOFs = the sub-matrix A[rows_keep, cols_keep] (ascending index lists, e.g. interior_simps of the test and
+ * trial grade, whitney_complex.rs:562-575), done as an index compaction on the device instead of two sparse products. */
+int fq_csr_restrict(fq_ctx* ctx, const fq_csr* a, const size_t* rows_keep, size_t nrows_keep, const size_t* cols_keep,
+                    size_t ncols_keep, fq_csr** out);
 int fq_hodge_destroy(fq_hodge* blocks);
 
 /* ---- CSR matrices ----------------------------------------------------------

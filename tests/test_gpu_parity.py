@@ -559,3 +559,38 @@ def test_mixed_hodge_laplacian_stitched_on_the_device(fq, ctx, dim, shape, k):
     x = np.cos(np.arange(exp.shape[1]) ** 2 + 1.0)
     y = hb.mixed_hodge_laplacian().apply(fq.DeviceVector.from_numpy(ctx, x)).to_numpy()
     assert np.abs(y - exp @ x).max() <= 1e-12 * np.abs(exp @ x).max()
+
+
+def test_relative_complex_restriction_is_the_submatrix(fq, ctx):
+    # whitney_complex.rs:620-624: E_test^T A E_trial on the interior DOFs (all simplices not on the boundary of the cube)
+    dim, shape = 3, [4, 3, 4]
+    cx, s, coords, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    # boundary vertices of the unjittered grid -> constrained simplices: those with every vertex on the boundary face set
+    grid = O.kuhn_vertex_coords(dim, shape)
+    on_bnd = np.any((np.abs(grid) < 1e-12) | (np.abs(grid - 1.0) < 1e-12), axis=1)
+    interior = {}
+    for g in (0, 1):
+        # simplex -> its vertices, recovered from the cell tables
+        cf, cv = cx.cell_faces(g), cx.cell_faces(0)
+        import itertools
+
+        combos = list(itertools.combinations(range(dim + 1), g + 1))
+        combos.sort(key=lambda c: sum(1 << i for i in c))  # colex order of the local faces
+        simplex_verts = {}
+        for c in range(cf.shape[0]):
+            for l, comb in enumerate(combos):
+                simplex_verts[int(cf[c, l])] = [int(cv[c, i]) for i in comb]
+        ids = np.array(sorted(simplex_verts))
+        keep = np.array([not all(on_bnd[v] for v in simplex_verts[i]) for i in ids])
+        interior[g] = ids[keep]
+    for kind, g, tg, rg in ((O.MASS, 1, 1, 1), (O.DIF_TEST, 1, 0, 1), (O.DIF_BOTH, 1, 0, 0)):
+        a = fq.WhitneyPairing(dim, g, kind).assemble(mesh)
+        got = a.restrict(interior[tg], interior[rg]).to_scipy()
+        exp = a.to_scipy()[interior[tg]][:, interior[rg]]
+        exp.sort_indices()
+        assert got.shape == exp.shape
+        assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+        assert np.array_equal(got.data, exp.data)
+    with pytest.raises(fq.FormoniqError):
+        a.restrict([3, 2], [0])
