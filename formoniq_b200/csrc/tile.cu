@@ -594,11 +594,6 @@ struct CoreEntryRt {
 static const CoreEntryRt g_cores[] = {FQ_GEN_CORE_LIST(FQ_CORE_ENTRY)};
 #undef FQ_CORE_ENTRY
 
-static const CoreEntryRt* find_core(int n, int k, int variant) {
-  for (const CoreEntryRt& e : g_cores)
-    if (e.n == n && e.k == k && e.variant == variant) return &e;
-  return nullptr;
-}
 // offset of the stored block (kind, g) inside the core's map, or -1 when the core does not store it
 static int stored_offset(const CoreEntryRt& core, int kind, int g) {
   const BlockSpec stored[3] = {{KIND_MASS, core.k - 1},
