@@ -1,10 +1,11 @@
 #!/bin/bash
-export FQ_TILE_THREADS=512 FQ_TILE_BRICK=5,3,2 FQ_TILE_SIG=1 FQ_TILE_STAGES=3
-for dbg in 0 1 2 3 4 6 7; do
+# per-phase warp-cycle statistics of the tile kernel for a list of FQ_TILE_DEBUG values
+for dbg in "$@"; do
   export FQ_TILE_DEBUG=$dbg
   echo -n "debug=$dbg  "
-  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
+  timeout 150 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/tmp/err.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline())
-print(d['kernels_ms_per_step'].get('k13_tile_fused'))"
+print(round(d['kernels_ms_per_step'].get('k13_tile_fused'),3), end='  ')"
+  grep "tile stats" /tmp/err.log | tail -1
 done
