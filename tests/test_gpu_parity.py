@@ -594,3 +594,47 @@ def test_relative_complex_restriction_is_the_submatrix(fq, ctx):
         assert np.array_equal(got.data, exp.data)
     with pytest.raises(fq.FormoniqError):
         a.restrict([3, 2], [0])
+
+
+def test_full_size_invariants_at_the_baseline_workload(fq, ctx):
+    # BASELINE configs[1] at full size (N = 128: 12 582 912 tets), checked through size-independent properties:
+    #  * the tile-fused pass reproduces the slab pass bit for bit (row sums and a probe product of every block);
+    #  * nnz(M0) equals the closed-form structural count 15N^3 + 21N^2 + 9N + 1;
+    #  * 1^T M0 1 = volume of the unit cube (the 0-form mass matrix integrates 1), to 1e-12;
+    #  * M1 and dif_both are symmetric operators: x^T (A y) == y^T (A x) to 1e-12.
+    import torch
+
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a large-memory GPU")
+    N = 128
+    mesh = fq.Mesh.kuhn(ctx, 3, N)
+    assert mesh.ncells == 6 * N ** 3
+    hb = fq.HodgeBlocks.symbolic(mesh, 1)
+    hb.numeric(mesh)                                  # slab pass
+    probes = []
+    for blk in hb.blocks:
+        ones = fq.DeviceVector.from_numpy(ctx, np.ones(blk.shape[1]))
+        x = fq.DeviceVector.from_numpy(ctx, np.cos(np.arange(blk.shape[1], dtype=np.float64) ** 2 + 1.0))
+        probes.append((blk.nnz, blk.apply(ones).to_numpy(), blk.apply(x).to_numpy()))
+    ctx.set_timing(True)
+    ctx.timing_report()
+    hb.numeric(mesh)                                  # builds the tile plan, runs the fused kernel
+    hb.numeric(mesh)
+    assert ctx.timing_report().get("k13_tile_fused", {}).get("count", 0) == 2
+    ctx.set_timing(False)
+    for blk, (nnz, rowsum, px) in zip(hb.blocks, probes):
+        ones = fq.DeviceVector.from_numpy(ctx, np.ones(blk.shape[1]))
+        x = fq.DeviceVector.from_numpy(ctx, np.cos(np.arange(blk.shape[1], dtype=np.float64) ** 2 + 1.0))
+        assert blk.nnz == nnz
+        assert np.array_equal(blk.apply(ones).to_numpy(), rowsum)
+        assert np.array_equal(blk.apply(x).to_numpy(), px)
+    assert hb.mass_sigma.nnz == 15 * N ** 3 + 21 * N ** 2 + 9 * N + 1
+    assert abs(probes[0][1].sum() - 1.0) <= 1e-12
+    for blk in (hb.mass_u, hb.dif_both):
+        n = blk.shape[0]
+        x = fq.DeviceVector.from_numpy(ctx, np.cos(np.arange(n, dtype=np.float64) ** 2 + 1.0))
+        y = fq.DeviceVector.from_numpy(ctx, np.sin(0.37 * np.arange(n, dtype=np.float64)))
+        a, b = x.dot(blk.apply(y)), y.dot(blk.apply(x))
+        assert abs(a - b) <= 1e-12 * max(abs(a), abs(b), 1e-300)
+    del hb, mesh
+    fq._lib.lib().fq_device_cache_trim()
