@@ -20,6 +20,7 @@ use simplicial::topology::{complex::Complex, incidence::FaceIncidence};
 #[repr(C)] pub struct fq_mesh { _p: [u8; 0] }
 #[repr(C)] pub struct fq_csr { _p: [u8; 0] }
 #[repr(C)] pub struct fq_vec { _p: [u8; 0] }
+#[repr(C)] pub struct fq_hodge { _p: [u8; 0] }
 
 // include/formoniq_b200.h
 unsafe extern "C" {
@@ -47,6 +48,17 @@ unsafe extern "C" {
   fn fq_vec_scale(ctx: *mut fq_ctx, x: *mut fq_vec, alpha: c_double) -> c_int;
   fn fq_vec_axpy(ctx: *mut fq_ctx, y: *mut fq_vec, alpha: c_double, x: *const fq_vec) -> c_int;
   fn fq_spmv(ctx: *mut fq_ctx, a: *const fq_csr, x: *const fq_vec, y: *mut fq_vec) -> c_int;
+  // HodgeBlocks (hodge.rs:62-99): symbolic once, numeric per geometry (one fused kernel from the second pass on)
+  fn fq_mesh_set_lengths(ctx: *mut fq_ctx, mesh: *mut fq_mesh, edge_lengths_sq: *const c_double) -> c_int;
+  fn fq_hodge_symbolic(ctx: *mut fq_ctx, mesh: *const fq_mesh, grade: c_int, sigma_row_begin: usize, sigma_row_end: usize,
+                       u_row_begin: usize, u_row_end: usize, out: *mut *mut fq_hodge) -> c_int;
+  fn fq_hodge_numeric(ctx: *mut fq_ctx, mesh: *const fq_mesh, blocks: *mut fq_hodge, drop_exact_zeros: c_int) -> c_int;
+  fn fq_hodge_block(blocks: *mut fq_hodge, which: c_int) -> *mut fq_csr;
+  fn fq_hodge_mixed_laplacian(ctx: *mut fq_ctx, blocks: *const fq_hodge, out: *mut *mut fq_csr) -> c_int;
+  fn fq_hodge_destroy(blocks: *mut fq_hodge) -> c_int;
+  // RelativeWhitneyComplex::assemble (whitney_complex.rs:620-624)
+  fn fq_csr_restrict(ctx: *mut fq_ctx, a: *const fq_csr, rows_keep: *const usize, nrows_keep: usize,
+                     cols_keep: *const usize, ncols_keep: usize, out: *mut *mut fq_csr) -> c_int;
 }
 
 /// The reference panics on contract violations (`galerkin.rs:184` unwraps);
@@ -189,6 +201,33 @@ impl<'d> LinearOperator for DeviceCsr<'d> {
     y
   }
 }
+
+/// `HodgeBlocks::compute` (hodge.rs:62-72) with the plan kept alive: `refresh` re-runs the numeric phase after
+/// `MeshLengthsSq` changed (time stepping, Regge flow); from the second pass on that is ONE fused kernel.
+pub struct GpuHodgeBlocks<'d> { dev: &'d Device, mesh: DeviceMesh<'d>, raw: *mut fq_hodge }
+impl<'d> GpuHodgeBlocks<'d> {
+  pub fn compute(dev: &'d Device, topology: &Complex, geometry: &MeshLengthsSq, grade: usize) -> Self {
+    let mesh = DeviceMesh::new(dev, topology, geometry);
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_hodge_symbolic(dev.0, mesh.raw, grade as c_int, 0, usize::MAX, 0, usize::MAX, &mut raw) });
+    check(unsafe { fq_hodge_numeric(dev.0, mesh.raw, raw, 1) });
+    Self { dev, mesh, raw }
+  }
+  pub fn refresh(&mut self, geometry: &MeshLengthsSq) {
+    check(unsafe { fq_mesh_set_lengths(self.dev.0, self.mesh.raw, geometry.vector().as_ptr()) });
+    check(unsafe { fq_hodge_numeric(self.dev.0, self.mesh.raw, self.raw, 1) });
+  }
+  /// 0 mass_sigma, 1 mass_u, 2 dif_test, 3 dif_both as `GalerkinMatrix` (host CSR, usize indices)
+  pub fn block(&self, which: usize) -> GalerkinMatrix { download(self.dev, unsafe { fq_hodge_block(self.raw, which as c_int) }) }
+  /// `mixed_hodge_laplacian` (hodge.rs:93-99) stitched on the device, left there for the Krylov solve
+  pub fn mixed_hodge_laplacian(&self) -> DeviceCsr<'d> {
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_hodge_mixed_laplacian(self.dev.0, self.raw, &mut raw) });
+    DeviceCsr { dev: self.dev, raw, n: self.block(0).nrows() + self.block(1).nrows() }
+  }
+}
+impl Drop for GpuHodgeBlocks<'_> { fn drop(&mut self) { unsafe { fq_hodge_destroy(self.raw) }; } }
+
 // `iterative::krylov::{cg, minres}` now run unmodified on `DeviceCsr` with
 // `iterative::precond::Identity<DeviceVector>` (precond.rs:16-41).
 #[allow(dead_code)]
