@@ -106,11 +106,16 @@ impl<'d> DeviceMesh<'d> {
 impl Drop for DeviceMesh<'_> { fn drop(&mut self) { unsafe { fq_mesh_destroy(self.raw) }; } }
 
 fn download(dev: &Device, csr: *mut fq_csr) -> GalerkinMatrix {
+  let m = download_borrowed(dev, csr);
+  unsafe { fq_csr_destroy(csr) };
+  m
+}
+/// Same for a matrix the library keeps (a block of an `fq_hodge` plan).
+fn download_borrowed(dev: &Device, csr: *mut fq_csr) -> GalerkinMatrix {
   let (mut nr, mut nc, mut nnz) = (0usize, 0usize, 0usize);
   check(unsafe { fq_csr_shape(csr, &mut nr, &mut nc, &mut nnz) });
   let (mut rp, mut ci, mut va) = (vec![0usize; nr + 1], vec![0usize; nnz], vec![0f64; nnz]);
   check(unsafe { fq_csr_download(dev.0, csr, rp.as_mut_ptr(), ci.as_mut_ptr(), va.as_mut_ptr()) });
-  unsafe { fq_csr_destroy(csr) };
   // the data contract handed to faer by linalg/faer.rs:16-24
   CsrMatrix::try_from_csr_data(nr, nc, rp, ci, va).unwrap()
 }
@@ -218,7 +223,9 @@ impl<'d> GpuHodgeBlocks<'d> {
     check(unsafe { fq_hodge_numeric(self.dev.0, self.mesh.raw, self.raw, 1) });
   }
   /// 0 mass_sigma, 1 mass_u, 2 dif_test, 3 dif_both as `GalerkinMatrix` (host CSR, usize indices)
-  pub fn block(&self, which: usize) -> GalerkinMatrix { download(self.dev, unsafe { fq_hodge_block(self.raw, which as c_int) }) }
+  pub fn block(&self, which: usize) -> GalerkinMatrix {
+    download_borrowed(self.dev, unsafe { fq_hodge_block(self.raw, which as c_int) })
+  }
   /// `mixed_hodge_laplacian` (hodge.rs:93-99) stitched on the device, left there for the Krylov solve
   pub fn mixed_hodge_laplacian(&self) -> DeviceCsr<'d> {
     let mut raw = ptr::null_mut();
