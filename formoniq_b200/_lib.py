@@ -65,6 +65,8 @@ SIGNATURES = [
     ("fq_csr_shape", _i, [_vp, _P(_sz), _P(_sz), _P(_sz)]),
     ("fq_csr_row_range", _i, [_vp, _P(_sz), _P(_sz)]),
     ("fq_csr_download", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("fq_csr_download_async", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("fq_ctx_wait_downloads", _i, [_vp]),
     ("fq_csr_upload", _i, [_vp, _sz, _sz, _vp, _vp, _vp, _P(_vp)]),
     ("fq_csr_destroy", _i, [_vp]),
     ("fq_csr_assembly_bytes", _i64, [_vp]),

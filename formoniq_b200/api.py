@@ -45,6 +45,10 @@ class Context:
     def set_stream(self, cuda_stream: int):
         check(_lib.lib().fq_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def wait_downloads(self):
+        """Block until every download_async issued on this context has landed in host memory."""
+        check(_lib.lib().fq_ctx_wait_downloads(self._h))
+
     def synchronize(self):
         check(_lib.lib().fq_ctx_synchronize(self._h))
 
@@ -338,6 +342,20 @@ class DeviceCsr:
             if rp.shape[0] != e - b + 1 or ci.shape[0] != nnz or va.shape[0] != nnz:
                 raise FormoniqError(-1, "download buffers are too small")
         check(_lib.lib().fq_csr_download(self.ctx._h, self._h, _p(rp), _p(ci), _p(va)))
+        return rp, ci, va
+
+    def download_async(self, out):
+        """Enqueue the download into `out` = (row_offsets, col_indices, values) buffers (pinned memory) on the copy
+        stream; it overlaps the work submitted afterwards.  Call ctx.wait_downloads() before reading the buffers, and
+        keep this matrix alive until then.  Returns views of the parts that will be filled."""
+        b, e = self.row_range
+        nnz = self.nnz
+        rp, ci, va = out[0][:e - b + 1], out[1][:nnz], out[2][:nnz]
+        if rp.dtype != np.uint64 or ci.dtype != np.uint64 or va.dtype != np.float64:
+            raise FormoniqError(-1, "download buffers must be uint64 / uint64 / float64")
+        if rp.shape[0] != e - b + 1 or ci.shape[0] != nnz or va.shape[0] != nnz:
+            raise FormoniqError(-1, "download buffers are too small")
+        check(_lib.lib().fq_csr_download_async(self.ctx._h, self._h, _p(rp), _p(ci), _p(va)))
         return rp, ci, va
 
     def transpose(self) -> "DeviceCsr":

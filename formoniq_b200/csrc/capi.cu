@@ -186,6 +186,10 @@ int fq_ctx_create(int device, fq_ctx** out) {
 int fq_ctx_destroy(fq_ctx* ctx) {
   FQ_API_BEGIN
   if (ctx) {
+    if (ctx->copy_stream) {
+      cudaStreamSynchronize(ctx->copy_stream);
+      cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
     delete ctx;
@@ -590,6 +594,39 @@ int fq_csr_download(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t*
     FQ_CUDA(cudaMemcpyAsync(values, csr->values.p, csr->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  FQ_API_END
+}
+// device u32 -> host u64 on the copy stream; the whole array is widened into one staging buffer kept until the wait
+static void download_widen_async(fq_ctx* ctx, const uint32_t* dev, size_t n, uint64_t* host) {
+  if (!n) return;
+  ctx->pending_staging.emplace_back(n);
+  uint64_t* stage = ctx->pending_staging.back().p;
+  widen_u32_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->copy_stream>>>(dev, n, stage);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaMemcpyAsync(host, stage, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+}
+int fq_csr_download_async(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t* col_indices, double* values) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && csr, "null argument");
+  if (!ctx->copy_stream) FQ_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  // everything enqueued so far on the compute stream (the assembly of this matrix) precedes the copies
+  cudaEvent_t ready;
+  FQ_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  FQ_CUDA(cudaEventRecord(ready, ctx->stream));
+  FQ_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+  FQ_CUDA(cudaEventDestroy(ready));
+  const size_t nrows_local = csr->row_end - csr->row_begin;
+  if (row_offsets) download_widen_async(ctx, csr->row_ptr.p, nrows_local + 1, reinterpret_cast<uint64_t*>(row_offsets));
+  if (col_indices) download_widen_async(ctx, csr->col_idx.p, csr->nnz, reinterpret_cast<uint64_t*>(col_indices));
+  if (values && csr->nnz)
+    FQ_CUDA(cudaMemcpyAsync(values, csr->values.p, csr->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  FQ_API_END
+}
+int fq_ctx_wait_downloads(fq_ctx* ctx) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx, "null argument");
+  if (ctx->copy_stream) FQ_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->pending_staging.clear();
   FQ_API_END
 }
 int fq_csr_upload(fq_ctx* ctx, size_t nrows, size_t ncols, const size_t* row_offsets, const size_t* col_indices,

@@ -102,6 +102,10 @@ struct fq_ctx {
   fq::DevBuf<double> reduce_scratch;  // two-stage reductions
   double* host_scalar = nullptr;      // pinned
   fq::DevBuf<int> d_flag_timeout;     // raised by a peer-flag wait that gave up
+  // asynchronous result downloads (fq_csr_download_async): a second stream so that the D2H copies of one matrix
+  // overlap the assembly of the next; the widened staging pieces live until fq_ctx_wait_downloads
+  cudaStream_t copy_stream = nullptr;
+  std::vector<fq::DevBuf<uint64_t>> pending_staging;
   // optional per-kernel timing (CUDA events on the launching stream)
   bool timing = false;
   std::vector<std::string> span_names;

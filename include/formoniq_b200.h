@@ -172,6 +172,11 @@ int fq_csr_row_range(const fq_csr* csr, size_t* row_begin, size_t* row_end);
 int fq_csr_download(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t* col_indices, double* values);
 int fq_csr_upload(fq_ctx* ctx, size_t nrows, size_t ncols, const size_t* row_offsets, const size_t* col_indices,
                   const double* values, fq_csr** out);
+/* The same download enqueued on the context's copy stream after everything submitted so far: it overlaps whatever the
+ * caller enqueues next (e.g. the assembly of the next block).  The host buffers (pinned for PCIe-rate copies) and the
+ * matrix must stay alive until fq_ctx_wait_downloads returns. */
+int fq_csr_download_async(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t* col_indices, double* values);
+int fq_ctx_wait_downloads(fq_ctx* ctx);
 int fq_csr_destroy(fq_csr* csr);
 /* algorithmic HBM bytes of the last numeric assembly / of one SpMV */
 int64_t fq_csr_assembly_bytes(const fq_csr* csr);

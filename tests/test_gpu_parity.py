@@ -638,3 +638,24 @@ def test_full_size_invariants_at_the_baseline_workload(fq, ctx):
         assert abs(a - b) <= 1e-12 * max(abs(a), abs(b), 1e-300)
     del hb, mesh
     fq._lib.lib().fq_device_cache_trim()
+
+
+def test_async_download_matches_the_blocking_one(fq, ctx):
+    import torch
+
+    cx, s, *_ = kuhn_problem(3, [4, 4, 3], jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    mats = [fq.WhitneyPairing(3, g, kind).assemble(mesh) for kind, g in ((O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2))]
+    outs = []
+    for a in mats:
+        b, e = a.row_range
+        out = (torch.empty(e - b + 1, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64),
+               torch.empty(a.nnz + 3, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64),
+               torch.empty(a.nnz + 3, dtype=torch.float64, pin_memory=True).numpy())
+        outs.append(a.download_async(out))
+    ctx.wait_downloads()
+    for a, (rp, ci, va) in zip(mats, outs):
+        erp, eci, eva = a.download()
+        assert np.array_equal(rp, erp) and np.array_equal(ci, eci) and np.array_equal(va, eva)
+    with pytest.raises(fq.FormoniqError):
+        mats[0].download_async((np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1)))
