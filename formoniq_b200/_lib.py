@@ -84,6 +84,12 @@ SIGNATURES = [
     ("fq_vec_device_ptr", _vp, [_vp]),
     ("fq_spmv", _i, [_vp, _vp, _vp, _vp]),
     ("fq_spmv_window", _i, [_vp, _vp, _vp, _sz, _vp]),
+    ("fq_matfree_create", _i, [_vp, _vp, _i, _i, _P(_vp)]),
+    ("fq_matfree_refresh", _i, [_vp, _vp]),
+    ("fq_matfree_destroy", _i, [_vp]),
+    ("fq_matfree_shape", _i, [_vp, _P(_sz), _P(_sz)]),
+    ("fq_matfree_apply", _i, [_vp, _vp, _vp, _vp]),
+    ("fq_matfree_diagonal", _i, [_vp, _vp, _vp]),
     ("fq_vec_ipc_export", _i, [_vp, _vp, _vp]),
     ("fq_vec_ipc_import", _i, [_vp, _vp, _sz, _P(_vp)]),
     ("fq_spmv_peer", _i, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _sz, _vp]),

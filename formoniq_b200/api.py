@@ -484,6 +484,42 @@ class ScalarLumpedMass(BilinearForm):
         return 0
 
 
+class ElementOperator:
+    """formoniq::matfree::ElementOperator: the matrix-free peer of the assembled matrix (matfree.rs:60-179)."""
+
+    def __init__(self, mesh: Mesh, form: "BilinearForm"):
+        self.ctx, self.mesh, self.form = mesh.ctx, mesh, form  # the mesh must outlive the operator
+        h = C.c_void_p()
+        check(_lib.lib().fq_matfree_create(mesh.ctx._h, mesh._h, form.kind, form.grade, C.byref(h)))
+        self._h = h
+        nr, nc = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().fq_matfree_shape(h, C.byref(nr), C.byref(nc)))
+        self.nrows, self.ncols = nr.value, nc.value
+
+    def refresh(self):
+        """Re-evaluate the element matrices after mesh.set_lengths()."""
+        check(_lib.lib().fq_matfree_refresh(self.ctx._h, self._h))
+
+    def apply(self, x: DeviceVector, out: DeviceVector | None = None) -> DeviceVector:
+        y = out if out is not None else DeviceVector(self.ctx, self.nrows)
+        check(_lib.lib().fq_matfree_apply(self.ctx._h, self._h, x._h, y._h))
+        return y
+
+    def diagonal(self) -> DeviceVector:
+        d = DeviceVector(self.ctx, self.nrows)
+        check(_lib.lib().fq_matfree_diagonal(self.ctx._h, self._h, d._h))
+        return d
+
+    def dim(self) -> int:
+        return self.nrows
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_matfree_destroy(self._h)
+        except Exception:
+            pass
+
+
 class _HodgePlan:
     def __init__(self, handle):
         self._h = handle

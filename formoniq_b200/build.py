@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "libformoniq_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 
-SOURCES = ["elmat.cu", "kuhn.cu", "assemble.cu", "tile.cu", "blockop.cu", "spmv.cu", "blas1.cu", "krylov.cu", "capi.cu"]
+SOURCES = ["elmat.cu", "kuhn.cu", "assemble.cu", "tile.cu", "blockop.cu", "matfree.cu", "spmv.cu", "blas1.cu", "krylov.cu", "capi.cu"]
 HEADERS = ["common.cuh", "internal.hpp", "stream.cuh", "tape.hpp", "kuhn.hpp", "gen_elmat.cpp",
            "../../include/formoniq_b200.h"]
 NVCC_FLAGS = [

@@ -822,6 +822,56 @@ int fq_spmv_peer(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t he
   FQ_API_END
 }
 
+// ---------------------------------------------------------------- matrix-free ElementOperator (matfree.rs)
+int fq_matfree_create(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_matfree** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out, "null argument");
+  FQ_REQUIRE(kind >= 0 && kind <= 4, "unknown kind");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  fq_matfree* op = matfree_new();
+  try {
+    matfree_build(ctx, mesh, kind, grade, op);
+    matfree_refresh(ctx, op);
+  } catch (...) {
+    matfree_delete(op);
+    throw;
+  }
+  *out = op;
+  FQ_API_END
+}
+int fq_matfree_refresh(fq_ctx* ctx, fq_matfree* op) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && op, "null argument");
+  matfree_refresh(ctx, op);
+  FQ_API_END
+}
+int fq_matfree_destroy(fq_matfree* op) {
+  if (op) matfree_delete(op);
+  return FQ_OK;
+}
+int fq_matfree_shape(const fq_matfree* op, size_t* nrows, size_t* ncols) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(op, "null argument");
+  if (nrows) *nrows = matfree_nrows(op);
+  if (ncols) *ncols = matfree_ncols(op);
+  FQ_API_END
+}
+int fq_matfree_apply(fq_ctx* ctx, const fq_matfree* op, const fq_vec* x, fq_vec* y) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && op && x && y, "null argument");
+  FQ_REQUIRE(x->d.n == matfree_ncols(op) && y->d.n == matfree_nrows(op), "operator and vector disagree");  // matfree.rs:101
+  FQ_REQUIRE(x != y, "apply: x and y must be distinct");
+  matfree_apply(ctx, op, x->d.p, y->d.p);
+  FQ_API_END
+}
+int fq_matfree_diagonal(fq_ctx* ctx, const fq_matfree* op, fq_vec* d) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && op && d, "null argument");
+  FQ_REQUIRE(d->d.n == matfree_nrows(op), "diagonal: dimension mismatch");
+  matfree_diagonal(ctx, op, d->d.p);
+  FQ_API_END
+}
+
 static int krylov_common(bool is_cg, fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol,
                          size_t max_iters, fq_vec* x, size_t* iters, double* residual, int* converged) {
   FQ_API_BEGIN

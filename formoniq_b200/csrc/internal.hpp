@@ -49,6 +49,19 @@ void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01,
 void csr_restrict(fq_ctx* ctx, const fq_csr* a, const uint32_t* rows_keep, size_t nr, const uint32_t* cols_keep, size_t nc,
                   fq_csr* out);
 
+// ---- matfree.cu
+}  // namespace fq
+struct fq_matfree;
+namespace fq {
+void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, ::fq_matfree* op);
+void matfree_refresh(fq_ctx* ctx, ::fq_matfree* op);
+void matfree_apply(fq_ctx* ctx, const ::fq_matfree* op, const double* x, double* y);
+void matfree_diagonal(fq_ctx* ctx, const ::fq_matfree* op, double* d);
+size_t matfree_nrows(const ::fq_matfree* op);
+size_t matfree_ncols(const ::fq_matfree* op);
+void matfree_delete(::fq_matfree* op);
+::fq_matfree* matfree_new();
+
 // ---- blas1.cu
 double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n);
 void vec_scale(fq_ctx* ctx, double* x, double alpha, size_t n);

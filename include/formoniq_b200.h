@@ -37,6 +37,7 @@ typedef struct fq_mesh fq_mesh;
 typedef struct fq_csr fq_csr;
 typedef struct fq_vec fq_vec;
 typedef struct fq_hodge fq_hodge;
+typedef struct fq_matfree fq_matfree;
 
 /* formoniq/src/operators.rs:169-191 (the four WhitneyPairing constructors) and
  * :27-40 (ScalarLumpedMass).  `grade` is always the grade of the inner
@@ -202,6 +203,18 @@ int fq_spmv(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, fq_vec* y);
 /* y = A x where x holds only the window [x_lo, x_lo + len(x)) of the global
  * column space (owned segment + halos of a row-partitioned operator). */
 int fq_spmv_window(fq_ctx* ctx, const fq_csr* a, const fq_vec* x, size_t x_lo, fq_vec* y);
+
+/* ---- matrix-free operator: formoniq::matfree::ElementOperator (formoniq/src/matfree.rs:60-179) --------------------
+ * y = sum_K P_K^T A_K P_K x by the reference's two-stage gather (per cell A_K * gathered x, then per DOF the sum over
+ * FaceIncidence::face_cells in cell order): no global matrix, no atomics.  create walks the mesh once (converse incidence
+ * + element matrices); refresh re-evaluates the element matrices after fq_mesh_set_lengths; diagonal is matfree.rs:155-179
+ * (the Jacobi preconditioner of a matrix-free operator).  The mesh must outlive the operator. */
+int fq_matfree_create(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_matfree** out);
+int fq_matfree_refresh(fq_ctx* ctx, fq_matfree* op);
+int fq_matfree_destroy(fq_matfree* op);
+int fq_matfree_shape(const fq_matfree* op, size_t* nrows, size_t* ncols);
+int fq_matfree_apply(fq_ctx* ctx, const fq_matfree* op, const fq_vec* x, fq_vec* y);
+int fq_matfree_diagonal(fq_ctx* ctx, const fq_matfree* op, fq_vec* d);
 
 /* ---- SpMV fused with the halo exchange (one process per GPU, NVLink 5 / NVSwitch peer memory) -----------------
  * The reference is single-process; under the owner-computes row partition the only exchange step of the path is

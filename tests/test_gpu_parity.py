@@ -659,3 +659,34 @@ def test_async_download_matches_the_blocking_one(fq, ctx):
         assert np.array_equal(rp, erp) and np.array_equal(ci, eci) and np.array_equal(va, eva)
     with pytest.raises(fq.FormoniqError):
         mats[0].download_async((np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1)))
+
+
+@pytest.mark.parametrize("dim,shape,variant", [(2, [6, 5], "jitter"), (3, [4, 3, 4], "jitter"), (3, [3, 3, 3], "minkowski")])
+def test_matrix_free_element_operator_equals_the_assembled_matrix(fq, ctx, dim, shape, variant):
+    # matfree.rs:217-248 (apply == assembled * x) and :265-278 (diagonal == assembled diagonal), every pairing
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    for kind, g in [(O.MASS, 0), (O.MASS, 1), (O.MASS, dim), (O.DIF_TEST, 1), (O.DIF_TRIAL, 1), (O.DIF_BOTH, 1), (O.DIF_BOTH, 2)]:
+        form = fq.WhitneyPairing(dim, g, kind)
+        op = fq.ElementOperator(mesh, form)
+        ref = cx.assemble(s, kind, g).to_scipy()
+        assert (op.nrows, op.ncols) == ref.shape
+        x = probe(op.ncols)
+        y = op.apply(fq.DeviceVector.from_numpy(ctx, x)).to_numpy()
+        exp = ref @ x
+        assert np.abs(y - exp).max() <= 1e-12 * max(np.abs(exp).max(), 1e-300)
+        if op.nrows == op.ncols:
+            d = op.diagonal().to_numpy()
+            assert np.abs(d - ref.diagonal()).max() <= 1e-12 * np.abs(ref.diagonal()).max()
+    # new geometry, same topology
+    _, s2, *_ = kuhn_problem(dim, shape, jitter=variant != "jitter")
+    form = fq.WhitneyPairing.mass(dim, 1)
+    op = fq.ElementOperator(mesh, form)
+    mesh.set_lengths(s2)
+    op.refresh()
+    ref = cx.assemble(s2, O.MASS, 1).to_scipy()
+    x = probe(op.ncols)
+    y = op.apply(fq.DeviceVector.from_numpy(ctx, x)).to_numpy()
+    assert np.abs(y - ref @ x).max() <= 1e-12 * np.abs(ref @ x).max()
+    with pytest.raises(fq.FormoniqError):
+        op.apply(fq.DeviceVector(ctx, op.ncols + 1))
