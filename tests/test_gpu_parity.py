@@ -690,3 +690,99 @@ def test_matrix_free_element_operator_equals_the_assembled_matrix(fq, ctx, dim, 
     assert np.abs(y - ref @ x).max() <= 1e-12 * np.abs(ref @ x).max()
     with pytest.raises(fq.FormoniqError):
         op.apply(fq.DeviceVector(ctx, op.ncols + 1))
+
+
+# ------------------------------------------------------------------ shift-invert Lanczos (linalg/eigen.rs:396-590)
+def _sym(n, f):
+    return np.array([[f(min(i, j), max(i, j)) for j in range(n)] for i in range(n)], float)
+
+
+def _dev(fq, ctx, dense):
+    import scipy.sparse as sp
+
+    return fq.DeviceCsr.from_scipy(ctx, sp.csr_matrix(dense))
+
+
+def test_eigen_pairs_solve_the_pencil_and_are_b_orthonormal(fq, ctx):
+    n = 6
+    a = _sym(n, lambda i, j: ((i * 7 + j * 3) % 11) - 5.0)
+    b = _sym(n, lambda i, j: float(n) if i == j else 0.3)
+    for nev in range(1, n + 1):  # eigen.rs:398-412
+        vals, vecs = fq.sparse_shift_invert_eigen(_dev(fq, ctx, a), _dev(fq, ctx, b), 0.0, nev)
+        for lam, x in zip(vals, vecs):
+            xh = x.to_numpy()
+            assert np.linalg.norm(a @ xh - lam * (b @ xh)) < 1e-9
+    a2 = _sym(n, lambda i, j: 2.0 * n if i == j else 0.5)  # eigen.rs:437-453
+    _, vecs = fq.sparse_shift_invert_eigen(_dev(fq, ctx, a2), _dev(fq, ctx, b), 0.0, n)
+    v = np.stack([x.to_numpy() for x in vecs], axis=1)
+    assert np.abs(v.T @ b @ v - np.eye(n)).max() < 1e-8
+
+
+def test_eigen_matches_the_dense_evd_and_handles_degenerate_cases(fq, ctx):
+    n = 7  # eigen.rs:415-434
+    a = _sym(n, lambda i, j: ((i * 5 + j * 2) % 13) - 6.0)
+    oracle = sorted(np.linalg.eigvalsh(a), key=abs)
+    for nev in range(1, n + 1):
+        vals, _ = fq.sparse_shift_invert_eigen(_dev(fq, ctx, a), _dev(fq, ctx, np.eye(n)), 0.0, nev)
+        assert np.abs(np.sort(vals) - np.sort(oracle[:nev])).max() < 1e-8
+    # null space of B is excluded (eigen.rs:456-471)
+    n = 5
+    a = _sym(n, lambda i, j: ((i * 3 + j * 7) % 11) - 5.0)
+    b = np.diag([1.0] * (n - 1) + [0.0])
+    vals, vecs = fq.sparse_shift_invert_eigen(_dev(fq, ctx, a), _dev(fq, ctx, b), 0.1, n - 1)
+    assert len(vals) == n - 1 and np.all(np.isfinite(vals))
+    for lam, x in zip(vals, vecs):
+        xh = x.to_numpy()
+        assert np.linalg.norm(a @ xh - lam * (b @ xh)) < 1e-8
+    # scalar pencil and k = 0 (eigen.rs:474-491)
+    vals, vecs = fq.sparse_shift_invert_eigen(_dev(fq, ctx, np.array([[3.0]])), _dev(fq, ctx, np.array([[4.0]])), 0.0, 3)
+    assert len(vals) == 1 and abs(vals[0] - 0.75) < 1e-9 and abs(vecs[0].to_numpy()[0] ** 2 * 4.0 - 1.0) < 1e-9
+    vals0, vecs0 = fq.sparse_shift_invert_eigen(_dev(fq, ctx, np.array([[3.0]])), _dev(fq, ctx, np.array([[4.0]])), 0.0, 0)
+    assert len(vals0) == 0 and vecs0 == []
+    # no finite eigenvalue (eigen.rs:494-501)
+    import scipy.sparse as sp
+
+    zero_b = fq.DeviceCsr.from_scipy(ctx, sp.csr_matrix((4, 4)))
+    with pytest.raises(fq.EigenError) as e:
+        fq.sparse_shift_invert_eigen(_dev(fq, ctx, np.eye(4)), zero_b, 0.0, 2)
+    assert e.value.kind == "NoFiniteEigenvalue"
+
+
+def test_eigen_large_sparse_pencil_closed_form(fq, ctx):
+    # eigen.rs:557-589: 1-D Laplacian, n = 3000, the five smallest eigenvalues against 2 - 2 cos(k pi / (n + 1))
+    import scipy.sparse as sp
+
+    n, nev = 3000, 5
+    a = sp.diags([-np.ones(n - 1), 2.0 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1], format="csr")
+    vals, vecs = fq.sparse_shift_invert_eigen(fq.DeviceCsr.from_scipy(ctx, a), fq.DeviceCsr.from_scipy(ctx, sp.identity(n, format="csr")),
+                                              0.0, nev)
+    assert len(vals) == nev
+    for k, (lam, x) in enumerate(zip(vals, vecs)):
+        xh = x.to_numpy()
+        assert np.linalg.norm(a @ xh - lam * xh) < 1e-6
+        assert abs(lam - (2.0 - 2.0 * np.cos((k + 1) * np.pi / (n + 1.0)))) < 1e-6
+
+
+def test_eigen_hodge_laplace_evp_on_the_device_blocks(fq, ctx):
+    # elliptic.rs:225-247 (solve_evp): A = mixed_hodge_laplacian, B = diag(0, M_k); 2-D 1-forms on the unit square.
+    # The pencil's finite eigenvalues are the Hodge-Laplace eigenvalues; check backward error and against scipy's eigsh.
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    cx, s, *_ = kuhn_problem(2, [6, 6])
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    hb = fq.HodgeBlocks.compute(mesh, 1)
+    a = hb.mixed_hodge_laplacian()
+    mu = hb.mass_u.to_scipy()
+    bh = sp.bmat([[sp.csr_matrix((hb.n_sigma, hb.n_sigma)), None], [None, mu]], format="csr")
+    b = fq.DeviceCsr.from_scipy(ctx, bh)
+    k = 4
+    vals, vecs = fq.sparse_shift_invert_eigen(a, b, 1.0, k)   # shift off the harmonic space / natural-BC zero modes
+    ah = a.to_scipy()
+    an, bn = abs(ah).sum(axis=1).max(), abs(bh).sum(axis=1).max()
+    for lam, x in zip(vals, vecs):
+        xh = x.to_numpy()
+        r = np.linalg.norm(ah @ xh - lam * (bh @ xh)) / ((an + abs(lam) * bn) * np.linalg.norm(xh))
+        assert r <= 1e-9
+    ref = spla.eigsh(ah.tocsc(), k=k, M=bh.tocsc(), sigma=1.0, which="LM", return_eigenvectors=False)
+    assert np.abs(np.sort(vals) - np.sort(ref)).max() <= 1e-8 * max(1.0, np.abs(ref).max())
