@@ -96,3 +96,16 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "fq_oracle" not in text and "liboracle" not in text and "import oracle" not in text and \
                     "from oracle" not in text, os.path.join(dp, f)
+
+
+def test_eigen_seed_vectors_match_the_reference_probe():
+    # eigen.rs:259-268: the vectorised splitmix64 fill of formoniq_b200.eigen equals the oracle's scalar restatement
+    import numpy as np
+
+    from formoniq_b200.eigen import MASK, pseudo_random
+    from oracle import oracle as O
+
+    for seed in (0, 1, 7, MASK):
+        v = pseudo_random(seed, 64)
+        assert all(v[i] == O.pseudo_random(seed, i) for i in range(64))
+        assert np.all(np.abs(v) <= 1.0)
