@@ -134,7 +134,7 @@ def run_reference(args):
         return
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_assembly_sample(args.sample_n, budget_s=8.0)
+        last = cpu_assembly_sample(args.sample_n, budget_s=5.0)
         if i >= args.warmup:
             vals.append(last)
         if args.sample_n is None:  # keep the calibrated size for the remaining steps

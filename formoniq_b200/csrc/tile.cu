@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
   // issue cursor (tile iteration it is on, next chunk, end of that tile's chunks); runs ahead across tiles
   uint32_t n_issued = 0, n_consumed = 0;
   uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
+  uint32_t eid_next[NEE];
+  bool have_eids = false;
   const bool prof = (P.debug & 8) && lane == 0;
   long long tk[6] = {0, 0, 0, 0, 0, 0};
   long long t_last = clock64();
@@ -322,10 +324,15 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
     // ---- K1: element values of the tile's cells -> shared slab [distinct][cell]
     if (c1 > c0 && !(P.debug & 1)) {
       for (uint32_t c = tid; c < nc; c += NT) {
-        const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
         uint32_t eid[NEE];
+        if (have_eids && c == uint32_t(tid)) {  // fetched while this thread waited at the previous tile's barrier
 #pragma unroll
-        for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
+          for (int e = 0; e < NE; ++e) eid[e] = eid_next[e];
+        } else {
+          const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
+        }
         double s[NEE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
@@ -348,6 +355,13 @@ __global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __
       lap(3);
       ++n_consumed;
       issue_more();
+    }
+    // edge ids of this thread's cell of the next tile: issued now, they arrive while the warp waits at the tile barrier
+    have_eids = !(P.debug & 16) && hnext[0] < P.ntiles;
+    if (have_eids && uint32_t(tid) < hnext[2] - hnext[1]) {
+      const uint32_t* ce = P.tile_cell_edges + size_t(hnext[1] + tid) * NE;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) eid_next[e] = __ldg(ce + e);
     }
   }
   if (prof)
