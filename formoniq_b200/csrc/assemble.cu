@@ -223,7 +223,8 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
 struct GatherStructural {
   static constexpr bool kHasValues = false;
   static constexpr bool kCustomSrc = false;
-  __device__ __forceinline__ double load(uint32_t) const { return 0.0; }
+  static constexpr bool kGated = false;
+  __device__ __forceinline__ double load(uint32_t, bool) const { return 0.0; }
   double* __restrict__ values;
   uint8_t* __restrict__ keep;
   __device__ __forceinline__ void store(uint32_t q, double sum, bool any) const {
@@ -234,7 +235,8 @@ struct GatherStructural {
 struct GatherCompacted {
   static constexpr bool kHasValues = false;
   static constexpr bool kCustomSrc = false;
-  __device__ __forceinline__ double load(uint32_t) const { return 0.0; }
+  static constexpr bool kGated = false;
+  __device__ __forceinline__ double load(uint32_t, bool) const { return 0.0; }
   double* __restrict__ values;
   const uint8_t* __restrict__ keep;
   const uint32_t* __restrict__ pos;

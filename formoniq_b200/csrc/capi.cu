@@ -815,10 +815,11 @@ int fq_spmv_peer(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t he
   FQ_REQUIRE(x_window != y, "spmv: x and y must be distinct");
   spmv_prepare(ctx, const_cast<fq_csr*>(a));
   // pointers pre-offset so that ptr[global column] addresses the right window
-  const double* own = x_window->d.p - held_lo;
-  const double* lower = x_lower ? x_lower->d.p - lower_held_lo : own;
-  const double* upper = x_upper ? x_upper->d.p - upper_held_lo : own;
-  spmv_apply_peer(ctx, a, own, lower, upper, x_lower ? own_lo : 0, x_upper ? own_hi : a->ncols, y->d.p);
+  FQ_REQUIRE(held_lo + x_window->d.n >= own_hi, "spmv_peer: window shorter than the owned range");
+  double* own = const_cast<double*>(x_window->d.p) - held_lo;  // the halo slots of the window are filled by the kernel
+  const double* lower = x_lower ? x_lower->d.p - lower_held_lo : nullptr;
+  const double* upper = x_upper ? x_upper->d.p - upper_held_lo : nullptr;
+  spmv_apply_peer(ctx, const_cast<fq_csr*>(a), own, lower, upper, held_lo, own_lo, own_hi, held_lo + x_window->d.n, y->d.p);
   FQ_API_END
 }
 

@@ -210,6 +210,10 @@ struct fq_csr {
   fq::DevBuf<uint32_t> rowblocks;
   size_t nrowblocks = 0;
   bool spmv_ready = false;
+  // fused halo-exchange SpMV: {free_lo, free_hi, ext0, ext1} for the owned range below, copy-completion counter
+  fq::DevBuf<uint32_t> peer_split;
+  fq::DevBuf<unsigned long long> peer_counter;
+  size_t peer_own_lo = 0, peer_own_hi = 0, peer_launches = 0;
   // Jacobi (inverse diagonal), built on demand
   fq::DevBuf<double> inv_diag;
   // tile-fused numeric path (shared by the blocks assembled together)

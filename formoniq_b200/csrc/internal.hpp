@@ -35,8 +35,8 @@ int64_t tile_plan_bytes(const TilePlan& plan);
 // ---- spmv.cu
 void spmv_prepare(fq_ctx* ctx, fq_csr* a);
 void spmv_apply(fq_ctx* ctx, const fq_csr* a, const double* x, double* y);
-void spmv_apply_peer(fq_ctx* ctx, const fq_csr* a, const double* own, const double* lower, const double* upper, size_t own_lo,
-                     size_t own_hi, double* y);
+void spmv_apply_peer(fq_ctx* ctx, fq_csr* a, double* own, const double* lower, const double* upper, size_t held_lo,
+                     size_t own_lo, size_t own_hi, size_t held_hi, double* y);
 void flag_signal(fq_ctx* ctx, double* flag, double value);
 void flag_wait(fq_ctx* ctx, const double* flag, double value, int* d_timeout);
 void csr_build_inv_diag(fq_ctx* ctx, fq_csr* a);

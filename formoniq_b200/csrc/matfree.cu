@@ -66,8 +66,9 @@ __global__ void mf_diag_kernel(const double* __restrict__ slab, size_t ncells, i
 struct MfGatherPolicy {
   static constexpr bool kHasValues = false;
   static constexpr bool kCustomSrc = false;
+  static constexpr bool kGated = false;
   double* __restrict__ y;
-  __device__ __forceinline__ double load(uint32_t) const { return 0.0; }
+  __device__ __forceinline__ double load(uint32_t, bool) const { return 0.0; }
   __device__ __forceinline__ void store(uint32_t dof, double sum, bool) const { y[dof] = sum; }
 };
 

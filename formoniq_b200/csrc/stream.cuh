@@ -69,7 +69,9 @@ inline void stream_build_blocks(fq_ctx* ctx, const uint32_t* seg_ptr, size_t nse
 // Policy interface:
 //   static constexpr bool kHasValues;
 //   static constexpr bool kCustomSrc;   // true: the gathered operand comes from policy.load(index) instead of src[index]
-//   __device__ double load(uint32_t index) const;
+//   static constexpr bool kGated;       // true: policy.prologue() runs first (e.g. a halo copy by a few CTAs); the
+//                                       // blocks with policy.is_late(b) depend on it and wait in policy.gate_wait()
+//   __device__ double load(uint32_t index, bool late) const;   // late: the block was gated (CTA-uniform)
 //   __device__ void store(uint32_t seg, double sum, bool any_nonzero) const;
 template <class Policy>
 __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uint32_t* __restrict__ blocks,
@@ -81,7 +83,13 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
   __shared__ double stage[kStreamStage];
   __shared__ double red[kStreamThreads / 32];
   __shared__ int red_any[kStreamThreads / 32];
+  if constexpr (Policy::kGated) policy.prologue();
   for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    bool late = false;  // CTA-uniform: this block reads what the prologue wrote
+    if constexpr (Policy::kGated) {
+      late = policy.is_late(b);
+      if (late) policy.gate_wait();
+    }
     const uint32_t s0 = blocks[b], s1 = blocks[b + 1];
     if (s0 >= s1) continue;
     const uint32_t p0 = seg_ptr[s0], p1 = seg_ptr[s1];
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
           const uint32_t k = base + u * kStreamThreads + threadIdx.x;
-          g[u] = k < cnt ? (Policy::kCustomSrc ? policy.load(idx[u]) : __ldg(src + idx[u])) : 0.0;
+          g[u] = k < cnt ? (Policy::kCustomSrc ? policy.load(idx[u], late) : __ldg(src + idx[u])) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_reduce_kernel(const uin
         int any = 0;
         for (uint32_t p = b0 + threadIdx.x; p < b1; p += kStreamThreads) {
           const uint32_t ip = __ldg(index + p);
-          const double g = Policy::kCustomSrc ? policy.load(ip) : __ldg(src + ip);
+          const double g = Policy::kCustomSrc ? policy.load(ip, late) : __ldg(src + ip);
           const double v = Policy::kHasValues ? __dmul_rn(__ldg(values + p), g) : g;
           any |= (v != 0.0);
           acc = __dadd_rn(acc, v);

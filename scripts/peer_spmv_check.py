@@ -75,6 +75,19 @@ for name, form in (("mass_u", fq.WhitneyPairing.mass(DIM, 1)), ("dif_test", fq.W
 
     t_nccl, t_peer = timed(nccl_path), timed(peer_path)
     ph.check()
+    # break-down: the local kernels alone (no exchange, no flags) on the torch window and on the IPC-exported window
+    t_local = timed(lambda: a.apply_window(xin, r.held_lo, y2))
+    t_local_ipc = timed(lambda: a.apply_window(xv, r.held_lo, y2))
+
+    def peer_kernel_only():
+        lo, hi = ph.peers.get(rank - 1), ph.peers.get(rank + 1)
+        fq._lib.check(fq._lib.lib().fq_spmv_peer(ctx._h, a._h, xv._h, r.held_lo, r.own_lo, r.own_hi,
+                                                 lo["x"]._h if lo else None, part.ranges[rank - 1].held_lo if lo else 0,
+                                                 hi["x"]._h if hi else None, part.ranges[rank + 1].held_lo if hi else 0, y_peer._h))
+
+    t_kernel = timed(peer_kernel_only)
+    if rank == 0:
+        print(f"   spmv local {t_local:.4f}  local on ipc window {t_local_ipc:.4f}  fused kernel without flags {t_kernel:.4f} ms", flush=True)
     if rank == 0:
         print(f"{name}: bitwise_equal={same}  nccl exchange + spmv {t_nccl:.4f} ms   fused peer spmv {t_peer:.4f} ms  (nnz/rank {a.nnz})", flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
