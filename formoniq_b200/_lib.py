@@ -93,6 +93,7 @@ SIGNATURES = [
     ("fq_vec_ipc_export", _i, [_vp, _vp, _vp]),
     ("fq_vec_ipc_import", _i, [_vp, _vp, _sz, _P(_vp)]),
     ("fq_spmv_peer", _i, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _sz, _vp]),
+    ("fq_spmv_peer_epoch", _i, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp, C.c_double, _vp, _vp]),
     ("fq_flag_signal", _i, [_vp, _vp, _d]),
     ("fq_flag_wait", _i, [_vp, _vp, _d]),
     ("fq_flag_check", _i, [_vp]),

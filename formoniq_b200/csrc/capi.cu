@@ -823,6 +823,35 @@ int fq_spmv_peer(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t he
   FQ_API_END
 }
 
+int fq_spmv_peer_epoch(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t held_lo, size_t own_lo, size_t own_hi,
+                       const fq_vec* x_lower, size_t lower_held_lo, const fq_vec* ready_lower, const fq_vec* x_upper,
+                       size_t upper_held_lo, const fq_vec* ready_upper, double epoch, fq_vec* consumed, fq_vec* y) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && x_window && y, "null argument");
+  FQ_REQUIRE(held_lo <= own_lo && own_lo <= own_hi && own_hi <= a->ncols, "spmv_peer: bad ranges");
+  FQ_REQUIRE(y->d.n == a->row_end - a->row_begin, "spmv_peer: dimension mismatch");
+  FQ_REQUIRE(x_window != y, "spmv: x and y must be distinct");
+  FQ_REQUIRE(held_lo + x_window->d.n >= own_hi, "spmv_peer: window shorter than the owned range");
+  FQ_REQUIRE((!ready_lower || x_lower) && (!ready_upper || x_upper), "spmv_peer: a ready flag without its window");
+  spmv_prepare(ctx, const_cast<fq_csr*>(a));
+  double* own = const_cast<double*>(x_window->d.p) - held_lo;
+  const double* lower = x_lower ? x_lower->d.p - lower_held_lo : nullptr;
+  const double* upper = x_upper ? x_upper->d.p - upper_held_lo : nullptr;
+  PeerSync sync;
+  sync.ready_lower = ready_lower ? ready_lower->d.p : nullptr;
+  sync.ready_upper = ready_upper ? ready_upper->d.p : nullptr;
+  sync.epoch = epoch;
+  sync.consumed = consumed ? consumed->d.p : nullptr;
+  if (ctx->d_flag_timeout.n != 1) {
+    ctx->d_flag_timeout.alloc(1);
+    FQ_CUDA(cudaMemsetAsync(ctx->d_flag_timeout.p, 0, sizeof(int), ctx->stream));
+  }
+  sync.timeout = ctx->d_flag_timeout.p;
+  spmv_apply_peer(ctx, const_cast<fq_csr*>(a), own, lower, upper, held_lo, own_lo, own_hi, held_lo + x_window->d.n, y->d.p,
+                  sync);
+  FQ_API_END
+}
+
 // ---------------------------------------------------------------- matrix-free ElementOperator (matfree.rs)
 int fq_matfree_create(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_matfree** out) {
   FQ_API_BEGIN

@@ -35,8 +35,17 @@ int64_t tile_plan_bytes(const TilePlan& plan);
 // ---- spmv.cu
 void spmv_prepare(fq_ctx* ctx, fq_csr* a);
 void spmv_apply(fq_ctx* ctx, const fq_csr* a, const double* x, double* y);
+// Epoch flags the fused halo SpMV can handle inside the kernel (all optional): wait until the neighbours' `ready`
+// flags reach `epoch` before the first P2P load, write `epoch` to `consumed` once the halo has been pulled.
+struct PeerSync {
+  const double* ready_lower = nullptr;
+  const double* ready_upper = nullptr;
+  double epoch = 0.0;
+  double* consumed = nullptr;
+  int* timeout = nullptr;
+};
 void spmv_apply_peer(fq_ctx* ctx, fq_csr* a, double* own, const double* lower, const double* upper, size_t held_lo,
-                     size_t own_lo, size_t own_hi, size_t held_hi, double* y);
+                     size_t own_lo, size_t own_hi, size_t held_hi, double* y, const PeerSync& sync = PeerSync());
 void flag_signal(fq_ctx* ctx, double* flag, double value);
 void flag_wait(fq_ctx* ctx, const double* flag, double value, int* d_timeout);
 void csr_build_inv_diag(fq_ctx* ctx, fq_csr* a);

@@ -60,10 +60,28 @@ struct SpmvHaloPolicy {
   const uint32_t* split;        // {first, one-past-last} row block free of halo columns
   unsigned long long* counter;  // copy CTAs that have finished, accumulated over launches
   unsigned long long target;    // value of *counter once this launch's copy is complete
+  PeerSync sync;                // optional epoch flags handled by the kernel itself (null pointers: none)
   uint32_t ncopy;               // CTAs taking part in the copy: the first ones dispatched, and they never wait before
                                 // their share is done, so the gate cannot deadlock whatever the residency
   __device__ __forceinline__ void prologue() const {
     if (blockIdx.x >= ncopy) return;
+    if (sync.ready_lower || sync.ready_upper) {
+      // the neighbours publish an epoch after their last write of x: wait for it before the first P2P load
+      if (threadIdx.x == 0) {
+        long long spins = 0;
+        const volatile double* f0 = sync.ready_lower;
+        const volatile double* f1 = sync.ready_upper;
+        while ((f0 && *f0 < sync.epoch) || (f1 && *f1 < sync.epoch)) {
+          __nanosleep(100);
+          if (++spins > (1ll << 23)) {  // ~3 s: never hang the device on a lost peer
+            *sync.timeout = 1;
+            break;
+          }
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
     const uint32_t nl = own_lo - held_lo, total = nl + (held_hi - own_hi);
     const uint32_t stride = ncopy * kStreamThreads;
     for (uint32_t base = blockIdx.x * kStreamThreads + threadIdx.x; base < total; base += 4 * stride) {
@@ -81,7 +99,14 @@ struct SpmvHaloPolicy {
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(counter, 1ull);
+    if (threadIdx.x == 0) {
+      const unsigned long long done = atomicAdd(counter, 1ull) + 1;
+      if (sync.consumed && done == target) {
+        // last share copied: the neighbours may overwrite their x (they wait for this epoch before doing so)
+        __threadfence_system();
+        *reinterpret_cast<volatile double*>(sync.consumed) = sync.epoch;
+      }
+    }
   }
   __device__ __forceinline__ bool is_late(uint32_t b) const { return b < __ldg(split) || b >= __ldg(split + 1); }
   __device__ __forceinline__ void gate_wait() const {
@@ -158,7 +183,7 @@ static void peer_prepare(fq_ctx* ctx, fq_csr* a, size_t own_lo, size_t own_hi) {
 }
 
 void spmv_apply_peer(fq_ctx* ctx, fq_csr* a, double* own, const double* lower, const double* upper, size_t held_lo,
-                     size_t own_lo, size_t own_hi, size_t held_hi, double* y) {
+                     size_t own_lo, size_t own_hi, size_t held_hi, double* y, const PeerSync& sync) {
   FQ_REQUIRE(a->spmv_ready, "spmv_prepare was not called");
   if (a->nrowblocks == 0) return;
   static const bool direct = [] {
@@ -166,6 +191,7 @@ void spmv_apply_peer(fq_ctx* ctx, fq_csr* a, double* own, const double* lower, c
     return e && *e && *e != '0';
   }();
   if (direct) {
+    FQ_REQUIRE(!sync.ready_lower && !sync.ready_upper && !sync.consumed, "FQ_PEER_DIRECT: in-kernel epoch flags are not supported");
     ScopedSpan span(ctx, "k4_spmv_peer_direct");
     stream_reduce(ctx, a->rowblocks.p, a->nrowblocks, a->row_ptr.p, a->col_idx.p, a->values.p, nullptr,
                   SpmvPeerPolicy{y, own, lower ? lower : own, upper ? upper : own, uint32_t(lower ? own_lo : 0), uint32_t(upper ? own_hi : a->ncols)});
@@ -184,7 +210,7 @@ void spmv_apply_peer(fq_ctx* ctx, fq_csr* a, double* own, const double* lower, c
   stream_reduce(ctx, a->rowblocks.p, a->nrowblocks, a->row_ptr.p, a->col_idx.p, a->values.p, nullptr,
                 SpmvHaloPolicy{y, own, lower ? lower : own, upper ? upper : own, uint32_t(held_lo), uint32_t(own_lo),
                                uint32_t(own_hi), uint32_t(held_hi), a->peer_split.p, a->peer_counter.p,
-                               (unsigned long long)(a->peer_launches * ncopy), uint32_t(ncopy)});
+                               (unsigned long long)(a->peer_launches * ncopy), sync, uint32_t(ncopy)});
 }
 
 // Stream-ordered flags in (peer-mapped) device memory: the producer of x publishes an epoch after its last write,

@@ -90,9 +90,10 @@ class PeerHalo:
     """SpMV fused with the halo exchange over peer memory (NVLink 5 / NVSwitch).
 
     Every rank keeps x as a window vector [held_lo, held_hi) allocated by the library; the windows and two
-    epoch flags per rank are mapped into the neighbouring processes with CUDA IPC.  `apply` runs ONE kernel
-    whose gather loads the columns owned by rank-1 / rank+1 straight from their windows (P2P loads), so no halo
-    is ever copied and the NVLink traffic overlaps the row blocks that do not need it.
+    epoch flags per rank are mapped into the neighbouring processes with CUDA IPC.  `apply` runs ONE kernel:
+    its first CTAs wait for the neighbours' published epoch, pull the halo segments out of their windows (P2P
+    loads over NVLink) and signal `consumed`, while all other CTAs already multiply the row blocks that only need
+    owned columns; the boundary row blocks wait on a device counter.  No separate exchange or flag launches.
 
         ph = PeerHalo(ctx, part, rank, x_window)        # collective: exchanges the IPC handles
         ph.publish()                                     # after this rank finished writing its owned x
@@ -100,8 +101,12 @@ class PeerHalo:
         ph.release()                                     # before x is overwritten again: neighbours are done reading
     """
 
-    def __init__(self, ctx, part: SlabPartition, rank: int, x_window, group=None):
+    def __init__(self, ctx, part: SlabPartition, rank: int, x_window, group=None, fused_flags=None):
         import ctypes as C
+        import os
+
+        # the kernel handles the epoch flags itself unless the direct-gather variant is selected
+        self.fused_flags = (os.environ.get("FQ_PEER_DIRECT", "0") in ("", "0")) if fused_flags is None else fused_flags
 
         import torch.distributed as dist
 
@@ -156,12 +161,19 @@ class PeerHalo:
 
         L = _lib.lib()
         r = self.part.ranges[self.rank]
+        lo, hi = self.peers.get(self.rank - 1), self.peers.get(self.rank + 1)
+        lo_base = self.part.ranges[self.rank - 1].held_lo if lo else 0
+        hi_base = self.part.ranges[self.rank + 1].held_lo if hi else 0
+        if self.fused_flags:
+            _lib.check(L.fq_spmv_peer_epoch(self.ctx._h, a._h, self.x._h, r.held_lo, r.own_lo, r.own_hi,
+                                            lo["x"]._h if lo else None, lo_base, lo["ready"]._h if lo else None,
+                                            hi["x"]._h if hi else None, hi_base, hi["ready"]._h if hi else None,
+                                            float(self.epoch), self.consumed._h, y._h))
+            return y
         for p in self.peers.values():
             _lib.check(L.fq_flag_wait(self.ctx._h, p["ready"]._h, float(self.epoch)))
-        lo, hi = self.peers.get(self.rank - 1), self.peers.get(self.rank + 1)
         _lib.check(L.fq_spmv_peer(self.ctx._h, a._h, self.x._h, r.held_lo, r.own_lo, r.own_hi,
-                                  lo["x"]._h if lo else None, self.part.ranges[self.rank - 1].held_lo if lo else 0,
-                                  hi["x"]._h if hi else None, self.part.ranges[self.rank + 1].held_lo if hi else 0, y._h))
+                                  lo["x"]._h if lo else None, lo_base, hi["x"]._h if hi else None, hi_base, y._h))
         _lib.check(L.fq_flag_signal(self.ctx._h, self.consumed._h, float(self.epoch)))
         return y
 

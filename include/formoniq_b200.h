@@ -223,7 +223,10 @@ int fq_matfree_diagonal(fq_ctx* ctx, const fq_matfree* op, fq_vec* d);
  *   fq_vec_ipc_export / fq_vec_ipc_import  map a peer rank's vector (64-byte CUDA IPC handle, shipped by the caller,
  *                                          e.g. with torch.distributed.all_gather_object)
  *   fq_spmv_peer   y = A x; x_window covers [held_lo, ..) of this rank, columns < own_lo come from x_lower (the
- *                  window of rank-1, starting at lower_held_lo), columns >= own_hi from x_upper; NULL = no neighbour
+ *                  window of rank-1, starting at lower_held_lo), columns >= own_hi from x_upper; NULL = no neighbour.
+ *                  The first CTAs of the kernel pull the halo segments into x_window's halo slots (coalesced P2P
+ *                  loads) while the others multiply the row blocks that need owned columns only; the boundary row
+ *                  blocks wait on a device counter.  (FQ_PEER_DIRECT=1: the gather loads remote columns itself.)
  *   fq_flag_signal / fq_flag_wait  stream-ordered epoch flags in peer-mapped memory: a rank signals after its last
  *                  write of x and waits for its neighbours' epochs before the fused SpMV reads them (and the
  *                  reverse before x is overwritten); fq_flag_check reports a wait that timed out (~3 s). */
@@ -231,6 +234,13 @@ int fq_vec_ipc_export(fq_ctx* ctx, const fq_vec* v, unsigned char* handle64);
 int fq_vec_ipc_import(fq_ctx* ctx, const unsigned char* handle64, size_t n, fq_vec** out);
 int fq_spmv_peer(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t held_lo, size_t own_lo, size_t own_hi,
                  const fq_vec* x_lower, size_t lower_held_lo, const fq_vec* x_upper, size_t upper_held_lo, fq_vec* y);
+/* The same kernel also doing the synchronisation: its first CTAs wait until ready_lower / ready_upper (the
+ * neighbours' published epochs, peer-mapped; NULL = none) reach `epoch`, pull the halo segments into x_window over
+ * NVLink while the other CTAs already multiply the interior row blocks, and write `epoch` to `consumed` (this rank's
+ * flag, polled by the neighbours before they overwrite x; NULL = none) as soon as the last halo entry has arrived. */
+int fq_spmv_peer_epoch(fq_ctx* ctx, const fq_csr* a, const fq_vec* x_window, size_t held_lo, size_t own_lo, size_t own_hi,
+                       const fq_vec* x_lower, size_t lower_held_lo, const fq_vec* ready_lower, const fq_vec* x_upper,
+                       size_t upper_held_lo, const fq_vec* ready_upper, double epoch, fq_vec* consumed, fq_vec* y);
 int fq_flag_signal(fq_ctx* ctx, fq_vec* flag, double value);
 int fq_flag_wait(fq_ctx* ctx, const fq_vec* flag, double value);
 int fq_flag_check(fq_ctx* ctx);
