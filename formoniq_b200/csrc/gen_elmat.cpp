@@ -124,53 +124,94 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
   for (const BlockLayout& l : layout) nouts += l.rows * l.cols;
   std::vector<int> map(size_t(nouts), -1);
   std::map<uint32_t, int> slot_of;
-  std::printf("// core n=%d k=%d variant=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, variant, t.ninputs, nouts,
-              t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
-  std::printf("template <class Sink>\n__device__ __forceinline__ void %s(const double* __restrict__ s, Sink& sink) {\n",
-              name.c_str());
-  for (int i = 0; i < t.ninputs; ++i) std::printf("  const double r%d = s[%d];\n", i, i);
-  for (const TapeOp& o : tb.ssa_ops()) {
+  const std::vector<TapeOp> ops = tb.ssa_ops();
+  // Two-stage form for the tile kernel: stage A = everything up to the last division / square root (the
+  // geometry: Gram matrix, determinant, inverse, volume — the latency-bound head of the tape), stage B = the
+  // division-free rest.  `mid` carries the SSA values that are live across the cut.
+  int cut = -1;
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (ops[i].op == OP_DIV || ops[i].op == OP_SQRTABS) cut = int(i);
+  auto is_store = [](const TapeOp& o) { return o.op == OP_STORE || o.op == OP_STOREN || o.op == OP_STOREC; };
+  auto uses = [&](const TapeOp& o, uint32_t* u) -> int {  // SSA registers an op reads
     switch (o.op) {
-      case OP_ADD:
-        std::printf("  const double %s = __dadd_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
-        break;
-      case OP_SUB:
-        std::printf("  const double %s = __dsub_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
-        break;
-      case OP_MUL:
-        std::printf("  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
-        break;
-      case OP_MULC:
-        std::printf("  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(),
-                    cst(tb.consts[o.b]).c_str());
-        break;
-      case OP_DIV:
-        std::printf("  const double %s = __ddiv_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str());
-        break;
-      case OP_SQRTABS:
-        std::printf("  const double %s = __dsqrt_rn(fabs(%s));\n", reg(o.d).c_str(), reg(o.a).c_str());
-        break;
-      case OP_LOADC:
-        std::printf("  const double %s = %s;\n", reg(o.d).c_str(), cst(tb.consts[o.b]).c_str());
-        break;
-      case OP_STORE:
-      case OP_STOREN: {
-        auto it = slot_of.find(o.a);
-        if (it == slot_of.end()) {
-          const int slot = int(slot_of.size());
-          it = slot_of.emplace(o.a, slot).first;
-          std::printf("  sink.template put<0, %d>(%s);\n", slot, reg(o.a).c_str());
+      case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: u[0] = o.a; u[1] = o.b; return 2;
+      case OP_MULC: case OP_SQRTABS: case OP_STORE: case OP_STOREN: u[0] = o.a; return 1;
+      default: return 0;
+    }
+  };
+  std::map<uint32_t, int> mid_of;  // SSA value -> index in mid[]
+  {
+    std::map<uint32_t, int> def_pos;
+    for (int i = 0; i < t.ninputs; ++i) def_pos[uint32_t(i)] = -1;
+    for (size_t i = 0; i < ops.size(); ++i)
+      if (!is_store(ops[i])) def_pos[ops[i].d] = int(i);
+    for (size_t i = 0; i < ops.size(); ++i) {
+      // stores of stage A are deferred to stage B, so their operands cross the cut as well
+      if (int(i) <= cut && !is_store(ops[i])) continue;
+      uint32_t u[2];
+      const int nu = uses(ops[i], u);
+      for (int q = 0; q < nu; ++q)
+        if (def_pos.at(u[q]) <= cut && !mid_of.count(u[q])) {
+          const int idx = int(mid_of.size());
+          mid_of[u[q]] = idx;
         }
-        map[o.d] = it->second | (o.op == OP_STOREN ? 0x100 : 0);
-        break;
-      }
-      case OP_STOREC:
-        if (tb.consts[o.b] != 0.0) throw std::runtime_error("core: non-zero constant mass entry");
-        map[o.d] = -1;
-        break;
     }
   }
+  std::ostringstream full, sa, sb_pro, sb;
+  auto line = [&](const TapeOp& o) -> std::string {
+    char buf[256];
+    switch (o.op) {
+      case OP_ADD: std::snprintf(buf, sizeof buf, "  const double %s = __dadd_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_SUB: std::snprintf(buf, sizeof buf, "  const double %s = __dsub_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_MUL: std::snprintf(buf, sizeof buf, "  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_MULC: std::snprintf(buf, sizeof buf, "  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), cst(tb.consts[o.b]).c_str()); break;
+      case OP_DIV: std::snprintf(buf, sizeof buf, "  const double %s = __ddiv_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_SQRTABS: std::snprintf(buf, sizeof buf, "  const double %s = __dsqrt_rn(fabs(%s));\n", reg(o.d).c_str(), reg(o.a).c_str()); break;
+      case OP_LOADC: std::snprintf(buf, sizeof buf, "  const double %s = %s;\n", reg(o.d).c_str(), cst(tb.consts[o.b]).c_str()); break;
+      default: buf[0] = 0; break;
+    }
+    return buf;
+  };
+  for (int i = 0; i < t.ninputs; ++i) {
+    full << "  const double r" << i << " = s[" << i << "];\n";
+    sa << "  const double r" << i << " = s[" << i << "];\n";
+  }
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const TapeOp& o = ops[i];
+    const bool in_a = int(i) <= cut;
+    if (o.op == OP_STORE || o.op == OP_STOREN) {
+      auto it = slot_of.find(o.a);
+      if (it == slot_of.end()) {
+        const int slot = int(slot_of.size());
+        it = slot_of.emplace(o.a, slot).first;
+        const std::string put = "  sink.template put<0, " + std::to_string(slot) + ">(" + reg(o.a) + ");\n";
+        full << put;
+        (in_a ? sb_pro : sb) << put;
+      }
+      map[o.d] = it->second | (o.op == OP_STOREN ? 0x100 : 0);
+    } else if (o.op == OP_STOREC) {
+      if (tb.consts[o.b] != 0.0) throw std::runtime_error("core: non-zero constant mass entry");
+      map[o.d] = -1;
+    } else {
+      const std::string l = line(o);
+      full << l;
+      (in_a ? sa : sb) << l;
+    }
+  }
+  std::printf("// core n=%d k=%d variant=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, variant, t.ninputs, nouts,
+              t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
+  std::printf("template <class Sink>\n__device__ __forceinline__ void %s(const double* __restrict__ s, Sink& sink) {\n%s}\n",
+              name.c_str(), full.str().c_str());
+  // stage A / stage B
+  const int nmid = int(mid_of.size());
+  std::printf("constexpr int %s_nmid = %d;\n", name.c_str(), nmid > 0 ? nmid : 1);
+  std::printf("__device__ __forceinline__ void %s_a(const double* __restrict__ s, double* __restrict__ mid) {\n%s", name.c_str(),
+              sa.str().c_str());
+  for (const auto& kv : mid_of) std::printf("  mid[%d] = %s;\n", kv.second, reg(kv.first).c_str());
   std::printf("}\n");
+  std::printf("template <class Sink>\n__device__ __forceinline__ void %s_b(const double* __restrict__ mid, Sink& sink) {\n", name.c_str());
+  for (const auto& kv : mid_of) std::printf("  const double %s = mid[%d];\n", reg(kv.first).c_str(), kv.second);
+  std::printf("%s%s}\n", sb_pro.str().c_str(), sb.str().c_str());
   std::printf("static const short %s_map[%d] = {", name.c_str(), nouts > 0 ? nouts : 1);
   for (int i = 0; i < nouts; ++i) std::printf("%s%d", i ? ", " : "", map[size_t(i)]);
   if (nouts == 0) std::printf("0");

@@ -457,6 +457,43 @@ def test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, 
         assert same_bits_mod_zero_sign(va, va0), (kind, g)
 
 
+@pytest.mark.parametrize("kernel", ["w", "p"])
+@pytest.mark.parametrize("dim,shape,variant,k,source", [TILE_CASES[i] for i in (0, 1, 2, 3, 5, 6, 9, 10)])
+def test_tile_fused_warp_specialised_kernels(fq, ctx, monkeypatch, kernel, dim, shape, variant, k, source):
+    # FQ_TILE_KERNEL=w: producer/consumer warps over two slabs; =p: the same with statically dealt tiles and the
+    # two-stage element tape (stage A of the next tile in the shadow of this tile's stage B).  Same bits as the oracle.
+    monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
+    test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, variant, k, source, True)
+
+
+@pytest.mark.parametrize("kernel", ["", "p"])
+def test_tile_fused_many_tiles_per_cta(fq, ctx, monkeypatch, kernel):
+    # enough tiles that every CTA runs several of them (pipelines in steady state, slabs recycled): tile pass == slab pass
+    # == oracle, bitwise, on a jittered mesh
+    if kernel:
+        monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
+    dim, shape = 3, [22, 19, 25]
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = fq.Mesh.kuhn(ctx, dim, shape, jitter=0.2)
+    assert np.array_equal(mesh.lengths(), s)
+    hb = fq.HodgeBlocks.symbolic(mesh, 1)
+    hb.numeric(mesh)
+    first = [blk.download() for blk in hb.blocks]
+    ctx.set_timing(True)
+    ctx.timing_report()
+    for _ in range(3):
+        hb.numeric(mesh)
+    assert _tile_fused_ran(ctx)
+    ctx.set_timing(False)
+    for blk, (kind, g), (rp0, ci0, va0) in zip(hb.blocks, [(O.MASS, 0), (O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2)], first):
+        rp, ci, va = blk.download()
+        assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+        assert same_bits_mod_zero_sign(va, va0), (kind, g)
+        erp, eci, eva = cx.assemble(s, kind, g).arrays()
+        assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci)
+        assert same_bits_mod_zero_sign(va, eva), (kind, g)
+
+
 def test_tile_fused_detects_a_classification_change(fq, ctx):
     # dyadic geometry (many exact zeros) -> jittered geometry (none): the cached pattern is stale and must be rebuilt
     dim, shape = 3, [4, 4, 4]
