@@ -124,6 +124,7 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
   for (const BlockLayout& l : layout) nouts += l.rows * l.cols;
   std::vector<int> map(size_t(nouts), -1);
   std::map<uint32_t, int> slot_of;
+  std::map<int, int> slot_group;  // distinct slot -> 0 (first two stored blocks) or 1 (third)
   const std::vector<TapeOp> ops = tb.ssa_ops();
   // Two-stage form for the tile kernel: stage A = everything up to the last division / square root (the
   // geometry: Gram matrix, determinant, inverse, volume — the latency-bound head of the tape), stage B = the
@@ -157,7 +158,28 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
         }
     }
   }
-  std::ostringstream full, sa, sb_pro, sb;
+  // Stage B in two halves for the alternating producer/consumer kernel: B1 = what the first two stored blocks
+  // (M_{k-1}, M_k) need, B2 = what the third (M_{k+1} or dif_both(k+1)) needs.  An op needed by both halves is
+  // evaluated by both (same operands, same rounding).  The split is usable when no stored value is shared.
+  auto out_group = [&](uint32_t out) {  // 0: blocks 0 and 1, 1: block 2
+    return (layout.size() >= 3 && int(out) >= layout[2].out_offset) ? 1 : 0;
+  };
+  std::map<uint32_t, int> need;  // SSA value -> bit 0: needed by group 0, bit 1: by group 1
+  for (size_t i = ops.size(); i-- > 0;) {
+    const TapeOp& o = ops[i];
+    uint32_t u[2];
+    const int nu = uses(o, u);
+    int mask;
+    if (o.op == OP_STORE || o.op == OP_STOREN)
+      mask = 1 << out_group(o.d);
+    else if (is_store(o))
+      continue;
+    else
+      mask = need.count(o.d) ? need[o.d] : 0;
+    for (int q = 0; q < nu; ++q) need[u[q]] |= mask;
+  }
+  bool split_ok = true;
+  std::ostringstream full, sa, sb_pro, sb, sb1_pro, sb1, sb2_pro, sb2;
   auto line = [&](const TapeOp& o) -> std::string {
     char buf[256];
     switch (o.op) {
@@ -187,6 +209,11 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
         const std::string put = "  sink.template put<0, " + std::to_string(slot) + ">(" + reg(o.a) + ");\n";
         full << put;
         (in_a ? sb_pro : sb) << put;
+        const int g = out_group(o.d);
+        slot_group[it->second] = g;
+        (g == 0 ? (in_a ? sb1_pro : sb1) : (in_a ? sb2_pro : sb2)) << put;
+      } else if (slot_group[it->second] != out_group(o.d)) {
+        split_ok = false;  // one stored value serves both halves
       }
       map[o.d] = it->second | (o.op == OP_STOREN ? 0x100 : 0);
     } else if (o.op == OP_STOREC) {
@@ -196,6 +223,11 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
       const std::string l = line(o);
       full << l;
       (in_a ? sa : sb) << l;
+      if (!in_a) {
+        const int m = need.count(o.d) ? need[o.d] : 0;
+        if (m & 1) sb1 << l;
+        if (m & 2) sb2 << l;
+      }
     }
   }
   std::printf("// core n=%d k=%d variant=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, variant, t.ninputs, nouts,
@@ -212,6 +244,18 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
   std::printf("template <class Sink>\n__device__ __forceinline__ void %s_b(const double* __restrict__ mid, Sink& sink) {\n", name.c_str());
   for (const auto& kv : mid_of) std::printf("  const double %s = mid[%d];\n", reg(kv.first).c_str(), kv.second);
   std::printf("%s%s}\n", sb_pro.str().c_str(), sb.str().c_str());
+  for (int half = 0; half < 2; ++half) {
+    std::printf("template <class Sink>\n__device__ __forceinline__ void %s_b%d(const double* __restrict__ mid, Sink& sink) {\n",
+                name.c_str(), half + 1);
+    for (const auto& kv : mid_of) std::printf("  const double %s = mid[%d];\n", reg(kv.first).c_str(), kv.second);
+    std::printf("%s%s}\n", (half ? sb2_pro : sb1_pro).str().c_str(), (half ? sb2 : sb1).str().c_str());
+  }
+  // bit s of the mask: distinct slot s belongs to the second half
+  unsigned long long gmask_lo = 0, gmask_hi = 0;
+  for (const auto& kv : slot_group)
+    if (kv.second) (kv.first < 64 ? gmask_lo : gmask_hi) |= 1ull << (kv.first & 63);
+  std::printf("constexpr int %s_split_ok = %d;\nstatic const unsigned long long %s_half2[2] = {0x%llxull, 0x%llxull};\n",
+              name.c_str(), (split_ok && slot_of.size() <= 128) ? 1 : 0, name.c_str(), gmask_lo, gmask_hi);
   std::printf("static const short %s_map[%d] = {", name.c_str(), nouts > 0 ? nouts : 1);
   for (int i = 0; i < nouts; ++i) std::printf("%s%d", i ? ", " : "", map[size_t(i)]);
   if (nouts == 0) std::printf("0");

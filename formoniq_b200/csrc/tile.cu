@@ -89,6 +89,7 @@ struct TileParams {
   int recipe_bytes;
   int debug;                        // development knobs (FQ_TILE_DEBUG): 1 skip K1, 2 skip records, 4 skip stores
   int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
+  uint32_t yblock_mask;             // alternating kernel: blocks whose records read second-half slab values only
   int* changed;                     // raised when the zero/non-zero classification differs from the plan's
   unsigned int* ticket;             // dynamic tile scheduler
   unsigned long long* stats;        // debug & 8: per-phase warp cycles [k1, bar_k1, chunk_wait, records, bar_top, other]
@@ -198,9 +199,20 @@ __device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict_
   }
 }
 
+// Alternating kernel: where a consumer warp stands in the tile (first-half records, then second-half records)
+struct AltState {
+  uint64_t* a_empty;
+  uint64_t* b_full;
+  uint32_t parity;
+  bool in_y;
+};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar);
+
 // All records of one chunk of the tile stream, processed by one warp.
+template <bool ALT = false>
 __device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ chunk, const TileParams& P,
-                                             const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane) {
+                                             const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane,
+                                             AltState* alt = nullptr) {
   const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
   const unsigned char* rp = chunk + kChunkHdr;
   for (uint32_t r = 0; r < nrec; ++r) {
@@ -213,6 +225,16 @@ __device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ c
     const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
     const uint16_t* __restrict__ ent1 = ent0 + (stride == 64u ? 32 : 0);
     rp += kRecHdr + stride * (4u + 2u * L);
+    if (ALT) {
+      // first record of this warp that reads the second half of the slab: the warp is done with the first half
+      // (released to the producers, who refill it for the next tile) and needs the second half of THIS tile
+      if (!alt->in_y && ((P.yblock_mask >> b) & 1u)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(alt->a_empty);
+        mbar_wait(alt->b_full, alt->parity);
+        alt->in_y = true;
+      }
+    }
     const TileBlockDev& B = P.blk[b];
     const uint16_t* __restrict__ brec = rec + B.recipe_off;
     const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
@@ -693,6 +715,191 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws2_kernel(Fn fn,
   }
 }
 
+// ---- alternating producer/consumer variant (FQ_TILE_KERNEL=a) ------------------------------------------------------
+// One full-size slab (the same tiles and record streams as the phase-serialised kernel), logically split in two halves:
+//   half 1 = the stored values of M_{k-1} and M_k      read by the records of M_{k-1}, M_k, dif_test(k)
+//   half 2 = the stored values of M_{k+1}              read by the records of dif_both(k+1)
+// The records of a tile are laid out block by block, so every consumer warp first works through first-half records
+// and then through second-half records.  While the consumers are in the second half of tile i the 8 producer warps
+// evaluate half 1 of tile i+1 (tape stage B1), and while they are in the first half of tile i+1 the producers
+// evaluate its half 2 (stage B2): the FP64 pipe works in the shadow of the shared-memory-bound gather with NO second
+// slab, i.e. without shrinking the tiles.  Tiles are dealt statically (tile = blockIdx.x + it * gridDim.x).
+//   a_full / b_full   (8 arrivals)   the producers stored half 1 / half 2 of tile it
+//   a_empty / b_empty (16 arrivals)  every consumer warp is past its first-half / second-half records of tile it
+// Stage A, B1, B2 execute exactly the operations of the unsplit tape: results are bit-identical.
+constexpr int kAltCellsPerThread = 2;  // a tile has at most 2 * 256 cells
+
+template <class Fn, int NE>
+__global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn, const __grid_constant__ TileParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NEE = NE > 0 ? NE : 1;
+  constexpr int NM = Fn::kMid;
+  constexpr int NP = 32 * kWsProducerWarps;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* slab = reinterpret_cast<double*>(smem_raw);
+  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
+  uint64_t* tma_bar = bars;                                       // [consumer warp][2]
+  uint64_t* a_full = bars + kWsConsumerWarps * kSlotsPerWarp;     // the 8 spare barriers of the layout
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* b_full = a_full + 2;
+  uint64_t* b_empty = a_full + 3;
+  if (tid == 0) {
+    mbar_init(a_full, kWsProducerWarps);
+    mbar_init(b_full, kWsProducerWarps);
+    mbar_init(a_empty, kWsConsumerWarps);
+    mbar_init(b_empty, kWsConsumerWarps);
+    for (int i = 0; i < kSlotsPerWarp * kWsConsumerWarps; ++i) mbar_init(&tma_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < P.recipe_bytes / 2; i += kWsThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
+  __syncthreads();
+  const uint32_t G = gridDim.x, t0 = blockIdx.x;
+  if (warp < kWsProducerWarps) {
+    // ------------------------------------------------------------------ producers: K1, two cells per thread
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    auto load_hdr = [&](uint64_t t, uint32_t& cb, uint32_t& nc) {
+      cb = 0;
+      nc = 0;
+      if (t < uint64_t(P.ntiles)) {
+        const uint32_t a = __ldg(P.tile_cell_ptr + t), e = __ldg(P.tile_cell_ptr + t + 1);
+        const uint32_t c0 = __ldg(P.tile_chunk_ptr + t), c1 = __ldg(P.tile_chunk_ptr + t + 1);
+        cb = a;
+        nc = (c1 > c0 && !(P.debug & 1)) ? e - a : 0u;
+      }
+    };
+    auto load_ids = [&](uint32_t cb, uint32_t nc, uint32_t (*eid)[NEE]) {
+#pragma unroll
+      for (int j = 0; j < kAltCellsPerThread; ++j) {
+        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
+        if (c < nc) {
+          const uint32_t* ce = P.tile_cell_edges + size_t(cb + c) * NE;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) eid[j][e] = __ldg(ce + e);
+        }
+      }
+    };
+    uint32_t cb0, nc0, cb1, nc1, cb2, nc2;
+    load_hdr(t0, cb0, nc0);
+    load_hdr(uint64_t(t0) + G, cb1, nc1);
+    uint32_t eid[kAltCellsPerThread][NEE];
+    load_ids(cb0, nc0, eid);
+    for (uint32_t it = 0;; ++it) {
+      const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
+      if (t >= uint64_t(P.ntiles)) break;
+      load_hdr(t + 2 * uint64_t(G), cb2, nc2);  // cell range two tiles ahead (its ids are loaded next iteration)
+      // edge lengths and stage A (metric, inverse, volume) of this tile's cells; the consumers are still busy with the
+      // previous tile, so this latency is off the critical path
+      double mid[kAltCellsPerThread][NM];
+#pragma unroll
+      for (int j = 0; j < kAltCellsPerThread; ++j) {
+        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
+        if (c < nc0) {
+          double sl[NEE];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) sl[e] = __ldg(P.lengths + (eid[j][e] - P.edge_lo));
+          fn.a(sl, mid[j]);
+        }
+      }
+      load_ids(cb1, nc1, eid);  // ids of the next tile: in flight while the two halves are evaluated
+      const uint32_t par_prev = (it - 1u) & 1u;
+      if (it >= 1) mbar_wait(a_empty, par_prev);  // every consumer warp is past the first-half records of the previous tile
+#pragma unroll
+      for (int j = 0; j < kAltCellsPerThread; ++j) {
+        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
+        if (c < nc0) {
+          TileSink sink{slab + c, P.cstride};
+          fn.b1(mid[j], sink);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      if (it >= 1) mbar_wait(b_empty, par_prev);  // ... and past its second-half records
+#pragma unroll
+      for (int j = 0; j < kAltCellsPerThread; ++j) {
+        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
+        if (c < nc0) {
+          TileSink sink{slab + c, P.cstride};
+          fn.b2(mid[j], sink);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full);
+      cb0 = cb1;
+      nc0 = nc1;
+      cb1 = cb2;
+      nc1 = nc2;
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers: K3
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 16 warps x 24 released = the 12288 registers the producers acquire
+    const int cw = warp - kWsProducerWarps;
+    unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
+    uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
+    uint32_t n_issued = 0, n_consumed = 0;
+    uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
+    auto load_chunks = [&](uint64_t t, uint32_t& a, uint32_t& e) {
+      a = 0;
+      e = 0;
+      if (t < uint64_t(P.ntiles)) {
+        a = __ldg(P.tile_chunk_ptr + t);
+        e = __ldg(P.tile_chunk_ptr + t + 1);
+      }
+    };
+    uint32_t c0, c1, c0n = 0, c1n = 0;
+    load_chunks(t0, c0, c1);
+    for (uint32_t it = 0;; ++it) {
+      const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
+      if (t >= uint64_t(P.ntiles)) break;
+      const bool has_next = t + G < uint64_t(P.ntiles);
+      load_chunks(t + G, c0n, c1n);
+      auto issue_more = [&]() {  // keep this warp's double buffer full, crossing into the next tile when this one is done
+        while (n_issued - n_consumed < uint32_t(kSlotsPerWarp)) {
+          if (cur_chunk >= cur_end) {
+            if (cur_it == it && has_next) {
+              cur_it = it + 1;
+              cur_chunk = c0n + cw;
+              cur_end = c1n;
+              if (cur_chunk >= cur_end) break;
+            } else {
+              break;
+            }
+          }
+          if (lane == 0) {
+            uint64_t* bar = &mybar[n_issued & 1u];
+            mbar_expect_tx(bar, kChunkBytes);
+            tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
+          }
+          cur_chunk += kWsConsumerWarps;
+          ++n_issued;
+        }
+      };
+      if (cur_it != it) {
+        cur_it = it;
+        cur_chunk = c0 + cw;
+        cur_end = c1;
+      }
+      issue_more();
+      AltState st{a_empty, b_full, it & 1u, false};
+      mbar_wait(a_full, it & 1u);
+      for (uint32_t c = c0 + cw; c < c1; c += kWsConsumerWarps) {
+        mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
+        gather_chunk<true>(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane, &st);
+        __syncwarp();
+        ++n_consumed;
+        issue_more();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (!st.in_y) mbar_arrive(a_empty);  // this warp had no second-half records in the tile
+        mbar_arrive(b_empty);
+      }
+      c0 = c0n;
+      c1 = c1n;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ plan
 struct TileBlockPlan {
   int no = 1, ni = 1, recipe_off = 0, slot_bits = 7;
@@ -709,6 +916,8 @@ struct TilePlan {
   int nthreads = 512;
   bool ws = false;
   bool ws_pipelined = false;  // FQ_TILE_KERNEL=p: static tile deal + two-stage tape (tile_assemble_ws2_kernel)
+  bool alt = false;           // FQ_TILE_KERNEL=a and the block set splits: tile_assemble_alt_kernel
+  uint32_t yblock_mask = 0;   // blocks reading only second-half values
   uint32_t slab_bytes = 0;
   size_t smem_bytes = 0;
   uint32_t ring_off = 0, rec_off = 0, mbar_off = 0;
@@ -739,6 +948,14 @@ struct TilePlan {
     template <class S>                                                                         \
     __device__ __forceinline__ void b(const double* __restrict__ mid, S& sink) const {         \
       fn##_b(mid, sink);                                                                       \
+    }                                                                                          \
+    template <class S>                                                                         \
+    __device__ __forceinline__ void b1(const double* __restrict__ mid, S& sink) const {        \
+      fn##_b1(mid, sink);                                                                      \
+    }                                                                                          \
+    template <class S>                                                                         \
+    __device__ __forceinline__ void b2(const double* __restrict__ mid, S& sink) const {        \
+      fn##_b2(mid, sink);                                                                      \
     }                                                                                          \
   };
 FQ_GEN_CORE_LIST(FQ_DECLARE_CORE)
@@ -773,8 +990,19 @@ static void launch_tile_ws2(fq_ctx* ctx, const TilePlan& plan, const TileParams&
   tile_assemble_ws2_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE>
+static void launch_tile_alt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    attr_set = true;
+  }
+  tile_assemble_alt_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+}
+template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  if (plan.ws && plan.ws_pipelined)
+  if (plan.alt)
+    launch_tile_alt<Fn, NE>(ctx, plan, params);
+  else if (plan.ws && plan.ws_pipelined)
     launch_tile_ws2<Fn, NE>(ctx, plan, params);
   else if (plan.ws)
     launch_tile_ws<Fn, NE>(ctx, plan, params);
@@ -790,10 +1018,12 @@ static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& par
 struct CoreEntryRt {
   int n, k, variant, nin, ndistinct, nouts;
   const short* map;
+  int split_ok;                      // the stored values split into two halves (gen_elmat.cpp)
+  const unsigned long long* half2;   // bit s: distinct slot s belongs to the second half
   void (*launch)(fq_ctx*, const TilePlan&, const TileParams&);
 };
 #define FQ_CORE_ENTRY(fn, n, k, variant, nin, nd, nout) \
-  CoreEntryRt{n, k, variant, nin, nd, nout, fn##_map, &launch_tile<Core_##fn, nin>},
+  CoreEntryRt{n, k, variant, nin, nd, nout, fn##_map, fn##_split_ok, fn##_half2, &launch_tile<Core_##fn, nin>},
 static const CoreEntryRt g_cores[] = {FQ_GEN_CORE_LIST(FQ_CORE_ENTRY)};
 #undef FQ_CORE_ENTRY
 
@@ -818,13 +1048,16 @@ struct TileConfig {
   size_t smem_cta;  // dynamic shared memory budget of the CTA
   bool ws;          // warp-specialised kernel: two slabs, 8 producer + 16 consumer warps
   bool ws_pipelined = false;  // ... with the software-pipelined producers
+  bool alt = false;           // alternating kernel: the layout of the phase-serialised kernel, 8 + 16 warps
 };
 static TileConfig tile_config() {
   TileConfig c{512, size_t(227) * 1024 - 256, false};
   if (const char* e = std::getenv("FQ_TILE_THREADS"))
     if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256, false};
-  if (const char* e = std::getenv("FQ_TILE_KERNEL"))
+  if (const char* e = std::getenv("FQ_TILE_KERNEL")) {
     if (e[0] == 'w' || e[0] == 'p') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true, e[0] == 'p'};
+    if (e[0] == 'a') c.alt = true;  // everything else as the default: 16 streaming warps, one slab, tiles of <= 512 cells
+  }
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
@@ -1509,6 +1742,25 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   }
   const size_t recipe_bytes = (recipe_u16 * 2 + 15) / 16 * 16;
   if (recipe_bytes > 2048) return nullptr;
+  // alternating kernel: every block must read one half of the slab only, second-half blocks last in the stream
+  if (cfg.alt && core->split_ok && cfg.nthreads == 512) {
+    bool ok = true;
+    uint32_t ymask = 0;
+    for (int b = 0; b < nblocks && ok; ++b) {
+      bool any1 = false, any2 = false;
+      for (uint8_t c : codes8[size_t(b)]) {
+        if (c == 0xFF) continue;
+        const int slot = c & 0x7F;
+        (((core->half2[slot >> 6] >> (slot & 63)) & 1ull) ? any2 : any1) = true;
+      }
+      if (any1 && any2) ok = false;
+      if (any2) ymask |= 1u << b;
+    }
+    for (int b = 0; b + 1 < nblocks; ++b)
+      if (((ymask >> b) & 1u) && !((ymask >> (b + 1)) & 1u)) ok = false;  // a first-half block after a second-half one
+    plan->alt = ok;
+    plan->yblock_mask = ok ? ymask : 0u;
+  }
   const int block = 256;
   const int nv = dim + 1;
   const int ne = int(binom(dim + 1, 2));
@@ -1775,6 +2027,7 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   P.recipe_bytes = plan.recipe_bytes;
   P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
   P.check_classification = (plan.blk[0].dropped_at_build && !(P.debug & 7)) ? 1 : 0;
+  P.yblock_mask = plan.yblock_mask;
   P.changed = plan.changed.p;
   P.ticket = plan.ticket.p;
   P.stats = plan.stats.p;

@@ -21,9 +21,9 @@ except Exception as e:
 }
 {
 run "" 0
-run p 0
-run p 1
-run p 2
-run w 0
-run p 0 2,2,2
+run a 0
+run a 1
+run a 2
+run a 0 4,4,2
+run a 0 5,3,2
 } 2>&1 | tee gpurun_out/exp_ws2.log
