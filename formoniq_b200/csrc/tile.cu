@@ -729,8 +729,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws2_kernel(Fn fn,
 // Stage A, B1, B2 execute exactly the operations of the unsplit tape: results are bit-identical.
 constexpr int kAltCellsPerThread = 2;  // a tile has at most 2 * 256 cells
 
-template <class Fn, int NE>
+template <class Fn, int NE, int PR, int CR>  // registers per producer / consumer thread: 256 * PR + 512 * CR = 768 * 80
 __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn, const __grid_constant__ TileParams P) {
+  static_assert(256 * PR + 512 * CR == 768 * 80 && PR % 8 == 0 && CR % 8 == 0, "register split");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NEE = NE > 0 ? NE : 1;
   constexpr int NM = Fn::kMid;
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn,
   const uint32_t G = gridDim.x, t0 = blockIdx.x;
   if (warp < kWsProducerWarps) {
     // ------------------------------------------------------------------ producers: K1, two cells per thread
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PR));
     auto load_hdr = [&](uint64_t t, uint32_t& cb, uint32_t& nc) {
       cb = 0;
       nc = 0;
@@ -832,7 +833,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn,
     }
   } else {
     // ------------------------------------------------------------------ consumers: K3
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 16 warps x 24 released = the 12288 registers the producers acquire
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CR));  // the 16 consumer warps release what the 8 producer warps acquire
     const int cw = warp - kWsProducerWarps;
     unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
     uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
@@ -918,6 +919,7 @@ struct TilePlan {
   bool ws_pipelined = false;  // FQ_TILE_KERNEL=p: static tile deal + two-stage tape (tile_assemble_ws2_kernel)
   bool alt = false;           // FQ_TILE_KERNEL=a and the block set splits: tile_assemble_alt_kernel
   uint32_t yblock_mask = 0;   // blocks reading only second-half values
+  bool pack = false;          // bank-aware lane packing (slab stride = 0 mod 16)
   uint32_t slab_bytes = 0;
   size_t smem_bytes = 0;
   uint32_t ring_off = 0, rec_off = 0, mbar_off = 0;
@@ -991,12 +993,21 @@ static void launch_tile_ws2(fq_ctx* ctx, const TilePlan& plan, const TileParams&
 }
 template <class Fn, int NE>
 static void launch_tile_alt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    attr_set = true;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = std::getenv("FQ_ALT_REGS");  // tuning: 0 = 128/56, 1 = 112/64, 2 = 96/72 (default)
+    variant = e ? std::atoi(e) : 2;
+    if (variant < 0 || variant > 2) variant = 2;
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, 128, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, 112, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, 96, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
   }
-  tile_assemble_alt_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  if (variant == 1)
+    tile_assemble_alt_kernel<Fn, NE, 112, 64><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  else if (variant == 2)
+    tile_assemble_alt_kernel<Fn, NE, 96, 72><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  else
+    tile_assemble_alt_kernel<Fn, NE, 128, 56><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
@@ -1052,11 +1063,12 @@ struct TileConfig {
 };
 static TileConfig tile_config() {
   TileConfig c{512, size_t(227) * 1024 - 256, false};
+  c.alt = true;  // default: the alternating producer/consumer kernel (FQ_TILE_KERNEL=s: the phase-serialised one)
   if (const char* e = std::getenv("FQ_TILE_THREADS"))
     if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256, false};
   if (const char* e = std::getenv("FQ_TILE_KERNEL")) {
     if (e[0] == 'w' || e[0] == 'p') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true, e[0] == 'p'};
-    if (e[0] == 'a') c.alt = true;  // everything else as the default: 16 streaming warps, one slab, tiles of <= 512 cells
+    if (e[0] == 's') c.alt = false;  // same plan (16 streaming warps, one slab, tiles of <= 512 cells), 512-thread kernel
   }
   return c;
 }
@@ -1337,6 +1349,93 @@ __global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t
       run_len_code[r] = uint32_t(key[i] >> 28) & 0xFFu;
     }
 }
+// ---- bank-aware lane packing ---------------------------------------------------------------------------------------
+// The gather's dominant cost is shared-memory wavefronts of the 8-byte slab loads: 32 lanes read slab[value * cstride +
+// cell slot], served as two half-warps of 16 lanes over 16 8-byte bank pairs.  With cstride a multiple of 16 the bank pair
+// of EVERY load of a contribution is (cell slot mod 16), whatever value it reads, so a half-warp is conflict-free at
+// step j iff its 16 lanes' j-th contributing cells have distinct slots mod 16.  One thread per (tile, L) run deals its
+// non-zeros to the half-warp bins of the records the run occupies anyway (first fit: a bin accepts a non-zero when
+// none of its L residues is taken yet); what fits nowhere goes to the free lane where it collides least.  Positions are
+// a permutation of the lanes the run already had plus its padding lanes: the stream does not grow, the sums do not
+// change (each lane still adds its own contributions in ascending cell order).
+constexpr int kPackMaxBins = 160, kPackMaxLen = 16;
+__global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ run_start,
+                                 const uint32_t* __restrict__ run_tile, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
+                                 const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
+                                 const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
+                                 const uint32_t* __restrict__ tile_local, int enable, uint32_t* __restrict__ ppos) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride) {
+    const uint32_t i0 = run_start[r], i1 = run_start[r + 1], n = i1 - i0;
+    const uint32_t L = run_len_code[r];
+    const uint32_t lanes = rec_lanes(L);
+    const uint32_t nb = (n + lanes - 1u) / lanes * (lanes / 16u);
+    if (!enable || L == 0 || L > uint32_t(kPackMaxLen) || nb > uint32_t(kPackMaxBins) || n <= 1) {
+      for (uint32_t i = i0; i < i1; ++i) ppos[i] = i - i0;
+      continue;
+    }
+    const uint32_t t = run_tile[r];
+    const uint32_t cb = tile_cell_ptr[t], ce = tile_cell_ptr[t + 1];
+    auto residues = [&](uint32_t q, uint8_t* res) {  // slot mod 16 of every contributing cell of non-zero q
+      const uint32_t p0 = contrib_ptr[q];
+      for (uint32_t j = 0; j < L; ++j) {
+        const uint32_t cell = contrib_src[p0 + j] / T;
+        uint32_t lo = cb, hi = ce;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (tile_cells[mid] < cell)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        res[j] = uint8_t(lo < ce ? (tile_local[lo] & 15u) : 0u);
+      }
+    };
+    uint16_t mask[kPackMaxBins][kPackMaxLen];
+    uint8_t cnt[kPackMaxBins];
+    for (uint32_t b = 0; b < nb; ++b) {
+      cnt[b] = 0;
+      for (uint32_t j = 0; j < L; ++j) mask[b][j] = 0;
+    }
+    uint32_t first_open = 0, nleft = 0;
+    uint8_t res[kPackMaxLen];
+    for (uint32_t i = i0; i < i1; ++i) {
+      residues(perm[i], res);
+      while (first_open < nb && cnt[first_open] >= 16) ++first_open;
+      uint32_t where = 0xFFFFFFFFu;
+      for (uint32_t b = first_open; b < nb; ++b) {
+        if (cnt[b] >= 16) continue;
+        bool ok = true;
+        for (uint32_t j = 0; j < L; ++j) ok = ok && !((mask[b][j] >> res[j]) & 1u);
+        if (ok) {
+          where = b;
+          break;
+        }
+      }
+      if (where == 0xFFFFFFFFu) {
+        ppos[i] = 0xFFFFFFFFu;
+        ++nleft;
+        continue;
+      }
+      for (uint32_t j = 0; j < L; ++j) mask[where][j] |= uint16_t(1u << res[j]);
+      ppos[i] = where * 16u + cnt[where]++;
+    }
+    for (uint32_t i = i0; i < i1 && nleft; ++i) {  // the rest: the free lane with the fewest collisions
+      if (ppos[i] != 0xFFFFFFFFu) continue;
+      residues(perm[i], res);
+      uint32_t best = 0xFFFFFFFFu, best_cost = 0xFFFFFFFFu;
+      for (uint32_t b = 0; b < nb; ++b) {
+        if (cnt[b] >= 16) continue;
+        uint32_t cost = 0;
+        for (uint32_t j = 0; j < L; ++j) cost += (mask[b][j] >> res[j]) & 1u;
+        if (cost < best_cost) best_cost = cost, best = b;
+      }
+      for (uint32_t j = 0; j < L; ++j) mask[best][j] |= uint16_t(1u << res[j]);
+      ppos[i] = best * 16u + cnt[best]++;
+      --nleft;
+    }
+  }
+}
 __global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
                                 uint32_t* __restrict__ nrec) {
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -1409,7 +1508,8 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
   }
 }
 // One thread per (sorted) non-zero: its lane of its record.
-__global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n, const uint32_t* __restrict__ run_scan,
+__global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ ppos, uint32_t n,
+                                   const uint32_t* __restrict__ run_scan,
                                    const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_tile,
                                    const uint32_t* __restrict__ run_len_code, const uint32_t* __restrict__ rec_base,
                                    const uint32_t* __restrict__ rec_rel, const uint32_t* __restrict__ tile_chunk_ptr,
@@ -1424,7 +1524,7 @@ __global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, uint32_t n
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t q = perm[i];
     const uint32_t r = run_scan[i] - 1;
-    const uint32_t idx = i - run_start[r];
+    const uint32_t idx = ppos[i];  // lane of the run dealt by pack_runs_kernel (i - run_start[r] when packing is off)
     const uint32_t lanes = rec_lanes(run_len_code[r]);
     const uint32_t k = rec_base[r] + idx / lanes, lane = idx % lanes;
     const uint32_t t = run_tile[r];
@@ -1667,7 +1767,7 @@ static void radix_sort_pairs_u64(fq_ctx* ctx, DevBuf<uint64_t>& keys, DevBuf<uin
 
 // Per-block intermediate data of the plan build (kept until the stream is filled).
 struct BlockBuild {
-  DevBuf<uint32_t> perm, run_scan, run_start, run_tile, run_len, rec_base, rec_tile_ptr, rec_rel;
+  DevBuf<uint32_t> perm, ppos, run_scan, run_start, run_tile, run_len, rec_base, rec_tile_ptr, rec_rel;
   DevBuf<uint8_t> rec_len;
   uint32_t nruns = 0, nrec = 0;
 };
@@ -1822,6 +1922,14 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     for (uint32_t t = 0; t < plan->ntiles; ++t) max_cells = std::max(max_cells, h_ptr[t + 1] - h_ptr[t]);
     if (int(max_cells) > tile_cells_capacity(plan->ndistinct)) return nullptr;
     plan->cstride = int(max_cells) | 1;  // odd stride: distinct rows start on different banks
+    {
+      // bank-aware lane packing wants every load of a contribution on the bank pair of its cell: stride = 0 mod 16
+      const char* e = std::getenv("FQ_TILE_PACK");
+      const int cs16 = (int(max_cells) + 15) / 16 * 16;
+      plan->pack = !(e && e[0] == '0') && !cfg.ws && cs16 <= tile_cells_capacity(plan->ndistinct) + 15 &&
+                   size_t(cs16) * size_t(plan->ndistinct) * sizeof(double) + tile_fixed_smem(cfg) <= cfg.smem_cta;
+      if (plan->pack) plan->cstride = cs16;
+    }
     // dynamic shared memory layout
     const size_t nwarps = plan->ws ? size_t(kWsConsumerWarps) : size_t(plan->nthreads) / 32;
     size_t off = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double);
@@ -1931,6 +2039,11 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
         key.p, head.p, B.run_scan.p, uint32_t(s_nnz), B.run_start.p, B.run_tile.p, B.run_len.p);
     const uint32_t n32 = uint32_t(s_nnz);
     FQ_CUDA(cudaMemcpyAsync(B.run_start.p + B.nruns, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    B.ppos.alloc(s_nnz);
+    pack_runs_kernel<<<grid_for(B.nruns, 64, ctx->sm_count), 64, 0, ctx->stream>>>(
+        B.perm.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.nruns, csr->contrib_ptr.p, csr->contrib_src.p, T,
+        plan->tile_cell_ptr.p, tile_cells.p, tile_local.p, plan->pack ? 1 : 0, B.ppos.p);
+    fq_count_launch(ctx);
     DevBuf<uint32_t> nrec_run(size_t(B.nruns) + 1);
     B.rec_base.alloc(size_t(B.nruns) + 1);
     run_nrec_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
@@ -1988,7 +2101,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     if (csr->s_nnz == 0) continue;
     const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
     stream_fill_kernel<<<grid_for(csr->s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        B.perm.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.rec_base.p, B.rec_rel.p,
+        B.perm.p, B.ppos.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.rec_base.p, B.rec_rel.p,
         plan->tile_chunk_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, plan->blk[b].slot_bits, plan->tile_cell_ptr.p,
         tile_cells.p, tile_local.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0,
         plan->blk[b].no * plan->blk[b].ni == 1 ? direct_map[size_t(b)].p : nullptr, plan->stream.p, d_err.p);

@@ -2,7 +2,7 @@
 # A/B of the tile kernels on the N=128 workload (gpurun): parity tests of the warp-specialised variants first,
 # then ms/step of default / pipelined (p) / old warp-specialised (w), and p with one side disabled.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "warp_specialised or many_tiles" > gpurun_out/exp_ws2_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -k "tile_fused" > gpurun_out/exp_ws2_tests.log 2>&1
 echo "tests exit $?" | tee -a gpurun_out/exp_ws2_tests.log
 tail -3 gpurun_out/exp_ws2_tests.log
 run() {
@@ -21,9 +21,8 @@ except Exception as e:
 }
 {
 run "" 0
-run a 0
-run a 1
-run a 2
-run a 0 4,4,2
-run a 0 5,3,2
+FQ_TILE_PACK=0 run "" 0
+run "" 1
+run s 0
+FQ_TILE_PACK=0 run s 0
 } 2>&1 | tee gpurun_out/exp_ws2.log

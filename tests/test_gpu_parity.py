@@ -457,21 +457,24 @@ def test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, 
         assert same_bits_mod_zero_sign(va, va0), (kind, g)
 
 
-@pytest.mark.parametrize("kernel", ["w", "p", "a"])
+@pytest.mark.parametrize("kernel", ["w", "p", "s"])
 @pytest.mark.parametrize("dim,shape,variant,k,source", [TILE_CASES[i] for i in (0, 1, 2, 3, 5, 6, 9, 10)])
 def test_tile_fused_warp_specialised_kernels(fq, ctx, monkeypatch, kernel, dim, shape, variant, k, source):
     # FQ_TILE_KERNEL=w: producer/consumer warps over two slabs; =p: the same with statically dealt tiles and the
     # two-stage element tape (stage A of the next tile in the shadow of this tile's stage B); =a: one slab in two halves,
-    # the producers refill one half while the consumers gather from the other.  Same bits as the oracle.
+    # the producers refill one half while the consumers gather from the other (the default; =s: phase-serialised).
+    # Same bits as the oracle.
     monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
     test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, variant, k, source, True)
 
 
-@pytest.mark.parametrize("kernel", ["", "p", "a"])
+@pytest.mark.parametrize("kernel", ["", "p", "s", "nopack"])
 def test_tile_fused_many_tiles_per_cta(fq, ctx, monkeypatch, kernel):
     # enough tiles that every CTA runs several of them (pipelines in steady state, slabs recycled): tile pass == slab pass
     # == oracle, bitwise, on a jittered mesh
-    if kernel:
+    if kernel == "nopack":
+        monkeypatch.setenv("FQ_TILE_PACK", "0")   # dense lane order instead of the bank-aware packing
+    elif kernel:
         monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
     dim, shape = 3, [22, 19, 25]
     cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
