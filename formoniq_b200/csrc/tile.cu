@@ -37,6 +37,7 @@
 // + hodge.rs:62-72 (the four HodgeBlocks), numeric phase.
 #include <cub/cub.cuh>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -1363,7 +1364,8 @@ __global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32
                                  const uint32_t* __restrict__ run_tile, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
                                  const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
                                  const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
-                                 const uint32_t* __restrict__ tile_local, int enable, uint32_t* __restrict__ ppos) {
+                                 const uint32_t* __restrict__ tile_local, int enable, uint32_t* __restrict__ ppos,
+                                 unsigned long long* __restrict__ stats /*optional: items, contributions, dense collisions, packed collisions, unplaced*/) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride) {
     const uint32_t i0 = run_start[r], i1 = run_start[r + 1], n = i1 - i0;
@@ -1399,6 +1401,23 @@ __global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32
     }
     uint32_t first_open = 0, nleft = 0;
     uint8_t res[kPackMaxLen];
+    if (stats) {  // collisions of the dense order (lane = position in the run), for comparison
+      unsigned long long coll = 0;
+      for (uint32_t i = i0; i < i1; ++i) {
+        residues(perm[i], res);
+        const uint32_t b = (i - i0) / 16u;
+        for (uint32_t j = 0; j < L; ++j) {
+          coll += (mask[b][j] >> res[j]) & 1u;
+          mask[b][j] |= uint16_t(1u << res[j]);
+        }
+      }
+      atomicAdd(stats + 0, (unsigned long long)n);
+      atomicAdd(stats + 1, (unsigned long long)n * L);
+      atomicAdd(stats + 2, coll);
+      for (uint32_t b = 0; b < nb; ++b)
+        for (uint32_t j = 0; j < L; ++j) mask[b][j] = 0;
+    }
+    unsigned long long pcoll = 0;
     for (uint32_t i = i0; i < i1; ++i) {
       residues(perm[i], res);
       while (first_open < nb && cnt[first_open] >= 16) ++first_open;
@@ -1433,7 +1452,10 @@ __global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32
       for (uint32_t j = 0; j < L; ++j) mask[best][j] |= uint16_t(1u << res[j]);
       ppos[i] = best * 16u + cnt[best]++;
       --nleft;
+      pcoll += best_cost;
+      if (stats) atomicAdd(stats + 4, 1ull);
     }
+    if (stats) atomicAdd(stats + 3, pcoll);
   }
 }
 __global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
@@ -1982,6 +2004,9 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   DevBuf<int> d_err(1);
   FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
   std::vector<BlockBuild> bb(static_cast<size_t>(nblocks));
+  const bool pack_stats = std::getenv("FQ_TILE_PACK_STATS") != nullptr;  // development aid: packing quality per block
+  DevBuf<unsigned long long> d_pack_stats(8);
+  FQ_CUDA(cudaMemsetAsync(d_pack_stats.p, 0, d_pack_stats.bytes(), ctx->stream));
   for (int b = 0; b < nblocks; ++b) {
     fq_csr* csr = csrs[b];
     BlockBuild& B = bb[size_t(b)];
@@ -2042,8 +2067,16 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     B.ppos.alloc(s_nnz);
     pack_runs_kernel<<<grid_for(B.nruns, 64, ctx->sm_count), 64, 0, ctx->stream>>>(
         B.perm.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.nruns, csr->contrib_ptr.p, csr->contrib_src.p, T,
-        plan->tile_cell_ptr.p, tile_cells.p, tile_local.p, plan->pack ? 1 : 0, B.ppos.p);
+        plan->tile_cell_ptr.p, tile_cells.p, tile_local.p, plan->pack ? 1 : 0, B.ppos.p, pack_stats ? d_pack_stats.p : nullptr);
     fq_count_launch(ctx);
+    if (pack_stats) {
+      unsigned long long h[5];
+      FQ_CUDA(cudaMemcpyAsync(h, d_pack_stats.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+      FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      std::fprintf(stderr, "[tile pack] block %d: %llu non-zeros, %llu contributions, collisions dense %llu -> packed %llu (%llu unplaced), stride %d\n",
+                   b, h[0], h[1], h[2], h[3], h[4], plan->cstride);
+      FQ_CUDA(cudaMemsetAsync(d_pack_stats.p, 0, sizeof h, ctx->stream));
+    }
     DevBuf<uint32_t> nrec_run(size_t(B.nruns) + 1);
     B.rec_base.alloc(size_t(B.nruns) + 1);
     run_nrec_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(

@@ -2,7 +2,7 @@
 # A/B of the tile kernels on the N=128 workload (gpurun): parity tests of the warp-specialised variants first,
 # then ms/step of default / pipelined (p) / old warp-specialised (w), and p with one side disabled.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "tile_fused" > gpurun_out/exp_ws2_tests.log 2>&1
+true || timeout 900 python -m pytest tests -m gpu -x -q -k "tile_fused" > gpurun_out/exp_ws2_tests.log 2>&1
 echo "tests exit $?" | tee -a gpurun_out/exp_ws2_tests.log
 tail -3 gpurun_out/exp_ws2_tests.log
 run() {
@@ -20,9 +20,12 @@ except Exception as e:
 "
 }
 {
-run "" 0
-FQ_TILE_PACK=0 run "" 0
-run "" 1
-run s 0
-FQ_TILE_PACK=0 run s 0
+FQ_TILE_PACK_STATS=1 run "" 0
+grep "tile pack" gpurun_out/exp_ws2_err.log
+}
+export FQ_TILE_KERNEL= FQ_TILE_DEBUG=0
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile_assemble -s 2 -c 1 -f -o gpurun_out/r01_tile_pack_n128 \
+    python scripts/microbench.py --n 128 --reps 1 --fused > gpurun_out/r01_tile_pack_n128.log 2>&1
+{
+tail -2 gpurun_out/r01_tile_pack_n128.log
 } 2>&1 | tee gpurun_out/exp_ws2.log
