@@ -1359,7 +1359,7 @@ __global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t
 // none of its L residues is taken yet); what fits nowhere goes to the free lane where it collides least.  Positions are
 // a permutation of the lanes the run already had plus its padding lanes: the stream does not grow, the sums do not
 // change (each lane still adds its own contributions in ascending cell order).
-constexpr int kPackMaxBins = 160, kPackMaxLen = 16;
+constexpr int kPackMaxBins = 160, kPackMaxLen = 24;
 __global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ run_start,
                                  const uint32_t* __restrict__ run_tile, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
                                  const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
@@ -1368,12 +1368,12 @@ __global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32
                                  unsigned long long* __restrict__ stats /*optional: items, contributions, dense collisions, packed collisions, unplaced*/) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride) {
-    const uint32_t i0 = run_start[r], i1 = run_start[r + 1], n = i1 - i0;
+    const uint32_t r0 = run_start[r], r1 = run_start[r + 1], ntot = r1 - r0;
     const uint32_t L = run_len_code[r];
     const uint32_t lanes = rec_lanes(L);
-    const uint32_t nb = (n + lanes - 1u) / lanes * (lanes / 16u);
-    if (!enable || L == 0 || L > uint32_t(kPackMaxLen) || nb > uint32_t(kPackMaxBins) || n <= 1) {
-      for (uint32_t i = i0; i < i1; ++i) ppos[i] = i - i0;
+    const uint32_t nb_tot = (ntot + lanes - 1u) / lanes * (lanes / 16u);  // half-warp bins of the records the run occupies
+    if (!enable || L == 0 || L > uint32_t(kPackMaxLen) || ntot <= 1) {
+      for (uint32_t i = r0; i < r1; ++i) ppos[i] = i - r0;
       continue;
     }
     const uint32_t t = run_tile[r];
@@ -1395,67 +1395,75 @@ __global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32
     };
     uint16_t mask[kPackMaxBins][kPackMaxLen];
     uint8_t cnt[kPackMaxBins];
-    for (uint32_t b = 0; b < nb; ++b) {
-      cnt[b] = 0;
-      for (uint32_t j = 0; j < L; ++j) mask[b][j] = 0;
-    }
-    uint32_t first_open = 0, nleft = 0;
     uint8_t res[kPackMaxLen];
-    if (stats) {  // collisions of the dense order (lane = position in the run), for comparison
-      unsigned long long coll = 0;
+    // long runs are dealt segment by segment (kPackMaxBins bins each; only the last one owns the run's padding lanes)
+    constexpr uint32_t kSeg = uint32_t(kPackMaxBins) * 16u;
+    for (uint32_t s0 = 0; s0 < ntot; s0 += kSeg) {
+      const uint32_t i0 = r0 + s0, n = min(kSeg, ntot - s0), i1 = i0 + n;
+      const uint32_t nb = min(uint32_t(kPackMaxBins), nb_tot - s0 / 16u);
+      auto clear = [&]() {
+        for (uint32_t b = 0; b < nb; ++b) {
+          cnt[b] = 0;
+          for (uint32_t j = 0; j < L; ++j) mask[b][j] = 0;
+        }
+      };
+      clear();
+      if (stats) {  // collisions of the dense order (lane = position in the run), for comparison
+        unsigned long long coll = 0;
+        for (uint32_t i = i0; i < i1; ++i) {
+          residues(perm[i], res);
+          const uint32_t b = (i - i0) / 16u;
+          for (uint32_t j = 0; j < L; ++j) {
+            coll += (mask[b][j] >> res[j]) & 1u;
+            mask[b][j] |= uint16_t(1u << res[j]);
+          }
+        }
+        atomicAdd(stats + 0, (unsigned long long)n);
+        atomicAdd(stats + 1, (unsigned long long)n * L);
+        atomicAdd(stats + 2, coll);
+        clear();
+      }
+      uint32_t first_open = 0, nleft = 0;
+      unsigned long long pcoll = 0;
       for (uint32_t i = i0; i < i1; ++i) {
         residues(perm[i], res);
-        const uint32_t b = (i - i0) / 16u;
-        for (uint32_t j = 0; j < L; ++j) {
-          coll += (mask[b][j] >> res[j]) & 1u;
-          mask[b][j] |= uint16_t(1u << res[j]);
+        while (first_open < nb && cnt[first_open] >= 16) ++first_open;
+        uint32_t where = 0xFFFFFFFFu;
+        for (uint32_t b = first_open; b < nb; ++b) {
+          if (cnt[b] >= 16) continue;
+          bool ok = true;
+          for (uint32_t j = 0; j < L; ++j) ok = ok && !((mask[b][j] >> res[j]) & 1u);
+          if (ok) {
+            where = b;
+            break;
+          }
         }
-      }
-      atomicAdd(stats + 0, (unsigned long long)n);
-      atomicAdd(stats + 1, (unsigned long long)n * L);
-      atomicAdd(stats + 2, coll);
-      for (uint32_t b = 0; b < nb; ++b)
-        for (uint32_t j = 0; j < L; ++j) mask[b][j] = 0;
-    }
-    unsigned long long pcoll = 0;
-    for (uint32_t i = i0; i < i1; ++i) {
-      residues(perm[i], res);
-      while (first_open < nb && cnt[first_open] >= 16) ++first_open;
-      uint32_t where = 0xFFFFFFFFu;
-      for (uint32_t b = first_open; b < nb; ++b) {
-        if (cnt[b] >= 16) continue;
-        bool ok = true;
-        for (uint32_t j = 0; j < L; ++j) ok = ok && !((mask[b][j] >> res[j]) & 1u);
-        if (ok) {
-          where = b;
-          break;
+        if (where == 0xFFFFFFFFu) {
+          ppos[i] = 0xFFFFFFFFu;
+          ++nleft;
+          continue;
         }
+        for (uint32_t j = 0; j < L; ++j) mask[where][j] |= uint16_t(1u << res[j]);
+        ppos[i] = s0 + where * 16u + cnt[where]++;
       }
-      if (where == 0xFFFFFFFFu) {
-        ppos[i] = 0xFFFFFFFFu;
-        ++nleft;
-        continue;
+      for (uint32_t i = i0; i < i1 && nleft; ++i) {  // the rest: the free lane with the fewest collisions
+        if (ppos[i] != 0xFFFFFFFFu) continue;
+        residues(perm[i], res);
+        uint32_t best = 0xFFFFFFFFu, best_cost = 0xFFFFFFFFu;
+        for (uint32_t b = 0; b < nb; ++b) {
+          if (cnt[b] >= 16) continue;
+          uint32_t cost = 0;
+          for (uint32_t j = 0; j < L; ++j) cost += (mask[b][j] >> res[j]) & 1u;
+          if (cost < best_cost) best_cost = cost, best = b;
+        }
+        for (uint32_t j = 0; j < L; ++j) mask[best][j] |= uint16_t(1u << res[j]);
+        ppos[i] = s0 + best * 16u + cnt[best]++;
+        --nleft;
+        pcoll += best_cost;
+        if (stats) atomicAdd(stats + 4, 1ull);
       }
-      for (uint32_t j = 0; j < L; ++j) mask[where][j] |= uint16_t(1u << res[j]);
-      ppos[i] = where * 16u + cnt[where]++;
+      if (stats) atomicAdd(stats + 3, pcoll);
     }
-    for (uint32_t i = i0; i < i1 && nleft; ++i) {  // the rest: the free lane with the fewest collisions
-      if (ppos[i] != 0xFFFFFFFFu) continue;
-      residues(perm[i], res);
-      uint32_t best = 0xFFFFFFFFu, best_cost = 0xFFFFFFFFu;
-      for (uint32_t b = 0; b < nb; ++b) {
-        if (cnt[b] >= 16) continue;
-        uint32_t cost = 0;
-        for (uint32_t j = 0; j < L; ++j) cost += (mask[b][j] >> res[j]) & 1u;
-        if (cost < best_cost) best_cost = cost, best = b;
-      }
-      for (uint32_t j = 0; j < L; ++j) mask[best][j] |= uint16_t(1u << res[j]);
-      ppos[i] = best * 16u + cnt[best]++;
-      --nleft;
-      pcoll += best_cost;
-      if (stats) atomicAdd(stats + 4, 1ull);
-    }
-    if (stats) atomicAdd(stats + 3, pcoll);
   }
 }
 __global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_len_code, uint32_t nruns,

@@ -2,7 +2,7 @@
 # A/B of the tile kernels on the N=128 workload (gpurun): parity tests of the warp-specialised variants first,
 # then ms/step of default / pipelined (p) / old warp-specialised (w), and p with one side disabled.
 mkdir -p gpurun_out
-true || timeout 900 python -m pytest tests -m gpu -x -q -k "tile_fused" > gpurun_out/exp_ws2_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -k "tile_fused" > gpurun_out/exp_ws2_tests.log 2>&1
 echo "tests exit $?" | tee -a gpurun_out/exp_ws2_tests.log
 tail -3 gpurun_out/exp_ws2_tests.log
 run() {
