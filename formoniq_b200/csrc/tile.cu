@@ -892,10 +892,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn,
         issue_more();
       }
       __syncwarp();
-      if (lane == 0) {
-        if (!st.in_y) mbar_arrive(a_empty);  // this warp had no second-half records in the tile
-        mbar_arrive(b_empty);
+      if (!st.in_y) {
+        // This warp had no second-half records in the tile.  It must still observe b_full(it) before it arrives on
+        // b_empty: otherwise it could run a whole tile ahead of a slow warp and its arrival for tile it+1 would
+        // complete phase it of b_empty while that warp still reads the second half of tile it.
+        if (lane == 0) mbar_arrive(a_empty);
+        mbar_wait(b_full, it & 1u);
       }
+      if (lane == 0) mbar_arrive(b_empty);
       c0 = c0n;
       c1 = c1n;
     }
