@@ -56,7 +56,7 @@ constexpr uint32_t kNoDest = 1u;
 #define FQ_TILE_CHUNK_BYTES 1536
 #endif
 constexpr int kChunkBytes = FQ_TILE_CHUNK_BYTES;  // TMA granule of the tile stream; records never straddle a chunk
-constexpr int kChunkHdr = 16;       // u32 nrec, u32 block + padding
+constexpr int kChunkHdr = 16;       // u32 nrec + padding
 constexpr int kRecHdr = 16;         // u32 (L | block << 8 | lanes << 16) + padding
 // a record is 16 + lanes * (4 + 2 L) bytes and must fit a chunk after its 16-byte header
 constexpr int kMaxLen64 = ((kChunkBytes - 32) / 64 - 4) / 2;   // 2 KB chunks: 64 lanes up to L = 13
@@ -210,19 +210,15 @@ struct AltState {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar);
 
 // All records of one chunk of the tile stream, processed by one warp.
-// The records of one chunk, all of one block (the layout never mixes blocks in a chunk): everything that depends on
-// the block - recipe shape, recipe table, value array - is resolved once per chunk, the record loop is straight-line.
-template <int NO, int NI>
-__device__ __forceinline__ void gather_records(const unsigned char* __restrict__ rp, uint32_t nrec, const TileParams& P,
-                                               const TileBlockDev& B, const double* __restrict__ slab,
-                                               const uint16_t* __restrict__ rec, int lane) {
-  const uint16_t* __restrict__ brec = rec + B.recipe_off;
-  const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
-  double* __restrict__ values = B.values;
-  const bool check = P.check_classification != 0, no_store = (P.debug & 4) != 0;
+template <bool ALT = false>
+__device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ chunk, const TileParams& P,
+                                             const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane,
+                                             AltState* alt = nullptr) {
+  const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
+  const unsigned char* rp = chunk + kChunkHdr;
   for (uint32_t r = 0; r < nrec; ++r) {
     const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
-    const uint32_t L = h & 0xFFu, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
+    const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
     const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
     const uint32_t l0 = lane & (stride - 1u);  // lanes beyond a 16-wide record shadow the first ones and never store
     const uint32_t dest0 = uint32_t(lane) < stride ? destp[l0] : kPadDest;
@@ -230,53 +226,38 @@ __device__ __forceinline__ void gather_records(const unsigned char* __restrict__
     const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
     const uint16_t* __restrict__ ent1 = ent0 + (stride == 64u ? 32 : 0);
     rp += kRecHdr + stride * (4u + 2u * L);
+    if (ALT) {
+      // first record of this warp that reads the second half of the slab: the warp is done with the first half
+      // (released to the producers, who refill it for the next tile) and needs the second half of THIS tile
+      if (!alt->in_y && ((P.yblock_mask >> b) & 1u)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(alt->a_empty);
+        mbar_wait(alt->b_full, alt->parity);
+        alt->in_y = true;
+      }
+    }
+    const TileBlockDev& B = P.blk[b];
+    const uint16_t* __restrict__ brec = rec + B.recipe_off;
+    const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
     double acc0 = 0.0, acc1 = 0.0;
     bool any0 = false, any1 = false;
-    if constexpr (NO == 0) {
-      // zero space: every contribution is an exact zero
-    } else if constexpr (NO == 1 && NI == 1) {
-      gather_record_direct(ent0, ent1, stride, L, slab, acc0, acc1, any0, any1);
-    } else {
-      gather_record<NO, NI>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1);
+    switch (B.no * 8 + B.ni) {
+      case 0: break;  // zero space: every contribution is an exact zero
+      case 1 * 8 + 1: gather_record_direct(ent0, ent1, stride, L, slab, acc0, acc1, any0, any1); break;
+      case 1 * 8 + 2: gather_record<1, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 1 * 8 + 3: gather_record<1, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 1 * 8 + 4: gather_record<1, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 2 * 8 + 2: gather_record<2, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      case 3 * 8 + 3: gather_record<3, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
+      default: gather_record<4, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
     }
     // padding lanes carry zero entries (they read slab[0]) and never store
-    if (check && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) || (dest1 != kPadDest && (dest1 != kNoDest) != any1)))
+    if (P.check_classification && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) ||
+                                   (dest1 != kPadDest && (dest1 != kNoDest) != any1)))
       *P.changed = 1;
-    if (no_store) continue;
-    if (dest0 > kNoDest) values[dest0 - 2u] = acc0;
-    if (dest1 > kNoDest) values[dest1 - 2u] = acc1;
-  }
-}
-
-// All records of one chunk of the tile stream, processed by one warp.  Chunk header: {u32 records, u32 block}.
-template <bool ALT = false>
-__device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ chunk, const TileParams& P,
-                                             const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane,
-                                             AltState* alt = nullptr) {
-  const uint2 ch = *reinterpret_cast<const uint2*>(chunk);
-  const uint32_t nrec = (P.debug & 2) ? 0u : ch.x, b = ch.y & 3u;
-  if (nrec == 0) return;
-  if (ALT) {
-    // first chunk of this warp that reads the second half of the slab: the warp is done with the first half
-    // (released to the producers, who refill it for the next tile) and needs the second half of THIS tile
-    if (!alt->in_y && ((P.yblock_mask >> b) & 1u)) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(alt->a_empty);
-      mbar_wait(alt->b_full, alt->parity);
-      alt->in_y = true;
-    }
-  }
-  const TileBlockDev& B = P.blk[b];
-  const unsigned char* rp = chunk + kChunkHdr;
-  switch (B.no * 8 + B.ni) {
-    case 0: gather_records<0, 0>(rp, nrec, P, B, slab, rec, lane); break;
-    case 1 * 8 + 1: gather_records<1, 1>(rp, nrec, P, B, slab, rec, lane); break;
-    case 1 * 8 + 2: gather_records<1, 2>(rp, nrec, P, B, slab, rec, lane); break;
-    case 1 * 8 + 3: gather_records<1, 3>(rp, nrec, P, B, slab, rec, lane); break;
-    case 1 * 8 + 4: gather_records<1, 4>(rp, nrec, P, B, slab, rec, lane); break;
-    case 2 * 8 + 2: gather_records<2, 2>(rp, nrec, P, B, slab, rec, lane); break;
-    case 3 * 8 + 3: gather_records<3, 3>(rp, nrec, P, B, slab, rec, lane); break;
-    default: gather_records<4, 4>(rp, nrec, P, B, slab, rec, lane); break;
+    if (P.debug & 4) continue;
+    if (dest0 > kNoDest) B.values[dest0 - 2u] = acc0;
+    if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
   }
 }
 
@@ -1530,7 +1511,6 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
     uint32_t off = 0;          // byte offset within the tile's stream; 0 = no chunk opened yet
     uint32_t in_chunk = 0;     // records in the open chunk
-    int chunk_block = -1;      // block of the open chunk (a chunk never mixes blocks: the gather dispatches per chunk)
     unsigned char* base = pass ? stream + size_t(tile_chunk_ptr[t]) * kChunkBytes : nullptr;
     for (int b = 0; b < A.nblocks; ++b) {
       const TileLayoutBlock& B = A.blk[b];
@@ -1538,14 +1518,13 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
         const uint32_t L = B.rec_len[k];
         const uint32_t size = rec_bytes(L);
         const uint32_t chunk = off / kChunkBytes;
-        if (off % kChunkBytes == 0 || off + size > (chunk + 1) * kChunkBytes || chunk_block != b) {  // open a new chunk
+        if (off % kChunkBytes == 0 || off + size > (chunk + 1) * kChunkBytes) {  // open a new chunk
           if (off % kChunkBytes != 0) {
-            if (pass) *reinterpret_cast<uint2*>(base + size_t(chunk) * kChunkBytes) = make_uint2(in_chunk, uint32_t(chunk_block));
+            if (pass) *reinterpret_cast<uint32_t*>(base + size_t(chunk) * kChunkBytes) = in_chunk;
             off = (chunk + 1) * kChunkBytes;
           }
           off += kChunkHdr;
           in_chunk = 0;
-          chunk_block = b;
         }
         if (pass) {
           B.rec_rel[k] = off / 16u;
@@ -1556,7 +1535,7 @@ __global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, 
       }
     }
     if (off % kChunkBytes != 0) {
-      if (pass) *reinterpret_cast<uint2*>(base + size_t(off / kChunkBytes) * kChunkBytes) = make_uint2(in_chunk, uint32_t(chunk_block));
+      if (pass) *reinterpret_cast<uint32_t*>(base + size_t(off / kChunkBytes) * kChunkBytes) = in_chunk;
       off = (off / kChunkBytes + 1) * kChunkBytes;
     }
     if (!pass) tile_nchunks[t] = off / kChunkBytes;
