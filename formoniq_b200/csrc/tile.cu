@@ -730,9 +730,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws2_kernel(Fn fn,
 // Stage A, B1, B2 execute exactly the operations of the unsplit tape: results are bit-identical.
 constexpr int kAltCellsPerThread = 2;  // a tile has at most 2 * 256 cells
 
-template <class Fn, int NE, int PR, int CR>  // registers per producer / consumer thread: 256 * PR + 512 * CR = 768 * 80
-__global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn, const __grid_constant__ TileParams P) {
-  static_assert(256 * PR + 512 * CR == 768 * 80 && PR % 8 == 0 && CR % 8 == 0, "register split");
+// NC consumer warps; PR / CR registers per producer / consumer thread after setmaxnreg (the launch allocates
+// LR = 65536 / threads rounded down to 8 per thread; what the consumers release must cover what the producers acquire)
+template <class Fn, int NE, int NC, int PR, int CR>
+__global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble_alt_kernel(Fn fn, const __grid_constant__ TileParams P) {
+  constexpr int kThreads = 32 * (kWsProducerWarps + NC);
+  constexpr int LR = 65536 / kThreads / 8 * 8;
+  static_assert(PR % 8 == 0 && CR % 8 == 0 && CR <= LR && PR >= LR && 32 * NC * (LR - CR) >= 256 * (PR - LR), "register split");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NEE = NE > 0 ? NE : 1;
   constexpr int NM = Fn::kMid;
@@ -742,19 +746,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn,
   uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
   uint64_t* tma_bar = bars;                                       // [consumer warp][2]
-  uint64_t* a_full = bars + kWsConsumerWarps * kSlotsPerWarp;     // the 8 spare barriers of the layout
+  uint64_t* a_full = bars + NC * kSlotsPerWarp;     // the 8 spare barriers of the layout
   uint64_t* a_empty = a_full + 1;
   uint64_t* b_full = a_full + 2;
   uint64_t* b_empty = a_full + 3;
   if (tid == 0) {
     mbar_init(a_full, kWsProducerWarps);
     mbar_init(b_full, kWsProducerWarps);
-    mbar_init(a_empty, kWsConsumerWarps);
-    mbar_init(b_empty, kWsConsumerWarps);
-    for (int i = 0; i < kSlotsPerWarp * kWsConsumerWarps; ++i) mbar_init(&tma_bar[i], 1);
+    mbar_init(a_empty, NC);
+    mbar_init(b_empty, NC);
+    for (int i = 0; i < kSlotsPerWarp * NC; ++i) mbar_init(&tma_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < P.recipe_bytes / 2; i += kWsThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
+  for (int i = tid; i < P.recipe_bytes / 2; i += kThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
   __syncthreads();
   const uint32_t G = gridDim.x, t0 = blockIdx.x;
   if (warp < kWsProducerWarps) {
@@ -872,7 +876,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn,
             mbar_expect_tx(bar, kChunkBytes);
             tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
           }
-          cur_chunk += kWsConsumerWarps;
+          cur_chunk += NC;
           ++n_issued;
         }
       };
@@ -884,7 +888,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_alt_kernel(Fn fn,
       issue_more();
       AltState st{a_empty, b_full, it & 1u, false};
       mbar_wait(a_full, it & 1u);
-      for (uint32_t c = c0 + cw; c < c1; c += kWsConsumerWarps) {
+      for (uint32_t c = c0 + cw; c < c1; c += NC) {
         mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
         gather_chunk<true>(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane, &st);
         __syncwarp();
@@ -925,6 +929,7 @@ struct TilePlan {
   bool alt = false;           // FQ_TILE_KERNEL=a and the block set splits: tile_assemble_alt_kernel
   uint32_t yblock_mask = 0;   // blocks reading only second-half values
   bool pack = false;          // bank-aware lane packing (slab stride = 0 mod 16)
+  int stream_warps = 0;       // alternating kernel with 20 / 24 consumer warps (0: 16)
   uint32_t slab_bytes = 0;
   size_t smem_bytes = 0;
   uint32_t ring_off = 0, rec_off = 0, mbar_off = 0;
@@ -996,23 +1001,34 @@ static void launch_tile_ws2(fq_ctx* ctx, const TilePlan& plan, const TileParams&
   }
   tile_assemble_ws2_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
+template <class Fn, int NE, int NC, int PR, int CR>
+static void launch_tile_alt_v(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, NC, PR, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024 - 256));
+    attr_set = true;
+  }
+  tile_assemble_alt_kernel<Fn, NE, NC, PR, CR><<<plan.grid, 32 * (kWsProducerWarps + NC), plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+}
 template <class Fn, int NE>
 static void launch_tile_alt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static int variant = -1;
   if (variant < 0) {
-    const char* e = std::getenv("FQ_ALT_REGS");  // tuning: 0 = 128/56, 1 = 112/64, 2 = 96/72 (default)
+    const char* e = std::getenv("FQ_ALT_REGS");  // tuning (16 consumer warps): 0 = 128/56, 1 = 112/64, 2 = 96/72 (default)
     variant = e ? std::atoi(e) : 2;
     if (variant < 0 || variant > 2) variant = 2;
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, 128, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, 112, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, 96, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
   }
-  if (variant == 1)
-    tile_assemble_alt_kernel<Fn, NE, 112, 64><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
-  else if (variant == 2)
-    tile_assemble_alt_kernel<Fn, NE, 96, 72><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  if (plan.stream_warps == 24)
+    launch_tile_alt_v<Fn, NE, 24, 88, 56>(ctx, plan, params);
+  else if (plan.stream_warps == 20)
+    launch_tile_alt_v<Fn, NE, 20, 88, 64>(ctx, plan, params);
+  else if (variant == 1)
+    launch_tile_alt_v<Fn, NE, 16, 112, 64>(ctx, plan, params);
+  else if (variant == 0)
+    launch_tile_alt_v<Fn, NE, 16, 128, 56>(ctx, plan, params);
   else
-    tile_assemble_alt_kernel<Fn, NE, 128, 56><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+    launch_tile_alt_v<Fn, NE, 16, 96, 72>(ctx, plan, params);
 }
 template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
@@ -1065,6 +1081,7 @@ struct TileConfig {
   bool ws;          // warp-specialised kernel: two slabs, 8 producer + 16 consumer warps
   bool ws_pipelined = false;  // ... with the software-pipelined producers
   bool alt = false;           // alternating kernel: the layout of the phase-serialised kernel, 8 + 16 warps
+  int stream_warps = 0;       // warps that stream chunks (0: nthreads / 32, or the 16 consumers of the w/p kernels)
 };
 static TileConfig tile_config() {
   TileConfig c{512, size_t(227) * 1024 - 256, false};
@@ -1075,10 +1092,16 @@ static TileConfig tile_config() {
     if (e[0] == 'w' || e[0] == 'p') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true, e[0] == 'p'};
     if (e[0] == 's') c.alt = false;  // same plan (16 streaming warps, one slab, tiles of <= 512 cells), 512-thread kernel
   }
+  if (c.alt)
+    if (const char* e = std::getenv("FQ_ALT_CONSUMERS")) {  // tuning: 20 or 24 consumer warps (larger ring, smaller tiles)
+      const int n = std::atoi(e);
+      if (n == 20 || n == 24) c.stream_warps = n;
+    }
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
-  const size_t nwarps = c.ws ? size_t(kWsConsumerWarps) : size_t(c.nthreads) / 32;  // warps that stream chunks
+  const size_t nwarps = c.stream_warps ? size_t(c.stream_warps)
+                                       : (c.ws ? size_t(kWsConsumerWarps) : size_t(c.nthreads) / 32);  // warps that stream chunks
   return nwarps * kSlotsPerWarp * kChunkBytes /*ring*/ + 2048 /*recipes*/ + (nwarps * kSlotsPerWarp + 8) * 8 /*mbarriers*/ +
          512 /*alignment slack*/;
 }
@@ -1856,6 +1879,7 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   plan->nthreads = cfg.nthreads;
   plan->ws = cfg.ws;
   plan->ws_pipelined = cfg.ws_pipelined;
+  plan->stream_warps = cfg.stream_warps;
   if (plan->ntiles >= (1u << 27)) return nullptr;
   // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)
   std::vector<std::vector<uint8_t>> codes8(static_cast<size_t>(nblocks));
@@ -1965,7 +1989,8 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
       if (plan->pack) plan->cstride = cs16;
     }
     // dynamic shared memory layout
-    const size_t nwarps = plan->ws ? size_t(kWsConsumerWarps) : size_t(plan->nthreads) / 32;
+    const size_t nwarps = plan->stream_warps ? size_t(plan->stream_warps)
+                                             : (plan->ws ? size_t(kWsConsumerWarps) : size_t(plan->nthreads) / 32);
     size_t off = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double);
     off = (off + 127) / 128 * 128;
     plan->slab_bytes = uint32_t(off);
