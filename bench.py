@@ -340,8 +340,9 @@ def run_b200(args):
                                "SpMV gather, epoch flags instead of a collective" if world > 1 else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
-                     "kernel": ("tile_assemble_kernel: K1 element masses + K3 segmented reduction fused in shared memory, "
-                                "all four blocks in one persistent launch (rank 0)") if fused else
+                     "kernel": ("tile_assemble_alt_kernel: K1 element masses (8 producer warps) + K3 segmented reduction "
+                                "(16 consumer warps) fused in shared memory, all four blocks in one persistent launch "
+                                "(rank 0)") if fused else
                                "numeric assembly pipeline K1 elmat -> K3 gather -> compaction (rank 0, all four blocks)",
                      "algorithmic_bytes_per_step": asm_bytes, "peak_source": peak_src,
                      "kernel_ms_per_launch": per_launch},
