@@ -520,6 +520,33 @@ class ElementOperator:
             pass
 
 
+class LinearFormPlan:
+    """formoniq::galerkin::assemble_vector (galerkin.rs:279-312) for linear forms of one grade on one mesh: the
+    load vector ell_sigma = sum_K elvec_K[position of sigma in K], cells in ascending order (`LinearForm::assemble`).
+    The element vectors come from the caller (`LinearForm::element` evaluates a user field: host code)."""
+
+    def __init__(self, mesh: Mesh, grade: int):
+        self.ctx, self.mesh, self.grade = mesh.ctx, mesh, grade  # the mesh must outlive the plan
+        h = C.c_void_p()
+        check(_lib.lib().fq_linear_form_create(mesh.ctx._h, mesh._h, grade, C.byref(h)))
+        self._h = h
+        nr, nc = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().fq_matfree_shape(h, C.byref(nr), C.byref(nc)))
+        self.nrows = nr.value
+
+    def assemble(self, element_vectors: np.ndarray, out: DeviceVector | None = None) -> DeviceVector:
+        ev = np.ascontiguousarray(element_vectors, dtype=np.float64)
+        y = out if out is not None else DeviceVector(self.ctx, self.nrows)
+        check(_lib.lib().fq_linear_form_assemble(self.ctx._h, self._h, ev.ctypes.data_as(C.c_void_p), y._h))
+        return y
+
+    def __del__(self):
+        try:
+            _lib.lib().fq_linear_form_destroy(self._h)
+        except Exception:
+            pass
+
+
 class _HodgePlan:
     def __init__(self, handle):
         self._h = handle

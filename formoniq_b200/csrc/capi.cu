@@ -869,6 +869,32 @@ int fq_matfree_create(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_
   *out = op;
   FQ_API_END
 }
+int fq_linear_form_create(fq_ctx* ctx, const fq_mesh* mesh, int grade, fq_matfree** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  fq_matfree* op = matfree_new();
+  try {
+    vector_plan_build(ctx, mesh, grade, op);
+  } catch (...) {
+    matfree_delete(op);
+    throw;
+  }
+  *out = op;
+  FQ_API_END
+}
+int fq_linear_form_assemble(fq_ctx* ctx, const fq_matfree* plan, const double* element_vectors, fq_vec* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && plan && out, "null argument");
+  FQ_REQUIRE(out->d.n == matfree_nrows(plan), "the load vector has one entry per simplex of the form's grade");  // galerkin.rs:285-286
+  FQ_REQUIRE(element_vectors || matfree_nrows(plan) == 0, "null element vectors");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  vector_plan_assemble(ctx, plan, element_vectors, out->d.p);
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffer may be reused on return
+  FQ_API_END
+}
+int fq_linear_form_destroy(fq_matfree* plan) { return fq_matfree_destroy(plan); }
+
 int fq_matfree_refresh(fq_ctx* ctx, fq_matfree* op) {
   FQ_API_BEGIN
   FQ_REQUIRE(ctx && op, "null argument");

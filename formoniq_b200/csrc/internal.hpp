@@ -62,7 +62,9 @@ void csr_restrict(fq_ctx* ctx, const fq_csr* a, const uint32_t* rows_keep, size_
 }  // namespace fq
 struct fq_matfree;
 namespace fq {
-void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, ::fq_matfree* op);
+void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, ::fq_matfree* op, bool with_slab = true);
+void vector_plan_build(fq_ctx* ctx, const fq_mesh* mesh, int grade, ::fq_matfree* op);
+void vector_plan_assemble(fq_ctx* ctx, const ::fq_matfree* op, const double* h_elvecs, double* y);
 void matfree_refresh(fq_ctx* ctx, ::fq_matfree* op);
 void matfree_apply(fq_ctx* ctx, const ::fq_matfree* op, const double* x, double* y);
 void matfree_diagonal(fq_ctx* ctx, const ::fq_matfree* op, double* d);

@@ -72,7 +72,7 @@ struct MfGatherPolicy {
   __device__ __forceinline__ void store(uint32_t dof, double sum, bool) const { y[dof] = sum; }
 };
 
-void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_matfree* op) {
+void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_matfree* op, bool with_slab) {
   const int dim = mesh->dim;
   int tg, rg;
   kind_grades(kind, grade, tg, rg);
@@ -92,7 +92,7 @@ void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_mat
   op->mesh = mesh;
   const size_t nplaces = op->ncells * size_t(op->nt);
   FQ_REQUIRE(nplaces < (size_t(1) << 32), "more than 2^32 (cell, position) places: not supported");
-  op->slab.alloc(op->ncells * size_t(op->nt) * size_t(op->nr));
+  if (with_slab) op->slab.alloc(op->ncells * size_t(op->nt) * size_t(op->nr));
   op->local.alloc(nplaces ? nplaces : 1);
   // converse incidence: places sorted by DOF, ascending cell within a DOF (stable sort of cell-major places)
   const int block = 256;
@@ -114,6 +114,20 @@ void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, fq_mat
   fq_count_launch(ctx, 6);
   stream_build_blocks(ctx, op->face_ptr.p, op->nrows, nplaces, op->blocks, op->nblocks);
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// LinearForm::assemble (formoniq/src/galerkin.rs:279-312): the converse incidence of one grade, no element matrices.
+// assemble_vector's reduction "for cells in order: galvec[face] += elvec[position]" is stage 2 of the matrix-free apply.
+void vector_plan_build(fq_ctx* ctx, const fq_mesh* mesh, int grade, fq_matfree* op) {
+  FQ_REQUIRE(grade >= 0 && grade <= mesh->dim, "linear form: the grade must lie in [0, dim]");
+  matfree_build(ctx, mesh, KIND_MASS, grade, op, /*with_slab=*/false);
+}
+void vector_plan_assemble(fq_ctx* ctx, const fq_matfree* op, const double* h_elvecs, double* y) {
+  if (op->nrows == 0) return;
+  const size_t nplaces = op->ncells * size_t(op->nt);
+  FQ_CUDA(cudaMemcpyAsync(op->local.p, h_elvecs, nplaces * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ScopedSpan span(ctx, "lf_gather");
+  stream_reduce(ctx, op->blocks.p, op->nblocks, op->face_ptr.p, op->face_src.p, nullptr, op->local.p, MfGatherPolicy{y});
 }
 
 void matfree_refresh(fq_ctx* ctx, fq_matfree* op) {  // element matrices from the mesh's current edge lengths

@@ -216,6 +216,19 @@ int fq_matfree_shape(const fq_matfree* op, size_t* nrows, size_t* ncols);
 int fq_matfree_apply(fq_ctx* ctx, const fq_matfree* op, const fq_vec* x, fq_vec* y);
 int fq_matfree_diagonal(fq_ctx* ctx, const fq_matfree* op, fq_vec* d);
 
+/* ---- LinearForm::assemble: formoniq::galerkin::assemble_vector (formoniq/src/galerkin.rs:279-312) ---------------
+ * The Galerkin (load) vector of a linear form of the given grade: ell_sigma = sum over the cells K containing sigma, in
+ * cell order, of elvec_K[position of sigma in K] - the reference's "for cell in cells: galvec[face] += elvec[ilocal]"
+ * (its `!= 0.0` filter only skips additions of zero), as a per-DOF segmented sum over the converse incidence: no
+ * atomics, the reference's summation order, bit-identical to the CPU.  `element_vectors` is a HOST array, cell-major
+ * [ncells][C(dim+1, grade+1)] in the local face order of SimplexRef::faces(grade): LinearForm::element evaluates a user
+ * closure (a Section sampled at quadrature nodes, operators.rs:607-635) and stays host code, as in the reference.
+ * A plan (the converse incidence, one radix sort) serves any number of right-hand sides on the same mesh; the handle is
+ * an fq_matfree without element matrices. */
+int fq_linear_form_create(fq_ctx* ctx, const fq_mesh* mesh, int grade, fq_matfree** out);
+int fq_linear_form_assemble(fq_ctx* ctx, const fq_matfree* plan, const double* element_vectors, fq_vec* out);
+int fq_linear_form_destroy(fq_matfree* plan);
+
 /* ---- SpMV fused with the halo exchange (one process per GPU, NVLink 5 / NVSwitch peer memory) -----------------
  * The reference is single-process; under the owner-computes row partition the only exchange step of the path is
  * the x halo of `LinearOperator::apply`.  Instead of exchanging halos and then multiplying, the gather of the SpMV

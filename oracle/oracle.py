@@ -329,3 +329,17 @@ def jitter_coords(coords, shape, amplitude=0.2):
         for v in range(coords.shape[0]):
             coords[v, a] += amplitude * h * pseudo_random(a, v)
     return coords
+
+
+def assemble_vector(cx: "Complex", grade: int, element_vectors: np.ndarray) -> np.ndarray:
+    """Restatement of formoniq::galerkin::assemble_vector (formoniq/src/galerkin.rs:279-312): cells in order, the
+    non-zero entries of each element vector as (global face, value) pairs, then `galvec[irow] += val` sequentially."""
+    faces = cx.cell_faces(grade)                      # [ncells][C(n+1, grade+1)], SimplexRef::faces order
+    ev = np.asarray(element_vectors, dtype=np.float64).reshape(faces.shape)
+    out = np.zeros(cx.nsimplices(grade))
+    rows = faces.reshape(-1)
+    vals = ev.reshape(-1)
+    keep = vals != 0.0                                # galerkin.rs:299
+    # np.add.at applies the additions one by one in index order == the reference's sequential loop
+    np.add.at(out, rows[keep], vals[keep])
+    return out

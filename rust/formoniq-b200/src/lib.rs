@@ -21,6 +21,7 @@ use simplicial::topology::{complex::Complex, incidence::FaceIncidence};
 #[repr(C)] pub struct fq_csr { _p: [u8; 0] }
 #[repr(C)] pub struct fq_vec { _p: [u8; 0] }
 #[repr(C)] pub struct fq_hodge { _p: [u8; 0] }
+#[repr(C)] pub struct fq_matfree { _p: [u8; 0] }
 
 // include/formoniq_b200.h
 unsafe extern "C" {
@@ -48,6 +49,10 @@ unsafe extern "C" {
   fn fq_vec_scale(ctx: *mut fq_ctx, x: *mut fq_vec, alpha: c_double) -> c_int;
   fn fq_vec_axpy(ctx: *mut fq_ctx, y: *mut fq_vec, alpha: c_double, x: *const fq_vec) -> c_int;
   fn fq_spmv(ctx: *mut fq_ctx, a: *const fq_csr, x: *const fq_vec, y: *mut fq_vec) -> c_int;
+  fn fq_linear_form_create(ctx: *mut fq_ctx, mesh: *const fq_mesh, grade: c_int, out: *mut *mut fq_matfree) -> c_int;
+  fn fq_linear_form_assemble(ctx: *mut fq_ctx, plan: *const fq_matfree, element_vectors: *const c_double,
+                             out: *mut fq_vec) -> c_int;
+  fn fq_linear_form_destroy(plan: *mut fq_matfree) -> c_int;
   // HodgeBlocks (hodge.rs:62-99): symbolic once, numeric per geometry (one fused kernel from the second pass on)
   fn fq_mesh_set_lengths(ctx: *mut fq_ctx, mesh: *mut fq_mesh, edge_lengths_sq: *const c_double) -> c_int;
   fn fq_hodge_symbolic(ctx: *mut fq_ctx, mesh: *const fq_mesh, grade: c_int, sigma_row_begin: usize, sigma_row_end: usize,
@@ -168,6 +173,18 @@ impl Clone for DeviceVector<'_> {
   }
 }
 impl Drop for DeviceVector<'_> { fn drop(&mut self) { unsafe { fq_vec_destroy(self.raw) }; } }
+impl<'d> DeviceVector<'d> {
+  pub fn zeros(dev: &'d Device, n: usize) -> Self {
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_vec_create(dev.0, n, &mut raw) });
+    Self { dev, raw }
+  }
+  pub fn to_host(&self) -> nalgebra::DVector<f64> {
+    let mut host = nalgebra::DVector::zeros(unsafe { fq_vec_len(self.raw) });
+    check(unsafe { fq_vec_download(self.dev.0, self.raw, host.as_mut_ptr()) });
+    host
+  }
+}
 impl InnerProductSpace for DeviceVector<'_> {
   type Scalar = f64;
   fn zeros_like(&self) -> Self {
@@ -234,6 +251,32 @@ impl<'d> GpuHodgeBlocks<'d> {
   }
 }
 impl Drop for GpuHodgeBlocks<'_> { fn drop(&mut self) { unsafe { fq_hodge_destroy(self.raw) }; } }
+
+// ---- LinearForm::assemble (formoniq/src/galerkin.rs:279-312) -----------------------------------------------------
+// `LinearForm::element` evaluates a user `Section` at quadrature nodes and stays host code; the element vectors of all
+// cells are evaluated with rayon exactly as `assemble_vector` does and handed over cell-major, the device does the
+// per-DOF sums (cells in order, no atomics).  One plan per (mesh, grade) serves every right-hand side.
+pub struct GpuLinearFormPlan<'d> { dev: &'d Device, raw: *mut fq_matfree, grade: usize, ndofs: usize }
+impl<'d> GpuLinearFormPlan<'d> {
+  pub fn new(dev: &'d Device, mesh: &DeviceMesh<'d>, topology: &Complex, grade: usize) -> Self {
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_linear_form_create(dev.0, mesh.raw, grade as c_int, &mut raw) });
+    Self { dev, raw, grade, ndofs: topology.skeleton(grade).len() }
+  }
+  /// Drop-in for `form.assemble(topology, geometry)` of any `LinearForm` of this plan's grade.
+  pub fn assemble(&self, topology: &Complex, geometry: &MeshLengthsSq, form: &impl formoniq::galerkin::LinearForm)
+    -> formoniq::galerkin::GalerkinVector {
+    use rayon::prelude::*;
+    assert_eq!(form.test_grade().index(), self.grade, "the plan was built for another grade");
+    let elvecs: Vec<f64> = topology.cells().handle_par_iter()
+      .flat_map_iter(|cell| form.element(&geometry.cell_metric(cell), cell).iter().copied().collect::<Vec<_>>())
+      .collect();
+    let out = DeviceVector::zeros(self.dev, self.ndofs);
+    check(unsafe { fq_linear_form_assemble(self.dev.0, self.raw, elvecs.as_ptr(), out.raw) });
+    formoniq::galerkin::GalerkinVector::new(form.test_grade(), out.to_host())
+  }
+}
+impl Drop for GpuLinearFormPlan<'_> { fn drop(&mut self) { unsafe { fq_linear_form_destroy(self.raw) }; } }
 
 // `iterative::krylov::{cg, minres}` now run unmodified on `DeviceCsr` with
 // `iterative::precond::Identity<DeviceVector>` (precond.rs:16-41).

@@ -827,3 +827,38 @@ def test_eigen_hodge_laplace_evp_on_the_device_blocks(fq, ctx):
         assert r <= 1e-9
     ref = spla.eigsh(ah.tocsc(), k=k, M=bh.tocsc(), sigma=1.0, which="LM", return_eigenvectors=False)
     assert np.abs(np.sort(vals) - np.sort(ref)).max() <= 1e-8 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------ LinearForm::assemble (galerkin.rs:279-312)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,shape,grade", [(2, [7, 5], 0), (2, [6, 6], 1), (3, [5, 4, 6], 1), (3, [4, 4, 4], 2), (3, [3, 4, 3], 3),
+                                             (1, [9], 1)])
+def test_linear_form_assembly_is_the_reference_scatter(fq, ctx, dim, shape, grade):
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    nl = O.nlocal(dim, grade)
+    rng = np.random.default_rng(7 * dim + grade)
+    ev = rng.standard_normal((cx.ncells, nl))
+    ev[rng.random(ev.shape) < 0.2] = 0.0          # exact zeros are skipped by the reference (no effect on the sums)
+    plan = fq.LinearFormPlan(mesh, grade)
+    got = plan.assemble(ev).to_numpy()
+    exp = O.assemble_vector(cx, grade, ev)
+    assert got.shape == exp.shape
+    assert same_bits_mod_zero_sign(got, exp)
+    # the defining law of the reference's own test (galerkin.rs:330-372): with the source a Whitney form lambda_tau
+    # the load vector is the column tau of the mass matrix, so ell(u) = u^T M e_tau
+    mass = cx.assemble(s, O.MASS, grade).to_scipy().toarray()
+    elm = cx.elmat_batch(s, O.MASS, grade)
+    faces = cx.cell_faces(grade)
+    tau = int(faces[cx.ncells // 2, 0])
+    ev_tau = np.zeros((cx.ncells, nl))
+    for c in range(cx.ncells):
+        hit = np.flatnonzero(faces[c] == tau)
+        if hit.size:
+            ev_tau[c] = elm[c][:, hit[0]]
+    col = plan.assemble(ev_tau).to_numpy()
+    assert np.abs(col - mass[:, tau]).max() <= 1e-12 * np.abs(mass[:, tau]).max()
+    # a second right-hand side through the same plan, and the shape contract
+    assert same_bits_mod_zero_sign(plan.assemble(2.0 * ev).to_numpy(), O.assemble_vector(cx, grade, 2.0 * ev))
+    with pytest.raises(fq.FormoniqError):
+        plan.assemble(ev, out=fq.DeviceVector(ctx, exp.shape[0] + 1))

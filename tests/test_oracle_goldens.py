@@ -456,3 +456,31 @@ def test_pseudo_random_is_splitmix():
     for seed in range(3):
         for idx in (0, 1, 17, 12345):
             assert O.pseudo_random(seed, idx) == ref(seed, idx)
+
+
+def test_assemble_vector_law_of_the_reference():
+    # crates/formoniq/src/galerkin.rs:330-372: with the source a Whitney form lambda_tau the assembled load is the
+    # column tau of the mass matrix; and the restatement equals the plain sequential loop of galerkin.rs:305-309.
+    for dim, n, grade in ((2, 4, 1), (3, 3, 1), (3, 2, 2)):
+        cx, s, _ = kuhn_problem(dim, n, jitter=True)
+        nl = O.nlocal(dim, grade)
+        faces = cx.cell_faces(grade)
+        elm = cx.elmat_batch(s, O.MASS, grade)
+        mass = cx.assemble(s, O.MASS, grade).to_scipy().toarray()
+        for tau in (0, cx.nsimplices(grade) // 2, cx.nsimplices(grade) - 1):
+            ev = np.zeros((cx.ncells, nl))
+            for c in range(cx.ncells):
+                hit = np.flatnonzero(faces[c] == tau)
+                if hit.size:
+                    ev[c] = elm[c][:, hit[0]]
+            got = O.assemble_vector(cx, grade, ev)
+            assert np.abs(got - mass[:, tau]).max() <= 1e-13 * np.abs(mass[:, tau]).max()
+        rng = np.random.default_rng(dim)
+        ev = rng.standard_normal((cx.ncells, nl))
+        ev[rng.random(ev.shape) < 0.3] = 0.0
+        naive = np.zeros(cx.nsimplices(grade))
+        for c in range(cx.ncells):
+            for i in range(nl):
+                if ev[c, i] != 0.0:
+                    naive[faces[c, i]] += ev[c, i]
+        assert np.array_equal(O.assemble_vector(cx, grade, ev), naive)
