@@ -200,32 +200,6 @@ __device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict_
   }
 }
 
-// Two consecutive 64-lane records of one run (same block, same L) processed together: four independent chains per
-// lane, twice the loads in flight per warp and one loop / one dispatch for 128 non-zeros.
-template <int NO, int NI>
-__device__ __forceinline__ void gather_record_pair(const uint16_t* __restrict__ entA, const uint16_t* __restrict__ entB,
-                                                   uint32_t L, const double* __restrict__ slab,
-                                                   const uint16_t* __restrict__ brec, uint32_t sb, uint32_t slot_mask,
-                                                   double (&acc)[4], bool (&any)[4]) {
-#pragma unroll 1
-  for (uint32_t j = 0; j < L; ++j) {
-    const uint32_t e[4] = {entA[j * 64u], entA[j * 64u + 32u], entB[j * 64u], entB[j * 64u + 32u]};
-    double v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if constexpr (NO == 1 && NI == 1)
-        v[q] = signed_load(slab, e[q]);
-      else
-        v[q] = recipe_value<NO, NI>(e[q], slab, brec, sb, slot_mask);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      any[q] = any[q] || (v[q] != 0.0);
-      acc[q] = __dadd_rn(acc[q], v[q]);
-    }
-  }
-}
-
 // Alternating kernel: where a consumer warp stands in the tile (first-half records, then second-half records)
 struct AltState {
   uint64_t* a_empty;
@@ -236,7 +210,7 @@ struct AltState {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar);
 
 // All records of one chunk of the tile stream, processed by one warp.
-template <bool ALT = false, bool PAIR = false>
+template <bool ALT = false>
 __device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ chunk, const TileParams& P,
                                              const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane,
                                              AltState* alt = nullptr) {
@@ -245,51 +219,6 @@ __device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ c
   for (uint32_t r = 0; r < nrec; ++r) {
     const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
     const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
-    if (PAIR && stride == 64u && r + 1 < nrec) {
-      const uint32_t rbytes = kRecHdr + 64u * (4u + 2u * L);
-      if (*reinterpret_cast<const uint32_t*>(rp + rbytes) == h) {  // the next record continues the run: take both
-        const TileBlockDev& B = P.blk[b];
-        const int shape = B.no * 8 + B.ni;
-        if (shape == 1 * 8 + 1 || shape == 1 * 8 + 3 || shape == 2 * 8 + 2) {
-          if (ALT) {
-            if (!alt->in_y && ((P.yblock_mask >> b) & 1u)) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(alt->a_empty);
-              mbar_wait(alt->b_full, alt->parity);
-              alt->in_y = true;
-            }
-          }
-          const uint32_t* dA = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
-          const uint32_t* dB = reinterpret_cast<const uint32_t*>(rp + rbytes + kRecHdr);
-          const uint32_t dest[4] = {dA[lane], dA[lane + 32], dB[lane], dB[lane + 32]};
-          const uint16_t* __restrict__ entA = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 256) + lane;
-          const uint16_t* __restrict__ entB = reinterpret_cast<const uint16_t*>(rp + rbytes + kRecHdr + 256) + lane;
-          rp += 2u * rbytes;
-          ++r;
-          const uint16_t* __restrict__ brec = rec + B.recipe_off;
-          const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          bool any[4] = {false, false, false, false};
-          if (shape == 1 * 8 + 1)
-            gather_record_pair<1, 1>(entA, entB, L, slab, brec, sb, slot_mask, acc, any);
-          else if (shape == 1 * 8 + 3)
-            gather_record_pair<1, 3>(entA, entB, L, slab, brec, sb, slot_mask, acc, any);
-          else
-            gather_record_pair<2, 2>(entA, entB, L, slab, brec, sb, slot_mask, acc, any);
-          if (P.check_classification) {
-            bool bad = false;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) bad = bad || (dest[q] != kPadDest && (dest[q] != kNoDest) != any[q]);
-            if (bad) *P.changed = 1;
-          }
-          if (P.debug & 4) continue;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (dest[q] > kNoDest) B.values[dest[q] - 2u] = acc[q];
-          continue;
-        }
-      }
-    }
     const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
     const uint32_t l0 = lane & (stride - 1u);  // lanes beyond a 16-wide record shadow the first ones and never store
     const uint32_t dest0 = uint32_t(lane) < stride ? destp[l0] : kPadDest;
@@ -803,7 +732,7 @@ constexpr int kAltCellsPerThread = 2;  // a tile has at most 2 * 256 cells
 
 // NC consumer warps; PR / CR registers per producer / consumer thread after setmaxnreg (the launch allocates
 // LR = 65536 / threads rounded down to 8 per thread; what the consumers release must cover what the producers acquire)
-template <class Fn, int NE, int NC, int PR, int CR, bool PAIR>
+template <class Fn, int NE, int NC, int PR, int CR>
 __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble_alt_kernel(Fn fn, const __grid_constant__ TileParams P) {
   constexpr int kThreads = 32 * (kWsProducerWarps + NC);
   constexpr int LR = 65536 / kThreads / 8 * 8;
@@ -834,7 +763,7 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
   const uint32_t G = gridDim.x, t0 = blockIdx.x;
   if (warp < kWsProducerWarps) {
     // ------------------------------------------------------------------ producers: K1, two cells per thread
-    if constexpr (PR != LR) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PR));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PR));
     auto load_hdr = [&](uint64_t t, uint32_t& cb, uint32_t& nc) {
       cb = 0;
       nc = 0;
@@ -909,8 +838,7 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
     }
   } else {
     // ------------------------------------------------------------------ consumers: K3
-    if constexpr (CR != LR)
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CR));  // the 16 consumer warps release what the 8 producer warps acquire
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CR));  // the 16 consumer warps release what the 8 producer warps acquire
     const int cw = warp - kWsProducerWarps;
     unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
     uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
@@ -962,7 +890,7 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
       mbar_wait(a_full, it & 1u);
       for (uint32_t c = c0 + cw; c < c1; c += NC) {
         mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
-        gather_chunk<true, PAIR>(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane, &st);
+        gather_chunk<true>(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane, &st);
         __syncwarp();
         ++n_consumed;
         issue_more();
@@ -1073,34 +1001,34 @@ static void launch_tile_ws2(fq_ctx* ctx, const TilePlan& plan, const TileParams&
   }
   tile_assemble_ws2_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
-template <class Fn, int NE, int NC, int PR, int CR, bool PAIR>
+template <class Fn, int NE, int NC, int PR, int CR>
 static void launch_tile_alt_v(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static bool attr_set = false;
   if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, NC, PR, CR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, NC, PR, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024 - 256));
     attr_set = true;
   }
-  tile_assemble_alt_kernel<Fn, NE, NC, PR, CR, PAIR><<<plan.grid, 32 * (kWsProducerWarps + NC), plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  tile_assemble_alt_kernel<Fn, NE, NC, PR, CR><<<plan.grid, 32 * (kWsProducerWarps + NC), plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE>
 static void launch_tile_alt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static int variant = -1;
   if (variant < 0) {
-    // tuning: registers per producer / consumer thread and record pairing (four chains per lane)
-    //   0 = 128/56, 1 = 112/64, 2 = 96/72, 3 = 96/72 + pairs, 4 = 80/80 + pairs, 5 = 112/64 + pairs
-    const char* e = std::getenv("FQ_ALT_REGS");
+    const char* e = std::getenv("FQ_ALT_REGS");  // tuning (16 consumer warps): 0 = 128/56, 1 = 112/64, 2 = 96/72 (default)
     variant = e ? std::atoi(e) : 2;
-    if (variant < 0 || variant > 5) variant = 2;
+    if (variant < 0 || variant > 2) variant = 2;
   }
-  switch (variant) {
-    case 0: launch_tile_alt_v<Fn, NE, 16, 128, 56, false>(ctx, plan, params); break;
-    case 1: launch_tile_alt_v<Fn, NE, 16, 112, 64, false>(ctx, plan, params); break;
-    case 3: launch_tile_alt_v<Fn, NE, 16, 96, 72, true>(ctx, plan, params); break;
-    case 4: launch_tile_alt_v<Fn, NE, 16, 80, 80, true>(ctx, plan, params); break;
-    case 5: launch_tile_alt_v<Fn, NE, 16, 112, 64, true>(ctx, plan, params); break;
-    default: launch_tile_alt_v<Fn, NE, 16, 96, 72, false>(ctx, plan, params); break;
-  }
+  if (plan.stream_warps == 24)
+    launch_tile_alt_v<Fn, NE, 24, 88, 56>(ctx, plan, params);
+  else if (plan.stream_warps == 20)
+    launch_tile_alt_v<Fn, NE, 20, 88, 64>(ctx, plan, params);
+  else if (variant == 1)
+    launch_tile_alt_v<Fn, NE, 16, 112, 64>(ctx, plan, params);
+  else if (variant == 0)
+    launch_tile_alt_v<Fn, NE, 16, 128, 56>(ctx, plan, params);
+  else
+    launch_tile_alt_v<Fn, NE, 16, 96, 72>(ctx, plan, params);
 }
 template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
@@ -1164,7 +1092,11 @@ static TileConfig tile_config() {
     if (e[0] == 'w' || e[0] == 'p') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true, e[0] == 'p'};
     if (e[0] == 's') c.alt = false;  // same plan (16 streaming warps, one slab, tiles of <= 512 cells), 512-thread kernel
   }
-
+  if (c.alt)
+    if (const char* e = std::getenv("FQ_ALT_CONSUMERS")) {  // tuning: 20 or 24 consumer warps (larger ring, smaller tiles)
+      const int n = std::atoi(e);
+      if (n == 20 || n == 24) c.stream_warps = n;
+    }
   return c;
 }
 static size_t tile_fixed_smem(const TileConfig& c) {
