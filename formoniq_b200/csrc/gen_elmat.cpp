@@ -126,7 +126,7 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
   std::map<uint32_t, int> slot_of;
   std::map<int, int> slot_group;  // distinct slot -> 0 (first two stored blocks) or 1 (third)
   const std::vector<TapeOp> ops = tb.ssa_ops();
-  // Two-stage form for the tile kernel: stage A = everything up to the last division / square root (the
+  // Staged form for the tile kernel: stage A = everything up to the last division / square root (the
   // geometry: Gram matrix, determinant, inverse, volume — the latency-bound head of the tape), stage B = the
   // division-free rest.  `mid` carries the SSA values that are live across the cut.
   int cut = -1;
@@ -241,9 +241,6 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
               sa.str().c_str());
   for (const auto& kv : mid_of) std::printf("  mid[%d] = %s;\n", kv.second, reg(kv.first).c_str());
   std::printf("}\n");
-  std::printf("template <class Sink>\n__device__ __forceinline__ void %s_b(const double* __restrict__ mid, Sink& sink) {\n", name.c_str());
-  for (const auto& kv : mid_of) std::printf("  const double %s = mid[%d];\n", reg(kv.first).c_str(), kv.second);
-  std::printf("%s%s}\n", sb_pro.str().c_str(), sb.str().c_str());
   for (int half = 0; half < 2; ++half) {
     std::printf("template <class Sink>\n__device__ __forceinline__ void %s_b%d(const double* __restrict__ mid, Sink& sink) {\n",
                 name.c_str(), half + 1);

@@ -547,176 +547,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws_kernel(Fn fn, 
   }
 }
 
-// ---- warp-specialised, software-pipelined variant (FQ_TILE_KERNEL=p) ---------------------------------------------
-// Same roles and slabs as tile_assemble_ws_kernel, but nothing latency-bound is left on the producers' critical path:
-//   * tiles are dealt statically (tile = blockIdx.x + it * gridDim.x), so every thread derives the tile headers itself
-//     with uniform loads issued three tiles ahead - no ticket atomic, no header hand-off barrier;
-//   * the element tape is split at its last division / square root (gen_elmat.cpp): stage A (Gram matrix, determinant,
-//     inverse, volume: dependent loads + the division chain) of tile it+1 is evaluated right after stage B (the
-//     division-free bulk, FP64-pipe bound) of tile it, from edge lengths whose loads were issued before stage B and
-//     edge ids loaded one tile earlier still.  A producer iteration is then stage B + stage A back to back with all
-//     its global loads already in flight, and the consumers (shared-memory bound) set the pace.
-// Stage A then stage B execute exactly the operations of the unsplit tape, in the same order: results are bit-identical.
-template <class Fn, int NE>
-__global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws2_kernel(Fn fn, const __grid_constant__ TileParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int NEE = NE > 0 ? NE : 1;
-  constexpr int NM = Fn::kMid;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* slabs[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + P.slab_bytes)};
-  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
-  uint64_t* slab_full = bars + 2;     // [2]  8 arrivals: every producer warp has stored its cells
-  uint64_t* slab_empty = bars + 4;    // [2]  16 arrivals: every consumer warp is done with the tile
-  uint64_t* tma_bar = bars + 6;       // [consumer warp][2]
-  if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&slab_full[b], kWsProducerWarps);
-      mbar_init(&slab_empty[b], kWsConsumerWarps);
-    }
-    for (int i = 0; i < 2 * kWsConsumerWarps; ++i) mbar_init(&tma_bar[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < P.recipe_bytes / 2; i += kWsThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
-  __syncthreads();
-  const uint32_t G = gridDim.x, t0 = blockIdx.x;
-  if (warp < kWsProducerWarps) {
-    // ------------------------------------------------------------------ producers: K1, one cell per thread
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-    // cell range of a tile (count 0: nothing to evaluate - beyond the last tile, or a tile without rows)
-    auto load_hdr = [&](uint64_t t, uint32_t& cb, uint32_t& nc) {
-      cb = 0;
-      nc = 0;
-      if (t < uint64_t(P.ntiles)) {
-        const uint32_t a = __ldg(P.tile_cell_ptr + t), e = __ldg(P.tile_cell_ptr + t + 1);
-        const uint32_t c0 = __ldg(P.tile_chunk_ptr + t), c1 = __ldg(P.tile_chunk_ptr + t + 1);
-        cb = a;
-        nc = (c1 > c0 && !(P.debug & 1)) ? e - a : 0u;
-      }
-    };
-    auto load_ids = [&](uint32_t cb, uint32_t nc, uint32_t* eid) {
-      if (uint32_t(tid) < nc) {
-        const uint32_t* ce = P.tile_cell_edges + size_t(cb + tid) * NE;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
-      }
-    };
-    auto load_len = [&](uint32_t nc, const uint32_t* eid, double* s) {
-      if (uint32_t(tid) < nc) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
-      }
-    };
-    uint32_t cb0, nc0, cb1, nc1, cb2, nc2;
-    load_hdr(t0, cb0, nc0);
-    load_hdr(uint64_t(t0) + G, cb1, nc1);
-    load_hdr(uint64_t(t0) + 2 * uint64_t(G), cb2, nc2);
-    double mid[NM];
-    uint32_t eid1[NEE];
-    {
-      uint32_t eid0[NEE];
-      double s0[NEE];
-      load_ids(cb0, nc0, eid0);
-      load_len(nc0, eid0, s0);
-      if (uint32_t(tid) < nc0) fn.a(s0, mid);
-    }
-    load_ids(cb1, nc1, eid1);
-    for (uint32_t it = 0;; ++it) {
-      const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
-      if (t >= uint64_t(P.ntiles)) break;
-      const uint32_t b = it & 1u, u = it >> 1;
-      // loads of the tiles ahead, all in flight while stage B runs
-      double s1[NEE];
-      load_len(nc1, eid1, s1);       // lengths of tile it+1 (its ids arrived during the previous iteration)
-      uint32_t eid2[NEE];
-      load_ids(cb2, nc2, eid2);      // ids of tile it+2
-      uint32_t cb3, nc3;
-      load_hdr(t + 3 * uint64_t(G), cb3, nc3);  // cell range of tile it+3
-      if (it >= 2) mbar_wait(&slab_empty[b], (u - 1u) & 1u);  // the consumers left the tile that used this slab
-      if (uint32_t(tid) < nc0) {
-        TileSink sink{slabs[b] + tid, P.cstride};
-        fn.b(mid, sink);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slab_full[b]);
-      if (uint32_t(tid) < nc1) fn.a(s1, mid);  // stage A of the next tile
-      nc0 = nc1;
-      cb1 = cb2;
-      nc1 = nc2;
-      cb2 = cb3;
-      nc2 = nc3;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) eid1[e] = eid2[e];
-    }
-  } else {
-    // ------------------------------------------------------------------ consumers: K3
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 16 warps x 24 released = the 12288 registers the producers acquire
-    const int cw = warp - kWsProducerWarps;
-    unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
-    uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
-    uint32_t n_issued = 0, n_consumed = 0;
-    uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
-    auto load_chunks = [&](uint64_t t, uint32_t& a, uint32_t& e) {
-      a = 0;
-      e = 0;
-      if (t < uint64_t(P.ntiles)) {
-        a = __ldg(P.tile_chunk_ptr + t);
-        e = __ldg(P.tile_chunk_ptr + t + 1);
-      }
-    };
-    uint32_t c0, c1, c0n = 0, c1n = 0;
-    load_chunks(t0, c0, c1);
-    for (uint32_t it = 0;; ++it) {
-      const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
-      if (t >= uint64_t(P.ntiles)) break;
-      const uint32_t b = it & 1u, u = it >> 1;
-      const bool has_next = t + G < uint64_t(P.ntiles);
-      load_chunks(t + G, c0n, c1n);
-      auto issue_more = [&]() {  // keep this warp's double buffer full, crossing into the next tile when this one is done
-        while (n_issued - n_consumed < uint32_t(kSlotsPerWarp)) {
-          if (cur_chunk >= cur_end) {
-            if (cur_it == it && has_next) {
-              cur_it = it + 1;
-              cur_chunk = c0n + cw;
-              cur_end = c1n;
-              if (cur_chunk >= cur_end) break;
-            } else {
-              break;
-            }
-          }
-          if (lane == 0) {
-            uint64_t* bar = &mybar[n_issued & 1u];
-            mbar_expect_tx(bar, kChunkBytes);
-            tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
-          }
-          cur_chunk += kWsConsumerWarps;
-          ++n_issued;
-        }
-      };
-      if (cur_it != it) {
-        cur_it = it;
-        cur_chunk = c0 + cw;
-        cur_end = c1;
-      }
-      issue_more();
-      mbar_wait(&slab_full[b], u & 1u);
-      const double* slab = slabs[b];
-      for (uint32_t c = c0 + cw; c < c1; c += kWsConsumerWarps) {
-        mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
-        gather_chunk(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane);
-        __syncwarp();
-        ++n_consumed;
-        issue_more();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slab_empty[b]);
-      c0 = c0n;
-      c1 = c1n;
-    }
-  }
-}
-
-// ---- alternating producer/consumer variant (FQ_TILE_KERNEL=a) ------------------------------------------------------
+// ---- alternating producer/consumer variant (the default) -----------------------------------------------------------
 // One full-size slab (the same tiles and record streams as the phase-serialised kernel), logically split in two halves:
 //   half 1 = the stored values of M_{k-1} and M_k      read by the records of M_{k-1}, M_k, dif_test(k)
 //   half 2 = the stored values of M_{k+1}              read by the records of dif_both(k+1)
@@ -925,7 +756,6 @@ struct TilePlan {
   int cstride = 0;
   int nthreads = 512;
   bool ws = false;
-  bool ws_pipelined = false;  // FQ_TILE_KERNEL=p: static tile deal + two-stage tape (tile_assemble_ws2_kernel)
   bool alt = false;           // FQ_TILE_KERNEL=a and the block set splits: tile_assemble_alt_kernel
   uint32_t yblock_mask = 0;   // blocks reading only second-half values
   bool pack = false;          // bank-aware lane packing (slab stride = 0 mod 16)
@@ -958,10 +788,6 @@ struct TilePlan {
       fn##_a(s, mid);                                                                          \
     }                                                                                          \
     template <class S>                                                                         \
-    __device__ __forceinline__ void b(const double* __restrict__ mid, S& sink) const {         \
-      fn##_b(mid, sink);                                                                       \
-    }                                                                                          \
-    template <class S>                                                                         \
     __device__ __forceinline__ void b1(const double* __restrict__ mid, S& sink) const {        \
       fn##_b1(mid, sink);                                                                      \
     }                                                                                          \
@@ -991,15 +817,6 @@ static void launch_tile_ws(fq_ctx* ctx, const TilePlan& plan, const TileParams& 
     attr_set = true;
   }
   tile_assemble_ws_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
-}
-template <class Fn, int NE>
-static void launch_tile_ws2(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_ws2_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    attr_set = true;
-  }
-  tile_assemble_ws2_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
 }
 template <class Fn, int NE, int NC, int PR, int CR>
 static void launch_tile_alt_v(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
@@ -1034,8 +851,6 @@ template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   if (plan.alt)
     launch_tile_alt<Fn, NE>(ctx, plan, params);
-  else if (plan.ws && plan.ws_pipelined)
-    launch_tile_ws2<Fn, NE>(ctx, plan, params);
   else if (plan.ws)
     launch_tile_ws<Fn, NE>(ctx, plan, params);
   else if (plan.nthreads == 256)
@@ -1079,7 +894,6 @@ struct TileConfig {
   int nthreads;
   size_t smem_cta;  // dynamic shared memory budget of the CTA
   bool ws;          // warp-specialised kernel: two slabs, 8 producer + 16 consumer warps
-  bool ws_pipelined = false;  // ... with the software-pipelined producers
   bool alt = false;           // alternating kernel: the layout of the phase-serialised kernel, 8 + 16 warps
   int stream_warps = 0;       // warps that stream chunks (0: nthreads / 32, or the 16 consumers of the w/p kernels)
 };
@@ -1089,7 +903,7 @@ static TileConfig tile_config() {
   if (const char* e = std::getenv("FQ_TILE_THREADS"))
     if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256, false};
   if (const char* e = std::getenv("FQ_TILE_KERNEL")) {
-    if (e[0] == 'w' || e[0] == 'p') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true, e[0] == 'p'};
+    if (e[0] == 'w') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true};
     if (e[0] == 's') c.alt = false;  // same plan (16 streaming warps, one slab, tiles of <= 512 cells), 512-thread kernel
   }
   if (c.alt)
@@ -1878,7 +1692,6 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
   plan->ntiles = uint32_t(mesh->ntiles);
   plan->nthreads = cfg.nthreads;
   plan->ws = cfg.ws;
-  plan->ws_pipelined = cfg.ws_pipelined;
   plan->stream_warps = cfg.stream_warps;
   if (plan->ntiles >= (1u << 27)) return nullptr;
   // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)

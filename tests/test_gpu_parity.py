@@ -457,18 +457,16 @@ def test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, 
         assert same_bits_mod_zero_sign(va, va0), (kind, g)
 
 
-@pytest.mark.parametrize("kernel", ["w", "p", "s"])
+@pytest.mark.parametrize("kernel", ["w", "s"])
 @pytest.mark.parametrize("dim,shape,variant,k,source", [TILE_CASES[i] for i in (0, 1, 2, 3, 5, 6, 9, 10)])
 def test_tile_fused_warp_specialised_kernels(fq, ctx, monkeypatch, kernel, dim, shape, variant, k, source):
-    # FQ_TILE_KERNEL=w: producer/consumer warps over two slabs; =p: the same with statically dealt tiles and the
-    # two-stage element tape (stage A of the next tile in the shadow of this tile's stage B); =a: one slab in two halves,
-    # the producers refill one half while the consumers gather from the other (the default; =s: phase-serialised).
-    # Same bits as the oracle.
+    # default: one slab in two halves, the producers refill one half while the consumers gather from the other (staged
+    # element tape); FQ_TILE_KERNEL=w: producer/consumer warps over two slabs; =s: phase-serialised.  Same bits as the oracle.
     monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
     test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, variant, k, source, True)
 
 
-@pytest.mark.parametrize("kernel", ["", "p", "s", "nopack"])
+@pytest.mark.parametrize("kernel", ["", "w", "s", "nopack"])
 def test_tile_fused_many_tiles_per_cta(fq, ctx, monkeypatch, kernel):
     # enough tiles that every CTA runs several of them (pipelines in steady state, slabs recycled): tile pass == slab pass
     # == oracle, bitwise, on a jittered mesh
