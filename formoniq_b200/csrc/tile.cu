@@ -14,10 +14,15 @@
 //     its non-zeros over the contributing (cell, slot) pairs in ascending cell
 //     order — the same order as the slab path, so values are bit-identical.
 //
+// Kernels (same plan, same streams): tile_assemble_alt_kernel (default) runs 8 producer warps (K1) and 16 consumer warps
+// (K3) over ONE slab used in two alternating halves, so the FP64 work hides completely behind the gather without
+// shrinking the tiles; tile_assemble_kernel (FQ_TILE_KERNEL=s) is the phase-serialised predecessor (K1, barrier, gather,
+// barrier on 16 warps); tile_assemble_ws_kernel (=w) the two-slab producer/consumer experiment.
+//
 // Shared memory holds only the DISTINCT values a cell contributes: for
-// HodgeBlocks the masses M_{k-1}, M_k and the sandwich dif_both(k+1) (74 doubles
-// for 3-D k = 1 instead of 112 element entries).  dif_test = d*M_k
-// (operators.rs:201-211) is evaluated by the gather through per-slot "recipes" —
+// HodgeBlocks the masses M_{k-1}, M_k, M_{k+1} (54 doubles for 3-D k = 1 instead of 112
+// element entries; FQ_TILE_CORE=h stores dif_both(k+1) instead of M_{k+1}: 74).  dif_test = d*M_k and dif_both
+// (operators.rs:201-211) are evaluated by the gather through per-slot "recipes" —
 // signed sums of mass entries in the reference's k-ascending gemm order, exact
 // because the incidence entries are 0/+-1 (tape.hpp evaluates the same products
 // symbolically).

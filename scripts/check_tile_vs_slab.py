@@ -1,4 +1,4 @@
-"""Debug aid: tile pass vs slab pass on a mid-size jittered mesh, mismatch statistics per block."""
+"""Debug aid (used to find the b_empty phase-mixing race): tile pass vs slab pass on a mid-size jittered mesh, mismatch statistics per block."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
