@@ -547,6 +547,39 @@ class LinearFormPlan:
             pass
 
 
+class SourceForm:
+    """formoniq::operators::SourceForm (operators.rs:607-635): the load [int_K <f, W_sigma> vol]_sigma of a k-form source.
+    `SourceForm(dim, grade, degree)` builds the reference data (`CellQuadrature::new` + `LsfSamples::whitney`; the default
+    rule is the degree-1 Grundmann-Moeller rule, operators.rs:229-231); `nodes` are the barycentric quadrature nodes at
+    which the caller samples its field: `samples[cell][node][component]`, components of f in the cell's reference frame
+    on the colex k-subsets of the axes (what `Section::at(point)` returns).  `assemble` = `LinearForm::assemble`."""
+
+    def __init__(self, dim: int, grade: int, degree: int = 1):
+        from . import quadrature
+        self.dim, self.grade = dim, grade
+        self.nodes, self.weights = quadrature.quad_rule(dim, degree)
+        self.shapes = np.ascontiguousarray(quadrature.whitney_shapes(dim, grade, self.nodes))
+        self.weights = np.ascontiguousarray(self.weights)
+        self._plans = {}
+
+    def test_grade(self) -> int:
+        return self.grade
+
+    def assemble(self, mesh: Mesh, samples: np.ndarray, plan: "LinearFormPlan | None" = None) -> DeviceVector:
+        if plan is None:
+            plan = self._plans.get(id(mesh))
+            if plan is None or plan.mesh is not mesh:
+                plan = self._plans[id(mesh)] = LinearFormPlan(mesh, self.grade)
+        nn, nd, nc = self.shapes.shape
+        f = np.ascontiguousarray(samples, dtype=np.float64)
+        if f.size != mesh.ncells * nn * nc:
+            raise FormoniqError(-1, "samples must be [ncells][nnodes][C(dim, grade)]")
+        y = DeviceVector(mesh.ctx, plan.nrows)
+        check(_lib.lib().fq_source_form_assemble(mesh.ctx._h, plan._h, nn, self.weights.ctypes.data_as(C.c_void_p),
+                                                 self.shapes.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p), y._h))
+        return y
+
+
 class _HodgePlan:
     def __init__(self, handle):
         self._h = handle

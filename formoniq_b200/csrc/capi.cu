@@ -893,6 +893,17 @@ int fq_linear_form_assemble(fq_ctx* ctx, const fq_matfree* plan, const double* e
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffer may be reused on return
   FQ_API_END
 }
+int fq_source_form_assemble(fq_ctx* ctx, const fq_matfree* plan, int nnodes, const double* weights, const double* shapes,
+                            const double* samples, fq_vec* out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && plan && out && weights && shapes, "null argument");
+  FQ_REQUIRE(out->d.n == matfree_nrows(plan), "the load vector has one entry per simplex of the form's grade");
+  FQ_REQUIRE(samples || matfree_nrows(plan) == 0, "null source samples");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  vector_plan_source(ctx, plan, nnodes, weights, shapes, samples, out->d.p);
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be reused on return
+  FQ_API_END
+}
 int fq_linear_form_destroy(fq_matfree* plan) { return fq_matfree_destroy(plan); }
 
 int fq_matfree_refresh(fq_ctx* ctx, fq_matfree* op) {

@@ -65,6 +65,10 @@ namespace fq {
 void matfree_build(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, ::fq_matfree* op, bool with_slab = true);
 void vector_plan_build(fq_ctx* ctx, const fq_mesh* mesh, int grade, ::fq_matfree* op);
 void vector_plan_assemble(fq_ctx* ctx, const ::fq_matfree* op, const double* h_elvecs, double* y);
+void vector_plan_source(fq_ctx* ctx, const ::fq_matfree* op, int nnodes, const double* h_weights, const double* h_shapes,
+                        const double* h_samples, double* y);
+void source_element_vectors(fq_ctx* ctx, const fq_mesh* mesh, int grade, int nnodes, const double* h_weights,
+                            const double* h_shapes, const double* h_samples, double* d_elvecs);
 void matfree_refresh(fq_ctx* ctx, ::fq_matfree* op);
 void matfree_apply(fq_ctx* ctx, const ::fq_matfree* op, const double* x, double* y);
 void matfree_diagonal(fq_ctx* ctx, const ::fq_matfree* op, double* d);

@@ -130,6 +130,16 @@ void vector_plan_assemble(fq_ctx* ctx, const fq_matfree* op, const double* h_elv
   stream_reduce(ctx, op->blocks.p, op->nblocks, op->face_ptr.p, op->face_src.p, nullptr, op->local.p, MfGatherPolicy{y});
 }
 
+// SourceForm (operators.rs:607-635) assembled: element vectors by device quadrature (quadform.cu) straight into the
+// plan's staging buffer, then the per-DOF gather.
+void vector_plan_source(fq_ctx* ctx, const fq_matfree* op, int nnodes, const double* h_weights, const double* h_shapes,
+                        const double* h_samples, double* y) {
+  if (op->nrows == 0) return;
+  source_element_vectors(ctx, op->mesh, op->tg, nnodes, h_weights, h_shapes, h_samples, op->local.p);
+  ScopedSpan span(ctx, "lf_gather");
+  stream_reduce(ctx, op->blocks.p, op->nblocks, op->face_ptr.p, op->face_src.p, nullptr, op->local.p, MfGatherPolicy{y});
+}
+
 void matfree_refresh(fq_ctx* ctx, fq_matfree* op) {  // element matrices from the mesh's current edge lengths
   double* outs[1] = {op->slab.p};
   DevBuf<int> err(1);

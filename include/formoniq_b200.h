@@ -228,6 +228,16 @@ int fq_matfree_diagonal(fq_ctx* ctx, const fq_matfree* op, fq_vec* d);
 int fq_linear_form_create(fq_ctx* ctx, const fq_mesh* mesh, int grade, fq_matfree** out);
 int fq_linear_form_assemble(fq_ctx* ctx, const fq_matfree* plan, const double* element_vectors, fq_vec* out);
 int fq_linear_form_destroy(fq_matfree* plan);
+/* SourceForm (formoniq/src/operators.rs:607-635) assembled in one call: the element vectors
+ *   elvec_K[sigma] = vol_K * sum_q w_q <f(x_q), W_sigma(x_q)>_{Lambda^k g_K^{-1}}      (operators.rs:247-261, tensor.rs:140-157)
+ * are evaluated on the device (one thread per cell: metric by polarisation, inverse, volume, k x k minors of g^{-1}) and
+ * reduced per DOF by the plan.  Host inputs: `weights[nnodes]` (normalised, SimplexQuadRule::weights), `shapes`
+ * [nnodes][C(n+1,k+1)][C(n,k)] = LsfSamples::whitney (derham/src/interpolate/samples.rs:31-40), `samples`
+ * [ncells][nnodes][C(n,k)] = the source Section evaluated at the nodes of every cell in the cell's reference frame
+ * (the user closure of the reference; the only per-cell host work).  Values agree with the reference to rounding
+ * (1e-12 relative), not bitwise: the reference sums through nalgebra's generic tensor contraction. */
+int fq_source_form_assemble(fq_ctx* ctx, const fq_matfree* plan, int nnodes, const double* weights, const double* shapes,
+                            const double* samples, fq_vec* out);
 
 /* ---- SpMV fused with the halo exchange (one process per GPU, NVLink 5 / NVSwitch peer memory) -----------------
  * The reference is single-process; under the owner-computes row partition the only exchange step of the path is

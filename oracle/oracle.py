@@ -343,3 +343,27 @@ def assemble_vector(cx: "Complex", grade: int, element_vectors: np.ndarray) -> n
     # np.add.at applies the additions one by one in index order == the reference's sequential loop
     np.add.at(out, rows[keep], vals[keep])
     return out
+
+
+def source_element_vectors(cx: "Complex", lengths_sq, grade: int, weights, shapes, samples) -> np.ndarray:
+    """Restatement of SourceForm::element (formoniq/src/operators.rs:624-634) for every cell:
+    CellQuadrature::integrate (operators.rs:247-261: elvec[i] += w_q * f(point, W_i(q)) node-outer, then vol * elvec) of
+    inner(source, whitney, metric) = source . (Lambda^k g^-1 whitney) (metric/src/tensor.rs:127-131,140-157), with
+    Lambda^k g^-1 = the k x k minors of g^-1 on colex k-subsets (multialgebra/src/lib.rs:285-305) and
+    vol = cell_volume (regge/src/lib.rs:26-28).  Returns [ncells][C(n+1, grade+1)]."""
+    import itertools
+    n = cx.dim
+    edges = cx.cell_faces(1)
+    nn, nd, nc = np.asarray(shapes).shape
+    f = np.asarray(samples, dtype=np.float64).reshape(cx.ncells, nn, nc)
+    subsets = sorted(itertools.combinations(range(n), grade), key=lambda c: c[::-1])
+    out = np.zeros((cx.ncells, nd))
+    for c in range(cx.ncells):
+        _, gi, vol = cell_geometry(n, np.asarray(lengths_sq)[edges[c]])
+        G = np.array([[np.linalg.det(gi[np.ix_(I, J)]) if grade else 1.0 for J in subsets] for I in subsets])
+        elvec = np.zeros(nd)
+        for q in range(nn):
+            for i in range(nd):
+                elvec[i] += weights[q] * float(f[c, q] @ (G @ shapes[q][i]))
+        out[c] = vol * elvec
+    return out

@@ -20,7 +20,7 @@ fn main() {
   let mut cmd = Command::new(nvcc);
   cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
             "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o"]).arg(&lib);
-  for f in ["elmat.cu", "kuhn.cu", "assemble.cu", "tile.cu", "blockop.cu", "matfree.cu", "spmv.cu", "blas1.cu", "krylov.cu", "capi.cu"] {
+  for f in ["elmat.cu", "kuhn.cu", "assemble.cu", "tile.cu", "blockop.cu", "matfree.cu", "quadform.cu", "spmv.cu", "blas1.cu", "krylov.cu", "capi.cu"] {
     cmd.arg(csrc.join(f));
     println!("cargo:rerun-if-changed={}", csrc.join(f).display());
   }

@@ -860,3 +860,38 @@ def test_linear_form_assembly_is_the_reference_scatter(fq, ctx, dim, shape, grad
     assert same_bits_mod_zero_sign(plan.assemble(2.0 * ev).to_numpy(), O.assemble_vector(cx, grade, 2.0 * ev))
     with pytest.raises(fq.FormoniqError):
         plan.assemble(ev, out=fq.DeviceVector(ctx, exp.shape[0] + 1))
+
+
+# ------------------------------------------------------------------ SourceForm (operators.rs:607-635)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,shape,grade,degree,variant", [
+    (2, [6, 5], 1, 1, "jitter"), (2, [5, 5], 0, 3, "jitter"), (2, [4, 6], 2, 3, "plain"),
+    (3, [4, 3, 4], 1, 3, "jitter"), (3, [3, 3, 3], 2, 3, "jitter"), (3, [3, 3, 3], 1, 5, "minkowski"), (3, [3, 2, 3], 3, 1, "plain"),
+    (4, [2, 2, 1, 2], 2, 3, "jitter"), (1, [7], 1, 1, "plain"),
+])
+def test_source_form_load_vector(fq, ctx, dim, shape, grade, degree, variant):
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    form = fq.SourceForm(dim, grade, degree)
+    nn, nd, nc = form.shapes.shape
+    rng = np.random.default_rng(100 * dim + 10 * grade + degree)
+    samples = rng.standard_normal((cx.ncells, nn, nc))
+    got = form.assemble(mesh, samples).to_numpy()
+    ev = O.source_element_vectors(cx, s, grade, form.weights, form.shapes, samples)
+    exp = O.assemble_vector(cx, grade, ev)
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() <= 1e-12 * np.abs(exp).max()          # north-star value tolerance (FP64)
+    # the reference's law (galerkin.rs:330-372): source = Whitney form of tau  =>  load = M e_tau  (rule exact: degree >= 2)
+    if degree >= 3:
+        mass = cx.assemble(s, O.MASS, grade).to_scipy().toarray()
+        faces = cx.cell_faces(grade)
+        tau = int(faces[cx.ncells // 2, 0])
+        f = np.zeros_like(samples)
+        for c in range(cx.ncells):
+            hit = np.flatnonzero(faces[c] == tau)
+            if hit.size:
+                f[c] = form.shapes[:, hit[0], :]
+        col = form.assemble(mesh, f).to_numpy()
+        assert np.abs(col - mass[:, tau]).max() <= 1e-12 * np.abs(mass[:, tau]).max()
+    with pytest.raises(fq.FormoniqError):
+        form.assemble(mesh, samples[:-1])

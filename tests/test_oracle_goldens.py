@@ -484,3 +484,54 @@ def test_assemble_vector_law_of_the_reference():
                 if ev[c, i] != 0.0:
                     naive[faces[c, i]] += ev[c, i]
         assert np.array_equal(O.assemble_vector(cx, grade, ev), naive)
+
+
+def test_grundmann_moeller_and_whitney_tables():
+    # simplicial/src/atlas/quadrature.rs:176-196 (the rule integrates every barycentric monomial of degree <= 2s+1
+    # exactly, in every dimension) and the de Rham duality of the lowest-order Whitney forms (int_tau W_sigma = delta)
+    from formoniq_b200 import quadrature as Q
+    for dim in range(0, 5):
+        for s in range(0, 4):
+            pts, w = Q.grundmann_moeller(dim, s)
+            assert abs(w.sum() - 1.0) < 1e-14 and pts.shape == (len(w), dim + 1)
+            assert np.abs(pts.sum(axis=1) - 1.0).max() < 1e-15
+            for deg in range(0, 2 * s + 2):
+                for alpha in Q._compositions(dim + 1, deg):
+                    val = sum(wi * np.prod(p ** np.array(alpha)) for p, wi in zip(pts, w))
+                    exact = math.factorial(dim) * np.prod([math.factorial(a) for a in alpha]) / math.factorial(dim + deg)
+                    assert abs(val - exact) < 1e-12
+    for dim in (1, 2, 3, 4):
+        verts = np.vstack([np.zeros(dim), np.eye(dim)])
+        dofs = Q._colex_subsets(dim + 1, 2)
+        for b, (p, q) in enumerate(dofs):
+            lam = np.zeros(dim + 1)
+            lam[p] = lam[q] = 0.5
+            w_mid = Q.whitney_shapes(dim, 1, [lam])[0]          # [dof][axis] at the midpoint of edge b
+            for a in range(len(dofs)):
+                assert abs(w_mid[a] @ (verts[q] - verts[p]) - (1.0 if a == b else 0.0)) < 1e-14
+        centroid = np.full(dim + 1, 1.0 / (dim + 1))
+        assert np.allclose(Q.whitney_shapes(dim, 0, [centroid])[0][:, 0], centroid)        # W_v = lambda_v
+        assert np.allclose(Q.whitney_shapes(dim, dim, [centroid])[0], math.factorial(dim))  # the volume form n! dx
+
+
+def test_source_form_law_of_the_reference():
+    # crates/formoniq/src/galerkin.rs:330-372: the source a Whitney form lambda_tau, the load is the column tau of the
+    # mass matrix (the integrand is quadratic: the degree-3 rule is exact) - pins rule + shape table + Lambda^k g^-1 +
+    # volume of the restatement against the golden-pinned mass matrices, Riemannian and Lorentzian.
+    from formoniq_b200 import quadrature as Q
+    for dim, n, grade, mink in ((2, 3, 1, False), (3, 2, 1, False), (3, 2, 2, False), (2, 3, 0, False), (3, 2, 3, False),
+                                (3, 2, 1, True)):
+        cx, s, _ = kuhn_problem(dim, n, jitter=not mink, minkowski=mink)
+        nodes, weights = Q.quad_rule(dim, 3)
+        shapes = Q.whitney_shapes(dim, grade, nodes)
+        faces = cx.cell_faces(grade)
+        mass = cx.assemble(s, O.MASS, grade).to_scipy().toarray()
+        for tau in (0, cx.nsimplices(grade) // 2):
+            samples = np.zeros((cx.ncells, len(weights), shapes.shape[2]))
+            for c in range(cx.ncells):
+                hit = np.flatnonzero(faces[c] == tau)
+                if hit.size:
+                    samples[c] = shapes[:, hit[0], :]
+            ev = O.source_element_vectors(cx, s, grade, weights, shapes, samples)
+            load = O.assemble_vector(cx, grade, ev)
+            assert np.abs(load - mass[:, tau]).max() <= 1e-12 * np.abs(mass[:, tau]).max(), (dim, grade, mink)
