@@ -53,6 +53,8 @@ unsafe extern "C" {
   fn fq_linear_form_assemble(ctx: *mut fq_ctx, plan: *const fq_matfree, element_vectors: *const c_double,
                              out: *mut fq_vec) -> c_int;
   fn fq_linear_form_destroy(plan: *mut fq_matfree) -> c_int;
+  fn fq_source_form_assemble(ctx: *mut fq_ctx, plan: *const fq_matfree, nnodes: c_int, weights: *const c_double,
+                             shapes: *const c_double, samples: *const c_double, out: *mut fq_vec) -> c_int;
   // HodgeBlocks (hodge.rs:62-99): symbolic once, numeric per geometry (one fused kernel from the second pass on)
   fn fq_mesh_set_lengths(ctx: *mut fq_ctx, mesh: *mut fq_mesh, edge_lengths_sq: *const c_double) -> c_int;
   fn fq_hodge_symbolic(ctx: *mut fq_ctx, mesh: *const fq_mesh, grade: c_int, sigma_row_begin: usize, sigma_row_end: usize,
@@ -274,6 +276,31 @@ impl<'d> GpuLinearFormPlan<'d> {
     let out = DeviceVector::zeros(self.dev, self.ndofs);
     check(unsafe { fq_linear_form_assemble(self.dev.0, self.raw, elvecs.as_ptr(), out.raw) });
     formoniq::galerkin::GalerkinVector::new(form.test_grade(), out.to_host())
+  }
+}
+impl<'d> GpuLinearFormPlan<'d> {
+  /// Drop-in for `SourceForm::new(source, qr).assemble(topology, geometry)` (operators.rs:607-635): the rule and the
+  /// `LsfSamples::whitney` table are built exactly as `SourceForm::new` does, the `Section` is sampled at the nodes of
+  /// every cell with rayon, and quadrature + scatter run on the device.
+  pub fn assemble_source<F: Sync + formoniq::Section>(&self, topology: &Complex, source: &F,
+                                                      qr: Option<simplicial::atlas::quadrature::SimplexQuadRule>)
+    -> formoniq::galerkin::GalerkinVector {
+    use rayon::prelude::*;
+    let dim = source.dim();
+    let qr = qr.unwrap_or(simplicial::atlas::quadrature::SimplexQuadRule::degree(dim, 1));
+    let nodes: Vec<_> = qr.points().map(|b| b.to_coords()).collect();
+    let shapes = derham::interpolate::samples::LsfSamples::whitney(dim, source.grade(), &nodes);
+    let weights: Vec<f64> = qr.weights().iter().copied().collect();
+    let mut table = Vec::new();
+    for q in 0..nodes.len() { for w in shapes.at_node(q) { table.extend(w.components().iter().copied()); } }
+    let samples: Vec<f64> = topology.cells().handle_par_iter()
+      .flat_map_iter(|cell| nodes.iter().flat_map(|b| source.at(&cell.point(b.clone())).components().iter().copied()
+        .collect::<Vec<_>>()).collect::<Vec<_>>())
+      .collect();
+    let out = DeviceVector::zeros(self.dev, self.ndofs);
+    check(unsafe { fq_source_form_assemble(self.dev.0, self.raw, nodes.len() as c_int, weights.as_ptr(), table.as_ptr(),
+                                           samples.as_ptr(), out.raw) });
+    formoniq::galerkin::GalerkinVector::new(source.grade(), out.to_host())
   }
 }
 impl Drop for GpuLinearFormPlan<'_> { fn drop(&mut self) { unsafe { fq_linear_form_destroy(self.raw) }; } }
