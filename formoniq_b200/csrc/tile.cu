@@ -96,6 +96,7 @@ struct TileParams {
   int debug;                        // development knobs (FQ_TILE_DEBUG): 1 skip K1, 2 skip records, 4 skip stores
   int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
   uint32_t yblock_mask;             // alternating kernel: blocks whose records read second-half slab values only
+  uint32_t chunk_rotation;          // alternating kernel: per-tile rotation of the chunk -> warp deal (0: none)
   int* changed;                     // raised when the zero/non-zero classification differs from the plan's
   unsigned int* ticket;             // dynamic tile scheduler
   unsigned long long* stats;        // debug & 8: per-phase warp cycles [k1, bar_k1, chunk_wait, records, bar_top, other]
@@ -690,6 +691,10 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
     };
     uint32_t c0, c1, c0n = 0, c1n = 0;
     load_chunks(t0, c0, c1);
+    // Chunk c of a tile goes to the warp (c - rotation) mod NC, the rotation advancing with every tile: a tile has
+    // ~3.75 chunks per warp, and without the rotation the same warps would get the extra chunk of every tile.
+    const uint32_t rot_step = P.chunk_rotation;
+    auto lane_of = [&](uint32_t iter) { return (uint32_t(cw) + iter * rot_step) % uint32_t(NC); };
     for (uint32_t it = 0;; ++it) {
       const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
       if (t >= uint64_t(P.ntiles)) break;
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
           if (cur_chunk >= cur_end) {
             if (cur_it == it && has_next) {
               cur_it = it + 1;
-              cur_chunk = c0n + cw;
+              cur_chunk = c0n + lane_of(it + 1);
               cur_end = c1n;
               if (cur_chunk >= cur_end) break;
             } else {
@@ -718,13 +723,13 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
       };
       if (cur_it != it) {
         cur_it = it;
-        cur_chunk = c0 + cw;
+        cur_chunk = c0 + lane_of(it);
         cur_end = c1;
       }
       issue_more();
       AltState st{a_empty, b_full, it & 1u, false};
       mbar_wait(a_full, it & 1u);
-      for (uint32_t c = c0 + cw; c < c1; c += NC) {
+      for (uint32_t c = c0 + lane_of(it); c < c1; c += NC) {
         mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
         gather_chunk<true>(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane, &st);
         __syncwarp();
@@ -2029,6 +2034,7 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
   P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
   P.check_classification = (plan.blk[0].dropped_at_build && !(P.debug & 7)) ? 1 : 0;
   P.yblock_mask = plan.yblock_mask;
+  P.chunk_rotation = std::getenv("FQ_TILE_ROTATE") ? uint32_t(std::atoi(std::getenv("FQ_TILE_ROTATE"))) : 5u;
   P.changed = plan.changed.p;
   P.ticket = plan.ticket.p;
   P.stats = plan.stats.p;
