@@ -62,6 +62,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, timeout: float = 5.0):
+        """Block until nvidia-smi delivers its first sample (its start-up can exceed a short timed region)."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -73,7 +83,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -197,24 +207,42 @@ def run_b200(args):
     def step():
         hb.numeric(mesh, True)  # one fused element kernel + one segmented reduction per block
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nvidia-smi needs ~0.1-1 s to deliver its first sample
     for _ in range(args.warmup):
         step()
     ctx.timing_report()
-    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.wait_first()
     launches0 = ctx.launch_count
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     kern = ctx.timing_report()
+    clocks = None
+    if rank == 0:
+        extended = False
+        if len(sampler.lines) - sampler.first < 2:
+            # the timed region was shorter than two sampling periods on this box: keep the same kernel running (untimed)
+            # until the sampler has seen it, and say so
+            extended = True
+            t_ext = time.time()
+            while len(sampler.lines) - sampler.first < 3 and time.time() - t_ext < 2.0:
+                step()
+                torch.cuda.synchronize()
+        clocks = sampler.stop()
+        if extended:
+            clocks["note"] = "timed region shorter than the sampling period: sampled over extra untimed steps of the same kernel"
+        ctx.timing_report()
     nnz_local = sum(a.nnz for _, _, a in mats)
     asm_bytes = sum(a.assembly_bytes for _, _, a in mats)
 
