@@ -1,11 +1,11 @@
 """formoniq_b200 — B200-native Galerkin assembly + CSR SpMV behind formoniq's interfaces."""
 from ._lib import (FQ_DIF_BOTH, FQ_DIF_TEST, FQ_DIF_TRIAL, FQ_LUMPED, FQ_MASS, LIB_PATH, FormoniqError)
-from .api import (BilinearForm, Context, DeviceCsr, DeviceVector, ElementOperator, HodgeBlocks, LinearFormPlan, SourceForm, Mesh, Report, ScalarLumpedMass,
+from .api import (BilinearForm, Context, DeviceCsr, DeviceVector, ElementOperator, HodgeBlocks, LinearFormPlan, SourceForm, WeightedHodgeMass, Mesh, Report, ScalarLumpedMass,
                   StopCriterion, WhitneyPairing, cg, kuhn_cell_faces_host, kuhn_counts, kuhn_slab_ranges, minres, nlocal)
 from .eigen import EigenError, sparse_shift_invert_eigen
 
 __all__ = [
     "FQ_MASS", "FQ_DIF_TRIAL", "FQ_DIF_TEST", "FQ_DIF_BOTH", "FQ_LUMPED", "LIB_PATH", "FormoniqError", "BilinearForm",
-    "Context", "DeviceCsr", "DeviceVector", "ElementOperator", "HodgeBlocks", "LinearFormPlan", "SourceForm", "Mesh", "Report", "ScalarLumpedMass", "StopCriterion",
+    "Context", "DeviceCsr", "DeviceVector", "ElementOperator", "HodgeBlocks", "LinearFormPlan", "SourceForm", "WeightedHodgeMass", "Mesh", "Report", "ScalarLumpedMass", "StopCriterion",
     "WhitneyPairing", "cg", "minres", "sparse_shift_invert_eigen", "EigenError", "kuhn_cell_faces_host", "kuhn_counts", "kuhn_slab_ranges", "nlocal",
 ]

@@ -94,6 +94,7 @@ SIGNATURES = [
     ("fq_linear_form_assemble", _i, [_vp, _vp, _vp, _vp]),
     ("fq_linear_form_destroy", _i, [_vp]),
     ("fq_source_form_assemble", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    ("fq_weighted_mass_numeric", _i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i]),
     ("fq_vec_ipc_export", _i, [_vp, _vp, _vp]),
     ("fq_vec_ipc_import", _i, [_vp, _vp, _sz, _P(_vp)]),
     ("fq_spmv_peer", _i, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _sz, _vp]),

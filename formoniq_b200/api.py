@@ -547,6 +547,35 @@ class LinearFormPlan:
             pass
 
 
+class WeightedHodgeMass(BilinearForm):
+    """formoniq::operators::WeightedHodgeMass (operators.rs:432-486): [int_K alpha <W_sigma, W_tau> vol] by quadrature,
+    alpha a scalar (grade-0) coefficient sampled by the caller at the rule's nodes: `coefficient[cell][node]`.
+    The default rule is the degree-1 Grundmann-Moeller rule (operators.rs:229-231)."""
+
+    def __init__(self, dim: int, grade: int, degree: int = 1):
+        from . import quadrature
+        self.dim, self.grade, self.kind = int(dim), int(grade), FQ_MASS
+        self.nodes, weights = quadrature.quad_rule(dim, degree)
+        self.weights = np.ascontiguousarray(weights)
+        self.shapes = np.ascontiguousarray(quadrature.whitney_shapes(dim, grade, self.nodes))
+
+    def numeric(self, mesh: Mesh, a: DeviceCsr, coefficient: np.ndarray, drop_exact_zeros: bool = True) -> DeviceCsr:
+        nn = self.shapes.shape[0]
+        al = np.ascontiguousarray(coefficient, dtype=np.float64)
+        if al.size != mesh.ncells * nn:
+            raise FormoniqError(-1, "coefficient must be [ncells][nnodes]")
+        check(_lib.lib().fq_weighted_mass_numeric(mesh.ctx._h, mesh._h, a._h, nn, self.weights.ctypes.data_as(C.c_void_p),
+                                                  self.shapes.ctypes.data_as(C.c_void_p), al.ctypes.data_as(C.c_void_p),
+                                                  int(drop_exact_zeros)))
+        return a
+
+    def assemble(self, mesh: Mesh, coefficient: np.ndarray, drop_exact_zeros: bool = True) -> DeviceCsr:  # type: ignore[override]
+        """BilinearForm::assemble for this form: symbolic phase of the mass pattern + the quadrature numeric pass."""
+        if mesh.dim != self.dim:
+            raise FormoniqError(-1, "form and mesh dimensions differ")
+        return self.numeric(mesh, self.symbolic(mesh), coefficient, drop_exact_zeros)
+
+
 class SourceForm:
     """formoniq::operators::SourceForm (operators.rs:607-635): the load [int_K <f, W_sigma> vol]_sigma of a k-form source.
     `SourceForm(dim, grade, degree)` builds the reference data (`CellQuadrature::new` + `LsfSamples::whitney`; the default

@@ -14,6 +14,8 @@
 //     compacted to exactly the reference's value-dependent pattern.
 #include <cub/cub.cuh>
 
+#include <functional>
+
 #include "internal.hpp"
 #include "stream.cuh"
 
@@ -425,6 +427,23 @@ void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csr
     numeric_reduce(ctx, mesh, csrs[b], drop_exact_zeros);
     csrs[b]->slab_passes += 1;
   }
+}
+
+// Numeric pass of a quadrature form: the element matrices come from `fill` (which writes the cell-major element slab)
+// instead of the generated K1 kernels; K3 and the pattern semantics are those of every other form.
+void assemble_numeric_custom(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros,
+                             const std::function<void(double*)>& fill) {
+  FQ_REQUIRE(csr->has_plan, "matrix has no assembly plan (uploaded matrices cannot be re-assembled)");
+  FQ_REQUIRE(csr->ncells == mesh->ncells && csr->dim == mesh->dim, "mesh does not match the symbolic phase");
+  csr->inv_diag.release();
+  csr->tile_plan.reset();  // the tile-fused kernel evaluates the closed-form masses: not this form
+  csr->tile_refused = 1;
+  const size_t T = size_t(csr->el_rows) * size_t(csr->el_cols);
+  const size_t want = mesh->ncells * T;
+  if (csr->slab.n != (want ? want : 1)) csr->slab.alloc(want ? want : 1);
+  if (csr->s_nnz > 0) fill(csr->slab.p);
+  numeric_reduce(ctx, mesh, csr, drop_exact_zeros);
+  csr->slab_passes += 1;
 }
 
 void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros) {

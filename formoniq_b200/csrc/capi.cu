@@ -904,6 +904,19 @@ int fq_source_form_assemble(fq_ctx* ctx, const fq_matfree* plan, int nnodes, con
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be reused on return
   FQ_API_END
 }
+int fq_weighted_mass_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, int nnodes, const double* weights,
+                             const double* shapes, const double* coefficient, int drop_exact_zeros) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && mesh && csr && weights && shapes, "null argument");
+  FQ_REQUIRE(csr->kind == KIND_MASS, "the weighted mass is assembled on the pattern of the mass of its grade");
+  FQ_REQUIRE(coefficient || mesh->ncells == 0, "null coefficient samples");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  const int grade = csr->grade;
+  assemble_numeric_custom(ctx, mesh, csr, drop_exact_zeros != 0, [&](double* slab) {
+    weighted_mass_to_slab(ctx, mesh, grade, nnodes, weights, shapes, coefficient, slab);
+  });
+  FQ_API_END
+}
 int fq_linear_form_destroy(fq_matfree* plan) { return fq_matfree_destroy(plan); }
 
 int fq_matfree_refresh(fq_ctx* ctx, fq_matfree* op) {

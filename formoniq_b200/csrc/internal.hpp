@@ -1,5 +1,6 @@
 // internal.hpp — functions shared between the translation units of the library.
 #pragma once
+#include <functional>
 #include "common.cuh"
 
 namespace fq {
@@ -21,6 +22,10 @@ void kuhn_build_mesh(fq_ctx* ctx, int dim, const size_t* shape, const double* vm
 void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
                        fq_csr* out);
 void assemble_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros);
+void assemble_numeric_custom(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool drop_exact_zeros,
+                             const std::function<void(double*)>& fill);
+void weighted_mass_to_slab(fq_ctx* ctx, const fq_mesh* mesh, int grade, int nnodes, const double* h_weights,
+                           const double* h_shapes, const double* h_coeff, double* d_slab);
 // fused numeric phase of several blocks sharing one element kernel launch (HodgeBlocks)
 void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros);
 

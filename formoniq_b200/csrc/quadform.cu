@@ -92,6 +92,90 @@ __global__ void __launch_bounds__(128) source_elvec_kernel(int n, int k, int nco
   }
 }
 
+// WeightedHodgeMass::element (formoniq/src/operators.rs:477-485): CellQuadrature::integrate_pair (operators.rs:266-290)
+// of alpha(x) * inner(W_i, W_j), times the cell volume:  A[i][j] = vol * sum_q w_q * alpha_q * W_i(q)^T G W_j(q).
+// One thread per cell writes its cell-major element matrix into the CSR's element slab; the K3 reduction of the slab path
+// (assemble.cu) scatters it under the structural pattern of the mass of the same grade.
+__global__ void __launch_bounds__(128) weighted_mass_kernel(int n, int k, int ncomp, int ndofs, int nnodes, size_t ncells,
+                                                            const uint32_t* __restrict__ cell_edges, const double* __restrict__ lengths,
+                                                            uint32_t edge_lo, const uint8_t* __restrict__ subsets,
+                                                            const double* __restrict__ weights, const double* __restrict__ shapes,
+                                                            const double* __restrict__ coeff /*[ncells][nnodes]*/,
+                                                            double* __restrict__ slab /*[ncells][ndofs*ndofs]*/, int* __restrict__ err) {
+  const int ne = n * (n + 1) / 2;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t c = size_t(blockIdx.x) * blockDim.x + threadIdx.x; c < ncells; c += stride) {
+    double s[kMaxDim * (kMaxDim + 1) / 2];
+    for (int e = 0; e < ne; ++e) s[e] = lengths[cell_edges[c * size_t(ne) + e] - edge_lo];
+    double ginv[kMaxDim * kMaxDim];
+    double vol;
+    if (!geometry_generic(n, s, ginv, &vol)) {
+      atomicExch(err, 1);
+      continue;
+    }
+    double G[kQfMaxComp * kQfMaxComp];
+    for (int i = 0; i < ncomp; ++i)
+      for (int j = 0; j < ncomp; ++j) G[i * ncomp + j] = minor_det(ginv, n, subsets + i * k, subsets + j * k, k);
+    double* out = slab + c * size_t(ndofs) * ndofs;
+    for (int d = 0; d < ndofs * ndofs; ++d) out[d] = 0.0;
+    for (int q = 0; q < nnodes; ++q) {
+      const double wa = coeff[c * size_t(nnodes) + q];
+      for (int j = 0; j < ndofs; ++j) {
+        const double* wj = shapes + (size_t(q) * ndofs + j) * ncomp;
+        double gw[kQfMaxComp];  // G * W_j(q): the measured column (tensor.rs:150-155)
+        for (int a = 0; a < ncomp; ++a) {
+          double m = 0.0;
+          for (int b = 0; b < ncomp; ++b) m += G[a * ncomp + b] * wj[b];
+          gw[a] = m;
+        }
+        for (int i = 0; i < ndofs; ++i) {
+          const double* wi = shapes + (size_t(q) * ndofs + i) * ncomp;
+          double val = 0.0;
+          for (int a = 0; a < ncomp; ++a) val += wi[a] * gw[a];
+          out[i * ndofs + j] += weights[q] * (wa * val);
+        }
+      }
+    }
+    for (int d = 0; d < ndofs * ndofs; ++d) out[d] = vol * out[d];
+  }
+}
+
+void weighted_mass_to_slab(fq_ctx* ctx, const fq_mesh* mesh, int grade, int nnodes, const double* h_weights,
+                           const double* h_shapes, const double* h_coeff, double* d_slab) {
+  const int n = mesh->dim;
+  FQ_REQUIRE(grade >= 0 && grade <= n, "weighted mass: the grade must lie in [0, dim]");
+  FQ_REQUIRE(nnodes >= 1, "weighted mass: a quadrature rule has at least one node");
+  const int ncomp = int(binom(n, grade)), ndofs = nlocal(n, grade);
+  if (ncomp > kQfMaxComp || grade > kQfMaxGrade) throw Error(FQ_ERR_UNSUPPORTED, "weighted mass: more than 20 form components");
+  if (mesh->ncells == 0) return;
+  std::vector<uint8_t> subsets;
+  for (uint32_t m : colex_subsets(n, grade))
+    for (int e : mask_elems(m)) subsets.push_back(uint8_t(e));
+  if (subsets.empty()) subsets.push_back(0);
+  const size_t nn = size_t(nnodes);
+  DevBuf<uint8_t> d_subsets(subsets.size());
+  DevBuf<double> d_weights(nn), d_shapes(nn * ndofs * ncomp), d_coeff(mesh->ncells * nn);
+  DevBuf<int> d_err(1);
+  FQ_CUDA(cudaMemcpyAsync(d_subsets.p, subsets.data(), subsets.size(), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(d_weights.p, h_weights, d_weights.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(d_shapes.p, h_shapes, d_shapes.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(d_coeff.p, h_coeff, d_coeff.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+  {
+    ScopedSpan span(ctx, "qf_weighted_mass");
+    const int block = 128;
+    weighted_mass_kernel<<<grid_for(mesh->ncells, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        n, grade, ncomp, ndofs, nnodes, mesh->ncells, mesh->cell_faces[1].p, mesh->lengths.p, uint32_t(mesh->edge_lo),
+        d_subsets.p, d_weights.p, d_shapes.p, d_coeff.p, d_slab, d_err.p);
+    fq_count_launch(ctx);
+    FQ_CUDA(cudaGetLastError());
+  }
+  int h = 0;
+  FQ_CUDA(cudaMemcpyAsync(&h, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h) throw Error(FQ_ERR_DEGENERATE, "a cell metric is singular");
+}
+
 // Fills `elvecs` (device, [ncells][ndofs]) from host tables and host samples.
 void source_element_vectors(fq_ctx* ctx, const fq_mesh* mesh, int grade, int nnodes, const double* h_weights,
                             const double* h_shapes, const double* h_samples, double* d_elvecs) {

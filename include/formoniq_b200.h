@@ -239,6 +239,17 @@ int fq_linear_form_destroy(fq_matfree* plan);
 int fq_source_form_assemble(fq_ctx* ctx, const fq_matfree* plan, int nnodes, const double* weights, const double* shapes,
                             const double* samples, fq_vec* out);
 
+/* ---- WeightedHodgeMass (formoniq/src/operators.rs:432-486) ----------------------------------------------------------
+ * [int_K alpha <W_sigma, W_tau> vol], the varying-coefficient mass, as a numeric pass on a matrix created by
+ * fq_assemble_symbolic(FQ_MASS, grade): the element matrices vol_K * sum_q w_q alpha(x_q) W_i(q)^T (Lambda^k g^-1) W_j(q)
+ * (CellQuadrature::integrate_pair, operators.rs:266-290) are evaluated on the device, one thread per cell, into the
+ * element slab and scattered by the K3 reduction under the same pattern semantics as every other form
+ * (`drop_exact_zeros` = galerkin.rs:173).  Host inputs as for fq_source_form_assemble; `coefficient` [ncells][nnodes] is the
+ * grade-0 section alpha sampled at the nodes of every cell (the user closure).  A later fq_assemble_numeric on the same
+ * handle re-assembles the plain (closed-form) mass. */
+int fq_weighted_mass_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, int nnodes, const double* weights,
+                             const double* shapes, const double* coefficient, int drop_exact_zeros);
+
 /* ---- SpMV fused with the halo exchange (one process per GPU, NVLink 5 / NVSwitch peer memory) -----------------
  * The reference is single-process; under the owner-computes row partition the only exchange step of the path is
  * the x halo of `LinearOperator::apply`.  Instead of exchanging halos and then multiplying, the gather of the SpMV

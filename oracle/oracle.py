@@ -367,3 +367,50 @@ def source_element_vectors(cx: "Complex", lengths_sq, grade: int, weights, shape
                 elvec[i] += weights[q] * float(f[c, q] @ (G @ shapes[q][i]))
         out[c] = vol * elvec
     return out
+
+
+def weighted_mass_elmats(cx: "Complex", lengths_sq, grade: int, weights, shapes, coefficient) -> np.ndarray:
+    """Restatement of WeightedHodgeMass::element (formoniq/src/operators.rs:477-485) for every cell:
+    CellQuadrature::integrate_pair (operators.rs:266-290: elmat[i][j] += w_q * alpha_q * inner(W_i, W_j) node-outer, then
+    vol * elmat), inner as in source_element_vectors.  Returns [ncells][nd][nd]."""
+    import itertools
+    n = cx.dim
+    edges = cx.cell_faces(1)
+    nn, nd, nc = np.asarray(shapes).shape
+    al = np.asarray(coefficient, dtype=np.float64).reshape(cx.ncells, nn)
+    subsets = sorted(itertools.combinations(range(n), grade), key=lambda c: c[::-1])
+    out = np.zeros((cx.ncells, nd, nd))
+    for c in range(cx.ncells):
+        _, gi, vol = cell_geometry(n, np.asarray(lengths_sq)[edges[c]])
+        G = np.array([[np.linalg.det(gi[np.ix_(I, J)]) if grade else 1.0 for J in subsets] for I in subsets])
+        elmat = np.zeros((nd, nd))
+        for q in range(nn):
+            W = np.asarray(shapes[q])                     # [dof][component]
+            elmat += weights[q] * (al[c, q] * (W @ (G @ W.T)))
+        out[c] = vol * elmat
+    return out
+
+
+def assemble_from_elmats(cx: "Complex", test_grade: int, trial_grade: int, elmats: np.ndarray, drop_zeros: bool = True):
+    """assemble_matrix (formoniq/src/galerkin.rs:138-188) on given element matrices: triplets in cell order, `!= 0.0`
+    filter, duplicates summed in order, CSR with ascending columns.  Returns scipy CSR (sorted, no explicit pattern loss)."""
+    import scipy.sparse as sp
+    rows_f, cols_f = cx.cell_faces(test_grade), cx.cell_faces(trial_grade)
+    nr, nc = rows_f.shape[1], cols_f.shape[1]
+    r = np.repeat(rows_f, nc, axis=1).reshape(-1)
+    c = np.tile(cols_f, (1, nr)).reshape(-1)
+    v = np.asarray(elmats, dtype=np.float64).reshape(-1)
+    if drop_zeros:
+        keep = v != 0.0
+        r, c, v = r[keep], c[keep], v[keep]
+    # stable sort by (row, col): duplicates stay in cell order and are summed sequentially
+    order = np.lexsort((c, r))
+    r, c, v = r[order], c[order], v[order]
+    key = r.astype(np.int64) * cx.nsimplices(trial_grade) + c
+    heads = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+    vals = np.zeros(len(heads))
+    seg = np.repeat(np.arange(len(heads)), np.diff(np.r_[heads, len(key)]))
+    np.add.at(vals, seg, v)
+    indptr = np.zeros(cx.nsimplices(test_grade) + 1, dtype=np.int64)
+    np.add.at(indptr, r[heads] + 1, 1)
+    return sp.csr_matrix((vals, c[heads], np.cumsum(indptr)), shape=(cx.nsimplices(test_grade), cx.nsimplices(trial_grade)))

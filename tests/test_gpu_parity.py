@@ -895,3 +895,38 @@ def test_source_form_load_vector(fq, ctx, dim, shape, grade, degree, variant):
         assert np.abs(col - mass[:, tau]).max() <= 1e-12 * np.abs(mass[:, tau]).max()
     with pytest.raises(fq.FormoniqError):
         form.assemble(mesh, samples[:-1])
+
+
+# ------------------------------------------------------------------ WeightedHodgeMass (operators.rs:432-486)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,shape,grade,variant", [(2, [5, 4], 1, "jitter"), (2, [4, 4], 0, "jitter"), (3, [3, 4, 3], 1, "jitter"),
+                                                     (3, [3, 3, 3], 2, "minkowski"), (3, [2, 3, 2], 3, "plain"), (4, [2, 1, 2, 2], 2, "jitter")])
+def test_weighted_hodge_mass(fq, ctx, dim, shape, grade, variant):
+    # structural pattern (drop_exact_zeros = False): a quadrature sum that should cancel exactly leaves rounding dust, so
+    # the value-dependent pattern of galerkin.rs:173 is not comparable between two summation orders
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=variant == "jitter", minkowski=variant == "minkowski")
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    form = fq.WeightedHodgeMass(dim, grade, degree=2)
+    nn = form.shapes.shape[0]
+    # the reference's own test (operators.rs:897-918): alpha = c  =>  c * the closed-form mass
+    plain = cx.assemble(s, O.MASS, grade, drop_zeros=False).to_scipy()
+    scale = np.abs(plain.data).max()
+    a = form.assemble(mesh, np.full((cx.ncells, nn), 2.5), drop_exact_zeros=False)
+    got = a.to_scipy()
+    assert np.array_equal(got.indptr, plain.indptr) and np.array_equal(got.indices, plain.indices)
+    assert np.abs(got.data - 2.5 * plain.data).max() <= 1e-12 * scale
+    # a varying coefficient against the oracle's restatement, assembled by the reference's scatter
+    rng = np.random.default_rng(dim * 10 + grade)
+    alpha = 1.0 + rng.random((cx.ncells, nn))
+    elm = O.weighted_mass_elmats(cx, s, grade, form.weights, form.shapes, alpha)
+    exp = O.assemble_from_elmats(cx, grade, grade, elm, drop_zeros=False)
+    form.numeric(mesh, a, alpha, drop_exact_zeros=False)
+    got = a.to_scipy()
+    assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+    assert np.abs(got.data - exp.data).max() <= 1e-12 * np.abs(exp.data).max()
+    # with the reference's `!= 0.0` filter the kept entries are the same values
+    b = form.assemble(mesh, alpha, drop_exact_zeros=True).to_scipy()
+    assert b.nnz <= got.nnz and abs((b - got)).max() <= 1e-12 * np.abs(exp.data).max()
+    # the handle goes back to the closed-form mass with the ordinary numeric pass
+    a.numeric(mesh, False)
+    assert np.abs(a.to_scipy().data - plain.data).max() <= 1e-12 * scale

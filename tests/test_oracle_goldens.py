@@ -535,3 +535,24 @@ def test_source_form_law_of_the_reference():
             ev = O.source_element_vectors(cx, s, grade, weights, shapes, samples)
             load = O.assemble_vector(cx, grade, ev)
             assert np.abs(load - mass[:, tau]).max() <= 1e-12 * np.abs(mass[:, tau]).max(), (dim, grade, mink)
+
+
+def test_weighted_hodge_mass_on_a_constant_is_the_closed_form():
+    # crates/formoniq/src/operators.rs:897-918: on alpha = c the degree-2 quadrature returns c times the exact HodgeMass,
+    # at every dimension and grade (here on jittered and Lorentzian cells too); and assemble_from_elmats reproduces the
+    # oracle's assembled mass from the oracle's own element matrices (pattern and values).
+    from formoniq_b200 import quadrature as Q
+    for dim, n, mink in ((1, 4, False), (2, 3, False), (3, 2, False), (3, 2, True)):
+        cx, s, _ = kuhn_problem(dim, n, jitter=not mink, minkowski=mink)
+        for grade in range(dim + 1):
+            nodes, weights = Q.quad_rule(dim, 2)
+            shapes = Q.whitney_shapes(dim, grade, nodes)
+            exact = cx.elmat_batch(s, O.MASS, grade)
+            for cval in (1.0, 2.5):
+                got = O.weighted_mass_elmats(cx, s, grade, weights, shapes, np.full((cx.ncells, len(weights)), cval))
+                assert np.abs(got - cval * exact).max() <= 1e-12 * np.abs(exact).max(), (dim, grade, mink)
+            ref = cx.assemble(s, O.MASS, grade)
+            erp, eci, eva = ref.arrays()
+            mine = O.assemble_from_elmats(cx, grade, grade, exact)
+            assert np.array_equal(mine.indptr, erp) and np.array_equal(mine.indices, eci)
+            assert np.array_equal(mine.data, eva)
