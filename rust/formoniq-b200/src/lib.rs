@@ -33,6 +33,8 @@ unsafe extern "C" {
   fn fq_mesh_destroy(mesh: *mut fq_mesh) -> c_int;
   fn fq_assemble(ctx: *mut fq_ctx, mesh: *const fq_mesh, kind: c_int, grade: c_int, drop_exact_zeros: c_int,
                  out: *mut *mut fq_csr) -> c_int;
+  fn fq_assemble_symbolic(ctx: *mut fq_ctx, mesh: *const fq_mesh, kind: c_int, grade: c_int, row_begin: usize,
+                          row_end: usize, out: *mut *mut fq_csr) -> c_int;
   fn fq_csr_shape(csr: *const fq_csr, nrows: *mut usize, ncols: *mut usize, nnz: *mut usize) -> c_int;
   fn fq_csr_download(ctx: *mut fq_ctx, csr: *const fq_csr, row_offsets: *mut usize, col_indices: *mut usize,
                      values: *mut c_double) -> c_int;
@@ -53,6 +55,8 @@ unsafe extern "C" {
   fn fq_linear_form_assemble(ctx: *mut fq_ctx, plan: *const fq_matfree, element_vectors: *const c_double,
                              out: *mut fq_vec) -> c_int;
   fn fq_linear_form_destroy(plan: *mut fq_matfree) -> c_int;
+  fn fq_weighted_mass_numeric(ctx: *mut fq_ctx, mesh: *const fq_mesh, csr: *mut fq_csr, nnodes: c_int, weights: *const c_double,
+                              shapes: *const c_double, coefficient: *const c_double, drop_exact_zeros: c_int) -> c_int;
   fn fq_source_form_assemble(ctx: *mut fq_ctx, plan: *const fq_matfree, nnodes: c_int, weights: *const c_double,
                              shapes: *const c_double, samples: *const c_double, out: *mut fq_vec) -> c_int;
   // HodgeBlocks (hodge.rs:62-99): symbolic once, numeric per geometry (one fused kernel from the second pass on)
@@ -253,6 +257,31 @@ impl<'d> GpuHodgeBlocks<'d> {
   }
 }
 impl Drop for GpuHodgeBlocks<'_> { fn drop(&mut self) { unsafe { fq_hodge_destroy(self.raw) }; } }
+
+// ---- WeightedHodgeMass (formoniq/src/operators.rs:432-486) -------------------------------------------------------------
+/// Drop-in for `WeightedHodgeMass::new(coefficient, grade, qr).assemble(topology, geometry)`: the rule and the shape
+/// table are built as `WeightedHodgeMass::new` does, the scalar coefficient is sampled at the nodes of every cell with
+/// rayon, element quadrature and scatter run on the device.
+pub fn assemble_weighted_mass<F: Sync + formoniq::Section>(dev: &Device, mesh: &DeviceMesh, topology: &Complex, coefficient: &F,
+                                                           grade: usize, qr: Option<simplicial::atlas::quadrature::SimplexQuadRule>)
+  -> GalerkinMatrix {
+  use rayon::prelude::*;
+  let dim = coefficient.dim();
+  let qr = qr.unwrap_or(simplicial::atlas::quadrature::SimplexQuadRule::degree(dim, 1));
+  let nodes: Vec<_> = qr.points().map(|b| b.to_coords()).collect();
+  let shapes = derham::interpolate::samples::LsfSamples::whitney(dim, grade, &nodes);
+  let weights: Vec<f64> = qr.weights().iter().copied().collect();
+  let mut table = Vec::new();
+  for q in 0..nodes.len() { for w in shapes.at_node(q) { table.extend(w.components().iter().copied()); } }
+  let alpha: Vec<f64> = topology.cells().handle_par_iter()
+    .flat_map_iter(|cell| nodes.iter().map(|b| coefficient.at(&cell.point(b.clone())).as_scalar()).collect::<Vec<_>>())
+    .collect();
+  let mut raw = ptr::null_mut();
+  check(unsafe { fq_assemble_symbolic(dev.0, mesh.raw, 0 /*FQ_MASS*/, grade as c_int, 0, usize::MAX, &mut raw) });
+  check(unsafe { fq_weighted_mass_numeric(dev.0, mesh.raw, raw, nodes.len() as c_int, weights.as_ptr(), table.as_ptr(),
+                                          alpha.as_ptr(), 1) });
+  download(dev, raw)
+}
 
 // ---- LinearForm::assemble (formoniq/src/galerkin.rs:279-312) -----------------------------------------------------
 // `LinearForm::element` evaluates a user `Section` at quadrature nodes and stays host code; the element vectors of all
