@@ -842,20 +842,20 @@ template <class Fn, int NE>
 static void launch_tile_alt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
   static int variant = -1;
   if (variant < 0) {
-    const char* e = std::getenv("FQ_ALT_REGS");  // tuning (16 consumer warps): 0 = 128/56, 1 = 112/64, 2 = 96/72 (default)
-    variant = e ? std::atoi(e) : 2;
-    if (variant < 0 || variant > 2) variant = 2;
+    const char* e = std::getenv("FQ_ALT_REGS");  // tuning (16 consumer warps): 0 = 128/56, 1 = 112/64 (default), 2 = 96/72
+    variant = e ? std::atoi(e) : 1;
+    if (variant < 0 || variant > 2) variant = 1;
   }
   if (plan.stream_warps == 24)
     launch_tile_alt_v<Fn, NE, 24, 88, 56>(ctx, plan, params);
   else if (plan.stream_warps == 20)
     launch_tile_alt_v<Fn, NE, 20, 88, 64>(ctx, plan, params);
-  else if (variant == 1)
-    launch_tile_alt_v<Fn, NE, 16, 112, 64>(ctx, plan, params);
+  else if (variant == 2)
+    launch_tile_alt_v<Fn, NE, 16, 96, 72>(ctx, plan, params);
   else if (variant == 0)
     launch_tile_alt_v<Fn, NE, 16, 128, 56>(ctx, plan, params);
   else
-    launch_tile_alt_v<Fn, NE, 16, 96, 72>(ctx, plan, params);
+    launch_tile_alt_v<Fn, NE, 16, 112, 64>(ctx, plan, params);
 }
 template <class Fn, int NE>
 static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
