@@ -266,6 +266,132 @@ static void emit_core(const std::string& name, int n, int k, int variant, CoreEn
   e.nouts = nouts;
 }
 
+// Staged "set" functions for the tile-fused kernel (tile.cu): the element matrices of a block set, every
+// distinct value of every row stored once (tape.hpp: set_layout).  Stage A = the geometry head of the tape (up to
+// the last division / square root; `mid` carries the values that are live across the cut), then one function per
+// stage group (the blocks deriving from one mass grade): the backward slice of that group's stores.  An operation
+// needed by several groups is evaluated by each of them on the same operands: same bits as the unsplit tape.
+struct SetEntry {
+  std::string name;
+  int n, fused_k, kind, grade, ninputs, ngroups;
+};
+static bool emit_set(const std::string& name, int n, const std::vector<BlockSpec>& blocks, SetEntry& e) {
+  TapeBuilder tb;
+  Tape t;
+  const SetLayout L = set_layout(n, blocks, &tb, &t);
+  if (L.puts.empty() || L.ngroups > 3) return false;
+  const std::vector<TapeOp> ops = tb.ssa_ops();
+  int cut = -1;
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (ops[i].op == OP_DIV || ops[i].op == OP_SQRTABS) cut = int(i);
+  auto is_store = [](const TapeOp& o) { return o.op == OP_STORE || o.op == OP_STOREN || o.op == OP_STOREC; };
+  auto uses = [&](const TapeOp& o, uint32_t* u) -> int {
+    switch (o.op) {
+      case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: u[0] = o.a; u[1] = o.b; return 2;
+      case OP_MULC: case OP_SQRTABS: case OP_STORE: case OP_STOREN: u[0] = o.a; return 1;
+      default: return 0;
+    }
+  };
+  std::map<int, const SetPut*> put_at;
+  for (const SetPut& p : L.puts) put_at[p.op] = &p;
+  std::map<uint32_t, int> def_pos;
+  for (int i = 0; i < t.ninputs; ++i) def_pos[uint32_t(i)] = -1;
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (!is_store(ops[i])) def_pos[ops[i].d] = int(i);
+  // group masks by backward slicing from the registered puts
+  std::map<uint32_t, int> need;
+  for (size_t i = ops.size(); i-- > 0;) {
+    const TapeOp& o = ops[i];
+    uint32_t u[2];
+    const int nu = uses(o, u);
+    int mask = 0;
+    if (is_store(o)) {
+      auto it = put_at.find(int(i));
+      if (it == put_at.end()) continue;  // a duplicate of an earlier put of the same row, or an exact zero
+      mask = 1 << L.blocks[size_t(it->second->block)].group;
+    } else {
+      mask = need.count(o.d) ? need[o.d] : 0;
+    }
+    for (int q = 0; q < nu; ++q) need[u[q]] |= mask;
+  }
+  std::map<uint32_t, int> mid_of;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const TapeOp& o = ops[i];
+    if (int(i) <= cut && !is_store(o)) continue;
+    if (is_store(o) && !put_at.count(int(i))) continue;
+    if (!is_store(o) && !(need.count(o.d) && need[o.d])) continue;
+    uint32_t u[2];
+    const int nu = uses(o, u);
+    for (int q = 0; q < nu; ++q)
+      if (def_pos.at(u[q]) <= cut && !mid_of.count(u[q])) {
+        const int idx = int(mid_of.size());
+        mid_of[u[q]] = idx;
+      }
+  }
+  auto line = [&](const TapeOp& o) -> std::string {
+    char buf[256];
+    switch (o.op) {
+      case OP_ADD: std::snprintf(buf, sizeof buf, "  const double %s = __dadd_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_SUB: std::snprintf(buf, sizeof buf, "  const double %s = __dsub_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_MUL: std::snprintf(buf, sizeof buf, "  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_MULC: std::snprintf(buf, sizeof buf, "  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), cst(tb.consts[o.b]).c_str()); break;
+      case OP_DIV: std::snprintf(buf, sizeof buf, "  const double %s = __ddiv_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
+      case OP_SQRTABS: std::snprintf(buf, sizeof buf, "  const double %s = __dsqrt_rn(fabs(%s));\n", reg(o.d).c_str(), reg(o.a).c_str()); break;
+      case OP_LOADC: std::snprintf(buf, sizeof buf, "  const double %s = %s;\n", reg(o.d).c_str(), cst(tb.consts[o.b]).c_str()); break;
+      default: buf[0] = 0; break;
+    }
+    return buf;
+  };
+  std::ostringstream sa;
+  std::vector<std::ostringstream> sg(3);
+  for (int i = 0; i < t.ninputs; ++i) sa << "  const double r" << i << " = s[" << i << "];\n";
+  // stage A keeps only what some group (or mid) needs
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const TapeOp& o = ops[i];
+    if (is_store(o)) {
+      auto it = put_at.find(int(i));
+      if (it == put_at.end()) continue;
+      const SetPut& p = *it->second;
+      const int g = L.blocks[size_t(p.block)].group;
+      std::string v;
+      if (o.op == OP_STORE) v = reg(o.a);
+      else if (o.op == OP_STOREN) v = "-" + reg(o.a);
+      else v = cst(tb.consts[o.b]);
+      sg[size_t(g)] << "  sink.template put<" << p.block << ", " << p.row << ", " << p.slot << ">(" << v << ");\n";
+      continue;
+    }
+    const int m = need.count(o.d) ? need[o.d] : 0;
+    if (!m) continue;
+    if (int(i) <= cut) {
+      sa << line(o);
+    } else {
+      for (int g = 0; g < 3; ++g)
+        if (m >> g & 1) sg[size_t(g)] << line(o);
+    }
+  }
+  std::printf("// set %s: n=%d inputs=%d groups=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", name.c_str(), n, t.ninputs, L.ngroups,
+              t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
+  const int nmid = int(mid_of.size());
+  std::printf("constexpr int %s_nmid = %d;\nconstexpr int %s_ngroups = %d;\n", name.c_str(), nmid > 0 ? nmid : 1, name.c_str(), L.ngroups);
+  std::printf("__device__ __forceinline__ void %s_a(const double* __restrict__ s, double* __restrict__ mid) {\n%s", name.c_str(),
+              sa.str().c_str());
+  for (const auto& kv : mid_of) std::printf("  mid[%d] = %s;\n", kv.second, reg(kv.first).c_str());
+  std::printf("}\n");
+  for (int g = 0; g < 3; ++g) {
+    std::printf("template <class Sink>\n__device__ __forceinline__ void %s_g%d(const double* __restrict__ mid, Sink& sink) {\n",
+                name.c_str(), g);
+    if (g < L.ngroups)
+      for (const auto& kv : mid_of) std::printf("  const double %s = mid[%d]; (void)%s;\n", reg(kv.first).c_str(), kv.second, reg(kv.first).c_str());
+    std::printf("%s}\n", sg[size_t(g)].str().c_str());
+  }
+  std::printf("\n");
+  e.name = name;
+  e.n = n;
+  e.ninputs = t.ninputs;
+  e.ngroups = L.ngroups;
+  return true;
+}
+
 int main() {
   std::printf("// GENERATED by gen_elmat.cpp from tape.hpp — do not edit.\n#pragma once\n\n");
   std::vector<Entry> entries;
@@ -324,6 +450,29 @@ int main() {
   std::printf("#define FQ_GEN_CORE_LIST(X) \\\n");
   for (const CoreEntry& e : cores)
     std::printf("  X(%s, %d, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.k, e.variant, e.ninputs, e.ndistinct, e.nouts);
+  std::printf("\n");
+  // staged block sets of the tile-fused kernel: hodge_blocks(k) and every single block
+  std::vector<SetEntry> sets;
+  for (int n = 1; n <= 3; ++n) {
+    for (int k = 0; k <= n; ++k) {
+      SetEntry e{};
+      e.fused_k = k, e.kind = -1, e.grade = k;
+      if (emit_set("fq_set_n" + std::to_string(n) + "_hodge" + std::to_string(k), n, hodge_blocks(k), e)) sets.push_back(e);
+    }
+    for (int k = 0; k <= n + 1; ++k)
+      for (int kind = 0; kind < 4; ++kind) {
+        if (kind != KIND_MASS && k == 0) continue;
+        if (k == n + 1 && kind != KIND_DIF_BOTH) continue;
+        SetEntry e{};
+        e.fused_k = -1, e.kind = kind, e.grade = k;
+        if (emit_set("fq_set_n" + std::to_string(n) + "_kind" + std::to_string(kind) + "_k" + std::to_string(k), n, {{kind, k}}, e))
+          sets.push_back(e);
+      }
+  }
+  // X-macro list: (function, n, fused_k, kind, grade, ninputs)
+  std::printf("#define FQ_GEN_SET_LIST(X) \\\n");
+  for (const SetEntry& e : sets)
+    std::printf("  X(%s, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.fused_k, e.kind, e.grade, e.ninputs);
   std::printf("\n");
   return 0;
 }

@@ -645,4 +645,82 @@ inline std::vector<BlockSpec> hodge_blocks(int k) {
   return {{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_DIF_TEST, k}, {KIND_DIF_BOTH, k + 1}};
 }
 
+// ---------------------------------------------------------------- block sets of the tile-fused kernel (tile.cu)
+// The tile kernel stores, for every (cell, owned local row) of a block, the DISTINCT values of that row of the
+// block's element matrix ("column slots"): entries of one row that the tape proves to be the same value (same
+// SSA register, same sign) share a slot, exact zeros have none.  Blocks are evaluated in stage groups: one group
+// per mass grade the blocks derive from (mass(g), dif_*(g) share M_g), in block order.
+struct SetBlock {
+  int kind = 0, grade = 0, tg = 0, rg = 0, rows = 0, cols = 0, out_offset = 0;
+  int group = -1;        // stage group, -1 for an empty block (a grade off [0, n]: the zero space)
+  int d = 0;             // column slots per row (max over the rows)
+  std::vector<int> cs;   // [rows*cols] column slot of every entry, -1 = exact zero
+};
+struct SetPut {          // one generated store: value of `op` (index into the SSA ops) -> (block, row, column slot)
+  int op, block, row, slot;
+};
+struct SetLayout {
+  int n = 0, ninputs = 0, ngroups = 0;
+  std::vector<SetBlock> blocks;
+  std::vector<SetPut> puts;   // in tape order
+};
+inline SetLayout set_layout(int n, const std::vector<BlockSpec>& specs, TapeBuilder* keep_builder = nullptr,
+                            Tape* keep_tape = nullptr) {
+  TapeBuilder local;
+  TapeBuilder& tb = keep_builder ? *keep_builder : local;
+  std::vector<BlockLayout> layout;
+  const Tape t = build_tape(n, specs, &layout, &tb);
+  if (keep_tape) *keep_tape = t;
+  SetLayout L;
+  L.n = n;
+  L.ninputs = t.ninputs;
+  std::vector<int> group_grade;
+  for (const BlockLayout& bl : layout) {
+    SetBlock b;
+    b.kind = bl.kind, b.grade = bl.grade, b.rows = bl.rows, b.cols = bl.cols, b.out_offset = bl.out_offset;
+    kind_grades(bl.kind, bl.grade, b.tg, b.rg);
+    b.cs.assign(size_t(b.rows) * size_t(b.cols), -1);
+    if (b.rows > 0 && b.cols > 0) {
+      int g = -1;
+      for (size_t i = 0; i < group_grade.size(); ++i)
+        if (group_grade[i] == bl.grade && bl.kind != KIND_LUMPED) g = int(i);
+      if (g < 0) {
+        group_grade.push_back(bl.kind == KIND_LUMPED ? -1000 : bl.grade);
+        g = int(group_grade.size()) - 1;
+      }
+      b.group = g;
+    }
+    L.blocks.push_back(b);
+  }
+  L.ngroups = int(group_grade.size());
+  // value identity of a store: (opcode class, register / constant index)
+  std::vector<std::map<std::tuple<int, uint32_t>, int>> slots;  // per (block, row)
+  std::vector<int> row_base(L.blocks.size() + 1, 0);
+  for (size_t b = 0; b < L.blocks.size(); ++b) row_base[b + 1] = row_base[b] + L.blocks[b].rows;
+  slots.resize(size_t(row_base.back()));
+  const std::vector<TapeOp>& ops = tb.ssa_ops();
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const TapeOp& o = ops[i];
+    if (o.op != OP_STORE && o.op != OP_STOREN && o.op != OP_STOREC) continue;
+    int blk = -1;
+    for (size_t b = 0; b < L.blocks.size(); ++b)
+      if (int(o.d) >= L.blocks[b].out_offset && int(o.d) < L.blocks[b].out_offset + L.blocks[b].rows * L.blocks[b].cols)
+        blk = int(b);
+    if (blk < 0) throw std::runtime_error("set_layout: store outside every block");
+    SetBlock& B = L.blocks[size_t(blk)];
+    const int e = int(o.d) - B.out_offset, r = e / B.cols;
+    if (o.op == OP_STOREC && tb.consts[o.b] == 0.0) continue;  // exact zero: no slot
+    const auto key = std::make_tuple(int(o.op), o.op == OP_STOREC ? o.b : o.a);
+    auto& m = slots[size_t(row_base[size_t(blk)] + r)];
+    auto it = m.find(key);
+    if (it == m.end()) {
+      it = m.emplace(key, int(m.size())).first;
+      L.puts.push_back(SetPut{int(i), blk, r, it->second});
+    }
+    B.cs[size_t(e)] = it->second;
+    B.d = std::max(B.d, it->second + 1);
+  }
+  return L;
+}
+
 }  // namespace fq

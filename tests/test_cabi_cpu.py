@@ -63,6 +63,23 @@ def test_staged_core_tapes_equal_the_unsplit_tapes_bitwise(tmp_path):
     assert ncores >= 18 and ncells >= 3600
 
 
+def test_tile_plan_host_builder_and_staged_sets_reproduce_the_oracle(tmp_path):
+    # the tile-fused kernel's plan (row slots, record streams) built by the host reference builder and interpreted on
+    # the CPU with the GENERATED staged block-set functions must give the oracle's structural pattern, its values
+    # bitwise, and its value-dependent (`!= 0.0`) pattern, for every Hodge block set and single block, dims 1..3
+    from formoniq_b200 import build as B
+
+    B.generate()
+    exe = tmp_path / "tile_plan_check"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-ffp-contract=off",
+                           os.path.join(ROOT, "tests", "cpp", "tile_plan_check.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.startswith("OK "), out.stdout
+    ncases, nnz = map(int, out.stdout.split()[1:3])
+    assert ncases >= 100 and nnz > 100000
+
+
 def test_kuhn_closed_form_numbering_matches_reference_construction(fq):
     from oracle import oracle as O
 
