@@ -88,6 +88,8 @@ __global__ void sym_rowptr_kernel(const uint32_t* __restrict__ row_of_nnz, uint3
   }
 }
 
+// Symbolic phase, part 1: shape, element layout and row range of the block; the pattern itself is produced either by
+// the tile plan builder (tile.cu) on the first numeric pass or, for the slab path, by K2 below (lazily).
 void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, size_t row_begin, size_t row_end,
                        fq_csr* out) {
   const int dim = mesh->dim;
@@ -111,12 +113,12 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
   out->has_plan = true;
   out->compact_valid = false;
   out->pattern_valid = false;
+  out->k2_done = false;
   const size_t nrows_local = row_end - row_begin;
-  const size_t T = size_t(nt) * size_t(nr);
-  const uint64_t ncontrib_all = uint64_t(mesh->ncells) * T;
-  out->s_row_ptr.alloc(nrows_local + 1);
+  const uint64_t ncontrib_all = uint64_t(mesh->ncells) * uint64_t(nt) * uint64_t(nr);
   if (ncontrib_all == 0 || nrows_local == 0) {
     // pairing() of an empty space: correctly shaped zero matrix (whitney_complex.rs:113-122)
+    out->s_row_ptr.alloc(nrows_local + 1);
     FQ_CUDA(cudaMemsetAsync(out->s_row_ptr.p, 0, (nrows_local + 1) * sizeof(uint32_t), ctx->stream));
     out->s_nnz = 0;
     out->ncontrib = 0;
@@ -126,12 +128,29 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
     out->contrib_src.alloc(1);
     out->s_values.alloc(1);
     out->keep.alloc(1);
+    out->k2_done = true;
     return;
   }
   FQ_REQUIRE(mesh->cell_faces[size_t(tg)].p && mesh->cell_faces[size_t(rg)].p,
              "mesh was created without the face tables of the required grades");
   FQ_REQUIRE(ncontrib_all < (1ull << 32), "more than 2^32 element entries in one block: not supported");
   FQ_REQUIRE(gcols < (1ull << 32) && grows < (1ull << 32), "more than 2^32 rows/cols: not supported");
+}
+
+// Symbolic phase, part 2 (K2): the global-sort pattern + cell-slot -> nnz map of the slab path.
+static void ensure_k2(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* out) {
+  if (out->k2_done) return;
+  const int dim = mesh->dim;
+  const int kind = out->kind, grade = out->grade;
+  int tg, rg;
+  kind_grades(kind, grade, tg, rg);
+  const int nt = nlocal(dim, tg), nr = nlocal(dim, rg);
+  const size_t gcols = out->ncols;
+  const size_t row_begin = out->row_begin, row_end = out->row_end;
+  const size_t nrows_local = row_end - row_begin;
+  const size_t T = size_t(nt) * size_t(nr);
+  const uint64_t ncontrib_all = uint64_t(mesh->ncells) * T;
+  out->s_row_ptr.alloc(nrows_local + 1);
   const int col_bits = bits_for(gcols);
   const int row_bits = bits_for(nrows_local + 1);
   FQ_REQUIRE(col_bits + row_bits <= 63, "key overflow");
@@ -211,6 +230,7 @@ void assemble_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int kind, int grade, si
   out->keep.alloc(s_nnz ? s_nnz : 1);
   stream_build_blocks(ctx, out->contrib_ptr.p, s_nnz, out->ncontrib, out->gather_blocks, out->ngather_blocks);
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->k2_done = true;
 }
 
 // ------------------------------------------------------------------ numeric
@@ -271,6 +291,43 @@ __global__ void num_rowptr_kernel(const uint32_t* __restrict__ s_row_ptr, const 
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nrows; r += stride) row_ptr[r] = pos[s_row_ptr[r]];
 }
 
+// keep[] / s_values[] of a structural pass -> the reference's value-dependent pattern (galerkin.rs:173): pos = exclusive
+// scan of keep, compacted row_ptr / col_idx / values.
+static void compact_pattern(fq_ctx* ctx, fq_csr* csr) {
+  const size_t nrows_local = csr->row_end - csr->row_begin;
+  const size_t s_nnz = csr->s_nnz;
+  const int block = 256;
+  ScopedSpan span_compact(ctx, "k3_compact");
+  DevBuf<uint32_t> k32(s_nnz + 1);
+  if (csr->pos.n != s_nnz + 1) csr->pos.alloc(s_nnz + 1);
+  if (csr->d_changed.n != 1) csr->d_changed.alloc(1);
+  num_keep_to_u32<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(csr->keep.p, uint32_t(s_nnz), k32.p);
+  FQ_CUDA(cudaMemsetAsync(k32.p + s_nnz, 0, sizeof(uint32_t), ctx->stream));
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, k32.p, csr->pos.p, int64_t(s_nnz + 1), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, k32.p, csr->pos.p, int64_t(s_nnz + 1), ctx->stream));
+  fq_count_launch(ctx, 3);
+  uint32_t nnz = 0;
+  FQ_CUDA(cudaMemcpyAsync(&nnz, csr->pos.p + s_nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  csr->dropped = true;
+  csr->nnz = nnz;
+  csr->row_ptr.alloc(nrows_local + 1);
+  csr->col_idx.alloc(nnz ? nnz : 1);
+  csr->values.alloc(nnz ? nnz : 1);
+  num_compact_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      csr->keep.p, csr->pos.p, uint32_t(s_nnz), csr->s_col_idx.p, csr->s_values.p, csr->col_idx.p, csr->values.p);
+  num_rowptr_kernel<<<grid_for(nrows_local + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      csr->s_row_ptr.p, csr->pos.p, uint32_t(nrows_local), csr->row_ptr.p);
+  fq_count_launch(ctx, 2);
+  FQ_CUDA(cudaGetLastError());
+  csr->compact_valid = true;
+  csr->pattern_valid = true;
+  csr->spmv_ready = false;
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 static void gather_structural(fq_ctx* ctx, fq_csr* csr) {
   ScopedSpan span(ctx, "k3_gather");
   stream_reduce(ctx, csr->gather_blocks.p, csr->ngather_blocks, csr->contrib_ptr.p, csr->contrib_src.p, nullptr, csr->slab.p,
@@ -325,76 +382,129 @@ static void numeric_reduce(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool d
   }
   // slow path: structural gather, then compaction to the reference's value-dependent pattern
   gather_structural(ctx, csr);
-  ScopedSpan span_compact(ctx, "k3_compact");
-  DevBuf<uint32_t> k32(s_nnz + 1);
-  if (csr->pos.n != s_nnz + 1) csr->pos.alloc(s_nnz + 1);
-  if (csr->d_changed.n != 1) csr->d_changed.alloc(1);
-  num_keep_to_u32<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(csr->keep.p, uint32_t(s_nnz), k32.p);
-  FQ_CUDA(cudaMemsetAsync(k32.p + s_nnz, 0, sizeof(uint32_t), ctx->stream));
-  size_t tmp_bytes = 0;
-  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, k32.p, csr->pos.p, int64_t(s_nnz + 1), ctx->stream));
-  DevBuf<uint8_t> tmp(tmp_bytes);
-  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, k32.p, csr->pos.p, int64_t(s_nnz + 1), ctx->stream));
-  fq_count_launch(ctx, 3);
-  uint32_t nnz = 0;
-  FQ_CUDA(cudaMemcpyAsync(&nnz, csr->pos.p + s_nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  csr->dropped = true;
-  csr->nnz = nnz;
-  csr->row_ptr.alloc(nrows_local + 1);
-  csr->col_idx.alloc(nnz ? nnz : 1);
-  csr->values.alloc(nnz ? nnz : 1);
-  num_compact_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      csr->keep.p, csr->pos.p, uint32_t(s_nnz), csr->s_col_idx.p, csr->s_values.p, csr->col_idx.p, csr->values.p);
-  num_rowptr_kernel<<<grid_for(nrows_local + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      csr->s_row_ptr.p, csr->pos.p, uint32_t(nrows_local), csr->row_ptr.p);
-  fq_count_launch(ctx, 2);
-  FQ_CUDA(cudaGetLastError());
-  csr->assembly_bytes += int64_t(8 * size_t(nnz));
-  csr->compact_valid = true;
-  csr->pattern_valid = true;
-  csr->spmv_ready = false;
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  compact_pattern(ctx, csr);
+  csr->assembly_bytes += int64_t(8 * csr->nnz);
 }
 
-// The pattern the tile plan would be built from is the one the last slab pass left.
-static bool pattern_ready(const fq_csr* csr, bool drop) {
-  if (!csr->has_plan || csr->slab_passes < 1) return false;
-  if (csr->s_nnz == 0) return true;
-  return drop ? (csr->dropped && csr->compact_valid) : (!csr->dropped && csr->pattern_valid);
+// The structural pattern becomes the active one (no dropping): index arrays copied once, values assembled in place.
+static void adopt_structural_pattern(fq_ctx* ctx, fq_csr* csr) {
+  const size_t nrows_local = csr->row_end - csr->row_begin;
+  const size_t s_nnz = csr->s_nnz;
+  if (csr->dropped || csr->row_ptr.n != nrows_local + 1 || csr->nnz != s_nnz || !csr->pattern_valid) {
+    csr->row_ptr.alloc(nrows_local + 1);
+    csr->col_idx.alloc(s_nnz ? s_nnz : 1);
+    csr->values.alloc(s_nnz ? s_nnz : 1);
+    FQ_CUDA(cudaMemcpyAsync(csr->row_ptr.p, csr->s_row_ptr.p, (nrows_local + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+    if (s_nnz)
+      FQ_CUDA(cudaMemcpyAsync(csr->col_idx.p, csr->s_col_idx.p, s_nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    csr->spmv_ready = false;
+  }
+  csr->dropped = false;
+  csr->pattern_valid = true;
+  csr->compact_valid = false;
+  csr->nnz = s_nnz;
+}
+
+// Numeric pass through the tile-fused kernel.  The plan's record streams carry either structural destinations (first
+// pass, or no dropping) or the destinations of the value-dependent pattern found by the first pass.
+static bool tile_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop) {
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    std::shared_ptr<TilePlan> plan = csrs[0]->tile_plan;
+    if (plan && !tile_plan_matches(*plan, mesh, csrs, nblocks)) plan.reset();
+    // a plan whose destinations were retargeted to a dropped pattern cannot serve a structural pass: rebuild
+    if (plan && tile_plan_compact(*plan) && !drop) plan.reset();
+    if (!plan) {
+      ScopedSpan span(ctx, "tile_plan_build");
+      plan = tile_plan_build(ctx, mesh, csrs, nblocks);
+      for (int b = 0; b < nblocks; ++b) {
+        csrs[b]->tile_plan = plan;
+        csrs[b]->pattern_valid = false;
+        csrs[b]->compact_valid = false;
+        csrs[b]->plan_build_ms = plan ? tile_plan_build_ms(*plan) : 0.0;
+      }
+      if (!plan) {
+        csrs[0]->tile_refused = 1;  // does not apply to this block set / mesh: stay on the slab path
+        return false;
+      }
+      for (int b = 0; b < nblocks; ++b) csrs[b]->slab.release();
+    }
+    double* vals[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t* keeps[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int b = 0; b < nblocks; ++b) csrs[b]->inv_diag.release();
+    if (!drop) {
+      for (int b = 0; b < nblocks; ++b) {
+        adopt_structural_pattern(ctx, csrs[b]);
+        vals[b] = csrs[b]->values.p;
+      }
+      tile_assemble(ctx, mesh, *plan, vals, nullptr);
+      tile_plan_drop(*plan) = false;
+      return true;
+    }
+    if (tile_plan_compact(*plan)) {
+      // steady state: the cached value-dependent pattern is reused and verified by the kernel
+      for (int b = 0; b < nblocks; ++b) vals[b] = csrs[b]->values.p;
+      if (tile_assemble(ctx, mesh, *plan, vals, nullptr)) return true;
+      // the zero / non-zero classification changed with the geometry: rebuild the structural plan and redo the pass
+      for (int b = 0; b < nblocks; ++b) csrs[b]->tile_plan.reset();
+      continue;
+    }
+    // first pass under dropping semantics: structural values + classification, then compaction
+    for (int b = 0; b < nblocks; ++b) {
+      fq_csr* csr = csrs[b];
+      const size_t n = csr->s_nnz ? csr->s_nnz : 1;
+      if (csr->s_values.n != n) csr->s_values.alloc(n);
+      if (csr->keep.n != n) csr->keep.alloc(n);
+      vals[b] = csr->s_values.p;
+      keeps[b] = csr->keep.p;
+    }
+    tile_assemble(ctx, mesh, *plan, vals, keeps);
+    for (int b = 0; b < nblocks; ++b) {
+      if (csrs[b]->s_nnz == 0) {
+        adopt_structural_pattern(ctx, csrs[b]);
+        csrs[b]->dropped = true;
+        csrs[b]->compact_valid = true;
+        if (csrs[b]->pos.n != 1) {
+          csrs[b]->pos.alloc(1);
+          FQ_CUDA(cudaMemsetAsync(csrs[b]->pos.p, 0, sizeof(uint32_t), ctx->stream));
+        }
+        continue;
+      }
+      compact_pattern(ctx, csrs[b]);
+    }
+    tile_retarget(ctx, *plan);
+    tile_plan_drop(*plan) = true;
+    for (int b = 0; b < nblocks; ++b) csrs[b]->s_values.release();  // scratch of the first pass only
+    return true;
+  }
+  return false;
 }
 
 void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop_exact_zeros) {
-  // ---- fast path: tile-fused K1+K3 (tile.cu), from the second numeric pass on
+  // ---- fast path: tile-fused K1+K3 (tile.cu); its plan builder is also the symbolic phase
   {
-    bool ready = nblocks >= 1;
+    bool ready = nblocks >= 1 && csrs[0]->tile_refused == 0;
     for (int b = 0; ready && b < nblocks; ++b)
-      ready = csrs[b]->ncells == mesh->ncells && csrs[b]->dim == mesh->dim && pattern_ready(csrs[b], drop_exact_zeros);
-    if (ready && !mesh->vertex_tile.p && !mesh->cluster_tried && csrs[0]->tile_refused == 0)
-      tile_cluster_generic(ctx, const_cast<fq_mesh*>(mesh));  // uploaded meshes: clustered on first reuse, never in one-shot assembly
+      ready = csrs[b]->has_plan && csrs[b]->ncells == mesh->ncells && csrs[b]->dim == mesh->dim;
+    if (ready && !mesh->vertex_tile.p && !mesh->cluster_tried)
+      tile_cluster_generic(ctx, const_cast<fq_mesh*>(mesh));  // uploaded meshes: clustered once, on first use
     ready = ready && mesh->vertex_tile.p != nullptr;
-    if (ready) {
-      std::shared_ptr<TilePlan> plan = csrs[0]->tile_plan;
-      if (plan && !tile_plan_matches(*plan, mesh, csrs, nblocks, drop_exact_zeros)) plan.reset();
-      if (!plan && csrs[0]->tile_refused == 0) {
-        plan = tile_plan_build(ctx, mesh, csrs, nblocks, drop_exact_zeros);
-        if (!plan) csrs[0]->tile_refused = 1;  // does not apply to this block set / mesh: stay on the slab path
-        if (plan)
-          for (int b = 0; b < nblocks; ++b) csrs[b]->slab.release();  // the slab is only needed by the slab path
-      }
-      for (int b = 0; b < nblocks; ++b) csrs[b]->tile_plan = plan;
-      if (plan) {
-        for (int b = 0; b < nblocks; ++b) csrs[b]->inv_diag.release();
-        if (tile_assemble(ctx, mesh, *plan)) {
-          const int ne = int(binom(mesh->dim + 1, 2));
-          for (int b = 0; b < nblocks; ++b)
-            csrs[b]->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csrs[b]->ncontrib +
-                                              8 * csrs[b]->nnz);
-          return;
-        }
-        // the zero / non-zero classification changed with the geometry: redo the slab pass
-        for (int b = 0; b < nblocks; ++b) csrs[b]->tile_plan.reset();
-      }
+    if (ready && tile_numeric(ctx, mesh, csrs, nblocks, drop_exact_zeros)) {
+      const int ne = int(binom(mesh->dim + 1, 2));
+      for (int b = 0; b < nblocks; ++b)
+        csrs[b]->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csrs[b]->ncontrib +
+                                          8 * csrs[b]->nnz);
+      return;
+    }
+  }
+  for (int b = 0; b < nblocks; ++b) {
+    FQ_REQUIRE(csrs[b]->has_plan, "matrix has no assembly plan (uploaded matrices cannot be re-assembled)");
+    FQ_REQUIRE(csrs[b]->ncells == mesh->ncells && csrs[b]->dim == mesh->dim, "mesh does not match the symbolic phase");
+    if (!csrs[b]->k2_done) {
+      // the tile builder may have left its structural pattern here: K2 recomputes the same one with the gather lists
+      csrs[b]->pattern_valid = false;
+      csrs[b]->compact_valid = false;
+      ensure_k2(ctx, mesh, csrs[b]);
     }
   }
   std::vector<BlockSpec> blocks;
@@ -438,6 +548,11 @@ void assemble_numeric_custom(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool
   csr->inv_diag.release();
   csr->tile_plan.reset();  // the tile-fused kernel evaluates the closed-form masses: not this form
   csr->tile_refused = 1;
+  if (!csr->k2_done) {
+    csr->pattern_valid = false;
+    csr->compact_valid = false;
+    ensure_k2(ctx, mesh, csr);
+  }
   const size_t T = size_t(csr->el_rows) * size_t(csr->el_cols);
   const size_t want = mesh->ncells * T;
   if (csr->slab.n != (want ? want : 1)) csr->slab.alloc(want ? want : 1);

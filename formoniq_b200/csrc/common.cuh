@@ -220,4 +220,8 @@ struct fq_csr {
   std::shared_ptr<fq::TilePlan> tile_plan;
   int tile_refused = 0;
   int slab_passes = 0;  // numeric passes done through the slab path since the symbolic phase
+  // K2 (the global-sort symbolic phase feeding the slab path) runs lazily: the tile plan builder produces the
+  // structural pattern itself, so a matrix that only ever goes through the fused kernel never pays for K2
+  bool k2_done = false;
+  double plan_build_ms = 0.0;  // device time of the last tile plan build (symbolic + plan), 0 when none
 };

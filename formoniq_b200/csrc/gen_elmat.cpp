@@ -7,6 +7,8 @@
 #include "tape.hpp"
 
 #include <cinttypes>
+#include <cstdlib>
+#include <functional>
 #include <sstream>
 
 using namespace fq;
@@ -346,27 +348,77 @@ static bool emit_set(const std::string& name, int n, const std::vector<BlockSpec
   std::vector<std::ostringstream> sg(3);
   for (int i = 0; i < t.ninputs; ++i) sa << "  const double r" << i << " = s[" << i << "];\n";
   // stage A keeps only what some group (or mid) needs
-  for (size_t i = 0; i < ops.size(); ++i) {
+  for (size_t i = 0; i < ops.size() && int(i) <= cut; ++i) {
     const TapeOp& o = ops[i];
-    if (is_store(o)) {
-      auto it = put_at.find(int(i));
-      if (it == put_at.end()) continue;
-      const SetPut& p = *it->second;
-      const int g = L.blocks[size_t(p.block)].group;
-      std::string v;
-      if (o.op == OP_STORE) v = reg(o.a);
-      else if (o.op == OP_STOREN) v = "-" + reg(o.a);
-      else v = cst(tb.consts[o.b]);
-      sg[size_t(g)] << "  sink.template put<" << p.block << ", " << p.row << ", " << p.slot << ">(" << v << ");\n";
-      continue;
+    if (is_store(o)) continue;
+    if (need.count(o.d) && need[o.d]) sa << line(o);
+  }
+  // Stage groups: the stores are emitted column by column (all blocks of the group for column 0, then column 1, ...),
+  // each preceded by the not yet emitted part of its dependency cone (depth first, operands in tape order).  Same
+  // operations on the same operands as the tape, scheduled so that few values are live at a time: a sandwich column
+  // (dif_test = d * M_k) only needs the same column of the mass, so the 36 entries of M_k never have to be live at once.
+  std::map<uint32_t, size_t> op_of;  // SSA value -> op index
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (!is_store(ops[i])) op_of[ops[i].d] = i;
+  for (int g = 0; g < L.ngroups && g < 3; ++g) {
+    struct PutRef {
+      int col, block, row;
+      const SetPut* p;
+    };
+    std::vector<PutRef> order;
+    for (const SetPut& p : L.puts) {
+      const SetBlock& B = L.blocks[size_t(p.block)];
+      if (B.group != g) continue;
+      int col = 0;
+      for (int j = 0; j < B.cols; ++j)
+        if (B.cs[size_t(p.row * B.cols + j)] == p.slot) {
+          col = j;
+          break;
+        }
+      order.push_back(PutRef{col, p.block, p.row, &p});
     }
-    const int m = need.count(o.d) ? need[o.d] : 0;
-    if (!m) continue;
-    if (int(i) <= cut) {
-      sa << line(o);
-    } else {
-      for (int g = 0; g < 3; ++g)
-        if (m >> g & 1) sg[size_t(g)] << line(o);
+    std::stable_sort(order.begin(), order.end(), [](const PutRef& a, const PutRef& b) {
+      if (a.col != b.col) return a.col < b.col;
+      if (a.block != b.block) return a.block < b.block;
+      return a.row < b.row;
+    });
+    std::map<uint32_t, bool> done;
+    for (const auto& kv : mid_of) done[kv.first] = true;
+    // not yet emitted part of the dependency cone of v, as op indices
+    std::function<void(uint32_t, std::vector<size_t>&)> collect = [&](uint32_t v, std::vector<size_t>& out) {
+      if (done.count(v)) return;
+      const size_t at = op_of.at(v);
+      if (int(at) <= cut) throw std::runtime_error("set: a stage-A value is missing from mid");
+      done[v] = true;
+      out.push_back(at);
+      uint32_t u[2];
+      const int nu = uses(ops[at], u);
+      for (int q = 0; q < nu; ++q) collect(u[q], out);
+    };
+    const char* gen_order = std::getenv("FQ_GEN_ORDER");
+    const bool tape_order = gen_order && gen_order[0] == 't';
+    if (tape_order)  // development knob: the whole group as one batch, stores in tape order (row-major per block)
+      std::stable_sort(order.begin(), order.end(), [](const PutRef& a, const PutRef& b) { return a.p->op < b.p->op; });
+    for (size_t p0 = 0; p0 < order.size();) {
+      size_t p1 = p0;
+      while (p1 < order.size() && (tape_order || order[p1].col == order[p0].col)) ++p1;
+      // one column of every block of the group: its operations in TAPE order (independent chains next to each other,
+      // which is what gives the FP64 pipe its instruction-level parallelism), then its stores
+      std::vector<size_t> batch;
+      for (size_t p = p0; p < p1; ++p) {
+        const TapeOp& o = ops[size_t(order[p].p->op)];
+        if (o.op == OP_STORE || o.op == OP_STOREN) collect(o.a, batch);
+      }
+      std::sort(batch.begin(), batch.end());
+      for (size_t at : batch) sg[size_t(g)] << line(ops[at]);
+      for (size_t p = p0; p < p1; ++p) {
+        const PutRef& pr = order[p];
+        const TapeOp& o = ops[size_t(pr.p->op)];
+        const std::string v = (o.op == OP_STORE || o.op == OP_STOREN) ? ((o.op == OP_STOREN ? "-" : "") + reg(o.a)) : cst(tb.consts[o.b]);
+      sg[size_t(g)] << "  sink.template put<" << pr.p->block << ", " << pr.p->row << ", " << pr.p->slot << ", "
+                    << L.blocks[size_t(pr.p->block)].d << ">(" << v << ");\n";
+      }
+      p0 = p1;
     }
   }
   std::printf("// set %s: n=%d inputs=%d groups=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", name.c_str(), n, t.ninputs, L.ngroups,

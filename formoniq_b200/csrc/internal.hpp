@@ -32,10 +32,17 @@ void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csr
 // ---- tile.cu (tile-fused numeric assembly)
 void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held);
 void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh);  // lazy: run when a tile plan is first built
-std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop);
-bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop);
-bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan);
+// builds the plan AND the structural patterns (s_row_ptr / s_col_idx / s_nnz / ncontrib) of the blocks
+std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks);
+bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks);
+bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan, double* const* values, uint8_t* const* keep);
+void tile_retarget(fq_ctx* ctx, TilePlan& plan);
+bool& tile_plan_compact(TilePlan& plan);
+bool& tile_plan_drop(TilePlan& plan);
+double tile_plan_build_ms(const TilePlan& plan);
 int64_t tile_plan_bytes(const TilePlan& plan);
+int64_t tile_plan_stream_bytes(const TilePlan& plan);
+int64_t tile_plan_cv_bytes(const TilePlan& plan);
 
 // ---- spmv.cu
 void spmv_prepare(fq_ctx* ctx, fq_csr* a);

@@ -1,115 +1,71 @@
-// tile.cu — tile-fused numeric assembly: K1 (element masses) and K3 (segmented
-// reduction into CSR) in ONE persistent kernel, with the element data of a tile
-// living only in shared memory.  The element slab of the two-kernel path
-// (8*T bytes per cell written and read back through HBM) disappears.
+// tile.cu — tile-fused numeric assembly: K1 (element matrices) and K3 (segmented reduction into CSR) in ONE
+// persistent kernel, with the element data of a tile living only in shared memory, plus the device builder of its
+// plan (which is at the same time the symbolic phase: it produces the structural CSR pattern of every block).
 //
 // Decomposition = the multi-GPU one, repeated at CTA level: *owner computes*.
-//   * vertices are clustered into tiles (closed-form bricks on Kuhn grids,
-//     breadth-first clusters on generic meshes);
-//   * a tile owns the rows (simplices) whose top vertex it contains, hence
-//     whole CSR rows, hence every structural non-zero of those rows;
-//   * it evaluates the element masses of ALL cells touching its vertices
-//     (owned + halo cells, recomputed by the neighbouring tiles — FP64 work is
-//     cheap here, HBM traffic is not) into shared memory, then reduces each of
-//     its non-zeros over the contributing (cell, slot) pairs in ascending cell
-//     order — the same order as the slab path, so values are bit-identical.
+//   * vertices are clustered into tiles (closed-form bricks on Kuhn grids, breadth-first clusters on generic meshes);
+//   * a tile owns the rows (simplices) whose top vertex it contains, hence whole CSR rows, hence every structural
+//     non-zero of those rows;
+//   * it visits every cell touching one of its vertices ("cell visit"; halo cells are evaluated by several tiles —
+//     FP64 work is cheap here, HBM traffic is not) and stores, for every OWNED local row of the cell, the distinct
+//     values of that row of every block's element matrix (sandwiches d*M*D included) into a shared slab;
+//   * every owned non-zero is then one lane of a warp-sized record that adds its contributions — plain 16-bit slab
+//     indices — left to right in ascending cell order and stores the sum once.
 //
-// Kernels (same plan, same streams): tile_assemble_alt_kernel (default) runs 8 producer warps (K1) and 16 consumer warps
-// (K3) over ONE slab used in two alternating halves, so the FP64 work hides completely behind the gather without
-// shrinking the tiles; tile_assemble_kernel (FQ_TILE_KERNEL=s) is the phase-serialised predecessor (K1, barrier, gather,
-// barrier on 16 warps); tile_assemble_ws_kernel (=w) the two-slab producer/consumer experiment.
+// tile_fused_kernel: 8 producer warps evaluate the generated staged tapes (elmat_gen.cuh: stage A = geometry, then one
+// stage group per mass grade), 16 consumer warps stream the tile's records through private TMA double buffers
+// (cp.async.bulk + mbarrier).  Every stage group has its own region of the slab and a full/empty mbarrier pair, so
+// the producers refill the region of group g for tile i+1 as soon as every consumer warp is past the group-g records
+// of tile i: the FP64 pipe works in the shadow of the gather without a second slab.
 //
-// Shared memory holds only the DISTINCT values a cell contributes: for
-// HodgeBlocks the masses M_{k-1}, M_k, M_{k+1} (54 doubles for 3-D k = 1 instead of 112
-// element entries; FQ_TILE_CORE=h stores dif_both(k+1) instead of M_{k+1}: 74).  dif_test = d*M_k and dif_both
-// (operators.rs:201-211) are evaluated by the gather through per-slot "recipes" —
-// signed sums of mass entries in the reference's k-ascending gemm order, exact
-// because the incidence entries are 0/+-1 (tape.hpp evaluates the same products
-// symbolically).
+// tile_build_kernel: one CTA per tile builds the plan from the mesh's face tables alone (no global sort of the
+// element entries): local face numbering, owned-row slots, block-wide radix sort of the tile's (row, col) keys,
+// run/record layout — first a counting pass (row lengths, chunks per tile), then the emitting pass.  The same bytes
+// as tile_plan.hpp's host reference builder (FQ_TILE_BUILD=host), which the CPU tests interpret against the oracle.
 //
-// The cell-slot -> nnz map is laid out per tile as ONE contiguous byte stream
-// of 2 KB chunks holding warp-sized records {header; dest[64]; entry[L][64]}
-// (non-zeros grouped by their number of contributions L, so a warp runs L
-// uniform iterations on two independent chains per lane, lanes read
-// consecutive 2-byte entries, no per-nnz offsets are stored).  Chunk c of a
-// tile belongs to warp c mod NW: every warp streams its own chunks through a
-// private double buffer filled by TMA bulk copies (cp.async.bulk + mbarrier),
-// prefetching across tile boundaries — no warp ever waits on another warp or
-// on a dependent global load during the gather, and HBM sees long sequential
-// reads.
-//
-// Reference path replaced: formoniq/src/galerkin.rs:138-188 (assemble_matrix)
-// + hodge.rs:62-72 (the four HodgeBlocks), numeric phase.
+// Reference path replaced: formoniq/src/galerkin.rs:138-188 (assemble_matrix) + hodge.rs:62-72 (HodgeBlocks).
 #include <cub/cub.cuh>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <type_traits>
 
 #include "elmat_gen.cuh"
 #include "internal.hpp"
 #include "kuhn.hpp"
+#include "tile_plan.hpp"
 
 namespace fq {
+using namespace tp;
 
-constexpr int kTileMaxBlocks = 4;
-// dest codes of the stream: 0 = padding lane, 1 = dropped non-zero (must stay all-zero, galerkin.rs:173),
-// d >= 2 = position d - 2 of csr->values
-constexpr uint32_t kPadDest = 0u;
-constexpr uint32_t kNoDest = 1u;
-#ifndef FQ_TILE_CHUNK_BYTES
-#define FQ_TILE_CHUNK_BYTES 1536
-#endif
-constexpr int kChunkBytes = FQ_TILE_CHUNK_BYTES;  // TMA granule of the tile stream; records never straddle a chunk
-constexpr int kChunkHdr = 16;       // u32 nrec + padding
-constexpr int kRecHdr = 16;         // u32 (L | block << 8 | lanes << 16) + padding
-// a record is 16 + lanes * (4 + 2 L) bytes and must fit a chunk after its 16-byte header
-constexpr int kMaxLen64 = ((kChunkBytes - 32) / 64 - 4) / 2;   // 2 KB chunks: 64 lanes up to L = 13
-constexpr int kMaxLen32 = ((kChunkBytes - 32) / 32 - 4) / 2;   //              32 lanes up to L = 29
-constexpr int kMaxLen = ((kChunkBytes - 32) / 16 - 4) / 2;     //              16 lanes up to L = 61
-constexpr int kSlotsPerWarp = 2;    // private double buffer of every warp
+constexpr int kMaxConsumerWarps = 16;
+constexpr int kSlotsPerWarp = 2;  // private TMA double buffer of every consumer warp
+constexpr int kMaxGroups = 3;
+constexpr size_t kSmemCta = size_t(227) * 1024 - 256;
+// the slab capacity the tiles are sized for assumes the largest ring (16 consumer warps)
+constexpr size_t kRingBytesMax = size_t(kMaxConsumerWarps) * kSlotsPerWarp * kChunkBytes;
+constexpr size_t kBarBytes = (size_t(kMaxConsumerWarps) * kSlotsPerWarp + 2 * kMaxGroups + 2) * 8;
+constexpr uint32_t kSlabCapacity = uint32_t((kSmemCta - kRingBytesMax - kBarBytes - 256) / 8);  // doubles
 
-__host__ __device__ inline uint32_t rec_lanes(uint32_t L) { return L <= uint32_t(kMaxLen64) ? 64u : (L <= uint32_t(kMaxLen32) ? 32u : 16u); }
-__host__ __device__ inline uint32_t rec_bytes(uint32_t L) { return uint32_t(kRecHdr) + rec_lanes(L) * (4u + 2u * L); }
-
-struct TileBlockDev {
-  double* values;
-  int no, ni;      // recipe shape: outer x inner signed terms per slot (1 x 1: entries are pre-translated)
-  int recipe_off;  // offset (u16 units) of this block's recipes
-  int slot_bits;
-};
-
-struct TileParams {
-  const uint32_t* tile_cell_ptr;    // [ntiles+1]
-  const uint32_t* tile_cell_edges;  // [tile cell slots][NE] edge ids, pre-gathered
+struct FusedParams {
+  const TileHdr* tiles;
+  uint32_t ntiles;
+  const uint32_t* cv_rec;
+  int cv_words;
   const double* lengths;
   uint32_t edge_lo;
-  uint32_t ntiles;
-  const uint32_t* tile_chunk_ptr;   // [ntiles+1] chunk index of the tile's stream
-  const unsigned char* stream;      // chunks of kChunkBytes
-  int cstride;                      // cells capacity of the shared slab
-  int nblocks;
-  uint32_t ring_off, rec_off, mbar_off;  // byte offsets in dynamic shared memory
-  uint32_t slab_bytes;                   // warp-specialised kernel: size of one of its two slabs
-  const uint8_t* recipes;           // u16 codes: sign << 15 | distinct * cstride
-  int recipe_bytes;
-  int debug;                        // development knobs (FQ_TILE_DEBUG): 1 skip K1, 2 skip records, 4 skip stores
-  int check_classification;         // 1 when the plan carries the reference's value-dependent pattern
-  uint32_t yblock_mask;             // alternating kernel: blocks whose records read second-half slab values only
-  uint32_t chunk_rotation;          // alternating kernel: per-tile rotation of the chunk -> warp deal (0: none)
-  int* changed;                     // raised when the zero/non-zero classification differs from the plan's
-  unsigned int* ticket;             // dynamic tile scheduler
-  unsigned long long* stats;        // debug & 8: per-phase warp cycles [k1, bar_k1, chunk_wait, records, bar_top, other]
-  TileBlockDev blk[kTileMaxBlocks];
-};
-
-struct TileSink {
-  double* __restrict__ slab;  // + local cell
-  int cstride;
-  template <int B, int E>
-  __device__ __forceinline__ void put(double v) const {
-    slab[E * cstride] = v;
-  }
+  const unsigned char* stream;
+  double* values[kMaxBlocks];
+  uint8_t* keep[kMaxBlocks];      // structural mode: "some contribution != 0.0" flags (galerkin.rs:173); may be null
+  int* changed;
+  uint32_t chunk_rotation;
+  uint32_t ring_off, mbar_off;
+  uint32_t group_pack;            // stage group of block b in byte b
+  uint32_t class_pack;            // cv record word (after the edge ids) of block b's row class in byte b
+  int debug;                      // FQ_TILE_DEBUG: 1 skip K1, 2 skip records
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -118,6 +74,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -139,560 +98,224 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                : "memory");
 }
 
-// x with the sign bit flipped when bit 15 of `code` is set (exact negation)
-__device__ __forceinline__ double signed_load(const double* __restrict__ p, uint32_t code) {
-  const double x = p[code & 0x7FFFu];
-  return __hiloint2double(__double2hiint(x) ^ int((code & 0x8000u) << 16), __double2loint(x));
+// Producer side: one cell visit's stores.  meta[b] = owned-row mask | first row slot << 8 of block b's row class.
+struct FusedSink {
+  double* __restrict__ slab;
+  uint32_t sb[kMaxBlocks];
+  uint32_t meta[kMaxBlocks];
+  template <int B, int R, int CS, int D>
+  __device__ __forceinline__ void put(double v) const {
+    const uint32_t m = meta[B];
+    if ((m >> R) & 1u) slab[sb[B] + ((m >> 8) + uint32_t(__popc(m & ((1u << R) - 1u)))) * uint32_t(D) + uint32_t(CS)] = v;
+  }
+};
+
+// non-zero bits of a double (x != 0.0 for finite and non-finite values alike; -0.0 counts as zero)
+__device__ __forceinline__ uint32_t nz_bits(double x) {
+  return (uint32_t(__double2hiint(x)) << 1) | uint32_t(__double2loint(x));
 }
 
-// Value of one contribution: a recipe of NO x NI signed stored entries
-//   v = (((x00 + x01) + ..) + ((x10 + x11) + ..)) + ..
-// (the k-ascending gemm order of operators.rs:201-211 with the +-1 incidence entries folded in).
-template <int NO, int NI>
-__device__ __forceinline__ double recipe_value(uint32_t e, const double* __restrict__ slab, const uint16_t* __restrict__ brec,
-                                               uint32_t sb, uint32_t slot_mask) {
-  constexpr int NT4 = (NO * NI + 3) / 4 * 4;  // codes per slot, padded to 8-byte groups
-  const double* __restrict__ sc = slab + (e >> sb);
-  const uint2* __restrict__ rr = reinterpret_cast<const uint2*>(brec + (e & slot_mask) * NT4);
-  uint32_t code[NT4];
-#pragma unroll
-  for (int w = 0; w < NT4 / 4; ++w) {
-    const uint2 c = rr[w];
-    code[4 * w + 0] = c.x & 0xFFFFu;
-    code[4 * w + 1] = c.x >> 16;
-    code[4 * w + 2] = c.y & 0xFFFFu;
-    code[4 * w + 3] = c.y >> 16;
-  }
-  double v = 0.0;
-#pragma unroll
-  for (int o = 0; o < NO; ++o) {
-    double inner = signed_load(sc, code[o * NI]);
-#pragma unroll
-    for (int q = 1; q < NI; ++q) inner = __dadd_rn(inner, signed_load(sc, code[o * NI + q]));
-    v = (o == 0) ? inner : __dadd_rn(v, inner);
-  }
-  return v;
-}
-// The two non-zeros of a lane (columns lane and lane + 32 of a wide record; a narrow record runs the
-// second chain on the first column and discards it): left-to-right sums over L contributions.
-template <int NO, int NI>
-__device__ __forceinline__ void gather_record(const uint16_t* __restrict__ ent0, const uint16_t* __restrict__ ent1,
-                                              uint32_t stride, uint32_t L, const double* __restrict__ slab,
-                                              const uint16_t* __restrict__ brec, uint32_t sb, uint32_t slot_mask, double& acc0,
-                                              double& acc1, bool& any0, bool& any1) {
-#pragma unroll 1
-  for (uint32_t j = 0; j < L; ++j) {
-    const uint32_t e0 = ent0[j * stride], e1 = ent1[j * stride];
-    const double v0 = recipe_value<NO, NI>(e0, slab, brec, sb, slot_mask);
-    const double v1 = recipe_value<NO, NI>(e1, slab, brec, sb, slot_mask);
-    any0 = any0 || (v0 != 0.0);
-    any1 = any1 || (v1 != 0.0);
-    acc0 = __dadd_rn(acc0, v0);
-    acc1 = __dadd_rn(acc1, v1);
+// What a record lane does with its sum: store it (and the classification) as the stream's destination says.
+template <bool COMPACT>
+__device__ __forceinline__ void finish_lane(uint32_t dest, double acc, uint32_t any, double* __restrict__ vals,
+                                            uint8_t* __restrict__ keep, int* __restrict__ changed) {
+  if (COMPACT) {
+    // dest = 0: padding lane (it read slab[0]); dest = 1: a dropped non-zero, every contribution must still be an exact
+    // zero; dest >= 2: a kept one, some contribution must be non-zero (galerkin.rs:173)
+    if (dest != kPadDest && ((dest != kNoDest) != (any != 0u))) *changed = 1;
+    if (dest > kNoDest) vals[dest - 2u] = acc;
+  } else if (dest > kNoDest) {
+    vals[dest - 2u] = acc;
+    if (keep) keep[dest - 2u] = any != 0u ? 1 : 0;
   }
 }
-// blocks stored directly: the stream entries are pre-translated to sign | slab offset
-__device__ __forceinline__ void gather_record_direct(const uint16_t* __restrict__ ent0, const uint16_t* __restrict__ ent1,
-                                                     uint32_t stride, uint32_t L, const double* __restrict__ slab,
-                                                     double& acc0, double& acc1, bool& any0, bool& any1) {
-#pragma unroll 1
+
+// A 64-lane record with a compile-time number of contributions: the two non-zeros of a lane (columns lane and
+// lane + 32), every load at an immediate offset from two lane pointers and issued before the first add, then the
+// left-to-right sums (the first contribution starts the sum, as in the reference's duplicate summation).
+template <int L, bool COMPACT>
+__device__ __forceinline__ void record_wide(const unsigned char* __restrict__ rp, int lane, const double* __restrict__ slab,
+                                            double* __restrict__ vals, uint8_t* __restrict__ keep, int* __restrict__ changed) {
+  const uint32_t* __restrict__ destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr) + lane;
+  const uint16_t* __restrict__ ent = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * 64) + lane;
+  const uint32_t dest0 = destp[0], dest1 = destp[32];
+  uint32_t c0[L], c1[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    c0[j] = ent[j * 64];
+    c1[j] = ent[j * 64 + 32];
+  }
+  double x0[L], x1[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    x0[j] = slab[c0[j]];
+    x1[j] = slab[c1[j]];
+  }
+  double acc0 = x0[0], acc1 = x1[0];
+  uint32_t any0 = nz_bits(x0[0]), any1 = nz_bits(x1[0]);
+#pragma unroll
+  for (int j = 1; j < L; ++j) {
+    any0 |= nz_bits(x0[j]);
+    any1 |= nz_bits(x1[j]);
+    acc0 = __dadd_rn(acc0, x0[j]);
+    acc1 = __dadd_rn(acc1, x1[j]);
+  }
+  finish_lane<COMPACT>(dest0, acc0, any0, vals, keep, changed);
+  finish_lane<COMPACT>(dest1, acc1, any1, vals, keep, changed);
+}
+
+// Any record (narrow ones for non-zeros with many contributions: 32 or 16 lanes; lanes beyond the record shadow the
+// first ones and never store): two chains per lane where the record is wide enough.
+template <bool COMPACT>
+__device__ __forceinline__ void record_any(const unsigned char* __restrict__ rp, uint32_t L, uint32_t stride, int lane,
+                                           const double* __restrict__ slab, double* __restrict__ vals, uint8_t* __restrict__ keep,
+                                           int* __restrict__ changed) {
+  const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
+  const uint32_t l0 = uint32_t(lane) & (stride - 1u);
+  const uint32_t dest0 = uint32_t(lane) < stride ? destp[l0] : kPadDest;
+  const uint32_t dest1 = stride == 64u ? destp[lane + 32] : kPadDest;
+  const uint16_t* __restrict__ e0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
+  const uint16_t* __restrict__ e1 = e0 + (stride == 64u ? 32 : 0);
+  double acc0 = 0.0, acc1 = 0.0;
+  uint32_t any0 = 0, any1 = 0;
+#pragma unroll 2
   for (uint32_t j = 0; j < L; ++j) {
-    const double x0 = signed_load(slab, ent0[j * stride]);
-    const double x1 = signed_load(slab, ent1[j * stride]);
-    any0 = any0 || (x0 != 0.0);
-    any1 = any1 || (x1 != 0.0);
+    const double x0 = slab[e0[j * stride]], x1 = slab[e1[j * stride]];
+    any0 |= nz_bits(x0);
+    any1 |= nz_bits(x1);
     acc0 = __dadd_rn(acc0, x0);
     acc1 = __dadd_rn(acc1, x1);
   }
+  finish_lane<COMPACT>(dest0, acc0, any0, vals, keep, changed);
+  finish_lane<COMPACT>(dest1, acc1, any1, vals, keep, changed);
 }
 
-// Alternating kernel: where a consumer warp stands in the tile (first-half records, then second-half records)
-struct AltState {
-  uint64_t* a_empty;
-  uint64_t* b_full;
-  uint32_t parity;
-  bool in_y;
-};
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar);
-
-// All records of one chunk of the tile stream, processed by one warp.
-template <bool ALT = false>
-__device__ __forceinline__ void gather_chunk(const unsigned char* __restrict__ chunk, const TileParams& P,
-                                             const double* __restrict__ slab, const uint16_t* __restrict__ rec, int lane,
-                                             AltState* alt = nullptr) {
-  const uint32_t nrec = (P.debug & 2) ? 0u : *reinterpret_cast<const uint32_t*>(chunk);
-  const unsigned char* rp = chunk + kChunkHdr;
-  for (uint32_t r = 0; r < nrec; ++r) {
-    const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
-    const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
-    const uint32_t* destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr);
-    const uint32_t l0 = lane & (stride - 1u);  // lanes beyond a 16-wide record shadow the first ones and never store
-    const uint32_t dest0 = uint32_t(lane) < stride ? destp[l0] : kPadDest;
-    const uint32_t dest1 = stride == 64u ? destp[lane + 32] : kPadDest;
-    const uint16_t* __restrict__ ent0 = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * stride) + l0;
-    const uint16_t* __restrict__ ent1 = ent0 + (stride == 64u ? 32 : 0);
-    rp += kRecHdr + stride * (4u + 2u * L);
-    if (ALT) {
-      // first record of this warp that reads the second half of the slab: the warp is done with the first half
-      // (released to the producers, who refill it for the next tile) and needs the second half of THIS tile
-      if (!alt->in_y && ((P.yblock_mask >> b) & 1u)) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(alt->a_empty);
-        mbar_wait(alt->b_full, alt->parity);
-        alt->in_y = true;
-      }
-    }
-    const TileBlockDev& B = P.blk[b];
-    const uint16_t* __restrict__ brec = rec + B.recipe_off;
-    const uint32_t sb = B.slot_bits, slot_mask = (1u << sb) - 1u;
-    double acc0 = 0.0, acc1 = 0.0;
-    bool any0 = false, any1 = false;
-    switch (B.no * 8 + B.ni) {
-      case 0: break;  // zero space: every contribution is an exact zero
-      case 1 * 8 + 1: gather_record_direct(ent0, ent1, stride, L, slab, acc0, acc1, any0, any1); break;
-      case 1 * 8 + 2: gather_record<1, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-      case 1 * 8 + 3: gather_record<1, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-      case 1 * 8 + 4: gather_record<1, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-      case 2 * 8 + 2: gather_record<2, 2>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-      case 3 * 8 + 3: gather_record<3, 3>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-      default: gather_record<4, 4>(ent0, ent1, stride, L, slab, brec, sb, slot_mask, acc0, acc1, any0, any1); break;
-    }
-    // padding lanes carry zero entries (they read slab[0]) and never store
-    if (P.check_classification && ((dest0 != kPadDest && (dest0 != kNoDest) != any0) ||
-                                   (dest1 != kPadDest && (dest1 != kNoDest) != any1)))
-      *P.changed = 1;
-    if (P.debug & 4) continue;
-    if (dest0 > kNoDest) B.values[dest0 - 2u] = acc0;
-    if (dest1 > kNoDest) B.values[dest1 - 2u] = acc1;
-  }
-}
-
-template <class Fn, int NE, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) tile_assemble_kernel(Fn fn, const __grid_constant__ TileParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* slab = reinterpret_cast<double*>(smem_raw);
-  constexpr int NW = NT / 32;
-  constexpr int NEE = NE > 0 ? NE : 1;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned char* myring = smem_raw + P.ring_off + size_t(warp) * kSlotsPerWarp * kChunkBytes;  // this warp's double buffer
-  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
-  uint64_t* mybar = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off) + warp * kSlotsPerWarp;
-  __shared__ uint32_t s_hdr[3][8];
-  auto fetch_header = [&](uint32_t* h) {  // thread 0: next tile from the dynamic scheduler
-    const uint32_t t = atomicAdd(P.ticket, 1u);
-    h[0] = t;
-    if (t < P.ntiles) {
-      h[1] = __ldg(P.tile_cell_ptr + t);
-      h[2] = __ldg(P.tile_cell_ptr + t + 1);
-      h[3] = __ldg(P.tile_chunk_ptr + t);
-      h[4] = __ldg(P.tile_chunk_ptr + t + 1);
-    }
-  };
-  if (lane == 0) {
-    for (int s = 0; s < kSlotsPerWarp; ++s) mbar_init(&mybar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (tid == 0) {
-    fetch_header(s_hdr[0]);
-    fetch_header(s_hdr[1]);
-  }
-  for (int i = tid; i < P.recipe_bytes / 2; i += NT) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
-  // this warp's chunk stream: chunks issued / consumed so far (slot = n & 1, parity = (n >> 1) & 1) and the
-  // issue cursor (tile iteration it is on, next chunk, end of that tile's chunks); runs ahead across tiles
-  uint32_t n_issued = 0, n_consumed = 0;
-  uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
-  uint32_t eid_next[NEE];
-  bool have_eids = false;
-  const bool prof = (P.debug & 8) && lane == 0;
-  long long tk[6] = {0, 0, 0, 0, 0, 0};
-  long long t_last = clock64();
-  auto lap = [&](int which) {
-    if (prof) {
-      const long long now = clock64();
-      tk[which] += now - t_last;
-      t_last = now;
-    }
-  };
-  for (uint32_t it = 0;; ++it) {
-    lap(5);
-    __syncthreads();  // previous tile fully consumed, this tile's header visible
-    lap(4);
-    const uint32_t* hdr = s_hdr[it % 3];
-    const uint32_t t = hdr[0];
-    if (t >= P.ntiles) break;
-    const uint32_t cbase = hdr[1], nc = hdr[2] - hdr[1];
-    const uint32_t c0 = hdr[3], c1 = hdr[4];
-    const uint32_t* hnext = s_hdr[(it + 1) % 3];
-    auto issue_more = [&]() {  // keep this warp's double buffer full, crossing into the next tile when this one is done
-      while (n_issued - n_consumed < uint32_t(kSlotsPerWarp)) {
-        if (cur_chunk >= cur_end) {
-          if (cur_it == it && hnext[0] < P.ntiles) {
-            cur_it = it + 1;
-            cur_chunk = hnext[3] + warp;
-            cur_end = hnext[4];
-            if (cur_chunk >= cur_end) break;
-          } else {
-            break;
-          }
-        }
-        if (lane == 0) {
-          uint64_t* bar = &mybar[n_issued & 1u];
-          mbar_expect_tx(bar, kChunkBytes);
-          tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
-        }
-        cur_chunk += NW;
-        ++n_issued;
-      }
-    };
-    if (cur_it != it) {  // the cursor did not run ahead into this tile: start here
-      cur_it = it;
-      cur_chunk = c0 + warp;
-      cur_end = c1;
-    }
-    issue_more();  // lands while K1 runs
-    // ---- K1: element values of the tile's cells -> shared slab [distinct][cell]
-    if (c1 > c0 && !(P.debug & 1)) {
-      for (uint32_t c = tid; c < nc; c += NT) {
-        uint32_t eid[NEE];
-        if (have_eids && c == uint32_t(tid)) {  // fetched while this thread waited at the previous tile's barrier
-#pragma unroll
-          for (int e = 0; e < NE; ++e) eid[e] = eid_next[e];
-        } else {
-          const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
-#pragma unroll
-          for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
-        }
-        double s[NEE];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
-        TileSink sink{slab + c, P.cstride};
-        fn(s, sink);
-      }
-    }
-    lap(0);
-    __syncthreads();
-    lap(1);
-    if (tid == 0) fetch_header(s_hdr[(it + 2) % 3]);  // two tiles ahead: its latency hides behind this gather
-    // ---- K3: this warp's chunks; one record at a time, two owned structural non-zeros per lane
-    for (uint32_t c = c0 + warp; c < c1; c += NW) {
-      lap(5);
-      mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
-      lap(2);
-      const unsigned char* chunk = myring + (n_consumed & 1u) * kChunkBytes;
-      gather_chunk(chunk, P, slab, rec, lane);
-      __syncwarp();  // every lane is done reading the slot before it is refilled
-      lap(3);
-      ++n_consumed;
-      issue_more();
-    }
-    // edge ids of this thread's cell of the next tile: issued now, they arrive while the warp waits at the tile barrier
-    have_eids = !(P.debug & 16) && hnext[0] < P.ntiles;
-    if (have_eids && uint32_t(tid) < hnext[2] - hnext[1]) {
-      const uint32_t* ce = P.tile_cell_edges + size_t(hnext[1] + tid) * NE;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) eid_next[e] = __ldg(ce + e);
-    }
-  }
-  if (prof)
-    for (int i = 0; i < 6; ++i) atomicAdd(P.stats + i, (unsigned long long)tk[i]);
-}
-
-
-// ---- warp-specialised variant --------------------------------------------------------------------------------
-// 8 producer warps evaluate the element values of tile i+1 into one of two shared slabs while 16 consumer warps
-// reduce tile i out of the other: the FP64 pipe (K1) and the shared-memory crossbar (gather) work concurrently and
-// no warp idles at a CTA barrier.  setmaxnreg gives the producers the 128 registers the straight-line tape needs
-// and leaves 56 to each consumer (launch: 768 x 80; the consumers release 16*32*24 = the 8*32*48 the producers acquire).  Hand-offs are mbarriers:
-// Measured on B200: 6.7 ms vs 5.8 ms for the phase-serialised kernel (the two slabs halve the tile, K1 of a small tile
-// is latency-bound at ~3 us) - kept behind FQ_TILE_KERNEL=w.
-//   hdr_ready[b]  (1 arrival)   the tile of buffer b is known (consumers start prefetching its stream)
-//   slab_full[b]  (8 arrivals)  every producer warp has stored its cells
-//   slab_empty[b] (16 arrivals) every consumer warp is done with the tile
-constexpr int kWsProducerWarps = 8, kWsConsumerWarps = 16;
-constexpr int kWsThreads = 32 * (kWsProducerWarps + kWsConsumerWarps);
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-template <class Fn, int NE>
-__global__ void __launch_bounds__(kWsThreads, 1) tile_assemble_ws_kernel(Fn fn, const __grid_constant__ TileParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int NEE = NE > 0 ? NE : 1;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* slabs[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + P.slab_bytes)};
-  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
-  uint64_t* hdr_ready = bars;         // [2]
-  uint64_t* slab_full = bars + 2;     // [2]
-  uint64_t* slab_empty = bars + 4;    // [2]
-  uint64_t* tma_bar = bars + 6;       // [consumer warp][2]
-  __shared__ uint32_t s_hdr[2][8];
-  if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&hdr_ready[b], 1);
-      mbar_init(&slab_full[b], kWsProducerWarps);
-      mbar_init(&slab_empty[b], kWsConsumerWarps);
-    }
-    for (int i = 0; i < 2 * kWsConsumerWarps; ++i) mbar_init(&tma_bar[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < P.recipe_bytes / 2; i += kWsThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
-  __syncthreads();
-  if (warp < kWsProducerWarps) {
-    // ------------------------------------------------------------------ producers: K1
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-    uint32_t h[5] = {0xFFFFFFFFu, 0, 0, 0, 0};
-    auto fetch = [&]() {  // thread 0: next tile from the dynamic scheduler (latency hidden behind the current K1)
-      h[0] = atomicAdd(P.ticket, 1u);
-      if (h[0] < P.ntiles) {
-        h[1] = __ldg(P.tile_cell_ptr + h[0]);
-        h[2] = __ldg(P.tile_cell_ptr + h[0] + 1);
-        h[3] = __ldg(P.tile_chunk_ptr + h[0]);
-        h[4] = __ldg(P.tile_chunk_ptr + h[0] + 1);
-      }
-    };
-    if (tid == 0) fetch();
-    for (uint32_t it = 0;; ++it) {
-      const uint32_t b = it & 1u, u = it >> 1;
-      if (it >= 2) mbar_wait(&slab_empty[b], (u - 1u) & 1u);  // the consumers left the tile that used this buffer
-      if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) s_hdr[b][i] = h[i];
-        mbar_arrive(&hdr_ready[b]);
-      }
-      mbar_wait(&hdr_ready[b], u & 1u);
-      const uint32_t t = s_hdr[b][0];
-      if (t >= P.ntiles) break;
-      const uint32_t cbase = s_hdr[b][1], nc = s_hdr[b][2] - s_hdr[b][1];
-      const bool work = s_hdr[b][4] > s_hdr[b][3];
-      if (tid == 0) fetch();
-      if (work && !(P.debug & 1)) {
-        double* slab = slabs[b];
-        for (uint32_t c = tid; c < nc; c += 32 * kWsProducerWarps) {
-          const uint32_t* ce = P.tile_cell_edges + size_t(cbase + c) * NE;
-          uint32_t eid[NEE];
-#pragma unroll
-          for (int e = 0; e < NE; ++e) eid[e] = __ldg(ce + e);
-          double s[NEE];
-#pragma unroll
-          for (int e = 0; e < NE; ++e) s[e] = __ldg(P.lengths + (eid[e] - P.edge_lo));
-          TileSink sink{slab + c, P.cstride};
-          fn(s, sink);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slab_full[b]);
-    }
-  } else {
-    // ------------------------------------------------------------------ consumers: K3
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 16 warps x 24 released = the 12288 registers the producers acquire
-    const int cw = warp - kWsProducerWarps;
-    unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
-    uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
-    uint32_t n_issued = 0, n_consumed = 0;
-    uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
-    for (uint32_t it = 0;; ++it) {
-      const uint32_t b = it & 1u, u = it >> 1;
-      mbar_wait(&hdr_ready[b], u & 1u);
-      const uint32_t t = s_hdr[b][0];
-      if (t >= P.ntiles) break;
-      const uint32_t c0 = s_hdr[b][3], c1 = s_hdr[b][4];
-      auto issue_more = [&]() {  // keep this warp's double buffer full, crossing into the next tile once it is known
-        while (n_issued - n_consumed < uint32_t(kSlotsPerWarp)) {
-          if (cur_chunk >= cur_end) {
-            if (cur_it == it && mbar_test(&hdr_ready[b ^ 1u], ((it + 1u) >> 1) & 1u) && s_hdr[b ^ 1u][0] < P.ntiles) {
-              cur_it = it + 1;
-              cur_chunk = s_hdr[b ^ 1u][3] + cw;
-              cur_end = s_hdr[b ^ 1u][4];
-              if (cur_chunk >= cur_end) break;
-            } else {
-              break;
-            }
-          }
-          if (lane == 0) {
-            uint64_t* bar = &mybar[n_issued & 1u];
-            mbar_expect_tx(bar, kChunkBytes);
-            tma_load_1d(myring + (n_issued & 1u) * kChunkBytes, P.stream + size_t(cur_chunk) * kChunkBytes, kChunkBytes, bar);
-          }
-          cur_chunk += kWsConsumerWarps;
-          ++n_issued;
-        }
-      };
-      if (cur_it != it) {
-        cur_it = it;
-        cur_chunk = c0 + cw;
-        cur_end = c1;
-      }
-      issue_more();
-      mbar_wait(&slab_full[b], u & 1u);
-      const double* slab = slabs[b];
-      for (uint32_t c = c0 + cw; c < c1; c += kWsConsumerWarps) {
-        mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
-        gather_chunk(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane);
-        __syncwarp();
-        ++n_consumed;
-        issue_more();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slab_empty[b]);
-    }
-  }
-}
-
-// ---- alternating producer/consumer variant (the default) -----------------------------------------------------------
-// One full-size slab (the same tiles and record streams as the phase-serialised kernel), logically split in two halves:
-//   half 1 = the stored values of M_{k-1} and M_k      read by the records of M_{k-1}, M_k, dif_test(k)
-//   half 2 = the stored values of M_{k+1}              read by the records of dif_both(k+1)
-// The records of a tile are laid out block by block, so every consumer warp first works through first-half records
-// and then through second-half records.  While the consumers are in the second half of tile i the 8 producer warps
-// evaluate half 1 of tile i+1 (tape stage B1), and while they are in the first half of tile i+1 the producers
-// evaluate its half 2 (stage B2): the FP64 pipe works in the shadow of the shared-memory-bound gather with NO second
-// slab, i.e. without shrinking the tiles.  Tiles are dealt statically (tile = blockIdx.x + it * gridDim.x).
-//   a_full / b_full   (8 arrivals)   the producers stored half 1 / half 2 of tile it
-//   a_empty / b_empty (16 arrivals)  every consumer warp is past its first-half / second-half records of tile it
-// Stage A, B1, B2 execute exactly the operations of the unsplit tape: results are bit-identical.
-constexpr int kAltCellsPerThread = 2;  // a tile has at most 2 * 256 cells
-
-// NC consumer warps; PR / CR registers per producer / consumer thread after setmaxnreg (the launch allocates
-// LR = 65536 / threads rounded down to 8 per thread; what the consumers release must cover what the producers acquire)
-template <class Fn, int NE, int NC, int PR, int CR>
-__global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble_alt_kernel(Fn fn, const __grid_constant__ TileParams P) {
-  constexpr int kThreads = 32 * (kWsProducerWarps + NC);
+// NP producer / NC consumer warps; PR / CR registers per producer / consumer thread after setmaxnreg (the launch
+// allocates LR = 65536 / threads rounded down to 8 per thread; what the consumers release must cover what the producers
+// acquire).  COMPACT: the stream's destinations target the value-dependent pattern and the classification is verified.
+template <class Fn, int NE, int NP, int NC, int PR, int CR, bool COMPACT>
+__global__ void __launch_bounds__(32 * (NP + NC), 1) tile_fused_kernel(const __grid_constant__ FusedParams P) {
+  constexpr int kThreads = 32 * (NP + NC);
   constexpr int LR = 65536 / kThreads / 8 * 8;
-  static_assert(PR % 8 == 0 && CR % 8 == 0 && CR <= LR && PR >= LR && 32 * NC * (LR - CR) >= 256 * (PR - LR), "register split");
+  static_assert(PR % 8 == 0 && CR % 8 == 0 && CR <= LR && PR >= LR && 32 * NC * (LR - CR) >= 32 * NP * (PR - LR), "register split");
+  static_assert(NC <= kMaxConsumerWarps, "ring size");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NEE = NE > 0 ? NE : 1;
   constexpr int NM = Fn::kMid;
-  constexpr int NP = 32 * kWsProducerWarps;
+  constexpr int NG = Fn::kGroups;
+  constexpr int NPT = 32 * NP;                       // producer threads
+  constexpr int CPT = (kMaxCv + NPT - 1) / NPT;      // cell visits per producer thread
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* slab = reinterpret_cast<double*>(smem_raw);
-  uint16_t* rec = reinterpret_cast<uint16_t*>(smem_raw + P.rec_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.mbar_off);
-  uint64_t* tma_bar = bars;                                       // [consumer warp][2]
-  uint64_t* a_full = bars + NC * kSlotsPerWarp;     // the 8 spare barriers of the layout
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* b_full = a_full + 2;
-  uint64_t* b_empty = a_full + 3;
+  uint64_t* tma_bar = bars;                                    // [consumer warp][2]
+  uint64_t* g_full = bars + kMaxConsumerWarps * kSlotsPerWarp; // [group]: the producers stored the group's rows of the tile
+  uint64_t* g_empty = g_full + kMaxGroups;                     // [group]: every consumer warp is past the group's records
   if (tid == 0) {
-    mbar_init(a_full, kWsProducerWarps);
-    mbar_init(b_full, kWsProducerWarps);
-    mbar_init(a_empty, NC);
-    mbar_init(b_empty, NC);
+    for (int g = 0; g < kMaxGroups; ++g) {
+      mbar_init(&g_full[g], NP);
+      mbar_init(&g_empty[g], NC);
+    }
     for (int i = 0; i < kSlotsPerWarp * NC; ++i) mbar_init(&tma_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < P.recipe_bytes / 2; i += kThreads) rec[i] = reinterpret_cast<const uint16_t*>(P.recipes)[i];
+  if (tid < kZeroSlots) slab[tid] = 0.0;
   __syncthreads();
   const uint32_t G = gridDim.x, t0 = blockIdx.x;
-  if (warp < kWsProducerWarps) {
-    // ------------------------------------------------------------------ producers: K1, two cells per thread
+  if (warp < NP) {
+    // ------------------------------------------------------------------ producers: K1, CPT cell visits per thread
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PR));
-    auto load_hdr = [&](uint64_t t, uint32_t& cb, uint32_t& nc) {
-      cb = 0;
-      nc = 0;
-      if (t < uint64_t(P.ntiles)) {
-        const uint32_t a = __ldg(P.tile_cell_ptr + t), e = __ldg(P.tile_cell_ptr + t + 1);
-        const uint32_t c0 = __ldg(P.tile_chunk_ptr + t), c1 = __ldg(P.tile_chunk_ptr + t + 1);
-        cb = a;
-        nc = (c1 > c0 && !(P.debug & 1)) ? e - a : 0u;
+    const uint32_t W = uint32_t(P.cv_words);
+    uint32_t cvb = 0, ncv = 0, cvb_n = 0, ncv_n = 0;
+    auto load_range = [&](uint64_t t, uint32_t& b, uint32_t& n) {
+      b = 0, n = 0;
+      if (t < uint64_t(P.ntiles) && !(P.debug & 1)) {
+        b = __ldg(&P.tiles[t].cv_begin);
+        n = __ldg(&P.tiles[t].ncv);
       }
     };
-    auto load_ids = [&](uint32_t cb, uint32_t nc, uint32_t (*eid)[NEE]) {
+    auto load_ids = [&](uint32_t b, uint32_t n, uint32_t (*eid)[NEE]) {
 #pragma unroll
-      for (int j = 0; j < kAltCellsPerThread; ++j) {
-        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
-        if (c < nc) {
-          const uint32_t* ce = P.tile_cell_edges + size_t(cb + c) * NE;
+      for (int j = 0; j < CPT; ++j) {
+        const uint32_t c = uint32_t(tid) + uint32_t(j) * NPT;
+        if (c < n) {
+          const uint32_t* rec = P.cv_rec + size_t(b + c) * W;
 #pragma unroll
-          for (int e = 0; e < NE; ++e) eid[j][e] = __ldg(ce + e);
+          for (int e = 0; e < NE; ++e) eid[j][e] = __ldg(rec + e);
         }
       }
     };
-    uint32_t cb0, nc0, cb1, nc1, cb2, nc2;
-    load_hdr(t0, cb0, nc0);
-    load_hdr(uint64_t(t0) + G, cb1, nc1);
-    uint32_t eid[kAltCellsPerThread][NEE];
-    load_ids(cb0, nc0, eid);
+    load_range(t0, cvb, ncv);
+    load_range(uint64_t(t0) + G, cvb_n, ncv_n);
+    uint32_t eid[CPT][NEE];
+    load_ids(cvb, ncv, eid);
+    uint32_t sb[kMaxBlocks];
+#pragma unroll
+    for (int b = 0; b < kMaxBlocks; ++b) sb[b] = __ldg(&P.tiles[t0].slab_base[b]);  // the regions are the same for every tile
     for (uint32_t it = 0;; ++it) {
       const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
       if (t >= uint64_t(P.ntiles)) break;
-      load_hdr(t + 2 * uint64_t(G), cb2, nc2);  // cell range two tiles ahead (its ids are loaded next iteration)
-      // edge lengths and stage A (metric, inverse, volume) of this tile's cells; the consumers are still busy with the
-      // previous tile, so this latency is off the critical path
-      double mid[kAltCellsPerThread][NM];
+      // edge lengths and stage A (metric, inverse, volume) of this tile's cell visits: the consumers are still busy
+      // with the previous tile, so this latency is off the critical path
+      double mid[CPT][NM];
+      FusedSink sink[CPT];
 #pragma unroll
-      for (int j = 0; j < kAltCellsPerThread; ++j) {
-        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
-        if (c < nc0) {
+      for (int j = 0; j < CPT; ++j) {
+        const uint32_t c = uint32_t(tid) + uint32_t(j) * NPT;
+        sink[j].slab = slab;
+#pragma unroll
+        for (int b = 0; b < kMaxBlocks; ++b) sink[j].sb[b] = sb[b];
+        if (c < ncv) {
           double sl[NEE];
 #pragma unroll
           for (int e = 0; e < NE; ++e) sl[e] = __ldg(P.lengths + (eid[j][e] - P.edge_lo));
-          fn.a(sl, mid[j]);
+          const uint32_t* rec = P.cv_rec + size_t(cvb + c) * W + NE;
+#pragma unroll
+          for (int b = 0; b < kMaxBlocks; ++b) sink[j].meta[b] = __ldg(rec + ((P.class_pack >> (8 * b)) & 0xFFu));
+          Fn::a(sl, mid[j]);
         }
       }
-      load_ids(cb1, nc1, eid);  // ids of the next tile: in flight while the two halves are evaluated
+      load_ids(cvb_n, ncv_n, eid);  // ids of the next tile: in flight while the groups are evaluated
+      uint32_t cvb_nn, ncv_nn;
+      load_range(t + 2 * uint64_t(G), cvb_nn, ncv_nn);
       const uint32_t par_prev = (it - 1u) & 1u;
-      if (it >= 1) mbar_wait(a_empty, par_prev);  // every consumer warp is past the first-half records of the previous tile
+      auto stage = [&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        if (g >= NG) return;
+        if (it >= 1) mbar_wait(&g_empty[g], par_prev);  // every consumer warp is past this group's records of the previous tile
 #pragma unroll
-      for (int j = 0; j < kAltCellsPerThread; ++j) {
-        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
-        if (c < nc0) {
-          TileSink sink{slab + c, P.cstride};
-          fn.b1(mid[j], sink);
+        for (int j = 0; j < CPT; ++j) {
+          const uint32_t c = uint32_t(tid) + uint32_t(j) * NPT;
+          if (c < ncv) Fn::template g<g>(mid[j], sink[j]);
         }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
-      if (it >= 1) mbar_wait(b_empty, par_prev);  // ... and past its second-half records
-#pragma unroll
-      for (int j = 0; j < kAltCellsPerThread; ++j) {
-        const uint32_t c = uint32_t(tid) + uint32_t(j) * NP;
-        if (c < nc0) {
-          TileSink sink{slab + c, P.cstride};
-          fn.b2(mid[j], sink);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_full);
-      cb0 = cb1;
-      nc0 = nc1;
-      cb1 = cb2;
-      nc1 = nc2;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&g_full[g]);
+      };
+      stage(std::integral_constant<int, 0>());
+      stage(std::integral_constant<int, 1>());
+      stage(std::integral_constant<int, 2>());
+      cvb = cvb_n, ncv = ncv_n;
+      cvb_n = cvb_nn, ncv_n = ncv_nn;
     }
   } else {
     // ------------------------------------------------------------------ consumers: K3
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CR));  // the 16 consumer warps release what the 8 producer warps acquire
-    const int cw = warp - kWsProducerWarps;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CR));
+    const int cw = warp - NP;
     unsigned char* myring = smem_raw + P.ring_off + size_t(cw) * kSlotsPerWarp * kChunkBytes;
     uint64_t* mybar = tma_bar + cw * kSlotsPerWarp;
     uint32_t n_issued = 0, n_consumed = 0;
     uint32_t cur_it = 0xFFFFFFFFu, cur_chunk = 0, cur_end = 0;
     auto load_chunks = [&](uint64_t t, uint32_t& a, uint32_t& e) {
-      a = 0;
-      e = 0;
+      a = 0, e = 0;
       if (t < uint64_t(P.ntiles)) {
-        a = __ldg(P.tile_chunk_ptr + t);
-        e = __ldg(P.tile_chunk_ptr + t + 1);
+        a = __ldg(&P.tiles[t].chunk_begin);
+        e = a + ((P.debug & 2) ? 0u : __ldg(&P.tiles[t].nchunks));
       }
     };
     uint32_t c0, c1, c0n = 0, c1n = 0;
     load_chunks(t0, c0, c1);
-    // Chunk c of a tile goes to the warp (c - rotation) mod NC, the rotation advancing with every tile: a tile has
-    // ~3.75 chunks per warp, and without the rotation the same warps would get the extra chunk of every tile.
+    // Chunk c of a tile goes to the warp (c - rotation) mod NC, the rotation advancing with every tile: without it the
+    // same warps would get the extra chunk of every tile.
     const uint32_t rot_step = P.chunk_rotation;
     auto lane_of = [&](uint32_t iter) { return (uint32_t(cw) + iter * rot_step) % uint32_t(NC); };
     for (uint32_t it = 0;; ++it) {
@@ -727,304 +350,606 @@ __global__ void __launch_bounds__(32 * (kWsProducerWarps + NC), 1) tile_assemble
         cur_end = c1;
       }
       issue_more();
-      AltState st{a_empty, b_full, it & 1u, false};
-      mbar_wait(a_full, it & 1u);
+      const uint32_t par = it & 1u;
+      uint32_t g_cur = 0;
+      mbar_wait(&g_full[0], par);
       for (uint32_t c = c0 + lane_of(it); c < c1; c += NC) {
         mbar_wait(&mybar[n_consumed & 1u], (n_consumed >> 1) & 1u);
-        gather_chunk<true>(myring + (n_consumed & 1u) * kChunkBytes, P, slab, rec, lane, &st);
-        __syncwarp();
+        const unsigned char* chunk = myring + (n_consumed & 1u) * kChunkBytes;
+        const uint32_t nrec = *reinterpret_cast<const uint32_t*>(chunk);
+        const unsigned char* rp = chunk + kChunkHdr;
+        uint32_t h = *reinterpret_cast<const uint32_t*>(rp);  // header of the first record (a chunk holds at least one)
+        for (uint32_t r = 0; r < nrec; ++r) {
+          const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, stride = h >> 16;  // stride = lanes of the record: 64, 32 or 16
+          const unsigned char* rec = rp;
+          rp += kRecHdr + stride * (4u + 2u * L);
+          // header of the next record: off the critical path
+          if (r + 1 < nrec) h = *reinterpret_cast<const uint32_t*>(rp);
+          const uint32_t g = (P.group_pack >> (8 * b)) & 0xFFu;
+          while (g_cur < g) {  // done with a stage group: its slab region goes back to the producers; wait for the next one
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&g_empty[g_cur]);
+            ++g_cur;
+            mbar_wait(&g_full[g_cur], par);
+          }
+          double* __restrict__ vals = P.values[b];
+          uint8_t* __restrict__ keep = COMPACT ? nullptr : P.keep[b];
+          if (stride == 64u) {
+            switch (L) {
+              case 1: record_wide<1, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
+              case 2: record_wide<2, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
+              case 3: record_wide<3, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
+              case 4: record_wide<4, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
+              case 5: record_wide<5, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
+              case 6: record_wide<6, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
+              default: record_any<COMPACT>(rec, L, stride, lane, slab, vals, keep, P.changed); break;
+            }
+          } else {
+            record_any<COMPACT>(rec, L, stride, lane, slab, vals, keep, P.changed);
+          }
+        }
+        __syncwarp();  // every lane is done reading the slot before it is refilled
         ++n_consumed;
         issue_more();
       }
+      // Release the remaining groups.  A warp always observes full(g) before it arrives on empty(g): otherwise it could
+      // run a tile ahead of a slow warp and complete a phase of empty(g) while that warp still reads the region.
       __syncwarp();
-      if (!st.in_y) {
-        // This warp had no second-half records in the tile.  It must still observe b_full(it) before it arrives on
-        // b_empty: otherwise it could run a whole tile ahead of a slow warp and its arrival for tile it+1 would
-        // complete phase it of b_empty while that warp still reads the second half of tile it.
-        if (lane == 0) mbar_arrive(a_empty);
-        mbar_wait(b_full, it & 1u);
+      for (;;) {
+        if (lane == 0) mbar_arrive(&g_empty[g_cur]);
+        if (++g_cur >= uint32_t(NG)) break;
+        mbar_wait(&g_full[g_cur], par);
       }
-      if (lane == 0) mbar_arrive(b_empty);
       c0 = c0n;
       c1 = c1n;
     }
   }
 }
 
-// ------------------------------------------------------------------ plan
-struct TileBlockPlan {
-  int no = 1, ni = 1, recipe_off = 0, slot_bits = 7;
-  fq_csr* csr = nullptr;
-  size_t nnz_at_build = 0;
-  bool dropped_at_build = false;
+// After the first (structural) pass of a dropping assembly: dest -> position in the compacted pattern, or kNoDest.
+struct RetargetArgs {
+  const uint8_t* keep[kMaxBlocks];
+  const uint32_t* pos[kMaxBlocks];
+};
+__global__ void retarget_kernel(unsigned char* __restrict__ stream, uint32_t nchunks, RetargetArgs A) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t wstride = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunks; c += wstride) {
+    unsigned char* chunk = stream + size_t(c) * kChunkBytes;
+    const uint32_t nrec = *reinterpret_cast<const uint32_t*>(chunk);
+    unsigned char* rp = chunk + kChunkHdr;
+    for (uint32_t r = 0; r < nrec; ++r) {
+      const uint32_t h = *reinterpret_cast<const uint32_t*>(rp);
+      const uint32_t L = h & 0xFFu, b = (h >> 8) & 3u, lanes = h >> 16;
+      uint32_t* dest = reinterpret_cast<uint32_t*>(rp + kRecHdr);
+      for (uint32_t l = lane; l < lanes; l += 32u) {
+        const uint32_t d = dest[l];
+        if (d > kNoDest) dest[l] = A.keep[b][d - 2u] ? A.pos[b][d - 2u] + 2u : kNoDest;
+      }
+      rp += kRecHdr + lanes * (4u + 2u * L);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ device plan builder
+constexpr int kBT = 512;                      // threads of a builder CTA
+constexpr int kIPT = kMaxEntries / kBT;       // entries per thread of the block-wide sorts
+constexpr int kIdIPT = kMaxCv * kMaxLocal / kBT;
+static_assert(kIPT * kBT == kMaxEntries && kIdIPT * kBT == kMaxCv * kMaxLocal, "sort tiling");
+typedef cub::BlockRadixSort<uint32_t, kBT, kIPT, uint16_t> EntSort;
+typedef cub::BlockRadixSort<uint32_t, kBT, kIdIPT, uint16_t> IdSort;
+typedef cub::BlockScan<uint32_t, kBT> BScan;
+
+struct BuildParams {
+  SetDesc S;
+  int gtab[4];                 // grade -> local-id table (0/1), -1 unused
+  int id_bits[4];              // significant bits of the global face ids per grade
+  const uint32_t* faces[4];
+  const uint32_t* vertex_tile;
+  uint32_t v_lo;
+  uint32_t ntiles;
+  const uint32_t* tile_cv_ptr;
+  const uint32_t* tile_cv_cells;
+  uint32_t slab_base[kMaxBlocks];    // emitting pass in: region of every block (the same for all tiles)
+  uint32_t* rs_max;                  // counting pass out: largest row-slot count per row class
+  uint32_t* row_ptr[kMaxBlocks];     // counting pass: row lengths out; emitting pass: structural row_ptr in
+  uint32_t* col_idx[kMaxBlocks];
+  uint32_t* tile_nchunks;            // counting pass out
+  unsigned long long* ncontrib;      // counting pass out: owned element entries per block
+  const uint32_t* tile_chunk_ptr;    // emitting pass in
+  TileHdr* tiles;
+  uint32_t* cv_rec;
+  unsigned char* stream;
+  int* err;
 };
 
-struct TilePlan {
-  const fq_mesh* mesh = nullptr;
-  int dim = 0, core_k = 0, ndistinct = 0;
-  uint32_t ntiles = 0;
-  int cstride = 0;
-  int nthreads = 512;
-  bool ws = false;
-  bool alt = false;           // FQ_TILE_KERNEL=a and the block set splits: tile_assemble_alt_kernel
-  uint32_t yblock_mask = 0;   // blocks reading only second-half values
-  bool pack = false;          // bank-aware lane packing (slab stride = 0 mod 16)
-  int stream_warps = 0;       // alternating kernel with 20 / 24 consumer warps (0: 16)
-  uint32_t slab_bytes = 0;
-  size_t smem_bytes = 0;
-  uint32_t ring_off = 0, rec_off = 0, mbar_off = 0;
-  int recipe_bytes = 0;
-  DevBuf<uint32_t> tile_cell_ptr, tile_cell_edges, tile_chunk_ptr;
-  DevBuf<unsigned char> stream;
-  DevBuf<uint8_t> recipes;
-  DevBuf<int> changed;
-  DevBuf<unsigned int> ticket;
-  DevBuf<unsigned long long> stats;
-  int nblocks = 0;
-  TileBlockPlan blk[kTileMaxBlocks];
-  int grid = 0;
-  void (*launch)(fq_ctx*, const TilePlan&, const TileParams&) = nullptr;
+struct RunInfo {
+  uint32_t p0, lanes, size, fits, m, off0, fresh0;
+};
+struct BuildSmem {
+  union {
+    typename EntSort::TempStorage ent;
+    typename IdSort::TempStorage id;
+    typename BScan::TempStorage scan;
+  } tmp;
+  uint32_t skey[kMaxEntries];
+  uint16_t sval[kMaxEntries];
+  uint16_t nz_first[kMaxEntries + 2];
+  uint16_t ord[kMaxEntries];
+  uint8_t Lp[kMaxEntries];
+  uint16_t lid[2][kMaxCv * kMaxLocal];
+  uint32_t glob[2][kMaxCv * kMaxLocal];
+  uint32_t cells[kMaxCv];
+  uint8_t cmask[kMaxClasses][kMaxCv];
+  uint16_t cbase[kMaxClasses][kMaxCv];
+  uint16_t ebase[kMaxCv];
+  uint16_t rowstart[kMaxCv * kMaxLocal];
+  uint16_t runstart[64];
+  RunInfo run[64];
+  uint32_t RS[kMaxClasses];
+  uint32_t slab_base[kMaxBlocks];
+  uint32_t E, Q, bad;
+  // placement cursor of the tile's stream (tile_plan.hpp: Cursor)
+  uint32_t cur_off, cur_chunk_start, cur_in_chunk, cur_open, cur_next_start;
 };
 
-#define FQ_DECLARE_CORE(fn, n, k, variant, nin, nd, nout)                                      \
-  struct Core_##fn {                                                                           \
-    static constexpr int kDistinct = nd;                                                       \
-    static constexpr int kMid = fn##_nmid; /* values live across the stage A / stage B cut */  \
-    template <class S>                                                                         \
-    __device__ __forceinline__ void operator()(const double* __restrict__ s, S& sink) const {  \
-      fn(s, sink);                                                                             \
-    }                                                                                          \
-    __device__ __forceinline__ void a(const double* __restrict__ s, double* __restrict__ mid) const { \
-      fn##_a(s, mid);                                                                          \
-    }                                                                                          \
-    template <class S>                                                                         \
-    __device__ __forceinline__ void b1(const double* __restrict__ mid, S& sink) const {        \
-      fn##_b1(mid, sink);                                                                      \
-    }                                                                                          \
-    template <class S>                                                                         \
-    __device__ __forceinline__ void b2(const double* __restrict__ mid, S& sink) const {        \
-      fn##_b2(mid, sink);                                                                      \
-    }                                                                                          \
+template <bool EMIT>
+__global__ void __launch_bounds__(kBT, 1) tile_build_kernel(const __grid_constant__ BuildParams P) {
+  extern __shared__ __align__(16) unsigned char build_smem_raw[];
+  BuildSmem& sm = *reinterpret_cast<BuildSmem*>(build_smem_raw);
+  const SetDesc& S = P.S;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+    __syncthreads();
+    const uint32_t cv0 = P.tile_cv_ptr[t], ncv = P.tile_cv_ptr[t + 1] - cv0;
+    if (tid == 0) {
+      sm.bad = ncv > uint32_t(kMaxCv) ? 1u : 0u;
+      sm.cur_off = 0, sm.cur_chunk_start = 0, sm.cur_in_chunk = 0, sm.cur_open = 0, sm.cur_next_start = 0;
+    }
+    if (tid < ncv && tid < uint32_t(kMaxCv)) sm.cells[tid] = P.tile_cv_cells[cv0 + tid];
+    __syncthreads();
+    if (sm.bad) {
+      if (tid == 0) atomicExch(P.err, 1);
+      if (!EMIT && tid == 0) P.tile_nchunks[t] = 0;
+      continue;
+    }
+    // ---- row classes: owned-row masks and first row slots
+    for (int c = 0; c < S.nclasses; ++c) {
+      const int g = S.class_grade[c], nl = S.nl[g];
+      uint32_t m = 0;
+      if (tid < ncv) {
+        const size_t cell = sm.cells[tid];
+        for (int r = 0; r < nl; ++r) {
+          const uint32_t row = P.faces[g][cell * nl + r];
+          const uint32_t topv = P.faces[0][cell * S.nv + S.top[g][r]];
+          if (P.vertex_tile[topv - P.v_lo] == t && row >= S.class_lo[c] && row < S.class_hi[c]) m |= 1u << r;
+        }
+        sm.cmask[c][tid] = uint8_t(m);
+      }
+      uint32_t base, total;
+      BScan(sm.tmp.scan).ExclusiveSum(uint32_t(__popc(m)), base, total);
+      if (tid < ncv) sm.cbase[c][tid] = uint16_t(base);
+      if (tid == 0) sm.RS[c] = total;
+      __syncthreads();
+    }
+    if (tid < uint32_t(kMaxBlocks)) sm.slab_base[tid] = P.slab_base[tid];
+    if (!EMIT && tid < uint32_t(S.nclasses)) atomicMax(&P.rs_max[tid], sm.RS[tid]);
+    __syncthreads();
+    if (EMIT) {
+      if (tid < ncv) {
+        const size_t cell = sm.cells[tid];
+        uint32_t* rec = P.cv_rec + size_t(cv0 + tid) * S.cv_words;
+        for (int e = 0; e < S.ne; ++e) rec[e] = P.faces[1][cell * S.ne + e];
+        for (int c = 0; c < S.nclasses; ++c) rec[S.ne + c] = uint32_t(sm.cmask[c][tid]) | (uint32_t(sm.cbase[c][tid]) << 8);
+      }
+      if (tid == 0) {
+        TileHdr H;
+        H.cv_begin = cv0, H.ncv = ncv;
+        H.chunk_begin = P.tile_chunk_ptr[t];
+        H.nchunks = P.tile_chunk_ptr[t + 1] - P.tile_chunk_ptr[t];
+        for (int b = 0; b < kMaxBlocks; ++b) H.slab_base[b] = b < S.nblocks ? sm.slab_base[b] : 0u;
+        P.tiles[t] = H;
+      }
+    }
+    // ---- local face numbering (monotone in the global id) of the grades the blocks use
+    for (int g = 0; g <= S.n; ++g) {
+      const int x = P.gtab[g];
+      if (x < 0) continue;
+      const uint32_t nl = uint32_t(S.nl[g]), N = ncv * nl;
+      uint32_t keys[kIdIPT];
+      uint16_t vals[kIdIPT];
+#pragma unroll
+      for (int k = 0; k < kIdIPT; ++k) {
+        const uint32_t idx = tid * kIdIPT + k;
+        keys[k] = 0xFFFFFFFFu, vals[k] = 0xFFFFu;
+        if (idx < N) {
+          keys[k] = P.faces[g][size_t(sm.cells[idx / nl]) * nl + idx % nl];
+          vals[k] = uint16_t(idx);
+        }
+      }
+      IdSort(sm.tmp.id).Sort(keys, vals, 0, P.id_bits[g]);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kIdIPT; ++k) {
+        sm.skey[tid * kIdIPT + k] = keys[k];
+        sm.sval[tid * kIdIPT + k] = vals[k];
+      }
+      __syncthreads();
+      uint32_t heads = 0;
+#pragma unroll
+      for (int k = 0; k < kIdIPT; ++k) {
+        const uint32_t idx = tid * kIdIPT + k;
+        if (idx < N && (idx == 0 || sm.skey[idx] != sm.skey[idx - 1])) heads |= 1u << k;
+      }
+      uint32_t prefix, total;
+      BScan(sm.tmp.scan).ExclusiveSum(uint32_t(__popc(heads)), prefix, total);
+#pragma unroll
+      for (int k = 0; k < kIdIPT; ++k) {
+        const uint32_t idx = tid * kIdIPT + k;
+        if (idx >= N) continue;
+        if (heads >> k & 1u) {
+          sm.glob[x][prefix] = sm.skey[idx];
+          ++prefix;
+        }
+        sm.lid[x][sm.sval[idx]] = uint16_t(prefix - 1u);
+      }
+      __syncthreads();
+    }
+    // ---- blocks
+    unsigned char* sbase = EMIT ? P.stream + size_t(P.tile_chunk_ptr[t]) * kChunkBytes : nullptr;
+    for (int b = 0; b < S.nblocks; ++b) {
+      const BlockDesc& B = S.blk[b];
+      if (B.empty) continue;
+      const int c = B.rclass, xt = P.gtab[B.tg], xr = P.gtab[B.rg];
+      const uint32_t nt = uint32_t(B.nt), nr = uint32_t(B.nr);
+      // entries of the owned rows, in (cell visit, row, column) order
+      {
+        const uint32_t m = tid < ncv ? uint32_t(sm.cmask[c][tid]) : 0u;
+        uint32_t ebase, E;
+        BScan(sm.tmp.scan).ExclusiveSum(uint32_t(__popc(m)) * nr, ebase, E);
+        if (tid == 0) {
+          sm.E = E;
+          if (E > uint32_t(kMaxEntries)) sm.bad = 1;
+          if (!EMIT) atomicAdd(&P.ncontrib[b], (unsigned long long)E);
+        }
+        __syncthreads();
+        if (sm.bad) break;
+        if (tid < ncv) {
+          uint32_t e = ebase, rs = sm.cbase[c][tid];
+          for (uint32_t r = 0; r < nt; ++r) {
+            if (!(m >> r & 1u)) continue;
+            const uint32_t rl = sm.lid[xt][tid * nt + r];
+            for (uint32_t j = 0; j < nr; ++j) {
+              const uint32_t cs = B.cs[r * nr + j];
+              sm.skey[e] = (rl << 12) | uint32_t(sm.lid[xr][tid * nr + j]);
+              sm.sval[e] = uint16_t(cs == 0xFFu ? 0u : sm.slab_base[b] + rs * uint32_t(B.d) + cs);
+              ++e;
+            }
+            ++rs;
+          }
+        }
+        for (uint32_t e = E + tid; e < uint32_t(kMaxEntries); e += kBT) sm.skey[e] = 0xFFFFFFFFu;
+        __syncthreads();
+      }
+      const uint32_t E = sm.E;
+      {
+        uint32_t keys[kIPT];
+        uint16_t vals[kIPT];
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          keys[k] = sm.skey[tid * kIPT + k];
+          vals[k] = sm.sval[tid * kIPT + k];
+        }
+        __syncthreads();
+        EntSort(sm.tmp.ent).Sort(keys, vals, 0, 24);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          sm.skey[tid * kIPT + k] = keys[k];
+          sm.sval[tid * kIPT + k] = vals[k];
+        }
+        __syncthreads();
+      }
+      // non-zeros = runs of equal keys (CSR order: local row, column)
+      {
+        uint32_t heads = 0;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          const uint32_t e = tid * kIPT + k;
+          if (e < E && (e == 0 || sm.skey[e] != sm.skey[e - 1])) heads |= 1u << k;
+        }
+        uint32_t prefix, Q;
+        BScan(sm.tmp.scan).ExclusiveSum(uint32_t(__popc(heads)), prefix, Q);
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k)
+          if (heads >> k & 1u) sm.nz_first[prefix++] = uint16_t(tid * kIPT + k);
+        if (tid == 0) {
+          sm.Q = Q;
+          sm.nz_first[Q] = uint16_t(E);
+        }
+        __syncthreads();
+      }
+      const uint32_t Q = sm.Q;
+      // rows of the tile: first non-zero, length (counting pass), column ids (emitting pass)
+      for (uint32_t q = tid; q < Q; q += kBT) {
+        const uint32_t rl = sm.skey[sm.nz_first[q]] >> 12;
+        if (q == 0 || (sm.skey[sm.nz_first[q - 1]] >> 12) != rl) sm.rowstart[rl] = uint16_t(q);
+      }
+      __syncthreads();
+      for (uint32_t q = tid; q < Q; q += kBT) {
+        const uint32_t key = sm.skey[sm.nz_first[q]];
+        const uint32_t rl = key >> 12;
+        const uint32_t grow = sm.glob[xt][rl] - B.row_begin;
+        if (!EMIT) {
+          if (q + 1 == Q || (sm.skey[sm.nz_first[q + 1]] >> 12) != rl) P.row_ptr[b][grow] = q + 1u - uint32_t(sm.rowstart[rl]);
+        } else {
+          P.col_idx[b][P.row_ptr[b][grow] + (q - uint32_t(sm.rowstart[rl]))] = sm.glob[xr][key & 0xFFFu];
+        }
+      }
+      // non-zeros grouped by their number of contributions (stable: CSR order inside a run)
+      {
+        uint32_t keys[kIPT];
+        uint16_t vals[kIPT];
+        bool too_long = false;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          const uint32_t q = tid * kIPT + k;
+          keys[k] = 0xFFFFFFFFu, vals[k] = 0xFFFFu;
+          if (q < Q) {
+            keys[k] = uint32_t(sm.nz_first[q + 1]) - uint32_t(sm.nz_first[q]);
+            vals[k] = uint16_t(q);
+            too_long = too_long || keys[k] > uint32_t(kMaxLen);
+          }
+        }
+        if (too_long) sm.bad = 1;
+        __syncthreads();
+        if (sm.bad) break;
+        EntSort(sm.tmp.ent).Sort(keys, vals, 0, 6);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          const uint32_t p = tid * kIPT + k;
+          if (p < Q) {
+            sm.ord[p] = vals[k];
+            sm.Lp[p] = uint8_t(keys[k]);
+          }
+        }
+        if (tid < 64) sm.runstart[tid] = 0xFFFFu;
+        __syncthreads();
+      }
+      for (uint32_t p = tid; p < Q; p += kBT)
+        if (p == 0 || sm.Lp[p] != sm.Lp[p - 1]) sm.runstart[sm.Lp[p]] = uint16_t(p);
+      __syncthreads();
+      // placement of the runs' records in the tile's chunks (closed form of Cursor::place per run)
+      if (tid == 0) {
+        uint32_t off = sm.cur_off, chunk_start = sm.cur_chunk_start, in_chunk = sm.cur_in_chunk, open = sm.cur_open,
+                 next_start = sm.cur_next_start;
+        int prevL = -1;
+        for (int L = 1; L <= kMaxLen + 1; ++L) {
+          const bool present = L <= kMaxLen && sm.runstart[L] != 0xFFFFu;
+          if (!present && L <= kMaxLen) continue;
+          if (prevL >= 0) {
+            RunInfo& R = sm.run[prevL];
+            const uint32_t p1 = L <= kMaxLen ? uint32_t(sm.runstart[L]) : Q;
+            const uint32_t cnt = p1 - R.p0;
+            R.lanes = rec_lanes(uint32_t(prevL));
+            R.size = rec_bytes(uint32_t(prevL));
+            const uint32_t nrec = (cnt + R.lanes - 1u) / R.lanes;
+            R.m = (uint32_t(kChunkBytes) - uint32_t(kChunkHdr)) / R.size;
+            R.fits = open ? (chunk_start + uint32_t(kChunkBytes) - off) / R.size : 0u;
+            R.off0 = off;
+            R.fresh0 = next_start;
+            if (nrec <= R.fits) {
+              off += nrec * R.size;
+              in_chunk += nrec;
+            } else {
+              if (open && EMIT) *reinterpret_cast<uint32_t*>(sbase + chunk_start) = in_chunk + R.fits;
+              const uint32_t rem = nrec - R.fits, nfull = rem / R.m, last = rem % R.m;
+              const uint32_t used = nfull + (last ? 1u : 0u);
+              if (EMIT)
+                for (uint32_t f = 0; f + 1 < used; ++f) *reinterpret_cast<uint32_t*>(sbase + R.fresh0 + f * kChunkBytes) = R.m;
+              in_chunk = last ? last : R.m;
+              chunk_start = R.fresh0 + (used - 1u) * uint32_t(kChunkBytes);
+              off = chunk_start + uint32_t(kChunkHdr) + in_chunk * R.size;
+              next_start = chunk_start + uint32_t(kChunkBytes);
+              open = 1;
+            }
+          }
+          if (L <= kMaxLen) {
+            sm.run[L].p0 = sm.runstart[L];
+            prevL = L;
+          }
+        }
+        sm.cur_off = off, sm.cur_chunk_start = chunk_start, sm.cur_in_chunk = in_chunk, sm.cur_open = open,
+        sm.cur_next_start = next_start;
+      }
+      __syncthreads();
+      if (EMIT) {
+        for (uint32_t p = tid; p < Q; p += kBT) {
+          const uint32_t L = sm.Lp[p], q = sm.ord[p];
+          const RunInfo& R = sm.run[L];
+          const uint32_t idx = p - R.p0, k = idx / R.lanes, lane = idx % R.lanes;
+          uint32_t at;
+          if (k < R.fits) {
+            at = R.off0 + k * R.size;
+          } else {
+            const uint32_t kk = k - R.fits;
+            at = R.fresh0 + (kk / R.m) * uint32_t(kChunkBytes) + uint32_t(kChunkHdr) + (kk % R.m) * R.size;
+          }
+          unsigned char* rp = sbase + at;
+          if (lane == 0) *reinterpret_cast<uint32_t*>(rp) = L | (uint32_t(b) << 8) | (R.lanes << 16);
+          const uint32_t first = sm.nz_first[q];
+          const uint32_t rl = sm.skey[first] >> 12;
+          const uint32_t grow = sm.glob[xt][rl] - B.row_begin;
+          reinterpret_cast<uint32_t*>(rp + kRecHdr)[lane] = P.row_ptr[b][grow] + (q - uint32_t(sm.rowstart[rl])) + 2u;
+          uint16_t* ent = reinterpret_cast<uint16_t*>(rp + kRecHdr + 4u * R.lanes) + lane;
+          for (uint32_t j = 0; j < L; ++j) ent[j * R.lanes] = sm.sval[first + j];
+        }
+      }
+      __syncthreads();
+    }
+    if (sm.bad) {
+      if (tid == 0) atomicExch(P.err, 3);
+      if (!EMIT && tid == 0) P.tile_nchunks[t] = 0;
+      continue;
+    }
+    if (tid == 0) {
+      if (sm.cur_open && EMIT) *reinterpret_cast<uint32_t*>(sbase + sm.cur_chunk_start) = sm.cur_in_chunk;
+      if (!EMIT) P.tile_nchunks[t] = sm.cur_next_start / uint32_t(kChunkBytes);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generated block sets
+#define FQ_DECLARE_SET(fn, n, fk, kind, grade, nin)                                                      \
+  struct Set_##fn {                                                                                      \
+    static constexpr int kMid = fn##_nmid;                                                               \
+    static constexpr int kGroups = fn##_ngroups;                                                         \
+    static __device__ __forceinline__ void a(const double* __restrict__ s, double* __restrict__ mid) {   \
+      fn##_a(s, mid);                                                                                    \
+    }                                                                                                    \
+    template <int G, class S>                                                                            \
+    static __device__ __forceinline__ void g(const double* __restrict__ mid, S& sink) {                  \
+      if (G == 0) fn##_g0(mid, sink);                                                                    \
+      if (G == 1) fn##_g1(mid, sink);                                                                    \
+      if (G == 2) fn##_g2(mid, sink);                                                                    \
+    }                                                                                                    \
   };
-FQ_GEN_CORE_LIST(FQ_DECLARE_CORE)
-#undef FQ_DECLARE_CORE
+FQ_GEN_SET_LIST(FQ_DECLARE_SET)
+#undef FQ_DECLARE_SET
 
-template <class Fn, int NE, int NT, int MINB>
-static void launch_tile_nt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+struct TilePlan;
+struct FusedLaunch {
+  int grid;
+  size_t slab_bytes;   // aligned size of the slab: ring and barriers follow
+  bool compact;
+};
+template <class Fn, int NE, int NP, int NC, int PR, int CR>
+static void launch_fused_v(fq_ctx* ctx, const FusedLaunch& L, FusedParams params) {
   static bool attr_set = false;
   if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_kernel<Fn, NE, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (MINB == 1 ? 227 : 113) * 1024 - 256));
+    FQ_CUDA(cudaFuncSetAttribute(tile_fused_kernel<Fn, NE, NP, NC, PR, CR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemCta)));
+    FQ_CUDA(cudaFuncSetAttribute(tile_fused_kernel<Fn, NE, NP, NC, PR, CR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemCta)));
     attr_set = true;
   }
-  tile_assemble_kernel<Fn, NE, NT, MINB><<<plan.grid, NT, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
+  params.ring_off = uint32_t(L.slab_bytes);
+  params.mbar_off = uint32_t(L.slab_bytes + size_t(NC) * kSlotsPerWarp * kChunkBytes);
+  const size_t smem = size_t(params.mbar_off) + kBarBytes;
+  if (L.compact)
+    tile_fused_kernel<Fn, NE, NP, NC, PR, CR, true><<<L.grid, 32 * (NP + NC), smem, ctx->stream>>>(params);
+  else
+    tile_fused_kernel<Fn, NE, NP, NC, PR, CR, false><<<L.grid, 32 * (NP + NC), smem, ctx->stream>>>(params);
 }
 template <class Fn, int NE>
-static void launch_tile_ws(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_ws_kernel<Fn, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    attr_set = true;
-  }
-  tile_assemble_ws_kernel<Fn, NE><<<plan.grid, kWsThreads, plan.smem_bytes, ctx->stream>>>(Fn{}, params);
-}
-template <class Fn, int NE, int NC, int PR, int CR>
-static void launch_tile_alt_v(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FQ_CUDA(cudaFuncSetAttribute(tile_assemble_alt_kernel<Fn, NE, NC, PR, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024 - 256));
-    attr_set = true;
-  }
-  tile_assemble_alt_kernel<Fn, NE, NC, PR, CR><<<plan.grid, 32 * (kWsProducerWarps + NC), plan.smem_bytes, ctx->stream>>>(Fn{}, params);
-}
-template <class Fn, int NE>
-static void launch_tile_alt(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
+static void launch_fused(fq_ctx* ctx, const FusedLaunch& L, const FusedParams& params) {
   static int variant = -1;
   if (variant < 0) {
-    const char* e = std::getenv("FQ_ALT_REGS");  // tuning (16 consumer warps): 0 = 128/56, 1 = 112/64 (default), 2 = 96/72
-    variant = e ? std::atoi(e) : 1;
-    if (variant < 0 || variant > 2) variant = 1;
+    // tuning: producer/consumer warps and registers.  0: 8+16 warps, 144/48 registers; 1: 8+16, 128/56;
+    // 2: 16+12 warps (one cell visit per producer thread), 96/40; 3: 16+16, 88/40; 4: 12+12, 112/48
+    const char* e = std::getenv("FQ_TILE_WARPS");
+    variant = e ? std::atoi(e) : 0;
+    if (variant < 0 || variant > 4) variant = 0;
   }
-  if (plan.stream_warps == 24)
-    launch_tile_alt_v<Fn, NE, 24, 88, 56>(ctx, plan, params);
-  else if (plan.stream_warps == 20)
-    launch_tile_alt_v<Fn, NE, 20, 88, 64>(ctx, plan, params);
-  else if (variant == 2)
-    launch_tile_alt_v<Fn, NE, 16, 96, 72>(ctx, plan, params);
-  else if (variant == 0)
-    launch_tile_alt_v<Fn, NE, 16, 128, 56>(ctx, plan, params);
-  else
-    launch_tile_alt_v<Fn, NE, 16, 112, 64>(ctx, plan, params);
-}
-template <class Fn, int NE>
-static void launch_tile(fq_ctx* ctx, const TilePlan& plan, const TileParams& params) {
-  if (plan.alt)
-    launch_tile_alt<Fn, NE>(ctx, plan, params);
-  else if (plan.ws)
-    launch_tile_ws<Fn, NE>(ctx, plan, params);
-  else if (plan.nthreads == 256)
-    launch_tile_nt<Fn, NE, 256, 2>(ctx, plan, params);  // two CTAs per SM: one tile's K1 overlaps the other's gather
-  else
-    launch_tile_nt<Fn, NE, 512, 1>(ctx, plan, params);
+  switch (variant) {
+    case 2: launch_fused_v<Fn, NE, 16, 12, 96, 40>(ctx, L, params); break;
+    case 3: launch_fused_v<Fn, NE, 16, 16, 88, 40>(ctx, L, params); break;
+    default: launch_fused_v<Fn, NE, 8, 16, 144, 48>(ctx, L, params); break;
+  }
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
 }
 
-// variant 0: stores M_{k-1}, M_k, M_{k+1};  variant 1: stores M_{k-1}, M_k, dif_both(k+1)
-struct CoreEntryRt {
-  int n, k, variant, nin, ndistinct, nouts;
-  const short* map;
-  int split_ok;                      // the stored values split into two halves (gen_elmat.cpp)
-  const unsigned long long* half2;   // bit s: distinct slot s belongs to the second half
-  void (*launch)(fq_ctx*, const TilePlan&, const TileParams&);
+struct SetEntryRt {
+  int n, fused_k, kind, grade, ninputs, ngroups;
+  void (*launch)(fq_ctx*, const FusedLaunch&, const FusedParams&);
 };
-#define FQ_CORE_ENTRY(fn, n, k, variant, nin, nd, nout) \
-  CoreEntryRt{n, k, variant, nin, nd, nout, fn##_map, fn##_split_ok, fn##_half2, &launch_tile<Core_##fn, nin>},
-static const CoreEntryRt g_cores[] = {FQ_GEN_CORE_LIST(FQ_CORE_ENTRY)};
-#undef FQ_CORE_ENTRY
+#define FQ_SET_ENTRY(fn, n, fk, kind, grade, nin) SetEntryRt{n, fk, kind, grade, nin, fn##_ngroups, &launch_fused<Set_##fn, nin>},
+static const SetEntryRt g_sets[] = {FQ_GEN_SET_LIST(FQ_SET_ENTRY)};
+#undef FQ_SET_ENTRY
 
-// offset of the stored block (kind, g) inside the core's map, or -1 when the core does not store it
-static int stored_offset(const CoreEntryRt& core, int kind, int g) {
-  const BlockSpec stored[3] = {{KIND_MASS, core.k - 1},
-                               {KIND_MASS, core.k},
-                               {core.variant == 1 ? int(KIND_DIF_BOTH) : int(KIND_MASS), core.k + 1}};
-  int off = 0;
-  for (const BlockSpec& b : stored) {
-    int tg, rg;
-    kind_grades(b.kind, b.grade, tg, rg);
-    if (b.kind == kind && b.grade == g) return off;
-    off += nlocal(core.n, tg) * nlocal(core.n, rg);
+// The generated set serving exactly these blocks: hodge_blocks(k) or one single block.
+static const SetEntryRt* find_set(int dim, fq_csr* const* csrs, int nblocks, std::vector<BlockSpec>& specs) {
+  specs.clear();
+  for (int b = 0; b < nblocks; ++b) specs.push_back(BlockSpec{csrs[b]->kind, csrs[b]->grade});
+  if (nblocks == 4) {
+    for (const SetEntryRt& e : g_sets) {
+      if (e.n != dim || e.fused_k < 0) continue;
+      const auto hb = hodge_blocks(e.fused_k);
+      bool same = true;
+      for (int b = 0; b < 4; ++b) same = same && hb[size_t(b)].kind == specs[size_t(b)].kind && hb[size_t(b)].grade == specs[size_t(b)].grade;
+      if (same) return &e;
+    }
+    return nullptr;
   }
-  return -1;
+  if (nblocks == 1)
+    for (const SetEntryRt& e : g_sets)
+      if (e.n == dim && e.fused_k < 0 && e.kind == specs[0].kind && e.grade == specs[0].grade) return &e;
+  return nullptr;
 }
 
-// ---- launch configuration (tunable through the environment for sweeps) -------
-struct TileConfig {
-  int nthreads;
-  size_t smem_cta;  // dynamic shared memory budget of the CTA
-  bool ws;          // warp-specialised kernel: two slabs, 8 producer + 16 consumer warps
-  bool alt = false;           // alternating kernel: the layout of the phase-serialised kernel, 8 + 16 warps
-  int stream_warps = 0;       // warps that stream chunks (0: nthreads / 32, or the 16 consumers of the w/p kernels)
+// ------------------------------------------------------------------ plan
+struct TilePlan {
+  const fq_mesh* mesh = nullptr;
+  int dim = 0, nblocks = 0;
+  const SetEntryRt* set = nullptr;
+  SetDesc desc;
+  int gtab[4] = {-1, -1, -1, -1};
+  uint32_t ntiles = 0, nchunks = 0;
+  uint32_t max_slab = 0;
+  size_t slab_bytes = 0;
+  DevBuf<uint32_t> tile_cv_ptr, tile_cv_cells;
+  DevBuf<TileHdr> tiles;
+  DevBuf<uint32_t> cv_rec;
+  DevBuf<unsigned char> stream;
+  DevBuf<int> changed;
+  fq_csr* csr[kMaxBlocks] = {nullptr, nullptr, nullptr, nullptr};
+  bool compact = false;     // the stream's dests target the value-dependent (dropped) pattern
+  bool drop = false;        // semantics the active pattern was produced under
+  bool fresh = true;        // no numeric pass yet: dests are structural
+  double build_ms = 0.0;
+  int grid = 0;
 };
-static TileConfig tile_config() {
-  TileConfig c{512, size_t(227) * 1024 - 256, false};
-  c.alt = true;  // default: the alternating producer/consumer kernel (FQ_TILE_KERNEL=s: the phase-serialised one)
-  if (const char* e = std::getenv("FQ_TILE_THREADS"))
-    if (std::atoi(e) == 256) c = TileConfig{256, size_t(113) * 1024 - 256, false};
-  if (const char* e = std::getenv("FQ_TILE_KERNEL")) {
-    if (e[0] == 'w') c = TileConfig{kWsThreads, size_t(227) * 1024 - 256, true};
-    if (e[0] == 's') c.alt = false;  // same plan (16 streaming warps, one slab, tiles of <= 512 cells), 512-thread kernel
-  }
-  if (c.alt)
-    if (const char* e = std::getenv("FQ_ALT_CONSUMERS")) {  // tuning: 20 or 24 consumer warps (larger ring, smaller tiles)
-      const int n = std::atoi(e);
-      if (n == 20 || n == 24) c.stream_warps = n;
-    }
-  return c;
-}
-static size_t tile_fixed_smem(const TileConfig& c) {
-  const size_t nwarps = c.stream_warps ? size_t(c.stream_warps)
-                                       : (c.ws ? size_t(kWsConsumerWarps) : size_t(c.nthreads) / 32);  // warps that stream chunks
-  return nwarps * kSlotsPerWarp * kChunkBytes /*ring*/ + 2048 /*recipes*/ + (nwarps * kSlotsPerWarp + 8) * 8 /*mbarriers*/ +
-         512 /*alignment slack*/;
-}
-int tile_cells_capacity(int ndistinct) {
-  const TileConfig c = tile_config();
-  const size_t slabs = c.ws ? 2 : 1;
-  const int cap = int((c.smem_cta - tile_fixed_smem(c)) / slabs / (size_t(ndistinct) * sizeof(double)));
-  return std::min(cap, c.ws ? 32 * kWsProducerWarps : c.nthreads);  // K1 evaluates one cell per thread in one pass
-}
-static int tile_core_variant() {
-  // default: masses only (54 doubles per 3-D cell -> larger tiles); FQ_TILE_CORE=h also stores dif_both(k+1)
-  const char* e = std::getenv("FQ_TILE_CORE");
-  return (e && e[0] == 'h') ? 1 : 0;
-}
 
-// Recipes of one block over the distinct values of core(n, kc).
-// Returns codes[nslots][no*ni]; mass entry (g, i, j) -> map code.
-static bool build_recipes(int n, int kc, const CoreEntryRt& core, int kind, int g, int& no, int& ni,
-                          std::vector<uint8_t>& codes) {
-  if (kind == KIND_LUMPED) return false;
-  int tg, rg;
-  kind_grades(kind, g, tg, rg);
-  const int rows = nlocal(n, tg), cols = nlocal(n, rg);
-  const int nslots = rows * cols;
-  (void)kc;
-  if (g < 0 || g > n || nslots == 0) {  // zero space: every entry is an exact zero
-    no = 0;
-    ni = 0;
-    codes.clear();
-    return true;
-  }
-  if (core.ndistinct > 127) return false;
-  auto direct_code = [&](int m) -> int { return m < 0 ? 0xFF : ((m & 0xFF) | ((m & 0x100) ? 0x80 : 0)); };
-  const int doff = stored_offset(core, kind, g);
-  if (doff >= 0) {  // the block itself is stored: every slot is one signed stored value
-    no = 1, ni = 1;
-    codes.resize(size_t(nslots));
-    for (int sl = 0; sl < nslots; ++sl) codes[size_t(sl)] = uint8_t(direct_code(core.map[doff + sl]));
-    return true;
-  }
-  // otherwise a sandwich of the stored mass of grade g
-  const int off = stored_offset(core, KIND_MASS, g);
-  if (off < 0 || kind == KIND_MASS) return false;
-  const int nd = nlocal(n, g);
-  auto mcode = [&](int i, int j, int sign) -> int {  // signed mass entry -> code or -1 (zero)
-    const int m = core.map[off + i * nd + j];
-    if (m < 0) return 0xFF;
-    const int slot = m & 0xFF;
-    const bool neg = ((m & 0x100) != 0) != (sign < 0);
-    return slot | (neg ? 0x80 : 0);
-  };
-  // boundary operator rows -> list of (coface index, sign), ascending
-  struct Inc {
-    int idx, sign;
-  };
-  std::vector<std::vector<Inc>> brow;  // brow[face] = its cofaces of grade g
-  if (kind != KIND_MASS) {
-    brow.assign(size_t(nlocal(n, g - 1)), {});
-    const auto cof = colex_subsets(n + 1, g + 1);
-    for (size_t ic = 0; ic < cof.size(); ++ic) {
-      const auto el = mask_elems(cof[ic]);
-      for (size_t pos = 0; pos < el.size(); ++pos) {
-        const uint32_t face = cof[ic] & ~(1u << el[pos]);
-        brow[size_t(colex_rank(face))].push_back(Inc{int(ic), (pos & 1) ? -1 : 1});
-      }
+// Per-grade row-slot budgets of a tile.  A row slot is one (cell visit, owned local row) pair; an interior Kuhn vertex
+// brings S_g = dim! * C(dim+1, g+1) of them for grade g.  The slab holds sum_g RSmax_g * D_g doubles, D_g = the column
+// slots of the blocks with test grade g and RSmax_g the largest row-slot count over ALL tiles (the regions are the
+// same for every tile), so each tile is limited per grade: R_g = V* * S_g with V* the number of interior vertices the
+// most demanding Hodge set of this dimension can hold.  Then any Hodge set (and any single block) fits.
+struct DimCost {
+  double vstar = 0;
+  std::vector<double> budget;   // [grade] row slots
+  std::vector<double> max_nr;   // [grade] widest block (columns) with this test grade: entries per row slot
+};
+static const DimCost& dim_cost(int dim) {
+  static std::mutex mu;
+  static std::map<int, DimCost> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(dim);
+  if (it != cache.end()) return it->second;
+  DimCost dc;
+  dc.budget.assign(size_t(dim) + 1, 0.0);
+  dc.max_nr.assign(size_t(dim) + 1, 0.0);
+  double worst = 1;
+  for (int k = 0; k <= dim; ++k) {
+    const SetDesc S = make_set(dim, hodge_blocks(k));
+    double per_vertex = 0;
+    for (int b = 0; b < S.nblocks; ++b) {
+      const BlockDesc& B = S.blk[b];
+      if (B.empty) continue;
+      per_vertex += double(fact(dim)) * double(binom(dim + 1, B.tg + 1)) * B.d;
+      dc.max_nr[size_t(B.tg)] = std::max(dc.max_nr[size_t(B.tg)], double(B.nr));
     }
-    for (auto& r : brow) std::sort(r.begin(), r.end(), [](const Inc& a, const Inc& b) { return a.idx < b.idx; });
+    worst = std::max(worst, per_vertex);
   }
-  const int ncof = (kind == KIND_MASS) ? 1 : (n + 1 - g);
-  if (kind == KIND_MASS) {
-    no = 1, ni = 1;
-  } else if (kind == KIND_DIF_BOTH) {
-    no = ncof, ni = ncof;
-  } else {
-    no = 1, ni = ncof;
+  dc.vstar = std::floor(double(kSlabCapacity - kZeroSlots) / worst);
+  for (int g = 0; g <= dim; ++g) {
+    const double sg = double(fact(dim)) * double(binom(dim + 1, g + 1));
+    dc.budget[size_t(g)] = dc.vstar * sg;
+    // one block's entries in a tile must also fit the builder's sort
+    if (dc.max_nr[size_t(g)] > 0) dc.budget[size_t(g)] = std::min(dc.budget[size_t(g)], std::floor(double(kMaxEntries) / dc.max_nr[size_t(g)]));
   }
-  codes.assign(size_t(nslots) * no * ni, 0xFF);
-  for (int r = 0; r < rows; ++r)
-    for (int c = 0; c < cols; ++c) {
-      uint8_t* out = codes.data() + size_t(r * cols + c) * no * ni;
-      if (kind == KIND_MASS) {
-        out[0] = uint8_t(mcode(r, c, 1));
-      } else if (kind == KIND_DIF_TRIAL) {  // (M * B^T)[r][c] = sum_m M[r][m] * B[c][m]
-        const auto& bc = brow[size_t(c)];
-        for (size_t q = 0; q < bc.size(); ++q) out[q] = uint8_t(mcode(r, bc[q].idx, bc[q].sign));
-      } else if (kind == KIND_DIF_TEST) {  // (B * M)[r][c] = sum_k B[r][k] * M[k][c]
-        const auto& br = brow[size_t(r)];
-        for (size_t q = 0; q < br.size(); ++q) out[q] = uint8_t(mcode(br[q].idx, c, br[q].sign));
-      } else {  // B * (M * B^T): outer over k (cofaces of r), inner over m (cofaces of c)
-        const auto& br = brow[size_t(r)];
-        const auto& bc = brow[size_t(c)];
-        for (size_t o = 0; o < br.size(); ++o)
-          for (size_t q = 0; q < bc.size(); ++q)
-            out[o * size_t(ni) + q] = uint8_t(mcode(br[o].idx, bc[q].idx, br[o].sign * bc[q].sign));
-      }
-    }
-  return true;
+  return cache.emplace(dim, dc).first->second;
 }
-
 
 // ---- vertex clustering -------------------------------------------------------
 __global__ void vtile_kuhn_kernel(int n, const uint32_t* __restrict__ nv /*[n] vertices per axis*/,
@@ -1045,6 +970,192 @@ __global__ void vtile_kuhn_kernel(int n, const uint32_t* __restrict__ nv /*[n] v
   }
 }
 
+template <class T>
+static void upload_vec(DevBuf<T>& d, const std::vector<T>& h) {
+  d.alloc(h.size() ? h.size() : 1);
+  // blocks may be recycled by the caching allocator: order this blocking copy after everything in flight
+  FQ_CUDA(cudaDeviceSynchronize());
+  if (!h.empty()) FQ_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+static uint32_t read_u32(fq_ctx* ctx, const uint32_t* p) {
+  uint32_t v = 0;
+  FQ_CUDA(cudaMemcpyAsync(&v, p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return v;
+}
+// in-place exclusive scan of n + 1 values (the last one is a zero pad); returns the total
+static uint32_t exclusive_scan_inplace(fq_ctx* ctx, uint32_t* a, size_t n_plus_1) {
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a, a, int64_t(n_plus_1), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, a, a, int64_t(n_plus_1), ctx->stream));
+  fq_count_launch(ctx, 2);
+  return read_u32(ctx, a + (n_plus_1 - 1));
+}
+
+// Closed-form vertex bricks on a Kuhn grid: the largest brick (most owned vertices, then fewest cell visits) whose
+// slab, cell visits and per-block entries fit the kernel's limits for every Hodge set of this dimension.
+void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held) {
+  if (dim > 3 || std::getenv("FQ_NO_TILE")) return;
+  const DimCost& dc = dim_cost(dim);
+  double vmax = dc.vstar;  // owned vertices of a brick: every grade's budget in units of interior vertices
+  for (int g = 0; g <= dim; ++g) vmax = std::min(vmax, std::floor(dc.budget[size_t(g)] / (double(fact(dim)) * double(binom(dim + 1, g + 1)))));
+  std::vector<uint32_t> brick(size_t(dim), 1);
+  // exact count for a brick in the interior of the grid: boxes with origin in prod [-1, b_a - 1], dim! chains each
+  auto cells_touching = [&](const std::vector<uint32_t>& b) {
+    std::vector<int> perm(size_t(dim), 0);
+    uint64_t count = 0;
+    std::vector<int> o(size_t(dim), -1);
+    for (;;) {
+      for (int a = 0; a < dim; ++a) perm[size_t(a)] = a;
+      do {
+        std::vector<int> v = o;
+        bool hit = true;
+        for (int a = 0; a < dim; ++a) hit = hit && v[size_t(a)] >= 0 && v[size_t(a)] < int(b[size_t(a)]);
+        for (int step = 0; step < dim && !hit; ++step) {
+          v[size_t(perm[size_t(step)])] += 1;
+          bool in = true;
+          for (int a = 0; a < dim; ++a) in = in && v[size_t(a)] >= 0 && v[size_t(a)] < int(b[size_t(a)]);
+          hit = in;
+        }
+        if (hit) ++count;
+      } while (std::next_permutation(perm.begin(), perm.end()));
+      int a = 0;
+      while (a < dim && ++o[size_t(a)] >= int(b[size_t(a)])) o[size_t(a++)] = -1;
+      if (a == dim) break;
+    }
+    return count;
+  };
+  auto fits = [&](const std::vector<uint32_t>& b) {
+    double owned = 1;
+    for (int a = 0; a < dim; ++a) owned *= b[size_t(a)];
+    return owned <= vmax && cells_touching(b) <= uint64_t(kMaxCv);
+  };
+  if (const char* env = std::getenv("FQ_TILE_BRICK")) {
+    int a = 0;
+    const char* p = env;
+    while (*p && a < dim) {
+      brick[size_t(a++)] = uint32_t(std::max(1l, std::strtol(p, const_cast<char**>(&p), 10)));
+      if (*p == ',') ++p;
+    }
+  } else {
+    // greedy: grow the axis that keeps the halo ratio smallest while the tile fits
+    for (;;) {
+      int best = -1;
+      double best_ratio = 1e300;
+      for (int a = 0; a < dim; ++a) {
+        if (brick[size_t(a)] >= shape[a] + 1) continue;
+        uint64_t owned = 1;
+        std::vector<uint32_t> cand = brick;
+        cand[size_t(a)] += 1;
+        for (int b = 0; b < dim; ++b) owned *= cand[size_t(b)];
+        if (!fits(cand)) continue;
+        const double ratio = double(cells_touching(cand)) / double(owned);
+        // prefer the lower axis on ties (longer contiguous CSR runs)
+        if (ratio < best_ratio - 1e-12) best_ratio = ratio, best = a;
+      }
+      if (best < 0) break;
+      brick[size_t(best)] += 1;
+    }
+  }
+  std::vector<uint32_t> nv(static_cast<size_t>(dim), 0u), nb(static_cast<size_t>(dim), 0u);
+  const uint32_t z_lo = uint32_t(slab_begin);
+  uint64_t ntiles = 1, layer = 1;
+  for (int a = 0; a < dim; ++a) {
+    nv[size_t(a)] = uint32_t(shape[a] + 1);
+    const uint64_t ext = (a == dim - 1) ? (slab_end_held - slab_begin + 1) : (shape[a] + 1);
+    nb[size_t(a)] = uint32_t((ext + brick[size_t(a)] - 1) / brick[size_t(a)]);
+    ntiles *= nb[size_t(a)];
+    if (a < dim - 1) layer *= shape[a] + 1;
+  }
+  FQ_REQUIRE(ntiles < (1ull << 31), "too many tiles");
+  const uint64_t v_lo = layer * slab_begin, v_hi = layer * (slab_end_held + 1);
+  DevBuf<uint32_t> d_nv, d_brick, d_nb;
+  upload_vec(d_nv, nv);
+  upload_vec(d_brick, brick);
+  upload_vec(d_nb, nb);
+  mesh->vertex_tile.alloc(size_t(v_hi - v_lo));
+  mesh->vtile_lo = size_t(v_lo);
+  mesh->ntiles = size_t(ntiles);
+  vtile_kuhn_kernel<<<grid_for(v_hi - v_lo, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+      dim, d_nv.p, d_brick.p, d_nb.p, v_lo, v_hi, z_lo, mesh->vertex_tile.p);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// Generic meshes: greedy breadth-first growth of vertex clusters on the host (once per mesh), each limited by the
+// slab doubles, cell visits and per-block entries it may need.  cell_verts is the grade-0 face table.
+void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh) {
+  const int dim = mesh->dim;
+  mesh->cluster_tried = true;
+  if (dim > 3 || std::getenv("FQ_NO_TILE") || !mesh->cell_faces[0].p || mesh->edge_lo != 0 || mesh->cell_offset != 0) return;
+  std::vector<uint32_t> cell_verts(mesh->cell_faces[0].n);
+  FQ_CUDA(cudaMemcpyAsync(cell_verts.data(), mesh->cell_faces[0].p, cell_verts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  const DimCost& dc = dim_cost(dim);
+  const size_t nv = size_t(dim) + 1, ncells = mesh->ncells, V = mesh->nsimplices[0];
+  if (V == 0 || ncells == 0 || V >= (size_t(1) << 32)) return;
+  // vertex -> cells incidence (CSR)
+  std::vector<uint32_t> vptr(V + 1, 0);
+  for (size_t i = 0; i < ncells * nv; ++i) {
+    if (cell_verts[i] >= V) return;  // malformed table: leave the mesh unclustered (slab path)
+    vptr[size_t(cell_verts[i]) + 1] += 1;
+  }
+  for (size_t v = 0; v < V; ++v) vptr[v + 1] += vptr[v];
+  std::vector<uint32_t> vcells(ncells * nv), fill(vptr.begin(), vptr.end() - 1);
+  std::vector<uint8_t> vpos(ncells * nv);
+  for (size_t c = 0; c < ncells; ++c)
+    for (size_t j = 0; j < nv; ++j) {
+      const uint32_t at = fill[size_t(cell_verts[c * nv + j])]++;
+      vcells[at] = uint32_t(c);
+      vpos[at] = uint8_t(j);
+    }
+  const uint32_t kNone = 0xFFFFFFFFu;
+  std::vector<uint32_t> vtile(V, kNone), stamp(ncells, kNone), queue;
+  uint32_t ntiles = 0;
+  for (size_t seed = 0; seed < V; ++seed) {
+    if (vtile[seed] != kNone) continue;
+    const uint32_t T = ntiles++;
+    uint32_t ncells_T = 0;
+    double rs_T[4] = {0, 0, 0, 0};
+    queue.clear();
+    queue.push_back(uint32_t(seed));
+    for (size_t head = 0; head < queue.size(); ++head) {
+      const uint32_t v = queue[head];
+      if (vtile[v] != kNone) continue;
+      uint32_t fresh = 0;
+      double rs_v[4] = {0, 0, 0, 0};
+      for (uint32_t p = vptr[v]; p < vptr[v + 1]; ++p) {
+        fresh += stamp[vcells[p]] != T;
+        for (int g = 0; g <= dim; ++g) rs_v[g] += double(binom(vpos[p], g));  // faces of grade g with this vertex on top
+      }
+      bool fits = ncells_T + fresh <= uint32_t(kMaxCv);
+      for (int g = 0; g <= dim; ++g) fits = fits && rs_T[g] + rs_v[g] <= dc.budget[size_t(g)];
+      if (ncells_T > 0 && !fits) continue;  // does not fit: left for a later tile
+      vtile[v] = T;
+      ncells_T += fresh;
+      for (int g = 0; g <= dim; ++g) rs_T[g] += rs_v[g];
+      for (uint32_t p = vptr[v]; p < vptr[v + 1]; ++p) {
+        const uint32_t c = vcells[p];
+        if (stamp[c] == T) continue;
+        stamp[c] = T;
+        for (size_t j = 0; j < nv; ++j) {
+          const uint32_t w = uint32_t(cell_verts[size_t(c) * nv + j]);
+          if (vtile[w] == kNone) queue.push_back(w);
+        }
+      }
+    }
+  }
+  mesh->vertex_tile.alloc(V);
+  mesh->vtile_lo = 0;
+  mesh->ntiles = ntiles;
+  FQ_CUDA(cudaMemcpyAsync(mesh->vertex_tile.p, vtile.data(), V * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- cell visits of every tile ------------------------------------------------
 // one key per (cell, distinct vertex tile): (tile << 32) | cell, ~0 for duplicates
 __global__ void tile_cell_keys_kernel(const uint32_t* __restrict__ cell_verts, int nv, size_t ncells,
                                       const uint32_t* __restrict__ vtile, uint32_t v_lo, uint64_t* __restrict__ keys) {
@@ -1080,1004 +1191,294 @@ __global__ void seg_ptr_kernel(const uint32_t* __restrict__ key, size_t n, uint3
     for (uint32_t t = lo; t <= hi && t <= nseg; ++t) ptr[t] = uint32_t(i);
   }
 }
-// type-major slot order inside every tile: key = tile | cell type | cell
-__global__ void tile_slot_keys_kernel(const uint32_t* __restrict__ tile_of, const uint32_t* __restrict__ tile_cells, size_t n,
-                                      uint32_t period, uint64_t cell_offset, uint64_t* __restrict__ keys,
-                                      uint32_t* __restrict__ pos) {
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint64_t type = period ? (cell_offset + tile_cells[i]) % period : 0;
-    keys[i] = (uint64_t(tile_of[i]) << 35) | (type << 32) | uint64_t(tile_cells[i]);
-    pos[i] = uint32_t(i);
-  }
-}
-// after the sort: slot i holds the cell at (tile, cell)-sorted position pos[i]
-__global__ void tile_slots_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, size_t n,
-                                  const uint32_t* __restrict__ tile_cell_ptr, uint32_t* __restrict__ cells_by_slot,
-                                  uint32_t* __restrict__ local_of_pos) {
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t t = uint32_t(keys[i] >> 35);
-    cells_by_slot[i] = uint32_t(keys[i]);
-    local_of_pos[pos[i]] = uint32_t(i) - tile_cell_ptr[t];
-  }
-}
-__global__ void tile_cell_edges_kernel(const uint32_t* __restrict__ tile_cells, size_t n, const uint32_t* __restrict__ cell_edges,
-                                       int ne, uint32_t* __restrict__ out) {
-  const size_t total = n * size_t(ne);
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x; p < total; p += stride)
-    out[p] = cell_edges[size_t(tile_cells[p / size_t(ne)]) * ne + p % size_t(ne)];
-}
-
-// row -> tile of its top vertex
-__global__ void row_tile_kernel(const uint32_t* __restrict__ faces, int nl, const uint32_t* __restrict__ cell_verts, int nv,
-                                const uint8_t* __restrict__ top_pos, size_t ncells, const uint32_t* __restrict__ vtile,
-                                uint32_t v_lo, uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ row_tile) {
-  const size_t total = ncells * size_t(nl);
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x; p < total; p += stride) {
-    const size_t c = p / size_t(nl);
-    const int i = int(p % size_t(nl));
-    const uint32_t row = faces[p];
-    if (row < row_begin || row >= row_end) continue;
-    row_tile[row - row_begin] = vtile[cell_verts[c * nv + top_pos[i]] - v_lo];
-  }
-}
-// sort key of every structural non-zero: tile | L | signature of its slot sequence
-__global__ void nnz_key_kernel(const uint32_t* __restrict__ row_ptr, uint32_t nrows, const uint32_t* __restrict__ row_tile,
-                               const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
-                               int use_sig, const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
-                               const uint32_t* __restrict__ tile_local, uint64_t* __restrict__ key,
-                               uint32_t* __restrict__ nnz_id, int* __restrict__ err) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
-    const uint64_t t = row_tile[r];
-    for (uint32_t q = row_ptr[r]; q < row_ptr[r + 1]; ++q) {
-      const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
-      uint32_t L = p1 - p0;
-      if (L > uint32_t(kMaxLen)) {  // does not fit a 32-lane record of one chunk: the slab path handles this mesh
-        atomicExch(err, 4);
-        L = kMaxLen;
-      }
-      uint32_t sig = 0;
-      if (use_sig) {  // "type" of the non-zero: its slot sequence and the relative cell offsets of its contributions
-        const uint32_t cell0 = contrib_src[p0] / T;
-        for (uint32_t p = p0; p < p1; ++p) {
-          const uint32_t cell = contrib_src[p] / T;
-          sig = (sig * 131u + (contrib_src[p] - cell * T) + 1u) * 31u + (cell - cell0);
-        }
-      }
-      sig = (sig ^ (sig >> 16)) & 0xFFFFu;
-      // shared-memory bank (8-byte units, 16 per wavefront) of the slab slot of the first contributing cell
-      uint32_t bank = 0;
-      if (tile_local) {
-        const uint32_t cell = contrib_src[p0] / T;
-        uint32_t lo = tile_cell_ptr[t], hi = tile_cell_ptr[t + 1];
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (tile_cells[mid] < cell)
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        bank = tile_local[lo] & 15u;
-      }
-      // tile | L | signature | occurrence (filled in later) | bank
-      key[q] = (t << 36) | (uint64_t(L) << 28) | (uint64_t(sig) << 12) | bank;
-      nnz_id[q] = q;
-    }
-  }
-}
-// Bank interleaving: within a group of equal (tile, L, signature, bank) the k-th member gets occurrence k; sorting by
-// (.., occurrence, bank) then makes consecutive lanes of a record hit different banks of the slab.
-__global__ void group_start_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ start) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    start[i] = (i == 0 || key[i] != key[i - 1]) ? i : 0u;
-}
-__global__ void occurrence_kernel(uint64_t* __restrict__ key, uint32_t n, const uint32_t* __restrict__ start_scan) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t occ = min(i - start_scan[i], 255u);
-    key[i] |= uint64_t(occ) << 4;
-  }
-}
-__global__ void run_heads_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ head) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    head[i] = (i == 0 || (key[i] >> 28) != (key[i - 1] >> 28)) ? 1u : 0u;
-}
-// run r: start, tile, L
-__global__ void run_info_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ head,
-                                const uint32_t* __restrict__ run_scan /*inclusive*/, uint32_t n, uint32_t* __restrict__ run_start,
-                                uint32_t* __restrict__ run_tile, uint32_t* __restrict__ run_len_code) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    if (head[i]) {
-      const uint32_t r = run_scan[i] - 1;
-      run_start[r] = i;
-      run_tile[r] = uint32_t(key[i] >> 36);
-      run_len_code[r] = uint32_t(key[i] >> 28) & 0xFFu;
-    }
-}
-// ---- bank-aware lane packing ---------------------------------------------------------------------------------------
-// The gather's dominant cost is shared-memory wavefronts of the 8-byte slab loads: 32 lanes read slab[value * cstride +
-// cell slot], served as two half-warps of 16 lanes over 16 8-byte bank pairs.  With cstride a multiple of 16 the bank pair
-// of EVERY load of a contribution is (cell slot mod 16), whatever value it reads, so a half-warp is conflict-free at
-// step j iff its 16 lanes' j-th contributing cells have distinct slots mod 16.  One thread per (tile, L) run deals its
-// non-zeros to the half-warp bins of the records the run occupies anyway (first fit: a bin accepts a non-zero when
-// none of its L residues is taken yet); what fits nowhere goes to the free lane where it collides least.  Positions are
-// a permutation of the lanes the run already had plus its padding lanes: the stream does not grow, the sums do not
-// change (each lane still adds its own contributions in ascending cell order).
-constexpr int kPackMaxBins = 160, kPackMaxLen = 24;
-__global__ void pack_runs_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ run_start,
-                                 const uint32_t* __restrict__ run_tile, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
-                                 const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
-                                 const uint32_t* __restrict__ tile_cell_ptr, const uint32_t* __restrict__ tile_cells,
-                                 const uint32_t* __restrict__ tile_local, int enable, uint32_t* __restrict__ ppos,
-                                 unsigned long long* __restrict__ stats /*optional: items, contributions, dense collisions, packed collisions, unplaced*/) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride) {
-    const uint32_t r0 = run_start[r], r1 = run_start[r + 1], ntot = r1 - r0;
-    const uint32_t L = run_len_code[r];
-    const uint32_t lanes = rec_lanes(L);
-    const uint32_t nb_tot = (ntot + lanes - 1u) / lanes * (lanes / 16u);  // half-warp bins of the records the run occupies
-    if (!enable || L == 0 || L > uint32_t(kPackMaxLen) || ntot <= 1) {
-      for (uint32_t i = r0; i < r1; ++i) ppos[i] = i - r0;
-      continue;
-    }
-    const uint32_t t = run_tile[r];
-    const uint32_t cb = tile_cell_ptr[t], ce = tile_cell_ptr[t + 1];
-    auto residues = [&](uint32_t q, uint8_t* res) {  // slot mod 16 of every contributing cell of non-zero q
-      const uint32_t p0 = contrib_ptr[q];
-      for (uint32_t j = 0; j < L; ++j) {
-        const uint32_t cell = contrib_src[p0 + j] / T;
-        uint32_t lo = cb, hi = ce;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (tile_cells[mid] < cell)
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        res[j] = uint8_t(lo < ce ? (tile_local[lo] & 15u) : 0u);
-      }
-    };
-    uint16_t mask[kPackMaxBins][kPackMaxLen];
-    uint8_t cnt[kPackMaxBins];
-    uint8_t res[kPackMaxLen];
-    // long runs are dealt segment by segment (kPackMaxBins bins each; only the last one owns the run's padding lanes)
-    constexpr uint32_t kSeg = uint32_t(kPackMaxBins) * 16u;
-    for (uint32_t s0 = 0; s0 < ntot; s0 += kSeg) {
-      const uint32_t i0 = r0 + s0, n = min(kSeg, ntot - s0), i1 = i0 + n;
-      const uint32_t nb = min(uint32_t(kPackMaxBins), nb_tot - s0 / 16u);
-      auto clear = [&]() {
-        for (uint32_t b = 0; b < nb; ++b) {
-          cnt[b] = 0;
-          for (uint32_t j = 0; j < L; ++j) mask[b][j] = 0;
-        }
-      };
-      clear();
-      if (stats) {  // collisions of the dense order (lane = position in the run), for comparison
-        unsigned long long coll = 0;
-        for (uint32_t i = i0; i < i1; ++i) {
-          residues(perm[i], res);
-          const uint32_t b = (i - i0) / 16u;
-          for (uint32_t j = 0; j < L; ++j) {
-            coll += (mask[b][j] >> res[j]) & 1u;
-            mask[b][j] |= uint16_t(1u << res[j]);
-          }
-        }
-        atomicAdd(stats + 0, (unsigned long long)n);
-        atomicAdd(stats + 1, (unsigned long long)n * L);
-        atomicAdd(stats + 2, coll);
-        clear();
-      }
-      uint32_t first_open = 0, nleft = 0;
-      unsigned long long pcoll = 0;
-      for (uint32_t i = i0; i < i1; ++i) {
-        residues(perm[i], res);
-        while (first_open < nb && cnt[first_open] >= 16) ++first_open;
-        uint32_t where = 0xFFFFFFFFu;
-        for (uint32_t b = first_open; b < nb; ++b) {
-          if (cnt[b] >= 16) continue;
-          bool ok = true;
-          for (uint32_t j = 0; j < L; ++j) ok = ok && !((mask[b][j] >> res[j]) & 1u);
-          if (ok) {
-            where = b;
-            break;
-          }
-        }
-        if (where == 0xFFFFFFFFu) {
-          ppos[i] = 0xFFFFFFFFu;
-          ++nleft;
-          continue;
-        }
-        for (uint32_t j = 0; j < L; ++j) mask[where][j] |= uint16_t(1u << res[j]);
-        ppos[i] = s0 + where * 16u + cnt[where]++;
-      }
-      for (uint32_t i = i0; i < i1 && nleft; ++i) {  // the rest: the free lane with the fewest collisions
-        if (ppos[i] != 0xFFFFFFFFu) continue;
-        residues(perm[i], res);
-        uint32_t best = 0xFFFFFFFFu, best_cost = 0xFFFFFFFFu;
-        for (uint32_t b = 0; b < nb; ++b) {
-          if (cnt[b] >= 16) continue;
-          uint32_t cost = 0;
-          for (uint32_t j = 0; j < L; ++j) cost += (mask[b][j] >> res[j]) & 1u;
-          if (cost < best_cost) best_cost = cost, best = b;
-        }
-        for (uint32_t j = 0; j < L; ++j) mask[best][j] |= uint16_t(1u << res[j]);
-        ppos[i] = s0 + best * 16u + cnt[best]++;
-        --nleft;
-        pcoll += best_cost;
-        if (stats) atomicAdd(stats + 4, 1ull);
-      }
-      if (stats) atomicAdd(stats + 3, pcoll);
-    }
-  }
-}
-__global__ void run_nrec_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
-                                uint32_t* __restrict__ nrec) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nruns; r += stride) {
-    if (r == nruns) {
-      nrec[r] = 0u;
-      continue;
-    }
-    const uint32_t lanes = rec_lanes(run_len_code[r]);
-    nrec[r] = (run_start[r + 1] - run_start[r] + lanes - 1u) / lanes;
-  }
-}
-__global__ void rec_len_kernel(const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ run_len_code, uint32_t nruns,
-                               uint8_t* __restrict__ rec_len) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride)
-    for (uint32_t k = rec_base[r]; k < rec_base[r + 1]; ++k) rec_len[k] = uint8_t(run_len_code[r]);
-}
-__global__ void gather_u32_kernel(const uint32_t* __restrict__ idx, uint32_t n, const uint32_t* __restrict__ src,
-                                  uint32_t* __restrict__ out) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = src[idx[i]];
-}
-
-struct TileLayoutBlock {
-  const uint32_t* rec_tile_ptr;  // [ntiles+1] first record of every tile
-  const uint8_t* rec_len;        // [nrec]
-  uint32_t* rec_rel;             // [nrec] out: byte offset / 16 of the record within the tile's stream
-};
-struct TileLayoutArgs {
-  TileLayoutBlock blk[kTileMaxBlocks];
-  int nblocks;
-};
-// One thread per tile packs its records into chunks (a record never straddles a chunk).
-// pass 0: chunk count of the tile;  pass 1: record offsets, record and chunk headers written into the stream.
-__global__ void tile_layout_kernel(TileLayoutArgs A, uint32_t ntiles, int pass, uint32_t* __restrict__ tile_nchunks,
-                                   const uint32_t* __restrict__ tile_chunk_ptr, unsigned char* __restrict__ stream) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
-    uint32_t off = 0;          // byte offset within the tile's stream; 0 = no chunk opened yet
-    uint32_t in_chunk = 0;     // records in the open chunk
-    unsigned char* base = pass ? stream + size_t(tile_chunk_ptr[t]) * kChunkBytes : nullptr;
-    for (int b = 0; b < A.nblocks; ++b) {
-      const TileLayoutBlock& B = A.blk[b];
-      for (uint32_t k = B.rec_tile_ptr[t]; k < B.rec_tile_ptr[t + 1]; ++k) {
-        const uint32_t L = B.rec_len[k];
-        const uint32_t size = rec_bytes(L);
-        const uint32_t chunk = off / kChunkBytes;
-        if (off % kChunkBytes == 0 || off + size > (chunk + 1) * kChunkBytes) {  // open a new chunk
-          if (off % kChunkBytes != 0) {
-            if (pass) *reinterpret_cast<uint32_t*>(base + size_t(chunk) * kChunkBytes) = in_chunk;
-            off = (chunk + 1) * kChunkBytes;
-          }
-          off += kChunkHdr;
-          in_chunk = 0;
-        }
-        if (pass) {
-          B.rec_rel[k] = off / 16u;
-          *reinterpret_cast<uint32_t*>(base + off) = L | (uint32_t(b) << 8) | (rec_lanes(L) << 16);
-        }
-        off += size;
-        ++in_chunk;
-      }
-    }
-    if (off % kChunkBytes != 0) {
-      if (pass) *reinterpret_cast<uint32_t*>(base + size_t(off / kChunkBytes) * kChunkBytes) = in_chunk;
-      off = (off / kChunkBytes + 1) * kChunkBytes;
-    }
-    if (!pass) tile_nchunks[t] = off / kChunkBytes;
-  }
-}
-// One thread per (sorted) non-zero: its lane of its record.
-__global__ void stream_fill_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ ppos, uint32_t n,
-                                   const uint32_t* __restrict__ run_scan,
-                                   const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_tile,
-                                   const uint32_t* __restrict__ run_len_code, const uint32_t* __restrict__ rec_base,
-                                   const uint32_t* __restrict__ rec_rel, const uint32_t* __restrict__ tile_chunk_ptr,
-                                   const uint32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib_src, uint32_t T,
-                                   int slot_bits, const uint32_t* __restrict__ tile_cell_ptr,
-                                   const uint32_t* __restrict__ tile_cells, const uint32_t* __restrict__ tile_local,
-                                   const uint8_t* __restrict__ keep,
-                                   const uint32_t* __restrict__ pos, int drop,
-                                   const uint16_t* __restrict__ direct_map /*stored blocks: slot -> sign | slab offset*/,
-                                   unsigned char* __restrict__ stream, int* __restrict__ err) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t q = perm[i];
-    const uint32_t r = run_scan[i] - 1;
-    const uint32_t idx = ppos[i];  // lane of the run dealt by pack_runs_kernel (i - run_start[r] when packing is off)
-    const uint32_t lanes = rec_lanes(run_len_code[r]);
-    const uint32_t k = rec_base[r] + idx / lanes, lane = idx % lanes;
-    const uint32_t t = run_tile[r];
-    unsigned char* rp = stream + size_t(tile_chunk_ptr[t]) * kChunkBytes + size_t(rec_rel[k]) * 16u + kRecHdr;
-    reinterpret_cast<uint32_t*>(rp)[lane] = drop ? (keep[q] ? pos[q] + 2u : kNoDest) : q + 2u;
-    uint16_t* ent = reinterpret_cast<uint16_t*>(rp + 4u * lanes) + lane;
-    const uint32_t p0 = contrib_ptr[q], p1 = contrib_ptr[q + 1];
-    const uint32_t cb = tile_cell_ptr[t], ce = tile_cell_ptr[t + 1];
-    for (uint32_t p = p0; p < p1 && p - p0 < uint32_t(kMaxLen); ++p) {
-      const uint32_t src = contrib_src[p];
-      const uint32_t cell = src / T, slot = src - cell * T;
-      uint32_t lo = cb, hi = ce;  // first index with tile_cells[idx] >= cell
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (tile_cells[mid] < cell)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      if (lo >= ce || tile_cells[lo] != cell) {
-        atomicExch(err, 2);
-        continue;
-      }
-      const uint32_t local = tile_local[lo];
-      if (direct_map) {
-        const uint32_t code = direct_map[slot];
-        if ((code & 0x7FFFu) + local > 0x7FFFu) atomicExch(err, 3);
-        ent[(p - p0) * lanes] = uint16_t((code & 0x8000u) | ((code & 0x7FFFu) + local));
-      } else {
-        if ((local << slot_bits) > 0xFFFFu) atomicExch(err, 3);
-        ent[(p - p0) * lanes] = uint16_t((local << slot_bits) | slot);
-      }
-    }
-  }
-}
-
 static int bits_for32(uint64_t n) {
   int b = 1;
   while ((1ull << b) < n) ++b;
   return b;
 }
-
-template <class T>
-static void upload_vec(DevBuf<T>& d, const std::vector<T>& h) {
-  d.alloc(h.size() ? h.size() : 1);
-  // blocks may be recycled by the caching allocator: order this blocking copy after everything in flight
-  FQ_CUDA(cudaDeviceSynchronize());
-  if (!h.empty()) FQ_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-}
-static uint32_t read_u32(fq_ctx* ctx, const uint32_t* p) {
-  uint32_t v = 0;
-  FQ_CUDA(cudaMemcpyAsync(&v, p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  return v;
-}
-static void exclusive_scan_u32(fq_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n) {
-  size_t tmp_bytes = 0;
-  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, int64_t(n), ctx->stream));
-  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
-  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, int64_t(n), ctx->stream));
-  fq_count_launch(ctx, 2);
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-}
-static void inclusive_scan_u32(fq_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n) {
-  size_t tmp_bytes = 0;
-  FQ_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, int64_t(n), ctx->stream));
-  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
-  FQ_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, in, out, int64_t(n), ctx->stream));
-  fq_count_launch(ctx, 2);
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-}
-
-// Closed-form vertex bricks on a Kuhn grid.
-// Closed-form vertex bricks on a Kuhn grid.
-void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held) {
-  if (dim > 3 || std::getenv("FQ_NO_TILE")) return;
-  int max_distinct = 1;
-  for (const CoreEntryRt& e : g_cores)
-    if (e.n == dim && (tile_core_variant() == 1 || e.variant == 0)) max_distinct = std::max(max_distinct, e.ndistinct);
-  const int cells_capacity = tile_cells_capacity(max_distinct);
-  // brick[a] owned vertices per axis; a tile needs every cell with a vertex in the brick
-  std::vector<uint32_t> brick(size_t(dim), 1);
-  // exact count for a brick in the interior of the grid: boxes with origin in prod [-1, b_a - 1], dim! chains each
-  auto cells_touching = [&](const std::vector<uint32_t>& b) {
-    std::vector<int> perm(size_t(dim), 0);
-    uint64_t count = 0;
-    std::vector<int> o(size_t(dim), -1);
-    for (;;) {
-      for (int a = 0; a < dim; ++a) perm[size_t(a)] = a;
-      do {
-        std::vector<int> v = o;
-        bool hit = true;
-        for (int a = 0; a < dim; ++a) hit = hit && v[size_t(a)] >= 0 && v[size_t(a)] < int(b[size_t(a)]);
-        for (int step = 0; step < dim && !hit; ++step) {
-          v[size_t(perm[size_t(step)])] += 1;
-          bool in = true;
-          for (int a = 0; a < dim; ++a) in = in && v[size_t(a)] >= 0 && v[size_t(a)] < int(b[size_t(a)]);
-          hit = in;
-        }
-        if (hit) ++count;
-      } while (std::next_permutation(perm.begin(), perm.end()));
-      int a = 0;
-      while (a < dim && ++o[size_t(a)] >= int(b[size_t(a)])) o[size_t(a++)] = -1;
-      if (a == dim) break;
-    }
-    return count;
-  };
-  if (const char* env = std::getenv("FQ_TILE_BRICK")) {
-    int a = 0;
-    const char* p = env;
-    while (*p && a < dim) {
-      brick[size_t(a++)] = uint32_t(std::max(1l, std::strtol(p, const_cast<char**>(&p), 10)));
-      if (*p == ',') ++p;
-    }
-  } else {
-    // greedy: grow the axis that keeps the halo ratio smallest while the tile fits
-    for (;;) {
-      int best = -1;
-      double best_ratio = 1e300;
-      for (int a = 0; a < dim; ++a) {
-        if (brick[size_t(a)] >= shape[a] + 1) continue;
-        uint64_t owned = 1;
-        std::vector<uint32_t> cand = brick;
-        cand[size_t(a)] += 1;
-        for (int b = 0; b < dim; ++b) owned *= cand[size_t(b)];
-        const uint64_t ncell = cells_touching(cand);
-        if (ncell > uint64_t(cells_capacity)) continue;
-        const double ratio = double(ncell) / double(owned);
-        // prefer the lower axis on ties (longer contiguous CSR runs)
-        if (ratio < best_ratio - 1e-12) best_ratio = ratio, best = a;
-      }
-      if (best < 0) break;
-      brick[size_t(best)] += 1;
-    }
-  }
-  std::vector<uint32_t> nv(static_cast<size_t>(dim), 0u), nb(static_cast<size_t>(dim), 0u);
-  const uint32_t z_lo = uint32_t(slab_begin);
-  uint64_t ntiles = 1, layer = 1;
-  for (int a = 0; a < dim; ++a) {
-    nv[size_t(a)] = uint32_t(shape[a] + 1);
-    const uint64_t ext = (a == dim - 1) ? (slab_end_held - slab_begin + 1) : (shape[a] + 1);
-    nb[size_t(a)] = uint32_t((ext + brick[size_t(a)] - 1) / brick[size_t(a)]);
-    ntiles *= nb[size_t(a)];
-    if (a < dim - 1) layer *= shape[a] + 1;
-  }
-  FQ_REQUIRE(ntiles < (1ull << 31), "too many tiles");
-  const uint64_t v_lo = layer * slab_begin, v_hi = layer * (slab_end_held + 1);
-  DevBuf<uint32_t> d_nv, d_brick, d_nb;
-  upload_vec(d_nv, nv);
-  upload_vec(d_brick, brick);
-  upload_vec(d_nb, nb);
-  mesh->vertex_tile.alloc(size_t(v_hi - v_lo));
-  mesh->vtile_lo = size_t(v_lo);
-  mesh->ntiles = size_t(ntiles);
-  vtile_kuhn_kernel<<<grid_for(v_hi - v_lo, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-      dim, d_nv.p, d_brick.p, d_nb.p, v_lo, v_hi, z_lo, mesh->vertex_tile.p);
+static void build_cell_visits(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
+  const int nv = mesh->dim + 1, block = 256;
+  const size_t ncells = mesh->ncells, nkeys = ncells * size_t(nv);
+  DevBuf<uint64_t> keys(nkeys ? nkeys : 1), keys_alt(nkeys ? nkeys : 1);
+  tile_cell_keys_kernel<<<grid_for(ncells, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      mesh->cell_faces[0].p, nv, ncells, mesh->vertex_tile.p, uint32_t(mesh->vtile_lo), keys.p);
   fq_count_launch(ctx);
-  FQ_CUDA(cudaGetLastError());
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-}
-
-// Generic meshes: greedy breadth-first growth of vertex clusters on the host (once
-// per mesh), each limited to `capacity` incident cells.  cell_verts is the
-// grade-0 FaceIncidence table ([ncells][dim+1], global vertex ids).
-void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh) {
-  const int dim = mesh->dim;
-  mesh->cluster_tried = true;
-  if (dim > 3 || std::getenv("FQ_NO_TILE") || !mesh->cell_faces[0].p || mesh->edge_lo != 0 || mesh->cell_offset != 0) return;
-  std::vector<uint32_t> cell_verts(mesh->cell_faces[0].n);
-  FQ_CUDA(cudaMemcpyAsync(cell_verts.data(), mesh->cell_faces[0].p, cell_verts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                          ctx->stream));
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  int max_distinct = 1;
-  for (const CoreEntryRt& e : g_cores)
-    if (e.n == dim && (tile_core_variant() == 1 || e.variant == 0)) max_distinct = std::max(max_distinct, e.ndistinct);
-  const uint32_t capacity = uint32_t(tile_cells_capacity(max_distinct));
-  const size_t nv = size_t(dim) + 1, ncells = mesh->ncells, V = mesh->nsimplices[0];
-  if (V == 0 || ncells == 0 || V >= (size_t(1) << 32)) return;
-  // vertex -> cells incidence (CSR)
-  std::vector<uint32_t> vptr(V + 1, 0);
-  for (size_t i = 0; i < ncells * nv; ++i) {
-    if (cell_verts[i] >= V) return;  // malformed table: leave the mesh unclustered (slab path)
-    vptr[size_t(cell_verts[i]) + 1] += 1;
-  }
-  for (size_t v = 0; v < V; ++v) vptr[v + 1] += vptr[v];
-  std::vector<uint32_t> vcells(ncells * nv), fill(vptr.begin(), vptr.end() - 1);
-  for (size_t c = 0; c < ncells; ++c)
-    for (size_t j = 0; j < nv; ++j) vcells[fill[size_t(cell_verts[c * nv + j])]++] = uint32_t(c);
-  const uint32_t kNone = 0xFFFFFFFFu;
-  std::vector<uint32_t> vtile(V, kNone), stamp(ncells, kNone), queue;
-  uint32_t ntiles = 0;
-  for (size_t seed = 0; seed < V; ++seed) {
-    if (vtile[seed] != kNone) continue;
-    const uint32_t T = ntiles++;
-    uint32_t ncells_T = 0;
-    queue.clear();
-    queue.push_back(uint32_t(seed));
-    for (size_t head = 0; head < queue.size(); ++head) {
-      const uint32_t v = queue[head];
-      if (vtile[v] != kNone) continue;
-      uint32_t fresh = 0;
-      for (uint32_t p = vptr[v]; p < vptr[v + 1]; ++p) fresh += stamp[vcells[p]] != T;
-      if (ncells_T > 0 && ncells_T + fresh > capacity) continue;  // does not fit: left for a later tile
-      vtile[v] = T;
-      ncells_T += fresh;
-      for (uint32_t p = vptr[v]; p < vptr[v + 1]; ++p) {
-        const uint32_t c = vcells[p];
-        if (stamp[c] == T) continue;
-        stamp[c] = T;
-        for (size_t j = 0; j < nv; ++j) {
-          const uint32_t w = uint32_t(cell_verts[size_t(c) * nv + j]);
-          if (vtile[w] == kNone) queue.push_back(w);
-        }
-      }
-      if (ncells_T >= capacity) break;
-    }
-  }
-  mesh->vertex_tile.alloc(V);
-  mesh->vtile_lo = 0;
-  mesh->ntiles = ntiles;
-  FQ_CUDA(cudaMemcpyAsync(mesh->vertex_tile.p, vtile.data(), V * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-}
-
-
-static void radix_sort_pairs_u64(fq_ctx* ctx, DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, size_t n, int end_bit) {
-  DevBuf<uint64_t> keys_alt(n ? n : 1);
-  DevBuf<uint32_t> vals_alt(n ? n : 1);
   cub::DoubleBuffer<uint64_t> dk(keys.p, keys_alt.p);
-  cub::DoubleBuffer<uint32_t> dv(vals.p, vals_alt.p);
   size_t tmp_bytes = 0;
-  FQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, int64_t(n), 0, end_bit, ctx->stream));
+  // the all-ones keys of duplicates sort last on any bit range that covers the valid keys
+  const int end_bit = std::min(64, 32 + bits_for32(uint64_t(plan.ntiles) + 1));
+  FQ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dk, int64_t(nkeys), 0, end_bit, ctx->stream));
   DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
-  FQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, int64_t(n), 0, end_bit, ctx->stream));
-  fq_count_launch(ctx, (end_bit + 7) / 8 + 1);
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (dk.Current() != keys.p) std::swap(keys, keys_alt);
-  if (dv.Current() != vals.p) std::swap(vals, vals_alt);
-}
-
-// Per-block intermediate data of the plan build (kept until the stream is filled).
-struct BlockBuild {
-  DevBuf<uint32_t> perm, ppos, run_scan, run_start, run_tile, run_len, rec_base, rec_tile_ptr, rec_rel;
-  DevBuf<uint8_t> rec_len;
-  uint32_t nruns = 0, nrec = 0;
-};
-
-// Picks the core (grade, variant) that can serve every block with the fewest gather terms.
-static const CoreEntryRt* choose_core(int dim, fq_csr* const* csrs, int nblocks) {
-  const int pref = tile_core_variant();
-  const CoreEntryRt* best = nullptr;
-  long best_score = 0;
-  for (const CoreEntryRt& core : g_cores) {
-    if (core.n != dim) continue;
-    if (pref == 0 && core.variant != 0) continue;
-    long score = 0;
-    bool ok = true;
-    for (int b = 0; ok && b < nblocks; ++b) {
-      int no, ni;
-      std::vector<uint8_t> codes;
-      ok = build_recipes(dim, core.k, core, csrs[b]->kind, csrs[b]->grade, no, ni, codes);
-      for (uint8_t c : codes) ok = ok && c != 0xFF;
-      score += long(no) * ni * 1000;
-    }
-    if (!ok) continue;
-    score += core.ndistinct;
-    if (!best || score < best_score) best = &core, best_score = score;
-  }
-  return best;
-}
-
-// Builds the tile plan for the fused blocks `csrs` (their structural phase and,
-// when dropping, their cached classification keep/pos must be valid).
-// Returns nullptr when the tile path does not apply (falls back to the slab path).
-std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop) {
-  if (std::getenv("FQ_NO_TILE")) return nullptr;
-  if (nblocks < 1 || nblocks > kTileMaxBlocks) return nullptr;
-  if (!mesh->vertex_tile.p || mesh->ntiles == 0 || !mesh->cell_faces[0].p) return nullptr;
-  const int dim = mesh->dim;
-  if (dim > 3) return nullptr;
-  for (int b = 0; b < nblocks; ++b)
-    if (csrs[b]->kind == KIND_LUMPED) return nullptr;
-  const CoreEntryRt* core = choose_core(dim, csrs, nblocks);
-  if (!core) return nullptr;
-  const int kc = core->k;
-  const TileConfig cfg = tile_config();
-  auto plan = std::make_shared<TilePlan>();
-  plan->mesh = mesh;
-  plan->dim = dim;
-  plan->core_k = kc;
-  plan->ndistinct = core->ndistinct;
-  plan->nblocks = nblocks;
-  plan->launch = core->launch;
-  plan->ntiles = uint32_t(mesh->ntiles);
-  plan->nthreads = cfg.nthreads;
-  plan->ws = cfg.ws;
-  plan->stream_warps = cfg.stream_warps;
-  if (plan->ntiles >= (1u << 27)) return nullptr;
-  // recipes (8-bit codes over the distinct values; widened to slab offsets once the slab stride is known)
-  std::vector<std::vector<uint8_t>> codes8(static_cast<size_t>(nblocks));
-  size_t recipe_u16 = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    TileBlockPlan& bp = plan->blk[b];
-    std::vector<uint8_t>& codes = codes8[size_t(b)];
-    if (!build_recipes(dim, kc, *core, csrs[b]->kind, csrs[b]->grade, bp.no, bp.ni, codes)) return nullptr;
-    const bool shape_ok = (bp.no == 0 && bp.ni == 0) || (bp.no == 1 && bp.ni >= 1 && bp.ni <= 4) ||
-                          (bp.no == bp.ni && bp.no >= 2 && bp.no <= 4);
-    if (!shape_ok) return nullptr;
-    if (bp.no * bp.ni > 1) recipe_u16 += size_t(csrs[b]->el_rows * csrs[b]->el_cols) * size_t((bp.no * bp.ni + 3) / 4 * 4);
-    bp.csr = csrs[b];
-    bp.nnz_at_build = csrs[b]->nnz;
-    bp.dropped_at_build = drop;
-    const uint32_t T = uint32_t(csrs[b]->el_rows * csrs[b]->el_cols);
-    bp.slot_bits = bits_for32(T ? T : 1);
-  }
-  const size_t recipe_bytes = (recipe_u16 * 2 + 15) / 16 * 16;
-  if (recipe_bytes > 2048) return nullptr;
-  // alternating kernel: every block must read one half of the slab only, second-half blocks last in the stream
-  if (cfg.alt && core->split_ok && cfg.nthreads == 512) {
-    bool ok = true;
-    uint32_t ymask = 0;
-    for (int b = 0; b < nblocks && ok; ++b) {
-      bool any1 = false, any2 = false;
-      for (uint8_t c : codes8[size_t(b)]) {
-        if (c == 0xFF) continue;
-        const int slot = c & 0x7F;
-        (((core->half2[slot >> 6] >> (slot & 63)) & 1ull) ? any2 : any1) = true;
-      }
-      if (any1 && any2) ok = false;
-      if (any2) ymask |= 1u << b;
-    }
-    for (int b = 0; b + 1 < nblocks; ++b)
-      if (((ymask >> b) & 1u) && !((ymask >> (b + 1)) & 1u)) ok = false;  // a first-half block after a second-half one
-    plan->alt = ok;
-    plan->yblock_mask = ok ? ymask : 0u;
-  }
-  const int block = 256;
-  const int nv = dim + 1;
-  const int ne = int(binom(dim + 1, 2));
-  const size_t ncells = mesh->ncells;
-  const uint32_t v_lo = uint32_t(mesh->vtile_lo);
-  // ---- tile cell lists
-  DevBuf<uint32_t> tile_cells, tile_local;  // cells of every tile sorted by id, and their slab slot
-  {
-    const size_t nkeys = ncells * size_t(nv);
-    DevBuf<uint64_t> keys(nkeys), keys_alt(nkeys);
-    tile_cell_keys_kernel<<<grid_for(ncells, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        mesh->cell_faces[0].p, nv, ncells, mesh->vertex_tile.p, v_lo, keys.p);
-    fq_count_launch(ctx);
-    cub::DoubleBuffer<uint64_t> dk(keys.p, keys_alt.p);
-    size_t tmp_bytes = 0;
-    const int end_bit = 64;
-    FQ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dk, int64_t(nkeys), 0, end_bit, ctx->stream));
-    DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
-    FQ_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, dk, int64_t(nkeys), 0, end_bit, ctx->stream));
-    fq_count_launch(ctx, 9);
-    cub::TransformInputIterator<uint32_t, IsValidKey64, const uint64_t*> it(dk.Current(), IsValidKey64());
-    DevBuf<uint32_t> d_count(1);
-    size_t tmp3 = 0;
-    FQ_CUDA(cub::DeviceReduce::Sum(nullptr, tmp3, it, d_count.p, int64_t(nkeys), ctx->stream));
-    if (tmp.n < tmp3) tmp.alloc(tmp3);
-    FQ_CUDA(cub::DeviceReduce::Sum(tmp.p, tmp3, it, d_count.p, int64_t(nkeys), ctx->stream));
-    fq_count_launch(ctx);
-    const uint32_t nvalid = read_u32(ctx, d_count.p);
-    DevBuf<uint32_t> tile_of(nvalid ? nvalid : 1);
-    tile_cells.alloc(nvalid ? nvalid : 1);
-    split_keys_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(dk.Current(), nvalid, tile_of.p,
-                                                                                       tile_cells.p);
-    plan->tile_cell_ptr.alloc(size_t(plan->ntiles) + 1);
-    seg_ptr_kernel<<<grid_for(size_t(nvalid) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        tile_of.p, nvalid, plan->ntiles, plan->tile_cell_ptr.p);
-    // slab slots: type-major inside a tile when the cell numbering is (box, type), else ascending cell id
-    DevBuf<uint32_t> cells_by_slot(nvalid ? nvalid : 1);
-    tile_local.alloc(nvalid ? nvalid : 1);
-    {
-      DevBuf<uint64_t> skeys(nvalid ? nvalid : 1);
-      DevBuf<uint32_t> spos(nvalid ? nvalid : 1);
-      const uint32_t period = std::getenv("FQ_TILE_NO_TYPE_MAJOR") ? 0u : uint32_t(mesh->cell_type_period);
-      tile_slot_keys_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(
-          tile_of.p, tile_cells.p, nvalid, period, uint64_t(mesh->cell_offset), skeys.p, spos.p);
-      radix_sort_pairs_u64(ctx, skeys, spos, nvalid, 64);
-      tile_slots_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(
-          skeys.p, spos.p, nvalid, plan->tile_cell_ptr.p, cells_by_slot.p, tile_local.p);
-    }
-    plan->tile_cell_edges.alloc(size_t(nvalid ? nvalid : 1) * size_t(ne));
-    tile_cell_edges_kernel<<<grid_for(size_t(nvalid) * ne, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        cells_by_slot.p, nvalid, mesh->cell_faces[1].p, ne, plan->tile_cell_edges.p);
-    fq_count_launch(ctx, 5);
-    FQ_CUDA(cudaGetLastError());
-    std::vector<uint32_t> h_ptr(size_t(plan->ntiles) + 1);
-    FQ_CUDA(cudaMemcpyAsync(h_ptr.data(), plan->tile_cell_ptr.p, h_ptr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                            ctx->stream));
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint32_t max_cells = 1;
-    for (uint32_t t = 0; t < plan->ntiles; ++t) max_cells = std::max(max_cells, h_ptr[t + 1] - h_ptr[t]);
-    if (int(max_cells) > tile_cells_capacity(plan->ndistinct)) return nullptr;
-    plan->cstride = int(max_cells) | 1;  // odd stride: distinct rows start on different banks
-    {
-      // bank-aware lane packing wants every load of a contribution on the bank pair of its cell: stride = 0 mod 16
-      const char* e = std::getenv("FQ_TILE_PACK");
-      const int cs16 = (int(max_cells) + 15) / 16 * 16;
-      plan->pack = !(e && e[0] == '0') && !cfg.ws && cs16 <= tile_cells_capacity(plan->ndistinct) + 15 &&
-                   size_t(cs16) * size_t(plan->ndistinct) * sizeof(double) + tile_fixed_smem(cfg) <= cfg.smem_cta;
-      if (plan->pack) plan->cstride = cs16;
-    }
-    // dynamic shared memory layout
-    const size_t nwarps = plan->stream_warps ? size_t(plan->stream_warps)
-                                             : (plan->ws ? size_t(kWsConsumerWarps) : size_t(plan->nthreads) / 32);
-    size_t off = size_t(plan->cstride) * size_t(plan->ndistinct) * sizeof(double);
-    off = (off + 127) / 128 * 128;
-    plan->slab_bytes = uint32_t(off);
-    if (plan->ws) off *= 2;
-    plan->ring_off = uint32_t(off);
-    off += nwarps * kSlotsPerWarp * kChunkBytes;
-    plan->rec_off = uint32_t(off);
-    off += recipe_bytes;
-    off = (off + 7) / 8 * 8;
-    plan->mbar_off = uint32_t(off);
-    off += (nwarps * kSlotsPerWarp + 8) * 8;
-    plan->smem_bytes = off;
-    if (plan->smem_bytes > cfg.smem_cta) return nullptr;
-  }
-  // ---- recipes as slab offsets: code16 = sign << 15 | distinct * cstride
-  if (size_t(plan->ndistinct) * size_t(plan->cstride) > 0x8000u) return nullptr;
-  std::vector<DevBuf<uint16_t>> direct_map(static_cast<size_t>(nblocks));  // stored blocks: slot -> code16, used by the stream fill
-  {
-    std::vector<uint16_t> table(recipe_bytes / 2, 0);
-    size_t off16 = 0;
-    for (int b = 0; b < nblocks; ++b) {
-      TileBlockPlan& bp = plan->blk[b];
-      const std::vector<uint8_t>& codes = codes8[size_t(b)];
-      const int nterms = bp.no * bp.ni;
-      const size_t nslots = size_t(csrs[b]->el_rows * csrs[b]->el_cols);
-      auto widen = [&](uint8_t c) { return uint16_t(((c & 0x80u) << 8) | uint32_t((c & 0x7Fu) * plan->cstride)); };
-      bp.recipe_off = int(off16);
-      if (nterms == 1) {
-        std::vector<uint16_t> dm(nslots);
-        for (size_t sl = 0; sl < nslots; ++sl) dm[sl] = widen(codes[sl]);
-        upload_vec(direct_map[size_t(b)], dm);
-      } else if (nterms > 1) {
-        const int nt4 = (nterms + 3) / 4 * 4;
-        for (size_t sl = 0; sl < nslots; ++sl)
-          for (int q = 0; q < nterms; ++q) table[off16 + sl * nt4 + q] = widen(codes[sl * nterms + q]);
-        off16 += nslots * size_t(nt4);
-      }
-    }
-    std::vector<uint8_t> bytes(recipe_bytes ? recipe_bytes : 16, 0);
-    if (recipe_bytes) std::memcpy(bytes.data(), table.data(), recipe_bytes);
-    upload_vec(plan->recipes, bytes);
-    plan->recipe_bytes = int(recipe_bytes);
-  }
-  // ---- per block: non-zeros sorted by (tile, L, signature), cut into warp records
-  // orderings inside a (tile, L) run — measured neutral on B200 (the gathers stay scattered), off by default
-  const int use_sig = std::getenv("FQ_TILE_SIG") ? std::atoi(std::getenv("FQ_TILE_SIG")) : 0;
-  const bool use_bank = std::getenv("FQ_TILE_BANK") ? std::atoi(std::getenv("FQ_TILE_BANK")) != 0 : false;
-  DevBuf<int> d_err(1);
-  FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
-  std::vector<BlockBuild> bb(static_cast<size_t>(nblocks));
-  const bool pack_stats = std::getenv("FQ_TILE_PACK_STATS") != nullptr;  // development aid: packing quality per block
-  DevBuf<unsigned long long> d_pack_stats(8);
-  FQ_CUDA(cudaMemsetAsync(d_pack_stats.p, 0, d_pack_stats.bytes(), ctx->stream));
-  for (int b = 0; b < nblocks; ++b) {
-    fq_csr* csr = csrs[b];
-    BlockBuild& B = bb[size_t(b)];
-    const size_t s_nnz = csr->s_nnz;
-    const size_t nrows_local = csr->row_end - csr->row_begin;
-    B.rec_tile_ptr.alloc(size_t(plan->ntiles) + 1);
-    if (s_nnz == 0) {
-      FQ_CUDA(cudaMemsetAsync(B.rec_tile_ptr.p, 0, B.rec_tile_ptr.bytes(), ctx->stream));
-      B.rec_len.alloc(1);
-      B.rec_rel.alloc(1);
-      continue;
-    }
-    int tg, rg;
-    kind_grades(csr->kind, csr->grade, tg, rg);
-    const int nt = nlocal(dim, tg);
-    const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
-    std::vector<uint8_t> top_pos;  // top position of every local face of the test grade
-    for (uint32_t m : colex_subsets(dim + 1, tg + 1)) top_pos.push_back(uint8_t(mask_elems(m).back()));
-    DevBuf<uint8_t> d_top;
-    upload_vec(d_top, top_pos);
-    DevBuf<uint32_t> row_tile(nrows_local ? nrows_local : 1);
-    FQ_CUDA(cudaMemsetAsync(row_tile.p, 0, row_tile.bytes(), ctx->stream));
-    row_tile_kernel<<<grid_for(ncells * size_t(nt), block, ctx->sm_count), block, 0, ctx->stream>>>(
-        mesh->cell_faces[size_t(tg)].p, nt, mesh->cell_faces[0].p, nv, d_top.p, ncells, mesh->vertex_tile.p, v_lo,
-        uint32_t(csr->row_begin), uint32_t(csr->row_end), row_tile.p);
-    DevBuf<uint64_t> key(s_nnz);
-    B.perm.alloc(s_nnz);
-    nnz_key_kernel<<<grid_for(nrows_local, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        csr->s_row_ptr.p, uint32_t(nrows_local), row_tile.p, csr->contrib_ptr.p, csr->contrib_src.p, T, use_sig,
-        use_bank ? plan->tile_cell_ptr.p : nullptr, tile_cells.p, use_bank ? tile_local.p : nullptr, key.p, B.perm.p, d_err.p);
-    fq_count_launch(ctx, 2);
-    FQ_CUDA(cudaGetLastError());
-    radix_sort_pairs_u64(ctx, key, B.perm, s_nnz, 36 + bits_for32(plan->ntiles));
-    if (use_bank) {
-      DevBuf<uint32_t> gstart(s_nnz), gscan(s_nnz);
-      group_start_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), gstart.p);
-      size_t tmp_bytes = 0;
-      FQ_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, gstart.p, gscan.p, cub::Max(), int64_t(s_nnz), ctx->stream));
-      DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
-      FQ_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, gstart.p, gscan.p, cub::Max(), int64_t(s_nnz), ctx->stream));
-      occurrence_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), gscan.p);
-      fq_count_launch(ctx, 4);
-      FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-      radix_sort_pairs_u64(ctx, key, B.perm, s_nnz, 36 + bits_for32(plan->ntiles));
-    }
-    DevBuf<uint32_t> head(s_nnz);
-    B.run_scan.alloc(s_nnz);
-    run_heads_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(key.p, uint32_t(s_nnz), head.p);
-    inclusive_scan_u32(ctx, head.p, B.run_scan.p, s_nnz);
-    B.nruns = read_u32(ctx, B.run_scan.p + (s_nnz - 1));
-    B.run_start.alloc(size_t(B.nruns) + 1);
-    B.run_tile.alloc(B.nruns);
-    B.run_len.alloc(B.nruns);
-    run_info_kernel<<<grid_for(s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        key.p, head.p, B.run_scan.p, uint32_t(s_nnz), B.run_start.p, B.run_tile.p, B.run_len.p);
-    const uint32_t n32 = uint32_t(s_nnz);
-    FQ_CUDA(cudaMemcpyAsync(B.run_start.p + B.nruns, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    B.ppos.alloc(s_nnz);
-    pack_runs_kernel<<<grid_for(B.nruns, 64, ctx->sm_count), 64, 0, ctx->stream>>>(
-        B.perm.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.nruns, csr->contrib_ptr.p, csr->contrib_src.p, T,
-        plan->tile_cell_ptr.p, tile_cells.p, tile_local.p, plan->pack ? 1 : 0, B.ppos.p, pack_stats ? d_pack_stats.p : nullptr);
-    fq_count_launch(ctx);
-    if (pack_stats) {
-      unsigned long long h[5];
-      FQ_CUDA(cudaMemcpyAsync(h, d_pack_stats.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-      FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-      std::fprintf(stderr, "[tile pack] block %d: %llu non-zeros, %llu contributions, collisions dense %llu -> packed %llu (%llu unplaced), stride %d\n",
-                   b, h[0], h[1], h[2], h[3], h[4], plan->cstride);
-      FQ_CUDA(cudaMemsetAsync(d_pack_stats.p, 0, sizeof h, ctx->stream));
-    }
-    DevBuf<uint32_t> nrec_run(size_t(B.nruns) + 1);
-    B.rec_base.alloc(size_t(B.nruns) + 1);
-    run_nrec_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        B.run_start.p, B.run_len.p, B.nruns, nrec_run.p);
-    exclusive_scan_u32(ctx, nrec_run.p, B.rec_base.p, size_t(B.nruns) + 1);
-    B.nrec = read_u32(ctx, B.rec_base.p + B.nruns);
-    B.rec_len.alloc(B.nrec ? B.nrec : 1);
-    B.rec_rel.alloc(B.nrec ? B.nrec : 1);
-    rec_len_kernel<<<grid_for(B.nruns, block, ctx->sm_count), block, 0, ctx->stream>>>(B.rec_base.p, B.run_len.p, B.nruns,
-                                                                                      B.rec_len.p);
-    // first record of every tile: first run of the tile -> its record base
-    DevBuf<uint32_t> first_run(size_t(plan->ntiles) + 1);
-    seg_ptr_kernel<<<grid_for(size_t(B.nruns) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(B.run_tile.p, B.nruns,
-                                                                                                 plan->ntiles, first_run.p);
-    gather_u32_kernel<<<grid_for(size_t(plan->ntiles) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        first_run.p, plan->ntiles + 1, B.rec_base.p, B.rec_tile_ptr.p);
-    fq_count_launch(ctx, 6);
-    FQ_CUDA(cudaGetLastError());
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  {
-    int h_err = 0;
-    FQ_CUDA(cudaMemcpy(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (h_err) return nullptr;  // a non-zero with more contributions than a record holds: keep the slab path
-  }
-  // ---- layout of the per-tile streams
-  TileLayoutArgs la{};
-  la.nblocks = nblocks;
-  for (int b = 0; b < nblocks; ++b)
-    la.blk[b] = TileLayoutBlock{bb[size_t(b)].rec_tile_ptr.p, bb[size_t(b)].rec_len.p, bb[size_t(b)].rec_rel.p};
-  DevBuf<uint32_t> tile_nchunks(size_t(plan->ntiles) + 1);
-  FQ_CUDA(cudaMemsetAsync(tile_nchunks.p, 0, tile_nchunks.bytes(), ctx->stream));
-  tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(la, plan->ntiles, 0,
-                                                                                             tile_nchunks.p, nullptr, nullptr);
+  FQ_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, dk, int64_t(nkeys), 0, end_bit, ctx->stream));
+  fq_count_launch(ctx, 9);
+  cub::TransformInputIterator<uint32_t, IsValidKey64, const uint64_t*> it(dk.Current(), IsValidKey64());
+  DevBuf<uint32_t> d_count(1);
+  size_t tmp3 = 0;
+  FQ_CUDA(cub::DeviceReduce::Sum(nullptr, tmp3, it, d_count.p, int64_t(nkeys), ctx->stream));
+  if (tmp.n < tmp3) tmp.alloc(tmp3);
+  FQ_CUDA(cub::DeviceReduce::Sum(tmp.p, tmp3, it, d_count.p, int64_t(nkeys), ctx->stream));
   fq_count_launch(ctx);
-  plan->tile_chunk_ptr.alloc(size_t(plan->ntiles) + 1);
-  {
-    std::vector<uint32_t> h_n(size_t(plan->ntiles) + 1);
-    FQ_CUDA(cudaMemcpyAsync(h_n.data(), tile_nchunks.p, h_n.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint64_t total = 0;
-    for (uint32_t t = 0; t < plan->ntiles; ++t) total += h_n[t];
-    if (total >= (1ull << 31)) return nullptr;
-  }
-  exclusive_scan_u32(ctx, tile_nchunks.p, plan->tile_chunk_ptr.p, size_t(plan->ntiles) + 1);
-  const uint32_t total_chunks = read_u32(ctx, plan->tile_chunk_ptr.p + plan->ntiles);
-  plan->stream.alloc(size_t(total_chunks ? total_chunks : 1) * kChunkBytes);
-  FQ_CUDA(cudaMemsetAsync(plan->stream.p, 0, plan->stream.bytes(), ctx->stream));  // padding lanes: dest 0, entries 0
-  tile_layout_kernel<<<grid_for(plan->ntiles, block, ctx->sm_count), block, 0, ctx->stream>>>(
-      la, plan->ntiles, 1, nullptr, plan->tile_chunk_ptr.p, plan->stream.p);
-  fq_count_launch(ctx);
-  for (int b = 0; b < nblocks; ++b) {
-    fq_csr* csr = csrs[b];
-    BlockBuild& B = bb[size_t(b)];
-    if (csr->s_nnz == 0) continue;
-    const uint32_t T = uint32_t(csr->el_rows * csr->el_cols);
-    stream_fill_kernel<<<grid_for(csr->s_nnz, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        B.perm.p, B.ppos.p, uint32_t(csr->s_nnz), B.run_scan.p, B.run_start.p, B.run_tile.p, B.run_len.p, B.rec_base.p, B.rec_rel.p,
-        plan->tile_chunk_ptr.p, csr->contrib_ptr.p, csr->contrib_src.p, T, plan->blk[b].slot_bits, plan->tile_cell_ptr.p,
-        tile_cells.p, tile_local.p, csr->keep.p, drop ? csr->pos.p : nullptr, drop ? 1 : 0,
-        plan->blk[b].no * plan->blk[b].ni == 1 ? direct_map[size_t(b)].p : nullptr, plan->stream.p, d_err.p);
-    fq_count_launch(ctx);
-  }
+  const uint32_t nvalid = read_u32(ctx, d_count.p);
+  DevBuf<uint32_t> tile_of(nvalid ? nvalid : 1);
+  plan.tile_cv_cells.alloc(nvalid ? nvalid : 1);
+  split_keys_kernel<<<grid_for(nvalid, block, ctx->sm_count), block, 0, ctx->stream>>>(dk.Current(), nvalid, tile_of.p,
+                                                                                     plan.tile_cv_cells.p);
+  plan.tile_cv_ptr.alloc(size_t(plan.ntiles) + 1);
+  seg_ptr_kernel<<<grid_for(size_t(nvalid) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(tile_of.p, nvalid, plan.ntiles,
+                                                                                              plan.tile_cv_ptr.p);
+  fq_count_launch(ctx, 2);
   FQ_CUDA(cudaGetLastError());
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  int h_err = 0;
-  FQ_CUDA(cudaMemcpy(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-  if (h_err) return nullptr;  // a tile exceeds the 15/16-bit local index space: keep the slab path
-  plan->changed.alloc(1);
-  plan->ticket.alloc(1);
-  plan->stats.alloc(8);
-  plan->grid = ctx->sm_count * (cfg.nthreads == 256 ? 2 : 1);
-  return plan;
 }
 
-// Runs the fused kernel.  Returns false when the zero/non-zero classification of
-// some entry differs from the plan's (the caller re-runs the slab path and rebuilds).
-bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
-  TileParams P{};
-  P.tile_cell_ptr = plan.tile_cell_ptr.p;
-  P.tile_cell_edges = plan.tile_cell_edges.p;
-  P.lengths = mesh->lengths.p;
-  P.edge_lo = uint32_t(mesh->edge_lo);
-  P.ntiles = plan.ntiles;
-  P.tile_chunk_ptr = plan.tile_chunk_ptr.p;
-  P.stream = plan.stream.p;
-  P.cstride = plan.cstride;
-  P.nblocks = plan.nblocks;
-  P.ring_off = plan.ring_off;
-  P.rec_off = plan.rec_off;
-  P.mbar_off = plan.mbar_off;
-  P.slab_bytes = plan.slab_bytes;
-  P.recipes = plan.recipes.p;
-  P.recipe_bytes = plan.recipe_bytes;
-  P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
-  P.check_classification = (plan.blk[0].dropped_at_build && !(P.debug & 7)) ? 1 : 0;
-  P.yblock_mask = plan.yblock_mask;
-  P.chunk_rotation = std::getenv("FQ_TILE_ROTATE") ? uint32_t(std::atoi(std::getenv("FQ_TILE_ROTATE"))) : 5u;
-  P.changed = plan.changed.p;
-  P.ticket = plan.ticket.p;
-  P.stats = plan.stats.p;
+// Host reference builder on downloaded tables (FQ_TILE_BUILD=host; development / validation of the device builder).
+static bool build_streams_host(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
+  const SetDesc& S = plan.desc;
+  HostMesh M;
+  std::vector<std::vector<uint32_t>> faces(4);
+  for (int g = 0; g <= mesh->dim; ++g) {
+    if (!mesh->cell_faces[size_t(g)].p) continue;
+    faces[size_t(g)].resize(mesh->cell_faces[size_t(g)].n);
+    FQ_CUDA(cudaMemcpy(faces[size_t(g)].data(), mesh->cell_faces[size_t(g)].p, faces[size_t(g)].size() * 4, cudaMemcpyDeviceToHost));
+    M.faces[g] = faces[size_t(g)].data();
+  }
+  std::vector<uint32_t> vtile(mesh->vertex_tile.n), cvp(plan.tile_cv_ptr.n), cvc(plan.tile_cv_cells.n);
+  FQ_CUDA(cudaMemcpy(vtile.data(), mesh->vertex_tile.p, vtile.size() * 4, cudaMemcpyDeviceToHost));
+  FQ_CUDA(cudaMemcpy(cvp.data(), plan.tile_cv_ptr.p, cvp.size() * 4, cudaMemcpyDeviceToHost));
+  FQ_CUDA(cudaMemcpy(cvc.data(), plan.tile_cv_cells.p, cvc.size() * 4, cudaMemcpyDeviceToHost));
+  M.ncells = mesh->ncells;
+  M.vertex_tile = vtile.data();
+  M.v_lo = uint32_t(mesh->vtile_lo);
+  M.ntiles = plan.ntiles;
+  M.tile_cv_ptr = cvp.data();
+  M.tile_cv_cells = cvc.data();
+  HostPlan H;
+  try {
+    HostBuilder builder(S, M);
+    H = builder.build(kSlabCapacity);
+  } catch (const std::runtime_error&) {
+    return false;
+  }
+  plan.max_slab = H.max_slab;
+  plan.nchunks = uint32_t(H.stream.size() / kChunkBytes);
+  upload_vec(plan.tiles, H.tiles);
+  upload_vec(plan.cv_rec, H.cv_rec);
+  upload_vec(plan.stream, H.stream);
   for (int b = 0; b < plan.nblocks; ++b) {
-    const TileBlockPlan& bp = plan.blk[b];
-    TileBlockDev& d = P.blk[b];
-    d.values = bp.csr->values.p;
-    d.no = bp.no;
-    d.ni = bp.ni;
-    d.recipe_off = bp.recipe_off;
-    d.slot_bits = bp.slot_bits;
-  }
-  {
-    ScopedSpan span(ctx, "k13_tile_fused");
-    FQ_CUDA(cudaMemsetAsync(plan.changed.p, 0, sizeof(int), ctx->stream));
-    FQ_CUDA(cudaMemsetAsync(plan.ticket.p, 0, sizeof(unsigned int), ctx->stream));
-    if (P.debug & 8) FQ_CUDA(cudaMemsetAsync(plan.stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    plan.launch(ctx, plan, P);
-  }
-  int changed = 0;
-  FQ_CUDA(cudaMemcpyAsync(&changed, plan.changed.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (P.debug & 8) {  // development aid: where the warps spend their cycles
-    unsigned long long h[6];
-    FQ_CUDA(cudaMemcpy(h, plan.stats.p, sizeof h, cudaMemcpyDeviceToHost));
-    const double tot = double(h[0] + h[1] + h[2] + h[3] + h[4] + h[5]);
-    std::fprintf(stderr, "[tile stats] k1 %.1f%%  bar_k1 %.1f%%  chunk_wait %.1f%%  records %.1f%%  bar_top %.1f%%  other %.1f%%  (warp-cycles %.3g)\n",
-                 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot);
-  }
-  return changed == 0;
-}
-
-bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks, bool drop) {
-  if (plan.mesh != mesh || plan.nblocks != nblocks) return false;
-  for (int b = 0; b < nblocks; ++b) {
-    const TileBlockPlan& bp = plan.blk[b];
-    if (bp.csr != csrs[b] || bp.dropped_at_build != drop || bp.nnz_at_build != csrs[b]->nnz) return false;
+    fq_csr* csr = plan.csr[b];
+    if (S.blk[b].empty) continue;
+    upload_vec(csr->s_row_ptr, H.row_ptr[b]);
+    upload_vec(csr->s_col_idx, H.col_idx[b]);
+    csr->s_nnz = H.col_idx[b].size();
+    csr->ncontrib = size_t(H.nentries[b]);
   }
   return true;
 }
 
-int64_t tile_plan_bytes(const TilePlan& plan) {
-  return int64_t(plan.tile_cell_ptr.bytes() + plan.tile_cell_edges.bytes() + plan.tile_chunk_ptr.bytes() + plan.stream.bytes());
+static bool build_streams_device(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
+  const SetDesc& S = plan.desc;
+  BuildParams P{};
+  P.S = S;
+  for (int g = 0; g < 4; ++g) {
+    P.gtab[g] = plan.gtab[g];
+    P.id_bits[g] = g <= mesh->dim ? std::min(32, bits_for32(uint64_t(mesh->nsimplices[size_t(g)]) + 1)) : 1;
+    P.faces[g] = (g <= mesh->dim) ? mesh->cell_faces[size_t(g)].p : nullptr;
+  }
+  P.vertex_tile = mesh->vertex_tile.p;
+  P.v_lo = uint32_t(mesh->vtile_lo);
+  P.ntiles = plan.ntiles;
+  P.tile_cv_ptr = plan.tile_cv_ptr.p;
+  P.tile_cv_cells = plan.tile_cv_cells.p;
+  DevBuf<int> d_err(1);
+  DevBuf<uint32_t> d_max(kMaxClasses), tile_chunks(size_t(plan.ntiles) + 1);
+  FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+  FQ_CUDA(cudaMemsetAsync(d_max.p, 0, d_max.bytes(), ctx->stream));
+  FQ_CUDA(cudaMemsetAsync(tile_chunks.p, 0, tile_chunks.bytes(), ctx->stream));
+  for (int b = 0; b < plan.nblocks; ++b) {
+    fq_csr* csr = plan.csr[b];
+    if (S.blk[b].empty) continue;
+    const size_t nrows_local = csr->row_end - csr->row_begin;
+    csr->s_row_ptr.alloc(nrows_local + 1);
+    FQ_CUDA(cudaMemsetAsync(csr->s_row_ptr.p, 0, csr->s_row_ptr.bytes(), ctx->stream));
+    P.row_ptr[b] = csr->s_row_ptr.p;
+  }
+  P.tile_nchunks = tile_chunks.p;
+  DevBuf<unsigned long long> d_ncontrib(kMaxBlocks);
+  FQ_CUDA(cudaMemsetAsync(d_ncontrib.p, 0, d_ncontrib.bytes(), ctx->stream));
+  P.ncontrib = d_ncontrib.p;
+  P.err = d_err.p;
+  P.rs_max = d_max.p;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQ_CUDA(cudaFuncSetAttribute(tile_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(BuildSmem))));
+    FQ_CUDA(cudaFuncSetAttribute(tile_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(BuildSmem))));
+    attr_set = true;
+  }
+  const int grid = int(std::min<uint64_t>(plan.ntiles, uint64_t(ctx->sm_count)));
+  tile_build_kernel<false><<<grid, kBT, sizeof(BuildSmem), ctx->stream>>>(P);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  int h_err = 0;
+  FQ_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_err) return false;
+  {
+    uint32_t rs_max[kMaxClasses];
+    FQ_CUDA(cudaMemcpy(rs_max, d_max.p, sizeof rs_max, cudaMemcpyDeviceToHost));
+    set_slab_bases(S, rs_max, P.slab_base, plan.max_slab);
+    if (plan.max_slab > kSlabCapacity || plan.max_slab > 0x10000u) return false;
+  }
+  unsigned long long h_ncontrib[kMaxBlocks];
+  FQ_CUDA(cudaMemcpy(h_ncontrib, d_ncontrib.p, sizeof h_ncontrib, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < plan.nblocks; ++b) {
+    fq_csr* csr = plan.csr[b];
+    if (S.blk[b].empty) continue;
+    csr->ncontrib = size_t(h_ncontrib[b]);
+    const size_t nrows_local = csr->row_end - csr->row_begin;
+    csr->s_nnz = exclusive_scan_inplace(ctx, csr->s_row_ptr.p, nrows_local + 1);
+    csr->s_col_idx.alloc(csr->s_nnz ? csr->s_nnz : 1);
+    P.col_idx[b] = csr->s_col_idx.p;
+  }
+  plan.nchunks = exclusive_scan_inplace(ctx, tile_chunks.p, size_t(plan.ntiles) + 1);
+  P.tile_chunk_ptr = tile_chunks.p;
+  plan.tiles.alloc(plan.ntiles ? plan.ntiles : 1);
+  plan.cv_rec.alloc(std::max<size_t>(1, plan.tile_cv_cells.n * size_t(S.cv_words)));
+  plan.stream.alloc(size_t(plan.nchunks ? plan.nchunks : 1) * kChunkBytes);
+  FQ_CUDA(cudaMemsetAsync(plan.stream.p, 0, plan.stream.bytes(), ctx->stream));  // padding lanes: dest 0, codes 0
+  P.tiles = plan.tiles.p;
+  P.cv_rec = plan.cv_rec.p;
+  P.stream = plan.stream.p;
+  tile_build_kernel<true><<<grid, kBT, sizeof(BuildSmem), ctx->stream>>>(P);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  FQ_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h_err == 0;
 }
+
+// Builds the plan of the fused blocks `csrs` and, with it, their structural patterns (s_row_ptr, s_col_idx, s_nnz).
+// Returns nullptr when the tile path does not apply (the caller falls back to the slab path).
+std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks) {
+  if (std::getenv("FQ_NO_TILE")) return nullptr;
+  if (nblocks < 1 || nblocks > kMaxBlocks) return nullptr;
+  if (!mesh->vertex_tile.p || mesh->ntiles == 0 || !mesh->cell_faces[0].p) return nullptr;
+  const int dim = mesh->dim;
+  if (dim > 3 || dim < 1) return nullptr;
+  std::vector<BlockSpec> specs;
+  const SetEntryRt* set = find_set(dim, csrs, nblocks, specs);
+  if (!set) return nullptr;
+  cudaEvent_t ev0, ev1;
+  FQ_CUDA(cudaEventCreate(&ev0));
+  FQ_CUDA(cudaEventCreate(&ev1));
+  FQ_CUDA(cudaEventRecord(ev0, ctx->stream));
+  auto plan = std::make_shared<TilePlan>();
+  plan->mesh = mesh;
+  plan->dim = dim;
+  plan->nblocks = nblocks;
+  plan->set = set;
+  plan->ntiles = uint32_t(mesh->ntiles);
+  plan->desc = make_set(dim, specs);
+  SetDesc& S = plan->desc;
+  int ntab = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    plan->csr[b] = csrs[b];
+    BlockDesc& B = S.blk[b];
+    if (B.empty) continue;
+    if (csrs[b]->row_end > 0xFFFFFFFEull) return nullptr;
+    B.row_begin = uint32_t(csrs[b]->row_begin);
+    B.row_end = uint32_t(csrs[b]->row_end);
+    for (int g : {B.tg, B.rg}) {
+      if (!mesh->cell_faces[size_t(g)].p) return nullptr;
+      if (plan->gtab[g] < 0) {
+        if (ntab == 2) return nullptr;
+        plan->gtab[g] = ntab++;
+      }
+    }
+  }
+  if (!mesh->cell_faces[1].p) return nullptr;
+  finish_classes(S);
+  build_cell_visits(ctx, mesh, *plan);
+  const char* how = std::getenv("FQ_TILE_BUILD");
+  const bool ok = (how && how[0] == 'h') ? build_streams_host(ctx, mesh, *plan) : build_streams_device(ctx, mesh, *plan);
+  if (!ok) return nullptr;
+  // dynamic shared memory of the fused kernel: slab | TMA ring | mbarriers (laid out at launch)
+  plan->slab_bytes = (size_t(plan->max_slab) * sizeof(double) + 127) / 128 * 128;
+  if (plan->slab_bytes + kRingBytesMax + kBarBytes > kSmemCta) return nullptr;
+  plan->changed.alloc(1);
+  plan->grid = int(std::min<uint64_t>(uint64_t(ctx->sm_count), std::max<uint32_t>(plan->ntiles, 1u)));
+  FQ_CUDA(cudaEventRecord(ev1, ctx->stream));
+  FQ_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0;
+  FQ_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  plan->build_ms = ms;
+  FQ_CUDA(cudaEventDestroy(ev0));
+  FQ_CUDA(cudaEventDestroy(ev1));
+  return plan;
+}
+
+// One launch of the fused kernel over the plan's blocks.  structural: dest = structural position, `keep` flags written
+// (when the block has a keep array); compact: dest = position in the value-dependent pattern, classification verified.
+// Returns false when the classification differs from the plan's.
+bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan, double* const* values, uint8_t* const* keep) {
+  FusedParams P{};
+  P.tiles = plan.tiles.p;
+  P.ntiles = plan.ntiles;
+  P.cv_rec = plan.cv_rec.p;
+  P.cv_words = plan.desc.cv_words;
+  P.lengths = mesh->lengths.p;
+  P.edge_lo = uint32_t(mesh->edge_lo);
+  P.stream = plan.stream.p;
+  P.changed = plan.changed.p;
+  P.chunk_rotation = std::getenv("FQ_TILE_ROTATE") ? uint32_t(std::atoi(std::getenv("FQ_TILE_ROTATE"))) : 5u;
+  P.debug = std::getenv("FQ_TILE_DEBUG") ? std::atoi(std::getenv("FQ_TILE_DEBUG")) : 0;
+  for (int b = 0; b < kMaxBlocks; ++b) {
+    P.values[b] = b < plan.nblocks ? values[b] : nullptr;
+    P.keep[b] = (b < plan.nblocks && keep) ? keep[b] : nullptr;
+    const bool live = b < plan.nblocks && !plan.desc.blk[b].empty;
+    P.group_pack |= uint32_t(live ? plan.desc.blk[b].group : 0) << (8 * b);
+    P.class_pack |= uint32_t(live ? plan.desc.blk[b].rclass : 0) << (8 * b);
+  }
+  {
+    ScopedSpan span(ctx, "k13_tile_fused");
+    FQ_CUDA(cudaMemsetAsync(plan.changed.p, 0, sizeof(int), ctx->stream));
+    plan.set->launch(ctx, FusedLaunch{plan.grid, plan.slab_bytes, plan.compact}, P);
+  }
+  if (!plan.compact) return true;
+  int changed = 0;
+  FQ_CUDA(cudaMemcpyAsync(&changed, plan.changed.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return changed == 0;
+}
+
+// dest of every record lane: structural position -> position in the compacted pattern (keep / pos of every block)
+void tile_retarget(fq_ctx* ctx, TilePlan& plan) {
+  RetargetArgs A{};
+  for (int b = 0; b < plan.nblocks; ++b) {
+    A.keep[b] = plan.csr[b]->keep.p;
+    A.pos[b] = plan.csr[b]->pos.p;
+  }
+  ScopedSpan span(ctx, "tile_retarget");
+  retarget_kernel<<<grid_for(size_t(plan.nchunks) * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(plan.stream.p, plan.nchunks, A);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+  plan.compact = true;
+}
+
+bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const* csrs, int nblocks) {
+  if (plan.mesh != mesh || plan.nblocks != nblocks) return false;
+  for (int b = 0; b < nblocks; ++b)
+    if (plan.csr[b] != csrs[b]) return false;
+  return true;
+}
+bool& tile_plan_compact(TilePlan& plan) { return plan.compact; }
+bool& tile_plan_drop(TilePlan& plan) { return plan.drop; }
+double tile_plan_build_ms(const TilePlan& plan) { return plan.build_ms; }
+
+int64_t tile_plan_bytes(const TilePlan& plan) {
+  return int64_t(plan.tiles.bytes() + plan.cv_rec.bytes() + plan.stream.bytes());
+}
+// bytes of the per-step inputs of the fused kernel other than the edge lengths: cell-visit records + record streams
+int64_t tile_plan_stream_bytes(const TilePlan& plan) { return int64_t(plan.stream.bytes()); }
+int64_t tile_plan_cv_bytes(const TilePlan& plan) { return int64_t(plan.cv_rec.bytes()); }
 
 }  // namespace fq

@@ -120,6 +120,16 @@ inline void finish_classes(SetDesc& S) {
   S.cv_words = S.ne + S.nclasses;
 }
 
+// Regions of the blocks in the slab from the largest row-slot count of every row class.
+inline void set_slab_bases(const SetDesc& S, const uint32_t* rs_max, uint32_t* slab_base, uint32_t& total) {
+  uint32_t slab = kZeroSlots;
+  for (int b = 0; b < kMaxBlocks; ++b) {
+    slab_base[b] = slab;
+    if (b < S.nblocks && !S.blk[b].empty) slab += rs_max[S.blk[b].rclass] * uint32_t(S.blk[b].d);
+  }
+  total = slab;
+}
+
 // ---------------------------------------------------------------- host reference builder
 struct HostMesh {
   size_t ncells = 0;
@@ -136,7 +146,41 @@ struct HostPlan {
   std::vector<unsigned char> stream;
   std::vector<uint32_t> row_ptr[kMaxBlocks];  // structural pattern of every block (local rows)
   std::vector<uint32_t> col_idx[kMaxBlocks];
-  uint32_t max_slab = 0;                      // slab doubles of the largest tile
+  uint32_t max_slab = 0;                      // slab doubles: kZeroSlots + the regions of all blocks
+  uint32_t rs_max[kMaxClasses] = {0, 0, 0, 0};  // largest row-slot count of every row class over the tiles
+  uint32_t slab_base[kMaxBlocks] = {0, 0, 0, 0};  // region of every block: the SAME for all tiles (a tile's producers
+                                              // refill one stage group's region while the consumers still read the others)
+  uint64_t nentries[kMaxBlocks] = {0, 0, 0, 0};  // owned element entries (contributions) of every block
+};
+
+// Sequential placement of records into the chunks of one tile's stream (the device builder computes the same
+// positions in closed form per run of equal-sized records).
+struct Cursor {
+  uint32_t off = 0;          // next free byte of the open chunk
+  uint32_t chunk_start = 0;  // byte offset of the open chunk
+  uint32_t in_chunk = 0;     // records in the open chunk
+  bool open = false;
+  uint32_t next_start = 0;   // where the next chunk begins
+  // returns the byte offset of a record of `size` bytes; writes the header of a chunk it closes when `base` is given
+  uint32_t place(uint32_t size, unsigned char* base) {
+    if (!open || off + size > chunk_start + uint32_t(kChunkBytes)) {
+      close(base);
+      chunk_start = next_start;
+      next_start = chunk_start + uint32_t(kChunkBytes);
+      off = chunk_start + uint32_t(kChunkHdr);
+      in_chunk = 0;
+      open = true;
+    }
+    const uint32_t at = off;
+    off += size;
+    ++in_chunk;
+    return at;
+  }
+  void close(unsigned char* base) {
+    if (open && base) std::memcpy(base + chunk_start, &in_chunk, 4);
+    open = false;
+  }
+  uint32_t nchunks() const { return next_start / uint32_t(kChunkBytes); }
 };
 
 class HostBuilder {
@@ -152,6 +196,8 @@ class HostBuilder {
     }
     std::vector<uint32_t> nchunks(M.ntiles, 0);
     for (uint32_t t = 0; t < M.ntiles; ++t) tile(t, false, slab_capacity_doubles, P, nchunks[t]);
+    set_slab_bases(S, P.rs_max, P.slab_base, P.max_slab);
+    if (P.max_slab > slab_capacity_doubles || P.max_slab > 0x10000u) throw std::runtime_error("tile plan: a tile exceeds the shared slab");
     for (int b = 0; b < S.nblocks; ++b) {  // row lengths -> exclusive scan
       uint32_t run = 0;
       for (uint32_t& v : P.row_ptr[b]) {
@@ -208,13 +254,9 @@ class HostBuilder {
         RS[c] += uint32_t(__builtin_popcount(m));
       }
     }
-    uint32_t slab = kZeroSlots;
-    for (int b = 0; b < S.nblocks; ++b) {
-      H.slab_base[b] = slab;
-      if (!S.blk[b].empty) slab += RS[S.blk[b].rclass] * uint32_t(S.blk[b].d);
-    }
-    if (slab > cap || slab > 0x10000u) throw std::runtime_error("tile plan: a tile exceeds the shared slab");
-    P.max_slab = std::max(P.max_slab, slab);
+    (void)cap;
+    for (int c = 0; c < S.nclasses; ++c) P.rs_max[c] = std::max(P.rs_max[c], RS[c]);
+    for (int b = 0; b < kMaxBlocks; ++b) H.slab_base[b] = P.slab_base[b];
     if (emit)
       for (uint32_t i = 0; i < ncv; ++i) {
         const size_t cell = M.tile_cv_cells[cv0 + i];
@@ -224,7 +266,7 @@ class HostBuilder {
       }
     // blocks
     unsigned char* sbase = emit ? P.stream.data() + size_t(H.chunk_begin) * kChunkBytes : nullptr;
-    uint32_t off = 0, in_chunk = 0;
+    Cursor cur;
     for (int b = 0; b < S.nblocks; ++b) {
       const BlockDesc& B = S.blk[b];
       if (B.empty) continue;
@@ -245,6 +287,7 @@ class HostBuilder {
           }
         }
       }
+      if (!emit) P.nentries[b] += ents.size();
       if (ents.size() > size_t(kMaxEntries)) throw std::runtime_error("tile plan: too many entries of one block in a tile");
       std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b2) { return a.key < b2.key; });
       struct Nz {
@@ -282,17 +325,9 @@ class HostBuilder {
         while (p1 < order.size() && nz[order[p1]].L == L) ++p1;
         const uint32_t lanes = rec_lanes(L), size = rec_bytes(L);
         for (size_t r0 = p0; r0 < p1; r0 += lanes) {
-          const uint32_t chunk = off / kChunkBytes;
-          if (off % kChunkBytes == 0 || off + size > (chunk + 1) * kChunkBytes) {  // open a new chunk
-            if (off % kChunkBytes != 0) {
-              if (emit) std::memcpy(sbase + size_t(chunk) * kChunkBytes, &in_chunk, 4);
-              off = (chunk + 1) * kChunkBytes;
-            }
-            off += kChunkHdr;
-            in_chunk = 0;
-          }
+          const uint32_t at = cur.place(size, sbase);
           if (emit) {
-            unsigned char* rp = sbase + off;
+            unsigned char* rp = sbase + at;
             const uint32_t h = L | (uint32_t(b) << 8) | (lanes << 16);
             std::memcpy(rp, &h, 4);
             for (size_t p = r0; p < std::min(p1, r0 + lanes); ++p) {
@@ -303,17 +338,12 @@ class HostBuilder {
                 std::memcpy(rp + kRecHdr + 4 * lanes + 2 * (j * lanes + lane), &ents[z.first + j].code, 2);
             }
           }
-          off += size;
-          ++in_chunk;
         }
         p0 = p1;
       }
     }
-    if (off % kChunkBytes != 0) {
-      if (emit) std::memcpy(sbase + size_t(off / kChunkBytes) * kChunkBytes, &in_chunk, 4);
-      off = (off / kChunkBytes + 1) * kChunkBytes;
-    }
-    nchunks_out = off / kChunkBytes;
+    cur.close(sbase);
+    nchunks_out = cur.nchunks();
   }
 };
 

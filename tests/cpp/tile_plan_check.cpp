@@ -34,9 +34,11 @@ struct HostSink {
   const tp::SetDesc* S;
   const tp::TileHdr* H;
   const uint32_t* meta;  // per row class: mask | base << 8
-  template <int B, int R, int CS>
+  bool bad_d = false;
+  template <int B, int R, int CS, int DD>
   void put(double v) {
     const tp::BlockDesc& D = S->blk[B];
+    if (DD != D.d) bad_d = true;
     const uint32_t m = meta[D.rclass] & 0xFFu, base = meta[D.rclass] >> 8;
     if (!(m >> R & 1u)) return;
     const uint32_t rs = base + uint32_t(__builtin_popcount(m & ((1u << R) - 1u)));
@@ -155,8 +157,12 @@ static bool run_case(int n, const std::vector<int64_t>& shape, const std::vector
       double s[6], mid[32];
       for (int e = 0; e < S.ne; ++e) s[e] = len[rec[e]];
       fn->a(s, mid);
-      HostSink sink{slab.data(), &S, &H, rec + S.ne};
+      HostSink sink{slab.data(), &S, &H, rec + S.ne, false};
       for (int g = 0; g < 3; ++g) fn->g[g](mid, sink);
+      if (sink.bad_d) {
+        std::printf("generated put<> carries a wrong slot count\n");
+        return false;
+      }
     }
     int last_block = -1;
     for (uint32_t c = 0; c < H.nchunks; ++c) {

@@ -527,7 +527,8 @@ def test_tile_fused_single_blocks(fq, ctx, kind, g):
     ctx.set_timing(True)
     ctx.timing_report()
     a.numeric(mesh)
-    assert _tile_fused_ran(ctx)
+    # dif_both(n + 1) is the zero operator (every element entry an exact zero): no generated tape, slab path
+    assert _tile_fused_ran(ctx) or (kind, g) == (3, 4)
     ctx.set_timing(False)
     ref = cx.assemble(s, kind, g)
     rp, ci, va = a.download()
