@@ -4,7 +4,7 @@
 // compiler can neither contract (FMA) nor re-associate it.
 //
 //   g++ -O1 -std=c++17 gen_elmat.cpp -o gen_elmat && ./gen_elmat > elmat_gen.cuh
-#include "tape.hpp"
+#include "tile_plan.hpp"
 
 #include <cinttypes>
 #include <cstdlib>
@@ -281,7 +281,7 @@ static bool emit_set(const std::string& name, int n, const std::vector<BlockSpec
   TapeBuilder tb;
   Tape t;
   const SetLayout L = set_layout(n, blocks, &tb, &t);
-  if (L.puts.empty() || L.ngroups > 3) return false;
+  if (L.puts.empty() || L.ngroups > 3 || L.nclasses > 2) return false;
   const std::vector<TapeOp> ops = tb.ssa_ops();
   int cut = -1;
   for (size_t i = 0; i < ops.size(); ++i)
@@ -395,9 +395,11 @@ static bool emit_set(const std::string& name, int n, const std::vector<BlockSpec
       const int nu = uses(ops[at], u);
       for (int q = 0; q < nu; ++q) collect(u[q], out);
     };
+    // Default: the whole group as one batch in tape order, stores in tape order (row-major per block).  Measured on
+    // B200: column batches (FQ_GEN_ORDER=col at generation time: fewer live values) make the producers 2x slower.
     const char* gen_order = std::getenv("FQ_GEN_ORDER");
-    const bool tape_order = gen_order && gen_order[0] == 't';
-    if (tape_order)  // development knob: the whole group as one batch, stores in tape order (row-major per block)
+    const bool tape_order = !(gen_order && gen_order[0] == 'c');
+    if (tape_order)
       std::stable_sort(order.begin(), order.end(), [](const PutRef& a, const PutRef& b) { return a.p->op < b.p->op; });
     for (size_t p0 = 0; p0 < order.size();) {
       size_t p1 = p0;
@@ -416,7 +418,7 @@ static bool emit_set(const std::string& name, int n, const std::vector<BlockSpec
         const TapeOp& o = ops[size_t(pr.p->op)];
         const std::string v = (o.op == OP_STORE || o.op == OP_STOREN) ? ((o.op == OP_STOREN ? "-" : "") + reg(o.a)) : cst(tb.consts[o.b]);
       sg[size_t(g)] << "  sink.template put<" << pr.p->block << ", " << pr.p->row << ", " << pr.p->slot << ", "
-                    << L.blocks[size_t(pr.p->block)].d << ">(" << v << ");\n";
+                    << L.blocks[size_t(pr.p->block)].d << ", " << L.blocks[size_t(pr.p->block)].tclass << ">(" << v << ");\n";
       }
       p0 = p1;
     }
@@ -425,6 +427,21 @@ static bool emit_set(const std::string& name, int n, const std::vector<BlockSpec
               t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
   const int nmid = int(mid_of.size());
   std::printf("constexpr int %s_nmid = %d;\nconstexpr int %s_ngroups = %d;\n", name.c_str(), nmid > 0 ? nmid : 1, name.c_str(), L.ngroups);
+  {
+    // slab layout of the tile-fused kernel for this set: plane strides of the row classes and block regions
+    // (tile_plan.hpp: dim_budget / set_slab_layout) as compile-time constants, so every store is one instruction
+    tp::SetDesc S = tp::make_set(n, blocks);
+    for (int b = 0; b < S.nblocks; ++b) S.blk[b].row_begin = 0, S.blk[b].row_end = 1;
+    if (!tp::finish_classes(S)) return false;
+    uint32_t plane[tp::kMaxClasses], sb[tp::kMaxBlocks], total;
+    tp::set_slab_layout(S, tp::dim_budget(n), plane, sb, total);
+    std::printf("constexpr unsigned %s_plane0 = %u, %s_plane1 = %u;\n", name.c_str(), plane[0], name.c_str(), plane[1]);
+    std::printf("constexpr unsigned %s_sb0 = %u, %s_sb1 = %u, %s_sb2 = %u, %s_sb3 = %u;\n", name.c_str(), sb[0], name.c_str(), sb[1],
+                name.c_str(), sb[2], name.c_str(), sb[3]);
+  }
+  // local rows of the (at most two) row classes = test grades of the set
+  std::printf("constexpr int %s_nclasses = %d;\nconstexpr int %s_crows0 = %d;\nconstexpr int %s_crows1 = %d;\n", name.c_str(), L.nclasses,
+              name.c_str(), L.nclasses > 0 ? nlocal(n, L.class_grade[0]) : 0, name.c_str(), L.nclasses > 1 ? nlocal(n, L.class_grade[1]) : 0);
   std::printf("__device__ __forceinline__ void %s_a(const double* __restrict__ s, double* __restrict__ mid) {\n%s", name.c_str(),
               sa.str().c_str());
   for (const auto& kv : mid_of) std::printf("  mid[%d] = %s;\n", kv.second, reg(kv.first).c_str());

@@ -653,6 +653,7 @@ inline std::vector<BlockSpec> hodge_blocks(int k) {
 struct SetBlock {
   int kind = 0, grade = 0, tg = 0, rg = 0, rows = 0, cols = 0, out_offset = 0;
   int group = -1;        // stage group, -1 for an empty block (a grade off [0, n]: the zero space)
+  int tclass = -1;       // row class: index of the test grade among the set's distinct test grades
   int d = 0;             // column slots per row (max over the rows)
   std::vector<int> cs;   // [rows*cols] column slot of every entry, -1 = exact zero
 };
@@ -660,7 +661,8 @@ struct SetPut {          // one generated store: value of `op` (index into the S
   int op, block, row, slot;
 };
 struct SetLayout {
-  int n = 0, ninputs = 0, ngroups = 0;
+  int n = 0, ninputs = 0, ngroups = 0, nclasses = 0;
+  int class_grade[4] = {-1, -1, -1, -1};
   std::vector<SetBlock> blocks;
   std::vector<SetPut> puts;   // in tape order
 };
@@ -689,6 +691,13 @@ inline SetLayout set_layout(int n, const std::vector<BlockSpec>& specs, TapeBuil
         g = int(group_grade.size()) - 1;
       }
       b.group = g;
+      for (int c = 0; c < L.nclasses; ++c)
+        if (L.class_grade[c] == b.tg) b.tclass = c;
+      if (b.tclass < 0) {
+        if (L.nclasses == 4) throw std::runtime_error("set_layout: too many test grades");
+        L.class_grade[L.nclasses] = b.tg;
+        b.tclass = L.nclasses++;
+      }
     }
     L.blocks.push_back(b);
   }

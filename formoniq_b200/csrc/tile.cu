@@ -41,20 +41,12 @@
 namespace fq {
 using namespace tp;
 
-constexpr int kMaxConsumerWarps = 16;
-constexpr int kSlotsPerWarp = 2;  // private TMA double buffer of every consumer warp
-constexpr int kMaxGroups = 3;
-constexpr size_t kSmemCta = size_t(227) * 1024 - 256;
-// the slab capacity the tiles are sized for assumes the largest ring (16 consumer warps)
-constexpr size_t kRingBytesMax = size_t(kMaxConsumerWarps) * kSlotsPerWarp * kChunkBytes;
-constexpr size_t kBarBytes = (size_t(kMaxConsumerWarps) * kSlotsPerWarp + 2 * kMaxGroups + 2) * 8;
-constexpr uint32_t kSlabCapacity = uint32_t((kSmemCta - kRingBytesMax - kBarBytes - 256) / 8);  // doubles
-
 struct FusedParams {
   const TileHdr* tiles;
   uint32_t ntiles;
   const uint32_t* cv_rec;
   int cv_words;
+  const uint16_t* gbase;          // group records: first row slot of every (class, local row) of 32 cell visits
   const double* lengths;
   uint32_t edge_lo;
   const unsigned char* stream;
@@ -64,7 +56,6 @@ struct FusedParams {
   uint32_t chunk_rotation;
   uint32_t ring_off, mbar_off;
   uint32_t group_pack;            // stage group of block b in byte b
-  uint32_t class_pack;            // cv record word (after the edge ids) of block b's row class in byte b
   int debug;                      // FQ_TILE_DEBUG: 1 skip K1, 2 skip records
 };
 
@@ -83,7 +74,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
@@ -98,15 +89,19 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                : "memory");
 }
 
-// Producer side: one cell visit's stores.  meta[b] = owned-row mask | first row slot << 8 of block b's row class.
+// Producer side: one cell visit's stores.  masks = owned-row masks (8 bits per row class), slot = the row slots of its
+// owned rows; the value of column slot CS of local row R of block B goes to Fn::sb(B) + CS * Fn::plane(C) + slot — the
+// region bases and plane strides are compile-time constants of the generated set, so a store is one predicated STS with
+// an immediate offset.  Lanes of a warp that own row R hold consecutive slots: the store is conflict-free.
+template <class Fn>
 struct FusedSink {
   double* __restrict__ slab;
-  uint32_t sb[kMaxBlocks];
-  uint32_t meta[kMaxBlocks];
-  template <int B, int R, int CS, int D>
+  uint32_t masks;
+  uint32_t slot[kMaxClasses][kMaxLocal];
+  template <int B, int R, int CS, int D, int C>
   __device__ __forceinline__ void put(double v) const {
-    const uint32_t m = meta[B];
-    if ((m >> R) & 1u) slab[sb[B] + ((m >> 8) + uint32_t(__popc(m & ((1u << R) - 1u)))) * uint32_t(D) + uint32_t(CS)] = v;
+    constexpr uint32_t off = Fn::sb(B) + uint32_t(CS) * Fn::plane(C);
+    if ((masks >> (8 * C + R)) & 1u) slab[slot[C][R] + off] = v;
   }
 };
 
@@ -130,20 +125,17 @@ __device__ __forceinline__ void finish_lane(uint32_t dest, double acc, uint32_t 
   }
 }
 
-// A 64-lane record with a compile-time number of contributions: the two non-zeros of a lane (columns lane and
-// lane + 32), every load at an immediate offset from two lane pointers and issued before the first add, then the
-// left-to-right sums (the first contribution starts the sum, as in the reference's duplicate summation).
-template <int L, bool COMPACT>
-__device__ __forceinline__ void record_wide(const unsigned char* __restrict__ rp, int lane, const double* __restrict__ slab,
-                                            double* __restrict__ vals, uint8_t* __restrict__ keep, int* __restrict__ changed) {
-  const uint32_t* __restrict__ destp = reinterpret_cast<const uint32_t*>(rp + kRecHdr) + lane;
-  const uint16_t* __restrict__ ent = reinterpret_cast<const uint16_t*>(rp + kRecHdr + 4 * 64) + lane;
-  const uint32_t dest0 = destp[0], dest1 = destp[32];
+// L contributions of the two chains of a lane, every load issued before the first add (memory-level parallelism is
+// what the consumer warps live on: they are bound by shared-memory latency, not by issue slots).
+template <int L>
+__device__ __forceinline__ void gather_fixed(const uint16_t* __restrict__ e0, const uint16_t* __restrict__ e1, uint32_t stride,
+                                             const double* __restrict__ slab, double& acc0, double& acc1, uint32_t& any0,
+                                             uint32_t& any1) {
   uint32_t c0[L], c1[L];
 #pragma unroll
   for (int j = 0; j < L; ++j) {
-    c0[j] = ent[j * 64];
-    c1[j] = ent[j * 64 + 32];
+    c0[j] = e0[j * stride];
+    c1[j] = e1[j * stride];
   }
   double x0[L], x1[L];
 #pragma unroll
@@ -151,21 +143,17 @@ __device__ __forceinline__ void record_wide(const unsigned char* __restrict__ rp
     x0[j] = slab[c0[j]];
     x1[j] = slab[c1[j]];
   }
-  double acc0 = x0[0], acc1 = x1[0];
-  uint32_t any0 = nz_bits(x0[0]), any1 = nz_bits(x1[0]);
 #pragma unroll
-  for (int j = 1; j < L; ++j) {
+  for (int j = 0; j < L; ++j) {
     any0 |= nz_bits(x0[j]);
     any1 |= nz_bits(x1[j]);
     acc0 = __dadd_rn(acc0, x0[j]);
     acc1 = __dadd_rn(acc1, x1[j]);
   }
-  finish_lane<COMPACT>(dest0, acc0, any0, vals, keep, changed);
-  finish_lane<COMPACT>(dest1, acc1, any1, vals, keep, changed);
 }
-
-// Any record (narrow ones for non-zeros with many contributions: 32 or 16 lanes; lanes beyond the record shadow the
-// first ones and never store): two chains per lane where the record is wide enough.
+// Any record: two non-zeros per lane (columns lane and lane + 32 of a wide record; a narrow record — 32 or 16 lanes,
+// for non-zeros with many contributions — runs the second chain on the first column and discards it; lanes beyond the
+// record shadow the first ones and never store), left-to-right sums.
 template <bool COMPACT>
 __device__ __forceinline__ void record_any(const unsigned char* __restrict__ rp, uint32_t L, uint32_t stride, int lane,
                                            const double* __restrict__ slab, double* __restrict__ vals, uint8_t* __restrict__ keep,
@@ -178,13 +166,25 @@ __device__ __forceinline__ void record_any(const unsigned char* __restrict__ rp,
   const uint16_t* __restrict__ e1 = e0 + (stride == 64u ? 32 : 0);
   double acc0 = 0.0, acc1 = 0.0;
   uint32_t any0 = 0, any1 = 0;
-#pragma unroll 2
-  for (uint32_t j = 0; j < L; ++j) {
-    const double x0 = slab[e0[j * stride]], x1 = slab[e1[j * stride]];
-    any0 |= nz_bits(x0);
-    any1 |= nz_bits(x1);
-    acc0 = __dadd_rn(acc0, x0);
-    acc1 = __dadd_rn(acc1, x1);
+  switch (L) {
+    case 1: gather_fixed<1>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+    case 2: gather_fixed<2>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+    case 3: gather_fixed<3>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+    case 4: gather_fixed<4>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+    default: {
+#pragma unroll 1
+      for (uint32_t j = 0; j + 4 <= L; j += 4) {
+        gather_fixed<4>(e0, e1, stride, slab, acc0, acc1, any0, any1);
+        e0 += 4 * stride;
+        e1 += 4 * stride;
+      }
+      switch (L & 3u) {
+        case 1: gather_fixed<1>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+        case 2: gather_fixed<2>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+        case 3: gather_fixed<3>(e0, e1, stride, slab, acc0, acc1, any0, any1); break;
+        default: break;
+      }
+    }
   }
   finish_lane<COMPACT>(dest0, acc0, any0, vals, keep, changed);
   finish_lane<COMPACT>(dest1, acc1, any1, vals, keep, changed);
@@ -249,29 +249,37 @@ __global__ void __launch_bounds__(32 * (NP + NC), 1) tile_fused_kernel(const __g
     load_range(uint64_t(t0) + G, cvb_n, ncv_n);
     uint32_t eid[CPT][NEE];
     load_ids(cvb, ncv, eid);
-    uint32_t sb[kMaxBlocks];
-#pragma unroll
-    for (int b = 0; b < kMaxBlocks; ++b) sb[b] = __ldg(&P.tiles[t0].slab_base[b]);  // the regions are the same for every tile
+    const uint32_t lt_mask = (1u << lane) - 1u;
     for (uint32_t it = 0;; ++it) {
       const uint64_t t = uint64_t(t0) + uint64_t(it) * G;
       if (t >= uint64_t(P.ntiles)) break;
       // edge lengths and stage A (metric, inverse, volume) of this tile's cell visits: the consumers are still busy
       // with the previous tile, so this latency is off the critical path
       double mid[CPT][NM];
-      FusedSink sink[CPT];
+      FusedSink<Fn> sink[CPT];
+      const uint32_t gb_slot = __ldg(&P.tiles[t].gb_slot);
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const uint32_t c = uint32_t(tid) + uint32_t(j) * NPT;
         sink[j].slab = slab;
+        sink[j].masks = c < ncv ? __ldg(P.cv_rec + size_t(cvb + c) * W + NE) : 0u;
+        // row slots: group record + rank among the lanes of the warp (= group of 32 cell visits) that own the row
+        const uint16_t* grec = P.gbase + (size_t(gb_slot) + (c >> 5)) * kGroupWords;
 #pragma unroll
-        for (int b = 0; b < kMaxBlocks; ++b) sink[j].sb[b] = sb[b];
+        for (int cl = 0; cl < kMaxClasses; ++cl) {
+          const int nrows = cl == 0 ? Fn::kRows0 : Fn::kRows1;
+#pragma unroll
+          for (int R = 0; R < kMaxLocal; ++R) {
+            sink[j].slot[cl][R] = 0u;
+            if (R >= nrows) continue;
+            const uint32_t owners = __ballot_sync(0xFFFFFFFFu, (sink[j].masks >> (8 * cl + R)) & 1u);
+            sink[j].slot[cl][R] = uint32_t(__ldg(grec + cl * kMaxLocal + R)) + uint32_t(__popc(owners & lt_mask));
+          }
+        }
         if (c < ncv) {
           double sl[NEE];
 #pragma unroll
           for (int e = 0; e < NE; ++e) sl[e] = __ldg(P.lengths + (eid[j][e] - P.edge_lo));
-          const uint32_t* rec = P.cv_rec + size_t(cvb + c) * W + NE;
-#pragma unroll
-          for (int b = 0; b < kMaxBlocks; ++b) sink[j].meta[b] = __ldg(rec + ((P.class_pack >> (8 * b)) & 0xFFu));
           Fn::a(sl, mid[j]);
         }
       }
@@ -374,19 +382,7 @@ __global__ void __launch_bounds__(32 * (NP + NC), 1) tile_fused_kernel(const __g
           }
           double* __restrict__ vals = P.values[b];
           uint8_t* __restrict__ keep = COMPACT ? nullptr : P.keep[b];
-          if (stride == 64u) {
-            switch (L) {
-              case 1: record_wide<1, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
-              case 2: record_wide<2, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
-              case 3: record_wide<3, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
-              case 4: record_wide<4, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
-              case 5: record_wide<5, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
-              case 6: record_wide<6, COMPACT>(rec, lane, slab, vals, keep, P.changed); break;
-              default: record_any<COMPACT>(rec, L, stride, lane, slab, vals, keep, P.changed); break;
-            }
-          } else {
-            record_any<COMPACT>(rec, L, stride, lane, slab, vals, keep, P.changed);
-          }
+          record_any<COMPACT>(rec, L, stride, lane, slab, vals, keep, P.changed);
         }
         __syncwarp();  // every lane is done reading the slot before it is refilled
         ++n_consumed;
@@ -451,7 +447,9 @@ struct BuildParams {
   const uint32_t* tile_cv_ptr;
   const uint32_t* tile_cv_cells;
   uint32_t slab_base[kMaxBlocks];    // emitting pass in: region of every block (the same for all tiles)
+  uint32_t plane[kMaxClasses];       // emitting pass in: plane strides
   uint32_t* rs_max;                  // counting pass out: largest row-slot count per row class
+  uint16_t* gbase;                   // emitting pass out: group records
   uint32_t* row_ptr[kMaxBlocks];     // counting pass: row lengths out; emitting pass: structural row_ptr in
   uint32_t* col_idx[kMaxBlocks];
   uint32_t* tile_nchunks;            // counting pass out
@@ -481,13 +479,13 @@ struct BuildSmem {
   uint32_t glob[2][kMaxCv * kMaxLocal];
   uint32_t cells[kMaxCv];
   uint8_t cmask[kMaxClasses][kMaxCv];
-  uint16_t cbase[kMaxClasses][kMaxCv];
+  uint16_t rs[kMaxClasses][kMaxCv * kMaxLocal];  // row slot of (cell visit, local row)
+  uint16_t gcnt[kMaxClasses][(kMaxCv / 32) * kMaxLocal];  // owners of (group, local row), then their first row slot
   uint16_t ebase[kMaxCv];
   uint16_t rowstart[kMaxCv * kMaxLocal];
   uint16_t runstart[64];
   RunInfo run[64];
   uint32_t RS[kMaxClasses];
-  uint32_t slab_base[kMaxBlocks];
   uint32_t E, Q, bad;
   // placement cursor of the tile's stream (tile_plan.hpp: Cursor)
   uint32_t cur_off, cur_chunk_start, cur_in_chunk, cur_open, cur_next_start;
@@ -513,7 +511,7 @@ __global__ void __launch_bounds__(kBT, 1) tile_build_kernel(const __grid_constan
       if (!EMIT && tid == 0) P.tile_nchunks[t] = 0;
       continue;
     }
-    // ---- row classes: owned-row masks and first row slots
+    // ---- row classes: owned-row masks; row slots numbered (group of 32 cell visits, local row, cell visit)
     for (int c = 0; c < S.nclasses; ++c) {
       const int g = S.class_grade[c], nl = S.nl[g];
       uint32_t m = 0;
@@ -526,28 +524,61 @@ __global__ void __launch_bounds__(kBT, 1) tile_build_kernel(const __grid_constan
         }
         sm.cmask[c][tid] = uint8_t(m);
       }
-      uint32_t base, total;
-      BScan(sm.tmp.scan).ExclusiveSum(uint32_t(__popc(m)), base, total);
-      if (tid < ncv) sm.cbase[c][tid] = uint16_t(base);
-      if (tid == 0) sm.RS[c] = total;
+      const uint32_t grp = tid >> 5, lane = tid & 31u;
+      uint32_t rank[kMaxLocal];
+#pragma unroll
+      for (int r = 0; r < kMaxLocal; ++r) {
+        const uint32_t owners = __ballot_sync(0xFFFFFFFFu, (m >> r) & 1u);
+        rank[r] = uint32_t(__popc(owners & ((1u << lane) - 1u)));
+        if (lane == 0) sm.gcnt[c][grp * kMaxLocal + r] = uint16_t(__popc(owners));
+      }
+      __syncthreads();
+      if (tid == 0) {  // exclusive scan over (group, row): 16 x 6 entries
+        uint32_t run = 0;
+        const uint32_t ngroups = (ncv + 31u) / 32u;
+        for (uint32_t i = 0; i < ngroups * kMaxLocal; ++i) {
+          const uint32_t cnt = sm.gcnt[c][i];
+          sm.gcnt[c][i] = uint16_t(run);
+          run += cnt;
+        }
+        sm.RS[c] = run;
+        if (run > 0xFFFFu) sm.bad = 1;
+      }
+      __syncthreads();
+      if (tid < ncv) {
+#pragma unroll
+        for (int r = 0; r < kMaxLocal; ++r) sm.rs[c][tid * kMaxLocal + r] = uint16_t(uint32_t(sm.gcnt[c][grp * kMaxLocal + r]) + rank[r]);
+      }
+      if (EMIT) {
+        const uint32_t gb_slot = (cv0 >> 5) + t;
+        const uint32_t ngroups = (ncv + 31u) / 32u;
+        for (uint32_t i = tid; i < ngroups * kMaxLocal; i += kBT)
+          P.gbase[(size_t(gb_slot) + i / kMaxLocal) * kGroupWords + size_t(c) * kMaxLocal + i % kMaxLocal] = sm.gcnt[c][i];
+      }
       __syncthreads();
     }
-    if (tid < uint32_t(kMaxBlocks)) sm.slab_base[tid] = P.slab_base[tid];
     if (!EMIT && tid < uint32_t(S.nclasses)) atomicMax(&P.rs_max[tid], sm.RS[tid]);
-    __syncthreads();
+    if (sm.bad) {
+      if (tid == 0) atomicExch(P.err, 2);
+      if (!EMIT && tid == 0) P.tile_nchunks[t] = 0;
+      continue;
+    }
     if (EMIT) {
       if (tid < ncv) {
         const size_t cell = sm.cells[tid];
         uint32_t* rec = P.cv_rec + size_t(cv0 + tid) * S.cv_words;
         for (int e = 0; e < S.ne; ++e) rec[e] = P.faces[1][cell * S.ne + e];
-        for (int c = 0; c < S.nclasses; ++c) rec[S.ne + c] = uint32_t(sm.cmask[c][tid]) | (uint32_t(sm.cbase[c][tid]) << 8);
+        uint32_t word = 0;
+        for (int c = 0; c < S.nclasses; ++c) word |= uint32_t(sm.cmask[c][tid]) << (8 * c);
+        rec[S.ne] = word;
       }
       if (tid == 0) {
         TileHdr H;
         H.cv_begin = cv0, H.ncv = ncv;
         H.chunk_begin = P.tile_chunk_ptr[t];
         H.nchunks = P.tile_chunk_ptr[t + 1] - P.tile_chunk_ptr[t];
-        for (int b = 0; b < kMaxBlocks; ++b) H.slab_base[b] = b < S.nblocks ? sm.slab_base[b] : 0u;
+        H.gb_slot = (cv0 >> 5) + t;
+        H.pad[0] = H.pad[1] = H.pad[2] = 0;
         P.tiles[t] = H;
       }
     }
@@ -615,17 +646,17 @@ __global__ void __launch_bounds__(kBT, 1) tile_build_kernel(const __grid_constan
         __syncthreads();
         if (sm.bad) break;
         if (tid < ncv) {
-          uint32_t e = ebase, rs = sm.cbase[c][tid];
+          uint32_t e = ebase;
           for (uint32_t r = 0; r < nt; ++r) {
             if (!(m >> r & 1u)) continue;
             const uint32_t rl = sm.lid[xt][tid * nt + r];
+            const uint32_t slot = sm.rs[c][tid * kMaxLocal + r];
             for (uint32_t j = 0; j < nr; ++j) {
               const uint32_t cs = B.cs[r * nr + j];
               sm.skey[e] = (rl << 12) | uint32_t(sm.lid[xr][tid * nr + j]);
-              sm.sval[e] = uint16_t(cs == 0xFFu ? 0u : sm.slab_base[b] + rs * uint32_t(B.d) + cs);
+              sm.sval[e] = uint16_t(cs == 0xFFu ? 0u : P.slab_base[b] + cs * P.plane[c] + slot);
               ++e;
             }
-            ++rs;
           }
         }
         for (uint32_t e = E + tid; e < uint32_t(kMaxEntries); e += kBT) sm.skey[e] = 0xFFFFFFFFu;
@@ -805,6 +836,12 @@ __global__ void __launch_bounds__(kBT, 1) tile_build_kernel(const __grid_constan
   struct Set_##fn {                                                                                      \
     static constexpr int kMid = fn##_nmid;                                                               \
     static constexpr int kGroups = fn##_ngroups;                                                         \
+    static constexpr int kRows0 = fn##_crows0;                                                           \
+    static constexpr int kRows1 = fn##_crows1;                                                           \
+    static __host__ __device__ constexpr uint32_t plane(int c) { return c == 0 ? fn##_plane0 : fn##_plane1; }            \
+    static __host__ __device__ constexpr uint32_t sb(int b) {                                                            \
+      return b == 0 ? fn##_sb0 : (b == 1 ? fn##_sb1 : (b == 2 ? fn##_sb2 : fn##_sb3));                                   \
+    }                                                                                                    \
     static __device__ __forceinline__ void a(const double* __restrict__ s, double* __restrict__ mid) {   \
       fn##_a(s, mid);                                                                                    \
     }                                                                                                    \
@@ -844,16 +881,18 @@ template <class Fn, int NE>
 static void launch_fused(fq_ctx* ctx, const FusedLaunch& L, const FusedParams& params) {
   static int variant = -1;
   if (variant < 0) {
-    // tuning: producer/consumer warps and registers.  0: 8+16 warps, 144/48 registers; 1: 8+16, 128/56;
-    // 2: 16+12 warps (one cell visit per producer thread), 96/40; 3: 16+16, 88/40; 4: 12+12, 112/48
+    // tuning: producer + consumer warps and registers per producer / consumer thread.  Default 16 + 16 warps (one
+    // cell visit per producer thread: one copy of the straight-line tape in the instruction cache), 80 / 48 registers:
+    // 3.95 ms at N = 128 against 4.42 ms for 1: 16 + 12 warps at 88 / 48 and 5.5 ms for 2: 8 + 16 warps at 144 / 48
+    // (two cell visits per producer thread) — the consumers are bound by shared-memory and TMA latency, so they want warps
     const char* e = std::getenv("FQ_TILE_WARPS");
     variant = e ? std::atoi(e) : 0;
-    if (variant < 0 || variant > 4) variant = 0;
+    if (variant < 0 || variant > 2) variant = 0;
   }
   switch (variant) {
-    case 2: launch_fused_v<Fn, NE, 16, 12, 96, 40>(ctx, L, params); break;
-    case 3: launch_fused_v<Fn, NE, 16, 16, 88, 40>(ctx, L, params); break;
-    default: launch_fused_v<Fn, NE, 8, 16, 144, 48>(ctx, L, params); break;
+    case 1: launch_fused_v<Fn, NE, 16, 12, 88, 48>(ctx, L, params); break;
+    case 2: launch_fused_v<Fn, NE, 8, 16, 144, 48>(ctx, L, params); break;
+    default: launch_fused_v<Fn, NE, 16, 16, 80, 48>(ctx, L, params); break;
   }
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
@@ -900,7 +939,10 @@ struct TilePlan {
   DevBuf<uint32_t> tile_cv_ptr, tile_cv_cells;
   DevBuf<TileHdr> tiles;
   DevBuf<uint32_t> cv_rec;
+  DevBuf<uint16_t> gbase;
   DevBuf<unsigned char> stream;
+  uint32_t plane[kMaxClasses] = {1, 1};
+  uint32_t slab_base[kMaxBlocks] = {0, 0, 0, 0};
   DevBuf<int> changed;
   fq_csr* csr[kMaxBlocks] = {nullptr, nullptr, nullptr, nullptr};
   bool compact = false;     // the stream's dests target the value-dependent (dropped) pattern
@@ -910,45 +952,13 @@ struct TilePlan {
   int grid = 0;
 };
 
-// Per-grade row-slot budgets of a tile.  A row slot is one (cell visit, owned local row) pair; an interior Kuhn vertex
-// brings S_g = dim! * C(dim+1, g+1) of them for grade g.  The slab holds sum_g RSmax_g * D_g doubles, D_g = the column
-// slots of the blocks with test grade g and RSmax_g the largest row-slot count over ALL tiles (the regions are the
-// same for every tile), so each tile is limited per grade: R_g = V* * S_g with V* the number of interior vertices the
-// most demanding Hodge set of this dimension can hold.  Then any Hodge set (and any single block) fits.
-struct DimCost {
-  double vstar = 0;
-  std::vector<double> budget;   // [grade] row slots
-  std::vector<double> max_nr;   // [grade] widest block (columns) with this test grade: entries per row slot
-};
-static const DimCost& dim_cost(int dim) {
+static const DimBudget& dim_cost(int dim) {
   static std::mutex mu;
-  static std::map<int, DimCost> cache;
+  static std::map<int, DimBudget> cache;
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(dim);
   if (it != cache.end()) return it->second;
-  DimCost dc;
-  dc.budget.assign(size_t(dim) + 1, 0.0);
-  dc.max_nr.assign(size_t(dim) + 1, 0.0);
-  double worst = 1;
-  for (int k = 0; k <= dim; ++k) {
-    const SetDesc S = make_set(dim, hodge_blocks(k));
-    double per_vertex = 0;
-    for (int b = 0; b < S.nblocks; ++b) {
-      const BlockDesc& B = S.blk[b];
-      if (B.empty) continue;
-      per_vertex += double(fact(dim)) * double(binom(dim + 1, B.tg + 1)) * B.d;
-      dc.max_nr[size_t(B.tg)] = std::max(dc.max_nr[size_t(B.tg)], double(B.nr));
-    }
-    worst = std::max(worst, per_vertex);
-  }
-  dc.vstar = std::floor(double(kSlabCapacity - kZeroSlots) / worst);
-  for (int g = 0; g <= dim; ++g) {
-    const double sg = double(fact(dim)) * double(binom(dim + 1, g + 1));
-    dc.budget[size_t(g)] = dc.vstar * sg;
-    // one block's entries in a tile must also fit the builder's sort
-    if (dc.max_nr[size_t(g)] > 0) dc.budget[size_t(g)] = std::min(dc.budget[size_t(g)], std::floor(double(kMaxEntries) / dc.max_nr[size_t(g)]));
-  }
-  return cache.emplace(dim, dc).first->second;
+  return cache.emplace(dim, dim_budget(dim)).first->second;
 }
 
 // ---- vertex clustering -------------------------------------------------------
@@ -997,9 +1007,8 @@ static uint32_t exclusive_scan_inplace(fq_ctx* ctx, uint32_t* a, size_t n_plus_1
 // slab, cell visits and per-block entries fit the kernel's limits for every Hodge set of this dimension.
 void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape, size_t slab_begin, size_t slab_end_held) {
   if (dim > 3 || std::getenv("FQ_NO_TILE")) return;
-  const DimCost& dc = dim_cost(dim);
-  double vmax = dc.vstar;  // owned vertices of a brick: every grade's budget in units of interior vertices
-  for (int g = 0; g <= dim; ++g) vmax = std::min(vmax, std::floor(dc.budget[size_t(g)] / (double(fact(dim)) * double(binom(dim + 1, g + 1)))));
+  const DimBudget& dc = dim_cost(dim);
+  const double vmax = double(dc.vstar);  // owned vertices of a brick
   std::vector<uint32_t> brick(size_t(dim), 1);
   // exact count for a brick in the interior of the grid: boxes with origin in prod [-1, b_a - 1], dim! chains each
   auto cells_touching = [&](const std::vector<uint32_t>& b) {
@@ -1094,7 +1103,7 @@ void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh) {
   FQ_CUDA(cudaMemcpyAsync(cell_verts.data(), mesh->cell_faces[0].p, cell_verts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                           ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  const DimCost& dc = dim_cost(dim);
+  const DimBudget& dc = dim_cost(dim);
   const size_t nv = size_t(dim) + 1, ncells = mesh->ncells, V = mesh->nsimplices[0];
   if (V == 0 || ncells == 0 || V >= (size_t(1) << 32)) return;
   // vertex -> cells incidence (CSR)
@@ -1132,7 +1141,7 @@ void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh) {
         for (int g = 0; g <= dim; ++g) rs_v[g] += double(binom(vpos[p], g));  // faces of grade g with this vertex on top
       }
       bool fits = ncells_T + fresh <= uint32_t(kMaxCv);
-      for (int g = 0; g <= dim; ++g) fits = fits && rs_T[g] + rs_v[g] <= dc.budget[size_t(g)];
+      for (int g = 0; g <= dim; ++g) fits = fits && rs_T[g] + rs_v[g] <= double(dc.budget[g]);
       if (ncells_T > 0 && !fits) continue;  // does not fit: left for a later tile
       vtile[v] = T;
       ncells_T += fresh;
@@ -1263,6 +1272,7 @@ static bool build_streams_host(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan)
   plan.nchunks = uint32_t(H.stream.size() / kChunkBytes);
   upload_vec(plan.tiles, H.tiles);
   upload_vec(plan.cv_rec, H.cv_rec);
+  upload_vec(plan.gbase, H.gbase);
   upload_vec(plan.stream, H.stream);
   for (int b = 0; b < plan.nblocks; ++b) {
     fq_csr* csr = plan.csr[b];
@@ -1289,6 +1299,8 @@ static bool build_streams_device(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& pla
   P.ntiles = plan.ntiles;
   P.tile_cv_ptr = plan.tile_cv_ptr.p;
   P.tile_cv_cells = plan.tile_cv_cells.p;
+  for (int c = 0; c < kMaxClasses; ++c) P.plane[c] = plan.plane[c];
+  for (int b = 0; b < kMaxBlocks; ++b) P.slab_base[b] = plan.slab_base[b];
   DevBuf<int> d_err(1);
   DevBuf<uint32_t> d_max(kMaxClasses), tile_chunks(size_t(plan.ntiles) + 1);
   FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
@@ -1325,8 +1337,8 @@ static bool build_streams_device(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& pla
   {
     uint32_t rs_max[kMaxClasses];
     FQ_CUDA(cudaMemcpy(rs_max, d_max.p, sizeof rs_max, cudaMemcpyDeviceToHost));
-    set_slab_bases(S, rs_max, P.slab_base, plan.max_slab);
-    if (plan.max_slab > kSlabCapacity || plan.max_slab > 0x10000u) return false;
+    for (int c = 0; c < S.nclasses; ++c)
+      if (rs_max[c] > plan.plane[c]) return false;  // a tile exceeds its row-slot budget: slab path
   }
   unsigned long long h_ncontrib[kMaxBlocks];
   FQ_CUDA(cudaMemcpy(h_ncontrib, d_ncontrib.p, sizeof h_ncontrib, cudaMemcpyDeviceToHost));
@@ -1343,6 +1355,8 @@ static bool build_streams_device(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& pla
   P.tile_chunk_ptr = tile_chunks.p;
   plan.tiles.alloc(plan.ntiles ? plan.ntiles : 1);
   plan.cv_rec.alloc(std::max<size_t>(1, plan.tile_cv_cells.n * size_t(S.cv_words)));
+  plan.gbase.alloc(((plan.tile_cv_cells.n >> 5) + size_t(plan.ntiles) + 1) * kGroupWords);
+  P.gbase = plan.gbase.p;
   plan.stream.alloc(size_t(plan.nchunks ? plan.nchunks : 1) * kChunkBytes);
   FQ_CUDA(cudaMemsetAsync(plan.stream.p, 0, plan.stream.bytes(), ctx->stream));  // padding lanes: dest 0, codes 0
   P.tiles = plan.tiles.p;
@@ -1396,7 +1410,9 @@ std::shared_ptr<TilePlan> tile_plan_build(fq_ctx* ctx, const fq_mesh* mesh, fq_c
     }
   }
   if (!mesh->cell_faces[1].p) return nullptr;
-  finish_classes(S);
+  if (!finish_classes(S)) return nullptr;  // blocks of one test grade with different row ranges: slab path
+  set_slab_layout(S, dim_cost(dim), plan->plane, plan->slab_base, plan->max_slab);
+  if (plan->max_slab > kSlabCapacity || plan->max_slab > 0x10000u) return nullptr;
   build_cell_visits(ctx, mesh, *plan);
   const char* how = std::getenv("FQ_TILE_BUILD");
   const bool ok = (how && how[0] == 'h') ? build_streams_host(ctx, mesh, *plan) : build_streams_device(ctx, mesh, *plan);
@@ -1425,6 +1441,7 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan, double* con
   P.ntiles = plan.ntiles;
   P.cv_rec = plan.cv_rec.p;
   P.cv_words = plan.desc.cv_words;
+  P.gbase = plan.gbase.p;
   P.lengths = mesh->lengths.p;
   P.edge_lo = uint32_t(mesh->edge_lo);
   P.stream = plan.stream.p;
@@ -1436,7 +1453,6 @@ bool tile_assemble(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan, double* con
     P.keep[b] = (b < plan.nblocks && keep) ? keep[b] : nullptr;
     const bool live = b < plan.nblocks && !plan.desc.blk[b].empty;
     P.group_pack |= uint32_t(live ? plan.desc.blk[b].group : 0) << (8 * b);
-    P.class_pack |= uint32_t(live ? plan.desc.blk[b].rclass : 0) << (8 * b);
   }
   {
     ScopedSpan span(ctx, "k13_tile_fused");
@@ -1475,7 +1491,7 @@ bool& tile_plan_drop(TilePlan& plan) { return plan.drop; }
 double tile_plan_build_ms(const TilePlan& plan) { return plan.build_ms; }
 
 int64_t tile_plan_bytes(const TilePlan& plan) {
-  return int64_t(plan.tiles.bytes() + plan.cv_rec.bytes() + plan.stream.bytes());
+  return int64_t(plan.tiles.bytes() + plan.cv_rec.bytes() + plan.gbase.bytes() + plan.stream.bytes());
 }
 // bytes of the per-step inputs of the fused kernel other than the edge lengths: cell-visit records + record streams
 int64_t tile_plan_stream_bytes(const TilePlan& plan) { return int64_t(plan.stream.bytes()); }

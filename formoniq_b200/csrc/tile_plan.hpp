@@ -7,10 +7,15 @@
 // (simplices) whose top vertex it contains, i.e. whole CSR rows, and visits every cell touching one of its vertices
 // ("cell visit", cv).  Reference path replaced: formoniq/src/galerkin.rs:138-188, hodge.rs:62-72.
 //
-//   slab (shared memory, doubles)   [0, 2) = 0.0;  block b: slab_base[b] + rowslot * d_b + column slot, where a
-//                                   row slot is one (cell visit, owned local row) pair of the block's row class and
-//                                   d_b the number of distinct values per row (tape.hpp: set_layout)
-//   cv record (u32 words)           eid[NE] edge ids of the cell | per row class: owned-row mask | first row slot << 8
+//   slab (shared memory, doubles)   [0, 2) = 0.0;  block b: slab_base[b] + column slot * plane[class] + row slot, where a
+//                                   row slot is one (cell visit, owned local row) pair of the block's row class (= test
+//                                   grade), d_b the number of distinct values per row (tape.hpp: set_layout) and the plane
+//                                   stride is 1 mod 16 doubles.  Row slots are numbered (group of 32 cell visits, local
+//                                   row, cell visit): the 32 producer lanes of a group store one row's value to
+//                                   consecutive doubles (conflict-free), and the column slots of one row slot fall on
+//                                   consecutive banks for the consumers.
+//   cv record (u32 words)           eid[NE] edge ids of the cell | owned-row masks, 8 bits per row class
+//   group record (u16)              first row slot of every (class, local row) of a group of 32 cell visits
 //   stream (per tile)               chunks of kChunkBytes: {u32 nrec; pad to 16} then records
 //                                   {u32 L | block << 8 | lanes << 16; pad to 16; u32 dest[lanes]; u16 code[L][lanes]}
 //                                   blocks in order, inside a block runs of equal L (ascending), inside a run CSR order;
@@ -30,8 +35,9 @@ namespace fq {
 namespace tp {
 
 constexpr int kMaxBlocks = 4;
-constexpr int kMaxClasses = 4;
+constexpr int kMaxClasses = 2;             // row classes = distinct test grades of a block set
 constexpr int kMaxLocal = 6;            // local faces of one grade, n <= 3
+constexpr int kGroupWords = kMaxClasses * kMaxLocal;  // u16 entries of a group record
 constexpr int kChunkBytes = 1536;       // TMA granule of the stream; a record never straddles a chunk
 constexpr int kChunkHdr = 16;
 constexpr int kRecHdr = 16;
@@ -40,8 +46,16 @@ constexpr int kMaxLen32 = ((kChunkBytes - 32) / 32 - 4) / 2;  // 32-lane records
 constexpr int kMaxLen = ((kChunkBytes - 32) / 16 - 4) / 2;    // 16-lane records up to L = 45
 constexpr uint32_t kPadDest = 0u, kNoDest = 1u;
 constexpr int kZeroSlots = 2;           // slab doubles holding 0.0 (padding lanes and exact-zero entries read them)
-constexpr int kMaxCv = 512;             // cell visits of a tile (two per producer thread)
+constexpr int kMaxCv = 512;             // cell visits of a tile
 constexpr int kMaxEntries = 9216;       // owned entries of one block in one tile (device sort: 512 threads x 18)
+// shared memory of the fused kernel: slab | TMA ring (two chunks per consumer warp, at most 16 warps) | mbarriers
+constexpr int kMaxConsumerWarps = 16;
+constexpr int kSlotsPerWarp = 2;
+constexpr int kMaxGroups = 3;
+constexpr size_t kSmemCta = size_t(227) * 1024 - 256;
+constexpr size_t kRingBytesMax = size_t(kMaxConsumerWarps) * kSlotsPerWarp * kChunkBytes;
+constexpr size_t kBarBytes = (size_t(kMaxConsumerWarps) * kSlotsPerWarp + 2 * kMaxGroups + 2) * 8;
+constexpr uint32_t kSlabCapacity = uint32_t((kSmemCta - kRingBytesMax - kBarBytes - 256) / 8);  // doubles
 
 #if defined(__CUDACC__)
 #define FQ_TP_HD __host__ __device__
@@ -54,8 +68,12 @@ FQ_TP_HD inline uint32_t rec_bytes(uint32_t L) { return uint32_t(kRecHdr) + rec_
 struct TileHdr {  // 32 bytes
   uint32_t cv_begin, ncv;
   uint32_t chunk_begin, nchunks;
-  uint32_t slab_base[kMaxBlocks];
+  uint32_t gb_slot;   // first group record of the tile: (cv_begin >> 5) + tile index
+  uint32_t pad[3];
 };
+inline uint32_t round_plane(uint32_t rs_max) {  // smallest stride >= rs_max that is 1 mod 16
+  return (rs_max + 14u) / 16u * 16u + 1u;
+}
 
 struct BlockDesc {
   int kind, grade, tg, rg;
@@ -75,7 +93,7 @@ struct SetDesc {
   BlockDesc blk[kMaxBlocks];
   int class_grade[kMaxClasses];
   uint32_t class_lo[kMaxClasses], class_hi[kMaxClasses];
-  int cv_words;         // ne + nclasses
+  int cv_words;         // ne + 1
 };
 
 // Description of a block set on n-cells; row ranges default to everything (set them, then call finish_classes).
@@ -104,28 +122,77 @@ inline SetDesc make_set(int n, const std::vector<BlockSpec>& specs) {
   }
   return S;
 }
-inline void finish_classes(SetDesc& S) {
+// Row classes = test grades; blocks of one class must cover the same row range.  false: unsupported set.
+inline bool finish_classes(SetDesc& S) {
   S.nclasses = 0;
   for (int b = 0; b < S.nblocks; ++b) {
     BlockDesc& B = S.blk[b];
     B.rclass = -1;
     if (B.empty) continue;
     for (int c = 0; c < S.nclasses; ++c)
-      if (S.class_grade[c] == B.tg && S.class_lo[c] == B.row_begin && S.class_hi[c] == B.row_end) B.rclass = c;
+      if (S.class_grade[c] == B.tg) {
+        if (S.class_lo[c] != B.row_begin || S.class_hi[c] != B.row_end) return false;
+        B.rclass = c;
+      }
     if (B.rclass < 0) {
+      if (S.nclasses == kMaxClasses) return false;
       S.class_grade[S.nclasses] = B.tg, S.class_lo[S.nclasses] = B.row_begin, S.class_hi[S.nclasses] = B.row_end;
       B.rclass = S.nclasses++;
     }
   }
-  S.cv_words = S.ne + S.nclasses;
+  S.cv_words = S.ne + 1;
+  return true;
 }
 
-// Regions of the blocks in the slab from the largest row-slot count of every row class.
-inline void set_slab_bases(const SetDesc& S, const uint32_t* rs_max, uint32_t* slab_base, uint32_t& total) {
+// Per-grade row-slot budgets of a tile and the plane strides that follow from them.  A row slot is one (cell visit,
+// owned local row) pair; an interior Kuhn vertex brings S_g = dim! * C(dim+1, g+1) of them for grade g.  The slab holds
+// sum_b d_b * plane[tg(b)] doubles whatever the tile, so each tile is limited per grade: R_g = V* * S_g with V* the
+// number of interior vertices the most demanding Hodge set of this dimension can hold.  Then any Hodge set (and any
+// single block) fits.  The planes are compile-time constants of the generated producers (gen_elmat.cpp prints them).
+struct DimBudget {
+  uint32_t vstar = 0;
+  uint32_t budget[4] = {0, 0, 0, 0};  // [grade] row slots of a tile
+  uint32_t plane[4] = {1, 1, 1, 1};   // [grade] plane stride (doubles, 1 mod 16)
+};
+inline DimBudget dim_budget(int dim) {
+  DimBudget db;
+  uint32_t max_nr[4] = {0, 0, 0, 0};
+  double sg[4] = {0, 0, 0, 0};
+  for (int g = 0; g <= dim; ++g) sg[g] = double(fact(dim)) * double(binom(dim + 1, g + 1));
+  // planes are a little larger than the budgets (rounded up to 1 mod 16): find the largest V* whose planes still fit
+  for (uint32_t v = 1; v < 4096; ++v) {
+    bool ok = true;
+    for (int k = 0; k <= dim && ok; ++k) {
+      const SetDesc S = make_set(dim, hodge_blocks(k));
+      uint64_t total = kZeroSlots;
+      for (int b = 0; b < S.nblocks; ++b) {
+        const BlockDesc& B = S.blk[b];
+        if (B.empty) continue;
+        total += uint64_t(round_plane(uint32_t(v * sg[B.tg]))) * uint64_t(B.d);
+        max_nr[B.tg] = std::max(max_nr[B.tg], uint32_t(B.nr));
+        if (uint64_t(v * sg[B.tg]) * uint64_t(B.nr) > uint64_t(kMaxEntries)) ok = false;  // the builder's sort
+        if (v * sg[B.tg] > 65000.0) ok = false;
+      }
+      if (total > kSlabCapacity) ok = false;
+    }
+    if (!ok) break;
+    db.vstar = v;
+  }
+  for (int g = 0; g <= dim; ++g) {
+    db.budget[g] = uint32_t(db.vstar * sg[g]);
+    db.plane[g] = round_plane(db.budget[g]);
+  }
+  return db;
+}
+
+// Plane strides and block regions of the slab: the planes of the dimension's budgets (compile-time constants of the
+// generated producers), regions in block order.
+inline void set_slab_layout(const SetDesc& S, const DimBudget& db, uint32_t* plane, uint32_t* slab_base, uint32_t& total) {
+  for (int c = 0; c < kMaxClasses; ++c) plane[c] = c < S.nclasses ? db.plane[S.class_grade[c]] : 1u;
   uint32_t slab = kZeroSlots;
   for (int b = 0; b < kMaxBlocks; ++b) {
     slab_base[b] = slab;
-    if (b < S.nblocks && !S.blk[b].empty) slab += rs_max[S.blk[b].rclass] * uint32_t(S.blk[b].d);
+    if (b < S.nblocks && !S.blk[b].empty) slab += plane[S.blk[b].rclass] * uint32_t(S.blk[b].d);
   }
   total = slab;
 }
@@ -146,8 +213,10 @@ struct HostPlan {
   std::vector<unsigned char> stream;
   std::vector<uint32_t> row_ptr[kMaxBlocks];  // structural pattern of every block (local rows)
   std::vector<uint32_t> col_idx[kMaxBlocks];
+  std::vector<uint16_t> gbase;                // group records [gb_slot + group][kGroupWords]
   uint32_t max_slab = 0;                      // slab doubles: kZeroSlots + the regions of all blocks
-  uint32_t rs_max[kMaxClasses] = {0, 0, 0, 0};  // largest row-slot count of every row class over the tiles
+  uint32_t rs_max[kMaxClasses] = {0, 0};      // largest row-slot count of every row class over the tiles
+  uint32_t plane[kMaxClasses] = {1, 1};       // plane strides (doubles)
   uint32_t slab_base[kMaxBlocks] = {0, 0, 0, 0};  // region of every block: the SAME for all tiles (a tile's producers
                                               // refill one stage group's region while the consumers still read the others)
   uint64_t nentries[kMaxBlocks] = {0, 0, 0, 0};  // owned element entries (contributions) of every block
@@ -194,10 +263,12 @@ class HostBuilder {
       const BlockDesc& B = S.blk[b];
       P.row_ptr[b].assign(size_t(B.empty ? 0 : B.row_end - B.row_begin) + 1, 0u);
     }
+    set_slab_layout(S, dim_budget(S.n), P.plane, P.slab_base, P.max_slab);
+    if (P.max_slab > slab_capacity_doubles || P.max_slab > 0x10000u) throw std::runtime_error("tile plan: the set exceeds the shared slab");
     std::vector<uint32_t> nchunks(M.ntiles, 0);
     for (uint32_t t = 0; t < M.ntiles; ++t) tile(t, false, slab_capacity_doubles, P, nchunks[t]);
-    set_slab_bases(S, P.rs_max, P.slab_base, P.max_slab);
-    if (P.max_slab > slab_capacity_doubles || P.max_slab > 0x10000u) throw std::runtime_error("tile plan: a tile exceeds the shared slab");
+    for (int c = 0; c < S.nclasses; ++c)
+      if (P.rs_max[c] > P.plane[c]) throw std::runtime_error("tile plan: a tile exceeds its row-slot budget");
     for (int b = 0; b < S.nblocks; ++b) {  // row lengths -> exclusive scan
       uint32_t run = 0;
       for (uint32_t& v : P.row_ptr[b]) {
@@ -215,6 +286,7 @@ class HostBuilder {
     }
     P.stream.assign(size_t(chunk) * kChunkBytes, 0);
     P.cv_rec.assign(size_t(M.tile_cv_ptr[M.ntiles]) * size_t(S.cv_words), 0u);
+    P.gbase.assign((size_t(M.tile_cv_ptr[M.ntiles] >> 5) + M.ntiles + 1) * kGroupWords, uint16_t(0));
     for (uint32_t t = 0; t < M.ntiles; ++t) {
       uint32_t n2 = 0;
       tile(t, true, slab_capacity_doubles, P, n2);
@@ -235,12 +307,15 @@ class HostBuilder {
     if (ncv > uint32_t(kMaxCv)) throw std::runtime_error("tile plan: too many cell visits in a tile");
     TileHdr& H = P.tiles[t];
     H.cv_begin = cv0, H.ncv = ncv;
-    // row classes: owned-row masks and first row slots of every cell visit
-    std::vector<uint32_t> mask[kMaxClasses], base[kMaxClasses];
-    uint32_t RS[kMaxClasses] = {0, 0, 0, 0};
+    H.gb_slot = (cv0 >> 5) + t;
+    // row classes: owned-row masks of every cell visit; row slots numbered (group of 32 cell visits, local row, cell visit)
+    std::vector<uint32_t> mask[kMaxClasses];
+    std::vector<uint16_t> rs[kMaxClasses];  // [cv * kMaxLocal + row]
+    const uint32_t ngroups = (ncv + 31u) / 32u;
     for (int c = 0; c < S.nclasses; ++c) {
       const int g = S.class_grade[c], nl = S.nl[g];
-      mask[c].assign(ncv, 0), base[c].assign(ncv, 0);
+      mask[c].assign(ncv, 0);
+      rs[c].assign(size_t(ncv) * kMaxLocal, 0);
       for (uint32_t i = 0; i < ncv; ++i) {
         const size_t cell = M.tile_cv_cells[cv0 + i];
         uint32_t m = 0;
@@ -250,19 +325,26 @@ class HostBuilder {
           if (M.vertex_tile[topv - M.v_lo] == t && row >= S.class_lo[c] && row < S.class_hi[c]) m |= 1u << r;
         }
         mask[c][i] = m;
-        base[c][i] = RS[c];
-        RS[c] += uint32_t(__builtin_popcount(m));
       }
+      uint32_t counter = 0;
+      for (uint32_t G = 0; G < ngroups; ++G)
+        for (int r = 0; r < nl; ++r) {
+          if (emit) P.gbase[(size_t(H.gb_slot) + G) * kGroupWords + size_t(c) * kMaxLocal + r] = uint16_t(counter);
+          for (uint32_t i = 32u * G; i < std::min(ncv, 32u * G + 32u); ++i)
+            if (mask[c][i] >> r & 1u) rs[c][size_t(i) * kMaxLocal + r] = uint16_t(counter++);
+        }
+      if (counter > 0xFFFFu) throw std::runtime_error("tile plan: too many row slots in a tile");
+      P.rs_max[c] = std::max(P.rs_max[c], counter);
     }
     (void)cap;
-    for (int c = 0; c < S.nclasses; ++c) P.rs_max[c] = std::max(P.rs_max[c], RS[c]);
-    for (int b = 0; b < kMaxBlocks; ++b) H.slab_base[b] = P.slab_base[b];
     if (emit)
       for (uint32_t i = 0; i < ncv; ++i) {
         const size_t cell = M.tile_cv_cells[cv0 + i];
         uint32_t* rec = P.cv_rec.data() + size_t(cv0 + i) * S.cv_words;
         for (int e = 0; e < S.ne; ++e) rec[e] = M.faces[1][cell * S.ne + e];
-        for (int c = 0; c < S.nclasses; ++c) rec[S.ne + c] = mask[c][i] | (base[c][i] << 8);
+        uint32_t word = 0;
+        for (int c = 0; c < S.nclasses; ++c) word |= mask[c][i] << (8 * c);
+        rec[S.ne] = word;
       }
     // blocks
     unsigned char* sbase = emit ? P.stream.data() + size_t(H.chunk_begin) * kChunkBytes : nullptr;
@@ -277,12 +359,12 @@ class HostBuilder {
         const uint32_t m = mask[c][i];
         for (int r = 0; r < B.nt; ++r) {
           if (!(m >> r & 1u)) continue;
-          const uint32_t rs = base[c][i] + uint32_t(__builtin_popcount(m & ((1u << r) - 1u)));
+          const uint32_t slot = rs[c][size_t(i) * kMaxLocal + r];
           const uint32_t row = M.faces[B.tg][cell * B.nt + r];
           for (int j = 0; j < B.nr; ++j) {
             const uint32_t col = M.faces[B.rg][cell * B.nr + j];
             const uint8_t cs = B.cs[r * B.nr + j];
-            const uint32_t code = cs == 0xFF ? 0u : H.slab_base[b] + rs * uint32_t(B.d) + cs;
+            const uint32_t code = cs == 0xFF ? 0u : P.slab_base[b] + uint32_t(cs) * P.plane[c] + slot;
             ents.push_back(Ent{(uint64_t(row) << 32) | col, uint16_t(code)});
           }
         }

@@ -32,17 +32,28 @@ using namespace fq;
 struct HostSink {
   double* slab;
   const tp::SetDesc* S;
+  const tp::HostPlan* P;
   const tp::TileHdr* H;
-  const uint32_t* meta;  // per row class: mask | base << 8
-  bool bad_d = false;
-  template <int B, int R, int CS, int DD>
+  uint32_t cv;           // cell visit within the tile
+  bool bad = false;
+  // row slot of (class C, local row R) of this cell visit the way the producers find it: the group record's first
+  // slot + the number of lower cell visits of the group that own the row
+  uint32_t row_slot(int C, int R) const {
+    const uint32_t G = cv >> 5;
+    uint32_t rs = P->gbase[(size_t(H->gb_slot) + G) * tp::kGroupWords + size_t(C) * tp::kMaxLocal + R];
+    for (uint32_t i = 32u * G; i < cv; ++i) {
+      const uint32_t word = P->cv_rec[size_t(H->cv_begin + i) * S->cv_words + S->ne];
+      rs += (word >> (8 * C) >> R) & 1u;
+    }
+    return rs;
+  }
+  template <int B, int R, int CS, int DD, int C>
   void put(double v) {
     const tp::BlockDesc& D = S->blk[B];
-    if (DD != D.d) bad_d = true;
-    const uint32_t m = meta[D.rclass] & 0xFFu, base = meta[D.rclass] >> 8;
-    if (!(m >> R & 1u)) return;
-    const uint32_t rs = base + uint32_t(__builtin_popcount(m & ((1u << R) - 1u)));
-    slab[H->slab_base[B] + rs * uint32_t(D.d) + CS] = v;
+    if (DD != D.d || C != D.rclass) bad = true;
+    const uint32_t word = P->cv_rec[size_t(H->cv_begin + cv) * S->cv_words + S->ne];
+    if (!((word >> (8 * C) >> R) & 1u)) return;
+    slab[P->slab_base[B] + uint32_t(CS) * P->plane[C] + row_slot(C, R)] = v;
   }
 };
 
@@ -123,7 +134,10 @@ static bool run_case(int n, const std::vector<int64_t>& shape, const std::vector
     S.blk[b].row_begin = 0;
     S.blk[b].row_end = S.blk[b].empty ? 0u : uint32_t(cx.nsimplices(S.blk[b].tg));
   }
-  tp::finish_classes(S);
+  if (!tp::finish_classes(S)) {
+    std::printf("unsupported set\n");
+    return false;
+  }
   tp::HostMesh M;
   M.ncells = ncells;
   for (int g = 0; g <= n; ++g) M.faces[g] = faces[size_t(g)].data();
@@ -132,7 +146,7 @@ static bool run_case(int n, const std::vector<int64_t>& shape, const std::vector
   M.tile_cv_ptr = cv_ptr.data();
   M.tile_cv_cells = cv_cells.data();
   tp::HostBuilder builder(S, M);
-  const tp::HostPlan P = builder.build(22000);
+  const tp::HostPlan P = builder.build(tp::kSlabCapacity);
   const SetFn* fn = find_set(n, fused_k, kind, grade);
   if (!fn) {
     std::printf("no generated set for n=%d fused_k=%d kind=%d grade=%d\n", n, fused_k, kind, grade);
@@ -157,10 +171,10 @@ static bool run_case(int n, const std::vector<int64_t>& shape, const std::vector
       double s[6], mid[32];
       for (int e = 0; e < S.ne; ++e) s[e] = len[rec[e]];
       fn->a(s, mid);
-      HostSink sink{slab.data(), &S, &H, rec + S.ne, false};
+      HostSink sink{slab.data(), &S, &P, &H, i, false};
       for (int g = 0; g < 3; ++g) fn->g[g](mid, sink);
-      if (sink.bad_d) {
-        std::printf("generated put<> carries a wrong slot count\n");
+      if (sink.bad) {
+        std::printf("generated put<> carries a wrong slot count or row class\n");
         return false;
       }
     }
