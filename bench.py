@@ -120,22 +120,26 @@ def cpu_assembly_sample(sample_n: int | None, budget_s: float = 20.0):
     def run(n):
         cx = O.Complex.kuhn(DIM, n)
         s = cx.edge_lengths_sq(O.kuhn_vertex_coords(DIM, n))
-        total, nnz = 0.0, 0
+        total, nnz, par, ser = 0.0, 0, 0.0, 0.0
         for kind, k in ((O.MASS, GRADE - 1), (O.MASS, GRADE), (O.DIF_TEST, GRADE), (O.DIF_BOTH, GRADE + 1)):
             tm = np.zeros(2)
             a = cx.assemble(s, kind, k, nthreads=threads, times=tm)
             total += float(tm.sum())
+            par += float(tm[0])
+            ser += float(tm[1])
             nnz += a.nnz
-        return cx.ncells, nnz, total
+        return cx.ncells, nnz, total, par, ser
 
     if sample_n is None:
-        cells, _, t = run(12)
+        cells, _, t, _, _ = run(12)
         rate = cells / t
         sample_n = int(max(12, min(64, (budget_s * rate / 6.0) ** (1.0 / 3.0))))
         sample_n -= sample_n % 4
-    cells, nnz, t = run(sample_n)
+    cells, nnz, t, t_par, t_ser = run(sample_n)
     return {"value": cells / t, "nnz_per_s": nnz / t, "cores": threads, "seconds": t,
-            "sample": f"3-D Kuhn cube N={sample_n} ({cells} tets), four Hodge blocks k=1, {threads} threads + serial COO->CSR"}
+            "parallel_elmat_s": t_par, "serial_coo_to_csr_s": t_ser,
+            "sample": f"3-D Kuhn cube N={sample_n} ({cells} tets), four Hodge blocks k=1: element matrices on {threads} threads "
+                      f"({t_par:.1f} s) + serial COO->CSR as in the reference ({t_ser:.1f} s)"}
 
 
 def run_reference(args):
@@ -157,7 +161,8 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3-D Hodge-Laplace k=1 mixed (AFW) assembly, Kuhn unit cube, four blocks; CPU sample of the "
                                f"N={args.n} per-GPU workload", "sample": last["sample"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
+                         "parallel_elmat_s": last["parallel_elmat_s"], "serial_coo_to_csr_s": last["serial_coo_to_csr_s"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "nnz_per_s": sum(v["nnz_per_s"] for v in vals) / len(vals),
     }
@@ -201,8 +206,18 @@ def run_b200(args):
     # HodgeBlocks plan: symbolic once (pattern + cell-slot -> nnz maps), rows owned by this rank
     hb = fq.HodgeBlocks.symbolic(mesh, GRADE, sigma_rows=mesh.owned_range(GRADE - 1), u_rows=mesh.owned_range(GRADE))
     mats = [(name, form, a) for (name, form), a in zip(forms, hb.blocks)]
-    sym_report = ctx.timing_report()
+    ctx.timing_report()
     owned_cells = mesh.nowned_cells
+    # first numeric pass of a fresh HodgeBlocks: builds the tile plan (= the symbolic phase: structural patterns + record
+    # streams), runs the fused kernel on the structural pattern, compacts to the reference's `!= 0.0` pattern and
+    # retargets the streams.  Reported separately: this is what a one-shot assembly pays.
+    torch.cuda.synchronize()
+    t_first = time.perf_counter()
+    hb.numeric(mesh, True)
+    torch.cuda.synchronize()
+    first_pass_wall_ms = 1e3 * (time.perf_counter() - t_first)
+    first_report = ctx.timing_report()
+    plan_build_ms = hb.blocks[1].plan_build_ms
 
     def step():
         hb.numeric(mesh, True)  # one fused element kernel + one segmented reduction per block
@@ -244,7 +259,34 @@ def run_b200(args):
             clocks["note"] = "timed region shorter than the sampling period: sampled over extra untimed steps of the same kernel"
         ctx.timing_report()
     nnz_local = sum(a.nnz for _, _, a in mats)
-    asm_bytes = sum(a.assembly_bytes for _, _, a in mats)
+    # SURVEY 8d per-block formula summed over the blocks, and the same with the inputs the fused launch shares (edge
+    # lengths + cell -> edge ids) counted ONCE: the second one is what one launch of the fused kernel has to move
+    asm_bytes_per_block_sum = sum(a.assembly_bytes for _, _, a in mats)
+    shared_bytes = max(a.assembly_shared_bytes for _, _, a in mats)
+    asm_bytes = shared_bytes + sum(a.assembly_bytes - a.assembly_shared_bytes for _, _, a in mats)
+
+    # ---- SpMV of the KKT operator [[M0, -dif_test], [dif_test^T, dif_both]] that MINRES / Lanczos apply (1 GPU)
+    kkt_entry = None
+    if world == 1 and not args.no_kkt:
+        try:
+            kkt = hb.mixed_hodge_laplacian()
+            xk = fq.DeviceVector.from_torch(ctx, torch.cos(torch.arange(kkt.shape[1], device="cuda", dtype=torch.float64) ** 2 + 1.0))
+            yk = fq.DeviceVector(ctx, kkt.shape[0])
+            for _ in range(max(args.warmup, 1)):
+                kkt.apply(xk, yk)
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            for _ in range(args.steps):
+                kkt.apply(xk, yk)
+            k1.record(stream)
+            torch.cuda.synchronize()
+            kms = k0.elapsed_time(k1) / args.steps
+            kkt_entry = {"nnz": kkt.nnz, "n": kkt.shape[0], "ms": kms, "gbs": kkt.spmv_bytes / 1e9 / (kms / 1e3),
+                         "bytes": kkt.spmv_bytes}
+            del kkt, xk, yk
+        except Exception as exc:
+            print(f"[bench] KKT SpMV skipped: {exc}", file=sys.stderr)
 
     # ---- SpMV: every block, K applies each (halo exchange included when world > 1)
     spmv = []
@@ -291,6 +333,12 @@ def run_b200(args):
                 barrier()
                 ph.check()
                 entry["peer_ms"] = p0.elapsed_time(p1) / args.steps
+                # the fused kernel must give the bits of exchange + windowed SpMV
+                exchange_halo(xw, part, rank)
+                y_ref = a.apply_window(x, r.held_lo).to_torch().clone()
+                ph.publish(); ph.apply(a, y); ph.release()
+                torch.cuda.synchronize()
+                entry["peer_parity"] = bool(torch.equal(y.to_torch(), y_ref))
                 del ph, xv
             except Exception as exc:  # never lose the bench line to the optional fused measurement
                 print(f"[bench] fused peer SpMV skipped on rank {rank}: {exc}", file=sys.stderr)
@@ -323,6 +371,9 @@ def run_b200(args):
     if world == 1:
         peer_ms = [None for _ in spmv]
     spmv_bytes = [allsum(s["bytes"]) for s in spmv]
+    peer_parity = None
+    if world > 1 and all("peer_parity" in s for s in spmv):
+        peer_parity = allsum(sum(0 if s["peer_parity"] else 1 for s in spmv)) == 0
     secs = ms_total / 1e3
     value = cells_all * args.steps / secs
 
@@ -336,49 +387,51 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    # dominant block pipeline (K1 element slab + K3 gather + compaction) for the roofline line
     per_launch = {k: v["ms"] / max(v["count"], 1) for k, v in kern.items()}
     asm_kernel_ms = sum(v["ms"] for k, v in kern.items() if k.startswith(("k1", "k3"))) / args.steps  # k13_tile_fused included
     fused = kern.get("k13_tile_fused", {}).get("count", 0) > 0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_tile_traffic.json")
-    if fused and os.path.exists(tp):  # dram__bytes_read+write per launch of the same workload, from the committed ncu capture
+    kernel_name = "tile_fused_kernel<n3_hodge1, 16+16 warps>" if fused else "k1_elmat + k3_gather (slab path)"
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_tile_traffic.json")
+    if fused and os.path.exists(tp):  # dram__bytes_read+write per launch of the same kernel and workload (ncu --set full)
         tj = json.load(open(tp))
-        if tj.get("n") == n and tj.get("cells") == owned_cells:
-            traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("n") == n and tj.get("cells") == owned_cells and tj.get("kernel") == kernel_name:
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     achieved = (asm_bytes / 1e9) / (asm_kernel_ms / 1e3) if asm_kernel_ms > 0 else 0.0
     big = max(range(len(spmv)), key=lambda i: spmv[i]["nnz"])
+    fused_ms = per_launch.get("k13_tile_fused", 0.0)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3-D Hodge-Laplace k=1 mixed (AFW): numeric assembly of M0, M1, dif_test(1), dif_both(2) "
-                               f"on a Kuhn grid {shape[0]}x{shape[1]}x{shape[2]} ({int(cells_all)} tets, {n}^3 boxes per GPU), "
-                               f"reference `!= 0.0` pattern semantics", "cells_per_gpu": owned_cells,
-                   "l2_policy": "inputs_larger_than_l2 (the per-tile map stream and the CSR values are GBs per step, L2 is 126 MB)",
-                   "parallelism": f"owner-computes z-slabs x{world}, no collective on the assembly path"},
+        "config": {"workload": f"3-D Hodge-Laplace k=1 mixed (AFW): numeric assembly of M0, M1, dif_test(1), dif_both(2) on a Kuhn "
+                               f"grid {shape[0]}x{shape[1]}x{shape[2]} ({int(cells_all)} tets), `!= 0.0` pattern semantics",
+                   "cells_per_gpu": owned_cells, "l2_policy": "inputs_larger_than_l2",
+                   "parallelism": f"owner-computes z-slabs x{world}, no assembly collective"},
         "nnz_per_s": nnz_all * args.steps / secs, "nnz": int(nnz_all),
         "spmv": {"block": spmv[big]["block"], "gbs": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3),
                  "ms": spmv_ms[big], "frac_of_hbm_peak": spmv_bytes[big] / 1e9 / (spmv_ms[big] / 1e3) / (peak * world),
                  "all_blocks_gbs": sum(spmv_bytes) / 1e9 / (sum(spmv_ms) / 1e3),
-                 "halo_exchange": "torch.distributed NCCL send/recv with z-neighbours" if world > 1 else "none (1 GPU)",
+                 "halo_exchange": "nccl send/recv" if world > 1 else "none",
                  "fused_peer_ms": peer_ms[big],
                  "fused_peer_gbs": (spmv_bytes[big] / 1e9 / (peer_ms[big] / 1e3)) if peer_ms[big] else None,
-                 "fused_peer": "one kernel: halo columns loaded from the neighbours' HBM over NVLink (CUDA IPC) inside the "
-                               "SpMV gather, epoch flags instead of a collective" if world > 1 else None},
+                 "spmv_multi_gpu_parity": peer_parity,
+                 "kkt": None if kkt_entry is None else {**kkt_entry, "frac_of_hbm_peak": kkt_entry["gbs"] / peak}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic,
-                     "kernel": ("tile_assemble_alt_kernel: K1 element masses (8 producer warps) + K3 segmented reduction "
-                                "(16 consumer warps) fused in shared memory, all four blocks in one persistent launch "
-                                "(rank 0)") if fused else
-                               "numeric assembly pipeline K1 elmat -> K3 gather -> compaction (rank 0, all four blocks)",
-                     "algorithmic_bytes_per_step": asm_bytes, "peak_source": peak_src,
-                     "kernel_ms_per_launch": per_launch},
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
+                     "algorithmic_bytes_fused": asm_bytes, "algorithmic_bytes_per_block_sum": asm_bytes_per_block_sum,
+                     "peak_source": peak_src, "kernel_ms_per_launch": per_launch},
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in kern.items()},
-        "symbolic_ms": {k: v["ms"] for k, v in sym_report.items()},
+        "first_pass": {"wall_ms": first_pass_wall_ms, "tile_plan_ms": plan_build_ms,
+                       "device_ms": {k: round(v["ms"], 3) for k, v in first_report.items()},
+                       "note": "first numeric pass after symbolic(): plan build (structural pattern + streams) + fused kernel "
+                               "+ compaction + retarget; later passes run the fused kernel alone"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if fused and args.slab_ms:  # break-even of the plan against re-running the two-kernel slab path (FQ_NO_TILE=1 bench)
+        out["first_pass"]["break_even_steps_vs_slab"] = plan_build_ms / max(args.slab_ms - fused_ms, 1e-9)
+        out["first_pass"]["slab_path_ms_per_step"] = args.slab_ms
     if e2e is not None:
         out["e2e"] = e2e
     try:
@@ -386,7 +439,8 @@ def run_b200(args):
             raise RuntimeError("skipped (--no-cpu)")
         cb = cpu_assembly_sample(args.sample_n)
         out["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
-                               "nnz_per_s": cb["nnz_per_s"]}
+                               "nnz_per_s": cb["nnz_per_s"], "parallel_elmat_s": cb["parallel_elmat_s"],
+                               "serial_coo_to_csr_s": cb["serial_coo_to_csr_s"]}
     except Exception as exc:  # the oracle is only the checker; never let it break the GPU line
         out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
     sys.stdout.flush()
@@ -471,13 +525,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=128, help="boxes per axis per GPU (128 -> 12.58 M tets)")
-    ap.add_argument("--sample-n", type=int, default=None, help="Kuhn cube size of the CPU sample (default: calibrated)")
+    ap.add_argument("--sample-n", type=int, default=64, help="Kuhn cube size of the CPU sample (0: calibrate to ~20 s)")
+    ap.add_argument("--no-kkt", action="store_true", help="skip the KKT-operator SpMV")
+    ap.add_argument("--slab-ms", type=float, default=10.95,
+                    help="ms per step of the two-kernel slab path on this workload (FQ_NO_TILE=1 run; default: the "
+                         "round-1 measurement, profiles/r01_v11_bench_n128.json) for the plan break-even")
     ap.add_argument("--e2e-n", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning runs only)")
     ap.add_argument("--no-peer", action="store_true", help="skip the fused peer-memory SpMV measurement (N > 1)")
     args = ap.parse_args()
+    if args.sample_n == 0:
+        args.sample_n = None
     if args.impl == "reference":
         run_reference(args)
     else:

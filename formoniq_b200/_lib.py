@@ -70,6 +70,8 @@ SIGNATURES = [
     ("fq_csr_upload", _i, [_vp, _sz, _sz, _vp, _vp, _vp, _P(_vp)]),
     ("fq_csr_destroy", _i, [_vp]),
     ("fq_csr_assembly_bytes", _i64, [_vp]),
+    ("fq_csr_assembly_shared_bytes", _i64, [_vp]),
+    ("fq_csr_plan_build_ms", C.c_double, [_vp]),
     ("fq_csr_spmv_bytes", _i64, [_vp]),
     ("fq_vec_create", _i, [_vp, _sz, _P(_vp)]),
     ("fq_vec_wrap", _i, [_vp, _vp, _sz, _P(_vp)]),

@@ -400,6 +400,15 @@ class DeviceCsr:
         return _lib.lib().fq_csr_assembly_bytes(self._h)
 
     @property
+    def assembly_shared_bytes(self) -> int:
+        """Inputs (edge lengths, cell -> edge ids) that blocks assembled in one fused launch read once."""
+        return _lib.lib().fq_csr_assembly_shared_bytes(self._h)
+
+    @property
+    def plan_build_ms(self) -> float:
+        return _lib.lib().fq_csr_plan_build_ms(self._h)
+
+    @property
     def spmv_bytes(self) -> int:
         return _lib.lib().fq_csr_spmv_bytes(self._h)
 

@@ -14,6 +14,7 @@
 //     compacted to exactly the reference's value-dependent pattern.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <functional>
 
 #include "internal.hpp"
@@ -340,7 +341,8 @@ static void numeric_reduce(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* csr, bool d
   const size_t s_nnz = csr->s_nnz;
   const int block = 256;
   const int ne = int(binom(mesh->dim + 1, 2));
-  csr->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csr->ncontrib);
+  csr->assembly_shared_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells);
+  csr->assembly_bytes = csr->assembly_shared_bytes + int64_t(4 * csr->ncontrib);
   if (!drop_exact_zeros || s_nnz == 0) {
     // the structural pattern is the result; its index arrays are shared once
     if (csr->dropped || csr->row_ptr.n != nrows_local + 1 || csr->nnz != s_nnz || !csr->pattern_valid) {
@@ -417,6 +419,14 @@ static bool tile_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, 
     if (!plan) {
       ScopedSpan span(ctx, "tile_plan_build");
       plan = tile_plan_build(ctx, mesh, csrs, nblocks);
+      // generic clustering estimates the cell visits of a tile: when a tile turns out too large, cut smaller ones
+      for (int retry = 0; !plan && mesh->cluster_generic && retry < 3; ++retry) {
+        fq_mesh* m = const_cast<fq_mesh*>(mesh);
+        m->cluster_scale *= 1.35f;
+        tile_cluster_generic(ctx, m);
+        if (!mesh->vertex_tile.p) break;
+        plan = tile_plan_build(ctx, mesh, csrs, nblocks);
+      }
       for (int b = 0; b < nblocks; ++b) {
         csrs[b]->tile_plan = plan;
         csrs[b]->pattern_valid = false;
@@ -427,7 +437,15 @@ static bool tile_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, 
         csrs[0]->tile_refused = 1;  // does not apply to this block set / mesh: stay on the slab path
         return false;
       }
-      for (int b = 0; b < nblocks; ++b) csrs[b]->slab.release();
+      for (int b = 0; b < nblocks; ++b) {  // the slab path's buffers are not needed any more
+        csrs[b]->slab.release();
+        if (csrs[b]->s_nnz > 0 && csrs[b]->k2_done) {
+          csrs[b]->contrib_ptr.release();
+          csrs[b]->contrib_src.release();
+          csrs[b]->gather_blocks.release();
+          csrs[b]->k2_done = false;
+        }
+      }
     }
     double* vals[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t* keeps[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -486,14 +504,22 @@ void assemble_numeric_multi(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csr
     bool ready = nblocks >= 1 && csrs[0]->tile_refused == 0;
     for (int b = 0; ready && b < nblocks; ++b)
       ready = csrs[b]->has_plan && csrs[b]->ncells == mesh->ncells && csrs[b]->dim == mesh->dim;
+    // Uploaded meshes: a one-shot assembly (BilinearForm::assemble: symbolic + one numeric pass) is cheaper through K2 and
+    // the slab path than through a tile plan (the plan builder sorts every tile's entries twice: ~60 ms per block at
+    // 12.6 M tets against ~30 ms for K2); the fused kernel takes over when the matrix is assembled again.  Meshes from
+    // the device Kuhn generator carry closed-form bricks and go through the fused kernel from the first pass.
+    if (ready && !mesh->vertex_tile.p && !std::getenv("FQ_TILE_FIRST")) {
+      for (int b = 0; ready && b < nblocks; ++b) ready = csrs[b]->slab_passes >= 1;
+    }
     if (ready && !mesh->vertex_tile.p && !mesh->cluster_tried)
-      tile_cluster_generic(ctx, const_cast<fq_mesh*>(mesh));  // uploaded meshes: clustered once, on first use
+      tile_cluster_generic(ctx, const_cast<fq_mesh*>(mesh));  // clustered once, on first reuse
     ready = ready && mesh->vertex_tile.p != nullptr;
     if (ready && tile_numeric(ctx, mesh, csrs, nblocks, drop_exact_zeros)) {
       const int ne = int(binom(mesh->dim + 1, 2));
-      for (int b = 0; b < nblocks; ++b)
-        csrs[b]->assembly_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells + 4 * csrs[b]->ncontrib +
-                                          8 * csrs[b]->nnz);
+      for (int b = 0; b < nblocks; ++b) {
+        csrs[b]->assembly_shared_bytes = int64_t(8 * mesh->lengths.n + 4 * size_t(ne) * mesh->ncells);
+        csrs[b]->assembly_bytes = csrs[b]->assembly_shared_bytes + int64_t(4 * csrs[b]->ncontrib + 8 * csrs[b]->nnz);
+      }
       return;
     }
   }

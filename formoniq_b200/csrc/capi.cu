@@ -657,6 +657,8 @@ int fq_csr_destroy(fq_csr* csr) {
   return FQ_OK;
 }
 int64_t fq_csr_assembly_bytes(const fq_csr* csr) { return csr ? csr->assembly_bytes : 0; }
+int64_t fq_csr_assembly_shared_bytes(const fq_csr* csr) { return csr ? csr->assembly_shared_bytes : 0; }
+double fq_csr_plan_build_ms(const fq_csr* csr) { return csr ? csr->plan_build_ms : 0.0; }
 int64_t fq_csr_spmv_bytes(const fq_csr* csr) {
   if (!csr) return 0;
   const size_t nrows_local = csr->row_end - csr->row_begin;

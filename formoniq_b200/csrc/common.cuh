@@ -168,6 +168,8 @@ struct fq_mesh {
   // The tile kernel numbers a tile's cells type-major so that same-type gathers hit distinct banks.
   int cell_type_period = 0;
   bool cluster_tried = false;  // generic meshes are clustered lazily, when a tile plan is first built
+  bool cluster_generic = false;  // tiles = runs of consecutive vertices sized by weight (tile.cu: tile_cluster_generic)
+  float cluster_scale = 0.0f;    // weight scale of the generic clustering; raised when a tile exceeds a budget
 };
 
 struct fq_vec {
@@ -206,6 +208,7 @@ struct fq_csr {
   bool compact_valid = false;       // pos / keep / compacted pattern describe the last geometry
   bool pattern_valid = false;
   int64_t assembly_bytes = 0;
+  int64_t assembly_shared_bytes = 0;  // inputs a fused launch reads once for all its blocks
   // SpMV row blocks (CSR-stream)
   fq::DevBuf<uint32_t> rowblocks;
   size_t nrowblocks = 0;

@@ -1093,75 +1093,97 @@ void tile_cluster_kuhn(fq_ctx* ctx, fq_mesh* mesh, int dim, const size_t* shape,
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// Generic meshes: greedy breadth-first growth of vertex clusters on the host (once per mesh), each limited by the
-// slab doubles, cell visits and per-block entries it may need.  cell_verts is the grade-0 face table.
+// Generic (uploaded) meshes: vertices are cut into tiles along their numbering, on the device.  Every vertex gets a
+// weight = its share of the tightest tile budget (row slots per grade are additive over vertices; the cell visits are
+// estimated as half the incident cells, neighbouring vertices sharing about that many); a tile is a run of
+// consecutive vertices of total weight ~1/scale.  Mesh generators number vertices with locality (Kuhn grids: x-lines),
+// so the runs are compact; the plan builder verifies the budgets exactly and the caller retries with a larger scale
+// (smaller tiles) when one is exceeded.
+__global__ void vertex_weight_kernel(const uint32_t* __restrict__ cell_verts, int nv, size_t ncells, size_t V,
+                                     uint32_t* __restrict__ rs /*[nv][V]*/, uint32_t* __restrict__ deg, int* __restrict__ err) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t c = size_t(blockIdx.x) * blockDim.x + threadIdx.x; c < ncells; c += stride)
+    for (int j = 0; j < nv; ++j) {
+      const uint32_t v = cell_verts[c * nv + j];
+      if (v >= V) {
+        *err = 1;
+        continue;
+      }
+      atomicAdd(&deg[v], 1u);
+      // faces of grade g with this vertex on top: C(j, g)
+      uint32_t bin = 1;
+      for (int g = 0; g < nv; ++g) {
+        if (bin) atomicAdd(&rs[size_t(g) * V + v], bin);
+        bin = bin * uint32_t(j - g) / uint32_t(g + 1);
+      }
+    }
+}
+struct VertexCostArgs {
+  float inv_budget[4];
+  float inv_cv;
+  float scale;
+  int ngrades;
+};
+__global__ void vertex_cost_kernel(size_t V, const uint32_t* __restrict__ rs, const uint32_t* __restrict__ deg, VertexCostArgs A,
+                                   unsigned long long* __restrict__ w) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride) {
+    float cost = float(deg[v]) * A.inv_cv;
+    for (int g = 0; g < A.ngrades; ++g) cost = fmaxf(cost, float(rs[size_t(g) * V + v]) * A.inv_budget[g]);
+    w[v] = (unsigned long long)(double(cost * A.scale) * 1048576.0) + 1ull;  // fixed point: the scan is exact
+  }
+}
+__global__ void vertex_tile_from_prefix_kernel(size_t V, const unsigned long long* __restrict__ prefix /*exclusive*/,
+                                               uint32_t* __restrict__ vtile) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride) vtile[v] = uint32_t(prefix[v] >> 20);
+}
 void tile_cluster_generic(fq_ctx* ctx, fq_mesh* mesh) {
   const int dim = mesh->dim;
   mesh->cluster_tried = true;
   if (dim > 3 || std::getenv("FQ_NO_TILE") || !mesh->cell_faces[0].p || mesh->edge_lo != 0 || mesh->cell_offset != 0) return;
-  std::vector<uint32_t> cell_verts(mesh->cell_faces[0].n);
-  FQ_CUDA(cudaMemcpyAsync(cell_verts.data(), mesh->cell_faces[0].p, cell_verts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                          ctx->stream));
-  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  ScopedSpan span(ctx, "tp_cluster");
   const DimBudget& dc = dim_cost(dim);
-  const size_t nv = size_t(dim) + 1, ncells = mesh->ncells, V = mesh->nsimplices[0];
+  const int nv = dim + 1, block = 256;
+  const size_t ncells = mesh->ncells, V = mesh->nsimplices[0];
   if (V == 0 || ncells == 0 || V >= (size_t(1) << 32)) return;
-  // vertex -> cells incidence (CSR)
-  std::vector<uint32_t> vptr(V + 1, 0);
-  for (size_t i = 0; i < ncells * nv; ++i) {
-    if (cell_verts[i] >= V) return;  // malformed table: leave the mesh unclustered (slab path)
-    vptr[size_t(cell_verts[i]) + 1] += 1;
-  }
-  for (size_t v = 0; v < V; ++v) vptr[v + 1] += vptr[v];
-  std::vector<uint32_t> vcells(ncells * nv), fill(vptr.begin(), vptr.end() - 1);
-  std::vector<uint8_t> vpos(ncells * nv);
-  for (size_t c = 0; c < ncells; ++c)
-    for (size_t j = 0; j < nv; ++j) {
-      const uint32_t at = fill[size_t(cell_verts[c * nv + j])]++;
-      vcells[at] = uint32_t(c);
-      vpos[at] = uint8_t(j);
-    }
-  const uint32_t kNone = 0xFFFFFFFFu;
-  std::vector<uint32_t> vtile(V, kNone), stamp(ncells, kNone), queue;
-  uint32_t ntiles = 0;
-  for (size_t seed = 0; seed < V; ++seed) {
-    if (vtile[seed] != kNone) continue;
-    const uint32_t T = ntiles++;
-    uint32_t ncells_T = 0;
-    double rs_T[4] = {0, 0, 0, 0};
-    queue.clear();
-    queue.push_back(uint32_t(seed));
-    for (size_t head = 0; head < queue.size(); ++head) {
-      const uint32_t v = queue[head];
-      if (vtile[v] != kNone) continue;
-      uint32_t fresh = 0;
-      double rs_v[4] = {0, 0, 0, 0};
-      for (uint32_t p = vptr[v]; p < vptr[v + 1]; ++p) {
-        fresh += stamp[vcells[p]] != T;
-        for (int g = 0; g <= dim; ++g) rs_v[g] += double(binom(vpos[p], g));  // faces of grade g with this vertex on top
-      }
-      bool fits = ncells_T + fresh <= uint32_t(kMaxCv);
-      for (int g = 0; g <= dim; ++g) fits = fits && rs_T[g] + rs_v[g] <= double(dc.budget[g]);
-      if (ncells_T > 0 && !fits) continue;  // does not fit: left for a later tile
-      vtile[v] = T;
-      ncells_T += fresh;
-      for (int g = 0; g <= dim; ++g) rs_T[g] += rs_v[g];
-      for (uint32_t p = vptr[v]; p < vptr[v + 1]; ++p) {
-        const uint32_t c = vcells[p];
-        if (stamp[c] == T) continue;
-        stamp[c] = T;
-        for (size_t j = 0; j < nv; ++j) {
-          const uint32_t w = uint32_t(cell_verts[size_t(c) * nv + j]);
-          if (vtile[w] == kNone) queue.push_back(w);
-        }
-      }
-    }
-  }
+  if (mesh->cluster_scale <= 0.0f) mesh->cluster_scale = 1.1f;
+  DevBuf<uint32_t> rs(size_t(nv) * V), deg(V);
+  DevBuf<unsigned long long> w(V + 1), prefix(V + 1);
+  DevBuf<int> d_err(1);
+  FQ_CUDA(cudaMemsetAsync(rs.p, 0, rs.bytes(), ctx->stream));
+  FQ_CUDA(cudaMemsetAsync(deg.p, 0, deg.bytes(), ctx->stream));
+  FQ_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+  vertex_weight_kernel<<<grid_for(ncells, block, ctx->sm_count), block, 0, ctx->stream>>>(mesh->cell_faces[0].p, nv, ncells, V, rs.p,
+                                                                                         deg.p, d_err.p);
+  VertexCostArgs A{};
+  A.ngrades = nv;
+  for (int g = 0; g < nv; ++g) A.inv_budget[g] = dc.budget[g] ? 1.0f / float(dc.budget[g]) : 0.0f;
+  A.inv_cv = 1.0f / (2.0f * float(kMaxCv));
+  A.scale = mesh->cluster_scale;
+  vertex_cost_kernel<<<grid_for(V, block, ctx->sm_count), block, 0, ctx->stream>>>(V, rs.p, deg.p, A, w.p);
+  FQ_CUDA(cudaMemsetAsync(w.p + V, 0, sizeof(unsigned long long), ctx->stream));
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, w.p, prefix.p, int64_t(V + 1), ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, w.p, prefix.p, int64_t(V + 1), ctx->stream));
   mesh->vertex_tile.alloc(V);
-  mesh->vtile_lo = 0;
-  mesh->ntiles = ntiles;
-  FQ_CUDA(cudaMemcpyAsync(mesh->vertex_tile.p, vtile.data(), V * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  vertex_tile_from_prefix_kernel<<<grid_for(V, block, ctx->sm_count), block, 0, ctx->stream>>>(V, prefix.p, mesh->vertex_tile.p);
+  fq_count_launch(ctx, 5);
+  FQ_CUDA(cudaGetLastError());
+  unsigned long long total = 0;
+  int h_err = 0;
+  FQ_CUDA(cudaMemcpyAsync(&total, prefix.p + V, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_err || (total >> 20) >= (1ull << 31)) {  // malformed table: leave the mesh unclustered (slab path)
+    mesh->vertex_tile.release();
+    mesh->ntiles = 0;
+    return;
+  }
+  mesh->vtile_lo = 0;
+  mesh->ntiles = size_t(total >> 20) + 1;
+  mesh->cluster_generic = true;
 }
 
 // ---- cell visits of every tile ------------------------------------------------
@@ -1206,6 +1228,7 @@ static int bits_for32(uint64_t n) {
   return b;
 }
 static void build_cell_visits(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& plan) {
+  ScopedSpan span(ctx, "tp_cell_visits");
   const int nv = mesh->dim + 1, block = 256;
   const size_t ncells = mesh->ncells, nkeys = ncells * size_t(nv);
   DevBuf<uint64_t> keys(nkeys ? nkeys : 1), keys_alt(nkeys ? nkeys : 1);
@@ -1327,7 +1350,10 @@ static bool build_streams_device(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& pla
     attr_set = true;
   }
   const int grid = int(std::min<uint64_t>(plan.ntiles, uint64_t(ctx->sm_count)));
-  tile_build_kernel<false><<<grid, kBT, sizeof(BuildSmem), ctx->stream>>>(P);
+  {
+    ScopedSpan span(ctx, "tp_count");
+    tile_build_kernel<false><<<grid, kBT, sizeof(BuildSmem), ctx->stream>>>(P);
+  }
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
   int h_err = 0;
@@ -1362,7 +1388,10 @@ static bool build_streams_device(fq_ctx* ctx, const fq_mesh* mesh, TilePlan& pla
   P.tiles = plan.tiles.p;
   P.cv_rec = plan.cv_rec.p;
   P.stream = plan.stream.p;
-  tile_build_kernel<true><<<grid, kBT, sizeof(BuildSmem), ctx->stream>>>(P);
+  {
+    ScopedSpan span(ctx, "tp_emit");
+    tile_build_kernel<true><<<grid, kBT, sizeof(BuildSmem), ctx->stream>>>(P);
+  }
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
   FQ_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

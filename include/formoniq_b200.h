@@ -181,6 +181,12 @@ int fq_ctx_wait_downloads(fq_ctx* ctx);
 int fq_csr_destroy(fq_csr* csr);
 /* algorithmic HBM bytes of the last numeric assembly / of one SpMV */
 int64_t fq_csr_assembly_bytes(const fq_csr* csr);
+/* the part of fq_csr_assembly_bytes that blocks assembled together in one fused launch (fq_hodge_numeric) read ONCE:
+   edge lengths + cell -> edge ids (8 E + 4 C(n+1,2) C); the rest (4 B per element entry of the map, 8 B per non-zero) is
+   per block */
+int64_t fq_csr_assembly_shared_bytes(const fq_csr* csr);
+/* device milliseconds the last tile-plan build of this matrix took (symbolic pattern + record streams; 0: none) */
+double fq_csr_plan_build_ms(const fq_csr* csr);
 int64_t fq_csr_spmv_bytes(const fq_csr* csr);
 
 /* ---- vectors: iterative::InnerProductSpace (iterative/src/lib.rs:84-141) ---- */

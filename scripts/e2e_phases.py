@@ -31,7 +31,9 @@ def T():
     torch.cuda.synchronize()
     return time.perf_counter()
 
+ctx.set_timing(True)
 for it in range(2):
+    ctx.timing_report()
     t0 = T()
     m = fq.Mesh.from_arrays(ctx, DIM, ns, faces, len_t.numpy())
     t1 = T()
@@ -49,4 +51,5 @@ for it in range(2):
         print(f"   block: symbolic {1e3 * (a1 - a0):8.1f}  numeric {1e3 * (a2 - a1):8.1f}  download {1e3 * (a3 - a2):8.1f} ms  nnz {a.nnz}")
         del a, rp, ci, va
     print(f"   total: symbolic {1e3 * tot_sym:.1f}  numeric {1e3 * tot_num:.1f}  download {1e3 * tot_dl:.1f}  all {1e3 * (T() - t0):.1f} ms")
+    print('   spans:', {k: round(v['ms'], 1) for k, v in ctx.timing_report().items()})
     del m

@@ -4,6 +4,8 @@ tables); values within 1e-12 relative (north-star tolerance) — and, for dim <=
 where the operation order is pinned, bitwise up to the sign of zero."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -457,23 +459,24 @@ def test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, 
         assert same_bits_mod_zero_sign(va, va0), (kind, g)
 
 
-@pytest.mark.parametrize("kernel", ["w", "s"])
+@pytest.mark.parametrize("warps", ["1", "2"])
 @pytest.mark.parametrize("dim,shape,variant,k,source", [TILE_CASES[i] for i in (0, 1, 2, 3, 5, 6, 9, 10)])
-def test_tile_fused_warp_specialised_kernels(fq, ctx, monkeypatch, kernel, dim, shape, variant, k, source):
-    # default: one slab in two halves, the producers refill one half while the consumers gather from the other (staged
-    # element tape); FQ_TILE_KERNEL=w: producer/consumer warps over two slabs; =s: phase-serialised.  Same bits as the oracle.
-    monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
+def test_tile_fused_warp_configurations(fq, ctx, monkeypatch, warps, dim, shape, variant, k, source):
+    # default: 16 producer + 16 consumer warps; FQ_TILE_WARPS=1: 16 + 12, =2: 8 + 16 (two cell visits per producer thread).
+    # Same bits as the oracle.
+    monkeypatch.setenv("FQ_TILE_WARPS", warps)
     test_tile_fused_hodge_blocks_are_bitwise_the_slab_path(fq, ctx, dim, shape, variant, k, source, True)
 
 
-@pytest.mark.parametrize("kernel", ["", "w", "s", "nopack"])
+@pytest.mark.parametrize("kernel", ["", "1", "2", "host"])
 def test_tile_fused_many_tiles_per_cta(fq, ctx, monkeypatch, kernel):
-    # enough tiles that every CTA runs several of them (pipelines in steady state, slabs recycled): tile pass == slab pass
-    # == oracle, bitwise, on a jittered mesh
-    if kernel == "nopack":
-        monkeypatch.setenv("FQ_TILE_PACK", "0")   # dense lane order instead of the bank-aware packing
+    # enough tiles that every CTA runs several of them (producers refilling a stage group's slab region while the
+    # consumers still read the others): every pass == oracle, bitwise, on a jittered mesh.  "host": the plan comes from
+    # the host reference builder (the one the CPU tests interpret), the others from the device builder.
+    if kernel == "host":
+        monkeypatch.setenv("FQ_TILE_BUILD", "host")
     elif kernel:
-        monkeypatch.setenv("FQ_TILE_KERNEL", kernel)
+        monkeypatch.setenv("FQ_TILE_WARPS", kernel)
     dim, shape = 3, [22, 19, 25]
     cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
     mesh = fq.Mesh.kuhn(ctx, dim, shape, jitter=0.2)
@@ -649,17 +652,24 @@ def test_full_size_invariants_at_the_baseline_workload(fq, ctx):
     N = 128
     mesh = fq.Mesh.kuhn(ctx, 3, N)
     assert mesh.ncells == 6 * N ** 3
+    os.environ["FQ_NO_TILE"] = "1"                    # two-kernel slab path (K2 global sort, element slabs in HBM)
+    try:
+        hb = fq.HodgeBlocks.symbolic(mesh, 1)
+        hb.numeric(mesh)
+        probes = []
+        for blk in hb.blocks:
+            ones = fq.DeviceVector.from_numpy(ctx, np.ones(blk.shape[1]))
+            x = fq.DeviceVector.from_numpy(ctx, np.cos(np.arange(blk.shape[1], dtype=np.float64) ** 2 + 1.0))
+            probes.append((blk.nnz, blk.apply(ones).to_numpy(), blk.apply(x).to_numpy()))
+        del hb
+        fq._lib.lib().fq_device_cache_trim()
+    finally:
+        del os.environ["FQ_NO_TILE"]
     hb = fq.HodgeBlocks.symbolic(mesh, 1)
-    hb.numeric(mesh)                                  # slab pass
-    probes = []
-    for blk in hb.blocks:
-        ones = fq.DeviceVector.from_numpy(ctx, np.ones(blk.shape[1]))
-        x = fq.DeviceVector.from_numpy(ctx, np.cos(np.arange(blk.shape[1], dtype=np.float64) ** 2 + 1.0))
-        probes.append((blk.nnz, blk.apply(ones).to_numpy(), blk.apply(x).to_numpy()))
     ctx.set_timing(True)
     ctx.timing_report()
-    hb.numeric(mesh)                                  # builds the tile plan, runs the fused kernel
-    hb.numeric(mesh)
+    hb.numeric(mesh)                                  # builds the tile plan, fused kernel (structural), compaction
+    hb.numeric(mesh)                                  # fused kernel on the value-dependent pattern
     assert ctx.timing_report().get("k13_tile_fused", {}).get("count", 0) == 2
     ctx.set_timing(False)
     for blk, (nnz, rowsum, px) in zip(hb.blocks, probes):
@@ -678,6 +688,47 @@ def test_full_size_invariants_at_the_baseline_workload(fq, ctx):
         assert abs(a - b) <= 1e-12 * max(abs(a), abs(b), 1e-300)
     del hb, mesh
     fq._lib.lib().fq_device_cache_trim()
+
+
+@pytest.mark.parametrize("N,variant", [(32, "plain"), (32, "jitter"), (48, "plain"), (48, "jitter")])
+def test_fused_kernel_against_the_oracle_at_scale(fq, ctx, N, variant):
+    # the headline path compared with the oracle well beyond toy sizes — 3-D k = 1 Hodge blocks on N^3 Kuhn
+    # cubes (N = 48: 663 552 tets, ~32 M non-zeros): pattern bit for bit, values bitwise (same operation order, same
+    # cell-ascending summation), first (structural + compaction) and steady-state (value-dependent pattern) passes
+    cx, s, *_ = kuhn_problem(3, [N, N, N], jitter=variant == "jitter")
+    mesh = fq.Mesh.kuhn(ctx, 3, [N, N, N], jitter=0.2 if variant == "jitter" else 0.0)
+    assert np.array_equal(mesh.lengths(), s)
+    hb = fq.HodgeBlocks.symbolic(mesh, 1)
+    ctx.set_timing(True)
+    ctx.timing_report()
+    hb.numeric(mesh)
+    hb.numeric(mesh)
+    assert ctx.timing_report().get("k13_tile_fused", {}).get("count", 0) == 2
+    ctx.set_timing(False)
+    for blk, (kind, g) in zip(hb.blocks, [(O.MASS, 0), (O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_BOTH, 2)]):
+        ref = cx.assemble(s, kind, g, nthreads=O.max_threads())
+        rp, ci, va = blk.download()
+        erp, eci, eva = ref.arrays()
+        assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci), (kind, g)
+        assert same_bits_mod_zero_sign(va, eva), (kind, g)
+
+
+def test_four_dimensional_k2_blocks_against_the_oracle(fq, ctx):
+    # BASELINE config 3 (arbitrary-dimension path): 4-D k = 2 Hodge blocks on a 4^4 Kuhn grid (6 144 pentatopes, 10 x 10
+    # element matrices): jittered geometry, so the reference pattern is the structural one and must match bit for bit;
+    # values to 1e-12 (the 4 x 4 inverse of the third-party dependency is restated)
+    shape = [4, 4, 4, 4]
+    cx, s, *_ = kuhn_problem(4, shape, jitter=True)
+    mesh = fq.Mesh.kuhn(ctx, 4, shape, jitter=0.2)
+    assert np.array_equal(mesh.lengths(), s)
+    hb = fq.HodgeBlocks.symbolic(mesh, 2)
+    hb.numeric(mesh)
+    for blk, (kind, g) in zip(hb.blocks, [(O.MASS, 1), (O.MASS, 2), (O.DIF_TEST, 2), (O.DIF_BOTH, 3)]):
+        ref = cx.assemble(s, kind, g, nthreads=O.max_threads())
+        rp, ci, va = blk.download()
+        erp, eci, eva = ref.arrays()
+        assert np.array_equal(rp.astype(np.int64), erp) and np.array_equal(ci.astype(np.int64), eci), (kind, g)
+        assert np.abs(va - eva).max() <= 1e-12 * np.abs(eva).max(), (kind, g)
 
 
 def test_async_download_matches_the_blocking_one(fq, ctx):
