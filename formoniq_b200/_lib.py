@@ -60,6 +60,9 @@ SIGNATURES = [
     ("fq_hodge_block", _vp, [_vp, _i]),
     ("fq_hodge_destroy", _i, [_vp]),
     ("fq_hodge_mixed_laplacian", _i, [_vp, _vp, _P(_vp)]),
+    ("fq_hodge_mixed_kkt_symmetric", _i, [_vp, _vp, _P(_vp)]),
+    ("fq_csr_row_abs_sums", _i, [_vp, _vp, _vp]),
+    ("fq_csr_add", _i, [_vp, _vp, _vp, _P(_vp)]),
     ("fq_csr_transpose", _i, [_vp, _vp, _P(_vp)]),
     ("fq_csr_restrict", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _P(_vp)]),
     ("fq_csr_shape", _i, [_vp, _P(_sz), _P(_sz), _P(_sz)]),
@@ -104,6 +107,10 @@ SIGNATURES = [
     ("fq_flag_signal", _i, [_vp, _vp, _d]),
     ("fq_flag_wait", _i, [_vp, _vp, _d]),
     ("fq_flag_check", _i, [_vp]),
+    ("fq_cg_op", _i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
+    ("fq_minres_op", _i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
+    ("fq_minres_blockdiag", _i, [_vp, _vp, _i, _P(_vp), _P(_sz), _d, _sz, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i), _P(_sz)]),
+    ("fq_vec_view", _i, [_vp, _vp, _sz, _sz, _P(_vp)]),
     ("fq_cg", _i, [_vp, _vp, _i, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
     ("fq_minres", _i, [_vp, _vp, _i, _vp, _d, _sz, _vp, _P(_sz), _P(_d), _P(_i)]),
 ]

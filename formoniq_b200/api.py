@@ -254,6 +254,20 @@ class DeviceVector:
         check(_lib.lib().fq_vec_copy(self.ctx._h, v._h, self._h))
         return v
 
+    def view(self, offset: int, n: int) -> "DeviceVector":
+        """Non-owning view of self[offset : offset + n] (the sigma / u segments of a mixed vector)."""
+        v = DeviceVector.__new__(DeviceVector)
+        h = C.c_void_p()
+        check(_lib.lib().fq_vec_view(self.ctx._h, self._h, int(offset), int(n), C.byref(h)))
+        v.ctx, v._h, v.n, v._keepalive = self.ctx, h, int(n), self
+        return v
+
+    def copy_from(self, src: "DeviceVector"):
+        check(_lib.lib().fq_vec_copy(self.ctx._h, self._h, src._h))
+
+    def fill_zero(self):
+        self.scale(0.0)
+
     def dot(self, other: "DeviceVector") -> float:
         out = C.c_double()
         check(_lib.lib().fq_vec_dot(self.ctx._h, self._h, other._h, C.byref(out)))
@@ -361,6 +375,19 @@ class DeviceCsr:
     def transpose(self) -> "DeviceCsr":
         h = C.c_void_p()
         check(_lib.lib().fq_csr_transpose(self.ctx._h, self._h, C.byref(h)))
+        return DeviceCsr(self.ctx, h)
+
+    def row_abs_sums(self) -> DeviceVector:
+        """y_i = sum_j |a_ij| of the held rows (the inf-norm is its maximum)."""
+        b, e = self.row_range
+        y = DeviceVector(self.ctx, e - b)
+        check(_lib.lib().fq_csr_row_abs_sums(self.ctx._h, self._h, y._h))
+        return y
+
+    def __add__(self, other: "DeviceCsr") -> "DeviceCsr":
+        """A + B on the union pattern (nalgebra-sparse `&a + &b`), on the device."""
+        h = C.c_void_p()
+        check(_lib.lib().fq_csr_add(self.ctx._h, self._h, other._h, C.byref(h)))
         return DeviceCsr(self.ctx, h)
 
     def restrict(self, rows_keep, cols_keep) -> "DeviceCsr":
@@ -666,12 +693,15 @@ class HodgeBlocks:
         hb.numeric(mesh, drop_exact_zeros)
         return hb
 
-    def mixed_hodge_laplacian(self, on_device: bool = True):
+    def mixed_hodge_laplacian(self, on_device: bool = True, symmetrized: bool = False):
         """[[M_{k-1}, -dif_test], [dif_test^T, dif_both]] (hodge.rs:93-99), stitched on the device
-        (on_device=False: on the host with scipy, then uploaded — the cross-check of the tests)."""
+        (on_device=False: on the host with scipy, then uploaded — the cross-check of the tests).
+        symmetrized: the sigma block-row negated, [[-M, dif_test], [dif_test^T, dif_both]] — the symmetric saddle point
+        assemble_mixed_kkt gives MINRES (problems/elliptic.rs:101-113)."""
         if on_device:
             h = C.c_void_p()
-            check(_lib.lib().fq_hodge_mixed_laplacian(self.mass_u.ctx._h, self._plan._h, C.byref(h)))
+            fn = _lib.lib().fq_hodge_mixed_kkt_symmetric if symmetrized else _lib.lib().fq_hodge_mixed_laplacian
+            check(fn(self.mass_u.ctx._h, self._plan._h, C.byref(h)))
             return DeviceCsr(self.mass_u.ctx, h)
         import scipy.sparse as sp
 
@@ -697,3 +727,114 @@ def cg(op: DeviceCsr, precond, b: DeviceVector, stop: StopCriterion):
 def minres(op: DeviceCsr, precond, b: DeviceVector, stop: StopCriterion):
     """iterative::krylov::minres on device vectors; precond in {None, "jacobi"}."""
     return _krylov(_lib.lib().fq_minres, op, precond, b, stop)
+
+
+# ---------------------------------------------------------------------------
+# Krylov over user operators and the AFW block preconditioner
+# ---------------------------------------------------------------------------
+_APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+_REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, C.POINTER(C.c_double))
+
+
+def _wrap_apply(ctx: Context, n: int, fn):
+    """fn(x: DeviceVector, y: DeviceVector) on views of the device pointers the library hands to the callback."""
+    if fn is None:
+        return C.cast(None, _APPLY_FN), None
+
+    def cb(_user, xp, yp):
+        try:
+            fn(DeviceVector.wrap(ctx, xp, n), DeviceVector.wrap(ctx, yp, n))
+            return 0
+        except Exception as exc:  # never unwind through the C frames
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    c = _APPLY_FN(cb)
+    return c, c
+
+
+def _krylov_op(fn, ctx: Context, n: int, apply, precond, reduce, b: DeviceVector, stop: StopCriterion):
+    a_cb, a_keep = _wrap_apply(ctx, n, apply)
+    p_cb, p_keep = _wrap_apply(ctx, n, precond)
+    if reduce is None:
+        r_cb = C.cast(None, _REDUCE_FN)
+    else:
+        def rcb(_user, local, out):
+            try:
+                out[0] = float(reduce(float(local)))
+                return 0
+            except Exception:
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        r_cb = _REDUCE_FN(rcb)
+    x = b.zeros_like()
+    it, res, conv = C.c_size_t(), C.c_double(), C.c_int()
+    check(fn(ctx._h, n, a_cb, p_cb, r_cb, None, b._h, float(stop.rtol), int(stop.max_iters), x._h, C.byref(it), C.byref(res),
+             C.byref(conv)))
+    del a_keep, p_keep
+    return x, Report(it.value, res.value, bool(conv.value))
+
+
+def cg_op(ctx: Context, n: int, apply, b: DeviceVector, stop: StopCriterion, precond=None, reduce=None):
+    """iterative::krylov::cg over a user operator: apply(x, y) / precond(r, z) act on DeviceVector views, reduce(local)
+    completes an inner product (all-reduce of a distributed space)."""
+    return _krylov_op(_lib.lib().fq_cg_op, ctx, n, apply, precond, reduce, b, stop)
+
+
+def minres_op(ctx: Context, n: int, apply, b: DeviceVector, stop: StopCriterion, precond=None, reduce=None):
+    """iterative::krylov::minres over a user operator (see cg_op)."""
+    return _krylov_op(_lib.lib().fq_minres_op, ctx, n, apply, precond, reduce, b, stop)
+
+
+def minres_blockdiag(op: DeviceCsr, blocks, offsets, b: DeviceVector, stop: StopCriterion, inner: StopCriterion):
+    """MINRES on `op` preconditioned by diag(blocks[i]^-1) on the segments [offsets[i], offsets[i+1]) (None = identity),
+    each block an inner Jacobi-CG solve: with blocks (hdif_gram(k-1), hdif_gram(k)) the AFW block preconditioner of
+    problems/elliptic.rs:29-47.  Returns (x, Report, total inner iterations)."""
+    nb = len(blocks)
+    arr = (C.c_void_p * nb)(*[None if blk is None else blk._h for blk in blocks])
+    offs = (C.c_size_t * (nb + 1))(*[int(o) for o in offsets])
+    x = b.zeros_like()
+    it, res, conv, inner_it = C.c_size_t(), C.c_double(), C.c_int(), C.c_size_t()
+    check(_lib.lib().fq_minres_blockdiag(op.ctx._h, op._h, nb, arr, offs, float(inner.rtol), int(inner.max_iters), b._h,
+                                         float(stop.rtol), int(stop.max_iters), x._h, C.byref(it), C.byref(res), C.byref(conv),
+                                         C.byref(inner_it)))
+    return x, Report(it.value, res.value, bool(conv.value)), inner_it.value
+
+
+class WhitneyComplex:
+    """HilbertComplex over a device mesh (crates/formoniq/src/whitney_complex.rs:55-183): the provided assemblies of the
+    trait — pairing / mass / dif_trial / dif_test / dif_both / hdif_gram — each one `assemble(form)` on the device.
+    Grades off [0, dim] give correctly shaped zero matrices (whitney_complex.rs:113-122)."""
+
+    def __init__(self, mesh: Mesh, drop_exact_zeros: bool = True):
+        self.mesh, self.drop = mesh, drop_exact_zeros
+
+    @property
+    def dim(self) -> int:
+        return self.mesh.dim
+
+    def assemble(self, form: "BilinearForm") -> DeviceCsr:
+        return form.assemble(self.mesh, self.drop)
+
+    pairing = assemble
+
+    def mass(self, grade: int) -> DeviceCsr:
+        return self.assemble(WhitneyPairing.mass(self.dim, grade))
+
+    def dif_trial(self, grade: int) -> DeviceCsr:
+        return self.assemble(WhitneyPairing.dif_trial(self.dim, grade))
+
+    def dif_test(self, grade: int) -> DeviceCsr:
+        return self.assemble(WhitneyPairing.dif_test(self.dim, grade))
+
+    def dif_both(self, grade: int) -> DeviceCsr:
+        return self.assemble(WhitneyPairing.dif_both(self.dim, grade))
+
+    def hdif_gram(self, grade: int) -> DeviceCsr:
+        """Gram matrix of the graph inner product <u,v> + <du,dv> (whitney_complex.rs:180-183): mass(k) + dif_both(k+1)."""
+        return self.mass(grade) + self.dif_both(grade + 1)

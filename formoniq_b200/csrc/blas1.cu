@@ -2,6 +2,8 @@
 // (iterative/src/lib.rs:84-141): dot, scale, add_scaled, plus the pointwise
 // product a diagonal preconditioner needs.  The dot product is a fixed-shape
 // two-stage reduction, so it is deterministic run to run.
+#include <algorithm>
+
 #include "internal.hpp"
 
 namespace fq {
@@ -42,7 +44,8 @@ __global__ void __launch_bounds__(kRedThreads) dot_final_kernel(const double* __
 double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n) {
   if (n == 0) return 0.0;
   if (ctx->reduce_scratch.n < size_t(kRedBlocksMax) + 1) ctx->reduce_scratch.alloc(size_t(kRedBlocksMax) + 1);
-  const int grid = grid_for(n, kRedThreads, ctx->sm_count, 8);
+  // the partials live in kRedBlocksMax slots and the result in the slot after them, whatever the SM count
+  const int grid = std::min(grid_for(n, kRedThreads, ctx->sm_count, 8), kRedBlocksMax);
   dot_partial_kernel<<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, ctx->reduce_scratch.p);
   dot_final_kernel<<<1, kRedThreads, 0, ctx->stream>>>(ctx->reduce_scratch.p, grid, ctx->reduce_scratch.p + kRedBlocksMax);
   fq_count_launch(ctx, 2);

@@ -97,7 +97,7 @@ __global__ void block2x2_fill_kernel(const uint32_t* __restrict__ pa, const uint
 }
 
 void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01, const fq_csr* a10, const fq_csr* a11,
-                  fq_csr* out) {
+                  fq_csr* out, double s00) {
   const size_t n0 = a00->nrows, n1 = a11->nrows;
   FQ_REQUIRE(a00->ncols == n0 && a11->ncols == n1 && a01->nrows == n0 && a01->ncols == n1 && a10->nrows == n1 && a10->ncols == n0,
              "block shapes do not fit");
@@ -116,7 +116,7 @@ void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01,
       a00->row_ptr.p, a01->row_ptr.p, a10->row_ptr.p, a11->row_ptr.p, uint32_t(n0), uint32_t(n1), out->row_ptr.p);
   if (n0)
     block2x2_fill_kernel<<<grid_for(n0, block, ctx->sm_count), block, 0, ctx->stream>>>(
-        a00->row_ptr.p, a00->col_idx.p, a00->values.p, 1.0, 0u, a01->row_ptr.p, a01->col_idx.p, a01->values.p, s01, uint32_t(n0),
+        a00->row_ptr.p, a00->col_idx.p, a00->values.p, s00, 0u, a01->row_ptr.p, a01->col_idx.p, a01->values.p, s01, uint32_t(n0),
         uint32_t(n0), 0u, out->row_ptr.p, out->col_idx.p, out->values.p);
   if (n1)
     block2x2_fill_kernel<<<grid_for(n1, block, ctx->sm_count), block, 0, ctx->stream>>>(
@@ -194,6 +194,102 @@ void csr_restrict(fq_ctx* ctx, const fq_csr* a, const uint32_t* rows_keep, size_
   fq_count_launch(ctx, 5);
   FQ_CUDA(cudaGetLastError());
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- C = A + B on the union pattern (nalgebra-sparse `&a + &b`: HilbertComplex::hdif_gram, whitney_complex.rs:180-183)
+// Rows are merged by column (both inputs are sorted); an entry present in both operands is a_ij + b_ij, one present in
+// a single operand is copied, explicit zeros stay in the pattern — entry for entry what the reference's spadd produces.
+__global__ void add_count_kernel(const uint32_t* __restrict__ arp, const uint32_t* __restrict__ aci,
+                                 const uint32_t* __restrict__ brp, const uint32_t* __restrict__ bci, uint32_t nrows,
+                                 uint32_t* __restrict__ len) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nrows; r += stride) {
+    if (r == nrows) {
+      len[r] = 0;
+      continue;
+    }
+    uint32_t p = arp[r], q = brp[r], n = 0;
+    const uint32_t pe = arp[r + 1], qe = brp[r + 1];
+    while (p < pe && q < qe) {
+      const uint32_t ca = aci[p], cb = bci[q];
+      p += ca <= cb;
+      q += cb <= ca;
+      ++n;
+    }
+    len[r] = n + (pe - p) + (qe - q);
+  }
+}
+__global__ void add_fill_kernel(const uint32_t* __restrict__ arp, const uint32_t* __restrict__ aci, const double* __restrict__ av,
+                                const uint32_t* __restrict__ brp, const uint32_t* __restrict__ bci, const double* __restrict__ bv,
+                                uint32_t nrows, const uint32_t* __restrict__ crp, uint32_t* __restrict__ cci,
+                                double* __restrict__ cv) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    uint32_t p = arp[r], q = brp[r], o = crp[r];
+    const uint32_t pe = arp[r + 1], qe = brp[r + 1];
+    while (p < pe || q < qe) {
+      const uint32_t ca = p < pe ? aci[p] : 0xFFFFFFFFu, cb = q < qe ? bci[q] : 0xFFFFFFFFu;
+      if (ca == cb) {
+        cci[o] = ca;
+        cv[o] = __dadd_rn(av[p], bv[q]);
+        ++p, ++q;
+      } else if (ca < cb) {
+        cci[o] = ca;
+        cv[o] = av[p];
+        ++p;
+      } else {
+        cci[o] = cb;
+        cv[o] = bv[q];
+        ++q;
+      }
+      ++o;
+    }
+  }
+}
+void csr_add(fq_ctx* ctx, const fq_csr* a, const fq_csr* b, fq_csr* out) {
+  FQ_REQUIRE(a->nrows == b->nrows && a->ncols == b->ncols && a->row_begin == b->row_begin && a->row_end == b->row_end,
+             "csr_add: the operands must have the same shape and row range");
+  const uint32_t nrows = uint32_t(a->row_end - a->row_begin);
+  out->nrows = a->nrows;
+  out->ncols = a->ncols;
+  out->row_begin = a->row_begin;
+  out->row_end = a->row_end;
+  out->row_ptr.alloc(size_t(nrows) + 1);
+  const int block = 256;
+  add_count_kernel<<<grid_for(size_t(nrows) + 1, block, ctx->sm_count), block, 0, ctx->stream>>>(
+      a->row_ptr.p, a->col_idx.p, b->row_ptr.p, b->col_idx.p, nrows, out->row_ptr.p);
+  size_t tmp_bytes = 0;
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, out->row_ptr.p, out->row_ptr.p, int64_t(nrows) + 1, ctx->stream));
+  DevBuf<uint8_t> tmp(tmp_bytes ? tmp_bytes : 1);
+  FQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, out->row_ptr.p, out->row_ptr.p, int64_t(nrows) + 1, ctx->stream));
+  uint32_t nnz = 0;
+  FQ_CUDA(cudaMemcpyAsync(&nnz, out->row_ptr.p + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->nnz = nnz;
+  out->col_idx.alloc(nnz ? nnz : 1);
+  out->values.alloc(nnz ? nnz : 1);
+  if (nnz)
+    add_fill_kernel<<<grid_for(nrows, block, ctx->sm_count), block, 0, ctx->stream>>>(
+        a->row_ptr.p, a->col_idx.p, a->values.p, b->row_ptr.p, b->col_idx.p, b->values.p, nrows, out->row_ptr.p, out->col_idx.p,
+        out->values.p);
+  fq_count_launch(ctx, 4);
+  FQ_CUDA(cudaGetLastError());
+}
+
+__global__ void row_abs_sum_kernel(const uint32_t* __restrict__ rp, const double* __restrict__ v, uint32_t nrows, double* __restrict__ y) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    double acc = 0.0;
+    for (uint32_t p = rp[r]; p < rp[r + 1]; ++p) acc += fabs(v[p]);
+    y[r] = acc;
+  }
+}
+void csr_row_abs_sums(fq_ctx* ctx, const fq_csr* a, double* y) {
+  const uint32_t nrows = uint32_t(a->row_end - a->row_begin);
+  if (!nrows) return;
+  row_abs_sum_kernel<<<grid_for(nrows, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a->row_ptr.p, a->values.p, nrows, y);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
 }
 
 }  // namespace fq

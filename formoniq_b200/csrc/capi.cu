@@ -94,18 +94,21 @@ __global__ void widen_u32_kernel(const uint32_t* __restrict__ in, size_t n, uint
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
 }
-__global__ void narrow_u64_kernel(const uint64_t* __restrict__ in, size_t n, uint32_t* __restrict__ out,
+// `limit`: every value must be below it (face ids against the simplex count of their grade): a malformed table
+// would otherwise become out-of-bounds device reads in every later kernel
+__global__ void narrow_u64_kernel(const uint64_t* __restrict__ in, size_t n, uint32_t* __restrict__ out, uint64_t limit,
                                   int* __restrict__ overflow) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint64_t v = in[i];
-    if (v >> 32) *overflow = 1;
+    if ((v >> 32) || v >= limit) *overflow = 1;
     out[i] = uint32_t(v);
   }
 }
 
 // host u64 array -> device u32 array (chunked through a staging buffer)
-static void upload_narrow(fq_ctx* ctx, const uint64_t* host, size_t n, DevBuf<uint32_t>& dst) {
+static void upload_narrow(fq_ctx* ctx, const uint64_t* host, size_t n, DevBuf<uint32_t>& dst,
+                          uint64_t limit = uint64_t(1) << 32) {
   dst.alloc(n ? n : 1);
   if (!n) return;
   const size_t chunk = size_t(1) << 24;
@@ -115,13 +118,13 @@ static void upload_narrow(fq_ctx* ctx, const uint64_t* host, size_t n, DevBuf<ui
   for (size_t off = 0; off < n; off += chunk) {
     const size_t m = std::min(chunk, n - off);
     FQ_CUDA(cudaMemcpyAsync(stage.p, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    narrow_u64_kernel<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(stage.p, m, dst.p + off, ovf.p);
+    narrow_u64_kernel<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(stage.p, m, dst.p + off, limit, ovf.p);
     fq_count_launch(ctx);
   }
   int h = 0;
   FQ_CUDA(cudaMemcpyAsync(&h, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  FQ_REQUIRE(h == 0, "index does not fit 32 bits");
+  FQ_REQUIRE(h == 0, "index out of range (face id >= the simplex count of its grade, or beyond 32 bits)");
 }
 // device u32 array -> host u64 array: widened on the device in pieces of up to 2 GB, each copied back with one
 // cudaMemcpyAsync (PCIe-bound when the destination is pinned or registered host memory)
@@ -273,7 +276,7 @@ int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices
   m->own_hi = m->id_hi;
   for (int j = 0; j <= dim; ++j) {
     FQ_REQUIRE(nsimplices[j] < (size_t(1) << 32), "more than 2^32 simplices of one grade: not supported");
-    if (cell_faces[j]) upload_narrow(ctx, cell_faces[j], ncells * size_t(nlocal(dim, j)), m->cell_faces[size_t(j)]);
+    if (cell_faces[j]) upload_narrow(ctx, cell_faces[j], ncells * size_t(nlocal(dim, j)), m->cell_faces[size_t(j)], nsimplices[j]);
   }
   m->lengths.alloc(nsimplices[1] ? nsimplices[1] : 1);
   m->edge_lo = 0;
@@ -528,6 +531,23 @@ int fq_csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr** out) {
   *out = t.release();
   FQ_API_END
 }
+int fq_csr_row_abs_sums(fq_ctx* ctx, const fq_csr* a, fq_vec* y) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && y, "null argument");
+  FQ_REQUIRE(y->d.n == a->row_end - a->row_begin, "row_abs_sums: dimension mismatch");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  csr_row_abs_sums(ctx, a, y->d.p);
+  FQ_API_END
+}
+int fq_csr_add(fq_ctx* ctx, const fq_csr* a, const fq_csr* b, fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && b && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<fq_csr> c(new fq_csr);
+  csr_add(ctx, a, b, c.get());
+  *out = c.release();
+  FQ_API_END
+}
 int fq_csr_restrict(fq_ctx* ctx, const fq_csr* a, const size_t* rows_keep, size_t nrows_keep, const size_t* cols_keep,
                     size_t ncols_keep, fq_csr** out) {
   FQ_API_BEGIN
@@ -556,6 +576,17 @@ int fq_hodge_mixed_laplacian(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out) 
   csr_transpose(ctx, dif_test, &dt_t);
   std::unique_ptr<fq_csr> a(new fq_csr);
   csr_block2x2(ctx, m_sigma, dif_test, -1.0, &dt_t, dif_both, a.get());
+  *out = a.release();
+  FQ_API_END
+}
+int fq_hodge_mixed_kkt_symmetric(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && blocks && out, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  fq_csr dt_t;
+  csr_transpose(ctx, blocks->blocks[2].get(), &dt_t);
+  std::unique_ptr<fq_csr> a(new fq_csr);
+  csr_block2x2(ctx, blocks->blocks[0].get(), blocks->blocks[2].get(), 1.0, &dt_t, blocks->blocks[3].get(), a.get(), -1.0);
   *out = a.release();
   FQ_API_END
 }
@@ -977,3 +1008,72 @@ int fq_minres(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double
 }
 
 }  // extern "C"
+
+// ---- Krylov over user operators (iterative::{cg, minres} are generic over LinearOperator / ApproxInverse /
+// InnerProductSpace, iterative/src/krylov.rs:48,113): the operator, the preconditioner and the completion of an inner
+// product (the all-reduce of a distributed space) are callbacks on device pointers
+static int krylov_op_common(bool is_cg, fq_ctx* ctx, size_t n, fq_apply_fn apply, fq_apply_fn precond, fq_reduce_fn reduce,
+                            void* user, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x, size_t* iters,
+                            double* residual, int* converged) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && apply && b && x, "null argument");
+  FQ_REQUIRE(b->d.n == n && x->d.n == n, "dimension mismatch");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  KrylovOps ops;
+  ops.apply = [=](const double* xin, double* y) {
+    if (apply(user, xin, y) != 0) throw Error(FQ_ERR_INVALID, "operator callback failed");
+  };
+  ops.precond = [=](const double* r, double* z) {
+    if (!precond) {
+      if (n) FQ_CUDA(cudaMemcpyAsync(z, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (precond(user, r, z) != 0) {
+      throw Error(FQ_ERR_INVALID, "preconditioner callback failed");
+    }
+  };
+  ops.dot = [=](const double* u, const double* v) {
+    double local = vec_dot(ctx, u, v, n), global = local;
+    if (reduce && reduce(user, local, &global) != 0) throw Error(FQ_ERR_INVALID, "reduction callback failed");
+    return global;
+  };
+  const KrylovReport rep = is_cg ? cg_core(ctx, n, ops, b->d.p, rtol, max_iters, x->d.p)
+                                 : minres_core(ctx, n, ops, b->d.p, rtol, max_iters, x->d.p);
+  if (iters) *iters = rep.iters;
+  if (residual) *residual = rep.residual;
+  if (converged) *converged = rep.converged ? 1 : 0;
+  FQ_API_END
+}
+int fq_cg_op(fq_ctx* ctx, size_t n, fq_apply_fn apply, fq_apply_fn precond, fq_reduce_fn reduce, void* user, const fq_vec* b,
+             double rtol, size_t max_iters, fq_vec* x, size_t* iters, double* residual, int* converged) {
+  return krylov_op_common(true, ctx, n, apply, precond, reduce, user, b, rtol, max_iters, x, iters, residual, converged);
+}
+int fq_minres_op(fq_ctx* ctx, size_t n, fq_apply_fn apply, fq_apply_fn precond, fq_reduce_fn reduce, void* user,
+                 const fq_vec* b, double rtol, size_t max_iters, fq_vec* x, size_t* iters, double* residual, int* converged) {
+  return krylov_op_common(false, ctx, n, apply, precond, reduce, user, b, rtol, max_iters, x, iters, residual, converged);
+}
+int fq_minres_blockdiag(fq_ctx* ctx, const fq_csr* a, int nblocks, const fq_csr* const* blocks, const size_t* offsets,
+                        double inner_rtol, size_t inner_max_iters, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
+                        size_t* iters, double* residual, int* converged, size_t* inner_iters) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && blocks && offsets && b && x, "null argument");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  std::vector<fq_csr*> blk(static_cast<size_t>(nblocks > 0 ? nblocks : 0));
+  for (int i = 0; i < nblocks; ++i) blk[size_t(i)] = const_cast<fq_csr*>(blocks[i]);
+  const KrylovReport rep = krylov_minres_blockdiag(ctx, const_cast<fq_csr*>(a), nblocks, blk.data(), offsets, inner_rtol,
+                                                   inner_max_iters, b, rtol, max_iters, x, inner_iters);
+  if (iters) *iters = rep.iters;
+  if (residual) *residual = rep.residual;
+  if (converged) *converged = rep.converged ? 1 : 0;
+  FQ_API_END
+}
+// non-owning view of a segment of a vector
+int fq_vec_view(fq_ctx* ctx, const fq_vec* v, size_t offset, size_t n, fq_vec** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && v && out, "null argument");
+  FQ_REQUIRE(offset + n <= v->d.n, "view out of range");
+  std::unique_ptr<fq_vec> w(new fq_vec);
+  w->d.p = v->d.p + offset;
+  w->d.n = n;
+  w->d.owned = false;
+  *out = w.release();
+  FQ_API_END
+}

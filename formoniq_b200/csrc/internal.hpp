@@ -64,8 +64,10 @@ void csr_build_inv_diag(fq_ctx* ctx, fq_csr* a);
 
 // ---- blockop.cu
 void csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr* out);
+void csr_add(fq_ctx* ctx, const fq_csr* a, const fq_csr* b, fq_csr* out);
+void csr_row_abs_sums(fq_ctx* ctx, const fq_csr* a, double* y);
 void csr_block2x2(fq_ctx* ctx, const fq_csr* a00, const fq_csr* a01, double s01, const fq_csr* a10, const fq_csr* a11,
-                  fq_csr* out);
+                  fq_csr* out, double s00 = 1.0);
 
 void csr_restrict(fq_ctx* ctx, const fq_csr* a, const uint32_t* rows_keep, size_t nr, const uint32_t* cols_keep, size_t nc,
                   fq_csr* out);
@@ -101,9 +103,21 @@ struct KrylovReport {
   double residual = 0.0;
   bool converged = false;
 };
+// what cg / minres need from their operands (iterative/src/lib.rs:84-157: LinearOperator, ApproxInverse and the inner
+// product of the space): y = A x, z = M^-1 r, <u, v> — the last one global when the vectors are distributed
+struct KrylovOps {
+  std::function<void(const double* x, double* y)> apply;
+  std::function<void(const double* r, double* z)> precond;
+  std::function<double(const double* u, const double* v)> dot;
+};
+KrylovReport cg_core(fq_ctx* ctx, size_t n, const KrylovOps& ops, const double* b, double rtol, size_t max_iters, double* x);
+KrylovReport minres_core(fq_ctx* ctx, size_t n, const KrylovOps& ops, const double* b, double rtol, size_t max_iters, double* x);
 KrylovReport krylov_cg(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x);
 KrylovReport krylov_minres(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters,
                            fq_vec* x);
+KrylovReport krylov_minres_blockdiag(fq_ctx* ctx, fq_csr* a, int nblocks, fq_csr* const* blocks, const size_t* offsets,
+                                     double inner_rtol, size_t inner_max_iters, const fq_vec* b, double rtol, size_t max_iters,
+                                     fq_vec* x, size_t* inner_iters_total);
 
 inline int grid_for(size_t n, int block, int sm_count, int ctas_per_sm = 8) {
   const size_t want = (n + size_t(block) - 1) / size_t(block);

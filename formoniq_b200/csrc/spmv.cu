@@ -259,13 +259,14 @@ void spmv_apply(fq_ctx* ctx, const fq_csr* a, const double* x, double* y) {
 // Inverse diagonal for the Jacobi preconditioner (iterative/src/precond.rs:113-121).
 __global__ void inv_diag_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
                                 const double* __restrict__ values, uint32_t nrows, uint32_t row_begin,
-                                double* __restrict__ inv_diag) {
+                                double* __restrict__ inv_diag, int* __restrict__ bad) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
-    double d = 1.0;
+    double d = 0.0;
     for (uint32_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p)
-      if (col_idx[p] == r + row_begin) d = __ddiv_rn(1.0, values[p]);
-    inv_diag[r] = d;
+      if (col_idx[p] == r + row_begin) d = values[p];
+    if (d == 0.0) *bad = 1;  // no stored diagonal entry, or an explicit zero
+    inv_diag[r] = __ddiv_rn(1.0, d);
   }
 }
 
@@ -274,10 +275,20 @@ void csr_build_inv_diag(fq_ctx* ctx, fq_csr* a) {
   if (a->inv_diag.n == nrows && nrows) return;
   a->inv_diag.alloc(nrows ? nrows : 1);
   if (!nrows) return;
+  DevBuf<int> d_bad(1);
+  FQ_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), ctx->stream));
   inv_diag_kernel<<<grid_for(nrows, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-      a->row_ptr.p, a->col_idx.p, a->values.p, uint32_t(nrows), uint32_t(a->row_begin), a->inv_diag.p);
+      a->row_ptr.p, a->col_idx.p, a->values.p, uint32_t(nrows), uint32_t(a->row_begin), a->inv_diag.p, d_bad.p);
   fq_count_launch(ctx);
   FQ_CUDA(cudaGetLastError());
+  int bad = 0;
+  FQ_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (bad) {
+    a->inv_diag.release();
+    // the reference asserts a non-zero diagonal (iterative/src/precond.rs:101-104); dropped exact zeros count as missing
+    throw Error(FQ_ERR_DEGENERATE, "Jacobi preconditioner: the matrix has a missing or zero diagonal entry");
+  }
 }
 
 }  // namespace fq

@@ -188,3 +188,158 @@ class PeerHalo:
         from . import _lib
 
         _lib.check(_lib.lib().fq_flag_check(self.ctx._h))
+
+
+def all_reduce_scalar(value: float, op: str = "sum", group=None, world: int | None = None) -> float:
+    """One scalar across the ranks (the only collective of the Krylov solvers besides the halo exchange).  `world` = 1
+    marks a single-rank object inside a multi-rank job (no collective)."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1 or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+class DistKktPencil:
+    """The pencil of `elliptic::solve_evp` (problems/elliptic.rs:225-247) row-partitioned over the ranks:
+
+        A = [[M_{k-1}, -dif_test(k)], [dif_test(k)^T, dif_both(k+1)]]   (hodge.rs:93-99),   B = diag(0, M_k).
+
+    Every rank owns the sigma rows and the u rows of its z-slab (owner computes: its blocks are assembled from its own
+    cells plus one halo layer, no assembly traffic).  The lower-left block is assembled as dif_trial(k) — the same
+    operator as dif_test(k)^T with rows = the rank's u rows, so no transpose crosses ranks.  A vector is the pair
+    (sigma_owned | u_owned); an operator application copies the two owned segments into column windows
+    [held_lo, held_hi), refreshes their halos with one send/recv pair per neighbour and runs the four windowed SpMVs;
+    inner products are completed by an all-reduce of one scalar.  Implements the pencil protocol of
+    eigen.shift_invert_lanczos; the inner solves of the shift-invert step are MINRES on A - shift*B (SpMV-only)."""
+
+    def __init__(self, ctx, dim: int, shape, grade: int, rank: int = 0, world: int = 1, group=None, jitter: float = 0.0,
+                 inner_rtol: float = 1e-13, inner_max_iters: int = 200000):
+        import torch
+
+        from .api import DeviceVector, HodgeBlocks, Mesh, WhitneyPairing
+
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.inner_rtol, self.inner_max_iters, self.inner_iterations, self.applies = inner_rtol, inner_max_iters, 0, 0
+        shape = list(shape)
+        slab = slab_of(rank, world, shape[dim - 1])
+        self.mesh = Mesh.kuhn(ctx, dim, shape, slab=slab, jitter=jitter)
+        self.part_s = SlabPartition(dim, shape, world, grade - 1)
+        self.part_u = SlabPartition(dim, shape, world, grade)
+        self.rs, self.ru = self.part_s.ranges[rank], self.part_u.ranges[rank]
+        srows, urows = (self.rs.own_lo, self.rs.own_hi), (self.ru.own_lo, self.ru.own_hi)
+        self.hb = HodgeBlocks.symbolic(self.mesh, grade, srows, urows)
+        self.hb.numeric(self.mesh, True)
+        self.dif_trial = WhitneyPairing.dif_trial(dim, grade).symbolic(self.mesh, *urows)
+        self.dif_trial.numeric(self.mesh, True)
+        self.ns, self.nu = srows[1] - srows[0], urows[1] - urows[0]
+        self.n = self.ns + self.nu
+        self.ns_global, self.nu_global = self.mesh.nsimplices(grade - 1), self.mesh.nsimplices(grade)
+        self.n_global = self.ns_global + self.nu_global
+        # column windows (torch owns the memory so that torch.distributed can send / receive slices of it)
+        self.win_s_t = torch.zeros(self.rs.held_hi - self.rs.held_lo, dtype=torch.float64, device="cuda")
+        self.win_u_t = torch.zeros(self.ru.held_hi - self.ru.held_lo, dtype=torch.float64, device="cuda")
+        self.win_s, self.win_u = DeviceVector.from_torch(ctx, self.win_s_t), DeviceVector.from_torch(ctx, self.win_u_t)
+        self.own_s = self.win_s.view(self.rs.own_lo - self.rs.held_lo, self.ns)
+        self.own_u = self.win_u.view(self.ru.own_lo - self.ru.held_lo, self.nu)
+        self.tmp_s, self.tmp_u = DeviceVector(ctx, max(self.ns, 1)).view(0, self.ns), DeviceVector(ctx, max(self.nu, 1)).view(0, self.nu)
+        self._shift = 0.0
+        # inf-norms of the block rows (linalg/eigen.rs:359-368)
+        hb = self.hb
+        rows_s = hb.mass_sigma.row_abs_sums().to_numpy() + hb.dif_test.row_abs_sums().to_numpy()
+        rows_u = self.dif_trial.row_abs_sums().to_numpy() + hb.dif_both.row_abs_sums().to_numpy()
+        a_local = max(float(rows_s.max()) if rows_s.size else 0.0, float(rows_u.max()) if rows_u.size else 0.0)
+        b_rows = hb.mass_u.row_abs_sums().to_numpy()
+        self.a_norm = all_reduce_scalar(a_local, "max", group, world)
+        self.b_norm = all_reduce_scalar(float(b_rows.max()) if b_rows.size else 0.0, "max", group, world)
+
+    # -- windows
+    def _load(self, x, sigma: bool = True, u: bool = True):
+        """Owned segments of x into the column windows, halos refreshed from the neighbours."""
+        if sigma:
+            self.own_s.copy_from(x.view(0, self.ns))
+            exchange_halo(self.win_s_t, self.part_s, self.rank, self.group)
+        if u:
+            self.own_u.copy_from(x.view(self.ns, self.nu))
+            exchange_halo(self.win_u_t, self.part_u, self.rank, self.group)
+
+    # -- pencil protocol
+    def a_apply(self, x, y=None, shift: float = 0.0, symmetrized: bool = False):
+        """y = A x - shift * B x on the rank's rows; symmetrized: the sigma rows negated (the form MINRES needs,
+        problems/elliptic.rs:101-113)."""
+        hb = self.hb
+        y = x.zeros_like() if y is None else y
+        self._load(x)
+        ys, yu = y.view(0, self.ns), y.view(self.ns, self.nu)
+        hb.mass_sigma.apply_window(self.win_s, self.rs.held_lo, ys)
+        hb.dif_test.apply_window(self.win_u, self.ru.held_lo, self.tmp_s)
+        ys.add_scaled(-1.0, self.tmp_s)
+        if symmetrized:
+            ys.scale(-1.0)
+        self.dif_trial.apply_window(self.win_s, self.rs.held_lo, yu)
+        hb.dif_both.apply_window(self.win_u, self.ru.held_lo, self.tmp_u)
+        yu.add(self.tmp_u)
+        if shift != 0.0:
+            hb.mass_u.apply_window(self.win_u, self.ru.held_lo, self.tmp_u)
+            yu.add_scaled(-shift, self.tmp_u)
+        self.applies += 1
+        return y
+
+    def b_apply(self, x, y=None):
+        y = x.zeros_like() if y is None else y
+        self._load(x, sigma=False)
+        y.view(0, self.ns).fill_zero()
+        self.hb.mass_u.apply_window(self.win_u, self.ru.held_lo, y.view(self.ns, self.nu))
+        return y
+
+    def dot(self, x, y) -> float:
+        return all_reduce_scalar(x.dot(y), "sum", self.group, self.world)
+
+    def seed(self, s: int):
+        import numpy as np
+
+        from .api import DeviceVector
+        from .eigen import pseudo_random
+
+        v = np.concatenate([pseudo_random(s, self.ns, self.rs.own_lo),
+                            pseudo_random(s, self.nu, self.ns_global + self.ru.own_lo)])
+        return DeviceVector.from_numpy(self.ctx, v)
+
+    def prepare(self, shift: float) -> float:
+        self._shift = shift
+        return shift
+
+    def solve(self, v):
+        from .api import StopCriterion, minres_op
+        from .eigen import EigenError
+
+        rhs = v.clone()                      # S (A - shift B) x = S v with S = diag(-1 on sigma, +1 on u)
+        rhs.view(0, self.ns).scale(-1.0)
+        x, rep = minres_op(self.ctx, self.n, lambda xin, y: self.a_apply(xin, y, self._shift, True), rhs,
+                           StopCriterion(self.inner_rtol, self.inner_max_iters),
+                           reduce=(lambda local: all_reduce_scalar(local, "sum", self.group, self.world)) if self.world > 1 else None)
+        self.inner_iterations += rep.iters
+        if not rep.converged:
+            raise EigenError("SingularPencil", shift=self._shift, inner_residual=rep.residual)
+        return x
+
+    def gather(self, x):
+        """The global vector (sigma | u) on every rank, for tests."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        mine = x.to_numpy()
+        if self.world == 1:
+            return mine
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (self.rs.own_lo, self.ru.own_lo, mine[:self.ns], mine[self.ns:]), group=self.group)
+        out = np.zeros(self.n_global)
+        for slo, ulo, s, u in parts:
+            out[slo:slo + len(s)] = s
+            out[self.ns_global + ulo:self.ns_global + ulo + len(u)] = u
+        return out

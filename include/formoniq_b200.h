@@ -4,7 +4,7 @@
  * The reference has no FFI of its own (pure Rust traits); each entry point
  * below names the reference interface it replaces (paths relative to the
  * reference checkout).  A Rust shim binds these with a plain `extern "C"`
- * block (see INTEGRATION.md and rust/formoniq-b200-sys/).
+ * block (see INTEGRATION.md and rust/formoniq-b200/src/lib.rs).
  *
  * Conventions
  *  - every function returns 0 on success, <0 on error; the message is
@@ -151,11 +151,22 @@ int fq_hodge_symbolic(fq_ctx* ctx, const fq_mesh* mesh, int grade, size_t sigma_
                       size_t u_row_begin, size_t u_row_end, fq_hodge** out);
 int fq_hodge_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_hodge* blocks, int drop_exact_zeros);
 fq_csr* fq_hodge_block(fq_hodge* blocks, int which);
+/* C = A + B on the union pattern, explicit zeros kept (nalgebra-sparse `&a + &b`): HilbertComplex::hdif_gram =
+ * mass(k) + dif_both(k + 1), crates/formoniq/src/whitney_complex.rs:180-183, whose sparse factorizations are the blocks
+ * of the AFW preconditioner (problems/elliptic.rs:29-47) */
+int fq_csr_add(fq_ctx* ctx, const fq_csr* a, const fq_csr* b, fq_csr** out);
+/* y_i = sum_j |a_ij| over the held rows; its maximum is the inf-norm the eigen solver scales residuals with
+ * (linalg/eigen.rs:359-368) */
+int fq_csr_row_abs_sums(fq_ctx* ctx, const fq_csr* a, fq_vec* y);
+
 /* HodgeBlocks::mixed_hodge_laplacian (formoniq/src/hodge.rs:93-99): [[M_{k-1}, -dif_test], [dif_test^T, dif_both]]
  * stitched on the device (stable transpose + row-wise concatenation instead of CooMatrixExt::block,
  * simplicial/src/linalg.rs:110-167, and a second COO->CSR); bit-identical entries.  The blocks must be fully held
  * (single-GPU row range).  fq_csr_transpose is the transpose used for the lower-left block. */
 int fq_hodge_mixed_laplacian(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out);
+/* the same saddle point with the sigma block-row negated, [[-M_{k-1}, dif_test], [dif_test^T, dif_both]]: the symmetric
+ * form assemble_mixed_kkt hands to MINRES (problems/elliptic.rs:101-113) */
+int fq_hodge_mixed_kkt_symmetric(fq_ctx* ctx, const fq_hodge* blocks, fq_csr** out);
 int fq_csr_transpose(fq_ctx* ctx, const fq_csr* a, fq_csr** out);
 /* RelativeWhitneyComplex::assemble (formoniq/src/whitney_complex.rs:620-624): E_test^T A E_trial for the 0/1 inclusions of
  * the interior DOFs = the sub-matrix A[rows_keep, cols_keep] (ascending index lists, e.g. interior_simps of the test and
@@ -292,6 +303,27 @@ int fq_cg(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rto
           size_t* iters, double* residual, int* converged);
 int fq_minres(fq_ctx* ctx, const fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
               size_t* iters, double* residual, int* converged);
+
+/* ---- Krylov over user operators: iterative::{cg, minres} are generic over LinearOperator / ApproxInverse /
+ * InnerProductSpace (iterative/src/krylov.rs:48-95, 113-211; lib.rs:84-157).  The operator and the preconditioner are
+ * callbacks on DEVICE pointers (y = A x, z = M^-1 r; precond NULL = Identity, precond.rs:16-41); `reduce` completes a
+ * rank-local inner product (the all-reduce of a distributed space; NULL = single process).  All vector updates of
+ * the iteration stay inside the library.  Callbacks return 0 on success. */
+typedef int (*fq_apply_fn)(void* user, const double* x_device, double* y_device);
+typedef int (*fq_reduce_fn)(void* user, double local, double* global);
+int fq_cg_op(fq_ctx* ctx, size_t n, fq_apply_fn apply, fq_apply_fn precond, fq_reduce_fn reduce, void* user, const fq_vec* b,
+             double rtol, size_t max_iters, fq_vec* x, size_t* iters, double* residual, int* converged);
+int fq_minres_op(fq_ctx* ctx, size_t n, fq_apply_fn apply, fq_apply_fn precond, fq_reduce_fn reduce, void* user,
+                 const fq_vec* b, double rtol, size_t max_iters, fq_vec* x, size_t* iters, double* residual, int* converged);
+/* MINRES on `a` with a block-diagonal preconditioner of inner solves: segment [offsets[i], offsets[i+1]) of the
+ * vector is preconditioned by blocks[i]^-1 (Jacobi-CG to inner_rtol; NULL = identity).  With blocks =
+ * {hdif_gram(k-1), hdif_gram(k)} this is the AFW mixed_block_preconditioner of problems/elliptic.rs:29-47, whose blocks
+ * the reference factorises with a sparse Cholesky. */
+int fq_minres_blockdiag(fq_ctx* ctx, const fq_csr* a, int nblocks, const fq_csr* const* blocks, const size_t* offsets,
+                        double inner_rtol, size_t inner_max_iters, const fq_vec* b, double rtol, size_t max_iters, fq_vec* x,
+                        size_t* iters, double* residual, int* converged, size_t* inner_iters);
+/* non-owning view of v[offset, offset + n) (the sigma / u segments of a mixed vector) */
+int fq_vec_view(fq_ctx* ctx, const fq_vec* v, size_t offset, size_t n, fq_vec** out);
 
 #ifdef __cplusplus
 }

@@ -142,3 +142,31 @@ def test_eigen_seed_vectors_match_the_reference_probe():
         v = pseudo_random(seed, 64)
         assert all(v[i] == O.pseudo_random(seed, i) for i in range(64))
         assert np.all(np.abs(v) <= 1.0)
+
+
+def _build_abi_smoke(tmp_path):
+    from formoniq_b200 import build as B
+
+    lib = B.build()
+    exe = tmp_path / "abi_smoke"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L", os.path.dirname(lib),
+                           "-lformoniq_b200", "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe
+
+
+def test_header_compiles_as_c_and_reports_the_missing_device(tmp_path):
+    # include/formoniq_b200.h exercised by a C compiler (not ctypes): without a device every compute entry point must
+    # fail with FQ_ERR_CUDA — there is no CPU fallback to route through
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    out = subprocess.run([str(_build_abi_smoke(tmp_path))], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok nogpu", out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_c_program_assembles_through_the_abi(tmp_path):
+    out = subprocess.run([str(_build_abi_smoke(tmp_path))], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok gpu", out.stdout + out.stderr

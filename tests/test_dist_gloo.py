@@ -86,3 +86,96 @@ def test_slab_partition_ranges_tile_every_grade():
                 for peer, lo, hi in recvs:
                     assert (r, lo, hi) in p.sends(peer)
                 assert len(sends) == len(recvs) == (0 if world == 1 else (1 if r in (0, world - 1) else 2))
+
+
+# ---- distributed shift-invert Lanczos: the driver (formoniq_b200/eigen.py) over a row-partitioned numpy pencil
+class _NpVec:
+    """The subset of DeviceVector the Lanczos driver uses, on host memory."""
+
+    def __init__(self, a):
+        self.a = np.array(a, dtype=np.float64)
+
+    def zeros_like(self):
+        return _NpVec(np.zeros_like(self.a))
+
+    def add_scaled(self, alpha, x):
+        self.a += alpha * x.a
+
+    def scale(self, alpha):
+        self.a *= alpha
+
+
+class _NpDistPencil:
+    """Rows [lo, hi) of (A, B) per rank; matvecs gather x from all ranks, inner products are all-reduced, the inner
+    solve is a (dense, replicated) solve whose result each rank slices — the protocol of dist.DistKktPencil."""
+
+    def __init__(self, a, b, rank, world):
+        from formoniq_b200.dist import all_reduce_scalar
+
+        self.A, self.B, self.rank, self.world = a, b, rank, world
+        self.n_global = a.shape[0]
+        self.lo = rank * self.n_global // world
+        self.hi = (rank + 1) * self.n_global // world
+        self.n = self.hi - self.lo
+        self._ar = all_reduce_scalar
+        self.a_norm = abs(a).sum(axis=1).max()
+        self.b_norm = abs(b).sum(axis=1).max()
+
+    def _gather(self, x):
+        parts = [None] * self.world
+        dist.all_gather_object(parts, x.a)
+        return np.concatenate(parts)
+
+    def a_apply(self, x):
+        return _NpVec(self.A[self.lo:self.hi] @ self._gather(x))
+
+    def b_apply(self, x):
+        return _NpVec(self.B[self.lo:self.hi] @ self._gather(x))
+
+    def dot(self, x, y):
+        return self._ar(float(x.a @ y.a), "sum")
+
+    def seed(self, s):
+        from formoniq_b200.eigen import pseudo_random
+
+        return _NpVec(pseudo_random(s, self.n, self.lo))
+
+    def prepare(self, shift):
+        self.M = self.A - shift * self.B
+        return shift
+
+    def solve(self, v):
+        return _NpVec(np.linalg.solve(self.M, self._gather(v))[self.lo:self.hi])
+
+
+def _eigen_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from formoniq_b200.eigen import shift_invert_lanczos
+
+        n = 40
+        a = np.diag(2.0 * np.ones(n)) - np.diag(np.ones(n - 1), 1) - np.diag(np.ones(n - 1), -1)
+        b = np.diag(1.0 + 0.5 * np.cos(np.arange(n)) ** 2)
+        vals, vecs = shift_invert_lanczos(_NpDistPencil(a, b, rank, world), 0.0, 4)
+        np.save(os.path.join(out_dir, f"eig{rank}.npy"), vals)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_distributed_lanczos_driver_gloo(tmp_path, world):
+    # the eigenvalues of a row-partitioned pencil do not depend on the number of ranks (VERDICT g2: 8-GPU eigenvalues ==
+    # 1-GPU eigenvalues) and equal the dense generalised eigenvalues closest to the shift
+    import scipy.linalg as sla
+
+    port = _free_port()
+    mp.spawn(_eigen_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    n = 40
+    a = np.diag(2.0 * np.ones(n)) - np.diag(np.ones(n - 1), 1) - np.diag(np.ones(n - 1), -1)
+    b = np.diag(1.0 + 0.5 * np.cos(np.arange(n)) ** 2)
+    ref = np.sort(sla.eigh(a, b, eigvals_only=True))[:4]
+    for r in range(world):
+        vals = np.load(os.path.join(str(tmp_path), f"eig{r}.npy"))
+        assert np.abs(vals - ref).max() <= 1e-9 * np.abs(ref).max()

@@ -106,6 +106,16 @@ def test_degenerate_and_invalid_inputs(fq, ctx):
         fq.WhitneyPairing.mass(2, 1).element_batch(mesh, 0, cx.ncells + 1)
     with pytest.raises(fq.FormoniqError):
         fq.Mesh.from_arrays(ctx, 2, [9, 16, 8], [cx.cell_faces(0), cx.cell_faces(1), cx.cell_faces(2)], s[:-1])
+    # a face id beyond the simplex count of its grade is rejected at upload (it would be an out-of-bounds device read)
+    bad_edges = cx.cell_faces(1).copy()
+    bad_edges[3] = cx.nsimplices(1)
+    with pytest.raises(fq.FormoniqError):
+        fq.Mesh.from_arrays(ctx, 2, [cx.nsimplices(j) for j in range(3)], [cx.cell_faces(0), bad_edges, cx.cell_faces(2)], s)
+    # Jacobi needs a non-zero diagonal (iterative/src/precond.rs:101-104 asserts it): dif_both(n + 1) = 0 has none
+    zero = fq.WhitneyPairing.dif_both(2, 3).assemble(mesh, False)
+    b = fq.DeviceVector.from_numpy(ctx, np.ones(zero.shape[0]))
+    with pytest.raises(fq.FormoniqError):
+        fq.cg(zero, "jacobi", b, fq.StopCriterion(1e-10, 10))
 
 
 # ------------------------------------------------------------------ Kuhn generator
@@ -877,6 +887,78 @@ def test_eigen_hodge_laplace_evp_on_the_device_blocks(fq, ctx):
         assert r <= 1e-9
     ref = spla.eigsh(ah.tocsc(), k=k, M=bh.tocsc(), sigma=1.0, which="LM", return_eigenvectors=False)
     assert np.abs(np.sort(vals) - np.sort(ref)).max() <= 1e-8 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------ hdif_gram, AFW block preconditioner, SpMV-based Lanczos
+@pytest.mark.parametrize("dim,shape,k", [(2, [6, 5], 0), (2, [5, 5], 1), (2, [4, 4], 2), (3, [3, 4, 3], 1), (3, [3, 3, 3], 3)])
+def test_hdif_gram_is_mass_plus_dif_both(fq, ctx, dim, shape, k):
+    # whitney_complex.rs:180-183: hdif_gram(k) = mass(k) + dif_both(k + 1), the sum on the union pattern with explicit
+    # zeros kept (nalgebra-sparse `+`); at k = dim the second operand is the zero matrix
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+    mesh = mesh_from_oracle(fq, ctx, cx, s)
+    wc = fq.WhitneyComplex(mesh)
+    m, d = wc.mass(k).to_scipy(), wc.dif_both(k + 1).to_scipy()
+    got = wc.hdif_gram(k).to_scipy()
+    exp = cx.assemble(s, O.MASS, k).to_scipy() + cx.assemble(s, O.DIF_BOTH, k + 1).to_scipy()
+    assert got.shape == exp.shape
+    ones = lambda a: type(a)((np.ones_like(a.data), a.indices, a.indptr), shape=a.shape)  # noqa: E731
+    assert got.nnz == (ones(m) + ones(d)).nnz                    # the union of the operands' patterns, nothing pruned
+    assert abs(got - exp).max() <= 1e-15 * max(abs(exp).max(), 1e-300)
+
+
+def test_afw_block_preconditioned_minres_solves_the_mixed_system(fq, ctx):
+    # problems/elliptic.rs:29-47, 132-182, 338-367: MINRES on the mixed KKT matrix with the block preconditioner
+    # diag(hdif_gram(k-1)^-1, hdif_gram(k)^-1) (inner Jacobi-CG solves instead of the reference's sparse Cholesky):
+    # the solution matches a direct solve to 1e-9 and the iteration count does not grow with the mesh (config 1: 2-D,
+    # 1-forms on the unit square).  Unpreconditioned MINRES needs thousands of iterations on the same systems.
+    import scipy.sparse.linalg as spla
+
+    iters = []
+    for n in (8, 16, 32):
+        mesh = fq.Mesh.kuhn(ctx, 2, [n, n])
+        hb = fq.HodgeBlocks.compute(mesh, 1)
+        kkt = hb.mixed_hodge_laplacian(symmetrized=True)           # sigma rows negated: symmetric (elliptic.rs:101-113)
+        wc = fq.WhitneyComplex(mesh)
+        blocks = [wc.hdif_gram(0), wc.hdif_gram(1)]
+        ntot = hb.n_sigma + hb.n_u
+        rhs = ((np.arange(ntot) % 7) - 3).astype(np.float64)       # the probe of elliptic.rs:270
+        b = fq.DeviceVector.from_numpy(ctx, rhs)
+        x, rep, inner = fq.minres_blockdiag(kkt, blocks, [0, hb.n_sigma, ntot], b, fq.StopCriterion(1e-10, 500),
+                                            fq.StopCriterion(1e-13, 5000))
+        assert rep.converged, (n, rep)
+        ref = spla.spsolve(kkt.to_scipy().tocsc(), rhs)
+        assert np.linalg.norm(x.to_numpy() - ref) <= 1e-7 * np.linalg.norm(ref), n
+        iters.append(rep.iters)
+    assert max(iters) <= 60 and iters[2] <= iters[0] + 10, iters     # mesh-independent (elliptic.rs:338-367)
+
+
+def test_lanczos_with_the_spmv_based_inner_solve(fq, ctx):
+    # SURVEY 7-H6 / VERDICT f3: the shift-invert step without a host factorisation — MINRES on A - shift*B, device only —
+    # gives the eigenvalues of the LU-based run (the reference's division of labour) to 1e-9; and the row-partitioned
+    # pencil (dist.DistKktPencil, here with one rank) gives them again
+    from formoniq_b200.dist import DistKktPencil
+
+    shape = [5, 4, 4]
+    mesh = fq.Mesh.kuhn(ctx, 3, shape)
+    hb = fq.HodgeBlocks.compute(mesh, 1)
+    a = hb.mixed_hodge_laplacian()
+    import scipy.sparse as sp
+
+    bh = sp.bmat([[sp.csr_matrix((hb.n_sigma, hb.n_sigma)), None], [None, hb.mass_u.to_scipy()]], format="csr")
+    b = fq.DeviceCsr.from_scipy(ctx, bh)
+    k, shift = 3, 5.0
+    v_lu, _ = fq.sparse_shift_invert_eigen(a, b, shift, k, inner="lu")
+    v_mr, vecs = fq.sparse_shift_invert_eigen(a, b, shift, k, inner="minres", negate_rows=hb.n_sigma)
+    assert np.abs(v_lu - v_mr).max() <= 1e-9 * np.abs(v_lu).max()
+    pencil = DistKktPencil(ctx, 3, shape, 1)
+    v_dist, vecs_d = fq.shift_invert_lanczos(pencil, shift, k)
+    assert np.abs(v_lu - v_dist).max() <= 1e-9 * np.abs(v_lu).max()
+    assert pencil.inner_iterations > 0 and pencil.applies > pencil.inner_iterations
+    ah = a.to_scipy()
+    for lam, x in zip(v_dist, vecs_d):
+        xh = x.to_numpy()
+        r = np.linalg.norm(ah @ xh - lam * (bh @ xh)) / ((abs(ah).sum(axis=1).max() + abs(lam) * abs(bh).sum(axis=1).max()) * np.linalg.norm(xh))
+        assert r <= 1e-8
 
 
 # ------------------------------------------------------------------ LinearForm::assemble (galerkin.rs:279-312)
