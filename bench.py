@@ -335,16 +335,57 @@ def run_b200(args):
                 entry["peer_ms"] = p0.elapsed_time(p1) / args.steps
                 # the fused kernel must give the bits of exchange + windowed SpMV
                 exchange_halo(xw, part, rank)
-                y_ref = a.apply_window(x, r.held_lo).to_torch().clone()
+                y_ref = a.apply_window(x, r.held_lo).to_numpy()
                 ph.publish(); ph.apply(a, y); ph.release()
                 torch.cuda.synchronize()
-                entry["peer_parity"] = bool(torch.equal(y.to_torch(), y_ref))
+                entry["peer_parity"] = bool(np.array_equal(y.to_numpy(), y_ref))
                 del ph, xv
             except Exception as exc:  # never lose the bench line to the optional fused measurement
                 print(f"[bench] fused peer SpMV skipped on rank {rank}: {exc}", file=sys.stderr)
                 entry["peer_ms"] = None
         spmv.append(entry)
         del x, y, xw
+
+    # ---- strong scaling: ONE fixed n^3 Kuhn cube (12.58 M tets at n = 128) cut into z-slabs over the ranks.  Assembly of
+    # the four blocks (owner computes: the halo layer is recomputed, no collective) and the mixed-operator application
+    # the Krylov / Lanczos solvers do per iteration: halo exchange of the two column windows (NCCL send/recv with the
+    # z-neighbours) + the four windowed SpMVs.  The second one is the line with a collective in it.
+    strong = None
+    if not args.no_strong and n >= world:
+        try:
+            from formoniq_b200.dist import DistKktPencil
+
+            del hb, mats
+            fq._lib.lib().fq_device_cache_trim()
+            pencil = DistKktPencil(ctx, DIM, [n, n, n], GRADE, rank, world)
+            for _ in range(2):
+                pencil.hb.numeric(pencil.mesh, True)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(args.steps):
+                pencil.hb.numeric(pencil.mesh, True)
+            a1.record(stream)
+            barrier()
+            asm_ms = a0.elapsed_time(a1) / args.steps
+            xk = fq.DeviceVector.from_torch(ctx, torch.cos(torch.arange(pencil.n, device="cuda", dtype=torch.float64) ** 2 + 1.0))
+            yk = fq.DeviceVector(ctx, pencil.n)
+            for _ in range(3):
+                pencil.a_apply(xk, yk)
+            barrier()
+            a0.record(stream)
+            for _ in range(args.steps):
+                pencil.a_apply(xk, yk)
+            a1.record(stream)
+            barrier()
+            op_ms = a0.elapsed_time(a1) / args.steps
+            blocks = [pencil.hb.mass_sigma, pencil.hb.dif_test, pencil.dif_trial, pencil.hb.dif_both]
+            strong = {"asm_ms": asm_ms, "op_ms": op_ms, "op_bytes": sum(b.spmv_bytes for b in blocks),
+                      "op_nnz": sum(b.nnz for b in blocks), "cells": 6 * n ** 3}
+            del pencil, xk, yk
+        except Exception as exc:
+            print(f"[bench] strong-scaling section skipped on rank {rank}: {exc}", file=sys.stderr)
+            strong = None
 
     # ---- reduce over ranks (max time, sum of work)
     def allmax(v):
@@ -376,6 +417,16 @@ def run_b200(args):
         peer_parity = allsum(sum(0 if s["peer_parity"] else 1 for s in spmv)) == 0
     secs = ms_total / 1e3
     value = cells_all * args.steps / secs
+    ok_all = allsum(0 if strong is not None else 1) == 0
+    strong_out = None
+    if ok_all:
+        s_asm, s_op = allmax(strong["asm_ms"]), allmax(strong["op_ms"])
+        s_bytes, s_nnz = allsum(strong["op_bytes"]), allsum(strong["op_nnz"])
+        strong_out = {"mesh": f"{n}^3 Kuhn cube ({strong['cells']} tets) over {world} z-slabs",
+                      "assembly_ms": s_asm, "assembly_elements_per_s": strong["cells"] / (s_asm / 1e3),
+                      "kkt_apply_ms": s_op, "kkt_apply_gbs": s_bytes / 1e9 / (s_op / 1e3), "kkt_nnz": int(s_nnz),
+                      "kkt_apply": "halo exchange of the sigma / u windows (NCCL send/recv) + 4 windowed SpMVs per apply"
+                                   if world > 1 else "4 windowed SpMVs per apply (1 GPU: no exchange)"}
 
     # ---- e2e through the C ABI with host buffers (rank-local; H2D + symbolic + numeric + D2H per step)
     e2e = None
@@ -428,6 +479,7 @@ def run_b200(args):
                                "+ compaction + retarget; later passes run the fused kernel alone"},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "strong_scaling": strong_out,
     }
     if fused and args.slab_ms:  # break-even of the plan against re-running the two-kernel slab path (FQ_NO_TILE=1 bench)
         out["first_pass"]["break_even_steps_vs_slab"] = plan_build_ms / max(args.slab_ms - fused_ms, 1e-9)
@@ -527,6 +579,7 @@ def main():
     ap.add_argument("--n", type=int, default=128, help="boxes per axis per GPU (128 -> 12.58 M tets)")
     ap.add_argument("--sample-n", type=int, default=64, help="Kuhn cube size of the CPU sample (0: calibrate to ~20 s)")
     ap.add_argument("--no-kkt", action="store_true", help="skip the KKT-operator SpMV")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling section (fixed n^3 mesh over the ranks)")
     ap.add_argument("--slab-ms", type=float, default=10.95,
                     help="ms per step of the two-kernel slab path on this workload (FQ_NO_TILE=1 run; default: the "
                          "round-1 measurement, profiles/r01_v11_bench_n128.json) for the plan break-even")
