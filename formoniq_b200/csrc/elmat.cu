@@ -75,6 +75,37 @@ __global__ void __launch_bounds__(128) elmat_gen_kernel(Fn fn, const uint32_t* _
   }
 }
 
+// dim >= 4: the tape's inputs are g^-1 (row-major) and the volume; the generic geometry stage runs in the same thread
+template <class Fn, int N>
+__global__ void __launch_bounds__(128) elmat_gen_geo_kernel(Fn fn, const uint32_t* __restrict__ cell_edges,
+                                                             const double* __restrict__ lengths, uint32_t edge_lo,
+                                                             size_t c0, size_t ncells, int max_t, SlabPtrs slabs,
+                                                             int* __restrict__ err) {
+  extern __shared__ double stage_all[];
+  constexpr int NE = N * (N + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* stage = stage_all + size_t(warp) * size_t(max_t) * kStagePad;
+  const size_t ngroups = (ncells + 31) / 32;
+  const size_t wstride = size_t(gridDim.x) * (blockDim.x >> 5);
+  for (size_t grp = size_t(blockIdx.x) * (blockDim.x >> 5) + warp; grp < ngroups; grp += wstride) {
+    const size_t first = grp * 32;
+    const int nvalid = int(ncells - first < 32 ? ncells - first : 32);
+    const size_t i = first + size_t(lane < nvalid ? lane : nvalid - 1);
+    const uint32_t* ce = cell_edges + (c0 + i) * NE;
+    double len[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) len[e] = __ldg(lengths + (ce[e] - edge_lo));
+    double s[N * N + 1];
+    if (!geometry_generic(N, len, s, &s[N * N])) {
+      if (err) atomicExch(err, 1);
+#pragma unroll
+      for (int e = 0; e <= N * N; ++e) s[e] = 0.0;
+    }
+    WarpStageSink sink{stage, slabs, first, lane, nvalid};
+    fn(s, sink);
+  }
+}
+
 #define FQ_DECLARE_FN(fn, n, fk, kind, grade, nin, nout)                                        \
   struct Fn_##fn {                                                                              \
     template <class S>                                                                          \
@@ -87,9 +118,26 @@ FQ_GEN_ELMAT_LIST(FQ_DECLARE_FN)
 
 struct GenEntry {
   int n, fused_k, kind, grade, nin, nout;
-  void (*launch)(fq_ctx*, const fq_mesh*, size_t, size_t, int, const SlabPtrs&);
+  void (*launch)(fq_ctx*, const fq_mesh*, size_t, size_t, int, const SlabPtrs&, int*);
 };
 
+template <class Fn, int N>
+static void launch_gen_geo(fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int max_t, const SlabPtrs& slabs, int* d_err) {
+  const size_t nc = c1 - c0;
+  if (nc == 0) return;
+  const int block = 128;
+  const size_t smem = size_t(block / 32) * size_t(max_t) * kStagePad * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQ_CUDA(cudaFuncSetAttribute(elmat_gen_geo_kernel<Fn, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const int grid = grid_for((nc + 31) / 32 * 32, block, ctx->sm_count, 4);
+  elmat_gen_geo_kernel<Fn, N><<<grid, block, smem, ctx->stream>>>(Fn{}, mesh->cell_faces[1].p, mesh->lengths.p,
+                                                                  uint32_t(mesh->edge_lo), c0, nc, max_t, slabs, d_err);
+  fq_count_launch(ctx);
+  FQ_CUDA(cudaGetLastError());
+}
 template <class Fn, int NE>
 static void launch_gen(fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int max_t, const SlabPtrs& slabs) {
   const size_t nc = c1 - c0;
@@ -110,8 +158,11 @@ static void launch_gen(fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, i
 
 #define FQ_ENTRY(fn, n, fk, kind, grade, nin, nout)                                                        \
   GenEntry{n, fk, kind, grade, nin, nout,                                                                  \
-           [](fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int max_t, const SlabPtrs& slabs) {  \
-             launch_gen<Fn_##fn, nin>(ctx, mesh, c0, c1, max_t, slabs);                                    \
+           [](fq_ctx* ctx, const fq_mesh* mesh, size_t c0, size_t c1, int max_t, const SlabPtrs& slabs, int* d_err) { \
+             if (n >= 4)                                                                                   \
+               launch_gen_geo<Fn_##fn, (n >= 4 ? n : 4)>(ctx, mesh, c0, c1, max_t, slabs, d_err);          \
+             else                                                                                          \
+               launch_gen<Fn_##fn, (n >= 4 ? 0 : nin)>(ctx, mesh, c0, c1, max_t, slabs);                   \
            }},
 static const GenEntry g_entries[] = {FQ_GEN_ELMAT_LIST(FQ_ENTRY)};
 #undef FQ_ENTRY
@@ -271,7 +322,7 @@ void elmat_to_slabs(fq_ctx* ctx, const fq_mesh* mesh, const std::vector<BlockSpe
         sp.p[b] = d_outs[b];
         max_t = std::max(max_t, block_nouts(dim, blocks[b]));
       }
-      e->launch(ctx, mesh, c0, c1, max_t, sp);
+      e->launch(ctx, mesh, c0, c1, max_t, sp, d_err);
       return;
     }
   }

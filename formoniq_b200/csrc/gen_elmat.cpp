@@ -101,173 +101,6 @@ static void emit_function(const std::string& name, int n, const std::vector<Bloc
 }
 
 
-// "Core" functions for the tile-fused assembly kernel (tile.cu): the masses of
-// grades k-1, k, k+1 of an n-cell, emitting every DISTINCT stored value once
-// (entries that hash-cons to one register share a slot).  The sandwiches
-// d*M*D are evaluated by the gather phase from these values.  map[] gives for
-// every mass entry (three row-major matrices concatenated) the distinct slot
-// | 0x100 when negated, or -1 for an exact zero.
-struct CoreEntry {
-  std::string name;
-  int n, k, variant, ninputs, ndistinct, nouts;
-};
-// variant 0: the three masses M_{k-1}, M_k, M_{k+1} (every sandwich is a recipe);
-// variant 1: M_{k-1}, M_k and the sandwich dif_both(k+1) stored directly (HodgeBlocks: fewer gather terms)
-static std::vector<BlockSpec> core_blocks(int k, int variant) {
-  if (variant == 1) return {{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_DIF_BOTH, k + 1}};
-  return {{KIND_MASS, k - 1}, {KIND_MASS, k}, {KIND_MASS, k + 1}};
-}
-static void emit_core(const std::string& name, int n, int k, int variant, CoreEntry& e) {
-  TapeBuilder tb;
-  std::vector<BlockLayout> layout;
-  const std::vector<BlockSpec> blocks = core_blocks(k, variant);
-  const Tape t = build_tape(n, blocks, &layout, &tb);
-  int nouts = 0;
-  for (const BlockLayout& l : layout) nouts += l.rows * l.cols;
-  std::vector<int> map(size_t(nouts), -1);
-  std::map<uint32_t, int> slot_of;
-  std::map<int, int> slot_group;  // distinct slot -> 0 (first two stored blocks) or 1 (third)
-  const std::vector<TapeOp> ops = tb.ssa_ops();
-  // Staged form for the tile kernel: stage A = everything up to the last division / square root (the
-  // geometry: Gram matrix, determinant, inverse, volume — the latency-bound head of the tape), stage B = the
-  // division-free rest.  `mid` carries the SSA values that are live across the cut.
-  int cut = -1;
-  for (size_t i = 0; i < ops.size(); ++i)
-    if (ops[i].op == OP_DIV || ops[i].op == OP_SQRTABS) cut = int(i);
-  auto is_store = [](const TapeOp& o) { return o.op == OP_STORE || o.op == OP_STOREN || o.op == OP_STOREC; };
-  auto uses = [&](const TapeOp& o, uint32_t* u) -> int {  // SSA registers an op reads
-    switch (o.op) {
-      case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: u[0] = o.a; u[1] = o.b; return 2;
-      case OP_MULC: case OP_SQRTABS: case OP_STORE: case OP_STOREN: u[0] = o.a; return 1;
-      default: return 0;
-    }
-  };
-  std::map<uint32_t, int> mid_of;  // SSA value -> index in mid[]
-  {
-    std::map<uint32_t, int> def_pos;
-    for (int i = 0; i < t.ninputs; ++i) def_pos[uint32_t(i)] = -1;
-    for (size_t i = 0; i < ops.size(); ++i)
-      if (!is_store(ops[i])) def_pos[ops[i].d] = int(i);
-    for (size_t i = 0; i < ops.size(); ++i) {
-      // stores of stage A are deferred to stage B, so their operands cross the cut as well
-      if (int(i) <= cut && !is_store(ops[i])) continue;
-      uint32_t u[2];
-      const int nu = uses(ops[i], u);
-      for (int q = 0; q < nu; ++q)
-        if (def_pos.at(u[q]) <= cut && !mid_of.count(u[q])) {
-          const int idx = int(mid_of.size());
-          mid_of[u[q]] = idx;
-        }
-    }
-  }
-  // Stage B in two halves for the alternating producer/consumer kernel: B1 = what the first two stored blocks
-  // (M_{k-1}, M_k) need, B2 = what the third (M_{k+1} or dif_both(k+1)) needs.  An op needed by both halves is
-  // evaluated by both (same operands, same rounding).  The split is usable when no stored value is shared.
-  auto out_group = [&](uint32_t out) {  // 0: blocks 0 and 1, 1: block 2
-    return (layout.size() >= 3 && int(out) >= layout[2].out_offset) ? 1 : 0;
-  };
-  std::map<uint32_t, int> need;  // SSA value -> bit 0: needed by group 0, bit 1: by group 1
-  for (size_t i = ops.size(); i-- > 0;) {
-    const TapeOp& o = ops[i];
-    uint32_t u[2];
-    const int nu = uses(o, u);
-    int mask;
-    if (o.op == OP_STORE || o.op == OP_STOREN)
-      mask = 1 << out_group(o.d);
-    else if (is_store(o))
-      continue;
-    else
-      mask = need.count(o.d) ? need[o.d] : 0;
-    for (int q = 0; q < nu; ++q) need[u[q]] |= mask;
-  }
-  bool split_ok = true;
-  std::ostringstream full, sa, sb_pro, sb, sb1_pro, sb1, sb2_pro, sb2;
-  auto line = [&](const TapeOp& o) -> std::string {
-    char buf[256];
-    switch (o.op) {
-      case OP_ADD: std::snprintf(buf, sizeof buf, "  const double %s = __dadd_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
-      case OP_SUB: std::snprintf(buf, sizeof buf, "  const double %s = __dsub_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
-      case OP_MUL: std::snprintf(buf, sizeof buf, "  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
-      case OP_MULC: std::snprintf(buf, sizeof buf, "  const double %s = __dmul_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), cst(tb.consts[o.b]).c_str()); break;
-      case OP_DIV: std::snprintf(buf, sizeof buf, "  const double %s = __ddiv_rn(%s, %s);\n", reg(o.d).c_str(), reg(o.a).c_str(), reg(o.b).c_str()); break;
-      case OP_SQRTABS: std::snprintf(buf, sizeof buf, "  const double %s = __dsqrt_rn(fabs(%s));\n", reg(o.d).c_str(), reg(o.a).c_str()); break;
-      case OP_LOADC: std::snprintf(buf, sizeof buf, "  const double %s = %s;\n", reg(o.d).c_str(), cst(tb.consts[o.b]).c_str()); break;
-      default: buf[0] = 0; break;
-    }
-    return buf;
-  };
-  for (int i = 0; i < t.ninputs; ++i) {
-    full << "  const double r" << i << " = s[" << i << "];\n";
-    sa << "  const double r" << i << " = s[" << i << "];\n";
-  }
-  for (size_t i = 0; i < ops.size(); ++i) {
-    const TapeOp& o = ops[i];
-    const bool in_a = int(i) <= cut;
-    if (o.op == OP_STORE || o.op == OP_STOREN) {
-      auto it = slot_of.find(o.a);
-      if (it == slot_of.end()) {
-        const int slot = int(slot_of.size());
-        it = slot_of.emplace(o.a, slot).first;
-        const std::string put = "  sink.template put<0, " + std::to_string(slot) + ">(" + reg(o.a) + ");\n";
-        full << put;
-        (in_a ? sb_pro : sb) << put;
-        const int g = out_group(o.d);
-        slot_group[it->second] = g;
-        (g == 0 ? (in_a ? sb1_pro : sb1) : (in_a ? sb2_pro : sb2)) << put;
-      } else if (slot_group[it->second] != out_group(o.d)) {
-        split_ok = false;  // one stored value serves both halves
-      }
-      map[o.d] = it->second | (o.op == OP_STOREN ? 0x100 : 0);
-    } else if (o.op == OP_STOREC) {
-      if (tb.consts[o.b] != 0.0) throw std::runtime_error("core: non-zero constant mass entry");
-      map[o.d] = -1;
-    } else {
-      const std::string l = line(o);
-      full << l;
-      (in_a ? sa : sb) << l;
-      if (!in_a) {
-        const int m = need.count(o.d) ? need[o.d] : 0;
-        if (m & 1) sb1 << l;
-        if (m & 2) sb2 << l;
-      }
-    }
-  }
-  std::printf("// core n=%d k=%d variant=%d  inputs=%d outputs=%d  ops: add/sub=%d mul=%d div=%d sqrt=%d\n", n, k, variant, t.ninputs, nouts,
-              t.n_addsub, t.n_mul, t.n_div, t.n_sqrt);
-  std::printf("template <class Sink>\n__device__ __forceinline__ void %s(const double* __restrict__ s, Sink& sink) {\n%s}\n",
-              name.c_str(), full.str().c_str());
-  // stage A / stage B
-  const int nmid = int(mid_of.size());
-  std::printf("constexpr int %s_nmid = %d;\n", name.c_str(), nmid > 0 ? nmid : 1);
-  std::printf("__device__ __forceinline__ void %s_a(const double* __restrict__ s, double* __restrict__ mid) {\n%s", name.c_str(),
-              sa.str().c_str());
-  for (const auto& kv : mid_of) std::printf("  mid[%d] = %s;\n", kv.second, reg(kv.first).c_str());
-  std::printf("}\n");
-  for (int half = 0; half < 2; ++half) {
-    std::printf("template <class Sink>\n__device__ __forceinline__ void %s_b%d(const double* __restrict__ mid, Sink& sink) {\n",
-                name.c_str(), half + 1);
-    for (const auto& kv : mid_of) std::printf("  const double %s = mid[%d];\n", reg(kv.first).c_str(), kv.second);
-    std::printf("%s%s}\n", (half ? sb2_pro : sb1_pro).str().c_str(), (half ? sb2 : sb1).str().c_str());
-  }
-  // bit s of the mask: distinct slot s belongs to the second half
-  unsigned long long gmask_lo = 0, gmask_hi = 0;
-  for (const auto& kv : slot_group)
-    if (kv.second) (kv.first < 64 ? gmask_lo : gmask_hi) |= 1ull << (kv.first & 63);
-  std::printf("constexpr int %s_split_ok = %d;\nstatic const unsigned long long %s_half2[2] = {0x%llxull, 0x%llxull};\n",
-              name.c_str(), (split_ok && slot_of.size() <= 128) ? 1 : 0, name.c_str(), gmask_lo, gmask_hi);
-  std::printf("static const short %s_map[%d] = {", name.c_str(), nouts > 0 ? nouts : 1);
-  for (int i = 0; i < nouts; ++i) std::printf("%s%d", i ? ", " : "", map[size_t(i)]);
-  if (nouts == 0) std::printf("0");
-  std::printf("};\n\n");
-  e.name = name;
-  e.n = n;
-  e.k = k;
-  e.variant = variant;
-  e.ninputs = t.ninputs;
-  e.ndistinct = int(slot_of.size());
-  e.nouts = nouts;
-}
-
 // Staged "set" functions for the tile-fused kernel (tile.cu): the element matrices of a block set, every
 // distinct value of every row stored once (tape.hpp: set_layout).  Stage A = the geometry head of the tape (up to
 // the last division / square root; `mid` carries the values that are live across the cut), then one function per
@@ -499,26 +332,24 @@ int main() {
       entries.push_back(e);
     }
   }
+  // dim 4 (BASELINE config 3: 4-D k = 2): the fused Hodge tapes as straight-line code as well; their inputs are g^-1
+  // (row-major) and the volume from the generic geometry stage (geometry.cuh: nalgebra's 4x4 cofactor inverse), so the
+  // 3 459 operations of hodge_blocks(2) run out of registers instead of the interpreter's global scratch slab
+  for (int k = 0; k <= 4; ++k) {
+    Entry e{};
+    e.name = "fq_el_n4_hodge" + std::to_string(k);
+    e.n = 4;
+    e.fused_k = k;
+    e.kind = -1;
+    e.grade = k;
+    emit_function(e.name, 4, hodge_blocks(k), e);
+    entries.push_back(e);
+  }
   // X-macro list: (function, n, fused_k, kind, grade, ninputs, nouts)
   std::printf("#define FQ_GEN_ELMAT_LIST(X) \\\n");
   for (const Entry& e : entries)
     std::printf("  X(%s, %d, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.fused_k, e.kind, e.grade, e.ninputs,
                 e.nouts);
-  std::printf("\n");
-  // cores: n <= 3, every grade
-  std::vector<CoreEntry> cores;
-  for (int n = 1; n <= 3; ++n)
-    for (int k = 0; k <= n; ++k)
-      for (int variant = 0; variant < 2; ++variant) {
-        CoreEntry e{};
-        emit_core(std::string(variant ? "fq_hcore_n" : "fq_core_n") + std::to_string(n) + "_k" + std::to_string(k), n, k,
-                  variant, e);
-        cores.push_back(e);
-      }
-  // X-macro list: (function, n, k, variant, ninputs, ndistinct, nouts)
-  std::printf("#define FQ_GEN_CORE_LIST(X) \\\n");
-  for (const CoreEntry& e : cores)
-    std::printf("  X(%s, %d, %d, %d, %d, %d, %d) \\\n", e.name.c_str(), e.n, e.k, e.variant, e.ninputs, e.ndistinct, e.nouts);
   std::printf("\n");
   // staged block sets of the tile-fused kernel: hodge_blocks(k) and every single block
   std::vector<SetEntry> sets;
