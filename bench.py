@@ -218,6 +218,7 @@ def run_b200(args):
     first_pass_wall_ms = 1e3 * (time.perf_counter() - t_first)
     first_report = ctx.timing_report()
     plan_build_ms = hb.blocks[1].plan_build_ms
+    cell_visits = hb.blocks[1].plan_cell_visits
 
     def step():
         hb.numeric(mesh, True)  # one fused element kernel + one segmented reduction per block
@@ -451,6 +452,16 @@ def run_b200(args):
     achieved = (asm_bytes / 1e9) / (asm_kernel_ms / 1e3) if asm_kernel_ms > 0 else 0.0
     big = max(range(len(spmv)), key=lambda i: spmv[i]["nnz"])
     fused_ms = per_launch.get("k13_tile_fused", 0.0)
+    # FP64 pipe of K1: the fused 3-D k = 1 Hodge tape is 386 add/sub + 159 mul + 6 div + 1 sqrt per cell visit, never
+    # contracted to FMA; the peak is the measured DADD/DMUL throughput (scripts/fp64_peak.cu -> profiles/r02_fp64_peak.json)
+    fp64 = None
+    fp = os.path.join(ROOT, "profiles", "r02_fp64_peak.json")
+    if fused and fused_ms > 0 and os.path.exists(fp):
+        pk = json.load(open(fp))
+        flops = 552.0 * cell_visits
+        fp64 = {"k1_fp64_ops_per_launch": flops, "cell_visits": cell_visits, "achieved_tflops": flops / (fused_ms / 1e3) / 1e12,
+                "peak_nofma_tflops": pk["fp64_nofma_tflops"], "frac_of_nofma_peak": flops / (fused_ms / 1e3) / 1e12 / pk["fp64_nofma_tflops"],
+                "peak_fma_tflops": pk["fp64_fma_tflops"]}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -471,7 +482,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
                      "algorithmic_bytes_fused": asm_bytes, "algorithmic_bytes_per_block_sum": asm_bytes_per_block_sum,
-                     "peak_source": peak_src, "kernel_ms_per_launch": per_launch},
+                     "peak_source": peak_src, "kernel_ms_per_launch": per_launch, "fp64_pipe": fp64},
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in kern.items()},
         "first_pass": {"wall_ms": first_pass_wall_ms, "tile_plan_ms": plan_build_ms,
                        "device_ms": {k: round(v["ms"], 3) for k, v in first_report.items()},

@@ -75,6 +75,7 @@ SIGNATURES = [
     ("fq_csr_assembly_bytes", _i64, [_vp]),
     ("fq_csr_assembly_shared_bytes", _i64, [_vp]),
     ("fq_csr_plan_build_ms", C.c_double, [_vp]),
+    ("fq_csr_plan_cell_visits", _sz, [_vp]),
     ("fq_csr_spmv_bytes", _i64, [_vp]),
     ("fq_vec_create", _i, [_vp, _sz, _P(_vp)]),
     ("fq_vec_wrap", _i, [_vp, _vp, _sz, _P(_vp)]),

@@ -436,6 +436,10 @@ class DeviceCsr:
         return _lib.lib().fq_csr_plan_build_ms(self._h)
 
     @property
+    def plan_cell_visits(self) -> int:
+        return _lib.lib().fq_csr_plan_cell_visits(self._h)
+
+    @property
     def spmv_bytes(self) -> int:
         return _lib.lib().fq_csr_spmv_bytes(self._h)
 

@@ -432,6 +432,7 @@ static bool tile_numeric(fq_ctx* ctx, const fq_mesh* mesh, fq_csr* const* csrs, 
         csrs[b]->pattern_valid = false;
         csrs[b]->compact_valid = false;
         csrs[b]->plan_build_ms = plan ? tile_plan_build_ms(*plan) : 0.0;
+        csrs[b]->plan_cell_visits = plan ? tile_plan_cell_visits(*plan) : 0;
       }
       if (!plan) {
         csrs[0]->tile_refused = 1;  // does not apply to this block set / mesh: stay on the slab path

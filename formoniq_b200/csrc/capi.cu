@@ -690,6 +690,7 @@ int fq_csr_destroy(fq_csr* csr) {
 int64_t fq_csr_assembly_bytes(const fq_csr* csr) { return csr ? csr->assembly_bytes : 0; }
 int64_t fq_csr_assembly_shared_bytes(const fq_csr* csr) { return csr ? csr->assembly_shared_bytes : 0; }
 double fq_csr_plan_build_ms(const fq_csr* csr) { return csr ? csr->plan_build_ms : 0.0; }
+size_t fq_csr_plan_cell_visits(const fq_csr* csr) { return csr ? csr->plan_cell_visits : 0; }
 int64_t fq_csr_spmv_bytes(const fq_csr* csr) {
   if (!csr) return 0;
   const size_t nrows_local = csr->row_end - csr->row_begin;

@@ -227,4 +227,5 @@ struct fq_csr {
   // structural pattern itself, so a matrix that only ever goes through the fused kernel never pays for K2
   bool k2_done = false;
   double plan_build_ms = 0.0;  // device time of the last tile plan build (symbolic + plan), 0 when none
+  size_t plan_cell_visits = 0; // cell visits (cells x tiles touching them) of the tile plan: element tapes per fused launch
 };

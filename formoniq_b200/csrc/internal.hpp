@@ -40,6 +40,7 @@ void tile_retarget(fq_ctx* ctx, TilePlan& plan);
 bool& tile_plan_compact(TilePlan& plan);
 bool& tile_plan_drop(TilePlan& plan);
 double tile_plan_build_ms(const TilePlan& plan);
+size_t tile_plan_cell_visits(const TilePlan& plan);
 int64_t tile_plan_bytes(const TilePlan& plan);
 int64_t tile_plan_stream_bytes(const TilePlan& plan);
 int64_t tile_plan_cv_bytes(const TilePlan& plan);

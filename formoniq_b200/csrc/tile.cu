@@ -1518,6 +1518,7 @@ bool tile_plan_matches(const TilePlan& plan, const fq_mesh* mesh, fq_csr* const*
 bool& tile_plan_compact(TilePlan& plan) { return plan.compact; }
 bool& tile_plan_drop(TilePlan& plan) { return plan.drop; }
 double tile_plan_build_ms(const TilePlan& plan) { return plan.build_ms; }
+size_t tile_plan_cell_visits(const TilePlan& plan) { return plan.tile_cv_cells.n; }
 
 int64_t tile_plan_bytes(const TilePlan& plan) {
   return int64_t(plan.tiles.bytes() + plan.cv_rec.bytes() + plan.gbase.bytes() + plan.stream.bytes());

@@ -198,6 +198,8 @@ int64_t fq_csr_assembly_bytes(const fq_csr* csr);
 int64_t fq_csr_assembly_shared_bytes(const fq_csr* csr);
 /* device milliseconds the last tile-plan build of this matrix took (symbolic pattern + record streams; 0: none) */
 double fq_csr_plan_build_ms(const fq_csr* csr);
+/* cell visits of the tile plan (a cell is evaluated once per tile touching it): element tapes per fused launch */
+size_t fq_csr_plan_cell_visits(const fq_csr* csr);
 int64_t fq_csr_spmv_bytes(const fq_csr* csr);
 
 /* ---- vectors: iterative::InnerProductSpace (iterative/src/lib.rs:84-141) ---- */
