@@ -12,7 +12,7 @@
 //   * every owned non-zero is then one lane of a warp-sized record that adds its contributions — plain 16-bit slab
 //     indices — left to right in ascending cell order and stores the sum once.
 //
-// tile_fused_kernel: 8 producer warps evaluate the generated staged tapes (elmat_gen.cuh: stage A = geometry, then one
+// tile_fused_kernel: 16 producer warps (one cell visit per thread) evaluate the generated staged tapes (elmat_gen.cuh: stage A = geometry, then one
 // stage group per mass grade), 16 consumer warps stream the tile's records through private TMA double buffers
 // (cp.async.bulk + mbarrier).  Every stage group has its own region of the slab and a full/empty mbarrier pair, so
 // the producers refill the region of group g for tile i+1 as soon as every consumer warp is past the group-g records

@@ -59,7 +59,7 @@ unsafe extern "C" {
                               shapes: *const c_double, coefficient: *const c_double, drop_exact_zeros: c_int) -> c_int;
   fn fq_source_form_assemble(ctx: *mut fq_ctx, plan: *const fq_matfree, nnodes: c_int, weights: *const c_double,
                              shapes: *const c_double, samples: *const c_double, out: *mut fq_vec) -> c_int;
-  // HodgeBlocks (hodge.rs:62-99): symbolic once, numeric per geometry (one fused kernel from the second pass on)
+  // HodgeBlocks (hodge.rs:62-99): symbolic once, numeric per geometry (the first pass builds the tile plan, every later pass is one fused kernel)
   fn fq_mesh_set_lengths(ctx: *mut fq_ctx, mesh: *mut fq_mesh, edge_lengths_sq: *const c_double) -> c_int;
   fn fq_hodge_symbolic(ctx: *mut fq_ctx, mesh: *const fq_mesh, grade: c_int, sigma_row_begin: usize, sigma_row_end: usize,
                        u_row_begin: usize, u_row_end: usize, out: *mut *mut fq_hodge) -> c_int;
@@ -70,6 +70,13 @@ unsafe extern "C" {
   // RelativeWhitneyComplex::assemble (whitney_complex.rs:620-624)
   fn fq_csr_restrict(ctx: *mut fq_ctx, a: *const fq_csr, rows_keep: *const usize, nrows_keep: usize,
                      cols_keep: *const usize, ncols_keep: usize, out: *mut *mut fq_csr) -> c_int;
+  // hdif_gram (whitney_complex.rs:118-125), symmetrised KKT and the AFW block preconditioner (problems/elliptic.rs:29-47,101-113)
+  fn fq_csr_add(ctx: *mut fq_ctx, a: *const fq_csr, b: *const fq_csr, out: *mut *mut fq_csr) -> c_int;
+  fn fq_hodge_mixed_kkt_symmetric(ctx: *mut fq_ctx, blocks: *const fq_hodge, out: *mut *mut fq_csr) -> c_int;
+  fn fq_minres_blockdiag(ctx: *mut fq_ctx, a: *const fq_csr, nblocks: c_int, blocks: *const *const fq_csr,
+                         offsets: *const usize, inner_rtol: c_double, inner_max_iters: usize, b: *const fq_vec,
+                         rtol: c_double, max_iters: usize, x: *mut fq_vec, iters: *mut usize, residual: *mut c_double,
+                         converged: *mut c_int, inner_iters: *mut usize) -> c_int;
 }
 
 /// The reference panics on contract violations (`galerkin.rs:184` unwraps);
@@ -256,7 +263,38 @@ impl<'d> GpuHodgeBlocks<'d> {
     DeviceCsr { dev: self.dev, raw, n: self.block(0).nrows() + self.block(1).nrows() }
   }
 }
+impl<'d> GpuHodgeBlocks<'d> {
+  /// The symmetric saddle point `assemble_mixed_kkt` hands to MINRES (problems/elliptic.rs:101-113): sigma rows negated.
+  pub fn mixed_kkt_symmetric(&self) -> DeviceCsr<'d> {
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_hodge_mixed_kkt_symmetric(self.dev.0, self.raw, &mut raw) });
+    DeviceCsr { dev: self.dev, raw, n: self.block(0).nrows() + self.block(1).nrows() }
+  }
+}
 impl Drop for GpuHodgeBlocks<'_> { fn drop(&mut self) { unsafe { fq_hodge_destroy(self.raw) }; } }
+
+impl<'d> DeviceCsr<'d> {
+  /// `hdif_gram(k) = mass(k) + dif_both(k + 1)` (whitney_complex.rs:118-125) as a device CSR add on the union pattern.
+  pub fn add(&self, other: &DeviceCsr<'d>) -> DeviceCsr<'d> {
+    let mut raw = ptr::null_mut();
+    check(unsafe { fq_csr_add(self.dev.0, self.raw, other.raw, &mut raw) });
+    DeviceCsr { dev: self.dev, raw, n: self.n }
+  }
+}
+
+/// MINRES on the symmetrised KKT operator with the AFW block-diagonal preconditioner (problems/elliptic.rs:29-47): the two
+/// `hdif_gram` blocks are solved by inner Jacobi-CG on the device where the reference applies a sparse Cholesky factor.
+/// Returns (solution, outer iterations, relative residual, converged).
+pub fn minres_afw<'d>(kkt: &DeviceCsr<'d>, hdif_gram_sigma: &DeviceCsr<'d>, hdif_gram_u: &DeviceCsr<'d>, rhs: &DeviceVector<'d>,
+                      rtol: f64, max_iters: usize, inner_rtol: f64, inner_max_iters: usize) -> (DeviceVector<'d>, usize, f64, bool) {
+  let x = DeviceVector::zeros(kkt.dev, kkt.n);
+  let blocks = [hdif_gram_sigma.raw as *const fq_csr, hdif_gram_u.raw as *const fq_csr];
+  let offsets = [0usize, hdif_gram_sigma.n, kkt.n];
+  let (mut iters, mut residual, mut converged, mut inner) = (0usize, 0f64, 0 as c_int, 0usize);
+  check(unsafe { fq_minres_blockdiag(kkt.dev.0, kkt.raw, 2, blocks.as_ptr(), offsets.as_ptr(), inner_rtol, inner_max_iters,
+                                     rhs.raw, rtol, max_iters, x.raw, &mut iters, &mut residual, &mut converged, &mut inner) });
+  (x, iters, residual, converged != 0)
+}
 
 // ---- WeightedHodgeMass (formoniq/src/operators.rs:432-486) -------------------------------------------------------------
 /// Drop-in for `WeightedHodgeMass::new(coefficient, grade, qr).assemble(topology, geometry)`: the rule and the shape
