@@ -181,6 +181,8 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads that widen the downloaded u32 index arrays to usize (e2e leg): the ranks of a node share its cores
+    os.environ.setdefault("FQ_HOST_WIDEN_THREADS", str(max(2, min(16, (os.cpu_count() or 8) // max(world, 1) - 1))))
     # stdout carries exactly ONE JSON line: anything a library prints (e.g. NCCL's
     # version banner) goes to stderr until the result is ready.
     sys.stdout.flush()
@@ -540,28 +542,34 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
     len_t = pinned(lengths)
     h2d = sum(f.nbytes for f in faces if f is not None) + len_t.numpy().nbytes
     cells = ns[DIM]
-    d2h = 0
+    d2h = pcie = 0
+    widen_threads = int(os.environ.get("FQ_HOST_WIDEN_THREADS", "0"))
     times = []
     # the caller's result buffers (the Vec<usize>/Vec<f64> of the four CsrMatrix): pinned, sized by the warm-up pass.
     # Each block's download is enqueued on the library's copy stream and overlaps the assembly of the next block;
     # the step ends when all four results are in host memory.
     outs = None
-    sizes = []
+    sizes = [None] * len(forms)
+    # blocks in HodgeBlocks order (issuing the two large ones first was measured: 262 instead of 234 ms, the widening
+    # threads of the big blocks then compete with the host side of the remaining assemblies)
+    order = list(range(len(forms)))
     for it in range(args.e2e_steps + 2):  # pass 0 sizes the result buffers, pass 1 warms the allocations up
         barrier()
         t0 = time.perf_counter()
         m = fq.Mesh.from_arrays(ctx, DIM, ns, faces, len_t.numpy())
-        d2h = 0
+        d2h = pcie = 0
         live = []
-        for i, (_, form) in enumerate(forms):
+        for i in order:
+            form = forms[i][1]
             a = form.assemble(m, True)
             if outs is None:
                 rp, ci, va = a.download()
-                sizes.append((rp.shape[0], ci.shape[0]))
+                sizes[i] = (rp.shape[0], ci.shape[0])
             else:
                 rp, ci, va = a.download_async(outs[i])
                 live.append(a)  # must outlive the copies
             d2h += rp.nbytes + ci.nbytes + va.nbytes
+            pcie += (rp.nbytes + ci.nbytes) // (2 if widen_threads > 0 else 1) + va.nbytes
             del a, rp, ci, va
         ctx.wait_downloads()
         torch.cuda.synchronize()
@@ -577,8 +585,9 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
         print("e2e step times (ms):", [round(1e3 * x, 1) for x in times], file=sys.stderr)
     t = allmax(sum(times) / len(times))
     return {"value": allsum(cells) / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": t * 1e3, "workload": f"per rank: fq_mesh_create + 4x fq_assemble + fq_csr_download on a Kuhn cube "
-                                                f"N={n_e2e} ({cells} tets), pinned host arrays in and out, downloads overlapped with the next block"}
+            "ms_per_step": t * 1e3, "d2h_pcie_bytes_per_step": int(pcie),
+            "workload": f"per rank: fq_mesh_create + 4x fq_assemble + fq_csr_download on a Kuhn cube "
+                                                f"N={n_e2e} ({cells} tets), pinned host arrays in and out, downloads overlapped with the next block, indices cross PCIe as u32 and are widened to usize by {os.environ.get('FQ_HOST_WIDEN_THREADS')} host threads"}
 
 
 def main():

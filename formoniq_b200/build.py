@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 
 SOURCES = ["elmat.cu", "kuhn.cu", "assemble.cu", "tile.cu", "blockop.cu", "matfree.cu", "quadform.cu", "spmv.cu", "blas1.cu", "krylov.cu", "capi.cu"]
-HEADERS = ["common.cuh", "internal.hpp", "stream.cuh", "tape.hpp", "tile_plan.hpp", "kuhn.hpp", "geometry.cuh", "gen_elmat.cpp",
+HEADERS = ["common.cuh", "internal.hpp", "stream.cuh", "host_widen.hpp", "tape.hpp", "tile_plan.hpp", "kuhn.hpp", "geometry.cuh", "gen_elmat.cpp",
            "../../include/formoniq_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -193,6 +193,10 @@ int fq_ctx_destroy(fq_ctx* ctx) {
       cudaStreamSynchronize(ctx->copy_stream);
       cudaStreamDestroy(ctx->copy_stream);
     }
+    if (ctx->widener) {
+      ctx->widener->wait_idle();
+      delete ctx->widener;
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
     delete ctx;
@@ -627,9 +631,32 @@ int fq_csr_download(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t*
   }
   FQ_API_END
 }
-// device u32 -> host u64 on the copy stream; the whole array is widened into one staging buffer kept until the wait
+// device u32 -> host u64 on the copy stream.  With host widening the u32 array is copied into the upper half of the
+// caller's buffer and a host callback hands it to the widening pool (half the PCIe bytes, no device staging);
+// otherwise the whole array is widened on the device into one staging buffer kept until the wait.
+struct WidenTicket {
+  fq::HostWidener* pool;
+  uint64_t* buf;
+  size_t n;
+};
+static void CUDART_CB widen_callback(void* p) {
+  WidenTicket* t = static_cast<WidenTicket*>(p);
+  t->pool->enqueue(t->buf, t->n);
+  delete t;
+}
 static void download_widen_async(fq_ctx* ctx, const uint32_t* dev, size_t n, uint64_t* host) {
   if (!n) return;
+  if (!ctx->widener_probed) {
+    ctx->widener_probed = true;
+    const int threads = fq::host_widen_threads();
+    if (threads > 0) ctx->widener = new fq::HostWidener(threads);
+  }
+  if (ctx->widener) {
+    FQ_CUDA(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(host) + n, dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            ctx->copy_stream));
+    FQ_CUDA(cudaLaunchHostFunc(ctx->copy_stream, widen_callback, new WidenTicket{ctx->widener, host, n}));
+    return;
+  }
   ctx->pending_staging.emplace_back(n);
   uint64_t* stage = ctx->pending_staging.back().p;
   widen_u32_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->copy_stream>>>(dev, n, stage);
@@ -657,6 +684,7 @@ int fq_ctx_wait_downloads(fq_ctx* ctx) {
   FQ_API_BEGIN
   FQ_REQUIRE(ctx, "null argument");
   if (ctx->copy_stream) FQ_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->widener) ctx->widener->wait_idle();
   ctx->pending_staging.clear();
   FQ_API_END
 }

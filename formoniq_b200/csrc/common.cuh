@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/formoniq_b200.h"
+#include "host_widen.hpp"
 #include "tape.hpp"
 
 namespace fq {
@@ -106,6 +107,10 @@ struct fq_ctx {
   // overlap the assembly of the next; the widened staging pieces live until fq_ctx_wait_downloads
   cudaStream_t copy_stream = nullptr;
   std::vector<fq::DevBuf<uint64_t>> pending_staging;
+  // index arrays cross PCIe as u32 and are widened to usize in place on host threads (host_widen.hpp); created on the
+  // first asynchronous download, absent when host widening is off (then the device widens and u64 crosses the bus)
+  fq::HostWidener* widener = nullptr;
+  bool widener_probed = false;
   // optional per-kernel timing (CUDA events on the launching stream)
   bool timing = false;
   std::vector<std::string> span_names;

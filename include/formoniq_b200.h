@@ -186,7 +186,9 @@ int fq_csr_upload(fq_ctx* ctx, size_t nrows, size_t ncols, const size_t* row_off
                   const double* values, fq_csr** out);
 /* The same download enqueued on the context's copy stream after everything submitted so far: it overlaps whatever the
  * caller enqueues next (e.g. the assembly of the next block).  The host buffers (pinned for PCIe-rate copies) and the
- * matrix must stay alive until fq_ctx_wait_downloads returns. */
+ * matrix must stay alive until fq_ctx_wait_downloads returns.  The index arrays cross PCIe as the device's u32 and are
+ * widened to usize IN the caller's buffers by a pool of host threads (FQ_HOST_WIDEN_THREADS, default min(16, cores - 1);
+ * 0 = widen on the device and move u64): the contents of row_offsets / col_indices are undefined until the wait. */
 int fq_csr_download_async(fq_ctx* ctx, const fq_csr* csr, size_t* row_offsets, size_t* col_indices, double* values);
 int fq_ctx_wait_downloads(fq_ctx* ctx);
 int fq_csr_destroy(fq_csr* csr);

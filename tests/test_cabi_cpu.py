@@ -64,6 +64,16 @@ def test_tile_plan_host_builder_and_staged_sets_reproduce_the_oracle(tmp_path):
     assert ncases >= 100 and nnz > 100000
 
 
+def test_host_widening_of_downloaded_indices(tmp_path):
+    # u32 -> usize in place on host threads (csrc/host_widen.hpp): what fq_csr_download_async does to the index arrays
+    exe = tmp_path / "host_widen_check"
+    subprocess.check_call(["/usr/bin/g++", "-O3", "-std=c++17", "-pthread",
+                           os.path.join(ROOT, "tests", "cpp", "host_widen_check.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.startswith("OK "), out.stdout
+
+
 def test_kuhn_closed_form_numbering_matches_reference_construction(fq):
     from oracle import oracle as O
 

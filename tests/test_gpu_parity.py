@@ -762,6 +762,28 @@ def test_async_download_matches_the_blocking_one(fq, ctx):
         mats[0].download_async((np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1)))
 
 
+def test_async_download_of_large_index_arrays(fq, ctx):
+    # index arrays long enough for the parallel waves of the host-side u32 -> usize widening (csrc/host_widen.hpp);
+    # pageable and pinned destination buffers
+    import torch
+
+    mesh = fq.Mesh.kuhn(ctx, 3, [24, 24, 20], jitter=0.2)
+    for kind, g in ((O.MASS, 1), (O.DIF_TEST, 1)):
+        a = fq.WhitneyPairing(3, g, kind).assemble(mesh)
+        b, e = a.row_range
+        assert a.nnz > 500000
+        pinned = (torch.empty(e - b + 1, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64),
+                  torch.empty(a.nnz, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64),
+                  torch.empty(a.nnz, dtype=torch.float64, pin_memory=True).numpy())
+        pageable = (np.empty(e - b + 1, dtype=np.uint64), np.empty(a.nnz, dtype=np.uint64), np.empty(a.nnz))
+        got_pinned = a.download_async(pinned)
+        got_pageable = a.download_async(pageable)
+        ctx.wait_downloads()
+        erp, eci, eva = a.download()
+        for rp, ci, va in (got_pinned, got_pageable):
+            assert np.array_equal(rp, erp) and np.array_equal(ci, eci) and np.array_equal(va, eva)
+
+
 @pytest.mark.parametrize("dim,shape,variant", [(2, [6, 5], "jitter"), (3, [4, 3, 4], "jitter"), (3, [3, 3, 3], "minkowski")])
 def test_matrix_free_element_operator_equals_the_assembled_matrix(fq, ctx, dim, shape, variant):
     # matfree.rs:217-248 (apply == assembled * x) and :265-278 (diagonal == assembled diagonal), every pairing
