@@ -182,7 +182,9 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # host threads that widen the downloaded u32 index arrays to usize (e2e leg): the ranks of a node share its cores
-    os.environ.setdefault("FQ_HOST_WIDEN_THREADS", str(max(2, min(16, (os.cpu_count() or 8) // max(world, 1) - 1))))
+    # (with fewer than 6 threads per rank the device-side widening is the faster one: 8 ranks on a 32-core host)
+    widen = min(16, (os.cpu_count() or 8) // max(world, 1) - 1)
+    os.environ.setdefault("FQ_HOST_WIDEN_THREADS", str(widen if widen >= 6 else 0))
     # stdout carries exactly ONE JSON line: anything a library prints (e.g. NCCL's
     # version banner) goes to stderr until the result is ready.
     sys.stdout.flush()
@@ -587,7 +589,7 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
     return {"value": allsum(cells) / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": t * 1e3, "d2h_pcie_bytes_per_step": int(pcie),
             "workload": f"per rank: fq_mesh_create + 4x fq_assemble + fq_csr_download on a Kuhn cube "
-                                                f"N={n_e2e} ({cells} tets), pinned host arrays in and out, downloads overlapped with the next block, indices cross PCIe as u32 and are widened to usize by {os.environ.get('FQ_HOST_WIDEN_THREADS')} host threads"}
+                                                f"N={n_e2e} ({cells} tets), pinned host arrays in and out, downloads overlapped with the next block, index arrays widened to usize by {os.environ.get('FQ_HOST_WIDEN_THREADS')} host threads (0 = on the device)"}
 
 
 def main():

@@ -150,7 +150,7 @@ class HostWidener {
 inline int host_widen_threads() {
   if (const char* e = std::getenv("FQ_HOST_WIDEN_THREADS")) return std::atoi(e);
   const unsigned hw = std::thread::hardware_concurrency();
-  if (hw < 4) return 0;
+  if (hw < 8) return 0;
   return int(hw - 1 < 16 ? hw - 1 : 16);
 }
 
