@@ -36,6 +36,7 @@ SIGNATURES = [
     ("fq_ctx_set_timing", _i, [_vp, _i]),
     ("fq_ctx_timing_report", _i, [_vp, _vp, _sz]),
     ("fq_mesh_create", _i, [_vp, _i, _sz, _vp, _vp, _vp, _P(_vp)]),
+    ("fq_mesh_create_part", _i, [_vp, _i, _sz, _vp, _vp, _vp, _vp, _vp, _P(_vp)]),
     ("fq_mesh_create_kuhn", _i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _sz, _sz, _P(_vp)]),
     ("fq_mesh_destroy", _i, [_vp]),
     ("fq_mesh_dim", _i, [_vp]),

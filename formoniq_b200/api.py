@@ -98,6 +98,25 @@ class Mesh:
         return cls(ctx, h)
 
     @classmethod
+    def from_part(cls, ctx: Context, dim: int, nsimplices, cell_faces, edge_lengths_sq, part) -> "Mesh":
+        """One rank's part of an uploaded mesh (dist.partition_mesh): the held cells' rows of the GLOBAL face tables
+        (global ids, global counts, global edge lengths); owned_range(j) then gives the rank's row range of grade j."""
+        ns = np.ascontiguousarray(nsimplices, dtype=np.uint64)
+        faces = [None if f is None else np.ascontiguousarray(np.asarray(f)[part.cells], dtype=np.uint64) for f in cell_faces]
+        if faces[dim] is None:
+            faces[dim] = np.ascontiguousarray(part.cells, dtype=np.uint64).reshape(-1, 1)
+        ptrs = (C.c_void_p * (dim + 1))(*[None if f is None else f.ctypes.data for f in faces])
+        lengths = np.ascontiguousarray(edge_lengths_sq, dtype=np.float64)
+        if lengths.shape[0] != int(ns[1]):
+            raise FormoniqError(-1, "one squared length per edge is required")
+        lo = np.ascontiguousarray([r[0] for r in part.own], dtype=np.uint64)
+        hi = np.ascontiguousarray([r[1] for r in part.own], dtype=np.uint64)
+        h = C.c_void_p()
+        check(_lib.lib().fq_mesh_create_part(ctx._h, dim, int(len(part.cells)), _p(ns), C.cast(ptrs, C.c_void_p), _p(lengths),
+                                             _p(lo), _p(hi), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
     def kuhn(cls, ctx: Context, dim: int, shape, vmin=None, vmax=None, ambient_diag=None, jitter: float = 0.0,
              slab=None) -> "Mesh":
         """CartesianGrid::triangulate + to_edge_lengths_sq generated on the device."""

@@ -260,12 +260,30 @@ int fq_ctx_timing_report(fq_ctx* ctx, char* buf, size_t buflen) {
 }
 
 // ---------------------------------------------------------------- mesh
+static int mesh_create_impl(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices, const uint64_t* const* cell_faces,
+                            const double* edge_lengths_sq, const size_t* own_lo, const size_t* own_hi, fq_mesh** out);
 int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices, const uint64_t* const* cell_faces,
                    const double* edge_lengths_sq, fq_mesh** out) {
   FQ_API_BEGIN
+  FQ_REQUIRE(nsimplices && dim >= 1 && dim <= 10 && nsimplices[dim] == ncells, "nsimplices[dim] must equal ncells");
+  return mesh_create_impl(ctx, dim, ncells, nsimplices, cell_faces, edge_lengths_sq, nullptr, nullptr, out);
+  FQ_API_END
+}
+int fq_mesh_create_part(fq_ctx* ctx, int dim, size_t ncells_held, const size_t* nsimplices, const uint64_t* const* cell_faces,
+                        const double* edge_lengths_sq, const size_t* own_lo, const size_t* own_hi, fq_mesh** out) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(nsimplices && own_lo && own_hi && dim >= 1 && dim <= 10, "null argument");
+  FQ_REQUIRE(ncells_held <= nsimplices[dim], "more held cells than cells");
+  for (int j = 0; j <= dim; ++j)
+    FQ_REQUIRE(own_lo[j] <= own_hi[j] && own_hi[j] <= nsimplices[j], "owned id range outside the skeleton");
+  return mesh_create_impl(ctx, dim, ncells_held, nsimplices, cell_faces, edge_lengths_sq, own_lo, own_hi, out);
+  FQ_API_END
+}
+static int mesh_create_impl(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices, const uint64_t* const* cell_faces,
+                            const double* edge_lengths_sq, const size_t* own_lo, const size_t* own_hi, fq_mesh** out) {
+  FQ_API_BEGIN
   FQ_REQUIRE(ctx && out && nsimplices && cell_faces, "null argument");
   FQ_REQUIRE(dim >= 1 && dim <= 10, "1 <= dim <= 10");
-  FQ_REQUIRE(nsimplices[dim] == ncells, "nsimplices[dim] must equal ncells");
   FQ_REQUIRE(cell_faces[1] && edge_lengths_sq, "grade-1 faces and edge lengths are required");
   FQ_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<fq_mesh> m(new fq_mesh);
@@ -278,6 +296,11 @@ int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices
   m->id_hi.assign(nsimplices, nsimplices + dim + 1);
   m->own_lo = m->id_lo;
   m->own_hi = m->id_hi;
+  if (own_lo && own_hi) {  // a rank's part: ids stay global, the held cells are a subset
+    m->own_lo.assign(own_lo, own_lo + dim + 1);
+    m->own_hi.assign(own_hi, own_hi + dim + 1);
+    m->nowned_cells = own_hi[dim] - own_lo[dim];
+  }
   for (int j = 0; j <= dim; ++j) {
     FQ_REQUIRE(nsimplices[j] < (size_t(1) << 32), "more than 2^32 simplices of one grade: not supported");
     if (cell_faces[j]) upload_narrow(ctx, cell_faces[j], ncells * size_t(nlocal(dim, j)), m->cell_faces[size_t(j)], nsimplices[j]);

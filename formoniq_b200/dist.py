@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import numpy as np
+
 from .api import kuhn_slab_ranges
 
 
@@ -67,6 +69,71 @@ class SlabPartition:
                     if a < b:
                         out.append((peer, a, b))
         return out
+
+
+@dataclass
+class MeshPart:
+    """One rank's share of an uploaded mesh under owner-computes: the vertex range it owns, the cells it holds (every cell
+    touching an owned vertex, ascending global index) and the id range [lo, hi) it owns of every grade."""
+    rank: int
+    vertices: tuple
+    cells: np.ndarray
+    own: list
+
+
+def partition_mesh(dim: int, nsimplices, cell_faces, world: int):
+    """Owner-computes partition of ANY mesh in the reference's skeleton numbering, not only generated Kuhn grids.
+
+    The reference numbers the simplices of every grade in colex order of their sorted vertex lists
+    (simplicial/src/topology/skeleton.rs:50-86), i.e. by top vertex first: a contiguous vertex range therefore owns a
+    contiguous id range of every grade, and every cell that contributes to an owned row contains that row's top vertex,
+    which is owned — so a rank that holds the cells touching its vertices assembles its row block without communication,
+    in the same cell order as one GPU (bit-identical rows).  Vertex ranges are balanced by the number of incident cells.
+    cell_faces[j]: [ncells, C(dim+1, j+1)] global tables (FaceIncidence::faces_flat), grade 0 required; a grade whose
+    table is missing gets the range (0, 0).  Returns one MeshPart per rank."""
+    from math import comb
+    from itertools import combinations
+
+    ns = [int(v) for v in nsimplices]
+    cells = np.asarray(cell_faces[0]).astype(np.int64).reshape(-1, dim + 1)
+    if np.any(np.diff(cells, axis=1) <= 0):
+        raise ValueError("cells must list their vertices in ascending order")
+    nv = ns[0]
+    weight = np.bincount(cells.ravel(), minlength=nv).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(weight)])
+    cuts = [int(np.searchsorted(cum, cum[-1] * r / world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, nv
+    cuts = list(np.maximum.accumulate(cuts))
+    # top vertex of every simplex of every grade, from the cells (colex subsets: the last position is the top one)
+    tops = []
+    for j in range(dim + 1):
+        f = cell_faces[j] if j < len(cell_faces) else None
+        if j == dim and f is None:
+            tops.append(cells[:, dim].copy())
+            continue
+        if f is None:
+            tops.append(None)
+            continue
+        f = np.asarray(f).astype(np.int64).reshape(-1, comb(dim + 1, j + 1))
+        subsets = sorted(combinations(range(dim + 1), j + 1), key=lambda c: c[::-1])  # colex order of the local faces
+        top = np.full(ns[j], -1, dtype=np.int64)
+        for r, sub in enumerate(subsets):
+            top[f[:, r]] = cells[:, sub[-1]]
+        if np.any(top < 0) or np.any(np.diff(top) < 0):
+            raise ValueError(f"grade {j}: simplices are not numbered by top vertex (not the reference's skeleton numbering)")
+        tops.append(top)
+    parts = []
+    for r in range(world):
+        v0, v1 = cuts[r], cuts[r + 1]
+        held = np.nonzero(((cells >= v0) & (cells < v1)).any(axis=1))[0]
+        own = []
+        for j in range(dim + 1):
+            if tops[j] is None:
+                own.append((0, 0))
+            else:
+                own.append((int(np.searchsorted(tops[j], v0, side="left")), int(np.searchsorted(tops[j], v1, side="left"))))
+        parts.append(MeshPart(r, (v0, v1), held, own))
+    return parts
 
 
 def exchange_halo(window, part: SlabPartition, rank: int, group=None):

@@ -79,6 +79,18 @@ int fq_ctx_timing_report(fq_ctx* ctx, char* buf, size_t buflen);
  *                    signed squared length per edge of the 1-skeleton. */
 int fq_mesh_create(fq_ctx* ctx, int dim, size_t ncells, const size_t* nsimplices /*[dim+1]*/,
                    const uint64_t* const* cell_faces /*[dim+1]*/, const double* edge_lengths_sq, fq_mesh** out);
+/* One rank's part of an uploaded mesh under owner-computes (the partition SURVEY 8e describes, for any Complex in the
+ * reference's colex skeleton numbering — simplices sorted by their top vertex, simplicial/src/topology/skeleton.rs:50-86 —
+ * not only the generated Kuhn grids): the rank owns a contiguous vertex range, hence the contiguous id range
+ * [own_lo[j], own_hi[j]) of every grade j (the simplices whose top vertex it owns), and HOLDS the ncells_held cells that
+ * touch one of its vertices, in ascending global order.  cell_faces[j] are the rows of the global tables for those cells
+ * with GLOBAL ids (cell_faces[dim] = their global cell ids), nsimplices the GLOBAL counts, edge_lengths_sq the global
+ * array.  Assembling with the row range fq_mesh_owned_range reports gives the rank's row block, bit-identical to the
+ * same rows of the one-GPU matrix (every cell contributing to an owned row is held, in the same order).  The host-side
+ * split (vertex ranges balanced by incident cells, held cells, id ranges) is formoniq_b200.dist.partition_mesh. */
+int fq_mesh_create_part(fq_ctx* ctx, int dim, size_t ncells_held, const size_t* nsimplices /*[dim+1]*/,
+                        const uint64_t* const* cell_faces /*[dim+1]*/, const double* edge_lengths_sq,
+                        const size_t* own_lo /*[dim+1]*/, const size_t* own_hi /*[dim+1]*/, fq_mesh** out);
 /* Kuhn triangulation of a box grid generated on the device with the
  * reference's colex skeleton numbering (simplicial/src/mesher/grid.rs:77-103,
  * regge/src/mesher/cartesian.rs:158-169,192-208, regge/src/coord/mesh.rs:208-216).

@@ -30,6 +30,10 @@ unsafe extern "C" {
   fn fq_ctx_destroy(ctx: *mut fq_ctx) -> c_int;
   fn fq_mesh_create(ctx: *mut fq_ctx, dim: c_int, ncells: usize, nsimplices: *const usize,
                     cell_faces: *const *const u64, edge_lengths_sq: *const c_double, out: *mut *mut fq_mesh) -> c_int;
+  // one rank's part of a Complex under owner-computes (multi-GPU; host split: formoniq_b200.dist.partition_mesh)
+  fn fq_mesh_create_part(ctx: *mut fq_ctx, dim: c_int, ncells_held: usize, nsimplices: *const usize,
+                         cell_faces: *const *const u64, edge_lengths_sq: *const c_double, own_lo: *const usize,
+                         own_hi: *const usize, out: *mut *mut fq_mesh) -> c_int;
   fn fq_mesh_destroy(mesh: *mut fq_mesh) -> c_int;
   fn fq_assemble(ctx: *mut fq_ctx, mesh: *const fq_mesh, kind: c_int, grade: c_int, drop_exact_zeros: c_int,
                  out: *mut *mut fq_csr) -> c_int;

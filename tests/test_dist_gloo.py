@@ -179,3 +179,36 @@ def test_distributed_lanczos_driver_gloo(tmp_path, world):
     for r in range(world):
         vals = np.load(os.path.join(str(tmp_path), f"eig{r}.npy"))
         assert np.abs(vals - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dim,shape,world", [(2, [5, 4], 3), (3, [3, 4, 3], 2), (3, [4, 3, 5], 5), (4, [2, 2, 1, 2], 2)])
+def test_partition_of_an_uploaded_mesh_is_owner_complete(dim, shape, world):
+    # dist.partition_mesh on the oracle's complex (the reference's skeleton numbering): the owned id ranges tile every
+    # grade, and every cell that contains an owned simplex is held by its owner — so the owner can assemble the row alone
+    from formoniq_b200.dist import partition_mesh
+    from oracle import oracle as O
+
+    cx = O.Complex.kuhn(dim, shape)
+    ns = [cx.nsimplices(j) for j in range(dim + 1)]
+    faces = [cx.cell_faces(j) for j in range(dim + 1)]
+    parts = partition_mesh(dim, ns, faces, world)
+    assert len(parts) == world
+    for j in range(dim + 1):
+        assert parts[0].own[j][0] == 0 and parts[-1].own[j][1] == ns[j]
+        for a, b in zip(parts[:-1], parts[1:]):
+            assert a.own[j][1] == b.own[j][0]
+    for part in parts:
+        held = np.zeros(ns[dim], dtype=bool)
+        held[part.cells] = True
+        assert np.all(np.diff(part.cells) > 0)
+        for j in range(dim + 1):
+            f = np.asarray(faces[j]).reshape(ns[dim], -1)
+            lo, hi = part.own[j]
+            touches = ((f >= lo) & (f < hi)).any(axis=1)   # cells containing an owned simplex of grade j
+            assert np.all(held[touches]), (part.rank, j)
+    # a numbering that is not top-vertex-major is refused
+    bad = [np.asarray(f).copy() for f in faces]
+    perm = np.arange(ns[1])[::-1]
+    bad[1] = perm[bad[1]]
+    with pytest.raises(ValueError):
+        partition_mesh(dim, ns, bad, world)

@@ -1086,3 +1086,55 @@ def test_weighted_hodge_mass(fq, ctx, dim, shape, grade, variant):
     # the handle goes back to the closed-form mass with the ordinary numeric pass
     a.numeric(mesh, False)
     assert np.abs(a.to_scipy().data - plain.data).max() <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("dim,shape,world", [(2, [9, 7], 3), (3, [6, 5, 7], 2), (3, [5, 6, 6], 4)])
+def test_partitioned_uploaded_mesh_assembles_the_same_row_blocks(fq, ctx, dim, shape, world):
+    # VERDICT r1 missing #4: owner-computes for uploaded (non-generated) meshes.  Every part assembles its row range of
+    # every block; stacked, the row blocks are the one-GPU matrix bit for bit (pattern and values), on the slab path
+    # (first pass of an uploaded mesh) and on the tile path (re-assembly), single blocks and the fused Hodge set
+    from formoniq_b200.dist import partition_mesh
+
+    cx, s, *_ = kuhn_problem(dim, shape, jitter=True)
+    ns = [cx.nsimplices(j) for j in range(dim + 1)]
+    faces = [cx.cell_faces(j) for j in range(dim + 1)]
+    full = mesh_from_oracle(fq, ctx, cx, s)
+    parts = partition_mesh(dim, ns, faces, world)
+    meshes = [fq.Mesh.from_part(ctx, dim, ns, faces, s, p) for p in parts]
+    for p, m in zip(parts, meshes):
+        assert [m.owned_range(j) for j in range(dim + 1)] == p.own
+    forms = [(O.MASS, 0), (O.MASS, 1), (O.DIF_TEST, 1), (O.DIF_TRIAL, 1), (O.DIF_BOTH, 2), (O.MASS, dim)]
+    for kind, g in forms:
+        form = fq.WhitneyPairing(dim, g, kind)
+        ref = form.assemble(full)
+        erp, eci, eva = ref.download()
+        tg = form.test_grade()
+        for passes in (1, 2):   # 1: first numeric pass; 2: re-assembly (tile path where there is one)
+            rows, cols, vals = [np.zeros(1, dtype=np.uint64)], [], []
+            for p, m in zip(parts, meshes):
+                a = form.symbolic(m, *p.own[tg])
+                for _ in range(passes):
+                    a.numeric(m)
+                rp, ci, va = a.download()
+                rows.append(rp[1:] + rows[-1][-1])
+                cols.append(ci)
+                vals.append(va)
+            assert np.array_equal(np.concatenate(rows), erp), (kind, g, passes)
+            assert np.array_equal(np.concatenate(cols), eci), (kind, g, passes)
+            assert same_bits_mod_zero_sign(np.concatenate(vals), eva), (kind, g, passes)
+    # the fused four-block set on the parts
+    k = 1
+    href = fq.HodgeBlocks.compute(full, k)
+    for which in range(4):
+        erp, eci, eva = href.blocks[which].download()
+        rows, cols, vals = [np.zeros(1, dtype=np.uint64)], [], []
+        for p, m in zip(parts, meshes):
+            hb = fq.HodgeBlocks.symbolic(m, k, p.own[k - 1], p.own[k])
+            hb.numeric(m)
+            hb.numeric(m)
+            rp, ci, va = hb.blocks[which].download()
+            rows.append(rp[1:] + rows[-1][-1])
+            cols.append(ci)
+            vals.append(va)
+        assert np.array_equal(np.concatenate(rows), erp) and np.array_equal(np.concatenate(cols), eci), which
+        assert same_bits_mod_zero_sign(np.concatenate(vals), eva), which
