@@ -94,35 +94,62 @@ fn check(rc: c_int) {
 
 /// One CUDA device. `Sync` because every entry point serialises on the
 /// context's stream (seam 1 needs `BilinearForm: Sync`).
-pub struct Device(*mut fq_ctx);
+pub struct Device {
+  ctx: *mut fq_ctx,
+  /// The last uploaded mesh, keyed by the addresses and sizes of the `Complex` and `MeshLengthsSq` it came from:
+  /// `HodgeBlocks::compute` calls `form.assemble(topology, geometry)` four times on the same pair, and materialising
+  /// `FaceIncidence` for every grade costs about twice an assembly (galerkin.rs:136-137), so seam 1 must not redo it.
+  mesh_cache: std::sync::Mutex<Option<(MeshKey, *mut fq_mesh)>>,
+}
+#[derive(PartialEq, Eq, Clone, Copy)]
+struct MeshKey { topology: usize, geometry: usize, ncells: usize, nedges: usize }
 unsafe impl Send for Device {}
 unsafe impl Sync for Device {}
 impl Device {
   pub fn new(index: i32) -> Self {
     let mut ctx = ptr::null_mut();
     check(unsafe { fq_ctx_create(index, &mut ctx) });
-    Self(ctx)
+    Self { ctx, mesh_cache: std::sync::Mutex::new(None) }
+  }
+  /// The device mesh of (topology, geometry): uploaded on first use, reused while the same pair is passed again.
+  /// (A caller that mutates the lengths in place keeps the handle and calls `fq_mesh_set_lengths` instead.)
+  fn cached_mesh(&self, topology: &Complex, geometry: &MeshLengthsSq) -> *mut fq_mesh {
+    let key = MeshKey { topology: topology as *const _ as usize, geometry: geometry as *const _ as usize,
+                        ncells: topology.cells().len(), nedges: geometry.vector().len() };
+    let mut slot = self.mesh_cache.lock().unwrap();
+    if let Some((k, raw)) = *slot { if k == key { return raw; } unsafe { fq_mesh_destroy(raw) }; }
+    let raw = upload_mesh(self, topology, geometry);
+    *slot = Some((key, raw));
+    raw
   }
 }
-impl Drop for Device { fn drop(&mut self) { unsafe { fq_ctx_destroy(self.0) }; } }
+impl Drop for Device {
+  fn drop(&mut self) {
+    if let Some((_, raw)) = self.mesh_cache.lock().unwrap().take() { unsafe { fq_mesh_destroy(raw) }; }
+    unsafe { fq_ctx_destroy(self.ctx) };
+  }
+}
+fn upload_mesh(dev: &Device, topology: &Complex, geometry: &MeshLengthsSq) -> *mut fq_mesh {
+  let dim = topology.dim().index();
+  let nsimplices: Vec<usize> = (0..=dim).map(|j| topology.nsimplices(j)).collect();
+  let tables: Vec<Vec<u64>> = (0..=dim)
+    .map(|j| FaceIncidence::new(topology, j).faces_flat().iter().map(|&i| i as u64).collect())
+    .collect();
+  let ptrs: Vec<*const u64> = tables.iter().map(|t| t.as_ptr()).collect();
+  let mut raw = ptr::null_mut();
+  check(unsafe {
+    fq_mesh_create(dev.ctx, dim as c_int, topology.cells().len(), nsimplices.as_ptr(), ptrs.as_ptr(),
+                   geometry.vector().as_ptr(), &mut raw)
+  });
+  raw
+}
 
 /// `Complex` + `MeshLengthsSq` uploaded once: the FaceIncidence tables of every
 /// grade (incidence.rs:42-53) and the edge lengths (lengths/mesh.rs:34-36).
 pub struct DeviceMesh<'d> { dev: &'d Device, raw: *mut fq_mesh, dim: usize }
 impl<'d> DeviceMesh<'d> {
   pub fn new(dev: &'d Device, topology: &Complex, geometry: &MeshLengthsSq) -> Self {
-    let dim = topology.dim().index();
-    let nsimplices: Vec<usize> = (0..=dim).map(|j| topology.nsimplices(j)).collect();
-    let tables: Vec<Vec<u64>> = (0..=dim)
-      .map(|j| FaceIncidence::new(topology, j).faces_flat().iter().map(|&i| i as u64).collect())
-      .collect();
-    let ptrs: Vec<*const u64> = tables.iter().map(|t| t.as_ptr()).collect();
-    let mut raw = ptr::null_mut();
-    check(unsafe {
-      fq_mesh_create(dev.0, dim as c_int, topology.cells().len(), nsimplices.as_ptr(), ptrs.as_ptr(),
-                     geometry.vector().as_ptr(), &mut raw)
-    });
-    Self { dev, raw, dim }
+    Self { dev, raw: upload_mesh(dev, topology, geometry), dim: topology.dim().index() }
   }
 }
 impl Drop for DeviceMesh<'_> { fn drop(&mut self) { unsafe { fq_mesh_destroy(self.raw) }; } }
@@ -137,7 +164,7 @@ fn download_borrowed(dev: &Device, csr: *mut fq_csr) -> GalerkinMatrix {
   let (mut nr, mut nc, mut nnz) = (0usize, 0usize, 0usize);
   check(unsafe { fq_csr_shape(csr, &mut nr, &mut nc, &mut nnz) });
   let (mut rp, mut ci, mut va) = (vec![0usize; nr + 1], vec![0usize; nnz], vec![0f64; nnz]);
-  check(unsafe { fq_csr_download(dev.0, csr, rp.as_mut_ptr(), ci.as_mut_ptr(), va.as_mut_ptr()) });
+  check(unsafe { fq_csr_download(dev.ctx, csr, rp.as_mut_ptr(), ci.as_mut_ptr(), va.as_mut_ptr()) });
   // the data contract handed to faer by linalg/faer.rs:16-24
   CsrMatrix::try_from_csr_data(nr, nc, rp, ci, va).unwrap()
 }
@@ -168,9 +195,9 @@ impl BilinearForm for GpuPairing<'_> {
     self.cpu.element(metric, chart)
   }
   fn assemble(&self, topology: &Complex, geometry: &MeshLengthsSq) -> GalerkinMatrix {
-    let mesh = DeviceMesh::new(self.dev, topology, geometry);
+    let mesh = self.dev.cached_mesh(topology, geometry);  // one upload for the four calls of HodgeBlocks::compute
     let mut csr = ptr::null_mut();
-    check(unsafe { fq_assemble(self.dev.0, mesh.raw, self.kind, self.grade, 1, &mut csr) });
+    check(unsafe { fq_assemble(self.dev.ctx, mesh, self.kind, self.grade, 1, &mut csr) });
     download(self.dev, csr)
   }
 }
@@ -185,7 +212,7 @@ pub struct DeviceVector<'d> { dev: &'d Device, raw: *mut fq_vec }
 impl Clone for DeviceVector<'_> {
   fn clone(&self) -> Self {
     let out = self.zeros_like();
-    check(unsafe { fq_vec_copy(self.dev.0, out.raw, self.raw) });
+    check(unsafe { fq_vec_copy(self.dev.ctx, out.raw, self.raw) });
     out
   }
 }
@@ -193,12 +220,12 @@ impl Drop for DeviceVector<'_> { fn drop(&mut self) { unsafe { fq_vec_destroy(se
 impl<'d> DeviceVector<'d> {
   pub fn zeros(dev: &'d Device, n: usize) -> Self {
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_vec_create(dev.0, n, &mut raw) });
+    check(unsafe { fq_vec_create(dev.ctx, n, &mut raw) });
     Self { dev, raw }
   }
   pub fn to_host(&self) -> nalgebra::DVector<f64> {
     let mut host = nalgebra::DVector::zeros(unsafe { fq_vec_len(self.raw) });
-    check(unsafe { fq_vec_download(self.dev.0, self.raw, host.as_mut_ptr()) });
+    check(unsafe { fq_vec_download(self.dev.ctx, self.raw, host.as_mut_ptr()) });
     host
   }
 }
@@ -206,16 +233,16 @@ impl InnerProductSpace for DeviceVector<'_> {
   type Scalar = f64;
   fn zeros_like(&self) -> Self {
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_vec_create(self.dev.0, fq_vec_len(self.raw), &mut raw) });
+    check(unsafe { fq_vec_create(self.dev.ctx, fq_vec_len(self.raw), &mut raw) });
     Self { dev: self.dev, raw }
   }
   fn dot(&self, other: &Self) -> f64 {
     let mut out = 0.0;
-    check(unsafe { fq_vec_dot(self.dev.0, self.raw, other.raw, &mut out) });
+    check(unsafe { fq_vec_dot(self.dev.ctx, self.raw, other.raw, &mut out) });
     out
   }
-  fn scale(&mut self, alpha: f64) { check(unsafe { fq_vec_scale(self.dev.0, self.raw, alpha) }); }
-  fn add_scaled(&mut self, alpha: f64, x: &Self) { check(unsafe { fq_vec_axpy(self.dev.0, self.raw, alpha, x.raw) }); }
+  fn scale(&mut self, alpha: f64) { check(unsafe { fq_vec_scale(self.dev.ctx, self.raw, alpha) }); }
+  fn add_scaled(&mut self, alpha: f64, x: &Self) { check(unsafe { fq_vec_axpy(self.dev.ctx, self.raw, alpha, x.raw) }); }
 }
 
 /// Seam 3b: the assembled operator applied on the device (iterative/src/operator.rs:5-14).
@@ -224,7 +251,7 @@ impl<'d> DeviceCsr<'d> {
   pub fn upload(dev: &'d Device, m: &CsrMatrix<f64>) -> Self {
     let mut raw = ptr::null_mut();
     check(unsafe {
-      fq_csr_upload(dev.0, m.nrows(), m.ncols(), m.row_offsets().as_ptr(), m.col_indices().as_ptr(),
+      fq_csr_upload(dev.ctx, m.nrows(), m.ncols(), m.row_offsets().as_ptr(), m.col_indices().as_ptr(),
                     m.values().as_ptr(), &mut raw)
     });
     Self { dev, raw, n: m.nrows() }
@@ -236,7 +263,7 @@ impl<'d> LinearOperator for DeviceCsr<'d> {
   fn dim(&self) -> usize { self.n }
   fn apply(&self, x: &Self::Space) -> Self::Space {
     let y = x.zeros_like();
-    check(unsafe { fq_spmv(self.dev.0, self.raw, x.raw, y.raw) });
+    check(unsafe { fq_spmv(self.dev.ctx, self.raw, x.raw, y.raw) });
     y
   }
 }
@@ -248,13 +275,13 @@ impl<'d> GpuHodgeBlocks<'d> {
   pub fn compute(dev: &'d Device, topology: &Complex, geometry: &MeshLengthsSq, grade: usize) -> Self {
     let mesh = DeviceMesh::new(dev, topology, geometry);
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_hodge_symbolic(dev.0, mesh.raw, grade as c_int, 0, usize::MAX, 0, usize::MAX, &mut raw) });
-    check(unsafe { fq_hodge_numeric(dev.0, mesh.raw, raw, 1) });
+    check(unsafe { fq_hodge_symbolic(dev.ctx, mesh.raw, grade as c_int, 0, usize::MAX, 0, usize::MAX, &mut raw) });
+    check(unsafe { fq_hodge_numeric(dev.ctx, mesh.raw, raw, 1) });
     Self { dev, mesh, raw }
   }
   pub fn refresh(&mut self, geometry: &MeshLengthsSq) {
-    check(unsafe { fq_mesh_set_lengths(self.dev.0, self.mesh.raw, geometry.vector().as_ptr()) });
-    check(unsafe { fq_hodge_numeric(self.dev.0, self.mesh.raw, self.raw, 1) });
+    check(unsafe { fq_mesh_set_lengths(self.dev.ctx, self.mesh.raw, geometry.vector().as_ptr()) });
+    check(unsafe { fq_hodge_numeric(self.dev.ctx, self.mesh.raw, self.raw, 1) });
   }
   /// 0 mass_sigma, 1 mass_u, 2 dif_test, 3 dif_both as `GalerkinMatrix` (host CSR, usize indices)
   pub fn block(&self, which: usize) -> GalerkinMatrix {
@@ -263,7 +290,7 @@ impl<'d> GpuHodgeBlocks<'d> {
   /// `mixed_hodge_laplacian` (hodge.rs:93-99) stitched on the device, left there for the Krylov solve
   pub fn mixed_hodge_laplacian(&self) -> DeviceCsr<'d> {
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_hodge_mixed_laplacian(self.dev.0, self.raw, &mut raw) });
+    check(unsafe { fq_hodge_mixed_laplacian(self.dev.ctx, self.raw, &mut raw) });
     DeviceCsr { dev: self.dev, raw, n: self.block(0).nrows() + self.block(1).nrows() }
   }
 }
@@ -271,7 +298,7 @@ impl<'d> GpuHodgeBlocks<'d> {
   /// The symmetric saddle point `assemble_mixed_kkt` hands to MINRES (problems/elliptic.rs:101-113): sigma rows negated.
   pub fn mixed_kkt_symmetric(&self) -> DeviceCsr<'d> {
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_hodge_mixed_kkt_symmetric(self.dev.0, self.raw, &mut raw) });
+    check(unsafe { fq_hodge_mixed_kkt_symmetric(self.dev.ctx, self.raw, &mut raw) });
     DeviceCsr { dev: self.dev, raw, n: self.block(0).nrows() + self.block(1).nrows() }
   }
 }
@@ -281,7 +308,7 @@ impl<'d> DeviceCsr<'d> {
   /// `hdif_gram(k) = mass(k) + dif_both(k + 1)` (whitney_complex.rs:118-125) as a device CSR add on the union pattern.
   pub fn add(&self, other: &DeviceCsr<'d>) -> DeviceCsr<'d> {
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_csr_add(self.dev.0, self.raw, other.raw, &mut raw) });
+    check(unsafe { fq_csr_add(self.dev.ctx, self.raw, other.raw, &mut raw) });
     DeviceCsr { dev: self.dev, raw, n: self.n }
   }
 }
@@ -295,7 +322,7 @@ pub fn minres_afw<'d>(kkt: &DeviceCsr<'d>, hdif_gram_sigma: &DeviceCsr<'d>, hdif
   let blocks = [hdif_gram_sigma.raw as *const fq_csr, hdif_gram_u.raw as *const fq_csr];
   let offsets = [0usize, hdif_gram_sigma.n, kkt.n];
   let (mut iters, mut residual, mut converged, mut inner) = (0usize, 0f64, 0 as c_int, 0usize);
-  check(unsafe { fq_minres_blockdiag(kkt.dev.0, kkt.raw, 2, blocks.as_ptr(), offsets.as_ptr(), inner_rtol, inner_max_iters,
+  check(unsafe { fq_minres_blockdiag(kkt.dev.ctx, kkt.raw, 2, blocks.as_ptr(), offsets.as_ptr(), inner_rtol, inner_max_iters,
                                      rhs.raw, rtol, max_iters, x.raw, &mut iters, &mut residual, &mut converged, &mut inner) });
   (x, iters, residual, converged != 0)
 }
@@ -319,8 +346,8 @@ pub fn assemble_weighted_mass<F: Sync + formoniq::Section>(dev: &Device, mesh: &
     .flat_map_iter(|cell| nodes.iter().map(|b| coefficient.at(&cell.point(b.clone())).as_scalar()).collect::<Vec<_>>())
     .collect();
   let mut raw = ptr::null_mut();
-  check(unsafe { fq_assemble_symbolic(dev.0, mesh.raw, 0 /*FQ_MASS*/, grade as c_int, 0, usize::MAX, &mut raw) });
-  check(unsafe { fq_weighted_mass_numeric(dev.0, mesh.raw, raw, nodes.len() as c_int, weights.as_ptr(), table.as_ptr(),
+  check(unsafe { fq_assemble_symbolic(dev.ctx, mesh.raw, 0 /*FQ_MASS*/, grade as c_int, 0, usize::MAX, &mut raw) });
+  check(unsafe { fq_weighted_mass_numeric(dev.ctx, mesh.raw, raw, nodes.len() as c_int, weights.as_ptr(), table.as_ptr(),
                                           alpha.as_ptr(), 1) });
   download(dev, raw)
 }
@@ -333,7 +360,7 @@ pub struct GpuLinearFormPlan<'d> { dev: &'d Device, raw: *mut fq_matfree, grade:
 impl<'d> GpuLinearFormPlan<'d> {
   pub fn new(dev: &'d Device, mesh: &DeviceMesh<'d>, topology: &Complex, grade: usize) -> Self {
     let mut raw = ptr::null_mut();
-    check(unsafe { fq_linear_form_create(dev.0, mesh.raw, grade as c_int, &mut raw) });
+    check(unsafe { fq_linear_form_create(dev.ctx, mesh.raw, grade as c_int, &mut raw) });
     Self { dev, raw, grade, ndofs: topology.skeleton(grade).len() }
   }
   /// Drop-in for `form.assemble(topology, geometry)` of any `LinearForm` of this plan's grade.
@@ -345,7 +372,7 @@ impl<'d> GpuLinearFormPlan<'d> {
       .flat_map_iter(|cell| form.element(&geometry.cell_metric(cell), cell).iter().copied().collect::<Vec<_>>())
       .collect();
     let out = DeviceVector::zeros(self.dev, self.ndofs);
-    check(unsafe { fq_linear_form_assemble(self.dev.0, self.raw, elvecs.as_ptr(), out.raw) });
+    check(unsafe { fq_linear_form_assemble(self.dev.ctx, self.raw, elvecs.as_ptr(), out.raw) });
     formoniq::galerkin::GalerkinVector::new(form.test_grade(), out.to_host())
   }
 }
@@ -369,7 +396,7 @@ impl<'d> GpuLinearFormPlan<'d> {
         .collect::<Vec<_>>()).collect::<Vec<_>>())
       .collect();
     let out = DeviceVector::zeros(self.dev, self.ndofs);
-    check(unsafe { fq_source_form_assemble(self.dev.0, self.raw, nodes.len() as c_int, weights.as_ptr(), table.as_ptr(),
+    check(unsafe { fq_source_form_assemble(self.dev.ctx, self.raw, nodes.len() as c_int, weights.as_ptr(), table.as_ptr(),
                                            samples.as_ptr(), out.raw) });
     formoniq::galerkin::GalerkinVector::new(source.grade(), out.to_host())
   }
