@@ -539,7 +539,10 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
         t.numpy()[...] = a
         return t
 
-    faces_t = [pinned(fq.kuhn_cell_faces_host(DIM, eshape, j).view(np.int64)) for j in range(DIM)] + [None]
+    # FaceIncidence tables of the grades the four blocks use as rows / columns (0 and 1 for k = 1; the header allows NULL
+    # for grades the caller will not use)
+    used = sorted({g for _, f in forms for g in (f.test_grade(), f.trial_grade())})
+    faces_t = [pinned(fq.kuhn_cell_faces_host(DIM, eshape, j).view(np.int64)) if j in used else None for j in range(DIM + 1)]
     faces = [None if t is None else t.numpy().view(np.uint64) for t in faces_t]
     len_t = pinned(lengths)
     h2d = sum(f.nbytes for f in faces if f is not None) + len_t.numpy().nbytes
@@ -555,6 +558,8 @@ def run_e2e(args, fq, ctx, mesh, forms, shape, slab, rank, world, allmax, allsum
     # blocks in HodgeBlocks order (issuing the two large ones first was measured: 262 instead of 234 ms, the widening
     # threads of the big blocks then compete with the host side of the remaining assemblies)
     order = list(range(len(forms)))
+    if os.environ.get("FQ_E2E_ORDER"):
+        order = [int(v) for v in os.environ["FQ_E2E_ORDER"].split(",")]
     for it in range(args.e2e_steps + 2):  # pass 0 sizes the result buffers, pass 1 warms the allocations up
         barrier()
         t0 = time.perf_counter()

@@ -63,6 +63,8 @@ SIGNATURES = [
     ("fq_hodge_mixed_laplacian", _i, [_vp, _vp, _P(_vp)]),
     ("fq_hodge_mixed_kkt_symmetric", _i, [_vp, _vp, _P(_vp)]),
     ("fq_csr_row_abs_sums", _i, [_vp, _vp, _vp]),
+    ("fq_csr_inv_diagonal", _i, [_vp, _vp, _vp]),
+    ("fq_vec_mul", _i, [_vp, _vp, _vp, _vp]),
     ("fq_csr_add", _i, [_vp, _vp, _vp, _P(_vp)]),
     ("fq_csr_transpose", _i, [_vp, _vp, _P(_vp)]),
     ("fq_csr_restrict", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _P(_vp)]),

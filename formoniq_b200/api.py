@@ -301,6 +301,10 @@ class DeviceVector:
     def add(self, x: "DeviceVector"):
         self.add_scaled(1.0, x)
 
+    def assign_product(self, d: "DeviceVector", r: "DeviceVector"):
+        """self = d .* r (component-wise; the Jacobi preconditioner applied to r)."""
+        check(_lib.lib().fq_vec_mul(self.ctx._h, self._h, d._h, r._h))
+
     def norm(self) -> float:
         return float(np.sqrt(self.dot(self)))
 
@@ -395,6 +399,13 @@ class DeviceCsr:
         h = C.c_void_p()
         check(_lib.lib().fq_csr_transpose(self.ctx._h, self._h, C.byref(h)))
         return DeviceCsr(self.ctx, h)
+
+    def inv_diagonal(self) -> DeviceVector:
+        """1 / a_ii of the held rows (Jacobi, iterative/src/precond.rs:87-121); FormoniqError on a zero / missing entry."""
+        b, e = self.row_range
+        d = DeviceVector(self.ctx, e - b)
+        check(_lib.lib().fq_csr_inv_diagonal(self.ctx._h, self._h, d._h))
+        return d
 
     def row_abs_sums(self) -> DeviceVector:
         """y_i = sum_j |a_ij| of the held rows (the inf-norm is its maximum)."""

@@ -566,6 +566,26 @@ int fq_csr_row_abs_sums(fq_ctx* ctx, const fq_csr* a, fq_vec* y) {
   csr_row_abs_sums(ctx, a, y->d.p);
   FQ_API_END
 }
+int fq_csr_inv_diagonal(fq_ctx* ctx, fq_csr* a, fq_vec* d) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && a && d, "null argument");
+  const size_t nrows = a->row_end - a->row_begin;
+  FQ_REQUIRE(d->d.n == nrows, "inv_diagonal: dimension mismatch");
+  FQ_REQUIRE(a->nrows == a->ncols, "inv_diagonal needs a square matrix");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  csr_build_inv_diag(ctx, a);
+  if (nrows)
+    FQ_CUDA(cudaMemcpyAsync(d->d.p, a->inv_diag.p, nrows * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  FQ_API_END
+}
+int fq_vec_mul(fq_ctx* ctx, fq_vec* z, const fq_vec* d, const fq_vec* r) {
+  FQ_API_BEGIN
+  FQ_REQUIRE(ctx && z && d && r, "null argument");
+  FQ_REQUIRE(z->d.n == d->d.n && z->d.n == r->d.n, "vec_mul: dimension mismatch");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  vec_mul_pointwise(ctx, z->d.p, d->d.p, r->d.p, z->d.n);
+  FQ_API_END
+}
 int fq_csr_add(fq_ctx* ctx, const fq_csr* a, const fq_csr* b, fq_csr** out) {
   FQ_API_BEGIN
   FQ_REQUIRE(ctx && a && b && out, "null argument");

@@ -282,10 +282,17 @@ class DistKktPencil:
     (sigma_owned | u_owned); an operator application copies the two owned segments into column windows
     [held_lo, held_hi), refreshes their halos with one send/recv pair per neighbour and runs the four windowed SpMVs;
     inner products are completed by an all-reduce of one scalar.  Implements the pencil protocol of
-    eigen.shift_invert_lanczos; the inner solves of the shift-invert step are MINRES on A - shift*B (SpMV-only)."""
+    eigen.shift_invert_lanczos; the inner solves of the shift-invert step are MINRES on A - shift*B (SpMV-only).
+
+    precond = "afw": MINRES is preconditioned by the AFW block diagonal diag(hdif_gram(k-1)^-1, hdif_gram(k)^-1)
+    (problems/elliptic.rs:29-47) across the ranks: hdif_gram(j) = M_j + dif_both(j+1) (whitney_complex.rs:118-125) is
+    assembled on the rank's rows, and each block solve is a Jacobi-preconditioned CG on the row-partitioned operator
+    (halo exchange + windowed SpMV per iteration, all-reduced inner products) to `afw_rtol`, where the reference applies
+    a sparse Cholesky factor.  The outer iteration count is then independent of the mesh width."""
 
     def __init__(self, ctx, dim: int, shape, grade: int, rank: int = 0, world: int = 1, group=None, jitter: float = 0.0,
-                 inner_rtol: float = 1e-13, inner_max_iters: int = 200000):
+                 inner_rtol: float = 1e-13, inner_max_iters: int = 200000, precond: str = "none", afw_rtol: float = 1e-12,
+                 afw_max_iters: int = 20000):
         import torch
 
         from .api import DeviceVector, HodgeBlocks, Mesh, WhitneyPairing
@@ -315,6 +322,16 @@ class DistKktPencil:
         self.own_u = self.win_u.view(self.ru.own_lo - self.ru.held_lo, self.nu)
         self.tmp_s, self.tmp_u = DeviceVector(ctx, max(self.ns, 1)).view(0, self.ns), DeviceVector(ctx, max(self.nu, 1)).view(0, self.nu)
         self._shift = 0.0
+        self.precond, self.afw_rtol, self.afw_max_iters, self.afw_iterations = precond, afw_rtol, afw_max_iters, 0
+        if precond == "afw":
+            stiff_s = WhitneyPairing.dif_both(dim, grade).symbolic(self.mesh, *srows)   # d^T M_k d on the sigma rows
+            stiff_s.numeric(self.mesh, True)
+            self.h_s = self.hb.mass_sigma + stiff_s          # hdif_gram(k-1), rows = the rank's sigma rows
+            self.h_u = self.hb.mass_u + self.hb.dif_both     # hdif_gram(k),   rows = the rank's u rows
+            self.jac_s = self.h_s.inv_diagonal() if self.ns else None
+            self.jac_u = self.h_u.inv_diagonal() if self.nu else None
+        elif precond != "none":
+            raise ValueError("precond must be 'none' or 'afw'")
         # inf-norms of the block rows (linalg/eigen.rs:359-368)
         hb = self.hb
         rows_s = hb.mass_sigma.row_abs_sums().to_numpy() + hb.dif_test.row_abs_sums().to_numpy()
@@ -380,6 +397,30 @@ class DistKktPencil:
         self._shift = shift
         return shift
 
+    def _reduce(self):
+        return (lambda local: all_reduce_scalar(local, "sum", self.group, self.world)) if self.world > 1 else None
+
+    def _block_solve(self, h, jac, n, window_t, window, part, ranges, own, r, z):
+        """z = h^-1 r on one block of the AFW preconditioner: Jacobi-CG on the row-partitioned hdif_gram."""
+        from .api import StopCriterion, cg_op
+
+        def apply(x, y):
+            own.copy_from(x)
+            exchange_halo(window_t, part, self.rank, self.group)
+            h.apply_window(window, ranges.held_lo, y)
+
+        sol, rep = cg_op(self.ctx, n, apply, r, StopCriterion(self.afw_rtol, self.afw_max_iters),
+                         precond=(lambda rr, zz: zz.assign_product(jac, rr)) if jac is not None else None, reduce=self._reduce())
+        self.afw_iterations += rep.iters
+        z.copy_from(sol)
+
+    def afw_apply(self, r, z):
+        """z = diag(hdif_gram(k-1)^-1, hdif_gram(k)^-1) r (problems/elliptic.rs:29-47)."""
+        self._block_solve(self.h_s, self.jac_s, self.ns, self.win_s_t, self.win_s, self.part_s, self.rs, self.own_s,
+                          r.view(0, self.ns), z.view(0, self.ns))
+        self._block_solve(self.h_u, self.jac_u, self.nu, self.win_u_t, self.win_u, self.part_u, self.ru, self.own_u,
+                          r.view(self.ns, self.nu), z.view(self.ns, self.nu))
+
     def solve(self, v):
         from .api import StopCriterion, minres_op
         from .eigen import EigenError
@@ -388,7 +429,7 @@ class DistKktPencil:
         rhs.view(0, self.ns).scale(-1.0)
         x, rep = minres_op(self.ctx, self.n, lambda xin, y: self.a_apply(xin, y, self._shift, True), rhs,
                            StopCriterion(self.inner_rtol, self.inner_max_iters),
-                           reduce=(lambda local: all_reduce_scalar(local, "sum", self.group, self.world)) if self.world > 1 else None)
+                           precond=self.afw_apply if self.precond == "afw" else None, reduce=self._reduce())
         self.inner_iterations += rep.iters
         if not rep.converged:
             raise EigenError("SingularPencil", shift=self._shift, inner_residual=rep.residual)

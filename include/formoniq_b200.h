@@ -170,6 +170,12 @@ int fq_csr_add(fq_ctx* ctx, const fq_csr* a, const fq_csr* b, fq_csr** out);
 /* y_i = sum_j |a_ij| over the held rows; its maximum is the inf-norm the eigen solver scales residuals with
  * (linalg/eigen.rs:359-368) */
 int fq_csr_row_abs_sums(fq_ctx* ctx, const fq_csr* a, fq_vec* y);
+/* d_i = 1 / a_ii over the held rows of a square matrix: the Jacobi preconditioner of iterative/src/precond.rs:87-121 as a
+ * vector, for callers that drive a Krylov method through fq_cg_op / fq_minres_op (a row-partitioned operator applies it
+ * with fq_vec_mul).  FQ_ERR_DEGENERATE on a missing or zero diagonal entry, as the reference asserts (:101-104). */
+int fq_csr_inv_diagonal(fq_ctx* ctx, fq_csr* a, fq_vec* d);
+/* z = d .* r (component-wise product; z may alias r) */
+int fq_vec_mul(fq_ctx* ctx, fq_vec* z, const fq_vec* d, const fq_vec* r);
 
 /* HodgeBlocks::mixed_hodge_laplacian (formoniq/src/hodge.rs:93-99): [[M_{k-1}, -dif_test], [dif_test^T, dif_both]]
  * stitched on the device (stable transpose + row-wise concatenation instead of CooMatrixExt::block,

@@ -1138,3 +1138,25 @@ def test_partitioned_uploaded_mesh_assembles_the_same_row_blocks(fq, ctx, dim, s
             vals.append(va)
         assert np.array_equal(np.concatenate(rows), erp) and np.array_equal(np.concatenate(cols), eci), which
         assert same_bits_mod_zero_sign(np.concatenate(vals), eva), which
+
+
+def test_distributed_pencil_with_the_afw_preconditioner(fq, ctx):
+    # DistKktPencil(precond="afw"): MINRES on the shifted, symmetrised KKT operator preconditioned by
+    # diag(hdif_gram(k-1)^-1, hdif_gram(k)^-1) (problems/elliptic.rs:29-47), each block a Jacobi-CG solve on the
+    # row-partitioned operator.  Same eigenvalues as the unpreconditioned solve, and an outer iteration count that does
+    # not grow with the mesh (the unpreconditioned one does)
+    from formoniq_b200.dist import DistKktPencil
+
+    outer = {}
+    for n in (3, 4):
+        plain = DistKktPencil(ctx, 3, [n, n, n], 1)
+        afw = DistKktPencil(ctx, 3, [n, n, n], 1, precond="afw")
+        v0, _ = fq.shift_invert_lanczos(plain, 5.0, 3)
+        v1, _ = fq.shift_invert_lanczos(afw, 5.0, 3)
+        assert np.abs(v0 - v1).max() <= 1e-8 * np.abs(v0).max(), (n, v0, v1)
+        assert afw.afw_iterations > 0
+        outer[n] = (plain.inner_iterations / max(plain.applies, 1), afw.inner_iterations, plain.inner_iterations)
+    # AFW: the outer MINRES iterations per Lanczos run stay of the same size as the mesh is refined ...
+    assert outer[4][1] <= 2.0 * outer[3][1], outer
+    # ... and are far fewer than without it
+    assert outer[4][1] * 5 < outer[4][2], outer
