@@ -55,6 +55,16 @@ double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n) {
   return *ctx->host_scalar;
 }
 
+// <x, y> by the same two-stage reduction, the result left in device memory (no host round trip): the device-resident
+// Krylov loops of krylov.cu read their scalars from there.  Same grid and order as vec_dot, hence the same bits.
+void vec_dot_device(fq_ctx* ctx, const double* x, const double* y, size_t n, double* d_partials, double* d_out) {
+  const int grid = std::min(grid_for(n ? n : 1, kRedThreads, ctx->sm_count, 8), kRedBlocksMax);
+  dot_partial_kernel<<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, d_partials);
+  dot_final_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d_partials, grid, d_out);
+  fq_count_launch(ctx, 2);
+}
+size_t vec_dot_scratch_doubles() { return size_t(kRedBlocksMax); }
+
 __global__ void scale_kernel(double* __restrict__ x, double alpha, size_t n) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = __dmul_rn(x[i], alpha);

@@ -94,6 +94,8 @@ void matfree_delete(::fq_matfree* op);
 
 // ---- blas1.cu
 double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n);
+void vec_dot_device(fq_ctx* ctx, const double* x, const double* y, size_t n, double* d_partials, double* d_out);
+size_t vec_dot_scratch_doubles();
 void vec_scale(fq_ctx* ctx, double* x, double alpha, size_t n);
 void vec_axpy(fq_ctx* ctx, double* y, double alpha, const double* x, size_t n);
 void vec_mul_pointwise(fq_ctx* ctx, double* z, const double* d, const double* r, size_t n);

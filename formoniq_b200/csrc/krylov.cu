@@ -10,6 +10,7 @@
 //     side, which owns the communicator: torch.distributed / NCCL).
 // Scalars live on the host exactly as in the reference; every vector operation is a kernel from blas1.cu / spmv.cu.
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 
 #include "internal.hpp"
@@ -129,6 +130,309 @@ KrylovReport minres_core(fq_ctx* ctx, size_t n, const KrylovOps& ops, const doub
   return rep;
 }
 
+// ---- device-resident CG for one assembled matrix (Identity / Jacobi)
+// The loop above synchronises with the host three times per iteration (one per inner product).  Here the scalars of
+// the recurrence live in device memory, the updates read them there, and a `done` flag turns every update into a no-op
+// once the stopping test of krylov.rs:62-66 fires: one iteration is a fixed sequence of kernels, captured once in a CUDA
+// graph and replayed in batches, with one host look at the flag per batch.  Same kernels, same reductions, same IEEE
+// operations on the scalars as cg_core: the iterates, the iteration count and the residual are the same bits.
+namespace {
+struct CgState {
+  double bb, rz, pap, rz_next, rr, residual;
+  unsigned long long iters;
+  int done, converged;
+};
+__global__ void cg_begin_kernel(CgState* s, double rtol, unsigned long long max_iters) {
+  if (s->done) return;
+  const double residual = __ddiv_rn(__dsqrt_rn(s->rr), __dsqrt_rn(s->bb));
+  s->residual = residual;
+  s->converged = residual <= rtol ? 1 : 0;
+  if (s->converged || s->iters >= max_iters) s->done = 1;
+}
+__global__ void cg_update_x_r_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                                     const double* __restrict__ ap, const CgState* __restrict__ s, size_t n) {
+  if (s->done) return;
+  const double alpha = __ddiv_rn(s->rz, s->pap);
+  const double nalpha = -alpha;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    x[i] = __dadd_rn(__dmul_rn(alpha, p[i]), x[i]);
+    r[i] = __dadd_rn(__dmul_rn(nalpha, ap[i]), r[i]);
+  }
+}
+__global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ z, const CgState* __restrict__ s, size_t n) {
+  if (s->done) return;
+  const double beta = __ddiv_rn(s->rz_next, s->rz);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    p[i] = __dadd_rn(__dmul_rn(1.0, z[i]), __dmul_rn(p[i], beta));  // p *= beta, then p += 1.0 * z (krylov.rs:90-91)
+}
+__global__ void cg_end_kernel(CgState* s) {
+  if (s->done) return;
+  s->rz = s->rz_next;
+  ++s->iters;
+}
+}  // namespace
+
+static KrylovReport cg_device(fq_ctx* ctx, fq_csr* a, int precond, const double* b, double rtol, size_t max_iters, double* x) {
+  const size_t n = a->nrows;
+  KrylovReport rep;
+  spmv_prepare(ctx, a);
+  if (precond == 1) csr_build_inv_diag(ctx, a);
+  if (n) FQ_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream));
+  Work w{ctx, n, {}};
+  double *r = w.get(), *z = w.get(), *p = w.get(), *ap = w.get();
+  DevBuf<double> partials(vec_dot_scratch_doubles());
+  DevBuf<CgState> state(1);
+  FQ_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CgState), ctx->stream));
+  auto apply_precond = [&]() {
+    if (precond == 0)
+      copy(ctx, z, r, n);
+    else
+      vec_mul_pointwise(ctx, z, a->inv_diag.p, r, n);
+  };
+  vec_dot_device(ctx, b, b, n, partials.p, &state.p->bb);
+  copy(ctx, r, b, n);
+  apply_precond();
+  copy(ctx, p, z, n);
+  vec_dot_device(ctx, r, z, n, partials.p, &state.p->rz);
+  vec_dot_device(ctx, r, r, n, partials.p, &state.p->rr);
+  CgState h{};
+  FQ_CUDA(cudaMemcpyAsync(&h, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (std::sqrt(h.bb) == 0.0) {  // krylov.rs:54-57
+    rep.converged = true;
+    return rep;
+  }
+  const int grid = grid_for(n, 256, ctx->sm_count);
+  auto iteration = [&]() {
+    cg_begin_kernel<<<1, 1, 0, ctx->stream>>>(state.p, rtol, (unsigned long long)max_iters);
+    spmv_apply(ctx, a, p, ap);
+    vec_dot_device(ctx, p, ap, n, partials.p, &state.p->pap);
+    cg_update_x_r_kernel<<<grid, 256, 0, ctx->stream>>>(x, r, p, ap, state.p, n);
+    apply_precond();
+    vec_dot_device(ctx, r, z, n, partials.p, &state.p->rz_next);
+    vec_dot_device(ctx, r, r, n, partials.p, &state.p->rr);
+    cg_update_p_kernel<<<grid, 256, 0, ctx->stream>>>(p, z, state.p, n);
+    cg_end_kernel<<<1, 1, 0, ctx->stream>>>(state.p);
+    fq_count_launch(ctx, 4);
+  };
+  // one iteration captured as a graph (not while per-kernel timing is on: its events do not belong in a capture)
+  cudaGraphExec_t exec = nullptr;
+  if (!ctx->timing && !std::getenv("FQ_KRYLOV_NO_GRAPH")) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int64_t launches_before = ctx->launches;
+      iteration();
+      ctx->launches = launches_before;  // counted per replay below
+      if (cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph) {
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+        cudaGraphDestroy(graph);
+      }
+    }
+    if (!exec) (void)cudaGetLastError();
+  }
+  const int launches_per_iteration = 12;
+  size_t batch = 4;
+  for (;;) {
+    for (size_t i = 0; i < batch; ++i) {
+      if (exec) {
+        FQ_CUDA(cudaGraphLaunch(exec, ctx->stream));
+        fq_count_launch(ctx, launches_per_iteration);
+      } else {
+        iteration();
+      }
+    }
+    FQ_CUDA(cudaMemcpyAsync(&h, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h.done) break;
+    if (batch < 64) batch *= 2;
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  FQ_CUDA(cudaGetLastError());
+  rep.iters = size_t(h.iters);
+  rep.residual = h.residual;
+  rep.converged = h.converged != 0;
+  return rep;
+}
+
+// ---- device-resident MINRES for one assembled matrix (Identity / Jacobi): minres_core above with its scalars (Lanczos
+// coefficients, Givens rotation, residual estimate) in device memory.  The three-term recurrences rotate their vectors
+// with period 3 (r1 <- r2 <- y_next, w2 <- w <- w_new), so THREE iterations are captured as one graph.
+namespace {
+struct MinresState {
+  double beta1, oldb, beta, dbar, epsln, phibar, cs, sn;
+  double alfa, t0, oldeps, delta, gamma, phi, residual;
+  unsigned long long iters;
+  int done, stop_next, converged;
+};
+__global__ void minres_begin_kernel(MinresState* s, unsigned long long max_iters) {
+  if (s->done) return;
+  if (s->stop_next || s->iters >= max_iters) {
+    s->done = 1;
+    return;
+  }
+  ++s->iters;
+}
+// v = y * (1 / beta)
+__global__ void minres_v_kernel(double* __restrict__ v, const double* __restrict__ y, const MinresState* __restrict__ s, size_t n) {
+  if (s->done) return;
+  const double inv = __ddiv_rn(1.0, s->beta);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = __dmul_rn(y[i], inv);
+}
+// yn += (-beta / oldb) * r1   (from the second iteration on)
+__global__ void minres_sub_r1_kernel(double* __restrict__ yn, const double* __restrict__ r1, const MinresState* __restrict__ s,
+                                     size_t n) {
+  if (s->done || s->iters < 2) return;
+  const double c = __ddiv_rn(-s->beta, s->oldb);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) yn[i] = __dadd_rn(__dmul_rn(c, r1[i]), yn[i]);
+}
+// yn += (-alfa / beta) * r2
+__global__ void minres_sub_r2_kernel(double* __restrict__ yn, const double* __restrict__ r2, const MinresState* __restrict__ s,
+                                     size_t n) {
+  if (s->done) return;
+  const double c = __ddiv_rn(-s->alfa, s->beta);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) yn[i] = __dadd_rn(__dmul_rn(c, r2[i]), yn[i]);
+}
+// the scalar recurrences of one step (krylov.rs:160-190), t0 = <r2, y>
+__global__ void minres_scalars_kernel(MinresState* s, double rtol) {
+  if (s->done) return;
+  const double eps = 2.220446049250313e-16;
+  s->oldb = s->beta;
+  s->beta = __dsqrt_rn(fmax(s->t0, 0.0));
+  s->oldeps = s->epsln;
+  s->delta = __dadd_rn(__dmul_rn(s->cs, s->dbar), __dmul_rn(s->sn, s->alfa));
+  const double gbar = __dadd_rn(__dmul_rn(s->sn, s->dbar), -__dmul_rn(s->cs, s->alfa));
+  s->epsln = __dmul_rn(s->sn, s->beta);
+  s->dbar = __dmul_rn(-s->cs, s->beta);
+  s->gamma = fmax(__dsqrt_rn(__dadd_rn(__dmul_rn(gbar, gbar), __dmul_rn(s->beta, s->beta))), eps);
+  s->cs = __ddiv_rn(gbar, s->gamma);
+  s->sn = __ddiv_rn(s->beta, s->gamma);
+  s->phi = __dmul_rn(s->cs, s->phibar);
+  s->phibar = __dmul_rn(s->phibar, s->sn);
+  s->residual = __ddiv_rn(s->phibar, s->beta1);
+  if (s->residual <= rtol) {
+    s->converged = 1;
+    s->stop_next = 1;
+  }
+}
+// w_new = (v - oldeps * w2 - delta * w) / gamma ;  x += phi * w_new
+__global__ void minres_w_x_kernel(double* __restrict__ wnew, const double* __restrict__ v, const double* __restrict__ w2,
+                                  const double* __restrict__ wv, double* __restrict__ x, const MinresState* __restrict__ s,
+                                  size_t n) {
+  if (s->done) return;
+  const double a = -s->oldeps, b = -s->delta, inv = __ddiv_rn(1.0, s->gamma), phi = s->phi;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double t = v[i];
+    t = __dadd_rn(__dmul_rn(a, w2[i]), t);
+    t = __dadd_rn(__dmul_rn(b, wv[i]), t);
+    t = __dmul_rn(t, inv);
+    wnew[i] = t;
+    x[i] = __dadd_rn(__dmul_rn(phi, t), x[i]);
+  }
+}
+}  // namespace
+
+static KrylovReport minres_device(fq_ctx* ctx, fq_csr* a, int precond, const double* b, double rtol, size_t max_iters, double* x) {
+  const size_t n = a->nrows;
+  KrylovReport rep;
+  spmv_prepare(ctx, a);
+  if (precond == 1) csr_build_inv_diag(ctx, a);
+  Work w{ctx, n, {}};
+  double *r1 = w.get(), *r2 = w.get(), *y = w.get(), *v = w.get(), *yn = w.get();
+  double *wv = w.get(), *w2 = w.get(), *wnew = w.get();
+  DevBuf<double> partials(vec_dot_scratch_doubles());
+  DevBuf<MinresState> state(1);
+  auto apply_precond = [&](const double* r, double* z) {
+    if (precond == 0)
+      copy(ctx, z, r, n);
+    else
+      vec_mul_pointwise(ctx, z, a->inv_diag.p, r, n);
+  };
+  FQ_CUDA(cudaMemsetAsync(state.p, 0, sizeof(MinresState), ctx->stream));
+  copy(ctx, r1, b, n);
+  apply_precond(r1, y);
+  vec_dot_device(ctx, r1, y, n, partials.p, &state.p->t0);
+  if (n) FQ_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream));
+  MinresState h{};
+  FQ_CUDA(cudaMemcpyAsync(&h, state.p, sizeof(MinresState), cudaMemcpyDeviceToHost, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h.t0 <= 0.0) {  // krylov.rs:127-131
+    rep.converged = true;
+    return rep;
+  }
+  h.beta1 = std::sqrt(h.t0);
+  h.oldb = 0.0, h.beta = h.beta1, h.dbar = 0.0, h.epsln = 0.0, h.phibar = h.beta1, h.cs = -1.0, h.sn = 0.0, h.residual = 1.0;
+  FQ_CUDA(cudaMemcpyAsync(state.p, &h, sizeof(MinresState), cudaMemcpyHostToDevice, ctx->stream));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));  // `h` is reused below
+  copy(ctx, r2, r1, n);
+  const int grid = grid_for(n, 256, ctx->sm_count);
+  auto iteration = [&]() {
+    minres_begin_kernel<<<1, 1, 0, ctx->stream>>>(state.p, (unsigned long long)max_iters);
+    minres_v_kernel<<<grid, 256, 0, ctx->stream>>>(v, y, state.p, n);
+    spmv_apply(ctx, a, v, yn);
+    minres_sub_r1_kernel<<<grid, 256, 0, ctx->stream>>>(yn, r1, state.p, n);
+    vec_dot_device(ctx, v, yn, n, partials.p, &state.p->alfa);
+    minres_sub_r2_kernel<<<grid, 256, 0, ctx->stream>>>(yn, r2, state.p, n);
+    std::swap(r1, r2);  // r1 = r2
+    std::swap(r2, yn);  // r2 = y_next (yn now holds the old r1: scratch)
+    apply_precond(r2, y);
+    vec_dot_device(ctx, r2, y, n, partials.p, &state.p->t0);
+    minres_scalars_kernel<<<1, 1, 0, ctx->stream>>>(state.p, rtol);
+    minres_w_x_kernel<<<grid, 256, 0, ctx->stream>>>(wnew, v, w2, wv, x, state.p, n);
+    double* t = w2;  // w2 = w ; w = w_new
+    w2 = wv;
+    wv = wnew;
+    wnew = t;
+    fq_count_launch(ctx, 6);
+  };
+  // the pointer roles come back after three iterations: capture three
+  cudaGraphExec_t exec = nullptr;
+  if (!ctx->timing && !std::getenv("FQ_KRYLOV_NO_GRAPH")) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int64_t launches_before = ctx->launches;
+      iteration();
+      iteration();
+      iteration();
+      ctx->launches = launches_before;
+      if (cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph) {
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+        cudaGraphDestroy(graph);
+      }
+    }
+    if (!exec) (void)cudaGetLastError();
+  }
+  const int launches_per_iteration = 12;
+  size_t batch = 2;  // in units of three iterations
+  for (;;) {
+    for (size_t i = 0; i < batch; ++i) {
+      if (exec) {
+        FQ_CUDA(cudaGraphLaunch(exec, ctx->stream));
+        fq_count_launch(ctx, 3 * launches_per_iteration);
+      } else {
+        iteration();
+        iteration();
+        iteration();
+      }
+    }
+    FQ_CUDA(cudaMemcpyAsync(&h, state.p, sizeof(MinresState), cudaMemcpyDeviceToHost, ctx->stream));
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h.done) break;
+    if (batch < 32) batch *= 2;
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  FQ_CUDA(cudaGetLastError());
+  rep.iters = size_t(h.iters);
+  rep.residual = h.residual;
+  rep.converged = h.converged != 0;
+  return rep;
+}
+
 // ---- one assembled matrix, Identity / Jacobi
 static KrylovOps csr_ops(fq_ctx* ctx, fq_csr* a, int precond, size_t n) {
   spmv_prepare(ctx, a);
@@ -148,7 +452,8 @@ KrylovReport krylov_cg(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b, dou
   const size_t n = b->d.n;
   FQ_REQUIRE(a->nrows == a->ncols && a->row_begin == 0 && a->row_end == a->nrows, "cg needs a square, fully held matrix");
   FQ_REQUIRE(n == a->nrows && x->d.n == n, "cg: dimension mismatch");
-  return cg_core(ctx, n, csr_ops(ctx, a, precond, n), b->d.p, rtol, max_iters, x->d.p);
+  if (std::getenv("FQ_KRYLOV_HOST")) return cg_core(ctx, n, csr_ops(ctx, a, precond, n), b->d.p, rtol, max_iters, x->d.p);
+  return cg_device(ctx, a, precond, b->d.p, rtol, max_iters, x->d.p);
 }
 KrylovReport krylov_minres(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b, double rtol, size_t max_iters,
                            fq_vec* x) {
@@ -156,7 +461,8 @@ KrylovReport krylov_minres(fq_ctx* ctx, fq_csr* a, int precond, const fq_vec* b,
   FQ_REQUIRE(a->nrows == a->ncols && a->row_begin == 0 && a->row_end == a->nrows,
              "minres needs a square, fully held matrix");
   FQ_REQUIRE(n == a->nrows && x->d.n == n, "minres: dimension mismatch");
-  return minres_core(ctx, n, csr_ops(ctx, a, precond, n), b->d.p, rtol, max_iters, x->d.p);
+  if (std::getenv("FQ_KRYLOV_HOST")) return minres_core(ctx, n, csr_ops(ctx, a, precond, n), b->d.p, rtol, max_iters, x->d.p);
+  return minres_device(ctx, a, precond, b->d.p, rtol, max_iters, x->d.p);
 }
 
 // ---- MINRES with a block-diagonal preconditioner of inner solves (the AFW preconditioner of elliptic.rs:29-47)
@@ -179,6 +485,7 @@ KrylovReport krylov_minres_blockdiag(fq_ctx* ctx, fq_csr* a, int nblocks, fq_csr
   }
   KrylovOps ops = csr_ops(ctx, a, 0, n);
   size_t total_inner = 0;
+  const bool host_scalars = std::getenv("FQ_KRYLOV_HOST") != nullptr;
   ops.precond = [&, ctx](const double* r, double* z) {
     for (int i = 0; i < nblocks; ++i) {
       const size_t off = offsets[i], ni = offsets[i + 1] - off;
@@ -186,7 +493,8 @@ KrylovReport krylov_minres_blockdiag(fq_ctx* ctx, fq_csr* a, int nblocks, fq_csr
         copy(ctx, z + off, r + off, ni);
         continue;
       }
-      const KrylovReport rep = cg_core(ctx, ni, inner[size_t(i)], r + off, inner_rtol, inner_max_iters, z + off);
+      const KrylovReport rep = host_scalars ? cg_core(ctx, ni, inner[size_t(i)], r + off, inner_rtol, inner_max_iters, z + off)
+                                            : cg_device(ctx, blocks[i], 1, r + off, inner_rtol, inner_max_iters, z + off);
       total_inner += rep.iters;
     }
   };

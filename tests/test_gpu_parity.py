@@ -1160,3 +1160,55 @@ def test_distributed_pencil_with_the_afw_preconditioner(fq, ctx):
     assert outer[4][1] <= 2.0 * outer[3][1], outer
     # ... and are far fewer than without it
     assert outer[4][1] * 5 < outer[4][2], outer
+
+
+def test_device_resident_cg_equals_the_host_scalar_loop(fq, ctx, monkeypatch):
+    # fq_cg keeps the recurrence scalars on the device and replays one iteration as a CUDA graph; the loop with host
+    # scalars (FQ_KRYLOV_HOST=1, one synchronisation per inner product, krylov.rs:48-95 step for step) must give the
+    # same bits: iterates, iteration count, residual.  Also without the graph, at an iteration cap, and for b = 0.
+    wc = fq.WhitneyComplex(fq.Mesh.kuhn(ctx, 3, [7, 6, 8], jitter=0.2))
+    for a in (wc.hdif_gram(0), wc.hdif_gram(1)):
+        n = a.shape[0]
+        b = fq.DeviceVector.from_numpy(ctx, np.cos(np.arange(n, dtype=np.float64) ** 2 + 1.0))
+        for precond in (None, "jacobi"):
+            for stop in (fq.StopCriterion(1e-11, 5000), fq.StopCriterion(1e-30, 37)):
+                monkeypatch.setenv("FQ_KRYLOV_HOST", "1")
+                x0, r0 = fq.cg(a, precond, b, stop)
+                monkeypatch.delenv("FQ_KRYLOV_HOST")
+                x1, r1 = fq.cg(a, precond, b, stop)
+                monkeypatch.setenv("FQ_KRYLOV_NO_GRAPH", "1")
+                x2, r2 = fq.cg(a, precond, b, stop)
+                monkeypatch.delenv("FQ_KRYLOV_NO_GRAPH")
+                for x, r in ((x1, r1), (x2, r2)):
+                    assert (r.iters, r.converged) == (r0.iters, r0.converged), (precond, stop, r, r0)
+                    assert r.residual == r0.residual
+                    assert np.array_equal(x.to_numpy(), x0.to_numpy())
+        z, rz = fq.cg(a, "jacobi", b.zeros_like(), fq.StopCriterion(1e-10, 10))
+        assert rz.converged and rz.iters == 0 and not z.to_numpy().any()
+
+
+def test_device_resident_minres_equals_the_host_scalar_loop(fq, ctx, monkeypatch):
+    # same statement for fq_minres (krylov.rs:113-211): Lanczos coefficients, Givens rotation and residual estimate on
+    # the device, three iterations per CUDA graph (the recurrences rotate their vectors with period 3)
+    mesh = fq.Mesh.kuhn(ctx, 3, [6, 5, 7], jitter=0.2)
+    kkt = fq.HodgeBlocks.compute(mesh, 1).mixed_hodge_laplacian(symmetrized=True)
+    spd = fq.WhitneyComplex(mesh).hdif_gram(1)
+    for a, preconds in ((kkt, (None,)), (spd, (None, "jacobi"))):
+        n = a.shape[0]
+        b = fq.DeviceVector.from_numpy(ctx, ((7 * np.arange(n)) % 13 - 6).astype(np.float64))
+        for precond in preconds:
+            for stop in (fq.StopCriterion(1e-9, 20000), fq.StopCriterion(1e-30, 1), fq.StopCriterion(1e-30, 2),
+                         fq.StopCriterion(1e-30, 50)):
+                monkeypatch.setenv("FQ_KRYLOV_HOST", "1")
+                x0, r0 = fq.minres(a, precond, b, stop)
+                monkeypatch.delenv("FQ_KRYLOV_HOST")
+                x1, r1 = fq.minres(a, precond, b, stop)
+                monkeypatch.setenv("FQ_KRYLOV_NO_GRAPH", "1")
+                x2, r2 = fq.minres(a, precond, b, stop)
+                monkeypatch.delenv("FQ_KRYLOV_NO_GRAPH")
+                for x, r in ((x1, r1), (x2, r2)):
+                    assert (r.iters, r.converged) == (r0.iters, r0.converged), (precond, stop, r, r0)
+                    assert r.residual == r0.residual
+                    assert np.array_equal(x.to_numpy(), x0.to_numpy())
+        z, rz = fq.minres(a, None, b.zeros_like(), fq.StopCriterion(1e-10, 10))
+        assert rz.converged and rz.iters == 0 and not z.to_numpy().any()
