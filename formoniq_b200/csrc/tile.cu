@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(32 * (NP + NC), 1) tile_fused_kernel(const __g
             sink[j].slot[cl][R] = 0u;
             if (R >= nrows) continue;
             const uint32_t owners = __ballot_sync(0xFFFFFFFFu, (sink[j].masks >> (8 * cl + R)) & 1u);
-            sink[j].slot[cl][R] = uint32_t(__ldg(grec + cl * kMaxLocal + R)) + uint32_t(__popc(owners & lt_mask));
+            // (lanes beyond the tile's cell visits take part in the ballot only: their group record may not exist)
+            const uint32_t first = c < ncv ? uint32_t(__ldg(grec + cl * kMaxLocal + R)) : 0u;
+            sink[j].slot[cl][R] = first + uint32_t(__popc(owners & lt_mask));
           }
         }
         if (c < ncv) {
