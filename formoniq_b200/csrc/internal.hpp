@@ -96,6 +96,9 @@ void matfree_delete(::fq_matfree* op);
 double vec_dot(fq_ctx* ctx, const double* x, const double* y, size_t n);
 void vec_dot_device(fq_ctx* ctx, const double* x, const double* y, size_t n, double* d_partials, double* d_out);
 size_t vec_dot_scratch_doubles();
+void cg_fused_update(fq_ctx* ctx, double* x, double* r, const double* p, const double* ap, double* z, const double* d,
+                     const double* rz, const double* pap, const int* done, size_t n, double* part_rz, double* part_rr,
+                     double* st, unsigned long long* iters, int* flags, double rtol, size_t max_iters);
 void vec_scale(fq_ctx* ctx, double* x, double alpha, size_t n);
 void vec_axpy(fq_ctx* ctx, double* y, double alpha, const double* x, size_t n);
 void vec_mul_pointwise(fq_ctx* ctx, double* z, const double* d, const double* r, size_t n);

@@ -134,43 +134,23 @@ KrylovReport minres_core(fq_ctx* ctx, size_t n, const KrylovOps& ops, const doub
 // The loop above synchronises with the host three times per iteration (one per inner product).  Here the scalars of
 // the recurrence live in device memory, the updates read them there, and a `done` flag turns every update into a no-op
 // once the stopping test of krylov.rs:62-66 fires: one iteration is a fixed sequence of kernels, captured once in a CUDA
-// graph and replayed in batches, with one host look at the flag per batch.  Same kernels, same reductions, same IEEE
+// graph and replayed in batches, with one host look at the flag per batch.  The vector updates, the Jacobi product and the
+// partial sums of the two inner products that follow them are ONE kernel, their final reduction and the scalar tail of the
+// iteration another (blas1.cu: cg_fused_update): six launches per iteration.  Same reductions, same IEEE
 // operations on the scalars as cg_core: the iterates, the iteration count and the residual are the same bits.
 namespace {
+// device scalars of the CG recurrence: st = {bb, rz, pap, rz_next, rr, residual, beta}, iters, flags = {done, converged}
 struct CgState {
-  double bb, rz, pap, rz_next, rr, residual;
+  double st[7];
   unsigned long long iters;
-  int done, converged;
+  int flags[2];
 };
-__global__ void cg_begin_kernel(CgState* s, double rtol, unsigned long long max_iters) {
-  if (s->done) return;
-  const double residual = __ddiv_rn(__dsqrt_rn(s->rr), __dsqrt_rn(s->bb));
-  s->residual = residual;
-  s->converged = residual <= rtol ? 1 : 0;
-  if (s->converged || s->iters >= max_iters) s->done = 1;
-}
-__global__ void cg_update_x_r_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                                     const double* __restrict__ ap, const CgState* __restrict__ s, size_t n) {
-  if (s->done) return;
-  const double alpha = __ddiv_rn(s->rz, s->pap);
-  const double nalpha = -alpha;
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    x[i] = __dadd_rn(__dmul_rn(alpha, p[i]), x[i]);
-    r[i] = __dadd_rn(__dmul_rn(nalpha, ap[i]), r[i]);
-  }
-}
 __global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ z, const CgState* __restrict__ s, size_t n) {
-  if (s->done) return;
-  const double beta = __ddiv_rn(s->rz_next, s->rz);
+  if (s->flags[0]) return;
+  const double beta = s->st[6];
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     p[i] = __dadd_rn(__dmul_rn(1.0, z[i]), __dmul_rn(p[i], beta));  // p *= beta, then p += 1.0 * z (krylov.rs:90-91)
-}
-__global__ void cg_end_kernel(CgState* s) {
-  if (s->done) return;
-  s->rz = s->rz_next;
-  ++s->iters;
 }
 }  // namespace
 
@@ -182,40 +162,41 @@ static KrylovReport cg_device(fq_ctx* ctx, fq_csr* a, int precond, const double*
   if (n) FQ_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream));
   Work w{ctx, n, {}};
   double *r = w.get(), *z = w.get(), *p = w.get(), *ap = w.get();
-  DevBuf<double> partials(vec_dot_scratch_doubles());
+  DevBuf<double> partials(2 * vec_dot_scratch_doubles());
+  double* partials2 = partials.p + vec_dot_scratch_doubles();
   DevBuf<CgState> state(1);
   FQ_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CgState), ctx->stream));
-  auto apply_precond = [&]() {
-    if (precond == 0)
-      copy(ctx, z, r, n);
-    else
-      vec_mul_pointwise(ctx, z, a->inv_diag.p, r, n);
-  };
-  vec_dot_device(ctx, b, b, n, partials.p, &state.p->bb);
+  const double* jacobi = precond == 1 ? a->inv_diag.p : nullptr;
+  double* st = state.p->st;
+  vec_dot_device(ctx, b, b, n, partials.p, &st[0]);
   copy(ctx, r, b, n);
-  apply_precond();
+  if (jacobi)
+    vec_mul_pointwise(ctx, z, jacobi, r, n);
+  else
+    copy(ctx, z, r, n);
   copy(ctx, p, z, n);
-  vec_dot_device(ctx, r, z, n, partials.p, &state.p->rz);
-  vec_dot_device(ctx, r, r, n, partials.p, &state.p->rr);
+  vec_dot_device(ctx, r, z, n, partials.p, &st[1]);
+  vec_dot_device(ctx, r, r, n, partials.p, &st[4]);
   CgState h{};
   FQ_CUDA(cudaMemcpyAsync(&h, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (std::sqrt(h.bb) == 0.0) {  // krylov.rs:54-57
+  const double b_norm = std::sqrt(h.st[0]);
+  if (b_norm == 0.0) {  // krylov.rs:54-57
     rep.converged = true;
     return rep;
   }
+  // the stopping test before the first iteration (the fused tail of an iteration does the test of the next one)
+  rep.residual = std::sqrt(h.st[4]) / b_norm;
+  rep.converged = rep.residual <= rtol;
+  if (rep.converged || max_iters == 0) return rep;
   const int grid = grid_for(n, 256, ctx->sm_count);
   auto iteration = [&]() {
-    cg_begin_kernel<<<1, 1, 0, ctx->stream>>>(state.p, rtol, (unsigned long long)max_iters);
     spmv_apply(ctx, a, p, ap);
-    vec_dot_device(ctx, p, ap, n, partials.p, &state.p->pap);
-    cg_update_x_r_kernel<<<grid, 256, 0, ctx->stream>>>(x, r, p, ap, state.p, n);
-    apply_precond();
-    vec_dot_device(ctx, r, z, n, partials.p, &state.p->rz_next);
-    vec_dot_device(ctx, r, r, n, partials.p, &state.p->rr);
+    vec_dot_device(ctx, p, ap, n, partials.p, &st[2]);
+    cg_fused_update(ctx, x, r, p, ap, z, jacobi, &st[1], &st[2], &state.p->flags[0], n, partials.p, partials2, st,
+                    &state.p->iters, state.p->flags, rtol, max_iters);
     cg_update_p_kernel<<<grid, 256, 0, ctx->stream>>>(p, z, state.p, n);
-    cg_end_kernel<<<1, 1, 0, ctx->stream>>>(state.p);
-    fq_count_launch(ctx, 4);
+    fq_count_launch(ctx);
   };
   // one iteration captured as a graph (not while per-kernel timing is on: its events do not belong in a capture)
   cudaGraphExec_t exec = nullptr;
@@ -232,7 +213,7 @@ static KrylovReport cg_device(fq_ctx* ctx, fq_csr* a, int precond, const double*
     }
     if (!exec) (void)cudaGetLastError();
   }
-  const int launches_per_iteration = 12;
+  const int launches_per_iteration = 6;
   size_t batch = 4;
   for (;;) {
     for (size_t i = 0; i < batch; ++i) {
@@ -245,14 +226,14 @@ static KrylovReport cg_device(fq_ctx* ctx, fq_csr* a, int precond, const double*
     }
     FQ_CUDA(cudaMemcpyAsync(&h, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
     FQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (h.done) break;
+    if (h.flags[0]) break;
     if (batch < 64) batch *= 2;
   }
   if (exec) cudaGraphExecDestroy(exec);
   FQ_CUDA(cudaGetLastError());
   rep.iters = size_t(h.iters);
-  rep.residual = h.residual;
-  rep.converged = h.converged != 0;
+  rep.residual = h.st[5];
+  rep.converged = h.flags[1] != 0;
   return rep;
 }
 
