@@ -617,6 +617,7 @@ def run_side_workload(args):
     """--workload spmv: the KKT operator of the mixed problem (what MINRES / Lanczos apply) on ONE fixed n^3 mesh cut
     into z-slabs over the ranks, halo exchange included, GB/s on the algorithmic bytes of SURVEY 8d.
     --workload krylov: device-resident MINRES on the symmetrised KKT operator (1 GPU), iterations/s.
+    --workload source: config 1 — the 2-D source problem assembled and solved on the device (AFW-preconditioned MINRES).
     --workload evp: config 5 — block shift-invert Lanczos on the row-partitioned pencil (dist.DistKktPencil)."""
     import numpy as np
     import torch
@@ -685,6 +686,36 @@ def run_side_workload(args):
                "scaling": "none", "config": {"workload": f"device-resident MINRES (CUDA-graph replay, scalars on the device) on "
                                                          f"the symmetrised KKT operator of a {n}^3 Kuhn cube", "n": kkt.shape[0],
                                              "nnz": kkt.nnz, "iterations_per_step": iters}}
+    elif args.workload == "source":
+        # config 1: the mixed source problem on 1-forms of the unit square (problems/elliptic.rs:132-182), assembled and
+        # solved on the device: HodgeBlocks + hdif_gram blocks, MINRES with the AFW block preconditioner (inner device-
+        # resident Jacobi-CG solves instead of the reference's sparse Cholesky)
+        n = args.source_n
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mesh = fq.Mesh.kuhn(ctx, 2, [n, n])
+        hb = fq.HodgeBlocks.compute(mesh, 1)
+        kkt = hb.mixed_hodge_laplacian(symmetrized=True)
+        wc = fq.WhitneyComplex(mesh)
+        blocks = [wc.hdif_gram(0), wc.hdif_gram(1)]
+        ntot = hb.n_sigma + hb.n_u
+        torch.cuda.synchronize()
+        t_asm = time.perf_counter() - t0
+        b = fq.DeviceVector.from_numpy(ctx, ((np.arange(ntot) % 7) - 3).astype(np.float64))  # the probe of elliptic.rs:270
+        t1 = time.perf_counter()
+        x, rep, inner = fq.minres_blockdiag(kkt, blocks, [0, hb.n_sigma, ntot], b, fq.StopCriterion(1e-10, 500),
+                                            fq.StopCriterion(1e-13, 20000))
+        torch.cuda.synchronize()
+        t_solve = time.perf_counter() - t1
+        y = kkt.apply(x)
+        y.add_scaled(-1.0, b)
+        out = {**base, "metric": "source_problem_seconds", "value": t_asm + t_solve, "unit": "s", "higher_is_better": False,
+               "ms_per_step": 1e3 * (t_asm + t_solve), "steps": 1, "warmup": 0, "scaling": "none",
+               "config": {"workload": f"2-D Hodge-Laplace source problem on 1-forms, Kuhn grid {n}x{n}: mesh + HodgeBlocks + hdif_gram "
+                                      f"on the device, MINRES with the AFW block preconditioner to 1e-10", "unknowns": ntot,
+                          "kkt_nnz": kkt.nnz},
+               "assembly_seconds": t_asm, "solve_seconds": t_solve, "outer_minres_iterations": rep.iters, "converged": rep.converged,
+               "inner_cg_iterations": int(inner), "true_relative_residual": y.norm() / b.norm()}
     else:
         g = args.evp_grid
         pencil = DistKktPencil(ctx, 3, [g, g, max(g, world)], GRADE, rank, world, precond=args.evp_precond)
@@ -724,9 +755,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning runs only)")
     ap.add_argument("--no-peer", action="store_true", help="skip the fused peer-memory SpMV measurement (N > 1)")
-    ap.add_argument("--workload", default="assembly", choices=["assembly", "spmv", "krylov", "evp"],
+    ap.add_argument("--workload", default="assembly", choices=["assembly", "spmv", "krylov", "evp", "source"],
                     help="assembly = the north-star line the driver reads; the others are side measurements")
     ap.add_argument("--evp-grid", type=int, default=6)
+    ap.add_argument("--source-n", type=int, default=256)
     ap.add_argument("--evp-precond", default="none", choices=["none", "afw"])
     args = ap.parse_args()
     if args.sample_n == 0:
