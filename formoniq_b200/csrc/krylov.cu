@@ -130,6 +130,48 @@ KrylovReport minres_core(fq_ctx* ctx, size_t n, const KrylovOps& ops, const doub
   return rep;
 }
 
+// One (or a few) iterations of a device-resident loop as an executable CUDA graph; nullptr when capture is not possible
+// (per-kernel timing on, FQ_KRYLOV_NO_GRAPH) — the caller then launches the kernels directly.  The capture runs on a
+// private stream: the context's stream may be the legacy default stream, which cannot be captured, and a graph can be
+// launched into any stream afterwards.
+namespace {
+template <class F>
+cudaGraphExec_t capture_iterations(fq_ctx* ctx, F&& body) {
+  if (ctx->timing || std::getenv("FQ_KRYLOV_NO_GRAPH")) return nullptr;
+  cudaStream_t cap = nullptr;
+  if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  cudaStream_t run = ctx->stream;
+  const int64_t launches_before = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    ctx->stream = cap;
+    try {
+      body();
+    } catch (...) {
+      ctx->stream = run;
+      cudaStreamEndCapture(cap, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cap);
+      (void)cudaGetLastError();
+      throw;
+    }
+    ctx->stream = run;
+    if (cudaStreamEndCapture(cap, &graph) == cudaSuccess && graph) {
+      if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+      cudaGraphDestroy(graph);
+    }
+  }
+  ctx->launches = launches_before;  // the replays are counted, not the capture
+  cudaStreamDestroy(cap);
+  if (!exec) (void)cudaGetLastError();
+  return exec;
+}
+}  // namespace
+
 // ---- device-resident CG for one assembled matrix (Identity / Jacobi)
 // The loop above synchronises with the host three times per iteration (one per inner product).  Here the scalars of
 // the recurrence live in device memory, the updates read them there, and a `done` flag turns every update into a no-op
@@ -198,21 +240,8 @@ static KrylovReport cg_device(fq_ctx* ctx, fq_csr* a, int precond, const double*
     cg_update_p_kernel<<<grid, 256, 0, ctx->stream>>>(p, z, state.p, n);
     fq_count_launch(ctx);
   };
-  // one iteration captured as a graph (not while per-kernel timing is on: its events do not belong in a capture)
-  cudaGraphExec_t exec = nullptr;
-  if (!ctx->timing && !std::getenv("FQ_KRYLOV_NO_GRAPH")) {
-    cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int64_t launches_before = ctx->launches;
-      iteration();
-      ctx->launches = launches_before;  // counted per replay below
-      if (cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph) {
-        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
-        cudaGraphDestroy(graph);
-      }
-    }
-    if (!exec) (void)cudaGetLastError();
-  }
+  // one iteration captured as a graph
+  cudaGraphExec_t exec = capture_iterations(ctx, iteration);
   const int launches_per_iteration = 6;
   size_t batch = 4;
   for (;;) {
@@ -372,22 +401,11 @@ static KrylovReport minres_device(fq_ctx* ctx, fq_csr* a, int precond, const dou
     fq_count_launch(ctx, 6);
   };
   // the pointer roles come back after three iterations: capture three
-  cudaGraphExec_t exec = nullptr;
-  if (!ctx->timing && !std::getenv("FQ_KRYLOV_NO_GRAPH")) {
-    cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int64_t launches_before = ctx->launches;
-      iteration();
-      iteration();
-      iteration();
-      ctx->launches = launches_before;
-      if (cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph) {
-        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
-        cudaGraphDestroy(graph);
-      }
-    }
-    if (!exec) (void)cudaGetLastError();
-  }
+  cudaGraphExec_t exec = capture_iterations(ctx, [&]() {
+    iteration();
+    iteration();
+    iteration();
+  });
   const int launches_per_iteration = 12;
   size_t batch = 2;  // in units of three iterations
   for (;;) {
