@@ -10,6 +10,9 @@
 // source elements < lo, which earlier waves have consumed.  Inside a wave every element is independent (threads split
 // it); the waves halve, and the last few elements are done front to back by one thread.
 #pragma once
+#if defined(__SSE2__) && defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -70,7 +73,21 @@ class HostWidener {
     uint64_t* buf;
     size_t n;
   };
+  // The destination of a wave is written once and not read again by the pool: streaming stores skip the read-for-
+  // ownership of 8 bytes per index that ordinary stores would add to the host memory traffic (which the DMA engines of
+  // the running downloads are competing for).
   static void widen_range(uint64_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t lo, size_t hi) {
+#if defined(__SSE2__) && defined(__x86_64__)
+    static const bool streaming = [] {
+      const char* e = std::getenv("FQ_HOST_WIDEN_NT");
+      return !(e && *e == '0');
+    }();
+    if (streaming) {
+      for (size_t i = lo; i < hi; ++i) _mm_stream_si64(reinterpret_cast<long long*>(dst + i), static_cast<long long>(src[i]));
+      _mm_sfence();
+      return;
+    }
+#endif
     for (size_t i = lo; i < hi; ++i) dst[i] = src[i];
   }
   void drive() {
