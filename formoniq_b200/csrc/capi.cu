@@ -697,7 +697,12 @@ static void download_widen_async(fq_ctx* ctx, const uint32_t* dev, size_t n, uin
   if (ctx->widener) {
     FQ_CUDA(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(host) + n, dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                             ctx->copy_stream));
-    FQ_CUDA(cudaLaunchHostFunc(ctx->copy_stream, widen_callback, new WidenTicket{ctx->widener, host, n}));
+    WidenTicket* ticket = new WidenTicket{ctx->widener, host, n};
+    const cudaError_t err = cudaLaunchHostFunc(ctx->copy_stream, widen_callback, ticket);
+    if (err != cudaSuccess) {
+      delete ticket;
+      FQ_CUDA(err);
+    }
     return;
   }
   ctx->pending_staging.emplace_back(n);

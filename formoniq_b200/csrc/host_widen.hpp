@@ -31,6 +31,7 @@ class HostWidener {
     driver_ = std::thread([this] { drive(); });
   }
   ~HostWidener() {
+    wait_idle();  // queued jobs need the workers
     {
       std::lock_guard<std::mutex> g(m_);
       stop_ = true;
