@@ -36,3 +36,27 @@ top = sorted(range(len(data)), key=lambda i: -int(data[i][ismp] or 0))[:25]
 for i in sorted(top):
     r = data[i]
     print(f"  {i:5d} {r[isrc][:70]:70s} ex={int(r[iex] or 0):>10d} samples={100 * int(r[ismp] or 0) / max(tots, 1):5.2f}%")
+
+# ---- warp-specialised kernels: split the source counters by role at the setmaxnreg instructions (producers first)
+marks = [i for i, r in enumerate(data) if "USETMAXREG" in r[isrc]]
+if len(marks) == 2:
+    def col(name):
+        return hdr.index(name) if name in hdr else None
+    iws, iwi = col("L1 Wavefronts Shared"), col("L1 Wavefronts Shared Ideal")
+    stall_cols = [(h[len("stall_"):], i) for i, h in enumerate(hdr) if h.startswith("stall_") and "(Not Issued)" not in h]
+    def num(r, i):
+        try:
+            return float(r[i] or 0)
+        except (TypeError, ValueError):
+            return 0.0
+    for name, lo, hi in (("producer warps", marks[0], marks[1]), ("consumer warps", marks[1], len(data))):
+        rows_ = data[lo:hi]
+        inst = sum(num(r, iex) for r in rows_)
+        polls = sum(num(r, iex) for r in rows_ if "SYNCS" in r[isrc] and "NANOSLEEP" not in r[isrc])
+        ws = sum(num(r, iws) for r in rows_) if iws is not None else 0
+        wi = sum(num(r, iwi) for r in rows_) if iwi is not None else 0
+        samples = sum(num(r, ismp) for r in rows_)
+        stalls = sorted(((sum(num(r, i) for r in rows_), n) for n, i in stall_cols), reverse=True)[:7]
+        print(f"  {name}: {inst / 1e6:.0f} M warp instructions ({polls / 1e6:.0f} M of them mbarrier polls), "
+              f"shared-memory wavefronts {ws / 1e6:.0f} M (ideal {wi / 1e6:.0f} M)")
+        print("      stall samples: " + ", ".join(f"{n} {100 * v / max(samples, 1):.1f}%" for v, n in stalls))
